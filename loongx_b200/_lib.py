@@ -1,0 +1,77 @@
+"""ctypes binding of libloongx_b200.so (the C ABI declared in include/loongx_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or does not load, importing this module
+raises, so a product path can never silently run on anything but the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libloongx_b200.so"
+
+
+class LoongXNativeError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not _LIB_PATH.exists():
+        raise LoongXNativeError(
+            f"{_LIB_PATH} not found: build it with `python -m loongx_b200.build` (needs nvcc); "
+            "there is no CPU / PyTorch fallback for the hot path"
+        )
+    return C.CDLL(str(_LIB_PATH))
+
+
+lib = _load()
+
+c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
+
+
+class TileMeta(C.Structure):
+    _fields_ = [("stream", c_int32), ("batch", c_int32), ("seq_row", c_int32), ("reserved", c_int32)]
+
+
+class GemmSegment(C.Structure):
+    _fields_ = [("mode", c_int32), ("col_offset", c_int32), ("out", c_void_p), ("ldo", c_int64)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_int64),
+        ("W", c_void_p), ("ldw", c_int64),
+        ("bias", c_void_p),
+        ("M", c_int32), ("N", c_int32), ("K", c_int32),
+        ("n_split", c_int32),
+        ("seg", GemmSegment * 2),
+        ("tile_meta", c_void_p),
+        ("residual", c_void_p), ("ldr", c_int64),
+        ("gate", c_void_p * 3), ("gate_stride", c_int64 * 3),
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p),
+        ("heads", c_int32), ("seq_total", c_int32),
+        ("rms_q", c_void_p * 3), ("rms_k", c_void_p * 3),
+        ("rope", c_void_p),
+        ("rms_eps", c_float), ("reserved", c_int32),
+    ]
+
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_QKV, EPI_BIAS_F32 = range(6)
+
+lib.lx_last_error.restype = C.c_char_p
+lib.lx_version.restype = c_int
+lib.lx_device_info.argtypes = [C.POINTER(c_int32)]
+lib.lx_gemm_bf16.argtypes = [C.POINTER(GemmDesc), c_void_p]
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise LoongXNativeError(f"{what} failed ({rc}): {lib.lx_last_error().decode()}")
+
+
+def exported_symbols() -> list[str]:
+    """Symbols include/loongx_b200.h declares; used by the CPU-side ABI test."""
+    import re
+
+    hdr = Path(__file__).resolve().parent.parent / "include" / "loongx_b200.h"
+    return sorted(set(re.findall(r"\b(lx_[a-z0-9_]+)\s*\(", hdr.read_text())))

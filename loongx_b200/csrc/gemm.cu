@@ -1,0 +1,378 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C = epilogue(A[M,K] · W[N,K]^T), bf16 in, fp32 accumulate.
+//
+//   warp 0      : TMA producer  (A tile 128x64, W tile 256x64 per k-block, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16, accumulators in TMEM,
+//                 two 256-column accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b: one thread = one output row) with the fused element-wise tails of
+//                 the DiT block: bias, GELU-tanh / SiLU, gate*x+residual, per-head RMSNorm + RoPE + head scatter.
+//
+// Tiles are scheduled M-fastest so that the CTAs resident at one time share a W panel (L2 reuse of the weights,
+// A is small enough to stay L2-resident).
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace lx {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  lx_gemm_desc_t d;
+  int tiles_m, tiles_n, num_kb;
+};
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
+  uint4 u;
+  u.x = pack_bf16(v[0], v[1]);
+  u.y = pack_bf16(v[2], v[3]);
+  u.z = pack_bf16(v[4], v[5]);
+  u.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+
+// acc (+bias) for one 32-column chunk -> x[32]
+__device__ __forceinline__ void chunk_bias(const uint32_t (&r)[32], const float* __restrict__ bias, int n, float (&x)[32]) {
+  if (bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      x[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+      x[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+      x[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+      x[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const lx_gemm_desc_t& d = p.d;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.tiles_m) * BM;
+        const int n0 = (tile / p.tiles_m) * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &tmB, &full[stage], kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_sdesc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = make_sdesc_sw128(sb + k * 32, 16, 1024);
+            umma_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile % p.tiles_m;
+      const int m0 = tm * BM;
+      const int n0 = (tile / p.tiles_m) * BN;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < d.M;
+      const int si = (n0 >= d.n_split) ? 1 : 0;
+      const lx_gemm_segment_t& seg = d.seg[si];
+      const int seg_n0 = si ? d.n_split : 0;
+      const int mode = seg.mode;
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      if (mode == LX_EPI_QKV) {
+        const lx_tile_meta_t meta = d.tile_meta[tm];
+        const int D = d.heads * 128;
+        const int sec = n0 / D;  // 0 = q, 1 = k, 2 = v
+        const int s_pos = meta.seq_row % d.seq_total + row_in_tile;
+        __nv_bfloat16* dst_base = reinterpret_cast<__nv_bfloat16*>(sec == 0 ? d.q : (sec == 1 ? d.k : d.v));
+        const float* rmsw = sec == 0 ? d.rms_q[meta.stream] : (sec == 1 ? d.rms_k[meta.stream] : nullptr);
+        const float4* rope_row =
+            (d.rope != nullptr && sec < 2) ? reinterpret_cast<const float4*>(d.rope + (size_t)s_pos * 128) : nullptr;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int nh = n0 + half * 128;
+          if (nh >= d.n_split) break;
+          const int head = (nh - sec * D) >> 7;
+          __nv_bfloat16* dst = dst_base + (((size_t)meta.batch * d.heads + head) * d.seq_total + s_pos) * 128;
+          float inv = 1.0f;
+          if (rmsw != nullptr) {
+            float ss = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t r[32];
+              float x[32];
+              tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
+                  chunk_bias(r, d.bias, nh + c * 32, x);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ss += x[j] * x[j];
+            }
+            inv = rsqrtf(ss * (1.0f / 128.0f) + d.rms_eps);
+          }
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            float x[32];
+            tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
+              chunk_bias(r, d.bias, nh + c * 32, x);
+            if (rmsw != nullptr) {
+              const float4* w4 = reinterpret_cast<const float4*>(rmsw + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 w = __ldg(w4 + j);
+                x[4 * j + 0] *= inv * w.x;
+                x[4 * j + 1] *= inv * w.y;
+                x[4 * j + 2] *= inv * w.z;
+                x[4 * j + 3] *= inv * w.w;
+              }
+            }
+            if (rope_row != nullptr && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 cs = __ldg(rope_row + c * 8 + j);  // (cos0, sin0, cos1, sin1) for two rotary pairs
+                float a0 = x[4 * j + 0], b0 = x[4 * j + 1], a1 = x[4 * j + 2], b1 = x[4 * j + 3];
+                x[4 * j + 0] = a0 * cs.x - b0 * cs.y;
+                x[4 * j + 1] = b0 * cs.x + a0 * cs.y;
+                x[4 * j + 2] = a1 * cs.z - b1 * cs.w;
+                x[4 * j + 3] = b1 * cs.z + a1 * cs.w;
+              }
+            }
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) store_bf16x8(dst + c * 32 + j * 8, &x[8 * j]);
+            }
+          }
+        }
+      } else if (mode == LX_EPI_GATE_RESIDUAL) {
+        const lx_tile_meta_t meta = d.tile_meta[tm];
+        const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(d.gate[meta.stream]) +
+                                    (size_t)meta.batch * d.gate_stride[meta.stream];
+        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual) + (size_t)row * d.ldr;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n = n0 + c * 32;
+          if (n >= d.N) break;
+          uint32_t r[32];
+          float x[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          chunk_bias(r, d.bias, n, x);
+          const int oc = n - seg_n0 + seg.col_offset;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j * 8 < d.N) {
+              uint4 g = __ldg(reinterpret_cast<const uint4*>(gate + n + j * 8));
+              uint32_t gu[4] = {g.x, g.y, g.z, g.w};
+              if (row_ok) {
+                uint4 rr = *reinterpret_cast<const uint4*>(res + oc + j * 8);
+                uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 gg = unpack_bf16(gu[e]);
+                  float2 r2 = unpack_bf16(ru[e]);
+                  o[2 * e + 0] = r2.x + gg.x * x[8 * j + 2 * e + 0];
+                  o[2 * e + 1] = r2.y + gg.y * x[8 * j + 2 * e + 1];
+                }
+                store_bf16x8(out + oc + j * 8, o);
+              }
+            }
+          }
+        }
+      } else {
+        // BIAS / GELU / SILU / F32
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n = n0 + c * 32;
+          if (n >= d.N) break;
+          uint32_t r[32];
+          float x[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          chunk_bias(r, d.bias, n, x);
+          if (mode == LX_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
+          } else if (mode == LX_EPI_BIAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = silu(x[j]);
+          }
+          const int oc = n - seg_n0 + seg.col_offset;
+          if (row_ok) {
+            if (mode == LX_EPI_BIAS_F32) {
+              float* out = reinterpret_cast<float*>(seg.out) + (size_t)row * seg.ldo + oc;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j * 4 < d.N)
+                  *reinterpret_cast<float4*>(out + j * 4) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            } else {
+              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo + oc;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j * 8 < d.N) store_bf16x8(out + j * 8, &x[8 * j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace lx
+
+extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
+  using namespace lx;
+  LX_CHECK_ARG(desc != nullptr, "lx_gemm_bf16: null descriptor");
+  const lx_gemm_desc_t& d = *desc;
+  LX_CHECK_ARG(d.M > 0 && d.N > 0 && d.K > 0, "lx_gemm_bf16: bad shape M=%d N=%d K=%d", d.M, d.N, d.K);
+  LX_CHECK_ARG(d.N % 8 == 0 && d.K % 8 == 0, "lx_gemm_bf16: N and K must be multiples of 8 (N=%d K=%d)", d.N, d.K);
+  LX_CHECK_ARG(d.A && d.W, "lx_gemm_bf16: null operand");
+  LX_CHECK_ARG(d.n_split > 0 && (d.n_split == d.N || d.n_split % BN == 0) && d.n_split <= d.N,
+               "lx_gemm_bf16: n_split=%d must be N or a multiple of %d", d.n_split, BN);
+  const int nseg = d.n_split < d.N ? 2 : 1;
+  for (int s = 0; s < nseg; ++s) {
+    const lx_gemm_segment_t& g = d.seg[s];
+    LX_CHECK_ARG(g.mode >= LX_EPI_BIAS && g.mode <= LX_EPI_BIAS_F32, "lx_gemm_bf16: bad epilogue mode %d", g.mode);
+    if (g.mode == LX_EPI_QKV) {
+      LX_CHECK_ARG(s == 0, "lx_gemm_bf16: QKV segment must be segment 0");
+      LX_CHECK_ARG(d.q && d.k && d.v && d.heads > 0 && d.seq_total > 0 && d.tile_meta,
+                   "lx_gemm_bf16: QKV epilogue needs q/k/v, heads, seq_total, tile_meta");
+      LX_CHECK_ARG(d.n_split == 3 * d.heads * 128, "lx_gemm_bf16: QKV segment must span 3*heads*128 columns");
+      LX_CHECK_ARG(d.seq_total % 128 == 0, "lx_gemm_bf16: seq_total must be a multiple of 128");
+      LX_CHECK_ARG(d.heads % 2 == 0, "lx_gemm_bf16: QKV epilogue needs an even head count (256-column tiles)");
+      LX_CHECK_ARG(d.M % 128 == 0, "lx_gemm_bf16: QKV epilogue needs M to be a multiple of 128");
+    } else {
+      LX_CHECK_ARG(g.out != nullptr && g.ldo > 0 && g.ldo % 8 == 0 && g.col_offset % 8 == 0,
+                   "lx_gemm_bf16: segment %d needs out / ldo (multiple of 8)", s);
+    }
+    if (g.mode == LX_EPI_GATE_RESIDUAL) {
+      LX_CHECK_ARG(d.residual && d.tile_meta && d.ldr % 8 == 0, "lx_gemm_bf16: GATE_RESIDUAL needs residual, tile_meta");
+    }
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, BM, BK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, d.W, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldw, BN, BK);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.d = d;
+  p.tiles_m = (d.M + BM - 1) / BM;
+  p.tiles_n = (d.N + BN - 1) / BN;
+  p.num_kb = (d.K + BK - 1) / BK;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
+  }
+  const int grid = min(p.tiles_m * p.tiles_n, num_sms());
+  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}

@@ -1,0 +1,43 @@
+// Host-side helpers shared by all translation units: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/loongx_b200.h"
+
+namespace lx {
+
+void set_error(const char* fmt, ...);
+
+#define LX_CHECK_ARG(cond, ...)   \
+  do {                            \
+    if (!(cond)) {                \
+      lx::set_error(__VA_ARGS__); \
+      return LX_ERR_ARG;          \
+    }                             \
+  } while (0)
+
+#define LX_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      lx::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));        \
+      return LX_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+// 2-D bf16 tensor map: `rows` x `cols` (cols contiguous), row stride `ld` elements, box = box_rows x box_cols,
+// 128-byte swizzle (box_cols must be 64 bf16 = 128 B).  Out-of-bounds elements are zero-filled on load and
+// clipped on store.
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols);
+// 3-D variant: dims (cols, rows, outer) with strides (ld, outer_stride) in elements.
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint64_t outer_stride, uint32_t box_rows, uint32_t box_cols);
+
+int num_sms();
+
+}  // namespace lx

@@ -1,0 +1,104 @@
+"""Tensor-level wrappers over the C ABI (include/loongx_b200.h).
+
+Each function takes torch CUDA tensors, extracts raw pointers / strides and calls the native entry point on the
+current torch CUDA stream.  No arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "loongx_b200 ops need CUDA tensors (there is no CPU fallback)"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_tile_meta(batch: int, n_txt: int, n_img: int, n_cond: int, device) -> torch.Tensor:
+    """Per-128-row tile metadata for the stream-major row layout [txt(B*Nt) | img(B*Ni) | cond(B*Nc)].
+
+    Integer layout work, bit-exact by construction: tile -> (stream, batch, batch*S + offset in [txt|img|cond]).
+    """
+    S = n_txt + n_img + n_cond
+    rows = []
+    for stream, (n, off) in enumerate(((n_txt, 0), (n_img, n_txt), (n_cond, n_txt + n_img))):
+        assert n % 128 == 0, f"stream length {n} must be a multiple of 128"
+        for b in range(batch):
+            for t in range(n // 128):
+                rows.append((stream, b, b * S + off + t * 128, 0))
+    return torch.tensor(rows, dtype=torch.int32, device=device).reshape(-1, 4).contiguous()
+
+
+def gemm(
+    A: torch.Tensor,
+    W: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    out: Optional[torch.Tensor] = None,
+    mode: int = L.EPI_BIAS,
+    *,
+    K: Optional[int] = None,
+    col_offset: int = 0,
+    n_split: Optional[int] = None,
+    seg1: Optional[tuple] = None,  # (mode, out, col_offset)
+    tile_meta: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    gate: Optional[Sequence[Optional[torch.Tensor]]] = None,  # per stream [B, *] views (row = batch)
+    qkv: Optional[tuple] = None,  # (q, k, v) each [B, H, S, 128]
+    rms_q: Optional[Sequence[Optional[torch.Tensor]]] = None,
+    rms_k: Optional[Sequence[Optional[torch.Tensor]]] = None,
+    rope: Optional[torch.Tensor] = None,
+    rms_eps: float = 1e-6,
+) -> None:
+    """C = epilogue(A[M,K] @ W[N,K]^T); A / W are 2-D bf16 views with unit inner stride."""
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    assert A.stride(1) == 1 and W.stride(1) == 1
+    d = L.GemmDesc()
+    d.A, d.lda = _ptr(A), A.stride(0)
+    d.W, d.ldw = _ptr(W), W.stride(0)
+    d.bias = _ptr(bias)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    d.M, d.N = A.shape[0], W.shape[0]
+    d.K = K if K is not None else A.shape[1]
+    assert W.shape[1] >= d.K and A.shape[1] >= d.K
+    d.n_split = n_split if n_split is not None else d.N
+    d.seg[0].mode = mode
+    d.seg[0].col_offset = col_offset
+    if out is not None:
+        assert out.stride(-1) == 1
+        d.seg[0].out, d.seg[0].ldo = _ptr(out), out.stride(0)
+    if seg1 is not None:
+        m1, o1, c1 = seg1
+        d.seg[1].mode, d.seg[1].out, d.seg[1].ldo, d.seg[1].col_offset = m1, _ptr(o1), o1.stride(0), c1
+    d.tile_meta = _ptr(tile_meta)
+    if residual is not None:
+        d.residual, d.ldr = _ptr(residual), residual.stride(0)
+    if gate is not None:
+        for i, g in enumerate(gate):
+            if g is not None:
+                assert g.dtype == torch.bfloat16 and g.stride(-1) == 1
+                d.gate[i] = _ptr(g)
+                d.gate_stride[i] = g.stride(0) if g.dim() > 1 else 0
+    if qkv is not None:
+        q, k, v = qkv
+        assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+        d.q, d.k, d.v = _ptr(q), _ptr(k), _ptr(v)
+        d.heads, d.seq_total = q.shape[1], q.shape[2]
+        for i in range(3):
+            if rms_q is not None and rms_q[i] is not None:
+                d.rms_q[i] = _ptr(rms_q[i])
+            if rms_k is not None and rms_k[i] is not None:
+                d.rms_k[i] = _ptr(rms_k[i])
+        d.rope = _ptr(rope)
+    d.rms_eps = rms_eps
+    L.check(L.lib.lx_gemm_bf16(C.byref(d), _stream()), "lx_gemm_bf16")

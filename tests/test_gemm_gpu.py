@@ -1,0 +1,180 @@
+"""GPU parity tests of the tcgen05 GEMM and its fused epilogues against plain torch fp32 math.
+
+Tolerance (stated): inputs are bf16, accumulation fp32; the output is rounded once to bf16, so
+|err| <= 2^-8 * |ref| + small absolute slack from accumulation-order differences.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * scale).to(dtype)
+
+
+def _close(out, ref, rtol=1.0 / 128, atol=2e-2, what=""):
+    out = out.float()
+    err = (out - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (
+        f"{what}: {int(bad.sum())} / {bad.numel()} mismatches, max err {err.max().item():.4g}, "
+        f"first at {tuple(torch.nonzero(bad)[0].tolist())}"
+    )
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 768, 3136), (200, 328, 200), (2560, 3072, 3072)])
+def test_gemm_bias(M, N, K):
+    from loongx_b200 import ops, _lib as L
+
+    A, W = _mk((M, K), 1.0, 1), _mk((N, K), 0.05, 2)
+    bias = _mk((N,), 1.0, 3, torch.float32)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, out, L.EPI_BIAS)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    _close(out, ref, what=f"bias {M}x{N}x{K}")
+
+
+def test_gemm_strided_ext_and_f32():
+    """A / W with row stride > K (the LoRA K-extension layout) and an fp32 output segment."""
+    from loongx_b200 import ops, _lib as L
+
+    M, N, K, ld = 256, 256, 128 + 64, 320
+    Abuf, Wbuf = _mk((M, ld), 1.0, 4), _mk((N, ld), 0.1, 5)
+    out = torch.zeros((M, N), device="cuda", dtype=torch.float32)
+    ops.gemm(Abuf, Wbuf, None, out, L.EPI_BIAS_F32, K=K)
+    torch.cuda.synchronize()
+    ref = Abuf[:, :K].float() @ Wbuf[:, :K].float().t()
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-2), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("mode", ["gelu", "silu"])
+def test_gemm_activation(mode):
+    from loongx_b200 import ops, _lib as L
+
+    M, N, K = 256, 512, 512
+    A, W = _mk((M, K), 1.0, 6), _mk((N, K), 0.06, 7)
+    bias = _mk((N,), 0.5, 8, torch.float32)
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, out, L.EPI_BIAS_GELU if mode == "gelu" else L.EPI_BIAS_SILU)
+    torch.cuda.synchronize()
+    pre = A.float() @ W.float().t() + bias
+    ref = torch.nn.functional.gelu(pre, approximate="tanh") if mode == "gelu" else torch.nn.functional.silu(pre)
+    _close(out, ref, what=mode)
+
+
+def test_gemm_gate_residual_inplace():
+    from loongx_b200 import ops, _lib as L
+
+    B, nt, ni, nc, D, K = 2, 128, 256, 128, 512, 256
+    S = nt + ni + nc
+    R = B * S
+    meta = ops.make_tile_meta(B, nt, ni, nc, "cuda")
+    A, W = _mk((R, K), 1.0, 9), _mk((D, K), 0.06, 10)
+    bias = _mk((D,), 0.5, 11, torch.float32)
+    x = _mk((R, D), 1.0, 12)
+    gates = [_mk((B, 3 * D), 1.0, 13 + i) for i in range(3)]  # gate = columns [D, 2D) of a modulation row
+    gviews = [g[:, D : 2 * D] for g in gates]
+    x0 = x.clone()
+    ops.gemm(A, W, bias, x, L.EPI_GATE_RESIDUAL, tile_meta=meta, residual=x, gate=gviews)
+    torch.cuda.synchronize()
+    lin = A.float() @ W.float().t() + bias
+    ref = torch.empty_like(lin)
+    m = meta.cpu().tolist()
+    for t, (stream, b, _, _) in enumerate(m):
+        sl = slice(t * 128, (t + 1) * 128)
+        ref[sl] = x0[sl].float() + gviews[stream][b].float()[None, :] * lin[sl]
+    _close(x, ref, what="gate_residual")
+
+
+def _rope_table(S, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ang = torch.rand((S, 64), generator=g, device="cuda") * 6.28
+    return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()  # [S, 64, 2]
+
+
+def _ref_qkv(lin, meta, B, H, S, rms_q, rms_k, rope, eps):
+    """lin [R, 3D] fp32 -> q,k,v [B,H,S,128] following block.py:34-41,74-78 (+ diffusers RMSNorm / apply_rotary_emb)."""
+    D = H * 128
+    outs = [torch.zeros((B, H, S, 128), device=lin.device) for _ in range(3)]
+    for t, (stream, b, seq_row, _) in enumerate(meta.cpu().tolist()):
+        s0 = seq_row % S
+        rows = lin[t * 128 : (t + 1) * 128]
+        for sec in range(3):
+            x = rows[:, sec * D : (sec + 1) * D].reshape(128, H, 128).permute(1, 0, 2)  # [H,128,128]
+            if sec < 2:
+                w = (rms_q if sec == 0 else rms_k)[stream]
+                x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * w
+                cos, sin = rope[s0 : s0 + 128, :, 0], rope[s0 : s0 + 128, :, 1]
+                xr, xi = x[..., 0::2], x[..., 1::2]
+                x = torch.stack([xr * cos - xi * sin, xi * cos + xr * sin], dim=-1).flatten(-2)
+            outs[sec][b, :, s0 : s0 + 128] = x
+    return outs
+
+
+def test_gemm_qkv_epilogue_and_split_gelu():
+    """Fused single-block projection: columns [0,3D) -> QKV epilogue, [3D,3D+F) -> GELU into a wider buffer."""
+    from loongx_b200 import ops, _lib as L
+
+    B, nt, ni, nc, H, K, F = 2, 128, 128, 256, 2, 320, 512
+    D = H * 128
+    S = nt + ni + nc
+    R = B * S
+    meta = ops.make_tile_meta(B, nt, ni, nc, "cuda")
+    A, W = _mk((R, K), 1.0, 20), _mk((3 * D + F, K), 0.06, 21)
+    bias = _mk((3 * D + F,), 0.3, 22, torch.float32)
+    rms_q = [(_mk((128,), 0.2, 23 + i, torch.float32) + 1.0) for i in range(3)]
+    rms_k = [(_mk((128,), 0.2, 26 + i, torch.float32) + 1.0) for i in range(3)]
+    rope = _rope_table(S, 29)
+    q = torch.full((B, H, S, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+    k, v = q.clone(), q.clone()
+    cat = torch.zeros((R, D + F + 64), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, None, L.EPI_QKV, n_split=3 * D, seg1=(L.EPI_BIAS_GELU, cat, D), tile_meta=meta,
+             qkv=(q, k, v), rms_q=rms_q, rms_k=rms_k, rope=rope, rms_eps=1e-6)
+    torch.cuda.synchronize()
+    lin = A.float() @ W.float().t() + bias
+    rq, rk, rv = _ref_qkv(lin[:, : 3 * D], meta, B, H, S, rms_q, rms_k, rope, 1e-6)
+    _close(q, rq, what="q")
+    _close(k, rk, what="k")
+    _close(v, rv, what="v")
+    ref_mlp = torch.nn.functional.gelu(lin[:, 3 * D :], approximate="tanh")
+    _close(cat[:, D : D + F], ref_mlp, what="mlp segment")
+    assert (cat[:, :D] == 0).all() and (cat[:, D + F :] == 0).all(), "GELU segment wrote outside its columns"
+
+
+def test_gemm_bad_args_raise():
+    from loongx_b200 import ops, _lib as L
+
+    A, W = _mk((128, 60), 1.0, 1), _mk((256, 60), 1.0, 2)  # K not a multiple of 8
+    out = torch.empty((128, 256), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(L.LoongXNativeError):
+        ops.gemm(A, W, None, out, L.EPI_BIAS)
+
+
+def test_gemm_throughput_smoke():
+    """Not a benchmark: prints achieved TFLOP/s of the plain GEMM so the first GPU run shows where we stand."""
+    from loongx_b200 import ops, _lib as L
+
+    M, N, K = 2560, 12288, 3072
+    A, W = _mk((M, K), 1.0, 30), _mk((N, K), 0.02, 31)
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(A, W, None, out, L.EPI_BIAS)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.gemm(A, W, None, out, L.EPI_BIAS)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    tf = 2 * M * N * K / ms / 1e9
+    print(f"\n[gemm smoke] {M}x{N}x{K}: {ms:.3f} ms, {tf:.1f} TFLOP/s")
+    ref = A.float() @ W.float().t()
+    _close(out, ref, what="throughput shape")
+    assert math.isfinite(tf)
