@@ -88,6 +88,29 @@ typedef struct lx_gemm_desc {
 
 int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Joint attention  out = softmax(Q K^T * scale [+ mask / bias]) V   over the [txt | img | cond] sequence.
+ * Replaces F.scaled_dot_product_attention and the surrounding concat / transpose / split
+ * (block.py:70-72, 102-135) plus the block masks (block.py:106-120) and the c_factor bias (block.py:121-128).
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct lx_attn_desc {
+  const void* q; /* bf16 [B, H, S, 128] (written by the LX_EPI_QKV epilogue) */
+  const void* k;
+  const void* v;
+  void* out; /* bf16 rows in the stream-major layout; head h occupies columns col_offset + [128h, 128h+128) */
+  int64_t ldo;
+  const int32_t* out_row_base; /* [B * S/128]: first output row of (batch, query tile) */
+  int32_t col_offset;
+  int32_t B, H, S;
+  int32_t n_cond;    /* trailing condition tokens of the sequence (multiple of 128, 0 = none) */
+  int32_t mask_mode; /* 0 = full; 1 = cond<->rest blocked (union_cond_attn=False); 2 = cond queries see only cond keys
+                        (independent_condition) */
+  float cross_bias;  /* log(c_factor) added to cond<->rest logits; non-zero overrides mask_mode like the reference */
+  float scale;       /* 1/sqrt(128) */
+} lx_attn_desc_t;
+
+int lx_attention(const lx_attn_desc_t* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,12 +56,25 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p),
+        ("out", c_void_p), ("ldo", c_int64),
+        ("out_row_base", c_void_p),
+        ("col_offset", c_int32),
+        ("B", c_int32), ("H", c_int32), ("S", c_int32),
+        ("n_cond", c_int32), ("mask_mode", c_int32),
+        ("cross_bias", c_float), ("scale", c_float),
+    ]
+
+
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_QKV, EPI_BIAS_F32 = range(6)
 
 lib.lx_last_error.restype = C.c_char_p
 lib.lx_version.restype = c_int
 lib.lx_device_info.argtypes = [C.POINTER(c_int32)]
 lib.lx_gemm_bf16.argtypes = [C.POINTER(GemmDesc), c_void_p]
+lib.lx_attention.argtypes = [C.POINTER(AttnDesc), c_void_p]
 
 
 def check(rc: int, what: str = "") -> None:

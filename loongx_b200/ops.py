@@ -102,3 +102,31 @@ def gemm(
         d.rope = _ptr(rope)
     d.rms_eps = rms_eps
     L.check(L.lib.lx_gemm_bf16(C.byref(d), _stream()), "lx_gemm_bf16")
+
+
+def make_out_row_base(batch: int, n_txt: int, n_img: int, n_cond: int, device) -> torch.Tensor:
+    """Inverse of make_tile_meta: (batch, sequence tile) -> first row in the stream-major activation layout."""
+    base = []
+    for b in range(batch):
+        for n, off in ((n_txt, 0), (n_img, batch * n_txt), (n_cond, batch * (n_txt + n_img))):
+            for t in range(n // 128):
+                base.append(off + b * n + t * 128)
+    return torch.tensor(base, dtype=torch.int32, device=device)
+
+
+def attention(q, k, v, out, out_row_base, *, n_cond: int = 0, mask_mode: int = 0, cross_bias: float = 0.0,
+              col_offset: int = 0, scale: Optional[float] = None) -> None:
+    """out rows <- softmax(q k^T * scale) v for q,k,v [B,H,S,128] bf16 (see lx_attention)."""
+    assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    B, H, S, Dh = q.shape
+    assert Dh == 128
+    d = L.AttnDesc()
+    d.q, d.k, d.v = _ptr(q), _ptr(k), _ptr(v)
+    d.out, d.ldo = _ptr(out), out.stride(0)
+    d.out_row_base = _ptr(out_row_base)
+    d.col_offset = col_offset
+    d.B, d.H, d.S = B, H, S
+    d.n_cond, d.mask_mode = n_cond, mask_mode
+    d.cross_bias = cross_bias
+    d.scale = scale if scale is not None else 1.0 / (Dh ** 0.5)
+    L.check(L.lib.lx_attention(C.byref(d), _stream()), "lx_attention")
