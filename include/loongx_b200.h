@@ -111,6 +111,161 @@ typedef struct lx_attn_desc {
 
 int lx_attention(const lx_attn_desc_t* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound).
+ * ------------------------------------------------------------------------------------------------------ */
+/* out[:, 0:D] = LayerNorm(x; no affine, eps) * (1 + scale[stream,batch]) + shift[stream,batch];
+ * out[:, D:D+ext] = (that bf16 row) . lora_a^T for rows whose stream is in lora_stream_mask, else 0.
+ * Replaces AdaLayerNormZero / -Single / -Continuous + norm2 FiLM (block.py:192-207, 238-253, 301-305;
+ * transformer.py:243) and peft's lora_A on the same operand. */
+typedef struct lx_lnmod_desc {
+  const void* x; /* bf16 [rows, ldx] */
+  int64_t ldx;
+  void* out; /* bf16 [rows, ldo], ldo >= D + ext */
+  int64_t ldo;
+  int32_t rows, D;
+  int32_t ext;    /* K-extension columns to fill (multiple of 64, 0 = none) */
+  int32_t lora_r; /* rows of lora_a (<= 16) */
+  const lx_tile_meta_t* tile_meta;
+  const void* shift[3]; /* bf16, per stream: shift[s] + batch*stride[s] */
+  const void* scale[3];
+  int64_t stride[3];
+  const void* lora_a; /* bf16 [lora_r, D] or NULL */
+  int32_t lora_stream_mask; /* bit s set = LoRA active on stream s (default: cond only = 4) */
+  float eps;
+} lx_lnmod_desc_t;
+int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream);
+
+/* x[:, K:K+ext] = x[:, 0:K] . lora_a^T (active rows) or 0: the LoRA "down" half for operands produced by another
+ * kernel (attention output, GELU hidden, packed latents). */
+typedef struct lx_lora_down_desc {
+  void* x; /* bf16 [rows, ldx], ldx >= K + ext */
+  int64_t ldx;
+  int32_t rows, K, ext, lora_r;
+  const lx_tile_meta_t* tile_meta; /* NULL = every row is a condition row */
+  const void* lora_a;              /* bf16 [lora_r, K] or NULL */
+  int32_t lora_stream_mask;
+  int32_t reserved;
+} lx_lora_down_desc_t;
+int lx_lora_down(const lx_lora_down_desc_t* desc, void* stream);
+
+/* Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[m] = [cos(t*mult*f), sin(t*mult*f)] bf16. */
+int lx_timestep_embed(const float* t, void* out, int64_t ldo, int32_t M, float mult, void* stream);
+/* out[m, 0:D] = silu(a[m] + b[m] + c[m % c_rows]) for bf16 [M, D] inputs (b, c may be NULL): temb = t_emb + g_emb +
+ * text_emb followed by the SiLU every AdaLN applies (transformer.py:102-114, App. A.2/A.5). */
+int lx_add_silu_bcast(const void* a, const void* b, const void* c, int32_t c_rows, void* out, int64_t ldo, int32_t M,
+                      int32_t D, void* stream);
+/* FlowMatchEulerDiscreteScheduler.step (generate.py:349): out = bf16(float(x) + dt*float(v)), n elements. */
+int lx_euler_step(const void* x, const void* v, void* out, float dt, int64_t n, void* stream);
+/* FluxPosEmbed (transformer.py:130-134): ids fp32 [S,3] -> table fp32 [S,64,2] (cos, sin), float64 internally. */
+int lx_rope_table(const float* ids, float* table, int32_t S, int32_t d0, int32_t d1, int32_t d2, double theta,
+                  void* stream);
+/* FluxPipeline._pack_latents / _unpack_latents (generate.py:262, 375): [B,C,h,w] <-> [B,(h/2)(w/2),4C], bit-exact. */
+int lx_pack_latents(const void* in, void* out, int32_t B, int32_t C, int32_t h, int32_t w, int32_t elem_bytes,
+                    int32_t unpack, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * DiT engine: the whole tranformer_forward (transformer.py:47-252) as one native call sequence.
+ * Weight layout: every nn.Linear is one lx_linear_t.  A LoRA-targeted Linear stores its weight K-extended:
+ * columns [0,k) = base W, columns [k, k+ext) = lora_B * (alpha/r) (zero padded to a multiple of 64), and
+ * lora_a holds the stacked lora_A rows; the operand producers fill the matching ext columns with x.A^T on the
+ * rows where LoRA is active (condition stream by default, lora_controller.py:5-43), so base + LoRA is ONE GEMM.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct lx_linear {
+  const void* w; /* bf16 [n, ldw] */
+  int64_t ldw;
+  const float* bias;  /* fp32 [n] or NULL */
+  const void* lora_a; /* bf16 [lora_r, k] or NULL */
+  int32_t n, k, ext, lora_r;
+} lx_linear_t;
+
+typedef struct lx_double_block {
+  lx_linear_t qkv;     /* [to_q;to_k;to_v]  (img + cond rows) */
+  lx_linear_t qkv_ctx; /* [add_q_proj;add_k_proj;add_v_proj] (txt rows) */
+  lx_linear_t out, out_ctx;
+  lx_linear_t ff_up, ff_down, ff_ctx_up, ff_ctx_down;
+  const float* norm_q; /* fp32 [128] */
+  const float* norm_k;
+  const float* norm_added_q;
+  const float* norm_added_k;
+} lx_double_block_t;
+
+typedef struct lx_single_block {
+  lx_linear_t qkv_mlp; /* [to_q;to_k;to_v;proj_mlp] */
+  lx_linear_t proj_out;
+  const float* norm_q;
+  const float* norm_k;
+} lx_single_block_t;
+
+typedef struct lx_dit_model {
+  int32_t num_layers, num_single_layers, heads, in_channels;
+  int32_t joint_dim, pooled_dim, guidance_embeds, reserved;
+  int32_t axes_dim[3];
+  int32_t reserved2;
+  lx_linear_t x_embedder, context_embedder;
+  lx_linear_t time_1, time_2, guid_1, guid_2, text_1, text_2;
+  lx_linear_t mod_img;    /* all double blocks' norm1.linear stacked:         [L*6D, D+ext] */
+  lx_linear_t mod_txt;    /* all double blocks' norm1_context.linear stacked: [L*6D, D]     */
+  lx_linear_t mod_single; /* all single blocks' norm.linear stacked:          [Ls*3D, D+ext] */
+  lx_linear_t norm_out, proj_out;
+  const lx_double_block_t* double_blocks; /* host array [num_layers] */
+  const lx_single_block_t* single_blocks; /* host array [num_single_layers] */
+} lx_dit_model_t;
+
+/* Geometry + caller-owned device buffers of one batch of edits (R = B*(n_txt+n_img+n_cond) rows, D = heads*128,
+ * T = number of denoise steps prepared). */
+typedef struct lx_dit_plan {
+  int32_t B, n_txt, n_img, n_cond;
+  int32_t T;
+  int32_t mask_mode;    /* see lx_attn_desc_t */
+  int32_t latent_lora;  /* model_config["latent_lora"]: LoRA also on the image (and, in single blocks, text) rows */
+  int32_t add_cond_attn;
+  float cross_bias;
+  int32_t reserved;
+  const lx_tile_meta_t* tile_meta; /* device [R/128] */
+  const int32_t* out_row_base;     /* device [B*S/128] */
+  const float* rope;               /* device [S,64,2] for the joint [txt|img|cond] ids, or NULL */
+  void* X;       /* bf16 [R, D] residual stream (stream-major rows) */
+  void* XN;      /* bf16 [R, D+64] modulated operand */
+  void* Q;       /* bf16 [B,H,S,128] */
+  void* K;
+  void* V;
+  void* scratch; /* bf16 [R, 5D+64]: attention out / FF hidden / single-block concat */
+  void* XE;      /* bf16 [B*max(n_img,n_cond), in_channels+64] packed-latent operand of x_embedder */
+  void* X0_txt;  /* bf16 [B*n_txt, D]  context_embedder(prompt_embeds)   (step invariant) */
+  void* X0_cond; /* bf16 [B*n_cond, D] x_embedder(cond_latents)          (step invariant) */
+  void* emb_tmp; /* bf16 [4, T*B + B, D] scratch of the timestep / guidance / text MLPs */
+  void* sin_tmp; /* bf16 [T*B + B, 256] */
+  void* silu_t;  /* bf16 [T*B, D + max ext] silu(temb) per (step, batch) */
+  void* silu_c;  /* bf16 [B,   D + max ext] silu(cond_temb) */
+  void* mod_img;      /* bf16 [T*B, L*6D] */
+  void* mod_txt;      /* bf16 [T*B, L*6D] */
+  void* mod_single;   /* bf16 [T*B, Ls*3D] */
+  void* mod_out;      /* bf16 [T*B, 2D] */
+  void* mod_cond_img;    /* bf16 [B, L*6D]  (cond stream, step invariant) */
+  void* mod_cond_single; /* bf16 [B, Ls*3D] */
+  float* t_dev;          /* fp32 [T*B + B] device scratch for timestep values */
+  float* g_dev;          /* fp32 [T*B + B] device scratch for guidance values */
+} lx_dit_plan_t;
+
+/* Step-invariant work, once per edit (generate.py:168-306 hoisted): context_embedder, x_embedder(cond), temb for all
+ * T timesteps + cond_temb (c_t), every block's AdaLN modulation vector.  timesteps / guidance are HOST arrays of
+ * length T*B and B (timestep in (0,1], the *1000 of transformer.py:95-98 is applied inside). */
+int lx_dit_prepare(const lx_dit_model_t* model, const lx_dit_plan_t* plan, const void* prompt_embeds,
+                   const void* pooled, const void* cond_latents, const float* timesteps, const float* guidance,
+                   float c_t, void* stream);
+/* x_embedder(latents) + copies of the step-invariant txt / cond embeddings into plan->X (transformer.py:91-93,115). */
+int lx_dit_embed(const lx_dit_model_t* model, const lx_dit_plan_t* plan, const void* latents, void* stream);
+/* One DiT forward at prepared step `step`: latents bf16 [B, n_img, in_channels] -> noise_pred (same shape). */
+int lx_dit_step(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, const void* latents,
+                void* noise_pred, void* stream);
+/* Reference-granularity entry points for parity tests (block.py:179-278 / 281-339): run ONE block of the prepared
+ * plan in place on plan->X. */
+int lx_dit_double_block(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, int32_t block,
+                        void* stream);
+int lx_dit_single_block(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, int32_t block,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

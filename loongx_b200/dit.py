@@ -1,0 +1,412 @@
+"""Host side of the native DiT engine: weight packing (diffusers-named tensors -> fused, K-extended bf16 panels),
+plan / workspace allocation through torch, and thin calls into lx_dit_prepare / lx_dit_step.
+
+No arithmetic of the hot path happens here — only one-time layout work at load (concatenating q/k/v(/proj_mlp)
+weights, appending LoRA-B columns, stacking the AdaLN linears) and pointer plumbing per call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .config import FluxConfig, linear_shapes, lora_targets, rmsnorm_names
+
+c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ctypes mirrors of include/loongx_b200.h
+# ---------------------------------------------------------------------------------------------------------------
+class LxLinear(C.Structure):
+    _fields_ = [("w", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("lora_a", c_void_p),
+                ("n", c_int32), ("k", c_int32), ("ext", c_int32), ("lora_r", c_int32)]
+
+
+class LxDoubleBlock(C.Structure):
+    _fields_ = [("qkv", LxLinear), ("qkv_ctx", LxLinear), ("out", LxLinear), ("out_ctx", LxLinear),
+                ("ff_up", LxLinear), ("ff_down", LxLinear), ("ff_ctx_up", LxLinear), ("ff_ctx_down", LxLinear),
+                ("norm_q", c_void_p), ("norm_k", c_void_p), ("norm_added_q", c_void_p), ("norm_added_k", c_void_p)]
+
+
+class LxSingleBlock(C.Structure):
+    _fields_ = [("qkv_mlp", LxLinear), ("proj_out", LxLinear), ("norm_q", c_void_p), ("norm_k", c_void_p)]
+
+
+class LxDitModel(C.Structure):
+    _fields_ = [("num_layers", c_int32), ("num_single_layers", c_int32), ("heads", c_int32), ("in_channels", c_int32),
+                ("joint_dim", c_int32), ("pooled_dim", c_int32), ("guidance_embeds", c_int32), ("reserved", c_int32),
+                ("axes_dim", c_int32 * 3), ("reserved2", c_int32),
+                ("x_embedder", LxLinear), ("context_embedder", LxLinear),
+                ("time_1", LxLinear), ("time_2", LxLinear), ("guid_1", LxLinear), ("guid_2", LxLinear),
+                ("text_1", LxLinear), ("text_2", LxLinear),
+                ("mod_img", LxLinear), ("mod_txt", LxLinear), ("mod_single", LxLinear),
+                ("norm_out", LxLinear), ("proj_out", LxLinear),
+                ("double_blocks", c_void_p), ("single_blocks", c_void_p)]
+
+
+class LxDitPlan(C.Structure):
+    _fields_ = [("B", c_int32), ("n_txt", c_int32), ("n_img", c_int32), ("n_cond", c_int32),
+                ("T", c_int32), ("mask_mode", c_int32), ("latent_lora", c_int32), ("add_cond_attn", c_int32),
+                ("cross_bias", c_float), ("reserved", c_int32),
+                ("tile_meta", c_void_p), ("out_row_base", c_void_p), ("rope", c_void_p),
+                ("X", c_void_p), ("XN", c_void_p), ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p),
+                ("scratch", c_void_p), ("XE", c_void_p), ("X0_txt", c_void_p), ("X0_cond", c_void_p),
+                ("emb_tmp", c_void_p), ("sin_tmp", c_void_p), ("silu_t", c_void_p), ("silu_c", c_void_p),
+                ("mod_img", c_void_p), ("mod_txt", c_void_p), ("mod_single", c_void_p), ("mod_out", c_void_p),
+                ("mod_cond_img", c_void_p), ("mod_cond_single", c_void_p),
+                ("t_dev", c_void_p), ("g_dev", c_void_p)]
+
+
+_lib = L.lib
+_lib.lx_dit_prepare.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_void_p, c_void_p, c_void_p,
+                                C.POINTER(c_float), C.POINTER(c_float), c_float, c_void_p]
+_lib.lx_dit_embed.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_void_p, c_void_p]
+_lib.lx_dit_step.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_void_p, c_void_p, c_void_p]
+_lib.lx_dit_double_block.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_int32, c_void_p]
+_lib.lx_dit_single_block.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_int32, c_void_p]
+_lib.lx_euler_step.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p]
+_lib.lx_rope_table.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, C.c_double, c_void_p]
+_lib.lx_pack_latents.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------------------------
+def random_params(cfg: FluxConfig, device, seed: int = 1234, w_std: float = 0.02, bias_std: float = 0.0,
+                  lora_b_std: float = 0.02, dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """Synthetic weights with the reference architecture (there are no checkpoints on the box): Linear ~ N(0, w_std^2),
+    RMSNorm weight 1 + 0.1 N(0,1), LoRA A ~ N(0, 1/r) ('gaussian' init), LoRA B ~ N(0, lora_b_std^2).  Generated
+    directly on `device` so the 12 B-parameter model never exists on the host."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    P: Dict[str, torch.Tensor] = {}
+    targets = set(lora_targets(cfg))
+
+    def randn(*shape, std):
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * std).to(dtype)
+
+    for name, (o, i) in linear_shapes(cfg).items():
+        P[name + ".weight"] = randn(o, i, std=w_std)
+        P[name + ".bias"] = randn(o, std=bias_std) if bias_std > 0 else torch.zeros(o, device=device, dtype=dtype)
+        if name in targets and cfg.lora_rank > 0:
+            P[name + ".lora_A.weight"] = randn(cfg.lora_rank, i, std=1.0 / cfg.lora_rank)
+            P[name + ".lora_B.weight"] = randn(o, cfg.lora_rank, std=lora_b_std)
+    for n in rmsnorm_names(cfg):
+        P[n] = (1.0 + 0.1 * torch.randn(cfg.attention_head_dim, generator=g, device=device)).to(dtype)
+    return P
+
+
+class PackedLinear:
+    """One (possibly fused / stacked) Linear in the native layout; keeps the tensors alive."""
+
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], lora_a: Optional[torch.Tensor], k: int, ext: int,
+                 lora_r: int):
+        self.w, self.bias, self.lora_a, self.k, self.ext, self.lora_r = w, bias, lora_a, k, ext, lora_r
+
+    def c(self) -> LxLinear:
+        s = LxLinear()
+        s.w, s.ldw = self.w.data_ptr(), self.w.stride(0)
+        s.bias = self.bias.data_ptr() if self.bias is not None else None
+        s.lora_a = self.lora_a.data_ptr() if self.lora_a is not None else None
+        s.n, s.k, s.ext, s.lora_r = self.w.shape[0], self.k, self.ext, self.lora_r
+        return s
+
+
+def pack_linear(P: Dict[str, torch.Tensor], names: Sequence[str], cfg: FluxConfig, device, *, per_block_lora=False,
+                pop: bool = False) -> PackedLinear:
+    """Stack the Linear layers `names` along the output dimension.  If any of them carries LoRA factors the weight is
+    K-extended: columns [k, k+ext) hold lora_B * (alpha / r) — layer i in columns [r*i, r*i+r), or, with
+    per_block_lora (stacked AdaLN linears evaluated one block at a time), always in columns [0, r)."""
+    get = (lambda key: P.pop(key)) if pop else (lambda key: P[key])
+    ws = [get(n + ".weight").to(device=device, dtype=torch.bfloat16) for n in names]
+    k = ws[0].shape[1]
+    n_total = sum(w.shape[0] for w in ws)
+    has_bias = (names[0] + ".bias") in P
+    bias = torch.cat([get(n + ".bias").to(device=device, dtype=torch.float32) for n in names]) if has_bias else None
+    lora_idx = [i for i, n in enumerate(names) if (n + ".lora_A.weight") in P]
+    if not lora_idx:
+        w = torch.cat(ws, 0).contiguous() if len(ws) > 1 else ws[0].contiguous()
+        return PackedLinear(w, bias, None, k, 0, 0)
+    r = P[names[lora_idx[0]] + ".lora_A.weight"].shape[0]
+    scaling = cfg.lora_alpha / r
+    r_cols = r if per_block_lora else r * len(lora_idx)
+    assert r_cols <= 16 or per_block_lora, "at most 16 LoRA rows per fused operand"
+    ext = 64
+    w = torch.zeros((n_total, k + ext), device=device, dtype=torch.bfloat16)
+    a_rows: List[torch.Tensor] = []
+    row = 0
+    slot = 0
+    for i, (n, wi) in enumerate(zip(names, ws)):
+        o = wi.shape[0]
+        w[row:row + o, :k] = wi
+        if i in lora_idx:
+            a = get(n + ".lora_A.weight").to(device=device, dtype=torch.bfloat16)
+            b = get(n + ".lora_B.weight").to(device=device, dtype=torch.float32) * scaling
+            c0 = 0 if per_block_lora else slot * r
+            w[row:row + o, k + c0:k + c0 + r] = b.to(torch.bfloat16)
+            a_rows.append(a)
+            slot += 1
+        elif per_block_lora:
+            raise ValueError("per_block_lora needs LoRA on every stacked layer")
+        row += o
+    del ws
+    lora_a = torch.cat(a_rows, 0).contiguous()
+    return PackedLinear(w, bias, lora_a, k, ext, r if per_block_lora else r * len(lora_idx))
+
+
+class DitWeights:
+    """Native weight container: packed device tensors + the ctypes model struct handed to the C ABI."""
+
+    def __init__(self, P: Dict[str, torch.Tensor], cfg: FluxConfig, device="cuda", consume: bool = False):
+        cfg.validate()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        dev = self.device
+        pk = lambda names, **kw: pack_linear(P, names, cfg, dev, pop=consume, **kw)  # noqa: E731
+        f32 = lambda key: (P.pop(key) if consume else P[key]).to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        self.keep: List[object] = []
+        m = LxDitModel()
+        m.num_layers, m.num_single_layers = cfg.num_layers, cfg.num_single_layers
+        m.heads, m.in_channels = cfg.num_attention_heads, cfg.in_channels
+        m.joint_dim, m.pooled_dim = cfg.joint_attention_dim, cfg.pooled_projection_dim
+        m.guidance_embeds = int(cfg.guidance_embeds)
+        for i in range(3):
+            m.axes_dim[i] = cfg.axes_dims_rope[i]
+
+        def put(field: str, pl: PackedLinear):
+            self.keep.append(pl)
+            setattr(m, field, pl.c())
+
+        put("x_embedder", pk(["x_embedder"]))
+        put("context_embedder", pk(["context_embedder"]))
+        put("time_1", pk(["time_text_embed.timestep_embedder.linear_1"]))
+        put("time_2", pk(["time_text_embed.timestep_embedder.linear_2"]))
+        if cfg.guidance_embeds:
+            put("guid_1", pk(["time_text_embed.guidance_embedder.linear_1"]))
+            put("guid_2", pk(["time_text_embed.guidance_embedder.linear_2"]))
+        put("text_1", pk(["time_text_embed.text_embedder.linear_1"]))
+        put("text_2", pk(["time_text_embed.text_embedder.linear_2"]))
+        has_lora = "transformer_blocks.0.norm1.linear.lora_A.weight" in P if cfg.num_layers else False
+        put("mod_img", pk([f"transformer_blocks.{i}.norm1.linear" for i in range(cfg.num_layers)], per_block_lora=has_lora))
+        put("mod_txt", pk([f"transformer_blocks.{i}.norm1_context.linear" for i in range(cfg.num_layers)]))
+        has_lora_s = "single_transformer_blocks.0.norm.linear.lora_A.weight" in P if cfg.num_single_layers else False
+        put("mod_single", pk([f"single_transformer_blocks.{i}.norm.linear" for i in range(cfg.num_single_layers)],
+                             per_block_lora=has_lora_s))
+        put("norm_out", pk(["norm_out.linear"]))
+        put("proj_out", pk(["proj_out"]))
+
+        self.dbl = (LxDoubleBlock * max(cfg.num_layers, 1))()
+        for i in range(cfg.num_layers):
+            p = f"transformer_blocks.{i}."
+            blk = self.dbl[i]
+            for field, names in (
+                ("qkv", [p + "attn.to_q", p + "attn.to_k", p + "attn.to_v"]),
+                ("qkv_ctx", [p + "attn.add_q_proj", p + "attn.add_k_proj", p + "attn.add_v_proj"]),
+                ("out", [p + "attn.to_out.0"]), ("out_ctx", [p + "attn.to_add_out"]),
+                ("ff_up", [p + "ff.net.0.proj"]), ("ff_down", [p + "ff.net.2"]),
+                ("ff_ctx_up", [p + "ff_context.net.0.proj"]), ("ff_ctx_down", [p + "ff_context.net.2"]),
+            ):
+                pl = pk(names)
+                self.keep.append(pl)
+                setattr(blk, field, pl.c())
+            for field in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+                t = f32(p + f"attn.{field}.weight")
+                self.keep.append(t)
+                setattr(blk, field, t.data_ptr())
+        self.sgl = (LxSingleBlock * max(cfg.num_single_layers, 1))()
+        for i in range(cfg.num_single_layers):
+            p = f"single_transformer_blocks.{i}."
+            blk = self.sgl[i]
+            pl = pk([p + "attn.to_q", p + "attn.to_k", p + "attn.to_v", p + "proj_mlp"])
+            self.keep.append(pl)
+            blk.qkv_mlp = pl.c()
+            pl = pk([p + "proj_out"])
+            self.keep.append(pl)
+            blk.proj_out = pl.c()
+            for field in ("norm_q", "norm_k"):
+                t = f32(p + f"attn.{field}.weight")
+                self.keep.append(t)
+                setattr(blk, field, t.data_ptr())
+        m.double_blocks = C.cast(self.dbl, c_void_p)
+        m.single_blocks = C.cast(self.sgl, c_void_p)
+        self.model = m
+
+    def param_bytes(self) -> int:
+        tot = 0
+        for k in self.keep:
+            if isinstance(k, PackedLinear):
+                tot += k.w.numel() * 2
+        return tot
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# plan (geometry + workspace)
+# ---------------------------------------------------------------------------------------------------------------
+MASK_NONE, MASK_NO_UNION, MASK_INDEPENDENT = 0, 1, 2
+
+
+def mask_mode_from_config(model_config: Optional[dict]) -> int:
+    """block.py:106-120: union_cond_attn=False wins over independent_condition."""
+    model_config = model_config or {}
+    if not model_config.get("union_cond_attn", True):
+        return MASK_NO_UNION
+    if model_config.get("independent_condition", False):
+        return MASK_INDEPENDENT
+    return MASK_NONE
+
+
+class DitPlan:
+    def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, T: int = 1,
+                 model_config: Optional[dict] = None, c_factor: Optional[float] = None):
+        cfg = weights.cfg
+        dev = weights.device
+        for n in (n_txt, n_img, n_cond):
+            if n % 128:
+                raise ValueError(f"stream lengths must be multiples of 128 tokens, got {(n_txt, n_img, n_cond)}")
+        model_config = model_config or {}
+        self.weights, self.B, self.nt, self.ni, self.nc, self.T = weights, B, n_txt, n_img, n_cond, T
+        D, H = cfg.inner_dim, cfg.num_attention_heads
+        S = n_txt + n_img + n_cond
+        R = B * S
+        L_, Ls = cfg.num_layers, cfg.num_single_layers
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        M = T * B + B
+        self.buf = dict(
+            tile_meta=ops.make_tile_meta(B, n_txt, n_img, n_cond, dev),
+            out_row_base=ops.make_out_row_base(B, n_txt, n_img, n_cond, dev),
+            rope=torch.zeros((S, 64, 2), device=dev, dtype=torch.float32),
+            X=torch.zeros((R, D), **bf),
+            XN=torch.zeros((R, D + 64), **bf),
+            Q=torch.zeros((B, H, S, 128), **bf), K=torch.zeros((B, H, S, 128), **bf), V=torch.zeros((B, H, S, 128), **bf),
+            scratch=torch.zeros((R, 5 * D + 64), **bf),
+            XE=torch.zeros((B * max(n_img, n_cond), cfg.in_channels + 64), **bf),
+            X0_txt=torch.zeros((B * n_txt, D), **bf),
+            X0_cond=torch.zeros((max(B * n_cond, 1), D), **bf),
+            emb_tmp=torch.zeros((4, M, D), **bf),
+            sin_tmp=torch.zeros((M, 256), **bf),
+            silu_t=torch.zeros((T * B, D + 64), **bf),
+            silu_c=torch.zeros((B, D + 64), **bf),
+            mod_img=torch.zeros((T * B, max(L_, 1) * 6 * D), **bf),
+            mod_txt=torch.zeros((T * B, max(L_, 1) * 6 * D), **bf),
+            mod_single=torch.zeros((T * B, max(Ls, 1) * 3 * D), **bf),
+            mod_out=torch.zeros((T * B, 2 * D), **bf),
+            mod_cond_img=torch.zeros((B, max(L_, 1) * 6 * D), **bf),
+            mod_cond_single=torch.zeros((B, max(Ls, 1) * 3 * D), **bf),
+            t_dev=torch.zeros((M,), device=dev, dtype=torch.float32),
+            g_dev=torch.zeros((M,), device=dev, dtype=torch.float32),
+        )
+        p = LxDitPlan()
+        p.B, p.n_txt, p.n_img, p.n_cond, p.T = B, n_txt, n_img, n_cond, T
+        p.mask_mode = mask_mode_from_config(model_config)
+        p.latent_lora = int(bool(model_config.get("latent_lora", False)))
+        p.add_cond_attn = int(bool(model_config.get("add_cond_attn", False)))
+        p.cross_bias = math.log(c_factor) if c_factor is not None else 0.0
+        for k, v in self.buf.items():
+            setattr(p, k, v.data_ptr())
+        self.plan = p
+        self.has_rope = False
+
+    def set_ids(self, txt_ids: torch.Tensor, img_ids: torch.Tensor, cond_ids: Optional[torch.Tensor]) -> None:
+        """RoPE table of the joint [txt | img | cond] sequence (transformer.py:130-134); ids are step-invariant so
+        this runs once per edit instead of once per forward."""
+        cfg = self.weights.cfg
+        parts = [txt_ids, img_ids] + ([cond_ids] if cond_ids is not None else [])
+        ids = torch.cat([x.to(device=self.weights.device, dtype=torch.float32) for x in parts], 0).contiguous()
+        assert ids.shape == (self.nt + self.ni + self.nc, 3), ids.shape
+        a = cfg.axes_dims_rope
+        L.check(_lib.lx_rope_table(ids.data_ptr(), self.buf["rope"].data_ptr(), ids.shape[0], a[0], a[1], a[2], 10000.0,
+                                   _stream()), "lx_rope_table")
+        self._ids_keepalive = ids
+        self.has_rope = True
+
+    # -- native calls ------------------------------------------------------------------------------------------
+    def prepare(self, prompt_embeds: torch.Tensor, pooled: torch.Tensor, cond_latents: Optional[torch.Tensor],
+                timesteps: Sequence[float], guidance: Optional[Sequence[float]], c_t: float = 0.0) -> None:
+        """timesteps: T*B values in (0,1] ordered step-major; guidance: B values or None."""
+        w = self.weights
+        assert self.has_rope, "call set_ids() first"
+        assert len(timesteps) == self.T * self.B
+        pe = prompt_embeds.to(torch.bfloat16).contiguous()
+        po = pooled.to(torch.bfloat16).contiguous()
+        cl = cond_latents.to(torch.bfloat16).contiguous() if cond_latents is not None else None
+        assert pe.shape == (self.B, self.nt, w.cfg.joint_attention_dim), pe.shape
+        assert po.shape == (self.B, w.cfg.pooled_projection_dim)
+        ts = (c_float * len(timesteps))(*[float(t) for t in timesteps])
+        gs = (c_float * self.B)(*[float(x) for x in guidance]) if guidance is not None else None
+        L.check(_lib.lx_dit_prepare(C.byref(w.model), C.byref(self.plan), pe.data_ptr(), po.data_ptr(),
+                                    cl.data_ptr() if cl is not None else None, ts, gs, float(c_t), _stream()),
+                "lx_dit_prepare")
+        self._prep_keepalive = (pe, po, cl)
+
+    def step(self, step: int, latents: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        w = self.weights
+        assert latents.dtype == torch.bfloat16 and latents.is_contiguous()
+        assert latents.shape == (self.B, self.ni, w.cfg.in_channels), latents.shape
+        if out is None:
+            out = torch.empty_like(latents)
+        L.check(_lib.lx_dit_step(C.byref(w.model), C.byref(self.plan), step, latents.data_ptr(), out.data_ptr(),
+                                 _stream()), "lx_dit_step")
+        return out
+
+    def embed(self, latents: torch.Tensor) -> None:
+        L.check(_lib.lx_dit_embed(C.byref(self.weights.model), C.byref(self.plan), latents.data_ptr(), _stream()),
+                "lx_dit_embed")
+
+    def double_block(self, step: int, block: int) -> None:
+        L.check(_lib.lx_dit_double_block(C.byref(self.weights.model), C.byref(self.plan), step, block, _stream()),
+                "lx_dit_double_block")
+
+    def single_block(self, step: int, block: int) -> None:
+        L.check(_lib.lx_dit_single_block(C.byref(self.weights.model), C.byref(self.plan), step, block, _stream()),
+                "lx_dit_single_block")
+
+    # -- stream-major row layout <-> reference [B, N, D] tensors (test / shim helpers, pure views + copies) ---------
+    def split_streams(self):
+        X, B, D = self.buf["X"], self.B, self.weights.cfg.inner_dim
+        rt, ri = B * self.nt, B * self.ni
+        txt = X[:rt].view(B, self.nt, D)
+        img = X[rt:rt + ri].view(B, self.ni, D)
+        cond = X[rt + ri:].view(B, self.nc, D) if self.nc else None
+        return txt, img, cond
+
+
+def euler_step(latents: torch.Tensor, noise_pred: torch.Tensor, dt: float, out: Optional[torch.Tensor] = None):
+    """scheduler.step (generate.py:349) on bf16 tensors: out = bf16(float(latents) + dt * float(noise_pred))."""
+    assert latents.dtype == torch.bfloat16 and noise_pred.dtype == torch.bfloat16
+    assert latents.is_contiguous() and noise_pred.is_contiguous()
+    if out is None:
+        out = torch.empty_like(latents)
+    L.check(_lib.lx_euler_step(latents.data_ptr(), noise_pred.data_ptr(), out.data_ptr(), float(dt), latents.numel(),
+                               _stream()), "lx_euler_step")
+    return out
+
+
+def pack_latents(x: torch.Tensor) -> torch.Tensor:
+    """FluxPipeline._pack_latents: [B, C, h, w] -> [B, (h/2)(w/2), 4C]."""
+    assert x.is_cuda and x.is_contiguous() and x.element_size() in (2, 4)
+    B, Cc, h, w = x.shape
+    out = torch.empty((B, (h // 2) * (w // 2), Cc * 4), device=x.device, dtype=x.dtype)
+    L.check(_lib.lx_pack_latents(x.data_ptr(), out.data_ptr(), B, Cc, h, w, x.element_size(), 0, _stream()),
+            "lx_pack_latents")
+    return out
+
+
+def unpack_latents(x: torch.Tensor, height: int, width: int, vae_scale_factor: int = 16) -> torch.Tensor:
+    """FluxPipeline._unpack_latents (diffusers 0.31: vae_scale_factor = 16): [B, N, 4C] -> [B, C, H/8, W/8]."""
+    assert x.is_cuda and x.is_contiguous() and x.element_size() in (2, 4)
+    B, N, ch = x.shape
+    h, w = 2 * (height // vae_scale_factor), 2 * (width // vae_scale_factor)
+    Cc = ch // 4
+    assert N == (h // 2) * (w // 2)
+    out = torch.empty((B, Cc, h, w), device=x.device, dtype=x.dtype)
+    L.check(_lib.lx_pack_latents(x.data_ptr(), out.data_ptr(), B, Cc, h, w, x.element_size(), 1, _stream()),
+            "lx_pack_latents")
+    return out

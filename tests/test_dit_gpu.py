@@ -1,0 +1,171 @@
+"""GPU parity of the native DiT engine (lx_dit_prepare / lx_dit_embed / lx_dit_double_block / lx_dit_single_block /
+lx_dit_step through the C ABI) against the oracle restatement of transformer.py / block.py, stage by stage.
+
+Stated tolerance: with identical bf16-rounded weights and inputs,
+  relL2(native, oracle_fp32) <= 1.5 * relL2(oracle_bf16_eager, oracle_fp32) + 2e-3   and   <= 2e-2 absolute.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ids(h, w, dc=0):
+    i = torch.zeros(h, w, 3)
+    i[..., 1] += torch.arange(h)[:, None]
+    i[..., 2] += torch.arange(w)[None, :] + dc
+    return i.reshape(-1, 3)
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def _setup(model_config=None, c_factor=None, n_cond=128, heads=2, layers=(2, 2), B=2, T=2, seed=0):
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitWeights, DitPlan
+
+    dev = "cuda"
+    ocfg = O.FluxConfig(num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=heads,
+                        joint_attention_dim=256, pooled_projection_dim=64)
+    cfg = FluxConfig(num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=heads,
+                     joint_attention_dim=256, pooled_projection_dim=64)
+    P = O.init_params(ocfg, seed=1234, dtype=torch.float32, device="cpu", w_std=0.05, bias_std=0.05, lora_b_std=0.05)
+    Pb = {k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}  # the shared, bf16-rounded weights
+    P32 = {k: v.float() for k, v in Pb.items()}
+    nt, ni, nc = 128, 128, n_cond
+    g = torch.Generator().manual_seed(seed)
+    inp = dict(
+        lat=torch.randn(B, ni, 64, generator=g).bfloat16().to(dev),
+        cond=torch.randn(B, nc, 64, generator=g).bfloat16().to(dev) if nc else None,
+        pe=(torch.randn(B, nt, 256, generator=g) * 0.5).bfloat16().to(dev),
+        pooled=torch.randn(B, 64, generator=g).bfloat16().to(dev),
+        img_ids=_ids(8, 16).to(dev), cond_ids=_ids(8, 16, -16).to(dev) if nc else None, txt_ids=torch.zeros(nt, 3).to(dev),
+        ts=[0.9, 0.35][:T], guidance=3.5,
+    )
+    W = DitWeights(Pb, cfg, dev)
+    plan = DitPlan(W, B, nt, ni, nc, T=T, model_config=model_config, c_factor=c_factor)
+    plan.set_ids(inp["txt_ids"], inp["img_ids"], inp["cond_ids"])
+    tsteps = [t for t in inp["ts"] for _ in range(B)]
+    plan.prepare(inp["pe"], inp["pooled"], inp["cond"], tsteps, [inp["guidance"]] * B, c_t=0.0)
+    return O, ocfg, Pb, P32, inp, W, plan
+
+
+def _oracle_full(O, ocfg, P, inp, t, dtype, model_config=None, c_factor=None):
+    B = inp["lat"].shape[0]
+    c = lambda x: x.to(dtype) if x is not None else None  # noqa: E731
+    return O.tranformer_forward(
+        P, ocfg, c(inp["cond"]), inp["cond_ids"], None, model_config or {}, 0,
+        hidden_states=c(inp["lat"]), encoder_hidden_states=c(inp["pe"]), pooled_projections=c(inp["pooled"]),
+        timestep=torch.full((B,), t, device="cuda", dtype=dtype), img_ids=inp["img_ids"], txt_ids=inp["txt_ids"],
+        guidance=torch.full((B,), inp["guidance"], device="cuda", dtype=dtype), c_factor=c_factor)
+
+
+def test_dit_stagewise_vs_oracle():
+    """embed -> each double block -> each single block, compared after every stage (localises a wrong kernel)."""
+    import torch.nn.functional as F
+
+    O, ocfg, Pb, P32, inp, W, plan = _setup()
+    B = 2
+    step, t = 1, inp["ts"][1]
+    f = lambda x: x.float()  # noqa: E731
+    # ---- oracle, fp32, same bf16-rounded weights
+    h = O.linear(P32, "x_embedder", f(inp["lat"]), False, ocfg)
+    c = O.linear(P32, "x_embedder", f(inp["cond"]), True, ocfg)
+    tt = torch.full((B,), t, device="cuda") * 1000
+    gg = torch.full((B,), inp["guidance"], device="cuda") * 1000
+    temb = O.time_text_embed(P32, ocfg, tt, gg, f(inp["pooled"]))
+    ctemb = O.time_text_embed(P32, ocfg, torch.zeros_like(tt), gg, f(inp["pooled"]))
+    e = O.linear(P32, "context_embedder", f(inp["pe"]), False, ocfg)
+    rope = O.rope_tables(torch.cat([inp["txt_ids"], inp["img_ids"]], 0))
+    crope = O.rope_tables(inp["cond_ids"])
+
+    # native: modulation tables vs oracle AdaLN linears
+    D = ocfg.inner_dim
+    mod_ref = O.linear(P32, "transformer_blocks.1.norm1.linear", F.silu(temb), False, ocfg)
+    mod_nat = plan.buf["mod_img"][step * B:(step + 1) * B, 6 * D:12 * D]
+    assert _rel(mod_nat, mod_ref) < 1e-2, ("mod_img", _rel(mod_nat, mod_ref))
+    modc_ref = O.linear(P32, "single_transformer_blocks.1.norm.linear", F.silu(ctemb), True, ocfg)
+    modc_nat = plan.buf["mod_cond_single"][:, 3 * D:6 * D]
+    assert _rel(modc_nat, modc_ref) < 1e-2, ("mod_cond_single", _rel(modc_nat, modc_ref))
+
+    plan.embed(inp["lat"])
+    torch.cuda.synchronize()
+    txt, img, cond = plan.split_streams()
+    for name, a, b in (("x_embedder(img)", img, h), ("x_embedder(cond)+LoRA", cond, c), ("context_embedder", txt, e)):
+        assert _rel(a, b) < 6e-3, (name, _rel(a, b))
+
+    for i in range(ocfg.num_layers):
+        e, h, c = O.block_forward(P32, ocfg, i, h, e, c, temb, ctemb, crope, rope, {})
+        plan.double_block(step, i)
+        torch.cuda.synchronize()
+        txt, img, cond = plan.split_streams()
+        for name, a, b in (("img", img, h), ("txt", txt, e), ("cond", cond, c)):
+            r = _rel(a, b)
+            assert r < 1.5e-2, (f"double block {i} {name}", r)
+    x = torch.cat([e, h], 1)
+    for i in range(ocfg.num_single_layers):
+        x, c = O.single_block_forward(P32, ocfg, i, x, temb, rope, c, ctemb, crope, {})
+        plan.single_block(step, i)
+        torch.cuda.synchronize()
+        txt, img, cond = plan.split_streams()
+        for name, a, b in (("txt+img", torch.cat([txt, img], 1), x), ("cond", cond, c)):
+            r = _rel(a, b)
+            assert r < 2e-2, (f"single block {i} {name}", r)
+
+
+@pytest.mark.parametrize("variant", ["default", "no_cond", "no_union", "independent", "c_factor", "latent_lora"])
+def test_dit_forward_vs_oracle(variant):
+    mc, cf, nc = {}, None, 128
+    if variant == "no_cond":
+        nc = 0
+    elif variant == "no_union":
+        mc = {"union_cond_attn": False}
+    elif variant == "independent":
+        mc = {"independent_condition": True}
+    elif variant == "c_factor":
+        cf = 1.6
+    elif variant == "latent_lora":
+        mc = {"latent_lora": True}
+    O, ocfg, Pb, P32, inp, W, plan = _setup(model_config=mc, c_factor=cf, n_cond=nc)
+    for step, t in enumerate(inp["ts"]):
+        ref32 = _oracle_full(O, ocfg, P32, inp, t, torch.float32, mc, cf)
+        ref16 = _oracle_full(O, ocfg, Pb, inp, t, torch.bfloat16, mc, cf)
+        got = plan.step(step, inp["lat"])
+        torch.cuda.synchronize()
+        e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
+        print(f"\n[{variant} step {step}] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
+        assert torch.isfinite(got.float()).all()
+        assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (variant, step, e_nat, e_bf)
+
+
+def test_dit_wider_model_and_batch():
+    """heads=4 (D=512), B=3, one prepared step, condition present."""
+    O, ocfg, Pb, P32, inp, W, plan = _setup(heads=4, layers=(1, 2), B=3, T=1)
+    ref32 = _oracle_full(O, ocfg, P32, inp, inp["ts"][0], torch.float32)
+    ref16 = _oracle_full(O, ocfg, Pb, inp, inp["ts"][0], torch.bfloat16)
+    got = plan.step(0, inp["lat"])
+    torch.cuda.synchronize()
+    e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
+    print(f"\n[wide] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
+    assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2
+
+
+def test_euler_and_pack_bit_exact():
+    from loongx_b200.dit import euler_step, pack_latents, unpack_latents
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((2, 16, 64, 64), generator=g, device="cuda").bfloat16()
+    packed = pack_latents(x)
+    ref = x.view(2, 16, 32, 2, 32, 2).permute(0, 2, 4, 1, 3, 5).reshape(2, 1024, 64)
+    assert torch.equal(packed, ref)
+    un = unpack_latents(packed, 512, 512)
+    ref_un = packed.view(2, 32, 32, 16, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(2, 16, 64, 64)
+    assert torch.equal(un, ref_un) and torch.equal(un, x)
+    xf = torch.randn((2, 16, 32, 48), generator=g, device="cuda")
+    assert torch.equal(unpack_latents(pack_latents(xf), 256, 384), xf)
+    v = torch.randn((2, 1024, 64), generator=g, device="cuda").bfloat16()
+    out = euler_step(packed, v, -0.0371)
+    ref_e = (packed.float() + (-0.0371) * v.float()).to(torch.bfloat16)
+    assert torch.equal(out, ref_e)
