@@ -59,14 +59,24 @@ typedef struct lx_gemm_segment {
   int64_t ldo;        /* elements */
 } lx_gemm_segment_t;
 
-typedef struct lx_gemm_desc {
-  const void* A; /* bf16 [M, K], row stride lda (elements, multiple of 8) */
-  int64_t lda;
+/* Row group: M-tiles [m_begin/128, next group's m_begin/128) multiply by this weight panel.  Lets one launch run the
+ * text rows against the *_context weights, the image rows against W and the condition rows against the LoRA-merged
+ * W + (alpha/r) B A (lora_controller.py:5-43 applies LoRA to the condition branch only). */
+typedef struct lx_gemm_group {
   const void* W; /* bf16 [N, K], row stride ldw */
   int64_t ldw;
   const float* bias; /* fp32 [N] or NULL */
-  int32_t M, N, K;
-  int32_t n_split; /* output columns >= n_split use seg[1] (multiple of 256); = N for a single segment */
+  int32_t K;         /* multiple of 8 */
+  int32_t m_begin;   /* first row of the group (multiple of 128; group 0 starts at 0) */
+} lx_gemm_group_t;
+
+typedef struct lx_gemm_desc {
+  const void* A; /* bf16 [M, K], row stride lda (elements, multiple of 8) */
+  int64_t lda;
+  int32_t M, N;
+  int32_t n_groups; /* 1..3 */
+  int32_t n_split;  /* output columns >= n_split use seg[1] (multiple of 256); = N for a single segment */
+  lx_gemm_group_t group[3];
   lx_gemm_segment_t seg[2];
   const lx_tile_meta_t* tile_meta; /* [ceil(M/128)]; required by GATE_RESIDUAL and QKV */
   /* LX_EPI_GATE_RESIDUAL */
@@ -83,7 +93,7 @@ typedef struct lx_gemm_desc {
   const float* rms_k[3];
   const float* rope; /* fp32 [seq_total, 64, 2] (cos, sin) per rotary pair, NULL = no RoPE */
   float rms_eps;
-  int32_t reserved;
+  int32_t tile_n; /* 0 = choose the N tile (256 / 224 / 192) that minimises wave quantisation; else force it */
 } lx_gemm_desc_t;
 
 int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream);
@@ -114,40 +124,23 @@ int lx_attention(const lx_attn_desc_t* desc, void* stream);
 /* ------------------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound).
  * ------------------------------------------------------------------------------------------------------ */
-/* out[:, 0:D] = LayerNorm(x; no affine, eps) * (1 + scale[stream,batch]) + shift[stream,batch];
- * out[:, D:D+ext] = (that bf16 row) . lora_a^T for rows whose stream is in lora_stream_mask, else 0.
+/* out = LayerNorm(x; no affine, eps) * (1 + scale[stream,batch]) + shift[stream,batch].
  * Replaces AdaLayerNormZero / -Single / -Continuous + norm2 FiLM (block.py:192-207, 238-253, 301-305;
- * transformer.py:243) and peft's lora_A on the same operand. */
+ * transformer.py:243). */
 typedef struct lx_lnmod_desc {
   const void* x; /* bf16 [rows, ldx] */
   int64_t ldx;
-  void* out; /* bf16 [rows, ldo], ldo >= D + ext */
+  void* out; /* bf16 [rows, ldo] */
   int64_t ldo;
   int32_t rows, D;
-  int32_t ext;    /* K-extension columns to fill (multiple of 64, 0 = none) */
-  int32_t lora_r; /* rows of lora_a (<= 16) */
   const lx_tile_meta_t* tile_meta;
   const void* shift[3]; /* bf16, per stream: shift[s] + batch*stride[s] */
   const void* scale[3];
   int64_t stride[3];
-  const void* lora_a; /* bf16 [lora_r, D] or NULL */
-  int32_t lora_stream_mask; /* bit s set = LoRA active on stream s (default: cond only = 4) */
   float eps;
+  int32_t reserved;
 } lx_lnmod_desc_t;
 int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream);
-
-/* x[:, K:K+ext] = x[:, 0:K] . lora_a^T (active rows) or 0: the LoRA "down" half for operands produced by another
- * kernel (attention output, GELU hidden, packed latents). */
-typedef struct lx_lora_down_desc {
-  void* x; /* bf16 [rows, ldx], ldx >= K + ext */
-  int64_t ldx;
-  int32_t rows, K, ext, lora_r;
-  const lx_tile_meta_t* tile_meta; /* NULL = every row is a condition row */
-  const void* lora_a;              /* bf16 [lora_r, K] or NULL */
-  int32_t lora_stream_mask;
-  int32_t reserved;
-} lx_lora_down_desc_t;
-int lx_lora_down(const lx_lora_down_desc_t* desc, void* stream);
 
 /* Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[m] = [cos(t*mult*f), sin(t*mult*f)] bf16. */
 int lx_timestep_embed(const float* t, void* out, int64_t ldo, int32_t M, float mult, void* stream);
@@ -166,17 +159,17 @@ int lx_pack_latents(const void* in, void* out, int32_t B, int32_t C, int32_t h, 
 
 /* ------------------------------------------------------------------------------------------------------
  * DiT engine: the whole tranformer_forward (transformer.py:47-252) as one native call sequence.
- * Weight layout: every nn.Linear is one lx_linear_t.  A LoRA-targeted Linear stores its weight K-extended:
- * columns [0,k) = base W, columns [k, k+ext) = lora_B * (alpha/r) (zero padded to a multiple of 64), and
- * lora_a holds the stacked lora_A rows; the operand producers fill the matching ext columns with x.A^T on the
- * rows where LoRA is active (condition stream by default, lora_controller.py:5-43), so base + LoRA is ONE GEMM.
+ * Weight layout: every nn.Linear is one lx_linear_t.  A LoRA-targeted Linear additionally carries w_lora =
+ * W + (alpha/r) lora_B lora_A, merged once at load (weights are frozen at inference); rows on which LoRA is active
+ * (the condition stream by default, lora_controller.py:5-43; also the image / text rows with latent_lora) are a
+ * separate row group of the same GEMM launch that reads w_lora instead of w.
  * ------------------------------------------------------------------------------------------------------ */
 typedef struct lx_linear {
   const void* w; /* bf16 [n, ldw] */
   int64_t ldw;
   const float* bias;  /* fp32 [n] or NULL */
-  const void* lora_a; /* bf16 [lora_r, k] or NULL */
-  int32_t n, k, ext, lora_r;
+  const void* w_lora; /* bf16 [n, ldw] merged weight, or NULL when the layer is not a LoRA target */
+  int32_t n, k;
 } lx_linear_t;
 
 typedef struct lx_double_block {
@@ -204,9 +197,9 @@ typedef struct lx_dit_model {
   int32_t reserved2;
   lx_linear_t x_embedder, context_embedder;
   lx_linear_t time_1, time_2, guid_1, guid_2, text_1, text_2;
-  lx_linear_t mod_img;    /* all double blocks' norm1.linear stacked:         [L*6D, D+ext] */
+  lx_linear_t mod_img;    /* all double blocks' norm1.linear stacked:         [L*6D, D] */
   lx_linear_t mod_txt;    /* all double blocks' norm1_context.linear stacked: [L*6D, D]     */
-  lx_linear_t mod_single; /* all single blocks' norm.linear stacked:          [Ls*3D, D+ext] */
+  lx_linear_t mod_single; /* all single blocks' norm.linear stacked:          [Ls*3D, D] */
   lx_linear_t norm_out, proj_out;
   const lx_double_block_t* double_blocks; /* host array [num_layers] */
   const lx_single_block_t* single_blocks; /* host array [num_single_layers] */
@@ -226,18 +219,17 @@ typedef struct lx_dit_plan {
   const int32_t* out_row_base;     /* device [B*S/128] */
   const float* rope;               /* device [S,64,2] for the joint [txt|img|cond] ids, or NULL */
   void* X;       /* bf16 [R, D] residual stream (stream-major rows) */
-  void* XN;      /* bf16 [R, D+64] modulated operand */
+  void* XN;      /* bf16 [R, D] modulated operand */
   void* Q;       /* bf16 [B,H,S,128] */
   void* K;
   void* V;
-  void* scratch; /* bf16 [R, 5D+64]: attention out / FF hidden / single-block concat */
-  void* XE;      /* bf16 [B*max(n_img,n_cond), in_channels+64] packed-latent operand of x_embedder */
+  void* scratch; /* bf16 [R, 5D]: attention out / FF hidden / single-block concat */
   void* X0_txt;  /* bf16 [B*n_txt, D]  context_embedder(prompt_embeds)   (step invariant) */
   void* X0_cond; /* bf16 [B*n_cond, D] x_embedder(cond_latents)          (step invariant) */
   void* emb_tmp; /* bf16 [4, T*B + B, D] scratch of the timestep / guidance / text MLPs */
   void* sin_tmp; /* bf16 [T*B + B, 256] */
-  void* silu_t;  /* bf16 [T*B, D + max ext] silu(temb) per (step, batch) */
-  void* silu_c;  /* bf16 [B,   D + max ext] silu(cond_temb) */
+  void* silu_t;  /* bf16 [T*B, D] silu(temb) per (step, batch) */
+  void* silu_c;  /* bf16 [B,   D] silu(cond_temb) */
   void* mod_img;      /* bf16 [T*B, L*6D] */
   void* mod_txt;      /* bf16 [T*B, L*6D] */
   void* mod_single;   /* bf16 [T*B, Ls*3D] */
@@ -265,6 +257,77 @@ int lx_dit_double_block(const lx_dit_model_t* model, const lx_dit_plan_t* plan, 
                         void* stream);
 int lx_dit_single_block(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, int32_t block,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * CS3 (cross-scale state-space signal encoders) and DGF (DUAN dynamic gated fusion): fp32, once per edit.
+ * Reference: src/train/model.py:16-373 (encoders), 479-511 (length normaliser), 731-779 (fuse_*), 947-1035 (DUAN);
+ * the S4 layer itself is the third-party s4torch package (model.py:14), restated per SURVEY.md App. B.
+ * ------------------------------------------------------------------------------------------------------ */
+/* OminiModel.spatial_pyramid_pooling (model.py:479-511): zero-pad / truncate rows of length Lin to Lout. */
+int lx_pad_truncate(const float* in, float* out, int32_t rows, int32_t Lin, int32_t Lout, void* stream);
+/* S4 DPLR convolution kernel K[d, L] from (lambda, p, q)[n] complex64, (B, Ct)[d, n] complex64, log_step[d]:
+ * Cauchy sums at the L roots of unity + inverse DFT, float64 internally.  workspace: L*d*16 bytes. */
+int lx_s4_kernel_gen(const void* lam, const void* p, const void* q, const void* Bm, const void* Ct, const float* log_step,
+                     float* K, void* workspace, int32_t d, int32_t n, int32_t L, void* stream);
+/* y[b,c,l] = gelu(sum_{j<=l} K[c,j] u[b,c,l-j] + D[c] u[b,c,l]) for u [B, d, L] (S4Layer + GELU). */
+int lx_s4_conv_gelu(const float* u, const float* K, const float* D, float* y, int32_t B, int32_t d, int32_t L,
+                    void* stream);
+/* out[b,j,l] = sum_c W[j,c] in[b,c,l] + bias[j] (+ residual[b,j,l]) (then LayerNorm over j with ln_w / ln_b). */
+int lx_channel_linear(const float* in, const float* W, const float* bias, const float* residual, const float* ln_w,
+                      const float* ln_b, float* out, int32_t B, int32_t d_in, int32_t d_out, int32_t L, float eps,
+                      void* stream);
+/* nn.AdaptiveAvgPool1d(O) on in [B, C, L]; out[b*out_bstride + c*cs + i*is + off] (model.py:83-103, 345-373). */
+int lx_adaptive_pool(const float* in, float* out, int32_t B, int32_t C, int32_t L, int32_t O, int64_t out_bstride,
+                     int32_t cs, int32_t is, int32_t off, void* stream);
+/* y[b, :] = W[n_out, n_in] x[b, :] + bias for B <= 8 rows (weights streamed once). */
+int lx_gemv_f32(const float* W, const float* bias, const float* x, float* y, int32_t B, int32_t n_out, int32_t n_in,
+                int64_t ldx, int64_t ldy, void* stream);
+/* y = relu(LayerNorm(x) * w + b) per row of [rows, n]. */
+int lx_ln_relu_rows(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t n, float eps,
+                    void* stream);
+/* Unflatten(tokens, 8) -> Linear(8, n_out): out[b, t, :] = W[n_out, 8] h[b, 8t:8t+8] + bias (model.py:70-71). */
+int lx_token_linear(const float* h, const float* W, const float* bias, float* out, int32_t B, int32_t tokens,
+                    int32_t n_out, int64_t out_bstride, void* stream);
+
+/* Batched fp32 GEMM  C[b] = act(A[M,K] . Bm[b][K,N] + bias[m] (+ R[b]));  act 0 none / 1 relu / 2 sigmoid.  With
+ * rowmean != NULL nothing is stored; mean_n(act(.)) is accumulated into rowmean[b, m] (must be zeroed). */
+typedef struct lx_sgemm_desc {
+  const float* A;
+  int64_t lda;
+  const float* Bm;
+  int64_t ldb;
+  int64_t b_bstride;
+  const float* bias; /* [M] or NULL */
+  const float* R;    /* residual with C's layout or NULL */
+  float* C;
+  int64_t ldc;
+  int64_t c_bstride;
+  float* rowmean; /* [batch, M] or NULL */
+  int32_t M, N, K, batch;
+  int32_t act;
+  int32_t reserved;
+} lx_sgemm_desc_t;
+int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream);
+
+/* fp32 <-> bf16 element cast (to_bf16 != 0: fp32 -> bf16). */
+int lx_cast(const void* in, void* out, int64_t n, int32_t to_bf16, void* stream);
+
+/* DUAN (model.py:947-1035): gate / FiLM 1x1-conv weights in nn.Conv1d layout [out, in]. */
+typedef struct lx_duan_weights {
+  const float* gate_w1; /* [hidden, C] */
+  const float* gate_b1;
+  const float* gate_w2; /* [C, hidden] */
+  const float* gate_b2;
+  const float* mlp_w1; /* [hidden, C] */
+  const float* mlp_b1;
+  const float* mlp_w2; /* [2C, hidden] */
+  const float* mlp_b2;
+  int32_t hidden;
+  float eps;
+} lx_duan_weights_t;
+/* y[b] (batch stride y_bstride) = DUAN(x, c) for fp32 x, c [B, C, L]; workspace: fp32 [B*(12*C + hidden*(L+1))]. */
+int lx_duan_forward(const lx_duan_weights_t* w, const float* x, const float* c, float* y, int64_t y_bstride, int32_t B,
+                    int32_t C, int32_t L, float keep_ratio, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

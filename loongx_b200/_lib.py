@@ -37,13 +37,16 @@ class GemmSegment(C.Structure):
     _fields_ = [("mode", c_int32), ("col_offset", c_int32), ("out", c_void_p), ("ldo", c_int64)]
 
 
+class GemmGroup(C.Structure):
+    _fields_ = [("W", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("K", c_int32), ("m_begin", c_int32)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("A", c_void_p), ("lda", c_int64),
-        ("W", c_void_p), ("ldw", c_int64),
-        ("bias", c_void_p),
-        ("M", c_int32), ("N", c_int32), ("K", c_int32),
-        ("n_split", c_int32),
+        ("M", c_int32), ("N", c_int32),
+        ("n_groups", c_int32), ("n_split", c_int32),
+        ("group", GemmGroup * 3),
         ("seg", GemmSegment * 2),
         ("tile_meta", c_void_p),
         ("residual", c_void_p), ("ldr", c_int64),
@@ -52,7 +55,7 @@ class GemmDesc(C.Structure):
         ("heads", c_int32), ("seq_total", c_int32),
         ("rms_q", c_void_p * 3), ("rms_k", c_void_p * 3),
         ("rope", c_void_p),
-        ("rms_eps", c_float), ("reserved", c_int32),
+        ("rms_eps", c_float), ("tile_n", c_int32),
     ]
 
 

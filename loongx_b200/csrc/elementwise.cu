@@ -1,7 +1,5 @@
 // HBM-bound row kernels of the DiT path (coalesced 16-byte loads/stores, one warp per activation row, fp32 math):
-//   ln_modulate      LayerNorm(no affine, eps) * (1 + scale) + shift  [+ rank-r LoRA "down" projection into the
-//                    K-extension columns of the GEMM A operand]                     (block.py:192-207,238-253,301-305)
-//   lora_down        rank-r LoRA "down" projection of an existing operand buffer    (peft LoRA Linear, App. A.8)
+//   ln_modulate      LayerNorm(no affine, eps) * (1 + scale) + shift               (block.py:192-207,238-253,301-305)
 //   timestep_embed   sinusoidal Timesteps(256, flip_sin_to_cos=True)                (transformer.py:102-114)
 //   add_silu         silu(a + b [+ c])  -> operand of every AdaLN modulation GEMM
 //   euler_step       FlowMatchEulerDiscreteScheduler.step                            (generate.py:349)
@@ -32,22 +30,6 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 constexpr int LN_MAX_NV = 12;  // D <= 3072 (NV = D / 256)
-constexpr int LORA_MAX_R = 16;
-
-// Writes the 64-column (or wider) K-extension of one row: columns [0, r) = t[], rest zero.
-__device__ __forceinline__ void write_ext(__nv_bfloat16* ext_ptr, int ext, const float* t, int r, int lane) {
-  for (int c = lane * 2; c < ext; c += 64) {
-    float lo = 0.f, hi = 0.f;
-#pragma unroll
-    for (int j = 0; j < LORA_MAX_R; ++j) {
-      if (j < r) {
-        if (c == j) lo = t[j];
-        if (c + 1 == j) hi = t[j];
-      }
-    }
-    *reinterpret_cast<uint32_t*>(ext_ptr + c) = pack_bf16(lo, hi);
-  }
-}
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln_modulate_kernel(const lx_lnmod_desc_t d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,69 +78,6 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_modulate_kernel(const lx_ln
       *reinterpret_cast<uint4*>(out + c0) = pack8(&v[i * 8]);
     }
   }
-  if (d.ext > 0) {
-    float t[LORA_MAX_R];
-#pragma unroll
-    for (int j = 0; j < LORA_MAX_R; ++j) t[j] = 0.f;
-    const bool active = d.lora_a != nullptr && ((d.lora_stream_mask >> meta.stream) & 1);
-    if (active) {
-      const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(d.lora_a);
-#pragma unroll
-      for (int i = 0; i < LN_MAX_NV; ++i) {
-        if (i < nv) {
-          float xb[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) xb[e] = bf16_round(v[i * 8 + e]);  // LoRA sees the bf16 operand
-#pragma unroll
-          for (int j = 0; j < LORA_MAX_R; ++j) {
-            if (j < d.lora_r) {
-              float a[8];
-              load8_ldg(A + (size_t)j * d.D + i * 256 + lane * 8, a);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) t[j] += xb[e] * a[e];
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < LORA_MAX_R; ++j)
-        if (j < d.lora_r) t[j] = warp_sum(t[j]);
-    }
-    write_ext(out + d.D, d.ext, t, active ? d.lora_r : 0, lane);
-  }
-}
-
-__global__ void __launch_bounds__(ROW_WARPS * 32) lora_down_kernel(const lx_lora_down_desc_t d) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + warp;
-  if (row >= d.rows) return;
-  int stream = 2;
-  if (d.tile_meta != nullptr) stream = d.tile_meta[row >> 7].stream;
-  const bool active = d.lora_a != nullptr && ((d.lora_stream_mask >> stream) & 1);
-  __nv_bfloat16* x = reinterpret_cast<__nv_bfloat16*>(d.x) + (size_t)row * d.ldx;
-  float t[LORA_MAX_R];
-#pragma unroll
-  for (int j = 0; j < LORA_MAX_R; ++j) t[j] = 0.f;
-  if (active) {
-    const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(d.lora_a);
-    for (int c0 = lane * 8; c0 < d.K; c0 += 256) {
-      float xv[8];
-      load8(x + c0, xv);
-#pragma unroll
-      for (int j = 0; j < LORA_MAX_R; ++j) {
-        if (j < d.lora_r) {
-          float a[8];
-          load8_ldg(A + (size_t)j * d.K + c0, a);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) t[j] += xv[e] * a[e];
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < LORA_MAX_R; ++j)
-      if (j < d.lora_r) t[j] = warp_sum(t[j]);
-  }
-  write_ext(x + d.K, d.ext, t, active ? d.lora_r : 0, lane);
 }
 
 // out[m, 0:128] = cos(t*f_j), out[m, 128:256] = sin(t*f_j), f_j = exp(-ln(1e4) j / 128)
@@ -269,24 +188,9 @@ extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.rows > 0 && d.D > 0 && d.D % 256 == 0 && d.D <= LN_MAX_NV * 256,
                "lx_ln_modulate: D=%d must be a multiple of 256 and <= %d", d.D, LN_MAX_NV * 256);
   LX_CHECK_ARG(d.x && d.out && d.tile_meta, "lx_ln_modulate: null pointer");
-  LX_CHECK_ARG(d.ldx % 8 == 0 && d.ldo % 8 == 0 && d.ldo >= d.D + d.ext, "lx_ln_modulate: bad strides");
-  LX_CHECK_ARG(d.ext % 64 == 0 && d.lora_r >= 0 && d.lora_r <= LORA_MAX_R && d.lora_r <= (d.ext > 0 ? d.ext : 0),
-               "lx_ln_modulate: bad LoRA extension (ext=%d r=%d)", d.ext, d.lora_r);
+  LX_CHECK_ARG(d.ldx % 8 == 0 && d.ldo % 8 == 0 && d.ldo >= d.D && d.ldx >= d.D, "lx_ln_modulate: bad strides");
   const int grid = (d.rows + ROW_WARPS - 1) / ROW_WARPS;
   ln_modulate_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(d);
-  LX_CUDA(cudaGetLastError());
-  return LX_OK;
-}
-
-extern "C" int lx_lora_down(const lx_lora_down_desc_t* desc, void* stream) {
-  LX_CHECK_ARG(desc != nullptr, "lx_lora_down: null descriptor");
-  const lx_lora_down_desc_t& d = *desc;
-  LX_CHECK_ARG(d.rows > 0 && d.K > 0 && d.K % 8 == 0 && d.x, "lx_lora_down: bad shape");
-  LX_CHECK_ARG(d.ext > 0 && d.ext % 64 == 0 && d.lora_r >= 0 && d.lora_r <= LORA_MAX_R && d.ldx >= d.K + d.ext &&
-                   d.ldx % 8 == 0,
-               "lx_lora_down: bad extension (ext=%d r=%d ldx=%lld)", d.ext, d.lora_r, (long long)d.ldx);
-  const int grid = (d.rows + ROW_WARPS - 1) / ROW_WARPS;
-  lora_down_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(d);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -9,7 +9,11 @@
 //     weights are streamed from HBM once per edit instead of once per step);
 //   * q/k/v (+ proj_mlp in single blocks) are one GEMM whose epilogue does bias + per-head RMSNorm + RoPE + the
 //     head-major scatter; out-projections / FF-down / proj_out apply gate*x + residual in the epilogue;
-//   * LoRA (condition rows only unless latent_lora) rides along as 64 extra K columns of the same GEMM.
+//   * the three streams of a double block (text rows x *_context weights, image rows x W, condition rows x the
+//     LoRA-merged W + (alpha/r)BA) are row groups of ONE GEMM launch, so LoRA costs no extra kernels and the small
+//     text GEMMs no longer leave two thirds of the SMs idle.
+#include <string.h>
+
 #include <vector>
 
 #include "host_util.cuh"
@@ -34,40 +38,48 @@ Geo geo(const lx_dit_model_t& m, const lx_dit_plan_t& p) {
 
 inline char* bptr(void* p) { return reinterpret_cast<char*>(p); }
 inline const char* bptr(const void* p) { return reinterpret_cast<const char*>(p); }
-// bf16 element offset
-inline void* off(void* p, int64_t elems) { return bptr(p) + elems * 2; }
+inline void* off(void* p, int64_t elems) { return bptr(p) + elems * 2; }  // bf16 element offset
 inline const void* off(const void* p, int64_t elems) { return bptr(p) + elems * 2; }
 
-#define LX_TRY(expr)          \
-  do {                        \
-    int rc__ = (expr);        \
+#define LX_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
     if (rc__ != 0) return rc__; \
   } while (0)
 
-lx_gemm_desc_t gemm_base(const lx_linear_t& L, const void* A, int64_t lda, int M, bool use_ext) {
+inline const void* lora_w(const lx_linear_t& L) { return L.w_lora ? L.w_lora : L.w; }
+
+lx_gemm_desc_t gemm_zero(const void* A, int64_t lda, int M, int N) {
   lx_gemm_desc_t d;
   memset(&d, 0, sizeof(d));
-  d.A = A; d.lda = lda;
-  d.W = L.w; d.ldw = L.ldw;
-  d.bias = L.bias;
-  d.M = M; d.N = L.n; d.K = L.k + (use_ext ? L.ext : 0);
-  d.n_split = L.n;
-  d.rms_eps = 1e-6f;
+  d.A = A; d.lda = lda; d.M = M; d.N = N; d.n_split = N; d.rms_eps = 1e-6f;
   return d;
 }
+void set_group(lx_gemm_desc_t& d, int g, const void* W, const lx_linear_t& L, int m_begin) {
+  d.group[g].W = W; d.group[g].ldw = L.ldw; d.group[g].bias = L.bias; d.group[g].K = L.k; d.group[g].m_begin = m_begin;
+  d.n_groups = g + 1;
+}
 
-int gemm_simple(const lx_linear_t& L, const void* A, int64_t lda, int M, bool use_ext, int mode, void* out, int64_t ldo,
+// One Linear over a contiguous row range, single weight panel.
+int gemm_simple(const lx_linear_t& L, const void* W, const void* A, int64_t lda, int M, int mode, void* out, int64_t ldo,
                 int col_offset, void* stream) {
-  lx_gemm_desc_t d = gemm_base(L, A, lda, M, use_ext);
+  lx_gemm_desc_t d = gemm_zero(A, lda, M, L.n);
+  set_group(d, 0, W, L, 0);
   d.seg[0].mode = mode; d.seg[0].out = out; d.seg[0].ldo = ldo; d.seg[0].col_offset = col_offset;
   return lx_gemm_bf16(&d, stream);
 }
 
-// views of one row of modulation tables for (step, block)
-struct ModPtrs {
-  const void* base[3];  // per stream, pointing at column 0 of this block's chunk group
-  int64_t stride[3];
-};
+// Row groups of a double-block GEMM over all R rows: [txt | img | cond].
+void double_groups(lx_gemm_desc_t& d, const Geo& g, const lx_linear_t& ctx, const lx_linear_t& L, bool latent_lora) {
+  set_group(d, 0, ctx.w, ctx, 0);
+  set_group(d, 1, latent_lora ? lora_w(L) : L.w, L, g.Rt);
+  if (g.nc > 0) set_group(d, 2, lora_w(L), L, g.Rt + g.Ri);
+}
+// Row groups of a single-block GEMM: [txt + img | cond].
+void single_groups(lx_gemm_desc_t& d, const Geo& g, const lx_linear_t& L, bool latent_lora) {
+  set_group(d, 0, latent_lora ? lora_w(L) : L.w, L, 0);
+  if (g.nc > 0) set_group(d, 1, lora_w(L), L, g.Rt + g.Ri);
+}
 
 int check_plan(const lx_dit_model_t* m, const lx_dit_plan_t* p) {
   LX_CHECK_ARG(m && p, "dit: null model / plan");
@@ -77,14 +89,21 @@ int check_plan(const lx_dit_model_t* m, const lx_dit_plan_t* p) {
   LX_CHECK_ARG(p->n_txt % 128 == 0 && p->n_img % 128 == 0 && p->n_cond % 128 == 0,
                "dit: stream lengths must be multiples of 128 (txt %d img %d cond %d)", p->n_txt, p->n_img, p->n_cond);
   LX_CHECK_ARG(p->T > 0, "dit: T must be positive");
-  LX_CHECK_ARG(m->in_channels % 8 == 0 && m->in_channels <= 64, "dit: in_channels=%d unsupported", m->in_channels);
+  LX_CHECK_ARG(m->in_channels % 8 == 0, "dit: in_channels=%d must be a multiple of 8", m->in_channels);
   if (p->add_cond_attn) {
     set_error("dit: model_config.add_cond_attn=True (block.py:233-234) is not implemented");
     return LX_ERR_UNSUPPORTED;
   }
-  LX_CHECK_ARG(p->tile_meta && p->out_row_base && p->X && p->XN && p->Q && p->K && p->V && p->scratch && p->XE,
+  LX_CHECK_ARG(p->tile_meta && p->out_row_base && p->X && p->XN && p->Q && p->K && p->V && p->scratch,
                "dit: missing work buffer");
   return LX_OK;
+}
+
+void fill_attn(lx_attn_desc_t& a, const lx_dit_plan_t& p, const Geo& g, int64_t ldo) {
+  memset(&a, 0, sizeof(a));
+  a.q = p.Q; a.k = p.K; a.v = p.V; a.out = p.scratch; a.ldo = ldo; a.out_row_base = p.out_row_base;
+  a.B = g.B; a.H = g.H; a.S = g.S; a.n_cond = g.nc; a.mask_mode = p.mask_mode; a.cross_bias = p.cross_bias;
+  a.scale = 0.08838834764831845f;  // 1/sqrt(128)
 }
 
 int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int blk, void* stream) {
@@ -93,10 +112,7 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   const int D = g.D;
   const int64_t ldm = (int64_t)m.num_layers * 6 * D;
   const bool has_cond = g.nc > 0;
-  const int lora_mask = 4 | (p.latent_lora ? 2 : 0);
-  const int Ric = g.Ri + g.Rc;
-  const int64_t ldxn = D + 64, ldao = D + 64, ldff = g.FF + 64;
-  const lx_tile_meta_t* meta_ic = p.tile_meta + g.Rt / 128;
+  const bool ll = p.latent_lora != 0;
 
   // modulation chunk base pointers for this (step, block): [shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp]
   const void* mod[3] = {off(p.mod_txt, (int64_t)step * g.B * ldm + (int64_t)blk * 6 * D),
@@ -105,103 +121,60 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   auto fill3 = [&](const void* (&dst)[3], int chunk) {
     for (int s = 0; s < 3; ++s) dst[s] = mod[s] ? off(mod[s], (int64_t)chunk * D) : nullptr;
   };
-
-  // 1. AdaLN-Zero on all three streams (+ LoRA-A of q/k/v on the active rows)
-  {
+  auto lnmod = [&](int shift_chunk, int scale_chunk) -> int {
     lx_lnmod_desc_t d;
     memset(&d, 0, sizeof(d));
-    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = ldxn; d.rows = g.R; d.D = D;
-    d.ext = W.qkv.ext; d.lora_r = W.qkv.lora_r; d.lora_a = W.qkv.lora_a; d.lora_stream_mask = lora_mask;
+    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.R; d.D = D;
     d.tile_meta = p.tile_meta; d.eps = 1e-6f;
-    fill3(d.shift, 0); fill3(d.scale, 1);
+    fill3(d.shift, shift_chunk); fill3(d.scale, scale_chunk);
     for (int s = 0; s < 3; ++s) d.stride[s] = ldm;
-    LX_TRY(lx_ln_modulate(&d, stream));
-  }
-  // 2. QKV projections with fused RMSNorm + RoPE + head scatter
-  {
-    lx_gemm_desc_t d = gemm_base(W.qkv_ctx, p.XN, ldxn, g.Rt, false);
-    d.seg[0].mode = LX_EPI_QKV; d.tile_meta = p.tile_meta;
-    d.q = p.Q; d.k = p.K; d.v = p.V; d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
-    for (int s = 0; s < 3; ++s) { d.rms_q[s] = W.norm_added_q; d.rms_k[s] = W.norm_added_k; }
-    LX_TRY(lx_gemm_bf16(&d, stream));
-  }
-  {
-    lx_gemm_desc_t d = gemm_base(W.qkv, off(p.XN, (int64_t)g.Rt * ldxn), ldxn, Ric, W.qkv.ext > 0);
-    d.seg[0].mode = LX_EPI_QKV; d.tile_meta = meta_ic;
-    d.q = p.Q; d.k = p.K; d.v = p.V; d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
-    for (int s = 0; s < 3; ++s) { d.rms_q[s] = W.norm_q; d.rms_k[s] = W.norm_k; }
-    LX_TRY(lx_gemm_bf16(&d, stream));
-  }
-  // 3. joint attention -> scratch viewed as AO [R, D+64]
-  {
-    lx_attn_desc_t a;
-    memset(&a, 0, sizeof(a));
-    a.q = p.Q; a.k = p.K; a.v = p.V; a.out = p.scratch; a.ldo = ldao; a.out_row_base = p.out_row_base;
-    a.B = g.B; a.H = g.H; a.S = g.S; a.n_cond = g.nc; a.mask_mode = p.mask_mode; a.cross_bias = p.cross_bias;
-    a.scale = 0.08838834764831845f;
-    LX_TRY(lx_attention(&a, stream));
-  }
-  // 4. out projections with gate * y + residual
-  if (W.out.ext > 0) {
-    lx_lora_down_desc_t l;
-    memset(&l, 0, sizeof(l));
-    l.x = off(p.scratch, (int64_t)g.Rt * ldao); l.ldx = ldao; l.rows = Ric; l.K = D; l.ext = W.out.ext;
-    l.lora_r = W.out.lora_r; l.lora_a = W.out.lora_a; l.tile_meta = meta_ic; l.lora_stream_mask = lora_mask;
-    LX_TRY(lx_lora_down(&l, stream));
-  }
-  {
-    lx_gemm_desc_t d = gemm_base(W.out_ctx, p.scratch, ldao, g.Rt, false);
+    return lx_ln_modulate(&d, stream);
+  };
+  auto gate_res = [&](lx_gemm_desc_t& d, int gate_chunk) {
     d.seg[0].mode = LX_EPI_GATE_RESIDUAL; d.seg[0].out = p.X; d.seg[0].ldo = D;
     d.residual = p.X; d.ldr = D; d.tile_meta = p.tile_meta;
-    fill3(d.gate, 2);
+    fill3(d.gate, gate_chunk);
     for (int s = 0; s < 3; ++s) d.gate_stride[s] = ldm;
+  };
+
+  // 1. AdaLN-Zero on all three streams
+  LX_TRY(lnmod(0, 1));
+  // 2. q/k/v of all streams in one launch; epilogue: bias + RMSNorm(q,k) + RoPE + scatter to [B,H,S,128]
+  {
+    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.R, 3 * D);
+    double_groups(d, g, W.qkv_ctx, W.qkv, ll);
+    d.seg[0].mode = LX_EPI_QKV; d.tile_meta = p.tile_meta;
+    d.q = p.Q; d.k = p.K; d.v = p.V; d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
+    d.rms_q[0] = W.norm_added_q; d.rms_k[0] = W.norm_added_k;
+    d.rms_q[1] = d.rms_q[2] = W.norm_q; d.rms_k[1] = d.rms_k[2] = W.norm_k;
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
+  // 3. joint attention -> scratch viewed as [R, D]
   {
-    lx_gemm_desc_t d = gemm_base(W.out, off(p.scratch, (int64_t)g.Rt * ldao), ldao, Ric, W.out.ext > 0);
-    void* x_ic = off(p.X, (int64_t)g.Rt * D);
-    d.seg[0].mode = LX_EPI_GATE_RESIDUAL; d.seg[0].out = x_ic; d.seg[0].ldo = D;
-    d.residual = x_ic; d.ldr = D; d.tile_meta = meta_ic;
-    fill3(d.gate, 2);
-    for (int s = 0; s < 3; ++s) d.gate_stride[s] = ldm;
+    lx_attn_desc_t a;
+    fill_attn(a, p, g, D);
+    LX_TRY(lx_attention(&a, stream));
+  }
+  // 4. to_out / to_add_out with gate_msa * y + residual
+  {
+    lx_gemm_desc_t d = gemm_zero(p.scratch, D, g.R, D);
+    double_groups(d, g, W.out_ctx, W.out, ll);
+    gate_res(d, 2);
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
   // 5. norm2 + FiLM (shift_mlp / scale_mlp)
+  LX_TRY(lnmod(3, 4));
+  // 6. feed-forward up (+GELU-tanh) -> scratch viewed as [R, 4D]; down with gate_mlp * y + residual
   {
-    lx_lnmod_desc_t d;
-    memset(&d, 0, sizeof(d));
-    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = ldxn; d.rows = g.R; d.D = D;
-    d.tile_meta = p.tile_meta; d.eps = 1e-6f;
-    fill3(d.shift, 3); fill3(d.scale, 4);
-    for (int s = 0; s < 3; ++s) d.stride[s] = ldm;
-    LX_TRY(lx_ln_modulate(&d, stream));
-  }
-  // 6. feed-forward: up (+GELU-tanh) -> scratch viewed as FFH [R, 4D+64]; down with gate * y + residual
-  LX_TRY(gemm_simple(W.ff_ctx_up, p.XN, ldxn, g.Rt, false, LX_EPI_BIAS_GELU, p.scratch, ldff, 0, stream));
-  LX_TRY(gemm_simple(W.ff_up, off(p.XN, (int64_t)g.Rt * ldxn), ldxn, Ric, false, LX_EPI_BIAS_GELU,
-                     off(p.scratch, (int64_t)g.Rt * ldff), ldff, 0, stream));
-  if (W.ff_down.ext > 0) {
-    lx_lora_down_desc_t l;
-    memset(&l, 0, sizeof(l));
-    l.x = off(p.scratch, (int64_t)g.Rt * ldff); l.ldx = ldff; l.rows = Ric; l.K = g.FF; l.ext = W.ff_down.ext;
-    l.lora_r = W.ff_down.lora_r; l.lora_a = W.ff_down.lora_a; l.tile_meta = meta_ic; l.lora_stream_mask = lora_mask;
-    LX_TRY(lx_lora_down(&l, stream));
-  }
-  {
-    lx_gemm_desc_t d = gemm_base(W.ff_ctx_down, p.scratch, ldff, g.Rt, false);
-    d.seg[0].mode = LX_EPI_GATE_RESIDUAL; d.seg[0].out = p.X; d.seg[0].ldo = D;
-    d.residual = p.X; d.ldr = D; d.tile_meta = p.tile_meta;
-    fill3(d.gate, 5);
-    for (int s = 0; s < 3; ++s) d.gate_stride[s] = ldm;
+    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.R, g.FF);
+    double_groups(d, g, W.ff_ctx_up, W.ff_up, ll);
+    d.seg[0].mode = LX_EPI_BIAS_GELU; d.seg[0].out = p.scratch; d.seg[0].ldo = g.FF;
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
   {
-    lx_gemm_desc_t d = gemm_base(W.ff_down, off(p.scratch, (int64_t)g.Rt * ldff), ldff, Ric, W.ff_down.ext > 0);
-    void* x_ic = off(p.X, (int64_t)g.Rt * D);
-    d.seg[0].mode = LX_EPI_GATE_RESIDUAL; d.seg[0].out = x_ic; d.seg[0].ldo = D;
-    d.residual = x_ic; d.ldr = D; d.tile_meta = meta_ic;
-    fill3(d.gate, 5);
-    for (int s = 0; s < 3; ++s) d.gate_stride[s] = ldm;
+    lx_gemm_desc_t d = gemm_zero(p.scratch, g.FF, g.R, D);
+    double_groups(d, g, W.ff_ctx_down, W.ff_down, ll);
+    gate_res(d, 5);
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
   return LX_OK;
@@ -213,8 +186,8 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   const int D = g.D;
   const int64_t ldm = (int64_t)m.num_single_layers * 3 * D;
   const bool has_cond = g.nc > 0;
-  const int lora_mask = 4 | (p.latent_lora ? 3 : 0);
-  const int64_t ldxn = D + 64, ldcat = 5 * (int64_t)D + 64;
+  const bool ll = p.latent_lora != 0;
+  const int64_t ldcat = 5 * (int64_t)D;
 
   // text and image rows share the temb modulation (the reference runs them as one tensor, block.py:301)
   const void* mod_t = off(p.mod_single, (int64_t)step * g.B * ldm + (int64_t)blk * 3 * D);
@@ -225,8 +198,7 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   {
     lx_lnmod_desc_t d;
     memset(&d, 0, sizeof(d));
-    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = ldxn; d.rows = g.R; d.D = D;
-    d.ext = W.qkv_mlp.ext; d.lora_r = W.qkv_mlp.lora_r; d.lora_a = W.qkv_mlp.lora_a; d.lora_stream_mask = lora_mask;
+    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.R; d.D = D;
     d.tile_meta = p.tile_meta; d.eps = 1e-6f;
     fill3(d.shift, 0); fill3(d.scale, 1);
     for (int s = 0; s < 3; ++s) d.stride[s] = ldm;
@@ -234,7 +206,8 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   }
   {
     // [q|k|v] -> QKV epilogue, proj_mlp -> GELU into the concat buffer columns [D, 5D)
-    lx_gemm_desc_t d = gemm_base(W.qkv_mlp, p.XN, ldxn, g.R, W.qkv_mlp.ext > 0);
+    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.R, 7 * D);
+    single_groups(d, g, W.qkv_mlp, ll);
     d.n_split = 3 * D;
     d.seg[0].mode = LX_EPI_QKV;
     d.seg[1].mode = LX_EPI_BIAS_GELU; d.seg[1].out = p.scratch; d.seg[1].ldo = ldcat; d.seg[1].col_offset = D;
@@ -245,21 +218,12 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   }
   {
     lx_attn_desc_t a;
-    memset(&a, 0, sizeof(a));
-    a.q = p.Q; a.k = p.K; a.v = p.V; a.out = p.scratch; a.ldo = ldcat; a.out_row_base = p.out_row_base;
-    a.B = g.B; a.H = g.H; a.S = g.S; a.n_cond = g.nc; a.mask_mode = p.mask_mode; a.cross_bias = p.cross_bias;
-    a.scale = 0.08838834764831845f;
+    fill_attn(a, p, g, ldcat);
     LX_TRY(lx_attention(&a, stream));
   }
-  if (W.proj_out.ext > 0) {
-    lx_lora_down_desc_t l;
-    memset(&l, 0, sizeof(l));
-    l.x = p.scratch; l.ldx = ldcat; l.rows = g.R; l.K = 5 * D; l.ext = W.proj_out.ext;
-    l.lora_r = W.proj_out.lora_r; l.lora_a = W.proj_out.lora_a; l.tile_meta = p.tile_meta; l.lora_stream_mask = lora_mask;
-    LX_TRY(lx_lora_down(&l, stream));
-  }
   {
-    lx_gemm_desc_t d = gemm_base(W.proj_out, p.scratch, ldcat, g.R, W.proj_out.ext > 0);
+    lx_gemm_desc_t d = gemm_zero(p.scratch, ldcat, g.R, D);
+    single_groups(d, g, W.proj_out, ll);
     d.seg[0].mode = LX_EPI_GATE_RESIDUAL; d.seg[0].out = p.X; d.seg[0].ldo = D;
     d.residual = p.X; d.ldr = D; d.tile_meta = p.tile_meta;
     fill3(d.gate, 2);
@@ -272,8 +236,21 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
 // y[M, D] = linear_2(silu(linear_1(x)))   (TimestepEmbedding / PixArtAlphaTextProjection)
 int mlp2(const lx_linear_t& l1, const lx_linear_t& l2, const void* x, int64_t ldx, int M, void* hidden, void* out, int D,
          void* stream) {
-  LX_TRY(gemm_simple(l1, x, ldx, M, false, LX_EPI_BIAS_SILU, hidden, D, 0, stream));
-  return gemm_simple(l2, hidden, D, M, false, LX_EPI_BIAS, out, D, 0, stream);
+  LX_TRY(gemm_simple(l1, l1.w, x, ldx, M, LX_EPI_BIAS_SILU, hidden, D, 0, stream));
+  return gemm_simple(l2, l2.w, hidden, D, M, LX_EPI_BIAS, out, D, 0, stream);
+}
+
+int embed_inputs(const lx_dit_model_t& m, const lx_dit_plan_t& p, const void* latents, void* stream) {
+  const Geo g = geo(m, p);
+  const int D = g.D, C = m.in_channels;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LX_TRY(gemm_simple(m.x_embedder, p.latent_lora ? lora_w(m.x_embedder) : m.x_embedder.w, latents, C, g.Ri, LX_EPI_BIAS,
+                     off(p.X, (int64_t)g.Rt * D), D, 0, stream));
+  LX_CUDA(cudaMemcpyAsync(p.X, p.X0_txt, (size_t)g.Rt * D * 2, cudaMemcpyDeviceToDevice, st));
+  if (g.nc > 0)
+    LX_CUDA(cudaMemcpyAsync(off(p.X, (int64_t)(g.Rt + g.Ri) * D), p.X0_cond, (size_t)g.Rc * D * 2,
+                            cudaMemcpyDeviceToDevice, st));
+  return LX_OK;
 }
 
 }  // namespace
@@ -294,7 +271,6 @@ extern "C" int lx_dit_prepare(const lx_dit_model_t* model, const lx_dit_plan_t* 
                    p.mod_out && p.t_dev && p.g_dev,
                "lx_dit_prepare: missing plan buffer");
   const int Mt = p.T * g.B, M = Mt + g.B;  // rows: all (step, batch) pairs, then the B cond_temb rows
-  const int64_t lds = D + 64;
 
   // timestep / guidance values -> device (pageable source: staged synchronously by the runtime)
   {
@@ -305,8 +281,8 @@ extern "C" int lx_dit_prepare(const lx_dit_model_t* model, const lx_dit_plan_t* 
     LX_CUDA(cudaMemcpyAsync(p.t_dev, tv.data(), M * sizeof(float), cudaMemcpyHostToDevice, st));
     LX_CUDA(cudaMemcpyAsync(p.g_dev, gv.data(), M * sizeof(float), cudaMemcpyHostToDevice, st));
   }
-  void* e_hid = p.emb_tmp;                       // [M, D] hidden of the embedder MLPs
-  void* e_t = off(p.emb_tmp, (int64_t)M * D);    // timestep embedding
+  void* e_hid = p.emb_tmp;                         // [M, D] hidden of the embedder MLPs
+  void* e_t = off(p.emb_tmp, (int64_t)M * D);      // timestep embedding
   void* e_g = off(p.emb_tmp, 2 * (int64_t)M * D);  // guidance embedding
   void* e_x = off(p.emb_tmp, 3 * (int64_t)M * D);  // pooled-text embedding [B, D]
   LX_TRY(lx_timestep_embed(p.t_dev, p.sin_tmp, 256, M, 1000.f, stream));
@@ -317,77 +293,29 @@ extern "C" int lx_dit_prepare(const lx_dit_model_t* model, const lx_dit_plan_t* 
   }
   LX_TRY(mlp2(m.text_1, m.text_2, pooled, m.pooled_dim, g.B, e_hid, e_x, D, stream));
   // silu(temb) for the T*B step rows and the B cond rows (text embedding broadcast over steps)
-  LX_TRY(lx_add_silu_bcast(e_t, m.guidance_embeds ? e_g : nullptr, e_x, g.B, p.silu_t, lds, Mt, D, stream));
+  LX_TRY(lx_add_silu_bcast(e_t, m.guidance_embeds ? e_g : nullptr, e_x, g.B, p.silu_t, D, Mt, D, stream));
   LX_TRY(lx_add_silu_bcast(off(e_t, (int64_t)Mt * D), m.guidance_embeds ? off(e_g, (int64_t)Mt * D) : nullptr, e_x, g.B,
-                           p.silu_c, lds, g.B, D, stream));
+                           p.silu_c, D, g.B, D, stream));
 
-  // modulation tables for the temb rows: one stacked GEMM per family (LoRA inactive unless latent_lora)
-  LX_TRY(gemm_simple(m.mod_txt, p.silu_t, lds, Mt, false, LX_EPI_BIAS, p.mod_txt, m.mod_txt.n, 0, stream));
-  LX_TRY(gemm_simple(m.norm_out, p.silu_t, lds, Mt, false, LX_EPI_BIAS, p.mod_out, m.norm_out.n, 0, stream));
-  auto per_block_mod = [&](const lx_linear_t& L, int nblk, void* A, int Mrows, void* out) -> int {
-    // LoRA-active rows: each block has its own lora_A, so run block by block (HBM-bound, once per edit)
-    const int per = L.n / nblk;
-    for (int b = 0; b < nblk; ++b) {
-      lx_linear_t Lb = L;
-      Lb.w = off(L.w, (int64_t)b * per * L.ldw);
-      Lb.bias = L.bias ? L.bias + (int64_t)b * per : nullptr;
-      Lb.n = per;
-      if (L.ext > 0) {
-        lx_lora_down_desc_t l;
-        memset(&l, 0, sizeof(l));
-        l.x = A; l.ldx = lds; l.rows = Mrows; l.K = D; l.ext = 64; l.lora_r = L.lora_r;
-        l.lora_a = L.lora_a ? off(L.lora_a, (int64_t)b * L.lora_r * D) : nullptr;
-        l.tile_meta = nullptr; l.lora_stream_mask = 4;
-        LX_TRY(lx_lora_down(&l, stream));
-      }
-      LX_TRY(gemm_simple(Lb, A, lds, Mrows, L.ext > 0, LX_EPI_BIAS, out, L.n, b * per, stream));
-    }
-    return LX_OK;
-  };
-  if (p.latent_lora) {
-    LX_TRY(per_block_mod(m.mod_img, m.num_layers, p.silu_t, Mt, p.mod_img));
-    LX_TRY(per_block_mod(m.mod_single, m.num_single_layers, p.silu_t, Mt, p.mod_single));
-  } else {
-    LX_TRY(gemm_simple(m.mod_img, p.silu_t, lds, Mt, false, LX_EPI_BIAS, p.mod_img, m.mod_img.n, 0, stream));
-    LX_TRY(gemm_simple(m.mod_single, p.silu_t, lds, Mt, false, LX_EPI_BIAS, p.mod_single, m.mod_single.n, 0, stream));
-  }
+  // AdaLN modulation tables of every block: one stacked GEMM per family
+  const bool ll = p.latent_lora != 0;
+  LX_TRY(gemm_simple(m.mod_txt, m.mod_txt.w, p.silu_t, D, Mt, LX_EPI_BIAS, p.mod_txt, m.mod_txt.n, 0, stream));
+  LX_TRY(gemm_simple(m.norm_out, m.norm_out.w, p.silu_t, D, Mt, LX_EPI_BIAS, p.mod_out, m.norm_out.n, 0, stream));
+  LX_TRY(gemm_simple(m.mod_img, ll ? lora_w(m.mod_img) : m.mod_img.w, p.silu_t, D, Mt, LX_EPI_BIAS, p.mod_img,
+                     m.mod_img.n, 0, stream));
+  LX_TRY(gemm_simple(m.mod_single, ll ? lora_w(m.mod_single) : m.mod_single.w, p.silu_t, D, Mt, LX_EPI_BIAS, p.mod_single,
+                     m.mod_single.n, 0, stream));
   if (g.nc > 0) {
     LX_CHECK_ARG(p.mod_cond_img && p.mod_cond_single && p.X0_cond, "lx_dit_prepare: missing cond buffers");
-    LX_TRY(per_block_mod(m.mod_img, m.num_layers, p.silu_c, g.B, p.mod_cond_img));
-    LX_TRY(per_block_mod(m.mod_single, m.num_single_layers, p.silu_c, g.B, p.mod_cond_single));
-    // x_embedder(cond) with LoRA
-    const int C = m.in_channels;
-    const int64_t ldxe = C + 64;
-    LX_CUDA(cudaMemcpy2DAsync(p.XE, ldxe * 2, cond_latents, C * 2, C * 2, g.Rc, cudaMemcpyDeviceToDevice, st));
-    lx_lora_down_desc_t l;
-    memset(&l, 0, sizeof(l));
-    l.x = p.XE; l.ldx = ldxe; l.rows = g.Rc; l.K = C; l.ext = 64; l.lora_r = m.x_embedder.lora_r;
-    l.lora_a = m.x_embedder.lora_a; l.tile_meta = nullptr; l.lora_stream_mask = 4;
-    LX_TRY(lx_lora_down(&l, stream));
-    LX_TRY(gemm_simple(m.x_embedder, p.XE, ldxe, g.Rc, m.x_embedder.ext > 0, LX_EPI_BIAS, p.X0_cond, D, 0, stream));
+    LX_TRY(gemm_simple(m.mod_img, lora_w(m.mod_img), p.silu_c, D, g.B, LX_EPI_BIAS, p.mod_cond_img, m.mod_img.n, 0, stream));
+    LX_TRY(gemm_simple(m.mod_single, lora_w(m.mod_single), p.silu_c, D, g.B, LX_EPI_BIAS, p.mod_cond_single,
+                       m.mod_single.n, 0, stream));
+    LX_TRY(gemm_simple(m.x_embedder, lora_w(m.x_embedder), cond_latents, m.in_channels, g.Rc, LX_EPI_BIAS, p.X0_cond, D, 0,
+                       stream));
   }
   // context_embedder(prompt_embeds)
-  LX_TRY(gemm_simple(m.context_embedder, prompt_embeds, m.joint_dim, g.Rt, false, LX_EPI_BIAS, p.X0_txt, D, 0, stream));
-  return LX_OK;
-}
-
-static int embed_inputs(const lx_dit_model_t& m, const lx_dit_plan_t& p, const void* latents, void* stream) {
-  const Geo g = geo(m, p);
-  const int D = g.D, C = m.in_channels;
-  const int64_t ldxe = C + 64;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LX_CUDA(cudaMemcpy2DAsync(p.XE, ldxe * 2, latents, C * 2, C * 2, g.Ri, cudaMemcpyDeviceToDevice, st));
-  lx_lora_down_desc_t l;
-  memset(&l, 0, sizeof(l));
-  l.x = p.XE; l.ldx = ldxe; l.rows = g.Ri; l.K = C; l.ext = 64; l.lora_r = m.x_embedder.lora_r;
-  l.lora_a = m.x_embedder.lora_a; l.tile_meta = nullptr; l.lora_stream_mask = p.latent_lora ? 4 : 0;
-  LX_TRY(lx_lora_down(&l, stream));
-  LX_TRY(gemm_simple(m.x_embedder, p.XE, ldxe, g.Ri, m.x_embedder.ext > 0, LX_EPI_BIAS, off(p.X, (int64_t)g.Rt * D), D, 0,
-                     stream));
-  LX_CUDA(cudaMemcpyAsync(p.X, p.X0_txt, (size_t)g.Rt * D * 2, cudaMemcpyDeviceToDevice, st));
-  if (g.nc > 0)
-    LX_CUDA(cudaMemcpyAsync(off(p.X, (int64_t)(g.Rt + g.Ri) * D), p.X0_cond, (size_t)g.Rc * D * 2,
-                            cudaMemcpyDeviceToDevice, st));
+  LX_TRY(gemm_simple(m.context_embedder, m.context_embedder.w, prompt_embeds, m.joint_dim, g.Rt, LX_EPI_BIAS, p.X0_txt, D,
+                     0, stream));
   return LX_OK;
 }
 
@@ -413,13 +341,13 @@ extern "C" int lx_dit_step(const lx_dit_model_t* model, const lx_dit_plan_t* pla
   {
     lx_lnmod_desc_t d;
     memset(&d, 0, sizeof(d));
-    d.x = off(p.X, (int64_t)g.Rt * D); d.ldx = D; d.out = p.XN; d.ldo = D + 64; d.rows = g.Ri; d.D = D;
+    d.x = off(p.X, (int64_t)g.Rt * D); d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.Ri; d.D = D;
     d.tile_meta = p.tile_meta + g.Rt / 128; d.eps = 1e-6f;
     const void* mo = off(p.mod_out, (int64_t)step * g.B * 2 * D);
     for (int s = 0; s < 3; ++s) { d.scale[s] = mo; d.shift[s] = off(mo, D); d.stride[s] = 2 * D; }
     LX_TRY(lx_ln_modulate(&d, stream));
   }
-  return gemm_simple(m.proj_out, p.XN, D + 64, g.Ri, false, LX_EPI_BIAS, noise_pred, m.proj_out.n, 0, stream);
+  return gemm_simple(m.proj_out, m.proj_out.w, p.XN, D, g.Ri, LX_EPI_BIAS, noise_pred, m.proj_out.n, 0, stream);
 }
 
 extern "C" int lx_dit_double_block(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, int32_t block,

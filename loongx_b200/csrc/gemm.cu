@@ -13,18 +13,32 @@
 
 namespace lx {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
+constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// N tile variants: 256 is the default; 224 / 192 exist to cut wave-quantisation loss (e.g. M=2560, N=3072 is
+// 240 tiles = 1.62 waves of 148 CTAs at BN=256 but 280 tiles = 1.89 waves of *smaller* tiles at BN=224).
+template <int BN>
+struct TileCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 5;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 
 struct GemmParams {
   lx_gemm_desc_t d;
-  int tiles_m, tiles_n, num_kb;
+  int tiles_m, tiles_n;
+  int num_kb[3];
+  int tile_begin[3];  // first M tile of group g (unused groups: tiles_m)
 };
+
+__device__ __forceinline__ int group_of(const GemmParams& p, int tm) {
+  return (tm >= p.tile_begin[1] ? 1 : 0) + (tm >= p.tile_begin[2] ? 1 : 0);
+}
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
   uint4 u;
@@ -53,9 +67,13 @@ __device__ __forceinline__ void chunk_bias(const uint32_t (&r)[32], const float*
   }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ GemmParams p) {
+  constexpr int STAGES = TileCfg<BN>::STAGES;
+  constexpr int STAGE_BYTES = TileCfg<BN>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -71,7 +89,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmB0);
+    if (p.d.n_groups > 1) prefetch_tmap(&tmB1);
+    if (p.d.n_groups > 2) prefetch_tmap(&tmB2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -99,14 +119,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.tiles_m) * BM;
+        const int tm = tile % p.tiles_m;
+        const int m0 = tm * BM;
         const int n0 = (tile / p.tiles_m) * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int g = group_of(p, tm);
+        const CUtensorMap* tmB = g == 0 ? &tmB0 : (g == 1 ? &tmB1 : &tmB2);
+        const int nkb = p.num_kb[g];
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-          tma_load_2d(sa + A_BYTES, &tmB, &full[stage], kb * BK, n0);
+          tma_load_2d(sa + A_BYTES, tmB, &full[stage], kb * BK, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -126,8 +150,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        const int nkb = p.num_kb[group_of(p, tile % p.tiles_m)];
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -168,12 +193,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const lx_gemm_segment_t& seg = d.seg[si];
       const int seg_n0 = si ? d.n_split : 0;
       const int mode = seg.mode;
+      const float* bias = d.group[group_of(p, tm)].bias;
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      if (mode == LX_EPI_QKV) {
+      if (BN == 256 && mode == LX_EPI_QKV) {
         const lx_tile_meta_t meta = d.tile_meta[tm];
         const int D = d.heads * 128;
         const int sec = n0 / D;  // 0 = q, 1 = k, 2 = v
@@ -196,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t r[32];
               float x[32];
               tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
-                  chunk_bias(r, d.bias, nh + c * 32, x);
+                  chunk_bias(r, bias, nh + c * 32, x);
 #pragma unroll
               for (int j = 0; j < 32; ++j) ss += x[j] * x[j];
             }
@@ -207,7 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t r[32];
             float x[32];
             tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
-              chunk_bias(r, d.bias, nh + c * 32, x);
+              chunk_bias(r, bias, nh + c * 32, x);
             if (rmsw != nullptr) {
               const float4* w4 = reinterpret_cast<const float4*>(rmsw + c * 32);
 #pragma unroll
@@ -249,7 +275,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           float x[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
-          chunk_bias(r, d.bias, n, x);
+          chunk_bias(r, bias, n, x);
           const int oc = n - seg_n0 + seg.col_offset;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -281,7 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           float x[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
-          chunk_bias(r, d.bias, n, x);
+          chunk_bias(r, bias, n, x);
           if (mode == LX_EPI_BIAS_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
@@ -325,20 +351,82 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 }  // namespace lx
 
+namespace lx {
+
+template <int BN>
+int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
+  CUtensorMap tmA, tmB[3];
+  GemmParams p;
+  p.d = d;
+  p.tiles_m = (d.M + BM - 1) / BM;
+  p.tiles_n = (d.N + BN - 1) / BN;
+  int kmax = 0;
+  for (int g = 0; g < 3; ++g) {
+    const int gi = g < d.n_groups ? g : 0;
+    p.num_kb[g] = (d.group[gi].K + BK - 1) / BK;
+    p.tile_begin[g] = g < d.n_groups ? d.group[g].m_begin / BM : p.tiles_m;
+    kmax = max(kmax, d.group[gi].K);
+    int rc = make_tmap_2d_bf16(&tmB[g], d.group[gi].W, (uint64_t)d.N, (uint64_t)d.group[gi].K,
+                               (uint64_t)d.group[gi].ldw, BN, BK);
+    if (rc) return rc;
+  }
+  int rc = make_tmap_2d_bf16(&tmA, d.A, (uint64_t)d.M, (uint64_t)kmax, (uint64_t)d.lda, BM, BK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  const int grid = min(p.tiles_m * p.tiles_n, num_sms());
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB[0], tmB[1],
+                                                                                                    tmB[2], p);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+// N tile that minimises (number of waves) x (tile width); ties go to the wider tile.
+int pick_tile_n(int M, int N, bool need_256) {
+  if (need_256) return 256;
+  const int sms = num_sms();
+  const int tiles_m = (M + BM - 1) / BM;
+  int best = 256;
+  long best_cost = -1;
+  for (int bn : {256, 224, 192}) {
+    const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
+    const long cost = ((tiles + sms - 1) / sms) * bn;
+    if (best_cost < 0 || cost < best_cost) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
+}  // namespace lx
+
 extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
   using namespace lx;
   LX_CHECK_ARG(desc != nullptr, "lx_gemm_bf16: null descriptor");
   const lx_gemm_desc_t& d = *desc;
-  LX_CHECK_ARG(d.M > 0 && d.N > 0 && d.K > 0, "lx_gemm_bf16: bad shape M=%d N=%d K=%d", d.M, d.N, d.K);
-  LX_CHECK_ARG(d.N % 8 == 0 && d.K % 8 == 0, "lx_gemm_bf16: N and K must be multiples of 8 (N=%d K=%d)", d.N, d.K);
-  LX_CHECK_ARG(d.A && d.W, "lx_gemm_bf16: null operand");
-  LX_CHECK_ARG(d.n_split > 0 && (d.n_split == d.N || d.n_split % BN == 0) && d.n_split <= d.N,
-               "lx_gemm_bf16: n_split=%d must be N or a multiple of %d", d.n_split, BN);
+  LX_CHECK_ARG(d.M > 0 && d.N > 0 && d.N % 8 == 0, "lx_gemm_bf16: bad shape M=%d N=%d", d.M, d.N);
+  LX_CHECK_ARG(d.A != nullptr, "lx_gemm_bf16: null A");
+  LX_CHECK_ARG(d.n_groups >= 1 && d.n_groups <= 3, "lx_gemm_bf16: n_groups=%d outside [1,3]", d.n_groups);
+  for (int g = 0; g < d.n_groups; ++g) {
+    const lx_gemm_group_t& G = d.group[g];
+    LX_CHECK_ARG(G.W != nullptr && G.K > 0 && G.K % 8 == 0, "lx_gemm_bf16: group %d needs W and K (multiple of 8), K=%d", g,
+                 G.K);
+    LX_CHECK_ARG(G.m_begin % 128 == 0 && (g == 0 ? G.m_begin == 0 : G.m_begin >= d.group[g - 1].m_begin),
+                 "lx_gemm_bf16: group %d m_begin=%d must be an ascending multiple of 128 (group 0 at 0)", g, G.m_begin);
+  }
+  LX_CHECK_ARG(d.n_split > 0 && (d.n_split == d.N || d.n_split % 256 == 0) && d.n_split <= d.N,
+               "lx_gemm_bf16: n_split=%d must be N or a multiple of 256", d.n_split);
   const int nseg = d.n_split < d.N ? 2 : 1;
+  bool need_256 = nseg == 2;
   for (int s = 0; s < nseg; ++s) {
     const lx_gemm_segment_t& g = d.seg[s];
     LX_CHECK_ARG(g.mode >= LX_EPI_BIAS && g.mode <= LX_EPI_BIAS_F32, "lx_gemm_bf16: bad epilogue mode %d", g.mode);
     if (g.mode == LX_EPI_QKV) {
+      need_256 = true;
       LX_CHECK_ARG(s == 0, "lx_gemm_bf16: QKV segment must be segment 0");
       LX_CHECK_ARG(d.q && d.k && d.v && d.heads > 0 && d.seq_total > 0 && d.tile_meta,
                    "lx_gemm_bf16: QKV epilogue needs q/k/v, heads, seq_total, tile_meta");
@@ -354,25 +442,10 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
       LX_CHECK_ARG(d.residual && d.tile_meta && d.ldr % 8 == 0, "lx_gemm_bf16: GATE_RESIDUAL needs residual, tile_meta");
     }
   }
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d_bf16(&tmA, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, BM, BK);
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmB, d.W, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldw, BN, BK);
-  if (rc) return rc;
-
-  GemmParams p;
-  p.d = d;
-  p.tiles_m = (d.M + BM - 1) / BM;
-  p.tiles_n = (d.N + BN - 1) / BN;
-  p.num_kb = (d.K + BK - 1) / BK;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
-  }
-  const int grid = min(p.tiles_m * p.tiles_n, num_sms());
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
-  LX_CUDA(cudaGetLastError());
-  return LX_OK;
+  int bn = d.tile_n;
+  if (bn == 0) bn = pick_tile_n(d.M, d.N, need_256);
+  LX_CHECK_ARG(bn == 256 || ((bn == 224 || bn == 192) && !need_256), "lx_gemm_bf16: tile_n=%d not allowed here", bn);
+  if (bn == 256) return launch_gemm<256>(d, stream);
+  if (bn == 224) return launch_gemm<224>(d, stream);
+  return launch_gemm<192>(d, stream);
 }

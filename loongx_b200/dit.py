@@ -1,8 +1,9 @@
-"""Host side of the native DiT engine: weight packing (diffusers-named tensors -> fused, K-extended bf16 panels),
-plan / workspace allocation through torch, and thin calls into lx_dit_prepare / lx_dit_step.
+"""Host side of the native DiT engine: weight packing (diffusers-named tensors -> fused bf16 panels), plan / workspace
+allocation through torch, and thin calls into lx_dit_prepare / lx_dit_step.
 
 No arithmetic of the hot path happens here — only one-time layout work at load (concatenating q/k/v(/proj_mlp)
-weights, appending LoRA-B columns, stacking the AdaLN linears) and pointer plumbing per call.
+weights, merging W + (alpha/r) B A for the LoRA-active row group, stacking the AdaLN linears) and pointer plumbing per
+call.
 """
 from __future__ import annotations
 
@@ -23,8 +24,8 @@ c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_floa
 # ctypes mirrors of include/loongx_b200.h
 # ---------------------------------------------------------------------------------------------------------------
 class LxLinear(C.Structure):
-    _fields_ = [("w", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("lora_a", c_void_p),
-                ("n", c_int32), ("k", c_int32), ("ext", c_int32), ("lora_r", c_int32)]
+    _fields_ = [("w", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("w_lora", c_void_p),
+                ("n", c_int32), ("k", c_int32)]
 
 
 class LxDoubleBlock(C.Structure):
@@ -55,7 +56,7 @@ class LxDitPlan(C.Structure):
                 ("cross_bias", c_float), ("reserved", c_int32),
                 ("tile_meta", c_void_p), ("out_row_base", c_void_p), ("rope", c_void_p),
                 ("X", c_void_p), ("XN", c_void_p), ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p),
-                ("scratch", c_void_p), ("XE", c_void_p), ("X0_txt", c_void_p), ("X0_cond", c_void_p),
+                ("scratch", c_void_p), ("X0_txt", c_void_p), ("X0_cond", c_void_p),
                 ("emb_tmp", c_void_p), ("sin_tmp", c_void_p), ("silu_t", c_void_p), ("silu_c", c_void_p),
                 ("mod_img", c_void_p), ("mod_txt", c_void_p), ("mod_single", c_void_p), ("mod_out", c_void_p),
                 ("mod_cond_img", c_void_p), ("mod_cond_single", c_void_p),
@@ -107,59 +108,45 @@ def random_params(cfg: FluxConfig, device, seed: int = 1234, w_std: float = 0.02
 class PackedLinear:
     """One (possibly fused / stacked) Linear in the native layout; keeps the tensors alive."""
 
-    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], lora_a: Optional[torch.Tensor], k: int, ext: int,
-                 lora_r: int):
-        self.w, self.bias, self.lora_a, self.k, self.ext, self.lora_r = w, bias, lora_a, k, ext, lora_r
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], w_lora: Optional[torch.Tensor]):
+        self.w, self.bias, self.w_lora = w, bias, w_lora
 
     def c(self) -> LxLinear:
         s = LxLinear()
         s.w, s.ldw = self.w.data_ptr(), self.w.stride(0)
         s.bias = self.bias.data_ptr() if self.bias is not None else None
-        s.lora_a = self.lora_a.data_ptr() if self.lora_a is not None else None
-        s.n, s.k, s.ext, s.lora_r = self.w.shape[0], self.k, self.ext, self.lora_r
+        s.w_lora = self.w_lora.data_ptr() if self.w_lora is not None else None
+        s.n, s.k = self.w.shape
         return s
 
 
-def pack_linear(P: Dict[str, torch.Tensor], names: Sequence[str], cfg: FluxConfig, device, *, per_block_lora=False,
+def pack_linear(P: Dict[str, torch.Tensor], names: Sequence[str], cfg: FluxConfig, device, *,
                 pop: bool = False) -> PackedLinear:
-    """Stack the Linear layers `names` along the output dimension.  If any of them carries LoRA factors the weight is
-    K-extended: columns [k, k+ext) hold lora_B * (alpha / r) — layer i in columns [r*i, r*i+r), or, with
-    per_block_lora (stacked AdaLN linears evaluated one block at a time), always in columns [0, r)."""
+    """Stack the Linear layers `names` along the output dimension (q|k|v(|proj_mlp), all blocks' AdaLN linears, ...).
+    If any of them carries LoRA factors, also build the merged panel W + (alpha/r) lora_B lora_A (fp32 sum, one bf16
+    rounding) that the LoRA-active row group of the GEMM reads (peft LoRA Linear)."""
     get = (lambda key: P.pop(key)) if pop else (lambda key: P[key])
-    ws = [get(n + ".weight").to(device=device, dtype=torch.bfloat16) for n in names]
-    k = ws[0].shape[1]
-    n_total = sum(w.shape[0] for w in ws)
+    has_lora = any((n + ".lora_A.weight") in P for n in names)
     has_bias = (names[0] + ".bias") in P
+    ws, merged = [], []
+    for n in names:
+        lora = (n + ".lora_A.weight") in P
+        w = get(n + ".weight").to(device=device, dtype=torch.bfloat16)
+        ws.append(w)
+        if has_lora:
+            if lora:
+                a = get(n + ".lora_A.weight").to(device=device, dtype=torch.float32)
+                b = get(n + ".lora_B.weight").to(device=device, dtype=torch.float32)
+                scaling = cfg.lora_alpha / a.shape[0]
+                merged.append(torch.addmm(w.float(), b, a, alpha=scaling).to(torch.bfloat16))
+            else:
+                merged.append(w)
     bias = torch.cat([get(n + ".bias").to(device=device, dtype=torch.float32) for n in names]) if has_bias else None
-    lora_idx = [i for i, n in enumerate(names) if (n + ".lora_A.weight") in P]
-    if not lora_idx:
-        w = torch.cat(ws, 0).contiguous() if len(ws) > 1 else ws[0].contiguous()
-        return PackedLinear(w, bias, None, k, 0, 0)
-    r = P[names[lora_idx[0]] + ".lora_A.weight"].shape[0]
-    scaling = cfg.lora_alpha / r
-    r_cols = r if per_block_lora else r * len(lora_idx)
-    assert r_cols <= 16 or per_block_lora, "at most 16 LoRA rows per fused operand"
-    ext = 64
-    w = torch.zeros((n_total, k + ext), device=device, dtype=torch.bfloat16)
-    a_rows: List[torch.Tensor] = []
-    row = 0
-    slot = 0
-    for i, (n, wi) in enumerate(zip(names, ws)):
-        o = wi.shape[0]
-        w[row:row + o, :k] = wi
-        if i in lora_idx:
-            a = get(n + ".lora_A.weight").to(device=device, dtype=torch.bfloat16)
-            b = get(n + ".lora_B.weight").to(device=device, dtype=torch.float32) * scaling
-            c0 = 0 if per_block_lora else slot * r
-            w[row:row + o, k + c0:k + c0 + r] = b.to(torch.bfloat16)
-            a_rows.append(a)
-            slot += 1
-        elif per_block_lora:
-            raise ValueError("per_block_lora needs LoRA on every stacked layer")
-        row += o
-    del ws
-    lora_a = torch.cat(a_rows, 0).contiguous()
-    return PackedLinear(w, bias, lora_a, k, ext, r if per_block_lora else r * len(lora_idx))
+    w = torch.cat(ws, 0).contiguous() if len(ws) > 1 else ws[0].contiguous()
+    w_lora = None
+    if has_lora:
+        w_lora = torch.cat(merged, 0).contiguous() if len(merged) > 1 else merged[0].contiguous()
+    return PackedLinear(w, bias, w_lora)
 
 
 class DitWeights:
@@ -194,12 +181,9 @@ class DitWeights:
             put("guid_2", pk(["time_text_embed.guidance_embedder.linear_2"]))
         put("text_1", pk(["time_text_embed.text_embedder.linear_1"]))
         put("text_2", pk(["time_text_embed.text_embedder.linear_2"]))
-        has_lora = "transformer_blocks.0.norm1.linear.lora_A.weight" in P if cfg.num_layers else False
-        put("mod_img", pk([f"transformer_blocks.{i}.norm1.linear" for i in range(cfg.num_layers)], per_block_lora=has_lora))
+        put("mod_img", pk([f"transformer_blocks.{i}.norm1.linear" for i in range(cfg.num_layers)]))
         put("mod_txt", pk([f"transformer_blocks.{i}.norm1_context.linear" for i in range(cfg.num_layers)]))
-        has_lora_s = "single_transformer_blocks.0.norm.linear.lora_A.weight" in P if cfg.num_single_layers else False
-        put("mod_single", pk([f"single_transformer_blocks.{i}.norm.linear" for i in range(cfg.num_single_layers)],
-                             per_block_lora=has_lora_s))
+        put("mod_single", pk([f"single_transformer_blocks.{i}.norm.linear" for i in range(cfg.num_single_layers)]))
         put("norm_out", pk(["norm_out.linear"]))
         put("proj_out", pk(["proj_out"]))
 
@@ -243,7 +227,7 @@ class DitWeights:
         tot = 0
         for k in self.keep:
             if isinstance(k, PackedLinear):
-                tot += k.w.numel() * 2
+                tot += k.w.numel() * 2 + (k.w_lora.numel() * 2 if k.w_lora is not None else 0)
         return tot
 
 
@@ -284,16 +268,15 @@ class DitPlan:
             out_row_base=ops.make_out_row_base(B, n_txt, n_img, n_cond, dev),
             rope=torch.zeros((S, 64, 2), device=dev, dtype=torch.float32),
             X=torch.zeros((R, D), **bf),
-            XN=torch.zeros((R, D + 64), **bf),
+            XN=torch.zeros((R, D), **bf),
             Q=torch.zeros((B, H, S, 128), **bf), K=torch.zeros((B, H, S, 128), **bf), V=torch.zeros((B, H, S, 128), **bf),
-            scratch=torch.zeros((R, 5 * D + 64), **bf),
-            XE=torch.zeros((B * max(n_img, n_cond), cfg.in_channels + 64), **bf),
+            scratch=torch.zeros((R, 5 * D), **bf),
             X0_txt=torch.zeros((B * n_txt, D), **bf),
             X0_cond=torch.zeros((max(B * n_cond, 1), D), **bf),
             emb_tmp=torch.zeros((4, M, D), **bf),
             sin_tmp=torch.zeros((M, 256), **bf),
-            silu_t=torch.zeros((T * B, D + 64), **bf),
-            silu_c=torch.zeros((B, D + 64), **bf),
+            silu_t=torch.zeros((T * B, D), **bf),
+            silu_c=torch.zeros((B, D), **bf),
             mod_img=torch.zeros((T * B, max(L_, 1) * 6 * D), **bf),
             mod_txt=torch.zeros((T * B, max(L_, 1) * 6 * D), **bf),
             mod_single=torch.zeros((T * B, max(Ls, 1) * 3 * D), **bf),

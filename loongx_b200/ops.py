@@ -50,6 +50,7 @@ def gemm(
     col_offset: int = 0,
     n_split: Optional[int] = None,
     seg1: Optional[tuple] = None,  # (mode, out, col_offset)
+    groups: Optional[Sequence[tuple]] = None,  # extra row groups: (W, bias, m_begin)
     tile_meta: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
     gate: Optional[Sequence[Optional[torch.Tensor]]] = None,  # per stream [B, *] views (row = batch)
@@ -58,19 +59,25 @@ def gemm(
     rms_k: Optional[Sequence[Optional[torch.Tensor]]] = None,
     rope: Optional[torch.Tensor] = None,
     rms_eps: float = 1e-6,
+    tile_n: int = 0,
 ) -> None:
-    """C = epilogue(A[M,K] @ W[N,K]^T); A / W are 2-D bf16 views with unit inner stride."""
+    """C = epilogue(A[M,K] @ W[N,K]^T); A / W are 2-D bf16 views with unit inner stride.  `groups` adds row groups
+    (rows >= m_begin use that weight panel / bias instead)."""
     assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
     assert A.stride(1) == 1 and W.stride(1) == 1
     d = L.GemmDesc()
     d.A, d.lda = _ptr(A), A.stride(0)
-    d.W, d.ldw = _ptr(W), W.stride(0)
-    d.bias = _ptr(bias)
-    if bias is not None:
-        assert bias.dtype == torch.float32
     d.M, d.N = A.shape[0], W.shape[0]
-    d.K = K if K is not None else A.shape[1]
-    assert W.shape[1] >= d.K and A.shape[1] >= d.K
+    kk = K if K is not None else A.shape[1]
+    assert W.shape[1] >= kk and A.shape[1] >= kk
+    panels = [(W, bias, 0)] + list(groups or [])
+    d.n_groups = len(panels)
+    for i, (w_i, b_i, m_i) in enumerate(panels):
+        assert w_i.dtype == torch.bfloat16 and w_i.stride(1) == 1 and w_i.shape[0] == d.N
+        if b_i is not None:
+            assert b_i.dtype == torch.float32
+        d.group[i].W, d.group[i].ldw, d.group[i].bias = _ptr(w_i), w_i.stride(0), _ptr(b_i)
+        d.group[i].K, d.group[i].m_begin = kk, m_i
     d.n_split = n_split if n_split is not None else d.N
     d.seg[0].mode = mode
     d.seg[0].col_offset = col_offset
@@ -101,6 +108,7 @@ def gemm(
                 d.rms_k[i] = _ptr(rms_k[i])
         d.rope = _ptr(rope)
     d.rms_eps = rms_eps
+    d.tile_n = tile_n
     L.check(L.lib.lx_gemm_bf16(C.byref(d), _stream()), "lx_gemm_bf16")
 
 

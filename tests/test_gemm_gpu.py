@@ -40,6 +40,37 @@ def test_gemm_bias(M, N, K):
     _close(out, ref, what=f"bias {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("tile_n", [256, 224, 192])
+def test_gemm_tile_variants(tile_n):
+    """Every N-tile variant of the kernel (wave-quantisation tuning) gives the same answer, incl. ragged M/N/K."""
+    from loongx_b200 import ops, _lib as L
+
+    for (M, N, K) in [(384, 3072, 320), (200, 456, 136)]:
+        A, W = _mk((M, K), 1.0, 41), _mk((N, K), 0.05, 42)
+        bias = _mk((N,), 1.0, 43, torch.float32)
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(A, W, bias, out, L.EPI_BIAS_GELU, tile_n=tile_n)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.gelu(A.float() @ W.float().t() + bias, approximate="tanh")
+        _close(out, ref, what=f"tile_n={tile_n} {M}x{N}x{K}")
+
+
+def test_gemm_row_groups():
+    """Three row groups (text / image / condition rows) with their own weight panel and bias in one launch."""
+    from loongx_b200 import ops, _lib as L
+
+    M, N, K = 640, 512, 256
+    A = _mk((M, K), 1.0, 50)
+    Ws = [_mk((N, K), 0.05, 51 + i) for i in range(3)]
+    bs = [_mk((N,), 1.0, 54 + i, torch.float32) for i in range(3)]
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, Ws[0], bs[0], out, L.EPI_BIAS, groups=[(Ws[1], bs[1], 128), (Ws[2], bs[2], 384)])
+    torch.cuda.synchronize()
+    ref = torch.cat([A[:128].float() @ Ws[0].float().t() + bs[0], A[128:384].float() @ Ws[1].float().t() + bs[1],
+                     A[384:].float() @ Ws[2].float().t() + bs[2]])
+    _close(out, ref, what="row groups")
+
+
 def test_gemm_strided_ext_and_f32():
     """A / W with row stride > K (the LoRA K-extension layout) and an fp32 output segment."""
     from loongx_b200 import ops, _lib as L
