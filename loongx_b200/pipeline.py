@@ -1,0 +1,223 @@
+"""Pipeline / transformer host objects with the attribute surface the reference's `generate()` and `OminiModel`
+consume from diffusers' FluxPipeline / FluxTransformer2DModel ("pipeline object consumed by generate()").
+
+They own the packed native weights and cached plans; every tensor operation they perform is either a native kernel or
+pure layout plumbing (views / copies).  Text encoders and the VAE are out of scope for this build:
+prompt embeddings and latents come in pre-computed, `output_type="latent"` is the supported output.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .config import FluxConfig
+from .dit import DitPlan, DitWeights, pack_latents, random_params, unpack_latents
+from .sampler import FlowMatchEulerDiscreteScheduler, latent_image_ids
+
+
+class _Cfg(dict):
+    """dict with attribute access (diffusers FrozenDict-like)."""
+
+    __getattr__ = dict.__getitem__
+
+
+class _AttnHandle:
+    """Stand-in for a diffusers `Attention` module: generate() only sets / deletes `.c_factor` on it
+    (generate.py:90-94, 385-389) and attn_forward() reads it (block.py:121-128)."""
+
+    def __init__(self, heads: int):
+        self.heads = heads
+
+
+class _BlockHandle:
+    def __init__(self, transformer: "NativeFluxTransformer", index: int, single: bool):
+        self.transformer, self.index, self.single = transformer, index, single
+        self.attn = _AttnHandle(transformer.cfg.num_attention_heads)
+
+
+class NativeFluxTransformer:
+    """FluxTransformer2DModel-shaped owner of the native DiT weights."""
+
+    def __init__(self, cfg: FluxConfig, params: Optional[Dict[str, torch.Tensor]] = None, device="cuda", seed: int = 1234,
+                 consume_params: bool = False):
+        cfg.validate()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.dtype = torch.bfloat16
+        if params is None:
+            params = random_params(cfg, self.device, seed=seed)
+            consume_params = True
+        self.weights = DitWeights(params, cfg, self.device, consume=consume_params)
+        self.config = _Cfg(in_channels=cfg.in_channels, guidance_embeds=cfg.guidance_embeds,
+                           num_layers=cfg.num_layers, num_single_layers=cfg.num_single_layers,
+                           attention_head_dim=cfg.attention_head_dim, num_attention_heads=cfg.num_attention_heads,
+                           joint_attention_dim=cfg.joint_attention_dim, pooled_projection_dim=cfg.pooled_projection_dim,
+                           axes_dims_rope=cfg.axes_dims_rope)
+        self.training = False
+        self.gradient_checkpointing = False
+        self.transformer_blocks = [_BlockHandle(self, i, False) for i in range(cfg.num_layers)]
+        self.single_transformer_blocks = [_BlockHandle(self, i, True) for i in range(cfg.num_single_layers)]
+        self._plans: Dict[tuple, DitPlan] = {}
+
+    # -- nn.Module-like surface --------------------------------------------------------------------------------
+    def named_modules(self):
+        yield "", self
+        for i, b in enumerate(self.transformer_blocks):
+            yield f"transformer_blocks.{i}", b
+            yield f"transformer_blocks.{i}.attn", b.attn
+        for i, b in enumerate(self.single_transformer_blocks):
+            yield f"single_transformer_blocks.{i}", b
+            yield f"single_transformer_blocks.{i}.attn", b.attn
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def c_factor(self) -> Optional[float]:
+        """The value generate() installed on every `*.attn` (None when condition_scale == 1)."""
+        for b in self.transformer_blocks + self.single_transformer_blocks:
+            cf = getattr(b.attn, "c_factor", None)
+            if cf is not None:
+                return float(cf.reshape(-1)[0]) if isinstance(cf, torch.Tensor) else float(cf)
+        return None
+
+    # -- plans -------------------------------------------------------------------------------------------------
+    def plan(self, B: int, n_txt: int, n_img: int, n_cond: int, T: int, model_config: Optional[dict],
+             c_factor: Optional[float]) -> DitPlan:
+        mc = model_config or {}
+        key = (B, n_txt, n_img, n_cond, T, bool(mc.get("latent_lora", False)), bool(mc.get("union_cond_attn", True)),
+               bool(mc.get("independent_condition", False)), bool(mc.get("add_cond_attn", False)), c_factor)
+        pl = self._plans.get(key)
+        if pl is None:
+            if len(self._plans) >= 4:  # bounded cache: plans own large activation buffers
+                self._plans.pop(next(iter(self._plans)))
+            pl = DitPlan(self.weights, B, n_txt, n_img, n_cond, T=T, model_config=mc, c_factor=c_factor)
+            self._plans[key] = pl
+        return pl
+
+
+class _Scheduler(FlowMatchEulerDiscreteScheduler):
+    pass
+
+
+class NativeFluxPipeline:
+    """FluxPipeline-shaped object for generate() (attribute list in SURVEY.md §8b)."""
+
+    def __init__(self, transformer: NativeFluxTransformer, scheduler: Optional[FlowMatchEulerDiscreteScheduler] = None):
+        self.transformer = transformer
+        self.scheduler = scheduler or _Scheduler()
+        self.vae = None
+        self.text_encoder = None
+        self.text_encoder_2 = None
+        self.image_processor = None
+        self.vae_scale_factor = 16  # diffusers 0.31.0
+        self.default_sample_size = 64
+        self._guidance_scale = 3.5
+        self._joint_attention_kwargs = None
+        self._interrupt = False
+        self._num_timesteps = 0
+
+    # properties generate() reads
+    @property
+    def device(self):
+        return self.transformer.device
+
+    @property
+    def dtype(self):
+        return self.transformer.dtype
+
+    @property
+    def _execution_device(self):
+        return self.transformer.device
+
+    @property
+    def joint_attention_kwargs(self):
+        return self._joint_attention_kwargs
+
+    @property
+    def interrupt(self):
+        return self._interrupt
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    # FluxPipeline methods generate() calls
+    def check_inputs(self, prompt, prompt_2, height, width, prompt_embeds=None, pooled_prompt_embeds=None,
+                     callback_on_step_end_tensor_inputs=None, max_sequence_length=None):
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`.")
+        if prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`.")
+        if prompt_embeds is not None and pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if max_sequence_length is not None and max_sequence_length > 512:
+            raise ValueError(f"`max_sequence_length` cannot be greater than 512 but is {max_sequence_length}")
+
+    def encode_prompt(self, prompt=None, prompt_2=None, device=None, num_images_per_prompt: int = 1, prompt_embeds=None,
+                      pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None):
+        if prompt_embeds is None:
+            raise NotImplementedError(
+                "text encoders (T5-XXL / CLIP-L) are outside this build's scope (SURVEY.md §8f.4): pass prompt_embeds "
+                "and pooled_prompt_embeds")
+        device = device or self._execution_device
+        pe = prompt_embeds.to(device=device, dtype=self.dtype)
+        po = pooled_prompt_embeds.to(device=device, dtype=self.dtype)
+        if num_images_per_prompt != 1:
+            pe = pe.repeat_interleave(num_images_per_prompt, dim=0)
+            po = po.repeat_interleave(num_images_per_prompt, dim=0)
+        text_ids = torch.zeros(pe.shape[1], 3, device=device, dtype=self.dtype)
+        return pe, po, text_ids
+
+    @staticmethod
+    def _prepare_latent_image_ids(batch_size, height, width, device, dtype):
+        return torch.from_numpy(latent_image_ids(height // 2, width // 2)).to(device=device, dtype=dtype)
+
+    @staticmethod
+    def _pack_latents(latents, batch_size=None, num_channels_latents=None, height=None, width=None):
+        return pack_latents(latents.contiguous())
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor):
+        return unpack_latents(latents.contiguous(), height, width, vae_scale_factor)
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        height = 2 * (int(height) // self.vae_scale_factor)
+        width = 2 * (int(width) // self.vae_scale_factor)
+        shape = (batch_size, num_channels_latents, height, width)
+        ids = self._prepare_latent_image_ids(batch_size, height, width, device, dtype)
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype), ids
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}.")
+        gen = generator[0] if isinstance(generator, list) else generator
+        gen_dev = gen.device if gen is not None else torch.device(device)
+        noise = torch.randn(shape, generator=gen, device=gen_dev, dtype=dtype).to(device)  # diffusers randn_tensor
+        return self._pack_latents(noise), ids
+
+    def set_adapters(self, *args, **kwargs):  # LoRA adapters are merged into the cond row group at load
+        return None
+
+    @contextlib.contextmanager
+    def progress_bar(self, total=None):
+        class _Bar:
+            def update(self, n=1):
+                pass
+
+        yield _Bar()
+
+    def maybe_free_model_hooks(self):
+        return None
+
+
+class FluxPipelineOutput:
+    def __init__(self, images):
+        self.images = images

@@ -1,0 +1,81 @@
+"""Drop-in for the reference's src/flux/condition.py (Condition, condition_dict; condition.py:10-138).
+
+Image pre-processing (canny / depth / blur, condition.py:53-90) and the VAE are outside this build; a Condition is
+constructed from already-encoded latents ([B, 16, h, w]) or packed tokens ([B, N, 64]).  The position arithmetic on the
+ids (condition.py:126-137) is kept operation for operation so the resulting ids are bit-identical.
+"""
+from typing import Tuple, Union
+
+import torch
+
+from .pipeline_tools import encode_images
+
+condition_dict = {
+    "depth": 0,
+    "canny": 1,
+    "subject": 4,
+    "coloring": 6,
+    "deblurring": 7,
+    "depth_pred": 8,
+    "fill": 9,
+    "sr": 10,
+    "cartoon": 11,
+    "eeg+fnirs": 12,
+}
+
+_IMAGE_TYPES = ("depth", "canny", "subject", "coloring", "deblurring", "depth_pred", "fill", "sr", "cartoon")
+
+
+class Condition(object):
+    def __init__(self, condition_type: str, raw_img=None, condition=None, mask=None, position_delta=None,
+                 position_scale=1.0, eeg=None, fnirs=None, ppg=None, motion=None) -> None:
+        self.condition_type = condition_type
+        assert raw_img is not None or condition is not None
+        if raw_img is not None:
+            self.condition = self.get_condition(condition_type, raw_img)
+        else:
+            self.condition = condition
+        self.position_delta = position_delta
+        self.position_scale = position_scale
+        self.eeg, self.fnirs, self.ppg, self.motion = eeg, fnirs, ppg, motion
+        assert mask is None, "Mask not supported yet"
+
+    def get_condition(self, condition_type: str, raw_img):
+        if isinstance(raw_img, torch.Tensor):
+            return raw_img
+        raise NotImplementedError("PIL / OpenCV condition pre-processing is outside this build; pass encoded latents")
+
+    @property
+    def type_id(self) -> int:
+        return condition_dict[self.condition_type]
+
+    @classmethod
+    def get_type_id(cls, condition_type: str) -> int:
+        return condition_dict[condition_type]
+
+    def encode(self, pipe) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> (tokens [B, N, 64], ids [N, 3], type_id [N, 1])."""
+        if self.condition_type not in _IMAGE_TYPES:
+            raise NotImplementedError(f"Condition type {self.condition_type} not implemented")
+        c = self.condition
+        if isinstance(c, torch.Tensor) and c.dim() == 3:  # packed tokens of a square latent grid
+            tokens = c.to(pipe.device).to(pipe.dtype)
+            side = int(round(tokens.shape[1] ** 0.5))
+            assert side * side == tokens.shape[1], "packed condition tokens must come from a square latent grid"
+            ids = pipe._prepare_latent_image_ids(tokens.shape[0], 2 * side, 2 * side, pipe.device, pipe.dtype)
+        else:
+            tokens, ids = encode_images(pipe, c)
+        if self.position_delta is None and self.condition_type == "subject":
+            width_px = c.size[0] if hasattr(c, "size") and not isinstance(c, torch.Tensor) else 16 * int(round(tokens.shape[1] ** 0.5))
+            self.position_delta = [0, -width_px // 16]
+        if self.position_delta is not None:
+            ids[:, 1] += self.position_delta[0]
+            ids[:, 2] += self.position_delta[1]
+        if self.position_scale != 1.0:
+            scale_bias = (self.position_scale - 1.0) / 2
+            ids[:, 1] *= self.position_scale
+            ids[:, 2] *= self.position_scale
+            ids[:, 1] += scale_bias
+            ids[:, 2] += scale_bias
+        type_id = torch.ones_like(ids[:, :1]) * self.type_id
+        return tokens, ids, type_id

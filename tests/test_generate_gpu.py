@@ -1,0 +1,169 @@
+"""End-to-end GPU parity through the reference-facing API: src.flux.generate.generate / tranformer_forward /
+Condition / OminiModel against the oracle's restated pipeline (oracle/sampler.py + oracle/cs3_dgf.py + oracle/flux_dit.py).
+
+Stated tolerance: after the full denoise loop relL2(native, oracle_fp32) <= 5e-2; indices bit-exact.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H_PX, W_PX = 256, 128  # -> latent 32 x 16 -> 128 image tokens
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def _build(seed=0, layers=(1, 2)):
+    from oracle import flux_dit as O
+    from oracle import cs3_dgf as OC
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.pipeline import NativeFluxPipeline, NativeFluxTransformer
+    from src.train.model import OminiModel
+
+    kw = dict(num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=2)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=1234, w_std=0.03, bias_std=0.03, lora_b_std=0.03)
+    Pb = {k: v.to(torch.bfloat16).cuda() for k, v in P.items()}
+    P32 = {k: v.float() for k, v in Pb.items()}
+    torch.manual_seed(seed)
+    cond = OC.NeuralConditioner().eval()
+    model = OminiModel(cfg, lora_config={"r": 4, "lora_alpha": 4}, device="cuda", model_config={})
+    model.load_state_dict(cond.state_dict(), strict=True)
+    model.transformer = NativeFluxTransformer(cfg, params=Pb, device="cuda")
+    model.flux_pipe = NativeFluxPipeline(model.transformer)
+    return O, ocfg, P32, cond.cuda(), model
+
+
+def _inputs(B=1, seed=42):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g, device="cuda")  # noqa: E731
+    return dict(
+        latents=r(B, 16, 32, 16).bfloat16(), cond=r(B, 16, 32, 16).bfloat16(),
+        pe=(r(B, 512, 4096) * 0.1).bfloat16(), pooled=r(B, 768).bfloat16(),
+        eeg=r(B, 4, 5000), fnirs=r(B, 6, 600), ppg=r(B, 4, 256), motion=r(B, 6, 100),
+    )
+
+
+def test_generate_neural_replace_vs_oracle():
+    """EEG+PPG -> prompt_embeds, fNIRS+Motion -> pooled (fuse_flag=False), image condition with position_delta, 4 steps."""
+    from oracle import sampler as OS
+    from src.flux.condition import Condition
+    from src.flux.generate import generate
+
+    O, ocfg, P32, cond, model = _build()
+    x = _inputs(B=2)
+    pipe = model.flux_pipe
+    packed0 = OS.pack_latents(x["latents"])
+    c = Condition("subject", condition=x["cond"], position_delta=[0, -8])
+    out = generate(model, pipe, conditions=[c], prompt_embeds=x["pe"], pooled_prompt_embeds=x["pooled"], height=H_PX,
+                   width=W_PX, num_inference_steps=4, latents=packed0.clone(), output_type="latent", default_lora=True,
+                   additional_condition1=x["eeg"], additional_condition2=x["fnirs"], additional_condition3=x["ppg"],
+                   additional_condition4=x["motion"], use_brain_condition=True, fuse_flag=False)
+    got = out.images
+    torch.cuda.synchronize()
+    assert got.shape == (2, 128, 64) and got.dtype == torch.bfloat16
+
+    with torch.no_grad():
+        pe, po = cond.conditioning(x["pe"], x["pooled"], x["eeg"], x["fnirs"], x["ppg"], x["motion"], fuse_flag=False)
+    img_ids = OS.prepare_latent_image_ids(32, 16).cuda()
+    cids = OS.condition_ids(img_ids, [0, -8])
+    ref = OS.denoise(P32, ocfg, packed0.float(), pe.float(), po.float(), torch.zeros(512, 3).cuda(), img_ids,
+                     OS.pack_latents(x["cond"]).float(), cids, num_inference_steps=4)
+    e = _rel(got, ref)
+    print(f"\n[generate replace] relL2 after 4 steps: {e:.4g}")
+    assert torch.isfinite(got.float()).all() and e <= 5e-2
+    assert pipe._num_timesteps == 4 and pipe._guidance_scale == 3.5
+
+
+def test_generate_fuse_flag_and_text_only_and_callbacks():
+    from oracle import sampler as OS
+    from src.flux.condition import Condition
+    from src.flux.generate import generate
+
+    O, ocfg, P32, cond, model = _build(seed=1)
+    x = _inputs(B=1, seed=7)
+    pipe = model.flux_pipe
+    packed0 = OS.pack_latents(x["latents"])
+    img_ids = OS.prepare_latent_image_ids(32, 16).cuda()
+    kw = dict(prompt_embeds=x["pe"], pooled_prompt_embeds=x["pooled"], height=H_PX, width=W_PX, num_inference_steps=3,
+              output_type="latent", default_lora=True)
+    # fuse_flag=True (generate.py:240-255)
+    seen = []
+    got = generate(model, pipe, conditions=[Condition("subject", condition=x["cond"], position_delta=[0, -8])],
+                   latents=packed0.clone(), additional_condition1=x["eeg"][0], additional_condition2=x["fnirs"][0],
+                   additional_condition3=x["ppg"][0], additional_condition4=x["motion"][0], fuse_flag=True,
+                   callback_on_step_end=lambda p, i, t, kws: (seen.append(i), {})[1], return_dict=False, **kw)[0]
+    with torch.no_grad():
+        pe, po = cond.conditioning(x["pe"], x["pooled"], x["eeg"], x["fnirs"], x["ppg"], x["motion"], fuse_flag=True,
+                                   mode="generate")
+    ref = OS.denoise(P32, ocfg, packed0.float(), pe.float(), po.float(), torch.zeros(512, 3).cuda(), img_ids,
+                     OS.pack_latents(x["cond"]).float(), OS.condition_ids(img_ids, [0, -8]), num_inference_steps=3)
+    e = _rel(got, ref)
+    print(f"\n[generate fuse] relL2 {e:.4g}")
+    assert e <= 5e-2 and seen == [0, 1, 2]
+    # text-only, no image condition, condition_scale path installs / removes c_factor
+    got2 = generate(model, pipe, conditions=None, latents=packed0.clone(), use_brain_condition=False, **kw).images
+    ref2 = OS.denoise(P32, ocfg, packed0.float(), x["pe"].float(), x["pooled"].float(), torch.zeros(512, 3).cuda(),
+                      img_ids, None, None, num_inference_steps=3)
+    assert _rel(got2, ref2) <= 5e-2
+    got3 = generate(model, pipe, conditions=[Condition("subject", condition=x["cond"], position_delta=[0, -8])],
+                    latents=packed0.clone(), use_brain_condition=False, condition_scale=1.5, **kw).images
+    ref3 = OS.denoise(P32, ocfg, packed0.float(), x["pe"].float(), x["pooled"].float(), torch.zeros(512, 3).cuda(),
+                      img_ids, OS.pack_latents(x["cond"]).float(), OS.condition_ids(img_ids, [0, -8]),
+                      num_inference_steps=3, c_factor=1.5)
+    assert _rel(got3, ref3) <= 5e-2
+    assert all(not hasattr(m, "c_factor") for n, m in pipe.transformer.named_modules() if n.endswith(".attn"))
+    # EEG-only is a no-op in the literal reference (D5) ...
+    got4 = generate(model, pipe, conditions=None, latents=packed0.clone(), additional_condition1=x["eeg"][0], **kw).images
+    assert torch.equal(got4, got2)
+    # ... and replaces prompt_embeds only with the documented opt-in
+    got5 = generate(model, pipe, conditions=None, latents=packed0.clone(), additional_condition1=x["eeg"][0],
+                    eeg_only_replace=True, **kw).images
+    assert not torch.equal(got5, got2)
+    with pytest.raises(AssertionError):
+        cnd = Condition("subject", condition=x["cond"])
+        generate(model, pipe, conditions=[cnd, cnd], latents=packed0.clone(), use_brain_condition=False, **kw)
+    with pytest.raises(NotImplementedError):
+        generate(model, pipe, conditions=None, latents=packed0.clone(), use_brain_condition=False,
+                 **{**kw, "output_type": "pil"})
+
+
+def test_tranformer_forward_shim_and_ids_bit_exact():
+    from oracle import flux_dit as OD
+    from oracle import sampler as OS
+    from src.flux.condition import Condition
+    from src.flux.transformer import tranformer_forward
+
+    O, ocfg, P32, cond, model = _build(seed=2)
+    x = _inputs(B=2, seed=3)
+    pipe = model.flux_pipe
+    tokens, ids, type_id = Condition("subject", condition=x["cond"], position_delta=[0, -8], position_scale=2.0).encode(pipe)
+    ref_ids = OS.condition_ids(OS.prepare_latent_image_ids(32, 16, torch.bfloat16).cuda(), [0, -8], 2.0)
+    assert torch.equal(ids, ref_ids) and torch.equal(tokens, OS.pack_latents(x["cond"]))
+    assert type_id.shape == (128, 1) and int(type_id[0]) == 4
+    lat = OS.pack_latents(x["latents"])
+    img_ids = pipe._prepare_latent_image_ids(2, 32, 16, "cuda", torch.bfloat16)
+    assert torch.equal(img_ids, OS.prepare_latent_image_ids(32, 16, torch.bfloat16).cuda())
+    t = torch.tensor([0.8, 0.3], device="cuda")
+    gd = torch.tensor([3.5, 3.5], device="cuda")
+    out = tranformer_forward(model.transformer, tokens, ids, type_id, model_config={}, c_t=0, hidden_states=lat,
+                             encoder_hidden_states=x["pe"], pooled_projections=x["pooled"], timestep=t, guidance=gd,
+                             img_ids=img_ids, txt_ids=torch.zeros(512, 3, device="cuda"), joint_attention_kwargs=None,
+                             return_dict=False)[0]
+    ref = OD.tranformer_forward(P32, ocfg, tokens.float(), ids.float(), None, {}, 0, hidden_states=lat.float(),
+                                encoder_hidden_states=x["pe"].float(), pooled_projections=x["pooled"].float(), timestep=t,
+                                img_ids=img_ids.float(), txt_ids=torch.zeros(512, 3).cuda(), guidance=gd)
+    e = _rel(out, ref)
+    print(f"\n[tranformer_forward shim] relL2 {e:.4g}")
+    assert e <= 2e-2
+    o2 = tranformer_forward(model.transformer, tokens, ids, type_id, hidden_states=lat, encoder_hidden_states=x["pe"],
+                            pooled_projections=x["pooled"], timestep=t, guidance=gd, img_ids=img_ids,
+                            txt_ids=torch.zeros(512, 3, device="cuda"))
+    assert torch.equal(o2.sample, out)
+    # latent noise from a generator: same numbers as torch.randn + the oracle pack
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    packed, _ = pipe.prepare_latents(2, 16, H_PX, W_PX, torch.bfloat16, "cuda", gen, None)
+    gen2 = torch.Generator(device="cuda").manual_seed(42)
+    assert torch.equal(packed, OS.pack_latents(torch.randn((2, 16, 32, 16), generator=gen2, device="cuda", dtype=torch.bfloat16)))
