@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the LoongX denoising hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            native arm (one process per GPU; N>1 via torchrun)
+  python bench.py --impl reference --steps K --warmup W    reference arm: the oracle port of the reference's PyTorch
+                                                            path on the host cores (the reference itself cannot be
+                                                            imported here: diffusers/peft/s4torch are not installed)
+
+A "step" is ONE EDIT of the per-GPU batch: neural conditioning (CS3, once) + 28 denoise steps of the Flux MM-DiT at
+512x512 with an image condition (S = 512 + 1024 + 1024 tokens) — BASELINE.json configs[1].  metric = edits/sec.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "512x512 28-step edits/sec"
+DENOISE_STEPS = 28
+RES = 512
+N_TXT = 512
+
+
+def flops_per_forward(n_txt, n_img, n_cond, D=3072, blocks=57):
+    """BASELINE.md §3 / SURVEY.md §8d algorithmic FLOPs of one DiT forward of one sample."""
+    S = n_txt + n_img + n_cond
+    return blocks * (24 * D * D * S + 4 * S * S * D) + 2 * 64 * D * (n_img + n_cond) + 2 * 4096 * D * n_txt + 2 * D * 64 * n_img + 10.8e9
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1424.9), hbm=d.get("hbm_gbs", 6445.6), which="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, which="fallback (B200_PROFILING.md: ~1.4 PF sustained, 6.65 TB/s)")
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: oracle port on the host cores, bounded sample
+# --------------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """One double-stream + one single-stream block forward (fp32, full FLUX width, B=1, S=2560) of the oracle; an edit
+    is 28 x (19 double + 38 single) of these (the embedders / final layer are < 0.1 % of the FLOPs)."""
+
+    def __init__(self):
+        from oracle import flux_dit as O
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.O = O
+        self.cfg = O.FluxConfig(num_layers=1, num_single_layers=1)
+        self.P = O.init_params(self.cfg, seed=1234, dtype=torch.float32)
+        g = torch.Generator().manual_seed(42)
+        n = (RES // 16) ** 2
+        D = self.cfg.inner_dim
+        self.h = torch.randn(1, n, D, generator=g)
+        self.e = torch.randn(1, N_TXT, D, generator=g)
+        self.c = torch.randn(1, n, D, generator=g)
+        self.temb = torch.randn(1, D, generator=g)
+        side = RES // 16
+        ids = torch.zeros(side, side, 3)
+        ids[..., 1] += torch.arange(side)[:, None]
+        ids[..., 2] += torch.arange(side)[None, :]
+        ids = ids.reshape(-1, 3)
+        cids = ids.clone()
+        cids[:, 2] -= side
+        self.rope = O.rope_tables(torch.cat([torch.zeros(N_TXT, 3), ids], 0))
+        self.crope = O.rope_tables(cids)
+        self.cores = torch.get_num_threads()
+        self.sample = ("oracle port (reference block.py restated in PyTorch fp32), 1 double-stream + 1 single-stream block "
+                       "forward at FLUX width, B=1, S=2560; extrapolated x28 steps x(19 double + 38 single) blocks")
+
+    @torch.no_grad()
+    def run(self):
+        """-> (seconds for the double block, seconds for the single block)."""
+        O, P, cfg = self.O, self.P, self.cfg
+        t0 = time.perf_counter()
+        e, h, c = O.block_forward(P, cfg, 0, self.h, self.e, self.c, self.temb, self.temb, self.crope, self.rope, {})
+        t1 = time.perf_counter()
+        x = torch.cat([e, h], 1)
+        t2 = time.perf_counter()
+        O.single_block_forward(P, cfg, 0, x, self.temb, self.rope, c, self.temb, self.crope, {})
+        t3 = time.perf_counter()
+        return t1 - t0, t3 - t2
+
+    @staticmethod
+    def edit_seconds(td, ts):
+        return DENOISE_STEPS * (19 * td + 38 * ts)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    s = CpuSample()
+    for _ in range(args.warmup):
+        s.run()
+    t0 = time.perf_counter()
+    tds, tss = [], []
+    for _ in range(args.steps):
+        td, ts = s.run()
+        tds.append(td)
+        tss.append(ts)
+    wall = time.perf_counter() - t0
+    td, ts = sum(tds) / len(tds), sum(tss) / len(tss)
+    edit_s = s.edit_seconds(td, ts)
+    val = 1.0 / edit_s
+    flop = 2 * 660.4e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "edits/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, args.gpus),
+        "cpu_baseline": {"value": val, "unit": "edits/s", "cores": s.cores, "kind": "port", "sample": s.sample,
+                         "sample_tflops": flop / (td + ts) / 1e12, "s_per_edit_extrapolated": edit_s},
+        "e2e": {"value": val, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference repo cannot be imported on this image (diffusers/peft/s4torch absent): this arm times the "
+                "oracle restatement of its PyTorch path on the host cores; each step is the bounded sample described in "
+                "cpu_baseline.sample",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch_per_gpu, n_gpus):
+    return {"workload": "BASELINE.json configs[1]: 512x512 edit, 28 denoise steps, EEG-only CS3 conditioning "
+                        "(eeg_only_replace), image condition (S=512+1024+1024), guidance 3.5",
+            "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus, "denoise_steps": DENOISE_STEPS,
+            "parallelism": f"dp{n_gpus} (edits sharded by batch, no data-path collective)",
+            "l2": "every denoise step streams ~40 GB of weights (>> 126 MB L2): inputs larger than L2, no explicit flush"}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_native(args, rank, local_rank, world):
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from loongx_b200 import _lib as L
+    from src.flux.condition import Condition
+    from src.flux.generate import generate
+    from src.train.model import OminiModel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = OminiModel("synthetic", lora_config={"r": 4, "lora_alpha": 4}, device=str(dev), model_config={
+        "union_cond_attn": True, "add_cond_attn": False, "latent_lora": False})
+    pipe = model.flux_pipe
+    side = RES // 8  # latent 64 x 64
+
+    def mk(seed, *shape, scale=1.0, dtype=torch.bfloat16, pin=False):
+        g = torch.Generator().manual_seed(seed + 1000 * rank)
+        t = (torch.randn(*shape, generator=g) * scale).to(dtype)
+        return t.pin_memory() if pin else t
+
+    host = dict(latents=mk(42, B, 16, side, side, pin=True), cond=mk(43, B, 16, side, side, pin=True),
+                pe=mk(44, B, N_TXT, 4096, scale=0.1, pin=True), pooled=mk(44, B, 768, pin=True),
+                eeg=mk(45, B, 4, 5000, dtype=torch.float32, pin=True))
+    devt = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = torch.empty((B, (side // 2) ** 2, 64), dtype=torch.bfloat16).pin_memory()
+    d2h = out_host.numel() * 2
+
+    def edit(t):
+        cnd = Condition("subject", condition=t["cond"], position_delta=[0, -(RES // 16)])
+        return generate(model, pipe, conditions=[cnd], prompt_embeds=t["pe"], pooled_prompt_embeds=t["pooled"],
+                        height=RES, width=RES, num_inference_steps=DENOISE_STEPS, latents=pipe._pack_latents(t["latents"]),
+                        output_type="latent", default_lora=True, additional_condition1=t["eeg"], use_brain_condition=True,
+                        fuse_flag=False, eeg_only_replace=True).images
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        out = edit(devt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "non-finite latents"
+
+    # ---- timed region: K edits, inputs resident in HBM
+    clocks = ClockSampler(local_rank)
+    barrier()
+    L.lib.lx_launch_count_reset()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        edit(devt)
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    launches = int(L.lib.lx_launch_count(-1))
+    secs = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    value = world * B * args.steps / secs
+
+    # ---- end to end through generate() with HOST buffers: H2D of every input + D2H of the result inside the timing
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out_host.copy_(edit(t), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_secs = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * B * args.steps / e2e_secs
+
+    # ---- per-kernel-class CUDA-event timing of one more edit (events recorded on the launching stream in the C ABI)
+    L.lib.lx_profile_begin()
+    edit(devt)
+    ms = (C.c_double * 4)()
+    cnt = (C.c_int64 * 4)()
+    work = (C.c_double * 4)()
+    L.check(L.lib.lx_profile_end(ms, cnt, work), "lx_profile_end")
+    peaks = load_peaks()
+    names = ["gemm_bf16_kernel", "attention_kernel", "dit_row_kernels", "cs3_dgf_kernels"]
+    tot_ms = sum(ms) or 1.0
+    gemm_tf = work[0] / ms[0] / 1e9 if ms[0] else 0.0
+    att_tf = work[1] / ms[1] / 1e9 if ms[1] else 0.0
+    row_gbs = work[2] / ms[2] / 1e6 if ms[2] else 0.0
+    roofline = {"bound": "tensor", "kernel": "lx::gemm_bf16_kernel (tcgen05 GEMM + fused epilogues)", "achieved": gemm_tf,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tflops"], "traffic": None,
+                "peak_source": peaks["which"], "launches_per_edit": int(cnt[0]), "avg_launch_us": ms[0] / max(cnt[0], 1) * 1e3,
+                "share_of_edit": ms[0] / tot_ms,
+                "method": "CUDA events around every launch of one extra edit, on the launching stream (lx_profile_*)"}
+    kernels = {names[i]: {"ms_per_edit": ms[i], "launches": int(cnt[i]), "share": ms[i] / tot_ms} for i in range(4)}
+    kernels["attention_kernel"].update({"achieved_tflops": att_tf, "frac_of_peak": att_tf / peaks["tflops"]})
+    kernels["dit_row_kernels"].update({"achieved_gbs": row_gbs, "frac_of_hbm_peak": row_gbs / peaks["hbm"]})
+    n_img = (RES // 16) ** 2
+    algo_tflops = B * DENOISE_STEPS * flops_per_forward(N_TXT, n_img, n_img) / (secs / args.steps) / 1e12
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s = CpuSample()
+        s.run()
+        reps = []
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 12.0 or len(reps) < 2:
+            reps.append(s.run())
+        td, ts = sum(r[0] for r in reps) / len(reps), sum(r[1] for r in reps) / len(reps)
+        cpu = {"value": 1.0 / s.edit_seconds(td, ts), "unit": "edits/s", "cores": s.cores, "kind": "port",
+               "sample": s.sample + f" ({len(reps)} repetitions, {time.perf_counter() - t0:.1f} s)",
+               "s_per_edit_extrapolated": s.edit_seconds(td, ts)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "edits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(B, world),
+            "e2e": {"value": e2e_value, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "src.flux.generate.generate(model, pipe, ...) with pinned host inputs, result copied to host"},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
+            "algorithmic_tflops_per_gpu": algo_tflops, "frac_of_peak_end_to_end": algo_tflops / peaks["tflops"],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="edits per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    run_native(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

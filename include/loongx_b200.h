@@ -25,6 +25,15 @@ int lx_version(void);
 /* Device properties the host layer needs for grid sizing: out[0]=SM count, out[1]=cc major, out[2]=cc minor. */
 int lx_device_info(int32_t* out3);
 
+/* Launch accounting (bench.py's gpu_launches / roofline): kernel classes 0 = tcgen05 GEMM, 1 = attention, 2 = DiT row
+ * kernels, 3 = CS3/DGF kernels; cls < 0 = all.  lx_profile_begin() switches on CUDA-event timing of every launch (on
+ * the stream it is launched on); lx_profile_end() synchronises and returns per-class totals in arrays of 4:
+ * milliseconds, launches, algorithmic work (FLOPs for classes 0-1, bytes for class 2, 0 for class 3). */
+int64_t lx_launch_count(int32_t cls);
+void lx_launch_count_reset(void);
+int lx_profile_begin(void);
+int lx_profile_end(double* ms, int64_t* launches, double* work);
+
 /* ------------------------------------------------------------------------------------------------------
  * Row-tile metadata.  Activations are stored stream-major: rows = [txt(B*Nt) | img(B*Ni) | cond(B*Nc)],
  * every stream length a multiple of 128, so each 128-row tile belongs to one (stream, batch element).

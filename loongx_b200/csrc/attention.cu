@@ -291,6 +291,13 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     attr_set = true;
   }
   dim3 grid(d.S / 128, d.H, d.B);
+  double pairs = (double)d.S * d.S;  // visible (query, key) pairs per head
+  if (d.cross_bias == 0.f && d.n_cond > 0) {
+    const double nc = d.n_cond, nr = d.S - d.n_cond;
+    if (d.mask_mode == 1) pairs = nc * nc + nr * nr;
+    if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
+  }
+  LaunchScope scope(KC_ATTENTION, stream, 4.0 * d.B * d.H * pairs * 128.0);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   LX_CUDA(cudaGetLastError());
   return LX_OK;

@@ -190,6 +190,7 @@ extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.x && d.out && d.tile_meta, "lx_ln_modulate: null pointer");
   LX_CHECK_ARG(d.ldx % 8 == 0 && d.ldo % 8 == 0 && d.ldo >= d.D && d.ldx >= d.D, "lx_ln_modulate: bad strides");
   const int grid = (d.rows + ROW_WARPS - 1) / ROW_WARPS;
+  LaunchScope scope(KC_ROW, stream, 4.0 * d.rows * d.D);  // bytes: read + write bf16 rows
   ln_modulate_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(d);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -197,6 +198,7 @@ extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
 
 extern "C" int lx_timestep_embed(const float* t, void* out, int64_t ldo, int32_t M, float mult, void* stream) {
   LX_CHECK_ARG(t && out && M > 0 && ldo >= 256, "lx_timestep_embed: bad arguments");
+  LaunchScope scope(KC_ROW, stream, 512.0 * M);
   timestep_embed_kernel<<<M, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, reinterpret_cast<__nv_bfloat16*>(out), ldo,
                                                                          M, mult);
   LX_CUDA(cudaGetLastError());
@@ -208,6 +210,7 @@ extern "C" int lx_add_silu_bcast(const void* a, const void* b, const void* c, in
   LX_CHECK_ARG(a && out && M > 0 && D > 0 && D % 8 == 0 && ldo % 8 == 0 && ldo >= D, "lx_add_silu_bcast: bad arguments");
   LX_CHECK_ARG(c == nullptr || c_rows > 0, "lx_add_silu_bcast: c_rows must be positive");
   const int n = M * (D / 8);
+  LaunchScope scope(KC_ROW, stream, 8.0 * M * D);
   add_silu_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
       reinterpret_cast<const __nv_bfloat16*>(c), c_rows, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, D);
@@ -219,6 +222,7 @@ extern "C" int lx_euler_step(const void* x, const void* v, void* out, float dt, 
   LX_CHECK_ARG(x && v && out && n > 0 && n % 8 == 0, "lx_euler_step: n=%lld must be a positive multiple of 8",
                (long long)n);
   const int64_t n8 = n / 8;
+  LaunchScope scope(KC_ROW, stream, 6.0 * n);
   euler_step_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(v),
       reinterpret_cast<__nv_bfloat16*>(out), dt, n8);
@@ -231,6 +235,7 @@ extern "C" int lx_rope_table(const float* ids, float* table, int32_t S, int32_t 
   LX_CHECK_ARG(ids && table && S > 0, "lx_rope_table: bad arguments");
   LX_CHECK_ARG(d0 + d1 + d2 == 128 && d0 % 2 == 0 && d1 % 2 == 0 && d2 % 2 == 0,
                "lx_rope_table: axes dims must be even and sum to 128");
+  LaunchScope scope(KC_ROW, stream, 512.0 * S);
   rope_table_kernel<<<S, 64, 0, static_cast<cudaStream_t>(stream)>>>(ids, table, S, d0, d1, d2, theta);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -243,6 +248,7 @@ extern "C" int lx_pack_latents(const void* in, void* out, int32_t B, int32_t C, 
   const int64_t n = (int64_t)B * C * h * w;
   const unsigned grid = (unsigned)((n + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchScope scope(KC_ROW, stream, 2.0 * n * elem_bytes);
   if (elem_bytes == 2) {
     if (unpack) unpack_latents_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, B, C, h, w);
     else pack_latents_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, B, C, h, w);

@@ -378,6 +378,12 @@ int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
     attr_set = true;
   }
   const int grid = min(p.tiles_m * p.tiles_n, num_sms());
+  double flops = 0;
+  for (int g = 0; g < d.n_groups; ++g) {
+    const int m_end = g + 1 < d.n_groups ? d.group[g + 1].m_begin : d.M;
+    flops += 2.0 * (m_end - d.group[g].m_begin) * (double)d.N * d.group[g].K;
+  }
+  LaunchScope scope(KC_GEMM, stream, flops);
   gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB[0], tmB[1],
                                                                                                     tmB[2], p);
   LX_CUDA(cudaGetLastError());

@@ -1,6 +1,7 @@
 #include "host_util.cuh"
 
 #include <mutex>
+#include <vector>
 #include <string.h>
 
 namespace lx {
@@ -91,9 +92,70 @@ int num_sms() {
   return n;
 }
 
+// ------------------------------------------------------------------------------------------- launch accounting
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int cls;
+  double work;
+};
+static long long g_launches[KC_COUNT] = {0, 0, 0, 0};
+static bool g_profiling = false;
+static std::vector<ProfRec> g_recs;
+
+LaunchScope::LaunchScope(int cls, void* stream, double work) : slot_(-1), stream_(stream) {
+  g_launches[cls]++;
+  if (!g_profiling) return;
+  ProfRec r;
+  r.cls = cls;
+  r.work = work;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, static_cast<cudaStream_t>(stream));
+  g_recs.push_back(r);
+  slot_ = (int)g_recs.size() - 1;
+}
+LaunchScope::~LaunchScope() {
+  if (slot_ >= 0) cudaEventRecord(g_recs[slot_].e1, static_cast<cudaStream_t>(stream_));
+}
+
 }  // namespace lx
 
 extern "C" {
+
+int64_t lx_launch_count(int32_t cls) {
+  if (cls < 0) {
+    long long t = 0;
+    for (int i = 0; i < lx::KC_COUNT; ++i) t += lx::g_launches[i];
+    return t;
+  }
+  return cls < lx::KC_COUNT ? lx::g_launches[cls] : 0;
+}
+void lx_launch_count_reset(void) {
+  for (int i = 0; i < lx::KC_COUNT; ++i) lx::g_launches[i] = 0;
+}
+int lx_profile_begin(void) {
+  lx::g_recs.clear();
+  lx::g_profiling = true;
+  return LX_OK;
+}
+// Synchronises the device, then fills per-class totals: ms[c], launches[c], work[c] (arrays of 4).
+int lx_profile_end(double* ms, int64_t* launches, double* work) {
+  lx::g_profiling = false;
+  LX_CHECK_ARG(ms && launches && work, "lx_profile_end: null output");
+  LX_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < lx::KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; work[i] = 0; }
+  for (auto& r : lx::g_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      ms[r.cls] += t;
+      launches[r.cls] += 1;
+      work[r.cls] += r.work;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  lx::g_recs.clear();
+  return LX_OK;
+}
 
 const char* lx_last_error(void) { return lx::g_err; }
 int lx_version(void) { return 100; }

@@ -40,4 +40,14 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64
 
 int num_sms();
 
+// Launch accounting + optional per-kernel-class CUDA-event timing (bench.py's roofline numbers): every extern "C"
+// launcher opens a LaunchScope; with profiling off it only bumps a counter.
+enum KernelClass { KC_GEMM = 0, KC_ATTENTION = 1, KC_ROW = 2, KC_CS3DGF = 3, KC_COUNT = 4 };
+struct LaunchScope {
+  LaunchScope(int cls, void* stream, double work);  // work: FLOPs (tensor kernels) or bytes (HBM-bound kernels)
+  ~LaunchScope();
+  int slot_;
+  void* stream_;
+};
+
 }  // namespace lx
