@@ -1,0 +1,53 @@
+"""world_size-2 gloo test of the multi-GPU host logic: edits are sharded by the reference's rule (inference.py:126-128),
+there is no data-path collective, timing is the max over ranks, and the aggregate is units / max time (bench.py)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from loongx_b200.sampler import shard_range
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s, e = shard_range(n_items, rank, world)
+    mine = torch.zeros(n_items, dtype=torch.int64)
+    mine[s:e] = 1  # "process" my shard; no exchange of edit data between ranks
+    elapsed = torch.tensor([0.25 * (rank + 1)], dtype=torch.float64)  # pretend per-rank device time
+    dist.barrier()
+    dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    cover = mine.clone()
+    dist.all_reduce(cover, op=dist.ReduceOp.SUM)  # test-only check that shards tile the work exactly once
+    if rank == 0:
+        q.put((cover.tolist(), float(elapsed.item()), n_items / float(elapsed.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [7, 8])
+def test_two_rank_sharding_and_max_timing(n_items):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    cover, t_max, agg = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert cover == [1] * n_items
+    assert t_max == 0.5 and agg == n_items / 0.5
