@@ -1,0 +1,25 @@
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from loongx_b200 import ops, _lib as L
+B,H,nt,ni,nc=1,24,512,1024,1024
+S=nt+ni+nc
+g=torch.Generator(device="cuda").manual_seed(1)
+q,k,v=[torch.randn((B,H,S,128),generator=g,device="cuda").bfloat16() for _ in range(3)]
+out=torch.empty((B*S,H*128),device="cuda",dtype=torch.bfloat16)
+orb=ops.make_out_row_base(B,nt,ni,nc,"cuda")
+for _ in range(3): ops.attention(q,k,v,out,orb,n_cond=nc)
+dbg=torch.zeros(20*8,dtype=torch.int64,device="cuda")
+L.lib.lx_attention_debug_timeline.argtypes=[C.c_void_p]
+L.lib.lx_attention_debug_timeline(dbg.data_ptr())
+ops.attention(q,k,v,out,orb,n_cond=nc)
+torch.cuda.synchronize()
+L.lib.lx_attention_debug_timeline(None)
+t=dbg.cpu().view(20,8)
+t0=t[0,0].item()
+names=["loop","s_full","tmem_ld","max+xchg","exp","pv_wait+resc","P_st","fence+arrive"]
+print("iter  start   "+"  ".join(f"{n:>12s}" for n in names[1:]))
+for i in range(20):
+    row=t[i].tolist()
+    d=[row[j]-row[j-1] for j in range(1,8)]
+    print(f"{i:3d} {row[0]-t0:8d}  "+"  ".join(f"{x:12d}" for x in d)+f"   total {row[7]-row[0]}")
