@@ -1,23 +1,27 @@
 // Joint [txt | img | cond] non-causal attention for sm_100a (head_dim 128), FlashAttention-style online softmax with
-// both GEMMs on tcgen05 tensor cores and the running output accumulator resident in TMEM.
+// both GEMMs on tcgen05 tensor cores and S, P and the running output accumulator all resident in TMEM.
 //
-//   one CTA = one 128-row query tile of one (batch, head)
-//   warp 0      : TMA producer (Q once; K/V tiles through a 2-stage mbarrier ring, 128-byte swizzle)
-//   warp 1      : tcgen05.mma issuer:  S_j = Q K_j^T  (TMEM, double buffered)  and  O += P_j V_j  (TMEM)
-//   warps 2..9  : softmax, TWO threads per query row (each owns 64 of the 128 key columns of the tile, tcgen05.ld
-//                 32x32b; the two halves exchange their row max through shared memory + one named barrier);
-//                 exp2 (single MUFU) with the 1/sqrt(d)·log2(e) scale folded in, lazy rescale of O (only when the
-//                 running max grows by > 8 in log2 units), P_j written to shared memory as the bf16 A operand of the
-//                 second GEMM.  The MUFU pipe (16 exp2/clk/SM = 1024 clk per 128x128 tile) then matches the tensor pipe
-//                 (2 x 512 clk per tile) instead of trailing it by 3x.
-//
-// The issue order on the tensor pipe is S_0, [S_1, PV_0], [S_2, PV_1], ... so softmax(j) overlaps PV(j-1) and S(j+1).
+//   one CTA = TWO 128-row query tiles (A, B) of one (batch, head), ping-ponged on the tensor pipe
+//   warp 0      : TMA producer (both Q tiles once; K and V tiles through 2-stage mbarrier rings, 128-byte swizzle)
+//   warp 1      : tcgen05.mma issuer.  Issue order  S_A0 S_B0 | PV_A0 S_A1 PV_B0 S_B1 | PV_A1 S_A2 PV_B1 S_B2 | ...
+//                 S_g = Q_g K_j^T   (SS form, TMEM columns [128g, 128g+128))
+//                 O_g += P_g V_j    (TS form: the bf16 probabilities are read from TMEM, where the softmax threads
+//                                    packed them in place over the first 64 columns of S_g; V is the MN-major smem operand)
+//   warps 2..9  : softmax of tile A, TWO threads per query row (each owns 64 of the tile's 128 key columns, tcgen05.ld
+//                 32x32b; the halves exchange their row max through shared memory + one named barrier per tile)
+//   warps 10..17: softmax of tile B
+//                 exp2 (single MUFU.EX2) with the 1/sqrt(d)·log2(e) scale folded into one FFMA, lazy rescale of O (only
+//                 when the running max grows by more than 8 in log2 units), P never touches shared memory.
+//   While one tile's rows are in the MUFU-bound softmax (16 exp2/clk/SM = 1024 clk per 128x128 tile) the tensor pipe
+//   runs the other tile's PV + next QK^T (2 x 512 clk), so the two pipes overlap instead of alternating.
+//   A launch whose tile counts are odd (tiny test shapes) runs with one query tile per CTA (group B idle).
 //
 // Replaces F.scaled_dot_product_attention + the q/k/v concat + head transpose at block.py:70-72,102-104,129-135,
 // including the optional block masks (block.py:106-120) and the log(c_factor) bias (block.py:121-128), which are
 // uniform per 128x128 tile because every stream length is a multiple of 128.
 #include "host_util.cuh"
 #include "ptx.cuh"
+#include "tmem_wide.cuh"
 
 namespace lx {
 
@@ -25,15 +29,15 @@ constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_D = 128;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KiB: two 128x64 swizzle atoms
 constexpr int ATT_ATOM_BYTES = 128 * 64 * 2;   // 16 KiB
 constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps
-constexpr int ATT_SOFTMAX_THREADS = 256;
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES + 1) + 1024 + 256 + 2 * 2 * 128 * 4;
+constexpr int ATT_THREADS = 576;  // TMA warp + MMA warp + 2 query tiles x 8 softmax warps
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
 
 struct AttnParams {
   long long* dbg;  // optional timeline buffer (development aid, NULL in production)
   lx_attn_desc_t d;
   float scale_log2;  // scale * log2(e)
   float bias_log2;   // cross_bias * log2(e)
+  int groups;        // query tiles per CTA (2, or 1 when the tile counts are odd)
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -41,32 +45,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;                    // [stages]
+  uint8_t* sQ = smem;                                   // [2 groups]
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // [stages]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;    // [stages]
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + ATT_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_TILE_BYTES);
   uint64_t* q_full = bars;          // 1
   uint64_t* k_full = bars + 1;      // [2]
   uint64_t* v_full = bars + 3;      // [2]
-  uint64_t* k_empty = bars + 5;     // [2] released by the commit after QK^T(it): K loads run a full iteration ahead
-  uint64_t* v_empty = bars + 14;    // [2] released by the commit after PV(it)
-  uint64_t* s_full = bars + 7;      // [2]
-  uint64_t* s_empty = bars + 9;     // [2]
-  uint64_t* p_full = bars + 11;     // 1
-  uint64_t* pv_done = bars + 12;    // 1
+  uint64_t* k_empty = bars + 5;     // [2] released by the commit after the last group's QK^T(it)
+  uint64_t* v_empty = bars + 7;     // [2] released by the commit after the last group's PV(it)
+  uint64_t* s_full = bars + 9;      // [2 groups] S_g(it) complete (and with it every earlier MMA, incl. PV_g(it-1))
+  uint64_t* p_full = bars + 11;     // [2 groups] P_g(it) packed into TMEM by all 128 rows
+  uint64_t* o_done = bars + 13;     // [2 groups] last PV_g complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* s_xchg = reinterpret_cast<float*>(bars + 32);  // [2 (parity)][2 (column half)][128 rows] row-max / row-sum exchange
+  float* s_xchg = reinterpret_cast<float*>(bars + 32);  // [2 groups][2 (parity)][2 (column half)][128 rows]
 
   const lx_attn_desc_t& d = p.d;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int G = p.groups;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int qt0 = blockIdx.x * G;  // first query tile of this CTA
   const int n_tiles = d.S / ATT_BKV;
   const int n_rest = (d.S - d.n_cond) / ATT_BKV;  // tiles of the non-condition part
-  const bool q_is_cond = qt >= n_rest;
-  // kv tile range visible to this query tile
-  int kv_begin = 0, kv_end = n_tiles;
+  // all query tiles of a CTA are on the same side of the rest|cond boundary (G == 2 only when n_rest is even)
+  const bool q_is_cond = qt0 >= n_rest;
+  int kv_begin = 0, kv_end = n_tiles;  // kv tile range visible to this CTA's query tiles
   const bool use_bias = p.bias_log2 != 0.0f;
   if (!use_bias && d.n_cond > 0) {
     if (q_is_cond && (d.mask_mode == 1 || d.mask_mode == 2)) kv_begin = n_rest;
@@ -86,10 +90,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], ATT_SOFTMAX_THREADS);
+      mbar_init(&p_full[s], 256);
+      mbar_init(&o_done[s], 1);
     }
-    mbar_init(p_full, ATT_SOFTMAX_THREADS);
-    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -100,14 +103,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // two 128-column buffers
-  const uint32_t tmem_O = tmem_base + 256;  // 128 columns
+  // columns [128g, 128g+128): S_g fp32, its first 64 columns re-used for the packed bf16 P_g;  [256+128g, +128): O_g
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, 0, head_row0 + qt * ATT_BQ);
-      tma_load_2d(sQ + ATT_ATOM_BYTES, &tmQ, q_full, 64, head_row0 + qt * ATT_BQ);
+    if (elect_one()) {
+      mbar_expect_tx(q_full, G * ATT_TILE_BYTES);
+      for (int g = 0; g < G; ++g) {
+        tma_load_2d(sQ + g * ATT_TILE_BYTES, &tmQ, q_full, 0, head_row0 + (qt0 + g) * ATT_BQ);
+        tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmQ, q_full, 64, head_row0 + (qt0 + g) * ATT_BQ);
+      }
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
         const uint32_t par = ((it >> 1) & 1) ^ 1;
@@ -124,153 +130,165 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);  // A = Q (K-major), B = K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, false, true);   // A = P (K-major), B = V (MN-major)
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      auto issue_qk = [&](int it) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, false, true);   // A = P (TMEM),    B = V (MN-major)
+      // Base descriptors are built once; per MMA only the 14-bit address field (bytes >> 4) is advanced, so the issue
+      // loop is UIADD + UTCHMMA (the tensor pipe needs a new 128x128x16 MMA every 64 clk).
+      const uint64_t q_desc0 = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t k_desc0 = make_sdesc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(sV), ATT_ATOM_BYTES, 1024);
+      auto issue_qk = [&](int g, int it) {
         const int st = it & 1;
         mbar_wait(&k_full[st], (it >> 1) & 1);
-        mbar_wait(&s_empty[st], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+        const uint64_t qd = q_desc0 + (uint64_t)(g * (ATT_TILE_BYTES >> 4));
+        const uint64_t kd = k_desc0 + (uint64_t)(st * (ATT_TILE_BYTES >> 4));
+        const uint32_t ts_g = tmem_S + g * 128;
 #pragma unroll
         for (int kk = 0; kk < ATT_D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * ATT_ATOM_BYTES + (kk & 3) * 32;
-          umma_ss(tmem_S + st * 128, make_sdesc_sw128(q_addr + off, 16, 1024), make_sdesc_sw128(k_addr + off, 16, 1024),
-                  idesc_qk, kk != 0 ? 1u : 0u);
+          const uint32_t off = ((kk >> 2) * ATT_ATOM_BYTES + (kk & 3) * 32) >> 4;
+          umma_ss(ts_g, qd + off, kd + off, idesc_qk, kk != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[st]);
-        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[g]);
+        if (g == G - 1) umma_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
+      for (int g = 0; g < G; ++g) issue_qk(g, 0);
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) issue_qk(it + 1);
         const int st = it & 1;
-        mbar_wait(&v_full[st], (it >> 1) & 1);
-        mbar_wait(p_full, it & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+        const uint64_t vd = v_desc0 + (uint64_t)(st * (ATT_TILE_BYTES >> 4));
+        for (int g = 0; g < G; ++g) {
+          const uint32_t to_g = tmem_O + g * 128, tp_g = tmem_S + g * 128;
+          mbar_wait(&v_full[st], (it >> 1) & 1);
+          mbar_wait(&p_full[g], it & 1);
+          tc_fence_after();
+          // A: P_g[128 x 16] slice kk = 8 TMEM columns of packed bf16 pairs; B: V rows [16kk, 16kk+16) x 128 d
+          // (MN-major: LBO = next 64-d atom)
+          if (it == 0) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-          // A: P[128 x 16] slice kk (K-major); B: V rows [16kk, 16kk+16) x 128 d (MN-major: LBO = next 64-d atom)
-          const uint64_t da = make_sdesc_sw128(p_addr + (kk >> 2) * ATT_ATOM_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = make_sdesc_sw128(v_addr + kk * 2048, ATT_ATOM_BYTES, 1024);
-          umma_ss(tmem_O, da, db, idesc_pv, (it | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+              umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+              umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
+          }
+          if (g == G - 1) umma_commit(&v_empty[st]);
+          // S_g(it+1) overwrites the columns P_g(it) is read from: the tensor pipe executes in issue order
+          if (it + 1 < n_it) issue_qk(g, it + 1);
+          else umma_commit(&o_done[g]);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
-    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which 64 key columns (and which 64 output columns) this thread owns
-    const int r = quarter * 32 + lane;   // query row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    float m_run = -INFINITY;  // running (possibly stale) max in log2 units, identical in both halves of a row
-    float l_run = 0.f;        // partial row sum over this thread's columns
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
-#define DBG(slot) if (dbg_on) p.dbg[it * 8 + (slot)] = clock64();
-    for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      const bool cross = use_bias && (q_is_cond != ((kv_begin + it) >= n_rest));
-      DBG(0)
-      const float bias = cross ? p.bias_log2 : 0.f;
-      mbar_wait(&s_full[st], (it >> 1) & 1);
-      tc_fence_after();
-      DBG(1)
-      const uint32_t ts = tmem_S + st * 128 + half * 64 + lane_off;
-      uint32_t v[64];
-      {
-        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32b_x32(ts, v0);
-        tmem_ld_32x32b_x32(ts + 32, v1);
-      }
-      tc_fence_before();
-      mbar_arrive(&s_empty[st]);  // S is in registers: the buffer may be overwritten by QK(it+2)
-      DBG(2)
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-      float* xch = s_xchg + (it & 1) * 256;
-      xch[half * 128 + r] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
-      DBG(3)
-      const float m_tile = mx * p.scale_log2 + bias;
-      float alpha = 1.0f;
-      bool rescale = false;
-      if (m_tile > m_run + 8.0f) {  // also true on the first tile (m_run = -inf)
-        alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile
-        m_run = m_tile;
-        rescale = it > 0;
-      }
-      uint32_t pk[32];
-      float lsum = 0.f;
-      const float moff = bias - m_run;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-        lsum += p0 + p1;
-        pk[j] = pack_bf16(p0, p1);
-      }
-      l_run = l_run * alpha + lsum;
-      DBG(4)
-      if (it > 0) {
-        mbar_wait(pv_done, (it - 1) & 1);  // PV(it-1) finished: O is stable and sP is free
+    const int g = (warp - 2) >> 3;           // query tile of this warp
+    const int half = ((warp - 2) >> 2) & 1;  // which 64 key columns (and which 64 output columns) this thread owns
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;       // query row inside the tile == TMEM lane
+    if (g < G) {
+      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t ts = tmem_S + g * 128 + half * 64 + lane_off;  // this thread's S columns
+      const uint32_t tp = tmem_S + g * 128 + half * 32 + lane_off;  // this thread's packed P columns
+      const uint32_t to = tmem_O + g * 128 + half * 64 + lane_off;  // this thread's O columns
+      float* xch_g = s_xchg + g * 512;  // [parity][half][128]
+      float m_run = -INFINITY;  // running (possibly stale) max in log2 units, identical in both halves of a row
+      float l_run = 0.f;        // partial row sum over this thread's columns
+      const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                          quarter == 2 && half == 0;
+#define DBG(slot) if (dbg_on) p.dbg[(g * n_it + it) * 8 + (slot)] = clock64();
+      for (int it = 0; it < n_it; ++it) {
+        const bool cross = use_bias && (q_is_cond != ((kv_begin + it) >= n_rest));
+        const float bias = cross ? p.bias_log2 : 0.f;
+        DBG(0)
+        mbar_wait(&s_full[g], it & 1);
         tc_fence_after();
+        DBG(1)
+        uint32_t v[64];
+        tmem_ld_32x32b_x64(ts, v);
+        DBG(2)
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(v[j]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(v[j + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(v[j + 3]));
+        }
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // exchange the half-row maxima.  The barrier also orders the S loads of both halves (done above) before either
+        // half overwrites columns [0, 64) of S_g with packed P below.
+        float* xch = xch_g + (it & 1) * 256;
+        xch[half * 128 + r] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
+        mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
+        const float m_tile = mx * p.scale_log2 + bias;
+        float alpha = 1.0f;
+        bool rescale = false;
+        if (m_tile > m_run + 8.0f) {  // also true on the first tile (m_run = -inf)
+          alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile
+          m_run = m_tile;
+          rescale = it > 0;
+        }
+        DBG(3)
+        // s_full(it) also covers PV_g(it-1): O_g is stable here
         if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_O + lane_off + half * 64 + c * 32, o);
+            tmem_ld_32x32b_x32(to + c * 32, o);
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st_32x32b_x32(tmem_O + lane_off + half * 64 + c * 32, o);
+            tmem_st_32x32b_x32(to + c * 32, o);
           }
-          tmem_st_wait();
         }
-      }
-      DBG(5)
-      // this thread's 64 P columns = one 128-byte-swizzled atom row
+        float ls0 = 0.f, ls1 = 0.f;
+        const float moff = bias - m_run;
 #pragma unroll
-      for (int c16 = 0; c16 < 8; ++c16) {
-        uint4 val = make_uint4(pk[4 * c16], pk[4 * c16 + 1], pk[4 * c16 + 2], pk[4 * c16 + 3]);
-        *reinterpret_cast<uint4*>(sP + half * ATT_ATOM_BYTES + r * 128 + ((c16 ^ (r & 7)) << 4)) = val;
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2_approx_ordered(fmaf(__uint_as_float(v[c * 32 + 2 * j]), p.scale_log2, moff));
+            const float p1 = ex2_approx_ordered(fmaf(__uint_as_float(v[c * 32 + 2 * j + 1]), p.scale_log2, moff));
+            ls0 += p0;
+            ls1 += p1;
+            pk[j] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x32b_x16(tp + c * 16, pk);
+        }
+        l_run = l_run * alpha + (ls0 + ls1);
+        DBG(4)
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[g]);
+        DBG(5)
       }
-      DBG(6)
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      DBG(7)
-    }
-    // epilogue: O / l -> bf16 -> out rows (each thread writes its 64 output columns)
-    float* xch = s_xchg + (n_it & 1) * 256;
-    xch[half * 128 + r] = l_run;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float inv_l = 1.0f / (l_run + xch[(half ^ 1) * 128 + r]);
-    mbar_wait(pv_done, (n_it - 1) & 1);
-    tc_fence_after();
-    const int out_row = d.out_row_base[b * n_tiles + qt] + r;
-    __nv_bfloat16* out =
-        reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)out_row * d.ldo + d.col_offset + h * ATT_D + half * 64;
+      // epilogue: O / l -> bf16 -> out rows (each thread writes its 64 output columns)
+      float* xch = xch_g + (n_it & 1) * 256;
+      xch[half * 128 + r] = l_run;
+      asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
+      const float inv_l = 1.0f / (l_run + xch[(half ^ 1) * 128 + r]);
+      mbar_wait(&o_done[g], 0);
+      tc_fence_after();
+      const int out_row = d.out_row_base[b * n_tiles + qt0 + g] + r;
+      __nv_bfloat16* out =
+          reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)out_row * d.ldo + d.col_offset + h * ATT_D + half * 64;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_off + half * 64 + c * 32, o);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(to + c * 32, o);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(o[8 * j + 0]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
-        u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
-        u.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
-        u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(out + c * 32 + j * 8) = u;
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[8 * j + 0]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(out + c * 32 + j * 8) = u;
+        }
       }
     }
   }
@@ -286,7 +304,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }  // namespace lx
 
 static long long* g_attn_dbg = nullptr;
-// development aid: per-iteration clock64 timeline of CTA (0,0,0)'s first softmax thread, 8 slots per KV iteration
+// development aid: per-iteration clock64 timeline of CTA (0,0,0): 8 slots per (query tile, KV iteration)
 extern "C" void lx_attention_debug_timeline(long long* device_buffer) { g_attn_dbg = device_buffer; }
 
 extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
@@ -312,12 +330,14 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   const float log2e = 1.4426950408889634f;
   p.scale_log2 = d.scale * log2e;
   p.bias_log2 = d.cross_bias * log2e;
+  const int n_tiles = d.S / 128, n_rest = (d.S - d.n_cond) / 128;
+  p.groups = (n_tiles % 2 == 0 && n_rest % 2 == 0) ? 2 : 1;
   static bool attr_set = false;
   if (!attr_set) {
     LX_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  dim3 grid(d.S / 128, d.H, d.B);
+  dim3 grid(n_tiles / p.groups, d.H, d.B);
   double pairs = (double)d.S * d.S;  // visible (query, key) pairs per head
   if (d.cross_bias == 0.f && d.n_cond > 0) {
     const double nc = d.n_cond, nr = d.S - d.n_cond;
@@ -326,6 +346,15 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   }
   LaunchScope scope(KC_ATTENTION, stream, 4.0 * d.B * d.H * pairs * 128.0);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
-  LX_CUDA(cudaGetLastError());
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      cudaFuncAttributes fa{};
+      cudaFuncGetAttributes(&fa, attention_kernel);
+      set_error("lx_attention launch: %s (regs %d, max threads/block %d, local %zu B, dyn smem %d)", cudaGetErrorString(e),
+                fa.numRegs, fa.maxThreadsPerBlock, fa.localSizeBytes, ATT_SMEM);
+      return LX_ERR_CUDA;
+    }
+  }
   return LX_OK;
 }

@@ -115,7 +115,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: the compiler keeps descriptors in uniform registers (no per-MMA waterfall loop)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -141,8 +141,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -155,13 +156,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          // base descriptors are built once; only the 14-bit address field (bytes >> 4) advances per stage / k-slice
+          const uint64_t da = a_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+          const uint64_t db = da + (uint64_t)(A_BYTES >> 4);
+          if (kb == 0) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_sdesc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = make_sdesc_sw128(sb + k * 32, 16, 1024);
-            umma_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
           }
           umma_commit(&empty[stage]);
           if (++stage == STAGES) {
