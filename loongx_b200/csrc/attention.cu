@@ -7,9 +7,9 @@
 //                 S_g = Q_g K_j^T   (SS form, TMEM columns [128g, 128g+128))
 //                 O_g += P_g V_j    (TS form: the bf16 probabilities are read from TMEM, where the softmax threads
 //                                    packed them in place over the first 64 columns of S_g; V is the MN-major smem operand)
-//   warps 2..9  : softmax of tile A, TWO threads per query row (each owns 64 of the tile's 128 key columns, tcgen05.ld
-//                 32x32b; the halves exchange their row max through shared memory + one named barrier per tile)
-//   warps 10..17: softmax of tile B
+//   warps 4..7  : softmax of tile A, one thread per query row (tcgen05.ld 32x32b: no cross-lane reductions)
+//   warps 8..11 : softmax of tile B   (setmaxnreg moves warpgroup 0's registers to these two: 240 regs / thread, the
+//                 whole 128-column S row stays in registers between the max and the exp pass)
 //                 exp2 (single MUFU.EX2) with the 1/sqrt(d)·log2(e) scale folded into one FFMA, lazy rescale of O (only
 //                 when the running max grows by more than 8 in log2 units), P never touches shared memory.
 //   While one tile's rows are in the MUFU-bound softmax (16 exp2/clk/SM = 1024 clk per 128x128 tile) the tensor pipe
@@ -29,7 +29,7 @@ constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_D = 128;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KiB: two 128x64 swizzle atoms
 constexpr int ATT_ATOM_BYTES = 128 * 64 * 2;   // 16 KiB
 constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_THREADS = 576;  // TMA warp + MMA warp + 2 query tiles x 8 softmax warps
+constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA warp + MMA warp (+2 idle); warpgroups 1, 2: softmax of tiles A, B
 constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
 
 struct AttnParams {
@@ -57,8 +57,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = bars + 9;      // [2 groups] S_g(it) complete (and with it every earlier MMA, incl. PV_g(it-1))
   uint64_t* p_full = bars + 11;     // [2 groups] P_g(it) packed into TMEM by all 128 rows
   uint64_t* o_done = bars + 13;     // [2 groups] last PV_g complete
+  uint64_t* p_half = bars + 20;     // [2 groups] first 64 key columns of P_g(it) packed (PV k-slices 0..3 may start)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* s_xchg = reinterpret_cast<float*>(bars + 32);  // [2 groups][2 (parity)][2 (column half)][128 rows]
 
   const lx_attn_desc_t& d = p.d;
   const int warp = threadIdx.x >> 5;
@@ -90,7 +90,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 256);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&p_half[s], 128);
       mbar_init(&o_done[s], 1);
     }
     fence_mbar_init();
@@ -107,6 +108,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 256;
 
+  if (warp < 4) {
+  reg_dealloc<96>();  // setmaxnreg: hand the producer warpgroup's registers to the softmax warpgroups
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, G * ATT_TILE_BYTES);
@@ -153,6 +156,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(&s_full[g]);
         if (g == G - 1) umma_commit(&k_empty[st]);
       };
+      const bool mma_dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       mbar_wait(q_full, 0);
       for (int g = 0; g < G; ++g) issue_qk(g, 0);
       for (int it = 0; it < n_it; ++it) {
@@ -161,43 +165,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int g = 0; g < G; ++g) {
           const uint32_t to_g = tmem_O + g * 128, tp_g = tmem_S + g * 128;
           mbar_wait(&v_full[st], (it >> 1) & 1);
-          mbar_wait(&p_full[g], it & 1);
-          tc_fence_after();
           // A: P_g[128 x 16] slice kk = 8 TMEM columns of packed bf16 pairs; B: V rows [16kk, 16kk+16) x 128 d
-          // (MN-major: LBO = next 64-d atom)
+          // (MN-major: LBO = next 64-d atom).  The first four k-slices start as soon as the first 64 key columns of P
+          // are packed, while the softmax threads are still exponentiating the other 64.
+          mbar_wait(&p_half[g], it & 1);
+          tc_fence_after();
           if (it == 0) {
 #pragma unroll
-            for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+            for (int kk = 0; kk < 4; ++kk)
               umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk != 0 ? 1u : 0u);
           } else {
 #pragma unroll
-            for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+            for (int kk = 0; kk < 4; ++kk)
               umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
           }
+          mbar_wait(&p_full[g], it & 1);
+          tc_fence_after();
+          if (mma_dbg) p.dbg[(g * n_it + it) * 8 + 6] = clock64();
+#pragma unroll
+          for (int kk = 4; kk < 8; ++kk)
+            umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
           if (g == G - 1) umma_commit(&v_empty[st]);
           // S_g(it+1) overwrites the columns P_g(it) is read from: the tensor pipe executes in issue order
           if (it + 1 < n_it) issue_qk(g, it + 1);
           else umma_commit(&o_done[g]);
+          if (mma_dbg) p.dbg[(g * n_it + it) * 8 + 7] = clock64();
         }
       }
     }
     __syncwarp();
+  }
   } else {
+    reg_alloc<200>();
     // ------------------------------------------------------------------ softmax / correction / epilogue
-    const int g = (warp - 2) >> 3;           // query tile of this warp
-    const int half = ((warp - 2) >> 2) & 1;  // which 64 key columns (and which 64 output columns) this thread owns
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int r = quarter * 32 + lane;       // query row inside the tile == TMEM lane
+    const int g = (warp - 4) >> 2;      // query tile of this warp
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     if (g < G) {
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t ts = tmem_S + g * 128 + half * 64 + lane_off;  // this thread's S columns
-      const uint32_t tp = tmem_S + g * 128 + half * 32 + lane_off;  // this thread's packed P columns
-      const uint32_t to = tmem_O + g * 128 + half * 64 + lane_off;  // this thread's O columns
-      float* xch_g = s_xchg + g * 512;  // [parity][half][128]
-      float m_run = -INFINITY;  // running (possibly stale) max in log2 units, identical in both halves of a row
-      float l_run = 0.f;        // partial row sum over this thread's columns
+      const uint32_t ts = tmem_S + g * 128 + lane_off;  // S_g row (fp32) / packed P_g row (first 64 columns)
+      const uint32_t to = tmem_O + g * 128 + lane_off;
+      float m_run = -INFINITY;  // running (possibly stale) max in log2 units
+      float l_run = 0.f;
       const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                          quarter == 2 && half == 0;
+                          quarter == 2;
 #define DBG(slot) if (dbg_on) p.dbg[(g * n_it + it) * 8 + (slot)] = clock64();
       for (int it = 0; it < n_it; ++it) {
         const bool cross = use_bias && (q_is_cond != ((kv_begin + it) >= n_rest));
@@ -206,24 +217,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&s_full[g], it & 1);
         tc_fence_after();
         DBG(1)
-        uint32_t v[64];
-        tmem_ld_32x32b_x64(ts, v);
+        uint32_t v[128];
+        {
+          uint32_t(&v0)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[0]);
+          uint32_t(&v1)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[64]);
+          tmem_ld_32x32b_x64(ts, v0);
+          tmem_ld_32x32b_x64(ts + 64, v1);
+        }
         DBG(2)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < 128; j += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(v[j]));
           mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(v[j + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(v[j + 3]));
         }
-        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        // exchange the half-row maxima.  The barrier also orders the S loads of both halves (done above) before either
-        // half overwrites columns [0, 64) of S_g with packed P below.
-        float* xch = xch_g + (it & 1) * 256;
-        xch[half * 128 + r] = mx;
-        asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
-        mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         const float m_tile = mx * p.scale_log2 + bias;
         float alpha = 1.0f;
         bool rescale = false;
@@ -236,7 +246,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // s_full(it) also covers PV_g(it-1): O_g is stable here
         if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
             tmem_ld_32x32b_x32(to + c * 32, o);
 #pragma unroll
@@ -247,7 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float ls0 = 0.f, ls1 = 0.f;
         const float moff = bias - m_run;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -257,7 +267,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ls1 += p1;
             pk[j] = pack_bf16(p0, p1);
           }
-          tmem_st_32x32b_x16(tp + c * 16, pk);
+          tmem_st_32x32b_x16(ts + c * 16, pk);
+          if (c == 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_half[g]);
+          }
         }
         l_run = l_run * alpha + (ls0 + ls1);
         DBG(4)
@@ -265,19 +280,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         mbar_arrive(&p_full[g]);
         DBG(5)
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)
+          p.dbg[2 * n_it * 8 + (g * n_it + it) * 4 + quarter] = clock64();
       }
-      // epilogue: O / l -> bf16 -> out rows (each thread writes its 64 output columns)
-      float* xch = xch_g + (n_it & 1) * 256;
-      xch[half * 128 + r] = l_run;
-      asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
-      const float inv_l = 1.0f / (l_run + xch[(half ^ 1) * 128 + r]);
+      // epilogue: O / l -> bf16 -> out rows
+      const float inv_l = 1.0f / l_run;
       mbar_wait(&o_done[g], 0);
       tc_fence_after();
       const int out_row = d.out_row_base[b * n_tiles + qt0 + g] + r;
       __nv_bfloat16* out =
-          reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)out_row * d.ldo + d.col_offset + h * ATT_D + half * 64;
+          reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)out_row * d.ldo + d.col_offset + h * ATT_D;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t o[32];
         tmem_ld_32x32b_x32(to + c * 32, o);
 #pragma unroll
