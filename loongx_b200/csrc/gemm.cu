@@ -8,6 +8,8 @@
 //
 // Tiles are scheduled M-fastest so that the CTAs resident at one time share a W panel (L2 reuse of the weights,
 // A is small enough to stay L2-resident).
+#include <stdlib.h>
+
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -19,11 +21,13 @@ constexpr int GEMM_THREADS = 192;
 
 // N tile variants: 256 is the default; 224 / 192 exist to cut wave-quantisation loss (e.g. M=2560, N=3072 is
 // 240 tiles = 1.62 waves of 148 CTAs at BN=256 but 280 tiles = 1.89 waves of *smaller* tiles at BN=224).
-template <int BN>
+template <int BN, int NCTA>
 struct TileCfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  // NCTA == 2: a CTA pair computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of A and
+  // half (BN/2 rows) of the W tile, so per-CTA L2->smem traffic and smem operand reads per FLOP drop by a third.
+  static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 5;
+  static constexpr int STAGES = NCTA == 2 ? (BN == 256 ? 6 : 7) : (BN == 256 ? 4 : 5);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -67,13 +71,13 @@ __device__ __forceinline__ void chunk_bias(const uint32_t (&r)[32], const float*
   }
 }
 
-template <int BN>
+template <int BN, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ GemmParams p) {
-  constexpr int STAGES = TileCfg<BN>::STAGES;
-  constexpr int STAGE_BYTES = TileCfg<BN>::STAGE_BYTES;
+  constexpr int STAGES = TileCfg<BN, NCTA>::STAGES;
+  constexpr int STAGE_BYTES = TileCfg<BN, NCTA>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -86,6 +90,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const lx_gemm_desc_t& d = p.d;
+  // CTA pair bookkeeping (NCTA == 1: rank 0, every CTA is its own "cluster")
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / NCTA;
+  const int num_clusters = gridDim.x / NCTA;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -98,16 +106,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 4 * NCTA);  // one arrival per epilogue warp of every CTA of the pair
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc_2cta(tmem_slot, 512);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -118,19 +132,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {  // elect.sync: the compiler keeps descriptors in uniform registers (no per-MMA waterfall loop)
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % p.tiles_m;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int tm = (tile % p.tiles_m) * NCTA + rank;  // this CTA's 128-row tile
         const int m0 = tm * BM;
-        const int n0 = (tile / p.tiles_m) * BN;
+        const int n0 = (tile / p.tiles_m) * BN + rank * (BN / NCTA);  // this CTA's slice of the W tile
         const int g = group_of(p, tm);
         const CUtensorMap* tmB = g == 0 ? &tmB0 : (g == 1 ? &tmB1 : &tmB2);
         const int nkb = p.num_kb[g];
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-          tma_load_2d(sa + A_BYTES, tmB, &full[stage], kb * BK, n0);
+          if (NCTA == 2) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (the leader issues the pair's MMAs)
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+            const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
+            tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
+            tma_load_2d_2sm(sa + A_BYTES, tmB, bar, kb * BK, n0);
+          } else {
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+            tma_load_2d(sa + A_BYTES, tmB, &full[stage], kb * BK, n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -141,38 +163,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * NCTA, BN, false, false);
       const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
-        const int nkb = p.num_kb[group_of(p, tile % p.tiles_m)];
+        const int nkb = p.num_kb[group_of(p, (tile % p.tiles_m) * NCTA)];
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           // base descriptors are built once; only the 14-bit address field (bytes >> 4) advances per stage / k-slice
           const uint64_t da = a_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
           const uint64_t db = da + (uint64_t)(A_BYTES >> 4);
-          if (kb == 0) {
+          if (NCTA == 2) {
+            if (kb == 0) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+            }
+            umma_commit_2cta(&empty[stage], 3);  // frees the stage in both CTAs
           } else {
+            if (kb == 0) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (NCTA == 2) umma_commit_2cta(&tfull[acc], 3);
+        else umma_commit(&tfull[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -186,8 +220,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile % p.tiles_m;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int tm = (tile % p.tiles_m) * NCTA + rank;
       const int m0 = tm * BM;
       const int n0 = (tile / p.tiles_m) * BN;
       const int row = m0 + row_in_tile;
@@ -336,7 +370,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));  // the leader's barrier
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -346,9 +384,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (NCTA == 2) tmem_dealloc_2cta(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -356,53 +396,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 namespace lx {
 
-template <int BN>
+template <int BN, int NCTA>
 int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
   CUtensorMap tmA, tmB[3];
   GemmParams p;
   p.d = d;
-  p.tiles_m = (d.M + BM - 1) / BM;
+  p.tiles_m = (d.M + BM * NCTA - 1) / (BM * NCTA);  // (pairs of) 128-row tiles
   p.tiles_n = (d.N + BN - 1) / BN;
   int kmax = 0;
   for (int g = 0; g < 3; ++g) {
     const int gi = g < d.n_groups ? g : 0;
     p.num_kb[g] = (d.group[gi].K + BK - 1) / BK;
-    p.tile_begin[g] = g < d.n_groups ? d.group[g].m_begin / BM : p.tiles_m;
+    p.tile_begin[g] = g < d.n_groups ? d.group[g].m_begin / BM : (d.M + BM - 1) / BM + NCTA;
     kmax = max(kmax, d.group[gi].K);
     int rc = make_tmap_2d_bf16(&tmB[g], d.group[gi].W, (uint64_t)d.N, (uint64_t)d.group[gi].K,
-                               (uint64_t)d.group[gi].ldw, BN, BK);
+                               (uint64_t)d.group[gi].ldw, BN / NCTA, BK);
     if (rc) return rc;
   }
   int rc = make_tmap_2d_bf16(&tmA, d.A, (uint64_t)d.M, (uint64_t)kmax, (uint64_t)d.lda, BM, BK);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::SMEM));
+    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TileCfg<BN, NCTA>::SMEM));
     attr_set = true;
   }
-  const int grid = min(p.tiles_m * p.tiles_n, num_sms());
+  const int grid = min(p.tiles_m * p.tiles_n, num_sms() / NCTA) * NCTA;
   double flops = 0;
   for (int g = 0; g < d.n_groups; ++g) {
     const int m_end = g + 1 < d.n_groups ? d.group[g + 1].m_begin : d.M;
     flops += 2.0 * (m_end - d.group[g].m_begin) * (double)d.N * d.group[g].K;
   }
   LaunchScope scope(KC_GEMM, stream, flops);
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB[0], tmB[1],
-                                                                                                    tmB[2], p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = TileCfg<BN, NCTA>::SMEM;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LX_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, NCTA>, tmA, tmB[0], tmB[1], tmB[2], p));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
 
 // N tile that minimises (number of waves) x (tile width); ties go to the wider tile.
-int pick_tile_n(int M, int N, bool need_256) {
+int pick_tile_n(int M, int N, bool need_256, int ncta) {
   if (need_256) return 256;
-  const int sms = num_sms();
-  const int tiles_m = (M + BM - 1) / BM;
+  const int units = num_sms() / ncta;
+  const int tiles_m = (M + BM * ncta - 1) / (BM * ncta);
   int best = 256;
   long best_cost = -1;
   for (int bn : {256, 224, 192}) {
     const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
-    const long cost = ((tiles + sms - 1) / sms) * bn;
+    const long cost = ((tiles + units - 1) / units) * bn;
     if (best_cost < 0 || cost < best_cost) {
       best = bn;
       best_cost = cost;
@@ -412,6 +464,10 @@ int pick_tile_n(int M, int N, bool need_256) {
 }
 
 }  // namespace lx
+
+static int g_force_ncta = 0;
+// development knob (scripts/gemm_shapes.py): 1 = never pair CTAs, 0 = automatic
+extern "C" void lx_debug_gemm_force_ncta(int ncta) { g_force_ncta = ncta; }
 
 extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
   using namespace lx;
@@ -451,10 +507,24 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
       LX_CHECK_ARG(d.residual && d.tile_meta && d.ldr % 8 == 0, "lx_gemm_bf16: GATE_RESIDUAL needs residual, tile_meta");
     }
   }
+  // CTA pairs (256-row tiles) whenever every row group starts on a 256-row boundary; LX_GEMM_NCTA=1 forces single CTAs
+  static const int env_ncta = [] {
+    const char* e = getenv("LX_GEMM_NCTA");
+    return e ? atoi(e) : 0;
+  }();
+  const int forced_ncta = g_force_ncta ? g_force_ncta : env_ncta;
+  bool pair_ok = d.M >= 256 && forced_ncta != 1;
+  for (int g = 0; g < d.n_groups; ++g) pair_ok = pair_ok && d.group[g].m_begin % 256 == 0;
+  const int ncta = pair_ok ? 2 : 1;
   int bn = d.tile_n;
-  if (bn == 0) bn = pick_tile_n(d.M, d.N, need_256);
+  if (bn == 0) bn = pick_tile_n(d.M, d.N, need_256, ncta);
   LX_CHECK_ARG(bn == 256 || ((bn == 224 || bn == 192) && !need_256), "lx_gemm_bf16: tile_n=%d not allowed here", bn);
-  if (bn == 256) return launch_gemm<256>(d, stream);
-  if (bn == 224) return launch_gemm<224>(d, stream);
-  return launch_gemm<192>(d, stream);
+  if (ncta == 2) {
+    if (bn == 256) return launch_gemm<256, 2>(d, stream);
+    if (bn == 224) return launch_gemm<224, 2>(d, stream);
+    return launch_gemm<192, 2>(d, stream);
+  }
+  if (bn == 256) return launch_gemm<256, 1>(d, stream);
+  if (bn == 224) return launch_gemm<224, 1>(d, stream);
+  return launch_gemm<192, 1>(d, stream);
 }
