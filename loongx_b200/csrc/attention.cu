@@ -29,11 +29,15 @@ constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_D = 128;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KiB: two 128x64 swizzle atoms
 constexpr int ATT_ATOM_BYTES = 128 * 64 * 2;   // 16 KiB
 constexpr int ATT_KV_STAGES = 2;
+#ifndef ATT_POLY_OF_8
+#define ATT_POLY_OF_8 2
+#endif
 constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA warp + MMA warp (+2 idle); warpgroups 1, 2: softmax of tiles A, B
 constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
 
 struct AttnParams {
   long long* dbg;  // optional timeline buffer (development aid, NULL in production)
+  long long* cta_trace;  // optional [n_ctas][6]: smid, t_entry, t_setup_done, t_first_s, t_loop_end, t_exit (CTA-level)
   lx_attn_desc_t d;
   float scale_log2;  // scale * log2(e)
   float bias_log2;   // cross_bias * log2(e)
@@ -42,7 +46,9 @@ struct AttnParams {
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ AttnParams p) {
+  const long long t_entry = clock64();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2 groups]
@@ -83,6 +89,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
+    prefetch_tmap(&tmO);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
@@ -103,6 +110,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  long long* trace = nullptr;
+  if (p.cta_trace != nullptr && threadIdx.x == 128) {  // first softmax thread of tile A
+    trace = p.cta_trace + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 6;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace[0] = smid;
+    trace[1] = t_entry;
+    trace[2] = clock64();
+  }
   const uint32_t tmem_base = *tmem_slot;
   // columns [128g, 128g+128): S_g fp32, its first 64 columns re-used for the packed bf16 P_g;  [256+128g, +128): O_g
   const uint32_t tmem_S = tmem_base;
@@ -217,6 +233,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&s_full[g], it & 1);
         tc_fence_after();
         DBG(1)
+        if (trace != nullptr && it == 0) trace[3] = clock64();
         uint32_t v[128];
         {
           uint32_t(&v0)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[0]);
@@ -254,18 +271,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_st_32x32b_x32(to + c * 32, o);
           }
         }
-        float ls0 = 0.f, ls1 = 0.f;
+        float2 ls = make_float2(0.f, 0.f);
         const float moff = bias - m_run;
+        const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), moff2 = make_float2(moff, moff);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2_approx_ordered(fmaf(__uint_as_float(v[c * 32 + 2 * j]), p.scale_log2, moff));
-            const float p1 = ex2_approx_ordered(fmaf(__uint_as_float(v[c * 32 + 2 * j + 1]), p.scale_log2, moff));
-            ls0 += p0;
-            ls1 += p1;
-            pk[j] = pack_bf16(p0, p1);
+            // packed fp32x2 FMA / ADD halve the issue slots; ATT_POLY_OF_8 of every 8 pairs are exponentiated by a
+            // polynomial on the FMA pipe, the rest by the MUFU
+            float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c * 32 + 2 * j]), __uint_as_float(v[c * 32 + 2 * j + 1])),
+                                  scale2, moff2);
+            float2 e;
+            if ((j & 7) < ATT_POLY_OF_8) {
+              e = ex2_poly2(x);
+            } else {
+              e.x = ex2_approx_ordered(x.x);
+              e.y = ex2_approx_ordered(x.y);
+            }
+            ls = __fadd2_rn(ls, e);
+            pk[j] = pack_bf16(e.x, e.y);
           }
           tmem_st_32x32b_x16(ts + c * 16, pk);
           if (c == 1) {
@@ -274,7 +300,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_arrive(&p_half[g]);
           }
         }
-        l_run = l_run * alpha + (ls0 + ls1);
+        l_run = l_run * alpha + (ls.x + ls.y);
         DBG(4)
         tmem_st_wait();
         tc_fence_before();
@@ -284,12 +310,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           p.dbg[2 * n_it * 8 + (g * n_it + it) * 4 + quarter] = clock64();
       }
       // epilogue: O / l -> bf16 -> out rows
+      if (trace != nullptr) trace[4] = clock64();
       const float inv_l = 1.0f / l_run;
       mbar_wait(&o_done[g], 0);
       tc_fence_after();
-      const int out_row = d.out_row_base[b * n_tiles + qt0 + g] + r;
-      __nv_bfloat16* out =
-          reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)out_row * d.ldo + d.col_offset + h * ATT_D;
+      // O_g / l -> bf16 -> this tile's (now idle) Q buffer in the 128-byte-swizzled TMA layout -> two TMA stores of
+      // 128 rows x 64 columns: full-line writes instead of 16-byte fragments at a 6 KB row stride
+      uint8_t* stage = sQ + g * ATT_TILE_BYTES;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t o[32];
@@ -301,8 +328,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
           u.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
           u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(out + c * 32 + j * 8) = u;
+          const int c16 = c * 4 + j;  // 16-byte chunk of the 256-byte output row
+          *reinterpret_cast<uint4*>(stage + (c16 >> 3) * ATT_ATOM_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = u;
         }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+      if (warp == 4 + 4 * g && elect_one()) {
+        const int out_row0 = d.out_row_base[b * n_tiles + qt0 + g];
+        const int col0 = d.col_offset + h * ATT_D;
+        tma_store_2d(&tmO, stage, col0, out_row0);
+        tma_store_2d(&tmO, stage + ATT_ATOM_BYTES, col0 + 64, out_row0);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // the staging buffer must outlive the bulk read; global visibility at kernel end
       }
     }
   }
@@ -313,11 +351,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (trace != nullptr) trace[5] = clock64();
 }
 
 }  // namespace lx
 
 static long long* g_attn_dbg = nullptr;
+static long long* g_attn_trace = nullptr;
+extern "C" void lx_attention_debug_cta_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 // development aid: per-iteration clock64 timeline of CTA (0,0,0): 8 slots per (query tile, KV iteration)
 extern "C" void lx_attention_debug_timeline(long long* device_buffer) { g_attn_dbg = device_buffer; }
 
@@ -338,9 +379,12 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   if ((rc = make_tmap_2d_bf16(&tmQ, d.q, rows, 128, 128, 128, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmK, d.k, rows, 128, 128, 128, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmV, d.v, rows, 128, 128, 128, 64))) return rc;
+  CUtensorMap tmO;  // output rows in the stream-major activation layout: [B*S, ldo], head h at columns col_offset + 128 h
+  if ((rc = make_tmap_2d_bf16(&tmO, d.out, (uint64_t)d.B * d.S, (uint64_t)d.ldo, (uint64_t)d.ldo, 128, 64))) return rc;
   AttnParams p;
   p.d = d;
   p.dbg = g_attn_dbg;
+  p.cta_trace = g_attn_trace;
   const float log2e = 1.4426950408889634f;
   p.scale_log2 = d.scale * log2e;
   p.bias_log2 = d.cross_bias * log2e;
@@ -359,7 +403,7 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
   }
   LaunchScope scope(KC_ATTENTION, stream, 4.0 * d.B * d.H * pairs * 128.0);
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

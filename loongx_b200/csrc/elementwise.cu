@@ -29,30 +29,47 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-constexpr int LN_MAX_NV = 12;  // D <= 3072 (NV = D / 256)
+constexpr int LN_THREADS = 128;  // one CTA (4 warps) per activation row: many small CTAs hide the load latency
+constexpr int LN_MAX_NV = 3;     // D <= 3072: each thread owns up to 3 chunks of 8 columns
 
-__global__ void __launch_bounds__(ROW_WARPS * 32) ln_modulate_kernel(const lx_lnmod_desc_t d) {
+__device__ __forceinline__ float block_sum_128(float v, float* red, int warp, int lane) {
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const float r = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_desc_t d) {
+  __shared__ float red[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + warp;
-  if (row >= d.rows) return;
+  const int row = blockIdx.x;
   const lx_tile_meta_t meta = d.tile_meta[row >> 7];
-  const int nv = d.D >> 8;
+  const int nchunk = d.D >> 3;  // 16-byte chunks per row
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x) + (size_t)row * d.ldx;
-  float v[LN_MAX_NV * 8];
+  const __nv_bfloat16* shift =
+      reinterpret_cast<const __nv_bfloat16*>(d.shift[meta.stream]) + (size_t)meta.batch * d.stride[meta.stream];
+  const __nv_bfloat16* scale =
+      reinterpret_cast<const __nv_bfloat16*>(d.scale[meta.stream]) + (size_t)meta.batch * d.stride[meta.stream];
+  float v[LN_MAX_NV * 8], sh[LN_MAX_NV * 8], sc[LN_MAX_NV * 8];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAX_NV; ++i) {
-    if (i < nv) {
-      load8(x + i * 256 + lane * 8, &v[i * 8]);
+    const int ch = i * LN_THREADS + threadIdx.x;
+    if (ch < nchunk) {
+      load8(x + ch * 8, &v[i * 8]);
+      load8_ldg(shift + ch * 8, &sh[i * 8]);  // issued with the row loads: not behind the two reductions
+      load8_ldg(scale + ch * 8, &sc[i * 8]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) sum += v[i * 8 + e];
     }
   }
-  const float mean = warp_sum(sum) / d.D;
+  const float mean = block_sum_128(sum, red, warp, lane) / d.D;
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAX_NV; ++i) {
-    if (i < nv) {
+    if (i * LN_THREADS + threadIdx.x < nchunk) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         float c = v[i * 8 + e] - mean;
@@ -60,22 +77,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_modulate_kernel(const lx_ln
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / d.D + d.eps);
-  const __nv_bfloat16* shift =
-      reinterpret_cast<const __nv_bfloat16*>(d.shift[meta.stream]) + (size_t)meta.batch * d.stride[meta.stream];
-  const __nv_bfloat16* scale =
-      reinterpret_cast<const __nv_bfloat16*>(d.scale[meta.stream]) + (size_t)meta.batch * d.stride[meta.stream];
+  const float rstd = rsqrtf(block_sum_128(sq, red, warp, lane) / d.D + d.eps);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo;
 #pragma unroll
   for (int i = 0; i < LN_MAX_NV; ++i) {
-    if (i < nv) {
-      const int c0 = i * 256 + lane * 8;
-      float sh[8], sc[8];
-      load8_ldg(shift + c0, sh);
-      load8_ldg(scale + c0, sc);
+    const int ch = i * LN_THREADS + threadIdx.x;
+    if (ch < nchunk) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[i * 8 + e] = (v[i * 8 + e] - mean) * rstd * (1.0f + sc[e]) + sh[e];
-      *reinterpret_cast<uint4*>(out + c0) = pack8(&v[i * 8]);
+      for (int e = 0; e < 8; ++e) v[i * 8 + e] = (v[i * 8 + e] - mean) * rstd * (1.0f + sc[i * 8 + e]) + sh[i * 8 + e];
+      *reinterpret_cast<uint4*>(out + ch * 8) = pack8(&v[i * 8]);
     }
   }
 }
@@ -185,13 +195,12 @@ using namespace lx;
 extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
   LX_CHECK_ARG(desc != nullptr, "lx_ln_modulate: null descriptor");
   const lx_lnmod_desc_t& d = *desc;
-  LX_CHECK_ARG(d.rows > 0 && d.D > 0 && d.D % 256 == 0 && d.D <= LN_MAX_NV * 256,
-               "lx_ln_modulate: D=%d must be a multiple of 256 and <= %d", d.D, LN_MAX_NV * 256);
+  LX_CHECK_ARG(d.rows > 0 && d.D > 0 && d.D % 256 == 0 && d.D <= LN_MAX_NV * LN_THREADS * 8,
+               "lx_ln_modulate: D=%d must be a multiple of 256 and <= %d", d.D, LN_MAX_NV * LN_THREADS * 8);
   LX_CHECK_ARG(d.x && d.out && d.tile_meta, "lx_ln_modulate: null pointer");
   LX_CHECK_ARG(d.ldx % 8 == 0 && d.ldo % 8 == 0 && d.ldo >= d.D && d.ldx >= d.D, "lx_ln_modulate: bad strides");
-  const int grid = (d.rows + ROW_WARPS - 1) / ROW_WARPS;
   LaunchScope scope(KC_ROW, stream, 4.0 * d.rows * d.D);  // bytes: read + write bf16 rows
-  ln_modulate_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(d);
+  ln_modulate_kernel<<<d.rows, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(d);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

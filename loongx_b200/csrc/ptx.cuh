@@ -322,6 +322,24 @@ __device__ __forceinline__ float ex2_approx_ordered(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair of values on the FMA/ALU pipes (no MUFU), with Blackwell's packed fp32x2 arithmetic: round-to-nearest
+// split x = n + r, r in [-0.5, 0.5], cubic minimax for 2^r (rel. error 7.5e-5, far below bf16's 2^-9), exponent patched
+// in with integer arithmetic.  Used for a fraction of the softmax exponentials so that the 16-per-clock MUFU unit is not
+// the only exp2 engine of the SM.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float magic = 12582912.0f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  const float2 xf = __fadd2_rn(x, make_float2(magic, magic));
+  const float2 n = __fadd2_rn(xf, make_float2(-magic, -magic));
+  const float2 r = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(r, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, r, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, r, make_float2(0.9999280572f, 0.9999280572f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xf.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xf.y) << 23));
+  return p;
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
