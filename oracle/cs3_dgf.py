@@ -11,7 +11,11 @@ Pure-PyTorch restatement of LoongX's neural-signal conditioning:
 The state-space layer is `from s4torch import S4Model` (model.py:14): a third-party PyPI package that is absent from
 /root/reference, un-vendored, un-pinned and not even listed in the requirements files.  Its algorithm is restated here
 from the published S4 (DPLR / HiPPO-LegS, "Annotated S4" formulation that s4torch implements) as recorded in
-SURVEY.md App. B.  **PARITY UNPINNED**: nothing in the reference pins these numbers; the only available cross-check
+SURVEY.md App. B.  PINNING: every class / method listed above is pinned bit-for-bit to the reference's own source executed
+on the CPU (oracle/ref_harness.py -> tests/golden/ref_v1.npz, tests/test_reference_pins_cpu.py: the four encoders,
+FeaturePyramidPooling, DUAN(512) / DUAN(1), fuse_eeg / fuse_fnirs, spatial_pyramid_pooling and the generate.py glue
+in both fuse modes) — with `S4Model` inside the reference encoders being THIS file's S4Model.  **PARITY UNPINNED** for
+the S4 layer itself: nothing in the reference pins s4torch's numbers; the only available cross-check
 (tests/test_oracle_cpu.py) is that the Cauchy/iFFT convolution kernel equals the bilinear-discretised recurrence.
 
 Documented deviations from the literal reference (all required for the path to run at all):

@@ -3,8 +3,10 @@
 Restatement of the sampler side of the reference: the denoise loop of src/flux/generate.py:260-372 and the diffusers
 0.31.0 helpers it calls (`FlowMatchEulerDiscreteScheduler.set_timesteps/step`, `calculate_shift`,
 `FluxPipeline._pack_latents / _unpack_latents / _prepare_latent_image_ids`), plus the id
-arithmetic of src/flux/condition.py:126-137.  diffusers is absent from /root/reference and from this image; PARITY
-UNPINNED except for the closed-form checks in tests/test_oracle_cpu.py.
+arithmetic of src/flux/condition.py:126-137.  The loop and the id arithmetic are pinned bit-for-bit to the reference's
+own generate.py / condition.py / pipeline_tools.py executed on the CPU (oracle/ref_harness.py, tests/golden/ref_v1.npz);
+diffusers itself is absent from /root/reference and from this image, so its scheduler / packing helpers are PARITY
+UNPINNED beyond the closed-form checks in tests/test_oracle_cpu.py.
 """
 from __future__ import annotations
 

@@ -169,3 +169,39 @@ def test_euler_and_pack_bit_exact():
     out = euler_step(packed, v, -0.0371)
     ref_e = (packed.float() + (-0.0371) * v.float()).to(torch.bfloat16)
     assert torch.equal(out, ref_e)
+
+
+@pytest.mark.parametrize("variant", ["default", "independent", "no_union"])
+def test_dit_forward_vs_reference_fixture(variant):
+    """Native DiT forward against outputs of the REFERENCE'S OWN transformer.py / block.py (executed on the CPU in the
+    build container, tests/golden/ref_v1.npz 'gpudit_*'): same bf16-rounded weights and inputs, reference in fp32.
+    Tolerance: relL2 <= 2e-2 (bf16 storage of activations / weights)."""
+    import os
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_golden as MR
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_v1.npz"))
+    ocfg, P, inp = MR.gpu_dit_case()
+    dev = "cuda"
+    cfg = FluxConfig(**MR.TINY)
+    W = DitWeights({k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}, cfg, dev)
+    B, T = inp["lat"].shape[0], len(MR.GPU_DIT_TS)
+    mc = MR.GPU_DIT_VARIANTS[variant]
+    plan = DitPlan(W, B, 128, 128, 128, T=T, model_config=mc)
+    plan.set_ids(inp["txt_ids"].to(dev), inp["img_ids"].to(dev), inp["cond_ids"].to(dev))
+    b16 = lambda x: x.to(torch.bfloat16).to(dev)  # noqa: E731
+    plan.prepare(b16(inp["pe"]), b16(inp["pooled"]), b16(inp["cond"]), [t for t in MR.GPU_DIT_TS for _ in range(B)],
+                 [3.5] * B, c_t=0.0)
+    for s in range(T):
+        got = plan.step(s, b16(inp["lat"]))
+        torch.cuda.synchronize()
+        ref = torch.from_numpy(gold[f"gpudit_{variant}_s{s}/full"]).to(dev)
+        r = _rel(got, ref)
+        print(f"\n[reference fixture {variant} step {s}] relL2 native vs reference {r:.4g}")
+        assert r <= 2e-2, (variant, s, r)
