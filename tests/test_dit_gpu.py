@@ -205,3 +205,52 @@ def test_dit_forward_vs_reference_fixture(variant):
         r = _rel(got, ref)
         print(f"\n[reference fixture {variant} step {s}] relL2 native vs reference {r:.4g}")
         assert r <= 2e-2, (variant, s, r)
+
+
+@pytest.mark.parametrize("res,B", [(512, 4), (1024, 1)])
+def test_dit_full_width_geometry(res, B):
+    """BASELINE.json configs[2] / configs[3] geometry at FULL FLUX width (24 heads, D=3072, joint 4096, 512 text tokens;
+    512^2 with 4 edits per GPU, and 1024^2 -> S = 512 + 4096 + 4096), one double + one single block deep so the fp32
+    oracle (run on the GPU) stays cheap.  Same tolerance as the tiny cases; also checks linearity of the final
+    projection through a size-independent property: identical batch elements give identical rows."""
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights
+
+    dev = "cuda"
+    kw = dict(num_layers=1, num_single_layers=1)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=1234, dtype=torch.float32, device="cpu", w_std=0.02, bias_std=0.02, lora_b_std=0.02)
+    Pb = {k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}
+    P32 = {k: v.float() for k, v in Pb.items()}
+    del P
+    side = res // 16
+    nt, ni = 512, side * side
+    g = torch.Generator().manual_seed(5)
+    lat1 = torch.randn(1, ni, 64, generator=g).bfloat16()
+    cond1 = torch.randn(1, ni, 64, generator=g).bfloat16()
+    pe1 = (torch.randn(1, nt, 4096, generator=g) * 0.1).bfloat16()
+    po1 = torch.randn(1, 768, generator=g).bfloat16()
+    # batch element 0 and the last one are identical; the middle ones differ
+    def batch(x):
+        if B == 1:
+            return x.to(dev)
+        mid = torch.randn(B - 2, *x.shape[1:], generator=g).bfloat16() * x.float().std().bfloat16()
+        return torch.cat([x, mid, x], 0).to(dev)
+    inp = dict(lat=batch(lat1), cond=batch(cond1), pe=batch(pe1), pooled=batch(po1), img_ids=_ids(side, side).to(dev),
+               cond_ids=_ids(side, side, -side).to(dev), txt_ids=torch.zeros(nt, 3).to(dev), guidance=3.5)
+    plan = DitPlan(DitWeights(Pb, cfg, dev), B, nt, ni, ni, T=1)
+    plan.set_ids(inp["txt_ids"], inp["img_ids"], inp["cond_ids"])
+    t = 0.7
+    plan.prepare(inp["pe"], inp["pooled"], inp["cond"], [t] * B, [3.5] * B, c_t=0.0)
+    got = plan.step(0, inp["lat"])
+    torch.cuda.synchronize()
+    assert got.shape == (B, ni, 64) and torch.isfinite(got.float()).all()
+    if B > 1:
+        assert torch.equal(got[0], got[-1]), "identical edits in one batch must give identical rows"
+    with torch.no_grad():
+        ref32 = _oracle_full(O, ocfg, P32, inp, t, torch.float32)
+        ref16 = _oracle_full(O, ocfg, Pb, inp, t, torch.bfloat16)
+    e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
+    print(f"\n[full width {res}^2 B={B}] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
+    assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (res, B, e_nat, e_bf)
