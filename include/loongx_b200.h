@@ -338,6 +338,56 @@ typedef struct lx_duan_weights {
 int lx_duan_forward(const lx_duan_weights_t* w, const float* x, const float* c, float* y, int64_t y_bstride, int32_t B,
                     int32_t C, int32_t L, float keep_ratio, float* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Training step (OminiModel.step, src/train/model.py:569-729): rectified-flow objective around tranformer_forward with
+ * gradients for the LoRA factors.  The forward runs block.py:179-339 un-fused where the backward needs an intermediate
+ * (pre-norm q/k/v, pre-GELU hidden, pre-gate projection outputs); dX of every Linear is lx_gemm_bf16 against the
+ * transposed weight panel.  Rows / tile_meta as above; per-stream vectors are `p[stream] + batch*stride[stream]`.
+ * ------------------------------------------------------------------------------------------------------ */
+/* GELU(tanh) and its derivative on bf16 [rows, cols] views (FeedForward act / act_mlp, block.py:258-265, 302). */
+int lx_gelu_fwd(const void* pre, int64_t ld_pre, void* out, int64_t ldo, int32_t rows, int32_t cols, void* stream);
+int lx_gelu_bwd(const void* pre, int64_t ld_pre, const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int32_t rows,
+                int32_t cols, void* stream);
+/* out = res + gate[stream,batch] * y (block.py:224-234, 268-274, 328-334) and its backward:
+ * dy = gate * dout; dgate[stream][batch, col] += sum_rows dout * y (fp32, skipped for NULL streams). */
+int lx_gate_residual_fwd(const void* res, const void* y, void* out, int64_t ld, int32_t rows, int32_t D,
+                         const lx_tile_meta_t* tile_meta, const void* const gate[3], const int64_t gate_stride[3],
+                         void* stream);
+int lx_gate_bwd(const void* dout, const void* y, void* dy, int64_t ld, int32_t rows, int32_t D,
+                const lx_tile_meta_t* tile_meta, const void* const gate[3], const int64_t gate_stride[3],
+                float* const dgate[3], const int64_t dgate_stride[3], void* stream);
+/* Backward of lx_ln_modulate: dx = dres + dLN(dxn * (1 + scale)) (dres may be NULL); dscale / dshift[stream][batch, col]
+ * accumulate in fp32 (NULL = skip).  stats_workspace: fp32 [rows, 2] (needed when any dscale / dshift is given). */
+int lx_ln_modulate_bwd(const void* x, const void* dxn, const void* dres, void* dx, int64_t ld, int32_t rows, int32_t D,
+                       const lx_tile_meta_t* tile_meta, const void* const scale[3], const int64_t scale_stride[3],
+                       float* const dscale[3], float* const dshift[3], const int64_t dstride[3], float eps,
+                       float* stats_workspace, void* stream);
+/* q/k/v post-processing of attn_forward (block.py:34-41, 60-67, 74-99): qkv_pre rows [rows, >= 3*heads*128] ->
+ * per-head RMSNorm(q,k)*w, RoPE, scatter to [B,H,S,128]; and its backward (dq/dk/dv head-major -> rows). */
+int lx_qkv_post_fwd(const void* qkv_pre, int64_t ld, int32_t rows, int32_t heads, const lx_tile_meta_t* tile_meta, void* q,
+                    void* k, void* v, int32_t seq_total, const float* const rms_q[3], const float* const rms_k[3],
+                    const float* rope, float eps, void* stream);
+int lx_qkv_post_bwd(const void* qkv_pre, int64_t ld, const void* dq, const void* dk, const void* dv, void* dqkv_pre,
+                    int64_t ldo, int32_t rows, int32_t heads, const lx_tile_meta_t* tile_meta, int32_t seq_total,
+                    const float* const rms_q[3], const float* const rms_k[3], const float* rope, float eps, void* stream);
+/* rows [rows, ld] with head h in columns [128h, 128h+128) -> [B,H,S,128] (inverse of the attention output layout). */
+int lx_rows_to_heads(const void* rows_in, int64_t ld, void* heads_out, int32_t rows, int32_t heads,
+                     const lx_tile_meta_t* tile_meta, int32_t seq_total, void* stream);
+/* peft LoRA Linear gradients: dA[r,K] += s (dy B)^T x, dB[N,r] += s dy^T (x A^T) for bf16 x [M,K],
+ * dy [M,N] and fp32 factors A [r,K], B [N,r] (r <= 16).  workspace: fp32 [2*M*r]. */
+int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t ldy, const float* A, const float* Bw, float* dA,
+                 float* dB, int32_t M, int32_t K, int32_t N, int32_t r, float scaling, float* workspace, void* stream);
+/* out = bf16(W + s B A): the merged panel of the LoRA-active row group, rebuilt after every optimizer step. */
+int lx_lora_merge(const void* W, int64_t ldw, const float* A, const float* Bw, void* out, int64_t ldo, int32_t N, int32_t K,
+                  int32_t r, float scaling, void* stream);
+/* out[c, r] = in[r, c] (bf16): K-major W^T panels for the dX GEMMs. */
+int lx_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols, void* stream);
+/* Rectified-flow objective (model.py:590-594, 726): x_t = (1 - t_b) x_0 + t_b x_1;
+ * loss += mean((pred - (x_1 - x_0))^2) (loss must be zeroed), dpred = grad_scale * 2 (pred - target) / n (may be NULL). */
+int lx_flow_noise_mix(const void* x0, const void* x1, const float* t, void* xt, int32_t B, int64_t per_sample, void* stream);
+int lx_flow_mse_loss(const void* pred, const void* x0, const void* x1, float* loss, void* dpred, int64_t n,
+                     float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

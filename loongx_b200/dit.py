@@ -106,10 +106,19 @@ def random_params(cfg: FluxConfig, device, seed: int = 1234, w_std: float = 0.02
 
 
 class PackedLinear:
-    """One (possibly fused / stacked) Linear in the native layout; keeps the tensors alive."""
+    """One (possibly fused / stacked) Linear in the native layout; keeps the tensors alive.
 
-    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], w_lora: Optional[torch.Tensor]):
+    `lora` lists the LoRA-targeted sub-Linears of the panel as (name, first_row, rows, A fp32 [r, K], B fp32 [rows, r]);
+    the training step (loongx_b200/train.py) differentiates w.r.t. those factors, re-merges `w_lora` after an optimizer
+    step and multiplies by the transposed panels `wT` / `w_loraT` in the dX GEMMs."""
+
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], w_lora: Optional[torch.Tensor], lora=None,
+                 scaling: float = 1.0):
         self.w, self.bias, self.w_lora = w, bias, w_lora
+        self.lora = lora or []
+        self.scaling = scaling
+        self.wT: Optional[torch.Tensor] = None
+        self.w_loraT: Optional[torch.Tensor] = None
 
     def c(self) -> LxLinear:
         s = LxLinear()
@@ -128,25 +137,28 @@ def pack_linear(P: Dict[str, torch.Tensor], names: Sequence[str], cfg: FluxConfi
     get = (lambda key: P.pop(key)) if pop else (lambda key: P[key])
     has_lora = any((n + ".lora_A.weight") in P for n in names)
     has_bias = (names[0] + ".bias") in P
-    ws, merged = [], []
+    ws, merged, factors = [], [], []
+    row0, scaling = 0, 1.0
     for n in names:
         lora = (n + ".lora_A.weight") in P
         w = get(n + ".weight").to(device=device, dtype=torch.bfloat16)
         ws.append(w)
         if has_lora:
             if lora:
-                a = get(n + ".lora_A.weight").to(device=device, dtype=torch.float32)
-                b = get(n + ".lora_B.weight").to(device=device, dtype=torch.float32)
+                a = get(n + ".lora_A.weight").to(device=device, dtype=torch.float32).contiguous()
+                b = get(n + ".lora_B.weight").to(device=device, dtype=torch.float32).contiguous()
                 scaling = cfg.lora_alpha / a.shape[0]
                 merged.append(torch.addmm(w.float(), b, a, alpha=scaling).to(torch.bfloat16))
+                factors.append((n, row0, w.shape[0], a, b))
             else:
                 merged.append(w)
+        row0 += w.shape[0]
     bias = torch.cat([get(n + ".bias").to(device=device, dtype=torch.float32) for n in names]) if has_bias else None
     w = torch.cat(ws, 0).contiguous() if len(ws) > 1 else ws[0].contiguous()
     w_lora = None
     if has_lora:
         w_lora = torch.cat(merged, 0).contiguous() if len(merged) > 1 else merged[0].contiguous()
-    return PackedLinear(w, bias, w_lora)
+    return PackedLinear(w, bias, w_lora, factors, scaling)
 
 
 class DitWeights:
@@ -160,6 +172,7 @@ class DitWeights:
         pk = lambda names, **kw: pack_linear(P, names, cfg, dev, pop=consume, **kw)  # noqa: E731
         f32 = lambda key: (P.pop(key) if consume else P[key]).to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
         self.keep: List[object] = []
+        self.named: Dict[str, PackedLinear] = {}  # "x_embedder", "double.3.qkv", "single.7.proj_out", ... -> panel
         m = LxDitModel()
         m.num_layers, m.num_single_layers = cfg.num_layers, cfg.num_single_layers
         m.heads, m.in_channels = cfg.num_attention_heads, cfg.in_channels
@@ -170,6 +183,7 @@ class DitWeights:
 
         def put(field: str, pl: PackedLinear):
             self.keep.append(pl)
+            self.named[field] = pl
             setattr(m, field, pl.c())
 
         put("x_embedder", pk(["x_embedder"]))
@@ -200,10 +214,12 @@ class DitWeights:
             ):
                 pl = pk(names)
                 self.keep.append(pl)
+                self.named[f"double.{i}.{field}"] = pl
                 setattr(blk, field, pl.c())
             for field in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
                 t = f32(p + f"attn.{field}.weight")
                 self.keep.append(t)
+                self.named[f"double.{i}.{field}"] = t
                 setattr(blk, field, t.data_ptr())
         self.sgl = (LxSingleBlock * max(cfg.num_single_layers, 1))()
         for i in range(cfg.num_single_layers):
@@ -211,13 +227,16 @@ class DitWeights:
             blk = self.sgl[i]
             pl = pk([p + "attn.to_q", p + "attn.to_k", p + "attn.to_v", p + "proj_mlp"])
             self.keep.append(pl)
+            self.named[f"single.{i}.qkv_mlp"] = pl
             blk.qkv_mlp = pl.c()
             pl = pk([p + "proj_out"])
             self.keep.append(pl)
+            self.named[f"single.{i}.proj_out"] = pl
             blk.proj_out = pl.c()
             for field in ("norm_q", "norm_k"):
                 t = f32(p + f"attn.{field}.weight")
                 self.keep.append(t)
+                self.named[f"single.{i}.{field}"] = t
                 setattr(blk, field, t.data_ptr())
         m.double_blocks = C.cast(self.dbl, c_void_p)
         m.single_blocks = C.cast(self.sgl, c_void_p)

@@ -1,0 +1,539 @@
+"""Training step of the LoongX DiT (reference: OminiModel.step, src/train/model.py:569-729, around tranformer_forward with
+`gradient_checkpointing`, transformer.py:138-228): rectified-flow loss and the gradients of the LoRA factors — the
+parameters the reference's optimizer trains (`self.trainable_params = self.lora_layers`, model.py:541).
+
+Python here is launch sequencing and pointer plumbing only; every arithmetic step is a native kernel behind the C ABI:
+
+  forward   block.py:179-339 with the epilogue fusions undone where the backward needs an intermediate: tcgen05 GEMMs
+            (plain bias epilogue), lx_qkv_post_fwd, the tcgen05 attention kernel, lx_gate_residual_fwd, lx_gelu_fwd,
+            lx_ln_modulate.  The residual stream entering each block is checkpointed; the block is recomputed in the
+            backward (the reference's torch.utils.checkpoint per block).
+  backward  dX of every Linear = the same tcgen05 GEMM against the transposed weight panel (row groups: text rows ->
+            *_context^T, image rows -> W^T, condition rows -> (W + sBA)^T); lx_gate_bwd, lx_gelu_bwd, lx_ln_modulate_bwd,
+            lx_qkv_post_bwd, lx_lora_grad, lx_flow_mse_loss.
+  LIBRARY CALL (interim, flagged in DESIGN.md): dQ/dK/dV of the joint attention come from torch's
+            scaled_dot_product_attention backward; a tcgen05 attention-backward kernel replaces `sdpa_backward_library`
+            in the next round.
+
+Scope of the gradients: LoRA A / B of every target of train/config/seed_512.yaml:38 on the condition branch
+(`latent_lora=False`, the shipped configuration).  The CS3 / DGF encoders run forward-only (they are not in the
+reference's optimizer parameter list).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .dit import DitPlan, DitWeights, LxDitPlan, PackedLinear, _stream, mask_mode_from_config
+
+c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_P3 = c_void_p * 3
+_I3 = c_int64 * 3
+_lib = L.lib
+
+
+class LnModDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("ldx", c_int64), ("out", c_void_p), ("ldo", c_int64), ("rows", c_int32), ("D", c_int32),
+                ("tile_meta", c_void_p), ("shift", _P3), ("scale", _P3), ("stride", _I3), ("eps", c_float),
+                ("reserved", c_int32)]
+
+
+_lib.lx_ln_modulate.argtypes = [C.POINTER(LnModDesc), c_void_p]
+_lib.lx_gelu_fwd.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p]
+_lib.lx_gelu_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p]
+_lib.lx_gate_residual_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, _P3, _I3, c_void_p]
+_lib.lx_gate_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, _P3, _I3, _P3, _I3, c_void_p]
+_lib.lx_ln_modulate_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, _P3, _I3,
+                                    _P3, _P3, _I3, c_float, c_void_p, c_void_p]
+_lib.lx_qkv_post_fwd.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, _P3,
+                                 _P3, c_void_p, c_float, c_void_p]
+_lib.lx_qkv_post_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                 c_void_p, c_int32, _P3, _P3, c_void_p, c_float, c_void_p]
+_lib.lx_rows_to_heads.argtypes = [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]
+_lib.lx_lora_grad.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                              c_int32, c_int32, c_float, c_void_p, c_void_p]
+_lib.lx_lora_merge.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
+                               c_void_p]
+_lib.lx_transpose_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p]
+_lib.lx_flow_noise_mix.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]
+_lib.lx_flow_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]
+_lib.lx_cast.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _vec3(vs) -> Tuple[_P3, _I3]:
+    """per-stream [B, n] views (row = batch element) -> (pointers, batch strides)."""
+    p, st = _P3(), _I3()
+    for i, v in enumerate(vs):
+        if v is not None:
+            assert v.stride(-1) == 1
+            p[i], st[i] = v.data_ptr(), v.stride(0)
+    return p, st
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin kernel wrappers (pointers + strides only)
+# ------------------------------------------------------------------------------------------------------------------
+def ln_modulate(x, out, tile_meta, shift, scale, eps=1e-6):
+    d = LnModDesc()
+    d.x, d.ldx, d.out, d.ldo = x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0)
+    d.rows, d.D = x.shape
+    d.tile_meta = tile_meta.data_ptr()
+    for i in range(3):
+        if shift[i] is not None:
+            assert shift[i].stride(0) == scale[i].stride(0)
+            d.shift[i], d.scale[i], d.stride[i] = shift[i].data_ptr(), scale[i].data_ptr(), shift[i].stride(0)
+    d.eps = eps
+    L.check(_lib.lx_ln_modulate(C.byref(d), _stream()), "lx_ln_modulate")
+
+
+def gelu_fwd(pre, out):
+    L.check(_lib.lx_gelu_fwd(pre.data_ptr(), pre.stride(0), out.data_ptr(), out.stride(0), pre.shape[0], pre.shape[1],
+                             _stream()), "lx_gelu_fwd")
+
+
+def gelu_bwd(pre, dy, dx):
+    L.check(_lib.lx_gelu_bwd(pre.data_ptr(), pre.stride(0), dy.data_ptr(), dy.stride(0), dx.data_ptr(), dx.stride(0),
+                             pre.shape[0], pre.shape[1], _stream()), "lx_gelu_bwd")
+
+
+def gate_residual_fwd(res, y, out, tile_meta, gate):
+    assert res.stride(0) == y.stride(0) == out.stride(0)
+    gp, gs = _vec3(gate)
+    L.check(_lib.lx_gate_residual_fwd(res.data_ptr(), y.data_ptr(), out.data_ptr(), res.stride(0), res.shape[0], res.shape[1],
+                                      tile_meta.data_ptr(), gp, gs, _stream()), "lx_gate_residual_fwd")
+
+
+def gate_bwd(dout, y, dy, tile_meta, gate, dgate):
+    assert dout.stride(0) == y.stride(0) == dy.stride(0)
+    gp, gs = _vec3(gate)
+    dp, ds = _vec3(dgate)
+    L.check(_lib.lx_gate_bwd(dout.data_ptr(), y.data_ptr(), dy.data_ptr(), dout.stride(0), dout.shape[0], dout.shape[1],
+                             tile_meta.data_ptr(), gp, gs, dp, ds, _stream()), "lx_gate_bwd")
+
+
+def ln_modulate_bwd(x, dxn, dres, dx, tile_meta, scale, dscale, dshift, stats, eps=1e-6):
+    assert x.stride(0) == dxn.stride(0) == dx.stride(0) and (dres is None or dres.stride(0) == x.stride(0))
+    sp, ss = _vec3(scale)
+    dsp, dss = _vec3(dscale)
+    dhp, dhs = _vec3(dshift)
+    for i in range(3):
+        assert dscale[i] is None or dshift[i] is None or dss[i] == dhs[i]
+        dss[i] = dss[i] or dhs[i]
+    L.check(_lib.lx_ln_modulate_bwd(x.data_ptr(), dxn.data_ptr(), _ptr(dres), dx.data_ptr(), x.stride(0), x.shape[0],
+                                    x.shape[1], tile_meta.data_ptr(), sp, ss, dsp, dhp, dss, eps, _ptr(stats), _stream()),
+            "lx_ln_modulate_bwd")
+
+
+def _rms3(ws):
+    p = _P3()
+    for i, w in enumerate(ws):
+        if w is not None:
+            p[i] = w.data_ptr()
+    return p
+
+
+def qkv_post_fwd(pre, heads, tile_meta, q, k, v, rms_q, rms_k, rope, eps=1e-6):
+    L.check(_lib.lx_qkv_post_fwd(pre.data_ptr(), pre.stride(0), pre.shape[0], heads, tile_meta.data_ptr(), q.data_ptr(),
+                                 k.data_ptr(), v.data_ptr(), q.shape[2], _rms3(rms_q), _rms3(rms_k), _ptr(rope), eps,
+                                 _stream()), "lx_qkv_post_fwd")
+
+
+def qkv_post_bwd(pre, dq, dk, dv, dpre, heads, tile_meta, rms_q, rms_k, rope, eps=1e-6):
+    L.check(_lib.lx_qkv_post_bwd(pre.data_ptr(), pre.stride(0), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dpre.data_ptr(),
+                                 dpre.stride(0), pre.shape[0], heads, tile_meta.data_ptr(), dq.shape[2], _rms3(rms_q),
+                                 _rms3(rms_k), _ptr(rope), eps, _stream()), "lx_qkv_post_bwd")
+
+
+def rows_to_heads(rows, heads, tile_meta, out):
+    L.check(_lib.lx_rows_to_heads(rows.data_ptr(), rows.stride(0), out.data_ptr(), rows.shape[0], heads, tile_meta.data_ptr(),
+                                  out.shape[2], _stream()), "lx_rows_to_heads")
+
+
+def lora_grad(x, dy, A, Bw, dA, dB, scaling, workspace):
+    M, K = x.shape
+    N, r = Bw.shape
+    assert dy.shape == (M, N) and A.shape == (r, K) and dA.shape == A.shape and dB.shape == Bw.shape
+    assert A.is_contiguous() and Bw.is_contiguous() and dA.is_contiguous() and dB.is_contiguous()
+    assert A.dtype == Bw.dtype == dA.dtype == dB.dtype == torch.float32 and workspace.numel() >= 2 * M * r
+    L.check(_lib.lx_lora_grad(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), A.data_ptr(), Bw.data_ptr(),
+                              dA.data_ptr(), dB.data_ptr(), M, K, N, r, float(scaling), workspace.data_ptr(), _stream()),
+            "lx_lora_grad")
+
+
+def lora_merge(W, A, Bw, out, scaling):
+    N, K = W.shape
+    L.check(_lib.lx_lora_merge(W.data_ptr(), W.stride(0), A.data_ptr(), Bw.data_ptr(), out.data_ptr(), out.stride(0), N, K,
+                               A.shape[0], float(scaling), _stream()), "lx_lora_merge")
+
+
+def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((cols, rows), device=x.device, dtype=torch.bfloat16)
+    L.check(_lib.lx_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _stream()),
+            "lx_transpose_bf16")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.check(_lib.lx_cast(x.data_ptr(), out.data_ptr(), x.numel(), 1, _stream()), "lx_cast")
+    return out
+
+
+def flow_noise_mix(x0, x1, t):
+    xt = torch.empty_like(x0)
+    L.check(_lib.lx_flow_noise_mix(x0.data_ptr(), x1.data_ptr(), t.data_ptr(), xt.data_ptr(), x0.shape[0],
+                                   x0.numel() // x0.shape[0], _stream()), "lx_flow_noise_mix")
+    return xt
+
+
+def flow_mse_loss(pred, x0, x1, loss, dpred, grad_scale=1.0):
+    L.check(_lib.lx_flow_mse_loss(pred.data_ptr(), x0.data_ptr(), x1.data_ptr(), loss.data_ptr(), _ptr(dpred), pred.numel(),
+                                  float(grad_scale), _stream()), "lx_flow_mse_loss")
+
+
+def sdpa_backward_library(q, k, v, d_out, n_cond: int, mask_mode: int, cross_bias: float):
+    """LIBRARY CALL (interim): dQ, dK, dV of softmax(q k^T / sqrt(128) + mask) v through torch's
+    scaled_dot_product_attention autograd, with the block masks / c_factor bias of block.py:106-128."""
+    import torch.nn.functional as F
+
+    S = q.shape[2]
+    mask = None
+    if n_cond > 0:
+        if cross_bias != 0.0:
+            mask = torch.zeros(S, S, device=q.device, dtype=q.dtype)
+            mask[-n_cond:, :-n_cond] = cross_bias
+            mask[:-n_cond, -n_cond:] = cross_bias
+        elif mask_mode == 1:
+            mask = torch.ones(S, S, device=q.device, dtype=torch.bool)
+            mask[-n_cond:, :-n_cond] = False
+            mask[:-n_cond, -n_cond:] = False
+        elif mask_mode == 2:
+            mask = torch.ones(S, S, device=q.device, dtype=torch.bool)
+            mask[-n_cond:, :-n_cond] = False
+    with torch.enable_grad():
+        q_, k_, v_ = (t.detach().requires_grad_(True) for t in (q, k, v))
+        o = F.scaled_dot_product_attention(q_, k_, v_, attn_mask=mask, dropout_p=0.0, is_causal=False)
+        return torch.autograd.grad(o, (q_, k_, v_), d_out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# trainable LoRA factors
+# ------------------------------------------------------------------------------------------------------------------
+class LoraFactor:
+    """One LoRA-targeted Linear: fp32 master factors living inside a PackedLinear panel."""
+
+    def __init__(self, name: str, panel: PackedLinear, row0: int, rows: int, A: torch.Tensor, Bw: torch.Tensor):
+        self.name, self.panel, self.row0, self.rows = name, panel, row0, rows
+        self.A = torch.nn.Parameter(A, requires_grad=True)
+        self.B = torch.nn.Parameter(Bw, requires_grad=True)
+        self.dA = torch.zeros_like(A)
+        self.dB = torch.zeros_like(Bw)
+
+    def remerge(self):
+        """w_lora[rows] = bf16(W + s B A) (+ the transposed panel) after the factors changed."""
+        p = self.panel
+        lora_merge(p.w[self.row0:self.row0 + self.rows], self.A.data, self.B.data,
+                   p.w_lora[self.row0:self.row0 + self.rows], p.scaling)
+        if p.w_loraT is not None:
+            transpose(p.w_lora[self.row0:self.row0 + self.rows], p.w_loraT[:, self.row0:self.row0 + self.rows])
+
+
+class DitTrainer:
+    """Native forward + backward of the rectified-flow objective for one batch geometry."""
+
+    def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, model_config: Optional[dict] = None):
+        model_config = model_config or {}
+        if model_config.get("latent_lora", False):
+            raise NotImplementedError("training with model_config.latent_lora=True (LoRA gradients from the image rows)")
+        if n_cond <= 0:
+            raise NotImplementedError("the training step needs a condition stream (the LoRA lives on the condition branch)")
+        self.w, self.cfg = weights, weights.cfg
+        self.plan = DitPlan(weights, B, n_txt, n_img, n_cond, T=1, model_config=model_config)
+        self.B, self.nt, self.ni, self.nc = B, n_txt, n_img, n_cond
+        cfg = self.cfg
+        self.D, self.H = cfg.inner_dim, cfg.num_attention_heads
+        D, dev = self.D, weights.device
+        S = n_txt + n_img + n_cond
+        self.S, self.R = S, B * S
+        self.Rt, self.Ri, self.Rc = B * n_txt, B * n_img, B * n_cond
+        R = self.R
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        z = lambda *s: torch.zeros(s, **bf)  # noqa: E731
+        self.a = dict(XN=self.plan.buf["XN"], QM=z(R, 7 * D), Cat=z(R, 5 * D), Y1=z(R, D), X1=z(R, D), XN2=z(R, D),
+                      Hid=z(R, 4 * D), Y2=z(R, D))
+        self.g = dict(dX=z(R, D), dX1=z(R, D), dY=z(R, D), dXN=z(R, D), dBig=z(R, 7 * D), dCat=z(R, 5 * D),
+                      dOh=z(B, self.H, S, 128))
+        self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
+        self.lora_ws = torch.zeros((2 * max(self.Rc, B) * max(cfg.lora_rank, 1),), device=dev, dtype=torch.float32)
+        self.ckpt = torch.zeros((cfg.num_layers + cfg.num_single_layers, R, D), **bf)
+        self.dmod_dbl = torch.zeros((B, max(cfg.num_layers, 1) * 6 * D), device=dev, dtype=torch.float32)
+        self.dmod_sgl = torch.zeros((B, max(cfg.num_single_layers, 1) * 3 * D), device=dev, dtype=torch.float32)
+        self.loss = torch.zeros((1,), device=dev, dtype=torch.float32)
+        self.factors: Dict[str, LoraFactor] = {}
+        for key, panel in weights.named.items():
+            if not isinstance(panel, PackedLinear):
+                continue
+            for (name, row0, rows, A, Bw) in panel.lora:
+                self.factors[name] = LoraFactor(name, panel, row0, rows, A, Bw)
+        self._ensure_transposed()
+        self._saved = None
+
+    # -- weights -----------------------------------------------------------------------------------------------------
+    def _ensure_transposed(self):
+        for key, p in self.w.named.items():
+            if not isinstance(p, PackedLinear) or not (key.startswith("double.") or key.startswith("single.") or key == "proj_out"):
+                continue
+            if p.wT is None:
+                p.wT = transpose(p.w)
+            if p.w_lora is not None and p.w_loraT is None:
+                p.w_loraT = transpose(p.w_lora)
+
+    def parameters(self) -> List[torch.nn.Parameter]:
+        out = []
+        for f in self.factors.values():
+            out += [f.A, f.B]
+        return out
+
+    def named_parameters(self):
+        for n, f in self.factors.items():
+            yield n + ".lora_A.weight", f.A
+            yield n + ".lora_B.weight", f.B
+
+    def remerge(self):
+        """Call after an optimizer step: rebuild every merged panel from the updated factors."""
+        for f in self.factors.values():
+            f.remerge()
+
+    def zero_grad(self):
+        for f in self.factors.values():
+            f.dA.zero_()
+            f.dB.zero_()
+
+    # -- per-block helpers ---------------------------------------------------------------------------------------------
+    def _mods_double(self, i):
+        """six [B, D] chunk views per stream of block i: [shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp]."""
+        D, b = self.D, self.plan.buf
+        sl = lambda t, c: t[:, (i * 6 + c) * D:(i * 6 + c + 1) * D]  # noqa: E731
+        return [[sl(b["mod_txt"], c), sl(b["mod_img"], c), sl(b["mod_cond_img"], c)] for c in range(6)]
+
+    def _mods_single(self, i):
+        D, b = self.D, self.plan.buf
+        sl = lambda t, c: t[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]  # noqa: E731
+        return [[sl(b["mod_single"], c), sl(b["mod_single"], c), sl(b["mod_cond_single"], c)] for c in range(3)]
+
+    def _groups(self, main: PackedLinear, ctx: Optional[PackedLinear], transposed: bool):
+        """row groups of a GEMM over all R rows -> (W0, bias0, extra groups)."""
+        pick = (lambda p, lora: (p.w_loraT if lora and p.w_loraT is not None else p.wT)) if transposed else \
+               (lambda p, lora: (p.w_lora if lora and p.w_lora is not None else p.w))
+        bias = (lambda p: None) if transposed else (lambda p: p.bias)
+        if ctx is not None:  # double block: [txt | img | cond]
+            return pick(ctx, False), bias(ctx), [(pick(main, False), bias(main), self.Rt),
+                                                 (pick(main, True), bias(main), self.Rt + self.Ri)]
+        return pick(main, False), bias(main), [(pick(main, True), bias(main), self.Rt + self.Ri)]  # single: [txt+img | cond]
+
+    def _gemm(self, A, main, ctx, out, transposed=False):
+        W0, b0, extra = self._groups(main, ctx, transposed)
+        ops.gemm(A, W0, b0, out, L.EPI_BIAS, groups=extra)
+
+    def _lora_grads(self, names, x_rows, dy_rows, col0=0):
+        """accumulate dA / dB of consecutive sub-Linears `names` whose outputs are adjacent column blocks of dy_rows."""
+        c = col0
+        for n in names:
+            f = self.factors.get(n)
+            width = f.rows if f is not None else None
+            if f is None:
+                raise KeyError(n)
+            lora_grad(x_rows, dy_rows[:, c:c + width], f.A.data, f.B.data, f.dA, f.dB, f.panel.scaling, self.lora_ws)
+            c += width
+
+    def _attention(self, out):
+        """out: [R, ld] view; head h lands in columns [128h, 128h+128)."""
+        b, p = self.plan.buf, self.plan.plan
+        ops.attention(b["Q"], b["K"], b["V"], out, b["out_row_base"], n_cond=self.nc, mask_mode=p.mask_mode,
+                      cross_bias=p.cross_bias)
+
+    def _attention_bwd(self, d_rows):
+        """d_rows: [R, >= D] view holding dO in its first D columns -> dq, dk, dv head-major."""
+        b, p = self.plan.buf, self.plan.plan
+        rows_to_heads(d_rows, self.H, b["tile_meta"], self.g["dOh"])
+        return sdpa_backward_library(b["Q"], b["K"], b["V"], self.g["dOh"], self.nc, p.mask_mode, p.cross_bias)
+
+    # -- blocks -------------------------------------------------------------------------------------------------------
+    def _double_fwd(self, i):
+        b, a, D, W = self.plan.buf, self.a, self.D, self.w.named
+        X, tm = b["X"], b["tile_meta"]
+        m = self._mods_double(i)
+        pre = a["QM"][:, :3 * D]
+        ln_modulate(X, a["XN"], tm, m[0], m[1])
+        self._gemm(a["XN"], W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], pre)
+        nq, nk, naq, nak = (W[f"double.{i}.{n}"] for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
+        qkv_post_fwd(pre, self.H, tm, b["Q"], b["K"], b["V"], [naq, nq, nq], [nak, nk, nk], b["rope"])
+        O = a["Cat"][:, :D]
+        self._attention(O)
+        self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
+        gate_residual_fwd(X, a["Y1"], a["X1"], tm, m[2])
+        ln_modulate(a["X1"], a["XN2"], tm, m[3], m[4])
+        pre_ff = a["QM"][:, 3 * D:7 * D]
+        self._gemm(a["XN2"], W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], pre_ff)
+        gelu_fwd(pre_ff, a["Hid"])
+        self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], a["Y2"])
+        gate_residual_fwd(a["X1"], a["Y2"], X, tm, m[5])
+
+    def _double_bwd(self, i, x_in):
+        """gradient wrt the block output is in g['dX']; leaves the gradient wrt the block input there."""
+        b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
+        tm = b["tile_meta"]
+        m = self._mods_double(i)
+        c0 = self.Rt + self.Ri  # first condition row
+        dm = lambda c: [None, None, self.dmod_dbl[:, (i * 6 + c) * D:(i * 6 + c + 1) * D]]  # noqa: E731
+        pfx = f"transformer_blocks.{i}."
+        pre, pre_ff = a["QM"][:, :3 * D], a["QM"][:, 3 * D:7 * D]
+        O = a["Cat"][:, :D]
+        # feed-forward branch
+        gate_bwd(g["dX"], a["Y2"], g["dY"], tm, m[5], dm(5))
+        self._lora_grads([pfx + "ff.net.2"], a["Hid"][c0:], g["dY"][c0:])
+        d_hid = g["dBig"][:, :4 * D]
+        self._gemm(g["dY"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], d_hid, transposed=True)
+        gelu_bwd(pre_ff, d_hid, d_hid)
+        self._gemm(d_hid, W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], g["dXN"], transposed=True)
+        ln_modulate_bwd(a["X1"], g["dXN"], g["dX"], g["dX1"], tm, m[4], dm(4), dm(3), self.stats)
+        # attention branch
+        gate_bwd(g["dX1"], a["Y1"], g["dY"], tm, m[2], dm(2))
+        self._lora_grads([pfx + "attn.to_out.0"], O[c0:], g["dY"][c0:])
+        d_o = g["dCat"][:, :D]
+        self._gemm(g["dY"], W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], d_o, transposed=True)
+        dq, dk, dv = self._attention_bwd(d_o)
+        nq, nk, naq, nak = (W[f"double.{i}.{n}"] for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
+        d_pre = g["dBig"][:, :3 * D]
+        qkv_post_bwd(pre, dq, dk, dv, d_pre, self.H, tm, [naq, nq, nq], [nak, nk, nk], b["rope"])
+        self._lora_grads([pfx + "attn.to_q", pfx + "attn.to_k", pfx + "attn.to_v"], a["XN"][c0:], d_pre[c0:])
+        self._gemm(d_pre, W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], g["dXN"], transposed=True)
+        ln_modulate_bwd(x_in, g["dXN"], g["dX1"], g["dX"], tm, m[1], dm(1), dm(0), self.stats)
+
+    def _single_fwd(self, i):
+        b, a, D, W = self.plan.buf, self.a, self.D, self.w.named
+        X, tm = b["X"], b["tile_meta"]
+        m = self._mods_single(i)
+        ln_modulate(X, a["XN"], tm, m[0], m[1])
+        self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"])
+        nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
+        qkv_post_fwd(a["QM"], self.H, tm, b["Q"], b["K"], b["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
+        gelu_fwd(a["QM"][:, 3 * D:], a["Cat"][:, D:])
+        self._attention(a["Cat"])
+        self._gemm(a["Cat"], W[f"single.{i}.proj_out"], None, a["Y1"])
+        gate_residual_fwd(X, a["Y1"], X, tm, m[2])
+
+    def _single_bwd(self, i, x_in):
+        b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
+        tm = b["tile_meta"]
+        m = self._mods_single(i)
+        c0 = self.Rt + self.Ri
+        dm = lambda c: [None, None, self.dmod_sgl[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]]  # noqa: E731
+        pfx = f"single_transformer_blocks.{i}."
+        gate_bwd(g["dX"], a["Y1"], g["dY"], tm, m[2], dm(2))
+        self._lora_grads([pfx + "proj_out"], a["Cat"][c0:], g["dY"][c0:])
+        self._gemm(g["dY"], W[f"single.{i}.proj_out"], None, g["dCat"], transposed=True)
+        gelu_bwd(a["QM"][:, 3 * D:], g["dCat"][:, D:], g["dBig"][:, 3 * D:])
+        dq, dk, dv = self._attention_bwd(g["dCat"])
+        nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
+        qkv_post_bwd(a["QM"], dq, dk, dv, g["dBig"], self.H, tm, [nq, nq, nq], [nk, nk, nk], b["rope"])
+        self._lora_grads([pfx + "attn.to_q", pfx + "attn.to_k", pfx + "attn.to_v", pfx + "proj_mlp"], a["XN"][c0:],
+                         g["dBig"][c0:])
+        self._gemm(g["dBig"], W[f"single.{i}.qkv_mlp"], None, g["dXN"], transposed=True)
+        ln_modulate_bwd(x_in, g["dXN"], g["dX"], g["dX"], tm, m[1], dm(1), dm(0), self.stats)  # in place: row-local
+
+    # -- public ---------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x0, x1, t, cond_latents, prompt_embeds, pooled, txt_ids, img_ids, cond_ids, guidance=1.0):
+        """x0, x1: bf16 [B, n_img, C] packed latents / noise; t: fp32 [B] in (0, 1) -> loss (fp32 [1] tensor).
+        model.py:590-594 (x_t), 705-723 (tranformer_forward), 726 (mse)."""
+        B, cfg, b, a = self.B, self.cfg, self.plan.buf, self.a
+        assert x0.dtype == torch.bfloat16 and x0.shape == (B, self.ni, cfg.in_channels) and x0.is_contiguous()
+        t = t.to(device=x0.device, dtype=torch.float32).contiguous()
+        xt = flow_noise_mix(x0, x1.contiguous(), t)
+        self.plan.set_ids(txt_ids, img_ids, cond_ids)
+        ts = [float(v) for v in t.tolist()]
+        self.plan.prepare(prompt_embeds, pooled, cond_latents, ts, [guidance] * B if cfg.guidance_embeds else None, c_t=0.0)
+        self.plan.embed(xt)
+        X = b["X"]
+        nl, ns = cfg.num_layers, cfg.num_single_layers
+        for i in range(nl):
+            self.ckpt[i].copy_(X)
+            self._double_fwd(i)
+        for i in range(ns):
+            self.ckpt[nl + i].copy_(X)
+            self._single_fwd(i)
+        # norm_out (scale first, then shift) + proj_out on the image rows (transformer.py:241-244)
+        Xi, XNi = X[self.Rt:self.Rt + self.Ri], a["XN"][self.Rt:self.Rt + self.Ri]
+        tm_i = b["tile_meta"][self.Rt // 128:]
+        mo = b["mod_out"]
+        sc, sh = mo[:, :self.D], mo[:, self.D:]
+        ln_modulate(Xi, XNi, tm_i, [sh, sh, sh], [sc, sc, sc])
+        pred = torch.empty((B, self.ni, cfg.in_channels), device=X.device, dtype=torch.bfloat16)
+        po = self.w.named["proj_out"]
+        ops.gemm(XNi, po.w, po.bias, pred.view(self.Ri, cfg.in_channels), L.EPI_BIAS)
+        self._saved = dict(x0=x0, x1=x1.contiguous(), pred=pred, cond_latents=cond_latents.to(torch.bfloat16).contiguous(),
+                           X_final=X.clone())
+        self.loss.zero_()
+        flow_mse_loss(pred, x0, self._saved["x1"], self.loss, None)
+        self.pred = pred
+        return self.loss
+
+    @torch.no_grad()
+    def backward(self, grad_scale: float = 1.0):
+        """Accumulates d loss / d (LoRA A, B) into LoraFactor.dA / dB (fp32)."""
+        assert self._saved is not None, "call forward() first"
+        s, b, a, g, cfg = self._saved, self.plan.buf, self.a, self.g, self.cfg
+        X, tm = b["X"], b["tile_meta"]
+        nl, ns = cfg.num_layers, cfg.num_single_layers
+        self.dmod_dbl.zero_()
+        self.dmod_sgl.zero_()
+        dpred = torch.empty_like(s["pred"])
+        scratch_loss = torch.zeros_like(self.loss)
+        flow_mse_loss(s["pred"], s["x0"], s["x1"], scratch_loss, dpred, grad_scale)
+        # proj_out / norm_out backward on the image rows; text and condition rows of the final stream get no gradient
+        g["dX"].zero_()
+        sl = slice(self.Rt, self.Rt + self.Ri)
+        po = self.w.named["proj_out"]
+        ops.gemm(dpred.view(self.Ri, cfg.in_channels), po.wT, None, g["dXN"][sl], L.EPI_BIAS)
+        mo = b["mod_out"]
+        sc = mo[:, :self.D]
+        ln_modulate_bwd(s["X_final"][sl], g["dXN"][sl], None, g["dX"][sl], tm[self.Rt // 128:], [sc, sc, sc],
+                        [None] * 3, [None] * 3, None)
+        for i in reversed(range(ns)):
+            X.copy_(self.ckpt[nl + i])
+            self._single_fwd(i)  # recompute (gradient checkpointing, transformer.py:184-206)
+            self._single_bwd(i, self.ckpt[nl + i])
+        for i in reversed(range(nl)):
+            X.copy_(self.ckpt[i])
+            self._double_fwd(i)
+            self._double_bwd(i, self.ckpt[i])
+        # x_embedder on the condition rows (transformer.py:93)
+        c0 = self.Rt + self.Ri
+        self._lora_grads(["x_embedder"], s["cond_latents"].view(self.Rc, cfg.in_channels), g["dX"][c0:])
+        # AdaLN linears of the condition stream: emb -> [B, 6D | 3D] per block, input silu(cond_temb)
+        silu_c = b["silu_c"]
+        dmd, dms = cast_bf16(self.dmod_dbl), cast_bf16(self.dmod_sgl)
+        for i in range(nl):
+            self._lora_grads([f"transformer_blocks.{i}.norm1.linear"], silu_c, dmd[:, i * 6 * self.D:(i + 1) * 6 * self.D])
+        for i in range(ns):
+            self._lora_grads([f"single_transformer_blocks.{i}.norm.linear"], silu_c,
+                             dms[:, i * 3 * self.D:(i + 1) * 3 * self.D])
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for n, f in self.factors.items():
+            out[n + ".lora_A.weight"] = f.dA
+            out[n + ".lora_B.weight"] = f.dB
+        return out

@@ -352,6 +352,8 @@ class FluxPipeline:
 
     def encode_prompt(self, prompt=None, prompt_2=None, prompt_embeds=None, pooled_prompt_embeds=None, device=None,
                       num_images_per_prompt=1, max_sequence_length=512, lora_scale=None):
+        if prompt_embeds is None and isinstance(prompt, tuple):  # (prompt_embeds, pooled) smuggled through `prompt`
+            prompt_embeds, pooled_prompt_embeds = prompt  # (model.py:585 passes batch["description"] to the text encoders)
         assert prompt_embeds is not None, "text encoders are out of scope: pass prompt_embeds"
         text_ids = torch.zeros(prompt_embeds.shape[1], 3).to(device=device, dtype=prompt_embeds.dtype)
         return prompt_embeds, pooled_prompt_embeds, text_ids

@@ -113,7 +113,7 @@ class _D1(nn.Module):
         return self.enc(flat.view(flat.shape[0], self.channels, -1))
 
 
-def ref_omini_model(nc: OC.NeuralConditioner):
+def ref_omini_model(nc: OC.NeuralConditioner, d1: bool = True):
     """An OminiModel (model.py:376) assembled WITHOUT its constructor (which downloads FLUX): the reference's own
     encoder / DUAN classes and its unbound methods, holding the parameters of the oracle conditioner `nc`."""
     M = R.ref_module("train.model")
@@ -126,7 +126,7 @@ def ref_omini_model(nc: OC.NeuralConditioner):
     for name, (cls, ch) in encs.items():
         enc = cls(**kw).eval()
         R.copy_module_params(enc, getattr(nc, name))
-        setattr(m, name, _D1(enc, ch))
+        setattr(m, name, _D1(enc, ch) if d1 else enc)
     for name, ch in dict(duan_norm1=512, duan_norm2=1, duan_norm_prompt=512, duan_norm_pooled=1).items():
         d = M.DUAN(channels=ch, **kw).eval()
         R.copy_module_params(d, getattr(nc, name))
@@ -235,6 +235,77 @@ def condition_id_cases(ref: bool):
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# training step (model.py:569-729): loss + LoRA gradients
+# ------------------------------------------------------------------------------------------------------------------
+STEP_CASES = {"text": dict(brain=False, fuse=True, seed=11), "brain_fuse1": dict(brain=True, fuse=True, seed=12),
+              "brain_fuse0": dict(brain=True, fuse=False, seed=13)}
+
+
+def step_batch(cfg, brain: bool, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    B, h, w = (1, 8, 16) if brain else (2, 8, 16)
+    nt = 512 if brain else 24
+    batch = dict(image=torch.randn(B, 16, h, w, generator=g), condition=torch.randn(B, 16, h, w, generator=g),
+                 prompt_embeds=torch.randn(B, nt, cfg.joint_attention_dim, generator=g) * 0.5,
+                 pooled_prompt_embeds=torch.randn(B, cfg.pooled_projection_dim, generator=g),
+                 position_delta=[[0, -(w // 2)]], condition_type=["subject"] * B)
+    if brain:
+        batch.update(signals(seed=seed + 100, B=B))
+    return batch
+
+
+def ref_step(cfg, P, batch, nc, brain: bool, fuse: bool, seed: int):
+    """The reference's OminiModel.step + loss.backward() on the CPU (stand-in pipeline / transformer, real step code)."""
+    model, M = ref_omini_model(nc, d1=False)
+    tr = R.build_transformer(P, cfg)
+    for n, p in tr.named_parameters():
+        p.requires_grad_(".lora_A." in n or ".lora_B." in n)
+    pipe = R.FluxPipeline(tr)
+    pipe.vae = R._PrecomputedVae(shift=0.0, scale=1.0)
+    pipe.image_processor = types.SimpleNamespace(preprocess=lambda z: z)
+    object.__setattr__(model, "flux_pipe", pipe)
+    object.__setattr__(model, "transformer", tr)
+    model.model_config, model.use_brain_condition, model.fuse_flag = {}, brain, fuse
+    model._dtype = torch.float32
+    type(model).device = property(lambda self: torch.device("cpu"))
+    b = dict(image=batch["image"], condition=batch["condition"], condition_type=batch["condition_type"],
+             description=(batch["prompt_embeds"], batch["pooled_prompt_embeds"]), position_delta=batch["position_delta"])
+    for k in ("eeg", "fnirs", "ppg", "motion"):
+        if k in batch:
+            b[k] = batch[k]
+    torch.manual_seed(seed)  # t = sigmoid(randn(B)); x_1 = randn_like(x_0)  (model.py:590-591)
+    loss = model.step(b)
+    loss.backward()
+    grads = {}
+    for n, p in tr.named_parameters():
+        if p.requires_grad:
+            key = n.replace(".default.weight", ".weight")
+            grads[key] = p.grad if p.grad is not None else torch.zeros_like(p)
+    return loss.detach(), grads
+
+
+def oracle_step(cfg, P, batch, nc, brain: bool, fuse: bool, seed: int):
+    from oracle import train_step as TS
+
+    torch.manual_seed(seed)
+    loss, grads, _ = TS.flow_step_grads(P, cfg, batch, model_config={}, conditioner=nc, use_brain_condition=brain,
+                                        fuse_flag=fuse)
+    return loss, grads
+
+
+def step_cases(ref: bool, nc) -> dict:
+    out = {}
+    for name, c in STEP_CASES.items():
+        cfg = O.FluxConfig(**(TINY_BRAIN if c["brain"] else TINY))
+        P = dit_params(cfg)
+        batch = step_batch(cfg, c["brain"], c["seed"])
+        loss, grads = (ref_step if ref else oracle_step)(cfg, P, batch, nc, c["brain"], c["fuse"], c["seed"])
+        out[f"step_{name}_loss"] = loss.reshape(1)
+        out[f"step_{name}_grads"] = torch.cat([grads[k].flatten() for k in sorted(grads)])
+    return out
+
+
 GPU_DIT_VARIANTS = {"default": {}, "independent": {"independent_condition": True}, "no_union": {"union_cond_attn": False}}
 GPU_DIT_TS = (0.9, 0.35)
 
@@ -281,6 +352,7 @@ def all_cases(ref: bool) -> dict:
                                                 use_brain_condition=True)
     res.update(condition_id_cases(ref))
     res.update(gpu_dit_cases(ref))
+    res.update(step_cases(ref, nc))
     return res
 
 

@@ -1,0 +1,294 @@
+"""GPU parity of the training step (a17: OminiModel.step, model.py:569-729): every backward / un-fused forward kernel
+against torch autograd of the same fp32 formula, then the whole native forward + backward (loss and LoRA-factor
+gradients) against the oracle restatement of the reference's step — which tests/test_reference_pins_cpu.py pins
+bit-for-bit to the reference's own `step()` + `loss.backward()`.
+
+Tolerances (bf16 storage of activations and activation gradients, fp32 accumulation): kernels relL2 <= 1e-2 against
+fp32 autograd on the same bf16-rounded inputs; end to end loss rel <= 2e-2, concatenated LoRA gradients relL2 <= 6e-2.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _geo(B=2, nt=128, ni=256, nc=128):
+    from loongx_b200 import ops
+
+    tm = ops.make_tile_meta(B, nt, ni, nc, DEV)
+    R = B * (nt + ni + nc)
+    return tm, R
+
+
+def _stream_batch_of_rows(tm, R):
+    t = tm.cpu()
+    stream = t[:, 0].repeat_interleave(128)[:R].to(DEV)
+    batch = t[:, 1].repeat_interleave(128)[:R].to(DEV)
+    return stream.long(), batch.long()
+
+
+def _rand(*s, scale=1.0, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(*s, generator=g, device=DEV) * scale).bfloat16()
+
+
+def test_gelu_fwd_bwd():
+    from loongx_b200 import train as T
+
+    x = _rand(256, 1024, scale=2.0)
+    dy = _rand(256, 1024, seed=1)
+    out = torch.empty_like(x)
+    T.gelu_fwd(x, out)
+    xf = x.float().requires_grad_(True)
+    ref = F.gelu(xf, approximate="tanh")
+    assert _rel(out, ref) < 5e-3
+    (gref,) = torch.autograd.grad(ref, xf, dy.float())
+    dx = torch.empty_like(x)
+    T.gelu_bwd(x, dy, dx)
+    assert _rel(dx, gref) < 5e-3
+    big = torch.zeros(256, 2048, device=DEV, dtype=torch.bfloat16)  # strided views + in place
+    big[:, 512:1536] = dy
+    T.gelu_bwd(x, big[:, 512:1536], big[:, 512:1536])
+    assert torch.equal(big[:, 512:1536], dx)
+
+
+def test_gate_residual_and_gate_bwd():
+    from loongx_b200 import train as T
+
+    B, D = 2, 512
+    tm, R = _geo(B)
+    stream, batch = _stream_batch_of_rows(tm, R)
+    res, y, dout = _rand(R, D), _rand(R, D, seed=1), _rand(R, D, seed=2)
+    gates = [_rand(B, 3 * D, seed=3 + s)[:, D:2 * D] for s in range(3)]  # strided [B, D] views
+    gfull = torch.stack([g.float() for g in gates])[stream, batch]  # [R, D]
+    out = torch.empty_like(res)
+    T.gate_residual_fwd(res, y, out, tm, gates)
+    assert _rel(out, res.float() + gfull * y.float()) < 4e-3
+    dy = torch.empty_like(res)
+    dg = torch.zeros(B, 2 * D, device=DEV)
+    T.gate_bwd(dout, y, dy, tm, gates, [None, None, dg[:, D:]])
+    assert _rel(dy, gfull * dout.float()) < 4e-3
+    prod = dout.float() * y.float()
+    ref = torch.stack([prod[(stream == 2) & (batch == b)].sum(0) for b in range(B)])
+    assert _rel(dg[:, D:], ref) < 1e-4 and float(dg[:, :D].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", [256, 3072])
+def test_ln_modulate_bwd(D):
+    from loongx_b200 import train as T
+
+    B = 2
+    tm, R = _geo(B)
+    stream, batch = _stream_batch_of_rows(tm, R)
+    x, dxn, dres = _rand(R, D, scale=1.5), _rand(R, D, seed=1), _rand(R, D, seed=2)
+    scales = [_rand(B, D, scale=0.3, seed=3 + s) for s in range(3)]
+    xf = x.float().requires_grad_(True)
+    sc = torch.stack([s.float() for s in scales]).requires_grad_(True)  # [3, B, D]
+    sh = torch.zeros_like(sc).requires_grad_(True)
+    xn = F.layer_norm(xf, (D,), eps=1e-6) * (1 + sc[stream, batch]) + sh[stream, batch]
+    gx, gsc, gsh = torch.autograd.grad(xn, (xf, sc, sh), dxn.float())
+    dx = torch.empty_like(x)
+    dscale = [torch.zeros(B, D, device=DEV) for _ in range(3)]
+    dshift = [torch.zeros(B, D, device=DEV) for _ in range(3)]
+    stats = torch.zeros(R, 2, device=DEV)
+    T.ln_modulate_bwd(x, dxn, dres, dx, tm, scales, dscale, dshift, stats)
+    assert _rel(dx, gx + dres.float()) < 6e-3
+    for s in range(3):
+        assert _rel(dscale[s], gsc[s]) < 2e-3 and _rel(dshift[s], gsh[s]) < 1e-4
+    # no residual, in place into dxn's buffer is not allowed but dres == dx is
+    dx2 = dres.clone()
+    T.ln_modulate_bwd(x, dxn, dx2, dx2, tm, scales, [None] * 3, [None] * 3, None)
+    assert torch.equal(dx2, dx)
+
+
+def test_qkv_post_fwd_bwd_and_rows_to_heads():
+    from oracle import flux_dit as O
+    from loongx_b200 import ops
+    from loongx_b200 import train as T
+
+    B, H, nt, ni, nc = 2, 2, 128, 128, 128
+    S = nt + ni + nc
+    tm = ops.make_tile_meta(B, nt, ni, nc, DEV)
+    orb = ops.make_out_row_base(B, nt, ni, nc, DEV)
+    R, D = B * S, H * 128
+    pre = torch.zeros(R, 7 * D, device=DEV, dtype=torch.bfloat16)
+    pre[:, :3 * D] = _rand(R, 3 * D, scale=1.3)
+    wq = [(1 + 0.1 * torch.randn(128, device=DEV)).float() for _ in range(2)]
+    wk = [(1 + 0.1 * torch.randn(128, device=DEV)).float() for _ in range(2)]
+    ids = torch.cat([torch.zeros(nt, 3), torch.rand(ni + nc, 3) * 20], 0).to(DEV)
+    ids[:, 0] = 0
+    rope = torch.zeros(S, 64, 2, device=DEV)
+    from loongx_b200.dit import _lib, _stream
+    from loongx_b200 import _lib as L
+
+    L.check(_lib.lx_rope_table(ids.contiguous().data_ptr(), rope.data_ptr(), S, 16, 56, 56, 10000.0, _stream()), "rope")
+    q, k, v = (torch.zeros(B, H, S, 128, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    T.qkv_post_fwd(pre, H, tm, q, k, v, [wq[0], wq[1], wq[1]], [wk[0], wk[1], wk[1]], rope)
+
+    # reference: rows -> [B, S, 3D] in joint-sequence order
+    def to_seq(rows):  # [R, C] -> [B, S, C]
+        rt, ri = B * nt, B * ni
+        return torch.cat([rows[:rt].view(B, nt, -1), rows[rt:rt + ri].view(B, ni, -1), rows[rt + ri:].view(B, nc, -1)], 1)
+
+    def from_seq(x):  # [B, S, C] -> [R, C]
+        return torch.cat([x[:, :nt].reshape(B * nt, -1), x[:, nt:nt + ni].reshape(B * ni, -1), x[:, nt + ni:].reshape(B * nc, -1)])
+
+    cos, sin = O.rope_tables(ids)
+    x = to_seq(pre[:, :3 * D].float()).requires_grad_(True)
+
+    def ref_fwd(x):
+        outs = []
+        for which in range(3):
+            t = x[..., which * D:(which + 1) * D].view(B, S, H, 128).transpose(1, 2)  # [B,H,S,128]
+            if which < 2:
+                w = wq if which == 0 else wk
+                wt = torch.cat([w[0].expand(nt, 128), w[1].expand(ni + nc, 128)], 0)  # per-position weight
+                var = t.pow(2).mean(-1, keepdim=True)
+                t = t * torch.rsqrt(var + 1e-6) * wt[None, None]
+                t = O.apply_rotary_emb(t, (cos, sin))
+            outs.append(t)
+        return outs
+
+    rq, rk, rv = ref_fwd(x)
+    for got, ref in ((q, rq), (k, rk), (v, rv)):
+        assert _rel(got, ref) < 5e-3
+    dq, dk, dv = _rand(B, H, S, 128, seed=5), _rand(B, H, S, 128, seed=6), _rand(B, H, S, 128, seed=7)
+    (gx,) = torch.autograd.grad([rq, rk, rv], x, [dq.float(), dk.float(), dv.float()])
+    dpre = torch.zeros(R, 7 * D, device=DEV, dtype=torch.bfloat16)
+    T.qkv_post_bwd(pre, dq, dk, dv, dpre, H, tm, [wq[0], wq[1], wq[1]], [wk[0], wk[1], wk[1]], rope)
+    assert _rel(dpre[:, :3 * D], from_seq(gx)) < 6e-3
+    assert float(dpre[:, 3 * D:].abs().max()) == 0.0
+    # rows_to_heads is the inverse of the attention kernel's output layout
+    rows = _rand(R, 5 * D, seed=9)
+    heads = torch.zeros(B, H, S, 128, device=DEV, dtype=torch.bfloat16)
+    T.rows_to_heads(rows, H, tm, heads)
+    ref_heads = to_seq(rows[:, :D]).view(B, S, H, 128).transpose(1, 2)
+    assert torch.equal(heads, ref_heads)
+    assert orb.numel() == B * S // 128
+
+
+@pytest.mark.parametrize("M,K,N,r", [(256, 256, 512, 4), (384, 64, 256, 4), (2, 256, 1536, 4), (130, 1280, 256, 8)])
+def test_lora_grad_merge_transpose(M, K, N, r):
+    from loongx_b200 import train as T
+
+    x, dy = _rand(M, K), _rand(M, N, seed=1)
+    A = torch.randn(r, K, device=DEV) / r
+    Bw = torch.randn(N, r, device=DEV) * 0.05
+    s = 1.7
+    Ag, Bg = A.clone().requires_grad_(True), Bw.clone().requires_grad_(True)
+    y = (x.float() @ Ag.t()) @ Bg.t() * s
+    gA, gB = torch.autograd.grad(y, (Ag, Bg), dy.float())
+    dA, dB = torch.zeros_like(A), torch.zeros_like(Bw)
+    ws = torch.zeros(2 * M * r, device=DEV)
+    T.lora_grad(x, dy, A, Bw, dA, dB, s, ws)
+    assert _rel(dA, gA) < 1e-4 and _rel(dB, gB) < 1e-4
+    T.lora_grad(x, dy, A, Bw, dA, dB, s, ws)  # accumulates
+    assert _rel(dA, 2 * gA) < 1e-4
+    W = _rand(N, K, scale=0.05, seed=2)
+    out = torch.empty_like(W)
+    T.lora_merge(W, A, Bw, out, s)
+    assert torch.equal(out, torch.addmm(W.float(), Bw, A, alpha=s).bfloat16()) or _rel(out, W.float() + s * Bw @ A) < 3e-3
+    assert torch.equal(T.transpose(W), W.t().contiguous())
+
+
+def test_flow_objective_kernels():
+    from loongx_b200 import train as T
+
+    B, n, C = 3, 128, 64
+    x0, x1, pred = _rand(B, n, C), _rand(B, n, C, seed=1), _rand(B, n, C, seed=2)
+    t = torch.tensor([0.1, 0.5, 0.93], device=DEV)
+    xt = T.flow_noise_mix(x0, x1, t)
+    ref = ((1 - t[:, None, None]) * x0.float() + t[:, None, None] * x1.float())
+    assert _rel(xt, ref) < 4e-3
+    loss = torch.zeros(1, device=DEV)
+    dpred = torch.empty_like(pred)
+    T.flow_mse_loss(pred, x0, x1, loss, dpred, 1.0)
+    pf = pred.float().requires_grad_(True)
+    lref = F.mse_loss(pf, (x1 - x0).float())
+    (gref,) = torch.autograd.grad(lref, pf)
+    assert abs(loss.item() - lref.item()) / lref.item() < 1e-5
+    assert _rel(dpred, gref) < 4e-3
+
+
+def _tiny_train_case(layers=(2, 2), B=2, nt=128, ni=128, nc=128, seed=0):
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+
+    kw = dict(num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=2, joint_attention_dim=256,
+              pooled_projection_dim=64)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=1234, dtype=torch.float32, device="cpu", w_std=0.05, bias_std=0.05, lora_b_std=0.05)
+    P = {k: v.to(torch.bfloat16) for k, v in P.items()}
+    g = torch.Generator().manual_seed(seed)
+    h, w = 16, 2 * ni // 8  # latent grid: (h/2)*(w/2) = ni
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16()  # noqa: E731
+    batch = dict(image=r(B, 16, h, w), condition=r(B, 16, h, w), prompt_embeds=r(B, nt, 256, scale=0.5),
+                 pooled_prompt_embeds=r(B, 64), position_delta=[[0, -(w // 2)]], t=torch.tensor([0.35, 0.8][:B]),
+                 noise=r(B, ni, 64))
+    return ocfg, cfg, P, batch
+
+
+@pytest.mark.parametrize("layers", [(1, 1), (2, 2)])
+def test_train_step_loss_and_lora_grads_vs_oracle(layers):
+    """Native forward + backward vs fp32 autograd over the oracle restatement of model.py:569-729."""
+    from oracle import sampler as OS
+    from oracle import train_step as TS
+    from loongx_b200.dit import DitWeights
+    from loongx_b200.train import DitTrainer
+
+    ocfg, cfg, P, batch = _tiny_train_case(layers)
+    B = batch["image"].shape[0]
+    P32 = {k: v.float().to(DEV) for k, v in P.items()}
+    b_dev = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    loss_ref, grads_ref, aux = TS.flow_step_grads(P32, ocfg, {k: (v.float() if isinstance(v, torch.Tensor) else v)
+                                                              for k, v in b_dev.items()}, model_config={})
+    W = DitWeights({k: v.to(DEV) for k, v in P.items()}, cfg, DEV)
+    tr = DitTrainer(W, B, 128, 128, 128, model_config={})
+    x0 = OS.pack_latents(b_dev["image"]).contiguous()
+    cond = OS.pack_latents(b_dev["condition"]).contiguous()
+    img_ids = OS.prepare_latent_image_ids(batch["image"].shape[2], batch["image"].shape[3]).to(DEV)
+    cond_ids = OS.condition_ids(img_ids, batch["position_delta"][0])
+    loss = tr.forward(x0, b_dev["noise"], b_dev["t"], cond, b_dev["prompt_embeds"], b_dev["pooled_prompt_embeds"],
+                      torch.zeros(128, 3, device=DEV), img_ids, cond_ids, guidance=1.0)
+    torch.cuda.synchronize()
+    loss1 = loss.item()  # the trainer reuses its loss buffer
+    e_pred = _rel(tr.pred, aux["pred"])
+    print(f"\n[train {layers}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
+    assert e_pred < 2e-2
+    assert abs(loss1 - loss_ref.item()) / loss_ref.item() < 2e-2
+    tr.zero_grad()
+    tr.backward()
+    torch.cuda.synchronize()
+    got = tr.grads()
+    assert set(got) == set(grads_ref)
+    names = sorted(got)
+    cat_g = torch.cat([got[n].flatten() for n in names])
+    cat_r = torch.cat([grads_ref[n].flatten() for n in names])
+    e_all = _rel(cat_g, cat_r)
+    worst = max(((_rel(got[n], grads_ref[n]), n) for n in names if grads_ref[n].norm() > 1e-3 * cat_r.norm()), default=(0, ""))
+    print(f"[train {layers}] LoRA grads relL2 {e_all:.4g}; worst significant param {worst[1]} {worst[0]:.4g}")
+    assert torch.isfinite(cat_g).all()
+    assert e_all < 6e-2, e_all
+    assert worst[0] < 0.15, worst
+    for n in names:  # parameters the loss does not depend on (last block's condition-only paths) get exactly zero
+        if float(grads_ref[n].abs().max()) == 0.0:
+            assert float(got[n].abs().max()) < 1e-6 * float(cat_r.abs().max()) + 1e-12, n
+    # an SGD step on the factors followed by remerge changes the loss in the descent direction
+    lr = 0.5 / float(cat_g.norm())
+    for f in tr.factors.values():
+        f.A.data.add_(f.dA, alpha=-lr)
+        f.B.data.add_(f.dB, alpha=-lr)
+    tr.remerge()
+    loss2 = tr.forward(x0, b_dev["noise"], b_dev["t"], cond, b_dev["prompt_embeds"], b_dev["pooled_prompt_embeds"],
+                       torch.zeros(128, 3, device=DEV), img_ids, cond_ids, guidance=1.0).item()
+    print(f"[train {layers}] loss after one SGD step {loss2:.6f}")
+    assert loss2 < loss1
