@@ -231,14 +231,16 @@ def sdpa_backward_library(q, k, v, d_out, n_cond: int, mask_mode: int, cross_bia
 # trainable LoRA factors
 # ------------------------------------------------------------------------------------------------------------------
 class LoraFactor:
-    """One LoRA-targeted Linear: fp32 master factors living inside a PackedLinear panel."""
+    """One LoRA-targeted Linear: fp32 master factors living inside a PackedLinear panel.  dA / dB are views into the
+    trainer's single flat gradient buffer (one NCCL all-reduce covers every factor)."""
 
     def __init__(self, name: str, panel: PackedLinear, row0: int, rows: int, A: torch.Tensor, Bw: torch.Tensor):
         self.name, self.panel, self.row0, self.rows = name, panel, row0, rows
         self.A = torch.nn.Parameter(A, requires_grad=True)
         self.B = torch.nn.Parameter(Bw, requires_grad=True)
-        self.dA = torch.zeros_like(A)
-        self.dB = torch.zeros_like(Bw)
+        self.dA: Optional[torch.Tensor] = None
+        self.dB: Optional[torch.Tensor] = None
+        self._merged_version = (self.A._version, self.B._version)
 
     def remerge(self):
         """w_lora[rows] = bf16(W + s B A) (+ the transposed panel) after the factors changed."""
@@ -247,6 +249,44 @@ class LoraFactor:
                    p.w_lora[self.row0:self.row0 + self.rows], p.scaling)
         if p.w_loraT is not None:
             transpose(p.w_lora[self.row0:self.row0 + self.rows], p.w_loraT[:, self.row0:self.row0 + self.rows])
+        self._merged_version = (self.A._version, self.B._version)
+
+    def stale(self) -> bool:
+        return self._merged_version != (self.A._version, self.B._version)
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """DDP gradient synchronisation of the reference's training harness (Lightning DDP): ONE all-reduce
+    over the flat fp32 gradient bucket, divided by the world size.  NCCL over NVLink on the GPUs; gloo in the CPU test."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / dist.get_world_size(group))
+    return flat
+
+
+class FlowStepFunction(torch.autograd.Function):
+    """loss = step(batch) as an autograd node: `loss.backward()` (what Lightning calls on the reference's step output)
+    runs the native backward, all-reduces the flat gradient bucket across ranks and hands every LoRA factor its slice."""
+
+    @staticmethod
+    def forward(ctx, trainer, inputs, *params):
+        loss = trainer.forward(*inputs)
+        ctx.trainer = trainer
+        return loss.clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tr = ctx.trainer
+        tr.zero_grad()
+        tr.backward(float(grad_out))
+        allreduce_mean_(tr.grad_flat)
+        grads = []
+        for f in tr.factors.values():
+            grads += [f.dA, f.dB]
+        return (None, None, *grads)
 
 
 class DitTrainer:
@@ -286,6 +326,14 @@ class DitTrainer:
                 continue
             for (name, row0, rows, A, Bw) in panel.lora:
                 self.factors[name] = LoraFactor(name, panel, row0, rows, A, Bw)
+        n_grad = sum(f.A.numel() + f.B.numel() for f in self.factors.values())
+        self.grad_flat = torch.zeros((n_grad,), device=dev, dtype=torch.float32)
+        o = 0
+        for f in self.factors.values():
+            f.dA = self.grad_flat[o:o + f.A.numel()].view_as(f.A)
+            o += f.A.numel()
+            f.dB = self.grad_flat[o:o + f.B.numel()].view_as(f.B)
+            o += f.B.numel()
         self._ensure_transposed()
         self._saved = None
 
@@ -315,10 +363,18 @@ class DitTrainer:
         for f in self.factors.values():
             f.remerge()
 
-    def zero_grad(self):
+    def remerge_if_stale(self):
         for f in self.factors.values():
-            f.dA.zero_()
-            f.dB.zero_()
+            if f.stale():
+                f.remerge()
+
+    def zero_grad(self):
+        self.grad_flat.zero_()
+
+    def step_loss(self, *inputs) -> torch.Tensor:
+        """Differentiable loss (0-dim fp32): forward now, native backward when autograd reaches it."""
+        self.remerge_if_stale()
+        return FlowStepFunction.apply(self, inputs, *self.parameters())
 
     # -- per-block helpers ---------------------------------------------------------------------------------------------
     def _mods_double(self, i):

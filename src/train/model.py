@@ -1,8 +1,9 @@
 """Drop-in for the reference's src/train/model.py: OminiModel + the CS3 / DGF modules (model.py:16-1035).
 
 Constructor signature and the attribute surface consumed by generate() (model.py:377-462) are kept;
-the sub-modules are the native-kernel shells from loongx_b200.cs3.  The Lightning training harness, optimisers and
-checkpoint serialisation (model.py:513-567, 780-943) are outside this build's scope.
+the sub-modules are the native-kernel shells from loongx_b200.cs3.  `step()` / `training_step()` (model.py:560-729) run
+the native forward + backward of loongx_b200.train; the Lightning harness itself and checkpoint serialisation
+(model.py:780-943) are outside this build's scope.
 """
 from typing import Optional
 
@@ -97,8 +98,108 @@ class OminiModel(nn.Module):
         cat[:, Dm:].copy_(fused.squeeze(1))
         return cs3.gemv(self.fusion2[0].weight, self.fusion2[0].bias, cat)
 
-    def step(self, batch):
-        raise NotImplementedError("the training step (model.py:569-729: backward kernels + DDP all-reduce) is not built "
-                                  "in this round; see DESIGN.md 'What comes next'")
+    # ---- training step (model.py:513-729) -------------------------------------------------------------------------
+    def _trainer(self, B, n_txt, n_img, n_cond):
+        from loongx_b200.train import DitTrainer
 
-    training_step = step
+        key = (B, n_txt, n_img, n_cond)
+        if getattr(self, "_trainer_key", None) != key:
+            self._trainer_obj = DitTrainer(self.transformer.weights, B, n_txt, n_img, n_cond, model_config=self.model_config)
+            self._trainer_key = key
+        return self._trainer_obj
+
+    @property
+    def lora_layers(self):
+        """model.py:513-524: the LoRA factors (fp32 masters) — the only parameters the reference's optimizer trains."""
+        tr = getattr(self, "_trainer_obj", None)
+        if tr is None:
+            raise RuntimeError("call step() once (it fixes the batch geometry) or _trainer(B, n_txt, n_img, n_cond) first")
+        return tr.parameters()
+
+    def configure_optimizers(self):
+        """model.py:533-558 (Prodigy is a third-party optimiser that is not installed here)."""
+        opt = self.optimizer_config
+        self.trainable_params = self.lora_layers
+        if opt["type"] == "AdamW":
+            return torch.optim.AdamW(self.trainable_params, **opt["params"])
+        if opt["type"] == "SGD":
+            return torch.optim.SGD(self.trainable_params, **opt["params"])
+        raise NotImplementedError(opt["type"])
+
+    def _step_conditioning(self, prompt_embeds, pooled, eeg, fnirs, ppg, motion):
+        """model.py:656-701: the *step* fuse order — DUAN(x = brain, c = text), cat, fusion3 / fusion4, residual."""
+        pe_b = po_b = None
+        if eeg is not None:
+            e = self.eeg_projection(self.spatial_pyramid_pooling(cs3._f32(eeg), self.eeg_fixed_length))
+            pe_b = self.fuse_eeg(e, self.ppg_projection(self.spatial_pyramid_pooling(cs3._f32(ppg), self.ppg_fixed_length))) \
+                if ppg is not None else e
+        if fnirs is not None:
+            f = self.fnirs_projection(self.spatial_pyramid_pooling(cs3._f32(fnirs), self.fnirs_fixed_length))
+            po_b = self.fuse_fnirs(f, self.motion_projection(self.spatial_pyramid_pooling(cs3._f32(motion), self.motion_fixed_length))) \
+                if motion is not None else f
+        if pe_b is None or po_b is None:
+            raise ValueError("step(): use_brain_condition needs eeg and fnirs (model.py:680-701 reads both embeddings)")
+        if not self.fuse_flag:  # model.py:699-701
+            return self.to_model_dtype(pe_b), self.to_model_dtype(po_b)
+        to32 = lambda x: cs3._f32(x) if x.dtype == torch.float32 else cs3.cast_f32(x.contiguous())  # noqa: E731
+        pe32, po32 = to32(prompt_embeds), to32(pooled)
+        B, n_tok, Dm = pe32.shape
+        cat = torch.empty((B, 2 * n_tok, Dm), device=pe32.device, dtype=torch.float32)
+        cat[:, :n_tok].copy_(pe32)
+        self.duan_norm_prompt(pe_b, pe32, out=cat[:, n_tok:])
+        pe = cs3.token_axis_linear(self.fusion3[0], cat, residual=pe32)
+        fp = self.duan_norm_pooled(po_b.unsqueeze(1), po32.unsqueeze(1)).squeeze(1)
+        catp = torch.empty((B, 2 * po32.shape[1], 1), device=po32.device, dtype=torch.float32)
+        catp[:, :po32.shape[1], 0].copy_(po32)
+        catp[:, po32.shape[1]:, 0].copy_(fp)
+        po = cs3.token_axis_linear(self.fusion4[0], catp, residual=po32.unsqueeze(2).contiguous()).squeeze(2)
+        return self.to_model_dtype(pe), self.to_model_dtype(po)
+
+    def step(self, batch):
+        """model.py:569-729 -> scalar loss whose `.backward()` runs the native backward (LoRA-factor gradients, mean
+        all-reduced across ranks when torch.distributed is initialised).  The VAE / text encoders are outside this build
+        (SURVEY.md §8f): `image` / `condition` are latents [B,16,h,w]; text comes as `prompt_embeds` +
+        `pooled_prompt_embeds` (or `description=(prompt_embeds, pooled)`).  `t` / `noise` may be supplied for
+        reproducibility; otherwise they are drawn like model.py:590-591."""
+        from src.flux.pipeline_tools import encode_images
+
+        imgs, conditions = batch["image"], batch["condition"]
+        position_delta = batch["position_delta"][0]
+        position_scale = float(batch.get("position_scale", [1.0])[0])
+        dev = self.device
+        with torch.no_grad():
+            x_0, img_ids = encode_images(self.flux_pipe, imgs)
+            if "prompt_embeds" in batch:
+                pe, po = batch["prompt_embeds"], batch["pooled_prompt_embeds"]
+            elif isinstance(batch.get("description"), tuple):
+                pe, po = batch["description"]
+            else:
+                raise NotImplementedError("text encoders are outside this build: put prompt_embeds / pooled_prompt_embeds "
+                                          "in the batch")
+            pe, po = pe.to(dev), po.to(dev)
+            B = x_0.shape[0]
+            t = batch["t"].to(dev).float() if "t" in batch else torch.sigmoid(torch.randn((B,), device=dev))
+            x_1 = batch["noise"].to(dev).to(x_0.dtype) if "noise" in batch else torch.randn_like(x_0)
+            condition_latents, condition_ids = encode_images(self.flux_pipe, conditions)
+            condition_ids = condition_ids.float()
+            condition_ids[:, 1] += position_delta[0]
+            condition_ids[:, 2] += position_delta[1]
+            if position_scale != 1.0:
+                scale_bias = (position_scale - 1.0) / 2
+                condition_ids[:, 1:] *= position_scale
+                condition_ids[:, 1:] += scale_bias
+            if self.use_brain_condition:
+                pe, po = self._step_conditioning(pe, po, batch.get("eeg"), batch.get("fnirs"), batch.get("ppg"),
+                                                 batch.get("motion"))
+            text_ids = torch.zeros(pe.shape[1], 3, device=dev)
+        tr = self._trainer(B, pe.shape[1], x_0.shape[1], condition_latents.shape[1])
+        loss = tr.step_loss(x_0.contiguous(), x_1.contiguous(), t, condition_latents, pe, po, text_ids, img_ids.float(),
+                            condition_ids, 1.0)
+        self.last_t = float(t.mean())
+        return loss
+
+    def training_step(self, batch, batch_idx=0):
+        step_loss = self.step(batch)
+        v = float(step_loss.detach())
+        self.log_loss = v if not hasattr(self, "log_loss") else self.log_loss * 0.95 + v * 0.05
+        return step_loss

@@ -51,3 +51,47 @@ def test_two_rank_sharding_and_max_timing(n_items):
         assert p.exitcode == 0
     assert cover == [1] * n_items
     assert t_max == 0.5 and agg == n_items / 0.5
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from loongx_b200.train import allreduce_mean_
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(1000, generator=g)  # this rank's flat LoRA-gradient bucket
+    mine = flat.clone()
+    out = allreduce_mean_(flat)
+    assert out.data_ptr() == flat.data_ptr()  # in place: the per-factor views of the bucket see the reduced values
+    other = torch.randn(1000, generator=torch.Generator().manual_seed(100 + (1 - rank)))
+    ok = torch.allclose(flat, (mine + other) / 2, atol=1e-6)
+    gathered = [torch.zeros(1000) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = torch.equal(gathered[0], gathered[1])  # replicas stay identical after the step
+    if rank == 0:
+        q.put((bool(ok), bool(same)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_mean():
+    """The one real collective of the path: DDP's mean all-reduce of the trainable gradients, here
+    one call over the flat LoRA-gradient bucket (gloo stands in for NCCL on the CPU)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, same = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok and same
+    # single process / no process group: identity
+    from loongx_b200.train import allreduce_mean_
+
+    x = torch.arange(4.0)
+    assert torch.equal(allreduce_mean_(x.clone()), x)

@@ -292,3 +292,93 @@ def test_train_step_loss_and_lora_grads_vs_oracle(layers):
                        torch.zeros(128, 3, device=DEV), img_ids, cond_ids, guidance=1.0).item()
     print(f"[train {layers}] loss after one SGD step {loss2:.6f}")
     assert loss2 < loss1
+
+
+def test_omini_model_step_api_and_optimizer():
+    """OminiModel.step (model.py:569-729) through the drop-in module surface: brain conditioning in the *step* fuse order,
+    loss vs the oracle, `loss.backward()` -> .grad on the LoRA factors, one optimizer step lowers the loss."""
+    from oracle import cs3_dgf as OC
+    from oracle import flux_dit as O
+    from oracle import train_step as TS
+    from loongx_b200.config import FluxConfig
+    from src.train.model import OminiModel
+
+    torch.manual_seed(11)
+    oc = OC.NeuralConditioner().eval()
+    kw = dict(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=4096, pooled_projection_dim=768)
+    cfg = FluxConfig(**kw)
+    m = OminiModel(cfg, lora_config={"r": 4, "lora_alpha": 4}, device=DEV, model_config={},
+                   optimizer_config={"type": "SGD", "params": {"lr": 0.0}}, use_brain_condition=True, fuse_flag=True)
+    m.load_state_dict(oc.state_dict(), strict=True)
+    oc = oc.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    B, h, w = 1, 16, 32
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).to(DEV)  # noqa: E731
+    batch = dict(image=r(B, 16, h, w).bfloat16(), condition=r(B, 16, h, w).bfloat16(),
+                 prompt_embeds=r(B, 512, 4096, scale=0.3).bfloat16(), pooled_prompt_embeds=r(B, 768).bfloat16(),
+                 position_delta=[[0, -16]], condition_type=["subject"], t=torch.tensor([0.6]),
+                 noise=r(B, 128, 64).bfloat16(), eeg=r(B, 4, 5000), fnirs=r(B, 6, 600), ppg=r(B, 4, 256), motion=r(B, 6, 100))
+    loss = m.step(batch)
+    assert loss.dim() == 0 and loss.requires_grad
+    # oracle with the same (bf16-rounded) DiT weights: pull them back out of the native container
+    tr = m._trainer_obj
+    ocfg = O.FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=0)  # shapes only; overwritten below
+    named = m.transformer.weights.named
+    # rebuild the oracle's flat dict from the packed panels (qkv panels are stacked in q, k, v(, mlp) order)
+    D = ocfg.inner_dim
+
+    def put(name, wt, bias):
+        P[name + ".weight"], P[name + ".bias"] = wt.float(), bias.float()
+
+    for key, names in (("x_embedder", ["x_embedder"]), ("context_embedder", ["context_embedder"]),
+                       ("time_1", ["time_text_embed.timestep_embedder.linear_1"]),
+                       ("time_2", ["time_text_embed.timestep_embedder.linear_2"]),
+                       ("guid_1", ["time_text_embed.guidance_embedder.linear_1"]),
+                       ("guid_2", ["time_text_embed.guidance_embedder.linear_2"]),
+                       ("text_1", ["time_text_embed.text_embedder.linear_1"]),
+                       ("text_2", ["time_text_embed.text_embedder.linear_2"]),
+                       ("mod_img", ["transformer_blocks.0.norm1.linear"]), ("mod_txt", ["transformer_blocks.0.norm1_context.linear"]),
+                       ("mod_single", ["single_transformer_blocks.0.norm.linear"]), ("norm_out", ["norm_out.linear"]),
+                       ("proj_out", ["proj_out"]),
+                       ("double.0.qkv", ["transformer_blocks.0.attn.to_q", "transformer_blocks.0.attn.to_k", "transformer_blocks.0.attn.to_v"]),
+                       ("double.0.qkv_ctx", ["transformer_blocks.0.attn.add_q_proj", "transformer_blocks.0.attn.add_k_proj", "transformer_blocks.0.attn.add_v_proj"]),
+                       ("double.0.out", ["transformer_blocks.0.attn.to_out.0"]), ("double.0.out_ctx", ["transformer_blocks.0.attn.to_add_out"]),
+                       ("double.0.ff_up", ["transformer_blocks.0.ff.net.0.proj"]), ("double.0.ff_down", ["transformer_blocks.0.ff.net.2"]),
+                       ("double.0.ff_ctx_up", ["transformer_blocks.0.ff_context.net.0.proj"]),
+                       ("double.0.ff_ctx_down", ["transformer_blocks.0.ff_context.net.2"]),
+                       ("single.0.qkv_mlp", ["single_transformer_blocks.0.attn.to_q", "single_transformer_blocks.0.attn.to_k",
+                                             "single_transformer_blocks.0.attn.to_v", "single_transformer_blocks.0.proj_mlp"]),
+                       ("single.0.proj_out", ["single_transformer_blocks.0.proj_out"])):
+        pl, r0 = named[key], 0
+        for n in names:
+            rows = P[n + ".weight"].shape[0]
+            put(n, pl.w[r0:r0 + rows], pl.bias[r0:r0 + rows])
+            r0 += rows
+    for key in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        P[f"transformer_blocks.0.attn.{key}.weight"] = named[f"double.0.{key}"].float()
+    for key in ("norm_q", "norm_k"):
+        P[f"single_transformer_blocks.0.attn.{key}.weight"] = named[f"single.0.{key}"].float()
+    for n, f in tr.factors.items():
+        P[n + ".lora_A.weight"], P[n + ".lora_B.weight"] = f.A.detach().clone(), f.B.detach().clone()
+    P = {k: v.to(DEV) for k, v in P.items()}
+    ob = {k: (v.float() if isinstance(v, torch.Tensor) and v.dtype == torch.bfloat16 else v) for k, v in batch.items()}
+    loss_ref, grads_ref, aux = TS.flow_step_grads(P, ocfg, ob, model_config={}, conditioner=oc, use_brain_condition=True,
+                                                  fuse_flag=True)
+    l1 = float(loss.detach())
+    print(f"\n[OminiModel.step] loss native {l1:.6f} oracle {loss_ref.item():.6f}")
+    assert abs(l1 - loss_ref.item()) / loss_ref.item() < 2e-2
+    opt = torch.optim.SGD(m.lora_layers, lr=1.0)
+    loss.backward()
+    got = dict(tr.named_parameters())
+    cat_g = torch.cat([got[n].grad.flatten() for n in sorted(got)])
+    cat_r = torch.cat([grads_ref[n].flatten() for n in sorted(got)])
+    e = _rel(cat_g, cat_r)
+    print(f"[OminiModel.step] LoRA .grad relL2 vs oracle autograd {e:.4g}")
+    assert e < 6e-2
+    for gr in opt.param_groups:
+        gr["lr"] = 0.5 / float(cat_g.norm())
+    opt.step()
+    loss2 = float(m.step(batch).detach())  # step() re-merges the panels whose factors changed
+    print(f"[OminiModel.step] loss after optimizer step {loss2:.6f}")
+    assert loss2 < l1
