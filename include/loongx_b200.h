@@ -126,6 +126,7 @@ typedef struct lx_attn_desc {
                         (independent_condition) */
   float cross_bias;  /* log(c_factor) added to cond<->rest logits; non-zero overrides mask_mode like the reference */
   float scale;       /* 1/sqrt(128) */
+  float* lse;        /* optional fp32 [B, H, S]: log2-domain log-sum-exp of every query row (for lx_attention_bwd) */
 } lx_attn_desc_t;
 
 int lx_attention(const lx_attn_desc_t* desc, void* stream);
@@ -344,6 +345,29 @@ int lx_duan_forward(const lx_duan_weights_t* w, const float* x, const float* c, 
  * (pre-norm q/k/v, pre-GELU hidden, pre-gate projection outputs); dX of every Linear is lx_gemm_bf16 against the
  * transposed weight panel.  Rows / tile_meta as above; per-stream vectors are `p[stream] + batch*stride[stream]`.
  * ------------------------------------------------------------------------------------------------------ */
+/* Backward of lx_attention (F.scaled_dot_product_attention in block.py:129-131, with the same block masks / c_factor
+ * bias): the five products of the FlashAttention backward on tcgen05, P^T / dS^T kept in tensor memory.
+ * lx_attention_bwd_prep: dO rows (stream-major, head h at columns [128h, 128h+128)) + O rows -> dO head-major and
+ * delta[b,h,s] = sum_d dO*O. */
+typedef struct lx_attn_bwd_desc {
+  const void* q; /* bf16 [B, H, S, 128] */
+  const void* k;
+  const void* v;
+  const void* d_out;  /* bf16 [B, H, S, 128] */
+  const float* lse;   /* fp32 [B, H, S] written by lx_attention (log2 domain) */
+  const float* delta; /* fp32 [B, H, S] */
+  float* dq;          /* fp32 [B, H, S, 128] accumulator, zero-initialised by the caller */
+  void* dk;           /* bf16 [B, H, S, 128] */
+  void* dv;
+  int32_t B, H, S;
+  int32_t n_cond, mask_mode;
+  float cross_bias, scale;
+  int32_t reserved;
+} lx_attn_bwd_desc_t;
+int lx_attention_bwd_prep(const void* d_out_rows, int64_t ld_do, const void* out_rows, int64_t ld_o, int32_t rows,
+                          int32_t heads, const lx_tile_meta_t* tile_meta, void* d_out_heads, float* delta,
+                          int32_t seq_total, void* stream);
+int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream);
 /* GELU(tanh) and its derivative on bf16 [rows, cols] views (FeedForward act / act_mlp, block.py:258-265, 302). */
 int lx_gelu_fwd(const void* pre, int64_t ld_pre, void* out, int64_t ldo, int32_t rows, int32_t cols, void* stream);
 int lx_gelu_bwd(const void* pre, int64_t ld_pre, const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int32_t rows,

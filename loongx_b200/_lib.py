@@ -68,6 +68,16 @@ class AttnDesc(C.Structure):
         ("B", c_int32), ("H", c_int32), ("S", c_int32),
         ("n_cond", c_int32), ("mask_mode", c_int32),
         ("cross_bias", c_float), ("scale", c_float),
+        ("lse", c_void_p),
+    ]
+
+
+class AttnBwdDesc(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("d_out", c_void_p),
+        ("lse", c_void_p), ("delta", c_void_p), ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+        ("B", c_int32), ("H", c_int32), ("S", c_int32), ("n_cond", c_int32), ("mask_mode", c_int32),
+        ("cross_bias", c_float), ("scale", c_float), ("reserved", c_int32),
     ]
 
 
@@ -78,6 +88,9 @@ lib.lx_version.restype = c_int
 lib.lx_device_info.argtypes = [C.POINTER(c_int32)]
 lib.lx_gemm_bf16.argtypes = [C.POINTER(GemmDesc), c_void_p]
 lib.lx_attention.argtypes = [C.POINTER(AttnDesc), c_void_p]
+lib.lx_attention_bwd.argtypes = [C.POINTER(AttnBwdDesc), c_void_p]
+lib.lx_attention_bwd_prep.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                      c_int32, c_void_p]
 
 
 def check(rc: int, what: str = "") -> None:

@@ -312,6 +312,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // epilogue: O / l -> bf16 -> out rows
       if (trace != nullptr) trace[4] = clock64();
       const float inv_l = 1.0f / l_run;
+      if (d.lse != nullptr) d.lse[head_row0 + (qt0 + g) * ATT_BQ + r] = m_run + log2f(l_run);  // for lx_attention_bwd
       mbar_wait(&o_done[g], 0);
       tc_fence_after();
       // O_g / l -> bf16 -> this tile's (now idle) Q buffer in the 128-byte-swizzled TMA layout -> two TMA stores of

@@ -1,0 +1,397 @@
+// Backward of the joint [txt | img | cond] attention (block.py:129-131) for sm_100a, head_dim 128: dQ, dK, dV from
+// Q, K, V, dO and the forward's per-row log-sum-exp, all five GEMMs of the FlashAttention backward on tcgen05.
+//
+//   one CTA = one 128-key tile j of one (batch, head); it walks the query tiles i that see those keys.
+//   Everything is computed TRANSPOSED (keys on the TMEM lanes), so that the probabilities never leave tensor memory
+//   for the two products that accumulate over query tiles:
+//       S^T  = K_j Q_i^T            SS   -> TMEM cols [0,128)     fp32
+//       dP^T = V_j dO_i^T           SS   -> TMEM cols [128,256)   fp32
+//       P^T  = exp2(S^T * scale*log2e + bias - lse_i)            (compute threads, one key row each; lse in log2 units)
+//       dS^T = scale * P^T * (dP^T - delta_i)                    delta_i = rowsum(dO_i * O_i)
+//              P^T, dS^T are packed to bf16 in place over TMEM cols [0,64) / [64,128); dS^T also goes to shared memory
+//       dV_j += P^T  dO_i           TS   (A from TMEM, B = dO_i as MN-major smem operand)   -> TMEM cols [256,384)
+//       dK_j += dS^T Q_i            TS   (B = Q_i MN-major)                                 -> TMEM cols [384,512)
+//       dQ_i  = dS   K_j            SS   (A = the dS^T tile read MN-major, B = K_j MN-major) -> TMEM cols [128,256),
+//               read back by the compute threads and added to the fp32 dQ accumulator in global memory (red.v4.f32)
+//   warp 0: TMA producer (K_j, V_j once; Q_i through a 2-stage ring, dO_i single-buffered: 192 KB of shared memory)
+//   warp 1: tcgen05.mma issuer        warps 2..5: compute (TMEM lane quarter = warp & 3)
+//   The tensor pipe executes in issue order, so S^T(i+1) may overwrite the columns P^T(i) / dS^T(i) are read from.
+//
+// Block masks (block.py:106-120) restrict the query-tile range of a key tile; the log(c_factor) bias (block.py:121-128)
+// is uniform per 128x128 tile.
+#include "host_util.cuh"
+#include "ptx.cuh"
+#include "tmem_wide.cuh"
+
+namespace lx {
+
+constexpr int AB_TILE_BYTES = 128 * 128 * 2;
+constexpr int AB_ATOM_BYTES = 128 * 64 * 2;
+constexpr int AB_THREADS = 192;
+constexpr int AB_SMEM = 6 * AB_TILE_BYTES + 2 * 2 * 128 * 4 + 256 + 1024;
+
+struct AttnBwdParams {
+  const float* lse;    // [B*H*S] log2-domain log-sum-exp of the forward
+  const float* delta;  // [B*H*S] rowsum(dO * O)
+  float* dq;           // fp32 [B,H,S,128], zero-initialised by the launcher's caller
+  __nv_bfloat16* dk;   // bf16 [B,H,S,128]
+  __nv_bfloat16* dv;
+  int B, H, S, n_cond, mask_mode;
+  float scale, scale_log2, bias_log2;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + AB_TILE_BYTES;
+  uint8_t* sQ = sV + AB_TILE_BYTES;         // [2 stages]
+  uint8_t* sdO = sQ + 2 * AB_TILE_BYTES;
+  uint8_t* sdS = sdO + AB_TILE_BYTES;
+  float* sStat = reinterpret_cast<float*>(sdS + AB_TILE_BYTES);  // [2 parities][lse | delta][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128);
+  uint64_t* kv_full = bars;        // 1
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* do_full = bars + 5;
+  uint64_t* do_empty = bars + 6;
+  uint64_t* sp_full = bars + 7;    // S^T(i) and dP^T(i) complete
+  uint64_t* p_ready = bars + 8;    // 128 arrivals: P^T / dS^T packed (TMEM + smem)
+  uint64_t* dq_full = bars + 9;    // dQ_i complete (and dV, dK of this iteration)
+  uint64_t* dq_read = bars + 10;   // 128 arrivals: dQ_i read out of TMEM
+  uint64_t* acc_done = bars + 11;  // all MMAs of the CTA complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.S / 128;
+  const int n_rest = (p.S - p.n_cond) / 128;
+  const bool k_is_cond = j >= n_rest;
+  const bool use_bias = p.bias_log2 != 0.0f;
+  int q_begin = 0, q_end = n_tiles;  // query tiles that see this key tile
+  if (!use_bias && p.n_cond > 0) {
+    if (p.mask_mode == 1) {
+      if (k_is_cond) q_begin = n_rest;
+      else q_end = n_rest;
+    } else if (p.mask_mode == 2 && !k_is_cond) {
+      q_end = n_rest;  // condition queries see condition keys only
+    }
+  }
+  const int n_it = q_end - q_begin;
+  const int head_row0 = (b * p.H + h) * p.S;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
+    mbar_init(sp_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_read, 128);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_S = tmem_base;         // S^T fp32 -> P^T bf16 [0,64) | dS^T bf16 [64,128)
+  const uint32_t tm_dP = tmem_base + 128;  // dP^T fp32, then the dQ_i accumulator
+  const uint32_t tm_dV = tmem_base + 256;
+  const uint32_t tm_dK = tmem_base + 384;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int krow = head_row0 + j * 128;
+      mbar_expect_tx(kv_full, 2 * AB_TILE_BYTES);
+      tma_load_2d(sK, &tmK, kv_full, 0, krow);
+      tma_load_2d(sK + AB_ATOM_BYTES, &tmK, kv_full, 64, krow);
+      tma_load_2d(sV, &tmV, kv_full, 0, krow);
+      tma_load_2d(sV + AB_ATOM_BYTES, &tmV, kv_full, 64, krow);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const int row = head_row0 + (q_begin + it) * 128;
+        mbar_wait(&q_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], AB_TILE_BYTES);
+        tma_load_2d(sQ + st * AB_TILE_BYTES, &tmQ, &q_full[st], 0, row);
+        tma_load_2d(sQ + st * AB_TILE_BYTES + AB_ATOM_BYTES, &tmQ, &q_full[st], 64, row);
+        mbar_wait(do_empty, (it & 1) ^ 1);
+        mbar_expect_tx(do_full, AB_TILE_BYTES);
+        tma_load_2d(sdO, &tmdO, do_full, 0, row);
+        tma_load_2d(sdO + AB_ATOM_BYTES, &tmdO, do_full, 64, row);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one() && n_it > 0) {
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, false, false);  // A K-major smem, B K-major smem
+      constexpr uint32_t idesc_tm = make_idesc_bf16(128, 128, false, true);   // A TMEM, B MN-major smem
+      constexpr uint32_t idesc_mm = make_idesc_bf16(128, 128, true, true);    // A MN-major smem, B MN-major smem
+      const uint64_t k_kmaj = make_sdesc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t v_kmaj = make_sdesc_sw128(smem_u32(sV), 16, 1024);
+      const uint64_t q_kmaj0 = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t do_kmaj = make_sdesc_sw128(smem_u32(sdO), 16, 1024);
+      const uint64_t q_mn0 = make_sdesc_sw128(smem_u32(sQ), AB_ATOM_BYTES, 1024);
+      const uint64_t do_mn = make_sdesc_sw128(smem_u32(sdO), AB_ATOM_BYTES, 1024);
+      const uint64_t ds_mn = make_sdesc_sw128(smem_u32(sdS), AB_ATOM_BYTES, 1024);
+      const uint64_t k_mn = make_sdesc_sw128(smem_u32(sK), AB_ATOM_BYTES, 1024);
+      auto issue_s = [&](int it) {  // S^T(it) = K_j Q^T
+        const int st = it & 1;
+        mbar_wait(&q_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t qd = q_kmaj0 + (uint64_t)(st * (AB_TILE_BYTES >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = ((kk >> 2) * AB_ATOM_BYTES + (kk & 3) * 32) >> 4;
+          umma_ss(tm_S, k_kmaj + off, qd + off, idesc_kk, kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_dp = [&](int it) {  // dP^T(it) = V_j dO^T
+        mbar_wait(do_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = ((kk >> 2) * AB_ATOM_BYTES + (kk & 3) * 32) >> 4;
+          umma_ss(tm_dP, v_kmaj + off, do_kmaj + off, idesc_kk, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(sp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      issue_dp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const uint32_t acc = it > 0 ? 1u : 0u;
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        // dV += P^T dO_i : k-slice kk = 16 queries = 8 packed TMEM columns / 16 rows (2048 B) of the dO tile
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tm_dV, tm_S + kk * 8, do_mn + (uint64_t)(kk * (2048 >> 4)), idesc_tm, kk == 0 ? acc : 1u);
+        umma_commit(do_empty);
+        // dK += dS^T Q_i
+        const uint64_t qm = q_mn0 + (uint64_t)(st * (AB_TILE_BYTES >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tm_dK, tm_S + 64 + kk * 8, qm + (uint64_t)(kk * (2048 >> 4)), idesc_tm, kk == 0 ? acc : 1u);
+        umma_commit(&q_empty[st]);
+        // dQ_i = dS K_j : A = dS^T tile [key rows][query cols] read MN-major (M = queries), k-slice = 16 key rows
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tm_dP, ds_mn + (uint64_t)(kk * (2048 >> 4)), k_mn + (uint64_t)(kk * (2048 >> 4)), idesc_mm,
+                  kk != 0 ? 1u : 0u);
+        umma_commit(dq_full);
+        if (it + 1 < n_it) {
+          issue_s(it + 1);
+          mbar_wait(dq_read, it & 1);  // dQ_i has left TMEM cols [128,256)
+          tc_fence_after();
+          issue_dp(it + 1);
+        } else {
+          umma_commit(acc_done);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- compute warps: one key row per thread
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;  // 0..127
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int qi = q_begin + it;
+      const bool cross = use_bias && (k_is_cond != (qi >= n_rest));
+      const float bias = cross ? p.bias_log2 : 0.f;
+      float* st_lse = sStat + (it & 1) * 256;
+      float* st_del = st_lse + 128;
+      st_lse[tid] = p.lse[head_row0 + qi * 128 + tid];
+      st_del[tid] = p.delta[head_row0 + qi * 128 + tid];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sp_full, it & 1);
+      tc_fence_after();
+      uint32_t s[128];
+      tmem_ld_32x32b_x128(tm_S + lane_off, s);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t dp[32];
+        tmem_ld_32x32b_x32(tm_dP + lane_off + c * 32, dp);
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int q0 = c * 32 + 2 * jj;
+          const float p0 = ex2_approx(__uint_as_float(s[q0]) * p.scale_log2 + (bias - st_lse[q0]));
+          const float p1 = ex2_approx(__uint_as_float(s[q0 + 1]) * p.scale_log2 + (bias - st_lse[q0 + 1]));
+          const float d0 = p.scale * p0 * (__uint_as_float(dp[2 * jj]) - st_del[q0]);
+          const float d1 = p.scale * p1 * (__uint_as_float(dp[2 * jj + 1]) - st_del[q0 + 1]);
+          pk[jj] = pack_bf16(p0, p1);
+          dk[jj] = pack_bf16(d0, d1);
+        }
+        tmem_st_32x32b_x16(tm_S + lane_off + c * 16, pk);
+        tmem_st_32x32b_x16(tm_S + lane_off + 64 + c * 16, dk);
+        // dS^T row r, query columns [32c, 32c+32) -> four 16-byte chunks of the 128B-swizzled [128 x 128] tile
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int c16 = c * 4 + q4;
+          uint4 u = make_uint4(dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(sdS + (c16 >> 3) * AB_ATOM_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // dQ_i (lanes = query rows) -> global fp32 accumulator
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      float* dq_row = p.dq + ((size_t)(head_row0 + qi * 128 + r)) * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tm_dP + lane_off + c * 32, o);
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          red_add_v4(dq_row + c * 32 + e, __uint_as_float(o[e]), __uint_as_float(o[e + 1]), __uint_as_float(o[e + 2]),
+                     __uint_as_float(o[e + 3]));
+      }
+      tc_fence_before();
+      mbar_arrive(dq_read);
+    }
+    // epilogue: dV_j, dK_j (lanes = key rows) -> bf16 rows
+    const size_t out_row = ((size_t)(head_row0 + j * 128 + r)) * 128;
+    if (n_it > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) + out_row;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        if (n_it > 0) tmem_ld_32x32b_x32((which == 0 ? tm_dV : tm_dK) + lane_off + c * 32, o);
+        else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = 0u;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
+          u.y = pack_bf16(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
+          u.z = pack_bf16(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
+          u.w = pack_bf16(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dO rows [R, ld] + O rows [R, ld] (head h in columns [128h, 128h+128)) -> dO head-major [B,H,S,128] and
+// delta[b,h,s] = sum_d dO * O.  One warp per (row, head), 4 elements per lane.
+__global__ void __launch_bounds__(128) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ d_out, int64_t ld_do,
+                                                            const __nv_bfloat16* __restrict__ out, int64_t ld_o, int rows,
+                                                            int heads, const lx_tile_meta_t* __restrict__ tm,
+                                                            __nv_bfloat16* __restrict__ do_heads, float* __restrict__ delta,
+                                                            int seq_total) {
+  const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const lx_tile_meta_t m = tm[row >> 7];
+  const int seq = m.seq_row + (row & 127);
+  const int b = seq / seq_total, s = seq % seq_total;
+  for (int h = warp; h < heads; h += 4) {
+    const uint2 ug = *reinterpret_cast<const uint2*>(d_out + (size_t)row * ld_do + h * 128 + lane * 4);
+    const uint2 uo = *reinterpret_cast<const uint2*>(out + (size_t)row * ld_o + h * 128 + lane * 4);
+    const float2 g0 = unpack_bf16(ug.x), g1 = unpack_bf16(ug.y), o0 = unpack_bf16(uo.x), o1 = unpack_bf16(uo.y);
+    const float dot = warp_sum(g0.x * o0.x + g0.y * o0.y + g1.x * o1.x + g1.y * o1.y);
+    const size_t hrow = ((size_t)b * heads + h) * seq_total + s;
+    *reinterpret_cast<uint2*>(do_heads + hrow * 128 + lane * 4) = ug;
+    if (lane == 0) delta[hrow] = dot;
+  }
+}
+
+}  // namespace lx
+
+using namespace lx;
+
+extern "C" int lx_attention_bwd_prep(const void* d_out_rows, int64_t ld_do, const void* out_rows, int64_t ld_o,
+                                     int32_t rows, int32_t heads, const lx_tile_meta_t* tile_meta, void* d_out_heads,
+                                     float* delta, int32_t seq_total, void* stream) {
+  LX_CHECK_ARG(d_out_rows && out_rows && tile_meta && d_out_heads && delta && rows > 0 && heads > 0 && seq_total > 0 &&
+                   ld_do % 4 == 0 && ld_o % 4 == 0,
+               "lx_attention_bwd_prep: bad arguments");
+  LaunchScope scope(KC_ROW, stream, 6.0 * rows * heads * 128);
+  attn_bwd_prep_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_out_rows), ld_do, reinterpret_cast<const __nv_bfloat16*>(out_rows), ld_o, rows,
+      heads, tile_meta, reinterpret_cast<__nv_bfloat16*>(d_out_heads), delta, seq_total);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
+  LX_CHECK_ARG(desc != nullptr, "lx_attention_bwd: null descriptor");
+  const lx_attn_bwd_desc_t& d = *desc;
+  LX_CHECK_ARG(d.q && d.k && d.v && d.d_out && d.lse && d.delta && d.dq && d.dk && d.dv, "lx_attention_bwd: null pointer");
+  LX_CHECK_ARG(d.B > 0 && d.H > 0 && d.S > 0 && d.S % 128 == 0, "lx_attention_bwd: S=%d must be a positive multiple of 128",
+               d.S);
+  LX_CHECK_ARG(d.n_cond >= 0 && d.n_cond % 128 == 0 && d.n_cond < d.S, "lx_attention_bwd: bad n_cond=%d", d.n_cond);
+  LX_CHECK_ARG(d.mask_mode >= 0 && d.mask_mode <= 2, "lx_attention_bwd: bad mask_mode=%d", d.mask_mode);
+  LX_CHECK_ARG(d.H <= 65535 && d.B <= 65535, "lx_attention_bwd: grid too large");
+  const uint64_t rows = (uint64_t)d.B * d.H * d.S;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmQ, d.q, rows, 128, 128, 128, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmK, d.k, rows, 128, 128, 128, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmV, d.v, rows, 128, 128, 128, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmdO, d.d_out, rows, 128, 128, 128, 64))) return rc;
+  AttnBwdParams p;
+  p.lse = d.lse; p.delta = d.delta; p.dq = d.dq;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(d.dk);
+  p.dv = reinterpret_cast<__nv_bfloat16*>(d.dv);
+  p.B = d.B; p.H = d.H; p.S = d.S; p.n_cond = d.n_cond; p.mask_mode = d.mask_mode;
+  const float log2e = 1.4426950408889634f;
+  p.scale = d.scale;
+  p.scale_log2 = d.scale * log2e;
+  p.bias_log2 = d.cross_bias * log2e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LX_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    attr_set = true;
+  }
+  double pairs = (double)d.S * d.S;
+  if (d.cross_bias == 0.f && d.n_cond > 0) {
+    const double nc = d.n_cond, nr = d.S - d.n_cond;
+    if (d.mask_mode == 1) pairs = nc * nc + nr * nr;
+    if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
+  }
+  LaunchScope scope(KC_ATTENTION, stream, 10.0 * d.B * d.H * pairs * 128.0);  // five 2*S*S*128 products
+  attention_bwd_kernel<<<dim3(d.S / 128, d.H, d.B), AB_THREADS, AB_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV,
+                                                                                                             tmdO, p);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}

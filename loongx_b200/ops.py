@@ -123,7 +123,7 @@ def make_out_row_base(batch: int, n_txt: int, n_img: int, n_cond: int, device) -
 
 
 def attention(q, k, v, out, out_row_base, *, n_cond: int = 0, mask_mode: int = 0, cross_bias: float = 0.0,
-              col_offset: int = 0, scale: Optional[float] = None) -> None:
+              col_offset: int = 0, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None) -> None:
     """out rows <- softmax(q k^T * scale) v for q,k,v [B,H,S,128] bf16 (see lx_attention)."""
     assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     B, H, S, Dh = q.shape
@@ -137,4 +137,29 @@ def attention(q, k, v, out, out_row_base, *, n_cond: int = 0, mask_mode: int = 0
     d.n_cond, d.mask_mode = n_cond, mask_mode
     d.cross_bias = cross_bias
     d.scale = scale if scale is not None else 1.0 / (Dh ** 0.5)
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S
+        d.lse = _ptr(lse)
     L.check(L.lib.lx_attention(C.byref(d), _stream()), "lx_attention")
+
+
+def attention_bwd(q, k, v, d_out_heads, lse, delta, dq_f32, dk, dv, *, n_cond: int = 0, mask_mode: int = 0,
+                  cross_bias: float = 0.0, scale: Optional[float] = None) -> None:
+    """dq_f32 (fp32, zeroed by the caller) += dQ; dk, dv (bf16) = dK, dV of lx_attention (see lx_attention_bwd)."""
+    B, H, S, Dh = q.shape
+    assert Dh == 128 and dq_f32.dtype == torch.float32 and dk.dtype == torch.bfloat16 and dv.dtype == torch.bfloat16
+    for t in (q, k, v, d_out_heads, lse, delta, dq_f32, dk, dv):
+        assert t.is_cuda and t.is_contiguous()
+    d = L.AttnBwdDesc()
+    d.q, d.k, d.v, d.d_out = _ptr(q), _ptr(k), _ptr(v), _ptr(d_out_heads)
+    d.lse, d.delta, d.dq, d.dk, d.dv = _ptr(lse), _ptr(delta), _ptr(dq_f32), _ptr(dk), _ptr(dv)
+    d.B, d.H, d.S, d.n_cond, d.mask_mode = B, H, S, n_cond, mask_mode
+    d.cross_bias = cross_bias
+    d.scale = scale if scale is not None else 1.0 / (Dh ** 0.5)
+    L.check(L.lib.lx_attention_bwd(C.byref(d), _stream()), "lx_attention_bwd")
+
+
+def attention_bwd_prep(d_out_rows, out_rows, heads: int, tile_meta, d_out_heads, delta) -> None:
+    L.check(L.lib.lx_attention_bwd_prep(_ptr(d_out_rows), d_out_rows.stride(0), _ptr(out_rows), out_rows.stride(0),
+                                        d_out_rows.shape[0], heads, _ptr(tile_meta), _ptr(d_out_heads), _ptr(delta),
+                                        d_out_heads.shape[2], _stream()), "lx_attention_bwd_prep")

@@ -11,9 +11,9 @@ Python here is launch sequencing and pointer plumbing only; every arithmetic ste
   backward  dX of every Linear = the same tcgen05 GEMM against the transposed weight panel (row groups: text rows ->
             *_context^T, image rows -> W^T, condition rows -> (W + sBA)^T); lx_gate_bwd, lx_gelu_bwd, lx_ln_modulate_bwd,
             lx_qkv_post_bwd, lx_lora_grad, lx_flow_mse_loss.
-  LIBRARY CALL (interim, flagged in DESIGN.md): dQ/dK/dV of the joint attention come from torch's
-            scaled_dot_product_attention backward; a tcgen05 attention-backward kernel replaces `sdpa_backward_library`
-            in the next round.
+            dQ/dK/dV of the joint attention: lx_attention_bwd (tcgen05, P^T / dS^T resident in tensor memory) from the
+            log-sum-exp rows the forward kernel records.  `attn_bwd="library"` swaps in torch's SDPA autograd for A/B
+            checks only.
 
 Scope of the gradients: LoRA A / B of every target of train/config/seed_512.yaml:38 on the condition branch
 (`latent_lora=False`, the shipped configuration).  The CS3 / DGF encoders run forward-only (they are not in the
@@ -292,8 +292,11 @@ class FlowStepFunction(torch.autograd.Function):
 class DitTrainer:
     """Native forward + backward of the rectified-flow objective for one batch geometry."""
 
-    def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, model_config: Optional[dict] = None):
+    def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, model_config: Optional[dict] = None,
+                 attn_bwd: str = "native"):
         model_config = model_config or {}
+        assert attn_bwd in ("native", "library")
+        self.attn_bwd = attn_bwd
         if model_config.get("latent_lora", False):
             raise NotImplementedError("training with model_config.latent_lora=True (LoRA gradients from the image rows)")
         if n_cond <= 0:
@@ -313,7 +316,10 @@ class DitTrainer:
         self.a = dict(XN=self.plan.buf["XN"], QM=z(R, 7 * D), Cat=z(R, 5 * D), Y1=z(R, D), X1=z(R, D), XN2=z(R, D),
                       Hid=z(R, 4 * D), Y2=z(R, D))
         self.g = dict(dX=z(R, D), dX1=z(R, D), dY=z(R, D), dXN=z(R, D), dBig=z(R, 7 * D), dCat=z(R, 5 * D),
-                      dOh=z(B, self.H, S, 128))
+                      dOh=z(B, self.H, S, 128), dQh=z(B, self.H, S, 128), dKh=z(B, self.H, S, 128), dVh=z(B, self.H, S, 128))
+        self.lse = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
+        self.delta = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
+        self.dq32 = torch.zeros((B, self.H, S, 128), device=dev, dtype=torch.float32)
         self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
         self.lora_ws = torch.zeros((2 * max(self.Rc, B) * max(cfg.lora_rank, 1),), device=dev, dtype=torch.float32)
         self.ckpt = torch.zeros((cfg.num_layers + cfg.num_single_layers, R, D), **bf)
@@ -414,16 +420,23 @@ class DitTrainer:
             c += width
 
     def _attention(self, out):
-        """out: [R, ld] view; head h lands in columns [128h, 128h+128)."""
+        """out: [R, ld] view; head h lands in columns [128h, 128h+128).  Also records the log-sum-exp rows."""
         b, p = self.plan.buf, self.plan.plan
         ops.attention(b["Q"], b["K"], b["V"], out, b["out_row_base"], n_cond=self.nc, mask_mode=p.mask_mode,
-                      cross_bias=p.cross_bias)
+                      cross_bias=p.cross_bias, lse=self.lse)
 
-    def _attention_bwd(self, d_rows):
-        """d_rows: [R, >= D] view holding dO in its first D columns -> dq, dk, dv head-major."""
-        b, p = self.plan.buf, self.plan.plan
-        rows_to_heads(d_rows, self.H, b["tile_meta"], self.g["dOh"])
-        return sdpa_backward_library(b["Q"], b["K"], b["V"], self.g["dOh"], self.nc, p.mask_mode, p.cross_bias)
+    def _attention_bwd(self, d_rows, o_rows):
+        """d_rows / o_rows: [R, >= D] views holding dO / O in their first D columns -> dq, dk, dv head-major (bf16)."""
+        b, p, g = self.plan.buf, self.plan.plan, self.g
+        if self.attn_bwd == "library":  # A/B check only: torch SDPA autograd
+            rows_to_heads(d_rows, self.H, b["tile_meta"], g["dOh"])
+            return sdpa_backward_library(b["Q"], b["K"], b["V"], g["dOh"], self.nc, p.mask_mode, p.cross_bias)
+        ops.attention_bwd_prep(d_rows, o_rows, self.H, b["tile_meta"], g["dOh"], self.delta)
+        self.dq32.zero_()
+        ops.attention_bwd(b["Q"], b["K"], b["V"], g["dOh"], self.lse, self.delta, self.dq32, g["dKh"], g["dVh"],
+                          n_cond=self.nc, mask_mode=p.mask_mode, cross_bias=p.cross_bias)
+        L.check(_lib.lx_cast(self.dq32.data_ptr(), g["dQh"].data_ptr(), self.dq32.numel(), 1, _stream()), "lx_cast")
+        return g["dQh"], g["dKh"], g["dVh"]
 
     # -- blocks -------------------------------------------------------------------------------------------------------
     def _double_fwd(self, i):
@@ -469,7 +482,7 @@ class DitTrainer:
         self._lora_grads([pfx + "attn.to_out.0"], O[c0:], g["dY"][c0:])
         d_o = g["dCat"][:, :D]
         self._gemm(g["dY"], W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], d_o, transposed=True)
-        dq, dk, dv = self._attention_bwd(d_o)
+        dq, dk, dv = self._attention_bwd(d_o, O)
         nq, nk, naq, nak = (W[f"double.{i}.{n}"] for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
         d_pre = g["dBig"][:, :3 * D]
         qkv_post_bwd(pre, dq, dk, dv, d_pre, self.H, tm, [naq, nq, nq], [nak, nk, nk], b["rope"])
@@ -501,7 +514,7 @@ class DitTrainer:
         self._lora_grads([pfx + "proj_out"], a["Cat"][c0:], g["dY"][c0:])
         self._gemm(g["dY"], W[f"single.{i}.proj_out"], None, g["dCat"], transposed=True)
         gelu_bwd(a["QM"][:, 3 * D:], g["dCat"][:, D:], g["dBig"][:, 3 * D:])
-        dq, dk, dv = self._attention_bwd(g["dCat"])
+        dq, dk, dv = self._attention_bwd(g["dCat"], a["Cat"])
         nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
         qkv_post_bwd(a["QM"], dq, dk, dv, g["dBig"], self.H, tm, [nq, nq, nq], [nk, nk, nk], b["rope"])
         self._lora_grads([pfx + "attn.to_q", pfx + "attn.to_k", pfx + "attn.to_v", pfx + "proj_mlp"], a["XN"][c0:],

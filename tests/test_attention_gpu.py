@@ -11,6 +11,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
 def _mk(shape, scale, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
@@ -112,3 +117,106 @@ def test_attention_flux_shape_throughput():
     got = out.reshape(S, H, 128).permute(1, 0, 2).float()  # B == 1: stream-major rows == sequence order
     err = (got - ref[0]).abs()
     assert (err <= 4e-3 + ref[0].abs() / 128).all(), err.max()
+
+
+def _sdpa_ref_grads(q, k, v, d_out, n_cond, mask_mode, c_factor):
+    import math
+
+    import torch.nn.functional as F
+
+    S = q.shape[2]
+    mask = None
+    if n_cond > 0:
+        if c_factor is not None:
+            mask = torch.zeros(S, S, device=q.device)
+            mask[-n_cond:, :-n_cond] = math.log(c_factor)
+            mask[:-n_cond, -n_cond:] = math.log(c_factor)
+        elif mask_mode == 1:
+            mask = torch.ones(S, S, device=q.device, dtype=torch.bool)
+            mask[-n_cond:, :-n_cond] = False
+            mask[:-n_cond, -n_cond:] = False
+        elif mask_mode == 2:
+            mask = torch.ones(S, S, device=q.device, dtype=torch.bool)
+            mask[-n_cond:, :-n_cond] = False
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    o = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask)
+    return (o,) + torch.autograd.grad(o, (qf, kf, vf), d_out.float())
+
+
+@pytest.mark.parametrize("B,H,nt,ni,nc,mask_mode,c_factor", [
+    (1, 1, 128, 0, 0, 0, None), (2, 2, 128, 128, 128, 0, None), (1, 2, 128, 256, 256, 1, None),
+    (1, 2, 128, 256, 256, 2, None), (1, 2, 256, 256, 128, 0, 1.7), (1, 3, 512, 1024, 1024, 0, None)])
+def test_attention_backward_vs_autograd(B, H, nt, ni, nc, mask_mode, c_factor):
+    """lx_attention (with lse) + lx_attention_bwd_prep + lx_attention_bwd against fp32 autograd of SDPA on the same
+    bf16 inputs.  Tolerance: relL2 <= 2e-2 per gradient (bf16 P / dS operands, fp32 accumulation)."""
+    import math
+
+    from loongx_b200 import ops
+
+    S = nt + ni + nc
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + S)
+    mk = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device="cuda") * scale).bfloat16()  # noqa: E731
+    q, k, v, d_o = mk(B, H, S, 128), mk(B, H, S, 128), mk(B, H, S, 128), mk(B, H, S, 128)
+    tm = ops.make_tile_meta(B, nt, ni, nc, "cuda")
+    orb = ops.make_out_row_base(B, nt, ni, nc, "cuda")
+    R, D = B * S, H * 128
+    out_rows = torch.zeros(R, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, S, device="cuda")
+    cb = math.log(c_factor) if c_factor is not None else 0.0
+    ops.attention(q, k, v, out_rows, orb, n_cond=nc, mask_mode=mask_mode, cross_bias=cb, lse=lse)
+    o_ref, dq_ref, dk_ref, dv_ref = _sdpa_ref_grads(q, k, v, d_o, nc, mask_mode, c_factor)
+    # lse (log2 domain) against the reference softmax normaliser
+    sc = 1.0 / math.sqrt(128)
+    logits = torch.einsum("bhqd,bhkd->bhqk", q.float(), k.float()) * sc
+    if nc > 0 and c_factor is not None:
+        logits[..., -nc:, :-nc] += cb
+        logits[..., :-nc, -nc:] += cb
+    elif nc > 0 and mask_mode == 1:
+        logits[..., -nc:, :-nc] = -float("inf")
+        logits[..., :-nc, -nc:] = -float("inf")
+    elif nc > 0 and mask_mode == 2:
+        logits[..., -nc:, :-nc] = -float("inf")
+    lse_ref = torch.logsumexp(logits, -1) / math.log(2.0)
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    # dO in the stream-major row layout (what the training step holds) -> prep -> backward
+    def to_rows(x):  # [B,H,S,128] -> [R, D]
+        xs = x.permute(0, 2, 1, 3).reshape(B, S, D)
+        return torch.cat([xs[:, :nt].reshape(B * nt, D), xs[:, nt:nt + ni].reshape(B * ni, D), xs[:, nt + ni:].reshape(B * nc, D)])
+    d_rows = to_rows(d_o).contiguous()
+    d_heads = torch.zeros_like(d_o)
+    delta = torch.zeros(B, H, S, device="cuda")
+    ops.attention_bwd_prep(d_rows, out_rows, H, tm, d_heads, delta)
+    assert torch.equal(d_heads, d_o)
+    delta_ref = (d_o.float() * o_ref).sum(-1)
+    assert _rel(delta, delta_ref) < 2e-2
+    dq = torch.zeros(B, H, S, 128, device="cuda")
+    dk, dv = torch.zeros_like(q), torch.zeros_like(q)
+    ops.attention_bwd(q, k, v, d_heads, lse, delta, dq, dk, dv, n_cond=nc, mask_mode=mask_mode, cross_bias=cb)
+    torch.cuda.synchronize()
+    e = (_rel(dq, dq_ref), _rel(dk, dk_ref), _rel(dv, dv_ref))
+    print(f"\n[attn bwd B{B} H{H} S{S} mask{mask_mode} cf{c_factor}] relL2 dq {e[0]:.4g} dk {e[1]:.4g} dv {e[2]:.4g}")
+    assert max(e) < 2e-2, e
+
+
+def test_attention_backward_flux_shape_throughput():
+    from loongx_b200 import ops
+
+    B, H, S = 1, 24, 2560
+    g = torch.Generator(device="cuda").manual_seed(0)
+    mk = lambda: torch.randn(B, H, S, 128, generator=g, device="cuda").bfloat16()  # noqa: E731
+    q, k, v, d_o = mk(), mk(), mk(), mk()
+    lse = torch.randn(B, H, S, device="cuda") + 12.0
+    delta = torch.randn(B, H, S, device="cuda")
+    dq = torch.zeros(B, H, S, 128, device="cuda")
+    dk, dv = torch.zeros_like(q), torch.zeros_like(q)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ops.attention_bwd(q, k, v, d_o, lse, delta, dq, dk, dv, n_cond=1024)
+    e0.record()
+    for _ in range(10):
+        ops.attention_bwd(q, k, v, d_o, lse, delta, dq, dk, dv, n_cond=1024)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"\n[attn bwd] S=2560 H=24: {ms:.3f} ms  {10.0 * B * H * S * S * 128 / ms / 1e9:.0f} TFLOP/s")
+    assert torch.isfinite(dk.float()).all()
