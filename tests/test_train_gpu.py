@@ -382,3 +382,17 @@ def test_omini_model_step_api_and_optimizer():
     loss2 = float(m.step(batch).detach())  # step() re-merges the panels whose factors changed
     print(f"[OminiModel.step] loss after optimizer step {loss2:.6f}")
     assert loss2 < l1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL all-reduce of the LoRA-gradient bucket)")
+def test_ddp_gradient_allreduce_two_gpus():
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "scripts", "ddp_train_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(out.stdout[-2000:], out.stderr[-2000:])
+    assert out.returncode == 0
