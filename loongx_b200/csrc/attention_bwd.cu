@@ -12,9 +12,11 @@
 //       dV_j += P^T  dO_i           TS   (A from TMEM, B = dO_i as MN-major smem operand)   -> TMEM cols [256,384)
 //       dK_j += dS^T Q_i            TS   (B = Q_i MN-major)                                 -> TMEM cols [384,512)
 //       dQ_i  = dS   K_j            SS   (A = the dS^T tile read MN-major, B = K_j MN-major) -> TMEM cols [128,256),
-//               read back by the compute threads and added to the fp32 dQ accumulator in global memory (red.v4.f32)
+//               read back by the compute threads, staged in shared memory and added to the fp32 dQ accumulator in
+//               global memory by the TMA unit (cp.reduce.async.bulk.tensor .add, one bulk op per 128 x 32 chunk)
 //   warp 0: TMA producer (K_j, V_j once; Q_i through a 2-stage ring, dO_i single-buffered: 192 KB of shared memory)
-//   warp 1: tcgen05.mma issuer        warps 2..5: compute (TMEM lane quarter = warp & 3)
+//   warp 1: tcgen05.mma issuer        warps 2..9: compute, two threads per key row (TMEM lane quarter = warp & 3,
+//           64 of the 128 query columns each)
 //   The tensor pipe executes in issue order, so S^T(i+1) may overwrite the columns P^T(i) / dS^T(i) are read from.
 //
 // Block masks (block.py:106-120) restrict the query-tile range of a key tile; the log(c_factor) bias (block.py:121-128)
@@ -27,8 +29,9 @@ namespace lx {
 
 constexpr int AB_TILE_BYTES = 128 * 128 * 2;
 constexpr int AB_ATOM_BYTES = 128 * 64 * 2;
-constexpr int AB_THREADS = 192;
-constexpr int AB_SMEM = 6 * AB_TILE_BYTES + 2 * 2 * 128 * 4 + 256 + 1024;
+constexpr int AB_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 compute warps
+constexpr int AB_DQ_SLOT = 128 * 32 * 4;  // 16 KiB: 128 query rows x 32 head dims fp32, one per compute group
+constexpr int AB_SMEM = 6 * AB_TILE_BYTES + 2 * AB_DQ_SLOT + 2 * 2 * 128 * 4 + 256;  // 226.25 KiB, base 1024-aligned
 
 struct AttnBwdParams {
   const float* lse;    // [B*H*S] log2-domain log-sum-exp of the forward
@@ -38,6 +41,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dv;
   int B, H, S, n_cond, mask_mode;
   float scale, scale_log2, bias_log2;
+  int dbg_flags;  // development aid: bit 0 = skip the dQ reduction (timing experiments only)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -47,15 +51,17 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                     const __grid_constant__ AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+                     const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the 128-byte-swizzle atoms need a 1 KiB-aligned base (no slack left)
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE_BYTES;
   uint8_t* sQ = sV + AB_TILE_BYTES;         // [2 stages]
   uint8_t* sdO = sQ + 2 * AB_TILE_BYTES;
   uint8_t* sdS = sdO + AB_TILE_BYTES;
-  float* sStat = reinterpret_cast<float*>(sdS + AB_TILE_BYTES);  // [2 parities][lse | delta][128]
+  uint8_t* sdQ = sdS + AB_TILE_BYTES;       // [2 compute groups] staging of dQ chunks for the TMA reduce
+  float* sStat = reinterpret_cast<float*>(sdQ + 2 * AB_DQ_SLOT);  // [2 parities][lse | delta][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128);
   uint64_t* kv_full = bars;        // 1
   uint64_t* q_full = bars + 1;     // [2]
@@ -92,6 +98,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmdO);
+    prefetch_tmap(&tmdQ);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
@@ -100,9 +107,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(do_full, 1);
     mbar_init(do_empty, 1);
     mbar_init(sp_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_read, 128);
+    mbar_init(dq_read, 256);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -212,10 +219,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     __syncwarp();
   } else {
-    // ---------------------------------------------------------------- compute warps: one key row per thread
+    // ------------------------------------------------- compute warps: one key row per thread PAIR (64 queries each)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 64 of the tile's 128 query columns this thread owns
     const int r = quarter * 32 + lane;
-    const int tid = threadIdx.x - 64;  // 0..127
+    const int tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     for (int it = 0; it < n_it; ++it) {
       const int qi = q_begin + it;
@@ -223,23 +231,26 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float bias = cross ? p.bias_log2 : 0.f;
       float* st_lse = sStat + (it & 1) * 256;
       float* st_del = st_lse + 128;
-      st_lse[tid] = p.lse[head_row0 + qi * 128 + tid];
-      st_del[tid] = p.delta[head_row0 + qi * 128 + tid];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < 128) st_lse[tid] = p.lse[head_row0 + qi * 128 + tid];
+      else st_del[tid - 128] = p.delta[head_row0 + qi * 128 + tid - 128];
       mbar_wait(sp_full, it & 1);
       tc_fence_after();
-      uint32_t s[128];
-      tmem_ld_32x32b_x128(tm_S + lane_off, s);
+      uint32_t s[64];
+      tmem_ld_32x32b_x64(tm_S + lane_off + half * 64, s);
+      // every thread has its S^T values in registers (and the statistics are staged) before anyone overwrites the
+      // S^T columns with packed P^T / dS^T
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;  // 32-query chunk of the tile
         uint32_t dp[32];
         tmem_ld_32x32b_x32(tm_dP + lane_off + c * 32, dp);
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int q0 = c * 32 + 2 * jj;
-          const float p0 = ex2_approx(__uint_as_float(s[q0]) * p.scale_log2 + (bias - st_lse[q0]));
-          const float p1 = ex2_approx(__uint_as_float(s[q0 + 1]) * p.scale_log2 + (bias - st_lse[q0 + 1]));
+          const float p0 = ex2_approx(__uint_as_float(s[cc * 32 + 2 * jj]) * p.scale_log2 + (bias - st_lse[q0]));
+          const float p1 = ex2_approx(__uint_as_float(s[cc * 32 + 2 * jj + 1]) * p.scale_log2 + (bias - st_lse[q0 + 1]));
           const float d0 = p.scale * p0 * (__uint_as_float(dp[2 * jj]) - st_del[q0]);
           const float d1 = p.scale * p1 * (__uint_as_float(dp[2 * jj + 1]) - st_del[q0 + 1]);
           pk[jj] = pack_bf16(p0, p1);
@@ -259,24 +270,40 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
-      // dQ_i (lanes = query rows) -> global fp32 accumulator
+      // dQ_i (lanes = query rows, this group's 64 of the 128 head dims): TMEM -> registers -> 128B-swizzled staging tile
+      // -> ONE cp.reduce.async.bulk.tensor (+=) per 128 x 32 chunk; the L2 does the fp32 adds on whole lines instead of
+      // 4096 scattered 16-byte atomics per tile
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
-      float* dq_row = p.dq + ((size_t)(head_row0 + qi * 128 + r)) * 128;
+      uint8_t* slot = sdQ + half * AB_DQ_SLOT;
+      const bool issuer = (threadIdx.x == 64 + 128 * half);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
-        tmem_ld_32x32b_x32(tm_dP + lane_off + c * 32, o);
+        tmem_ld_32x32b_x32(tm_dP + lane_off + half * 64 + c * 32, o);
+        if (c == 1) {  // this thread's part of dQ_i has left tensor memory
+          tc_fence_before();
+          mbar_arrive(dq_read);
+        }
+        if (issuer) tma_store_wait_read<0>();  // the previous chunk's bulk read of the slot is complete
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+        if (!(p.dbg_flags & 1)) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          red_add_v4(dq_row + c * 32 + e, __uint_as_float(o[e]), __uint_as_float(o[e + 1]), __uint_as_float(o[e + 2]),
-                     __uint_as_float(o[e + 3]));
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(slot + r * 128 + ((ch ^ (r & 7)) << 4)) =
+                make_uint4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+        if (issuer && !(p.dbg_flags & 1)) {
+          tma_reduce_add_2d(&tmdQ, slot, half * 64 + c * 32, head_row0 + qi * 128);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(dq_read);
     }
-    // epilogue: dV_j, dK_j (lanes = key rows) -> bf16 rows
-    const size_t out_row = ((size_t)(head_row0 + j * 128 + r)) * 128;
+    if (threadIdx.x == 64 || threadIdx.x == 192) tma_store_wait_read<0>();  // staging must outlive the last bulk read
+    // epilogue: dV_j, dK_j (lanes = key rows, this thread's 64 head dims) -> bf16 rows
+    const size_t out_row = ((size_t)(head_row0 + j * 128 + r)) * 128 + half * 64;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
@@ -285,9 +312,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int which = 0; which < 2; ++which) {
       __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) + out_row;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
-        if (n_it > 0) tmem_ld_32x32b_x32((which == 0 ? tm_dV : tm_dK) + lane_off + c * 32, o);
+        if (n_it > 0) tmem_ld_32x32b_x32((which == 0 ? tm_dV : tm_dK) + lane_off + half * 64 + c * 32, o);
         else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) o[e] = 0u;
@@ -353,6 +380,9 @@ extern "C" int lx_attention_bwd_prep(const void* d_out_rows, int64_t ld_do, cons
   return LX_OK;
 }
 
+static int g_attn_bwd_dbg = 0;
+extern "C" void lx_attention_bwd_debug_flags(int flags) { g_attn_bwd_dbg = flags; }
+
 extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   LX_CHECK_ARG(desc != nullptr, "lx_attention_bwd: null descriptor");
   const lx_attn_bwd_desc_t& d = *desc;
@@ -363,8 +393,9 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.mask_mode >= 0 && d.mask_mode <= 2, "lx_attention_bwd: bad mask_mode=%d", d.mask_mode);
   LX_CHECK_ARG(d.H <= 65535 && d.B <= 65535, "lx_attention_bwd: grid too large");
   const uint64_t rows = (uint64_t)d.B * d.H * d.S;
-  CUtensorMap tmQ, tmK, tmV, tmdO;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
   int rc;
+  if ((rc = make_tmap_2d_f32(&tmdQ, d.dq, rows, 128, 128, 128, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmQ, d.q, rows, 128, 128, 128, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmK, d.k, rows, 128, 128, 128, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmV, d.v, rows, 128, 128, 128, 64))) return rc;
@@ -378,6 +409,7 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   p.scale = d.scale;
   p.scale_log2 = d.scale * log2e;
   p.bias_log2 = d.cross_bias * log2e;
+  p.dbg_flags = g_attn_bwd_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     LX_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -391,7 +423,7 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   }
   LaunchScope scope(KC_ATTENTION, stream, 10.0 * d.B * d.H * pairs * 128.0);  // five 2*S*S*128 products
   attention_bwd_kernel<<<dim3(d.S / 128, d.H, d.B), AB_THREADS, AB_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV,
-                                                                                                             tmdO, p);
+                                                                                                             tmdO, tmdQ, p);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -59,6 +59,32 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return LX_OK;
 }
 
+// fp32 variant (box_cols * 4 bytes must be 128): used as the destination of cp.reduce.async.bulk.tensor (+= tiles)
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return LX_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) != 0) {
+    set_error("tensor map (f32): base must be 16-byte aligned and row stride a multiple of 4 elements");
+    return LX_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d f32) failed: %d", (int)r);
+    return LX_ERR_CUDA;
+  }
+  return LX_OK;
+}
+
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint64_t outer_stride, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();

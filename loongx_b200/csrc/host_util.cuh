@@ -34,6 +34,8 @@ void set_error(const char* fmt, ...);
 // clipped on store.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols);
 // 3-D variant: dims (cols, rows, outer) with strides (ld, outer_stride) in elements.
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint64_t outer_stride, uint32_t box_rows, uint32_t box_cols);

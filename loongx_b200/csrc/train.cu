@@ -369,56 +369,94 @@ __global__ void __launch_bounds__(128) rows_to_heads_kernel(const __nv_bfloat16*
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LORA_MAX_R = 16;
 
+// RPW rows per warp: the factor values F[c, 0:r] are loaded once per lane and reused across the rows, so the kernel
+// streams Z (bf16, 4 bytes per lane per row, RPW independent rows in flight) instead of re-reading F for every row.
+template <int RMAX, int RPW>
 __global__ void __launch_bounds__(128) lora_project_kernel(const __nv_bfloat16* __restrict__ Z, int64_t ldz, int M, int C,
                                                            const float* __restrict__ F, int64_t f_stride_c,
                                                            int64_t f_stride_j, int r, float* __restrict__ P) {
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float acc[LORA_MAX_R];
+  const int row0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * RPW, lane = threadIdx.x & 31;
+  if (row0 >= M) return;
+  float acc[RPW][RMAX];
 #pragma unroll
-  for (int j = 0; j < LORA_MAX_R; ++j) acc[j] = 0.f;
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) acc[i][j] = 0.f;
   for (int c = lane * 2; c < C; c += 64) {
-    const float2 z = unpack_bf16(*reinterpret_cast<const uint32_t*>(Z + (size_t)row * ldz + c));
+    float f0[RMAX], f1[RMAX];
 #pragma unroll
-    for (int j = 0; j < LORA_MAX_R; ++j)
-      if (j < r) acc[j] += z.x * F[(size_t)c * f_stride_c + j * f_stride_j] + z.y * F[(size_t)(c + 1) * f_stride_c + j * f_stride_j];
+    for (int j = 0; j < RMAX; ++j) {
+      f0[j] = j < r ? F[(size_t)c * f_stride_c + j * f_stride_j] : 0.f;
+      f1[j] = j < r ? F[(size_t)(c + 1) * f_stride_c + j * f_stride_j] : 0.f;
+    }
+    float2 z[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int row = min(row0 + i, M - 1);
+      z[i] = unpack_bf16(*reinterpret_cast<const uint32_t*>(Z + (size_t)row * ldz + c));
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) acc[i][j] += z[i].x * f0[j] + z[i].y * f1[j];
   }
 #pragma unroll
-  for (int j = 0; j < LORA_MAX_R; ++j)
-    if (j < r) {
-      const float s = warp_sum(acc[j]);
-      if (lane == 0) P[(size_t)row * r + j] = s;
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      const float sm = warp_sum(acc[i][j]);
+      if (lane == 0 && j < r && row0 + i < M) P[(size_t)(row0 + i) * r + j] = sm;
     }
 }
 
+// G[c, j] += s * sum_m Z[m, c] P[m, j]: one CTA = 128 rows x 512 columns, 4 adjacent columns (8 bytes) per thread,
+// four rows in flight per thread; P rows are broadcast from shared memory.
+template <int RMAX>
 __global__ void __launch_bounds__(128) lora_reduce_kernel(const __nv_bfloat16* __restrict__ Z, int64_t ldz, int M, int C,
                                                           const float* __restrict__ P, int r, float scaling,
                                                           float* __restrict__ G, int64_t g_stride_c, int64_t g_stride_j) {
-  __shared__ float ps[128 * LORA_MAX_R];
+  __shared__ float ps[128 * RMAX];
   const int r0 = blockIdx.x * 128, r1 = min(M, r0 + 128);
-  for (int i = threadIdx.x; i < (r1 - r0) * r; i += 128) ps[i] = P[(size_t)r0 * r + i];
+  for (int i = threadIdx.x; i < 128 * RMAX; i += 128) {
+    const int m = i / RMAX, j = i % RMAX;
+    ps[i] = (r0 + m < r1 && j < r) ? P[(size_t)(r0 + m) * r + j] : 0.f;
+  }
   __syncthreads();
-  const int c = blockIdx.y * 256 + threadIdx.x * 2;
+  const int c = blockIdx.y * 512 + threadIdx.x * 4;
   if (c >= C) return;
-  float ax[LORA_MAX_R], ay[LORA_MAX_R];
+  float acc[4][RMAX];
 #pragma unroll
-  for (int j = 0; j < LORA_MAX_R; ++j) ax[j] = ay[j] = 0.f;
-  for (int m = r0; m < r1; ++m) {
-    const float2 z = unpack_bf16(*reinterpret_cast<const uint32_t*>(Z + (size_t)m * ldz + c));
+  for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int j = 0; j < LORA_MAX_R; ++j)
-      if (j < r) {
-        const float p = ps[(m - r0) * r + j];
-        ax[j] += z.x * p;
-        ay[j] += z.y * p;
+    for (int j = 0; j < RMAX; ++j) acc[e][j] = 0.f;
+  const int nrow = r1 - r0;
+  for (int m = 0; m < nrow; m += 4) {
+    uint2 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int mm = min(m + i, nrow - 1);  // rows past the end re-read the last row and multiply by ps = 0
+      u[i] = *reinterpret_cast<const uint2*>(Z + (size_t)(r0 + mm) * ldz + c);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = unpack_bf16(u[i].x), b = unpack_bf16(u[i].y);
+      const float* pr = ps + (m + i < nrow ? m + i : 127) * RMAX;
+      const float valid = (m + i < nrow) ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        const float pv = pr[j] * valid;
+        acc[0][j] += a.x * pv;
+        acc[1][j] += a.y * pv;
+        acc[2][j] += b.x * pv;
+        acc[3][j] += b.y * pv;
       }
+    }
   }
 #pragma unroll
-  for (int j = 0; j < LORA_MAX_R; ++j)
-    if (j < r) {
-      atomicAdd(G + (size_t)c * g_stride_c + j * g_stride_j, scaling * ax[j]);
-      atomicAdd(G + (size_t)(c + 1) * g_stride_c + j * g_stride_j, scaling * ay[j]);
-    }
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j)
+      if (j < r) atomicAdd(G + (size_t)(c + e) * g_stride_c + j * g_stride_j, scaling * acc[e][j]);
 }
 
 // out[n, k] = bf16(W[n, k] + s * sum_j B[n, j] A[j, k])   (the merged panel the LoRA-active row group multiplies by)
@@ -648,16 +686,26 @@ extern "C" int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t 
                             float* dA, float* dB, int32_t M, int32_t K, int32_t N, int32_t r, float scaling,
                             float* workspace, void* stream) {
   LX_CHECK_ARG(x && dy && A && Bw && dA && dB && workspace && M > 0 && K > 0 && N > 0, "lx_lora_grad: bad arguments");
-  LX_CHECK_ARG(r > 0 && r <= LORA_MAX_R && K % 2 == 0 && N % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0,
-               "lx_lora_grad: rank %d must be in [1, %d], K / N / strides even", r, LORA_MAX_R);
+  LX_CHECK_ARG(r > 0 && r <= LORA_MAX_R && K % 4 == 0 && N % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0,
+               "lx_lora_grad: rank %d must be in [1, %d], K / N / strides multiples of 4", r, LORA_MAX_R);
   float* P1 = workspace;                  // [M, r] = dy B
   float* P2 = workspace + (size_t)M * r;  // [M, r] = x A^T
-  const unsigned gm = (M + 3) / 4, gr = (M + 127) / 128;
+  cudaStream_t st = cs(stream);
+  const unsigned gr = (M + 127) / 128;
   LaunchScope scope(KC_ROW, stream, 4.0 * M * ((double)K + N));
-  lora_project_kernel<<<gm, 128, 0, cs(stream)>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);        // F[c=n, j] = B[n*r + j]
-  lora_project_kernel<<<gm, 128, 0, cs(stream)>>>(bf(x), ldx, M, K, A, 1, K, r, P2);          // F[c=k, j] = A[j*K + k]
-  lora_reduce_kernel<<<dim3(gr, (K + 255) / 256), 128, 0, cs(stream)>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
-  lora_reduce_kernel<<<dim3(gr, (N + 255) / 256), 128, 0, cs(stream)>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
+  if (r <= 4) {
+    const unsigned gm = (M + 31) / 32;  // 4 warps x 8 rows
+    lora_project_kernel<4, 8><<<gm, 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
+    lora_project_kernel<4, 8><<<gm, 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);    // F[c=k, j] = A[j*K + k]
+    lora_reduce_kernel<4><<<dim3(gr, (K + 511) / 512), 128, 0, st>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
+    lora_reduce_kernel<4><<<dim3(gr, (N + 511) / 512), 128, 0, st>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
+  } else {
+    const unsigned gm = (M + 7) / 8;  // 4 warps x 2 rows
+    lora_project_kernel<LORA_MAX_R, 2><<<gm, 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);
+    lora_project_kernel<LORA_MAX_R, 2><<<gm, 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);
+    lora_reduce_kernel<LORA_MAX_R><<<dim3(gr, (K + 511) / 512), 128, 0, st>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
+    lora_reduce_kernel<LORA_MAX_R><<<dim3(gr, (N + 511) / 512), 128, 0, st>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
+  }
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
