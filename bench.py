@@ -280,8 +280,15 @@ def run_native(args, rank, local_rank, world):
     gemm_tf = work[0] / ms[0] / 1e9 if ms[0] else 0.0
     att_tf = work[1] / ms[1] / 1e9 if ms[1] else 0.0
     row_gbs = work[2] / ms[2] / 1e6 if ms[2] else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic_r1e.json")
+    if os.path.exists(tp) and B == 1:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     roofline = {"bound": "tensor", "kernel": "lx::gemm_bf16_kernel (tcgen05 GEMM + fused epilogues)", "achieved": gemm_tf,
-                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tflops"], "traffic": None,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tflops"], "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram read + write), average over the 152 block GEMMs of a step",
+                "traffic_source": traffic_src,
                 "peak_source": peaks["which"], "launches_per_edit": int(cnt[0]), "avg_launch_us": ms[0] / max(cnt[0], 1) * 1e3,
                 "share_of_edit": ms[0] / tot_ms,
                 "method": "CUDA events around every launch of one extra edit, on the launching stream (lx_profile_*)"}

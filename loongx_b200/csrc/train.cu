@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(128) rows_to_heads_kernel(const __nv_bfloat16*
 // kernel 2: G[c, j]  += s * sum_m Z[m, c] * P[m, j]       (128-row chunk x 256 columns per CTA, atomics)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LORA_MAX_R = 16;
+constexpr int LORA_CCHUNK = 2048;  // columns per CTA of the projection kernel (fills the GPU when M is small)
 
 // RPW rows per warp: the factor values F[c, 0:r] are loaded once per lane and reused across the rows, so the kernel
 // streams Z (bf16, 4 bytes per lane per row, RPW independent rows in flight) instead of re-reading F for every row.
@@ -377,12 +378,13 @@ __global__ void __launch_bounds__(128) lora_project_kernel(const __nv_bfloat16* 
                                                            int64_t f_stride_j, int r, float* __restrict__ P) {
   const int row0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * RPW, lane = threadIdx.x & 31;
   if (row0 >= M) return;
+  const int c_begin = blockIdx.y * LORA_CCHUNK, c_end = min(C, c_begin + LORA_CCHUNK);  // column split: partial sums
   float acc[RPW][RMAX];
 #pragma unroll
   for (int i = 0; i < RPW; ++i)
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) acc[i][j] = 0.f;
-  for (int c = lane * 2; c < C; c += 64) {
+  for (int c = c_begin + lane * 2; c < c_end; c += 64) {
     float f0[RMAX], f1[RMAX];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(128) lora_project_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
       const float sm = warp_sum(acc[i][j]);
-      if (lane == 0 && j < r && row0 + i < M) P[(size_t)(row0 + i) * r + j] = sm;
+      if (lane == 0 && j < r && row0 + i < M) atomicAdd(P + (size_t)(row0 + i) * r + j, sm);  // P zeroed by the launcher
     }
 }
 
@@ -693,16 +695,18 @@ extern "C" int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t 
   cudaStream_t st = cs(stream);
   const unsigned gr = (M + 127) / 128;
   LaunchScope scope(KC_ROW, stream, 4.0 * M * ((double)K + N));
+  LX_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * (size_t)M * r, st));
+  const unsigned gn = (N + LORA_CCHUNK - 1) / LORA_CCHUNK, gk = (K + LORA_CCHUNK - 1) / LORA_CCHUNK;
   if (r <= 4) {
     const unsigned gm = (M + 31) / 32;  // 4 warps x 8 rows
-    lora_project_kernel<4, 8><<<gm, 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
-    lora_project_kernel<4, 8><<<gm, 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);    // F[c=k, j] = A[j*K + k]
+    lora_project_kernel<4, 8><<<dim3(gm, gn), 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
+    lora_project_kernel<4, 8><<<dim3(gm, gk), 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);    // F[c=k, j] = A[j*K + k]
     lora_reduce_kernel<4><<<dim3(gr, (K + 511) / 512), 128, 0, st>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
     lora_reduce_kernel<4><<<dim3(gr, (N + 511) / 512), 128, 0, st>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
   } else {
     const unsigned gm = (M + 7) / 8;  // 4 warps x 2 rows
-    lora_project_kernel<LORA_MAX_R, 2><<<gm, 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);
-    lora_project_kernel<LORA_MAX_R, 2><<<gm, 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);
+    lora_project_kernel<LORA_MAX_R, 2><<<dim3(gm, gn), 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);
+    lora_project_kernel<LORA_MAX_R, 2><<<dim3(gm, gk), 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);
     lora_reduce_kernel<LORA_MAX_R><<<dim3(gr, (K + 511) / 512), 128, 0, st>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
     lora_reduce_kernel<LORA_MAX_R><<<dim3(gr, (N + 511) / 512), 128, 0, st>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
   }

@@ -8,7 +8,8 @@ from loongx_b200.dit import DitWeights, DitPlan, random_params, euler_step
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 4
-cfg = FluxConfig()
+_l = os.environ.get("LX_LAYERS")  # e.g. "1,1": shallow model at full width for ncu captures
+cfg = FluxConfig(num_layers=int(_l.split(",")[0]), num_single_layers=int(_l.split(",")[1])) if _l else FluxConfig()
 dev = "cuda"
 t0 = time.time()
 P = random_params(cfg, dev)
