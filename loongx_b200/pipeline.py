@@ -61,6 +61,54 @@ class NativeFluxTransformer:
         self.single_transformer_blocks = [_BlockHandle(self, i, True) for i in range(cfg.num_single_layers)]
         self._plans: Dict[tuple, DitPlan] = {}
 
+    # -- checkpoints --------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, flux_path: str, device="cuda", lora_rank: int = 4, lora_alpha: float = 4.0, seed: int = 1234):
+        """diffusers-format FLUX transformer directory -> native weights; fresh LoRA factors like
+        `transformer.add_adapter(LoraConfig(init_lora_weights="gaussian"))` (model.py:519): A ~ N(0, 1/r), B = 0."""
+        from .checkpoint import read_diffusers_transformer
+
+        cfg, P = read_diffusers_transformer(flux_path, device=device, lora_rank=lora_rank, lora_alpha=lora_alpha)
+        init_lora_factors(P, cfg, device, seed)
+        return cls(cfg, P, device=device, consume_params=True)
+
+    def load_params(self, params: Dict[str, torch.Tensor]) -> None:
+        """Replace every weight (base + LoRA factors) from a flat diffusers-named dict; drops the cached plans."""
+        from .checkpoint import check_transformer_params
+
+        check_transformer_params(params, self.cfg)
+        self._plans.clear()
+        self.weights = None  # free the old panels before packing the new ones
+        self.weights = DitWeights(dict(params), self.cfg, self.device, consume=True)
+
+    def load_lora_factors(self, lora: Dict[str, torch.Tensor]) -> int:
+        """Overwrite LoRA factors in place (`<module>.lora_A.weight` / `.lora_B.weight`) and re-merge the affected
+        panels with the native merge kernel; returns the number of modules updated."""
+        from .dit import PackedLinear
+        from .train import lora_merge, transpose
+
+        seen = set()
+        for panel in self.weights.named.values():
+            if not isinstance(panel, PackedLinear):
+                continue
+            for (name, row0, rows, A, Bw) in panel.lora:
+                ka, kb = name + ".lora_A.weight", name + ".lora_B.weight"
+                if ka not in lora and kb not in lora:
+                    continue
+                if lora[ka].shape != A.shape or lora[kb].shape != Bw.shape:
+                    raise ValueError(f"{name}: LoRA factors {tuple(lora[ka].shape)} / {tuple(lora[kb].shape)} do not match "
+                                     f"rank-{A.shape[0]} factors {tuple(A.shape)} / {tuple(Bw.shape)}")
+                A.copy_(lora[ka].to(device=A.device, dtype=A.dtype))
+                Bw.copy_(lora[kb].to(device=A.device, dtype=A.dtype))
+                lora_merge(panel.w[row0:row0 + rows], A, Bw, panel.w_lora[row0:row0 + rows], panel.scaling)
+                if panel.w_loraT is not None:
+                    transpose(panel.w_lora[row0:row0 + rows], panel.w_loraT[:, row0:row0 + rows])
+                seen.add(name)
+        unknown = {k.rsplit(".lora_", 1)[0] for k in lora} - seen
+        if unknown:
+            raise KeyError(f"LoRA factors for modules that are not LoRA targets here: {sorted(unknown)[:4]}")
+        return len(seen)
+
     # -- nn.Module-like surface --------------------------------------------------------------------------------
     def named_modules(self):
         yield "", self
@@ -99,6 +147,22 @@ class NativeFluxTransformer:
             pl = DitPlan(self.weights, B, n_txt, n_img, n_cond, T=T, model_config=mc, c_factor=c_factor)
             self._plans[key] = pl
         return pl
+
+
+def init_lora_factors(P: Dict[str, torch.Tensor], cfg: FluxConfig, device, seed: int = 1234, b_std: float = 0.0) -> None:
+    """peft 'gaussian' initialisation of every LoRA target that has no factors yet (in place)."""
+    from .config import lora_targets
+
+    if cfg.lora_rank <= 0:
+        return
+    g = torch.Generator(device=device).manual_seed(seed)
+    for name in lora_targets(cfg):
+        if name + ".lora_A.weight" in P:
+            continue
+        o, i = P[name + ".weight"].shape
+        P[name + ".lora_A.weight"] = torch.randn(cfg.lora_rank, i, generator=g, device=device) / cfg.lora_rank
+        P[name + ".lora_B.weight"] = (torch.randn(o, cfg.lora_rank, generator=g, device=device) * b_std) if b_std > 0 else \
+            torch.zeros(o, cfg.lora_rank, device=device)
 
 
 class _Scheduler(FlowMatchEulerDiscreteScheduler):

@@ -26,15 +26,21 @@ class OminiModel(nn.Module):
         super().__init__()
         if dtype != torch.bfloat16:
             raise NotImplementedError("the native DiT computes in bf16 (fp32 accumulate); CS3/DGF run in float32")
+        import os
+
+        r = int((lora_config or {}).get("r", 4))
+        alpha = float((lora_config or {}).get("lora_alpha", 4.0))
+        pretrained = None
         if isinstance(flux_pipe_id, FluxConfig):
             cfg = flux_pipe_id
         elif flux_pipe_id == "synthetic":
             cfg = FluxConfig()
+        elif isinstance(flux_pipe_id, str) and os.path.isdir(flux_pipe_id):
+            pretrained, cfg = flux_pipe_id, None  # diffusers-format directory (FluxPipeline.from_pretrained, model.py:398)
         else:
-            raise NotImplementedError(f"checkpoint loading ({flux_pipe_id!r}) is not built yet: pass a FluxConfig or 'synthetic'")
-        if lora_config is not None:
-            cfg.lora_rank = int(lora_config.get("r", cfg.lora_rank))
-            cfg.lora_alpha = float(lora_config.get("lora_alpha", cfg.lora_alpha))
+            raise FileNotFoundError(f"{flux_pipe_id!r}: expected a FluxConfig, 'synthetic' or a diffusers-format FLUX directory")
+        if cfg is not None and lora_config is not None:
+            cfg.lora_rank, cfg.lora_alpha = r, alpha
         if lora_path:
             raise NotImplementedError  # model.py:517 raises as well
         self.model_config = model_config
@@ -42,7 +48,12 @@ class OminiModel(nn.Module):
         self._dtype = dtype
         self._device = torch.device(device)
         torch.manual_seed(seed)
-        self.transformer = NativeFluxTransformer(cfg, device=device, seed=seed)
+        if pretrained is not None:
+            self.transformer = NativeFluxTransformer.from_pretrained(pretrained, device=device, lora_rank=r, lora_alpha=alpha,
+                                                                     seed=seed)
+            cfg = self.transformer.cfg
+        else:
+            self.transformer = NativeFluxTransformer(cfg, device=device, seed=seed)
         self.transformer.gradient_checkpointing = gradient_checkpointing
         self.flux_pipe = NativeFluxPipeline(self.transformer)
         self.fuse_flag = fuse_flag
@@ -67,6 +78,30 @@ class OminiModel(nn.Module):
     @property
     def device(self):
         return self._device
+
+    # ---- checkpoints (model.py:464-477, 526-531; inference.py:43-53) ------------------------------------------------
+    def load_lora(self, checkpoint_path: str):
+        """peft LoRA weights written by `save_lora` / FluxPipeline.save_lora_weights -> factors + native re-merge."""
+        from loongx_b200.checkpoint import read_peft_lora
+
+        n = self.transformer.load_lora_factors(read_peft_lora(checkpoint_path, device=self.device))
+        self._trainer_key = None  # a cached trainer holds views of the old factors
+        return n
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """LoongX `model.state_dict()` (inference.py:46-52): `transformer.*` keys (peft spellings accepted) replace the
+        native DiT weights, everything else goes to the CS3 / DGF modules."""
+        from loongx_b200.checkpoint import split_loongx_state_dict
+
+        tr, rest = split_loongx_state_dict(state_dict)
+        if tr:
+            from loongx_b200.pipeline import init_lora_factors
+
+            tr = {k: v.to(self.device) for k, v in tr.items()}
+            init_lora_factors(tr, self.transformer.cfg, self.device)
+            self.transformer.load_params(tr)
+            self._trainer_key = None
+        return super().load_state_dict(rest, strict=strict, assign=assign)
 
     def to_model_dtype(self, x: torch.Tensor) -> torch.Tensor:
         """fp32 conditioning output -> DiT dtype (native cast kernel)."""
