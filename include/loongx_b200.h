@@ -127,6 +127,11 @@ typedef struct lx_attn_desc {
   float cross_bias;  /* log(c_factor) added to cond<->rest logits; non-zero overrides mask_mode like the reference */
   float scale;       /* 1/sqrt(128) */
   float* lse;        /* optional fp32 [B, H, S]: log2-domain log-sum-exp of every query row (for lx_attention_bwd) */
+  /* Ragged streams: each of [txt | img | cond] is padded to a multiple of 128 tokens; stream_end[s] is the (padded) end
+   * of stream s inside the sequence and pad[s] in [0,128) the number of padding tokens at its end.  Padding KEYS are
+   * masked out; padding query rows produce don't-care output rows.  All zeros = no padding. */
+  int32_t stream_end[3];
+  int32_t pad[3];
 } lx_attn_desc_t;
 
 int lx_attention(const lx_attn_desc_t* desc, void* stream);
@@ -248,6 +253,9 @@ typedef struct lx_dit_plan {
   void* mod_cond_single; /* bf16 [B, Ls*3D] */
   float* t_dev;          /* fp32 [T*B + B] device scratch for timestep values */
   float* g_dev;          /* fp32 [T*B + B] device scratch for guidance values */
+  int32_t pad[3];        /* padding tokens at the end of the txt / img / cond stream (n_* above are the PADDED lengths,
+                            multiples of 128; the reference accepts any H, W divisible by 16) */
+  int32_t reserved3;
 } lx_dit_plan_t;
 
 /* Step-invariant work, once per edit (generate.py:168-306 hoisted): context_embedder, x_embedder(cond), temb for all
@@ -363,6 +371,8 @@ typedef struct lx_attn_bwd_desc {
   int32_t n_cond, mask_mode;
   float cross_bias, scale;
   int32_t reserved;
+  int32_t stream_end[3]; /* see lx_attn_desc_t */
+  int32_t pad[3];
 } lx_attn_bwd_desc_t;
 int lx_attention_bwd_prep(const void* d_out_rows, int64_t ld_do, const void* out_rows, int64_t ld_o, int32_t rows,
                           int32_t heads, const lx_tile_meta_t* tile_meta, void* d_out_heads, float* delta,

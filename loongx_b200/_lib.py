@@ -69,6 +69,7 @@ class AttnDesc(C.Structure):
         ("n_cond", c_int32), ("mask_mode", c_int32),
         ("cross_bias", c_float), ("scale", c_float),
         ("lse", c_void_p),
+        ("stream_end", c_int32 * 3), ("pad", c_int32 * 3),
     ]
 
 
@@ -78,6 +79,7 @@ class AttnBwdDesc(C.Structure):
         ("lse", c_void_p), ("delta", c_void_p), ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
         ("B", c_int32), ("H", c_int32), ("S", c_int32), ("n_cond", c_int32), ("mask_mode", c_int32),
         ("cross_bias", c_float), ("scale", c_float), ("reserved", c_int32),
+        ("stream_end", c_int32 * 3), ("pad", c_int32 * 3),
     ]
 
 

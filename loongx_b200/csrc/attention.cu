@@ -44,6 +44,9 @@ struct AttnParams {
   int groups;        // query tiles per CTA (2, or 1 when the tile counts are odd)
 };
 
+// kPad: ragged streams (padding keys at the end of a stream's last tile are masked); a separate instantiation so that
+// the aligned case pays nothing for it.
+template <bool kPad>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -241,6 +244,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_32x32b_x64(ts, v0);
           tmem_ld_32x32b_x64(ts + 64, v1);
         }
+        if (kPad) {  // ragged streams: the last key tile of a stream may end in padding tokens -> -inf logits
+          const int kend = (kv_begin + it + 1) * ATT_BKV;
+          int nvalid = ATT_BKV;
+#pragma unroll
+          for (int s3 = 0; s3 < 3; ++s3)
+            if (kend == d.stream_end[s3]) nvalid -= d.pad[s3];
+          if (nvalid < ATT_BKV) {
+#pragma unroll
+            for (int j = 0; j < 128; ++j)
+              if (j >= nvalid) v[j] = 0xff800000u;
+          }
+        }
         DBG(2)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -374,6 +389,10 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.mask_mode >= 0 && d.mask_mode <= 2, "lx_attention: bad mask_mode=%d", d.mask_mode);
   LX_CHECK_ARG(d.ldo % 8 == 0 && d.col_offset % 8 == 0, "lx_attention: ldo / col_offset must be multiples of 8");
   LX_CHECK_ARG(d.H <= 65535 && d.B <= 65535, "lx_attention: grid too large");
+  for (int s3 = 0; s3 < 3; ++s3)
+    LX_CHECK_ARG(d.pad[s3] >= 0 && d.pad[s3] < 128 && (d.pad[s3] == 0 || (d.stream_end[s3] > 0 && d.stream_end[s3] <= d.S &&
+                                                                           d.stream_end[s3] % 128 == 0)),
+                 "lx_attention: bad padding description for stream %d", s3);
   const uint64_t rows = (uint64_t)d.B * d.H * d.S;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
@@ -391,9 +410,11 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   p.bias_log2 = d.cross_bias * log2e;
   const int n_tiles = d.S / 128, n_rest = (d.S - d.n_cond) / 128;
   p.groups = (n_tiles % 2 == 0 && n_rest % 2 == 0) ? 2 : 1;
+  const bool has_pad = (d.pad[0] | d.pad[1] | d.pad[2]) != 0;
   static bool attr_set = false;
   if (!attr_set) {
-    LX_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    LX_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    LX_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   dim3 grid(n_tiles / p.groups, d.H, d.B);
@@ -404,12 +425,13 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
   }
   LaunchScope scope(KC_ATTENTION, stream, 4.0 * d.B * d.H * pairs * 128.0);
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
+  if (has_pad) attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
+  else attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       cudaFuncAttributes fa{};
-      cudaFuncGetAttributes(&fa, attention_kernel);
+      cudaFuncGetAttributes(&fa, attention_kernel<false>);
       set_error("lx_attention launch: %s (regs %d, max threads/block %d, local %zu B, dyn smem %d)", cudaGetErrorString(e),
                 fa.numRegs, fa.maxThreadsPerBlock, fa.localSizeBytes, ATT_SMEM);
       return LX_ERR_CUDA;

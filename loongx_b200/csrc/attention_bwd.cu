@@ -41,6 +41,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dv;
   int B, H, S, n_cond, mask_mode;
   float scale, scale_log2, bias_log2;
+  int stream_end[3], pad[3];  // ragged streams (see lx_attn_desc_t): padding keys get P = dS = 0
   int dbg_flags;  // development aid: bit 0 = skip the dQ reduction (timing experiments only)
 };
 
@@ -225,6 +226,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int r = quarter * 32 + lane;
     const int tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    int nvalid = 128;  // keys of this tile that are not stream padding
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3)
+      if ((j + 1) * 128 == p.stream_end[s3]) nvalid -= p.pad[s3];
+    const float keep = r < nvalid ? 1.0f : 0.0f;
     for (int it = 0; it < n_it; ++it) {
       const int qi = q_begin + it;
       const bool cross = use_bias && (k_is_cond != (qi >= n_rest));
@@ -249,8 +255,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int q0 = c * 32 + 2 * jj;
-          const float p0 = ex2_approx(__uint_as_float(s[cc * 32 + 2 * jj]) * p.scale_log2 + (bias - st_lse[q0]));
-          const float p1 = ex2_approx(__uint_as_float(s[cc * 32 + 2 * jj + 1]) * p.scale_log2 + (bias - st_lse[q0 + 1]));
+          const float p0 = keep * ex2_approx(__uint_as_float(s[cc * 32 + 2 * jj]) * p.scale_log2 + (bias - st_lse[q0]));
+          const float p1 = keep * ex2_approx(__uint_as_float(s[cc * 32 + 2 * jj + 1]) * p.scale_log2 + (bias - st_lse[q0 + 1]));
           const float d0 = p.scale * p0 * (__uint_as_float(dp[2 * jj]) - st_del[q0]);
           const float d1 = p.scale * p1 * (__uint_as_float(dp[2 * jj + 1]) - st_del[q0 + 1]);
           pk[jj] = pack_bf16(p0, p1);
@@ -409,6 +415,11 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   p.scale = d.scale;
   p.scale_log2 = d.scale * log2e;
   p.bias_log2 = d.cross_bias * log2e;
+  for (int s3 = 0; s3 < 3; ++s3) {
+    LX_CHECK_ARG(d.pad[s3] >= 0 && d.pad[s3] < 128, "lx_attention_bwd: bad pad[%d]", s3);
+    p.stream_end[s3] = d.pad[s3] ? d.stream_end[s3] : 0;
+    p.pad[s3] = d.pad[s3];
+  }
   p.dbg_flags = g_attn_bwd_dbg;
   static bool attr_set = false;
   if (!attr_set) {

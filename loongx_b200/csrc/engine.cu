@@ -89,6 +89,9 @@ int check_plan(const lx_dit_model_t* m, const lx_dit_plan_t* p) {
   LX_CHECK_ARG(p->n_txt % 128 == 0 && p->n_img % 128 == 0 && p->n_cond % 128 == 0,
                "dit: stream lengths must be multiples of 128 (txt %d img %d cond %d)", p->n_txt, p->n_img, p->n_cond);
   LX_CHECK_ARG(p->T > 0, "dit: T must be positive");
+  LX_CHECK_ARG(p->pad[0] >= 0 && p->pad[0] < 128 && p->pad[1] >= 0 && p->pad[1] < 128 && p->pad[2] >= 0 && p->pad[2] < 128 &&
+                   (p->n_cond > 0 || p->pad[2] == 0),
+               "dit: stream padding must be in [0, 128)");
   LX_CHECK_ARG(m->in_channels % 8 == 0, "dit: in_channels=%d must be a multiple of 8", m->in_channels);
   if (p->add_cond_attn) {
     set_error("dit: model_config.add_cond_attn=True (block.py:233-234) is not implemented");
@@ -104,6 +107,8 @@ void fill_attn(lx_attn_desc_t& a, const lx_dit_plan_t& p, const Geo& g, int64_t 
   a.q = p.Q; a.k = p.K; a.v = p.V; a.out = p.scratch; a.ldo = ldo; a.out_row_base = p.out_row_base;
   a.B = g.B; a.H = g.H; a.S = g.S; a.n_cond = g.nc; a.mask_mode = p.mask_mode; a.cross_bias = p.cross_bias;
   a.scale = 0.08838834764831845f;  // 1/sqrt(128)
+  a.stream_end[0] = g.nt; a.stream_end[1] = g.nt + g.ni; a.stream_end[2] = g.S;
+  for (int s = 0; s < 3; ++s) a.pad[s] = p.pad[s];
 }
 
 int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int blk, void* stream) {

@@ -60,7 +60,7 @@ class LxDitPlan(C.Structure):
                 ("emb_tmp", c_void_p), ("sin_tmp", c_void_p), ("silu_t", c_void_p), ("silu_c", c_void_p),
                 ("mod_img", c_void_p), ("mod_txt", c_void_p), ("mod_single", c_void_p), ("mod_out", c_void_p),
                 ("mod_cond_img", c_void_p), ("mod_cond_single", c_void_p),
-                ("t_dev", c_void_p), ("g_dev", c_void_p)]
+                ("t_dev", c_void_p), ("g_dev", c_void_p), ("pad", c_int32 * 3), ("reserved3", c_int32)]
 
 
 _lib = L.lib
@@ -266,16 +266,28 @@ def mask_mode_from_config(model_config: Optional[dict]) -> int:
     return MASK_NONE
 
 
+def _pad128(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
 class DitPlan:
+    """Geometry + workspace of one batch of edits.  Stream lengths are arbitrary (the reference accepts any H, W divisible
+    by 16 and any prompt length); internally every stream is padded to a multiple of 128 tokens — the row-tile size of
+    every kernel — and the padding keys are masked inside the attention kernels.  `nt, ni, nc` are the caller's lengths,
+    `ntp, nip, ncp` the padded ones; inputs are zero-padded on the way in and the padding rows dropped on the way out
+    (layout plumbing)."""
+
     def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, T: int = 1,
                  model_config: Optional[dict] = None, c_factor: Optional[float] = None):
         cfg = weights.cfg
         dev = weights.device
-        for n in (n_txt, n_img, n_cond):
-            if n % 128:
-                raise ValueError(f"stream lengths must be multiples of 128 tokens, got {(n_txt, n_img, n_cond)}")
+        if n_txt <= 0 or n_img <= 0 or n_cond < 0:
+            raise ValueError(f"bad stream lengths {(n_txt, n_img, n_cond)}")
         model_config = model_config or {}
         self.weights, self.B, self.nt, self.ni, self.nc, self.T = weights, B, n_txt, n_img, n_cond, T
+        self.ntp, self.nip, self.ncp = _pad128(n_txt), _pad128(n_img), _pad128(n_cond)
+        self.padded = (self.ntp, self.nip, self.ncp) != (n_txt, n_img, n_cond)
+        n_txt, n_img, n_cond = self.ntp, self.nip, self.ncp  # everything below is in padded tokens
         D, H = cfg.inner_dim, cfg.num_attention_heads
         S = n_txt + n_img + n_cond
         R = B * S
@@ -313,16 +325,37 @@ class DitPlan:
         p.cross_bias = math.log(c_factor) if c_factor is not None else 0.0
         for k, v in self.buf.items():
             setattr(p, k, v.data_ptr())
+        p.pad[0], p.pad[1], p.pad[2] = self.ntp - self.nt, self.nip - self.ni, self.ncp - self.nc
         self.plan = p
         self.has_rope = False
+        if self.padded:  # staging for the zero-padded latents / predictions of step()
+            self._lat_pad = torch.zeros((B, self.nip, cfg.in_channels), **bf)
+            self._out_pad = torch.zeros((B, self.nip, cfg.in_channels), **bf)
+
+    @staticmethod
+    def _pad_tokens(x: torch.Tensor, n_pad: int) -> torch.Tensor:
+        """[B, n, C] -> [B, n_pad, C] with zero rows appended (no-op when already that long)."""
+        if x.shape[1] == n_pad:
+            return x
+        out = torch.zeros((x.shape[0], n_pad, x.shape[2]), device=x.device, dtype=x.dtype)
+        out[:, :x.shape[1]].copy_(x)
+        return out
 
     def set_ids(self, txt_ids: torch.Tensor, img_ids: torch.Tensor, cond_ids: Optional[torch.Tensor]) -> None:
         """RoPE table of the joint [txt | img | cond] sequence (transformer.py:130-134); ids are step-invariant so
         this runs once per edit instead of once per forward."""
         cfg = self.weights.cfg
-        parts = [txt_ids, img_ids] + ([cond_ids] if cond_ids is not None else [])
-        ids = torch.cat([x.to(device=self.weights.device, dtype=torch.float32) for x in parts], 0).contiguous()
-        assert ids.shape == (self.nt + self.ni + self.nc, 3), ids.shape
+        parts = [(txt_ids, self.nt, self.ntp), (img_ids, self.ni, self.nip)] + \
+            ([(cond_ids, self.nc, self.ncp)] if cond_ids is not None else [])
+        padded = []
+        for x, n, n_pad in parts:
+            x = x.to(device=self.weights.device, dtype=torch.float32)
+            assert x.shape == (n, 3), (tuple(x.shape), n)
+            padded.append(x)
+            if n_pad > n:
+                padded.append(torch.zeros((n_pad - n, 3), device=x.device))  # padding tokens: position 0, masked as keys
+        ids = torch.cat(padded, 0).contiguous()
+        assert ids.shape == (self.ntp + self.nip + self.ncp, 3), ids.shape
         a = cfg.axes_dims_rope
         L.check(_lib.lx_rope_table(ids.data_ptr(), self.buf["rope"].data_ptr(), ids.shape[0], a[0], a[1], a[2], 10000.0,
                                    _stream()), "lx_rope_table")
@@ -340,6 +373,9 @@ class DitPlan:
         po = pooled.to(torch.bfloat16).contiguous()
         cl = cond_latents.to(torch.bfloat16).contiguous() if cond_latents is not None else None
         assert pe.shape == (self.B, self.nt, w.cfg.joint_attention_dim), pe.shape
+        assert cl is None or cl.shape == (self.B, self.nc, w.cfg.in_channels), cl.shape
+        pe = self._pad_tokens(pe, self.ntp)
+        cl = self._pad_tokens(cl, self.ncp) if cl is not None else None
         assert po.shape == (self.B, w.cfg.pooled_projection_dim)
         ts = (c_float * len(timesteps))(*[float(t) for t in timesteps])
         gs = (c_float * self.B)(*[float(x) for x in guidance]) if guidance is not None else None
@@ -354,11 +390,21 @@ class DitPlan:
         assert latents.shape == (self.B, self.ni, w.cfg.in_channels), latents.shape
         if out is None:
             out = torch.empty_like(latents)
-        L.check(_lib.lx_dit_step(C.byref(w.model), C.byref(self.plan), step, latents.data_ptr(), out.data_ptr(),
+        if self.padded:
+            self._lat_pad[:, :self.ni].copy_(latents)
+            src, dst = self._lat_pad, self._out_pad
+        else:
+            src, dst = latents, out
+        L.check(_lib.lx_dit_step(C.byref(w.model), C.byref(self.plan), step, src.data_ptr(), dst.data_ptr(),
                                  _stream()), "lx_dit_step")
+        if self.padded:
+            out.copy_(self._out_pad[:, :self.ni])
         return out
 
     def embed(self, latents: torch.Tensor) -> None:
+        if self.padded:
+            self._lat_pad[:, :self.ni].copy_(latents)
+            latents = self._lat_pad
         L.check(_lib.lx_dit_embed(C.byref(self.weights.model), C.byref(self.plan), latents.data_ptr(), _stream()),
                 "lx_dit_embed")
 
@@ -373,10 +419,10 @@ class DitPlan:
     # -- stream-major row layout <-> reference [B, N, D] tensors (test / shim helpers, pure views + copies) ---------
     def split_streams(self):
         X, B, D = self.buf["X"], self.B, self.weights.cfg.inner_dim
-        rt, ri = B * self.nt, B * self.ni
-        txt = X[:rt].view(B, self.nt, D)
-        img = X[rt:rt + ri].view(B, self.ni, D)
-        cond = X[rt + ri:].view(B, self.nc, D) if self.nc else None
+        rt, ri = B * self.ntp, B * self.nip
+        txt = X[:rt].view(B, self.ntp, D)[:, :self.nt]
+        img = X[rt:rt + ri].view(B, self.nip, D)[:, :self.ni]
+        cond = X[rt + ri:].view(B, self.ncp, D)[:, :self.nc] if self.nc else None
         return txt, img, cond
 
 

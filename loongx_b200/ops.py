@@ -122,8 +122,19 @@ def make_out_row_base(batch: int, n_txt: int, n_img: int, n_cond: int, device) -
     return torch.tensor(base, dtype=torch.int32, device=device)
 
 
+def _set_pads(d, S: int, n_cond: int, pads: Optional[Sequence[int]], n_txt: Optional[int]) -> None:
+    """pads = (pad_txt, pad_img, pad_cond); n_txt = padded text length (needed to locate the end of the text stream)."""
+    if pads is None or not any(pads):
+        return
+    assert n_txt is not None, "n_txt (padded) is needed to place the stream boundaries"
+    d.stream_end[0], d.stream_end[1], d.stream_end[2] = n_txt, S - n_cond, S
+    for i in range(3):
+        d.pad[i] = int(pads[i])
+
+
 def attention(q, k, v, out, out_row_base, *, n_cond: int = 0, mask_mode: int = 0, cross_bias: float = 0.0,
-              col_offset: int = 0, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None) -> None:
+              col_offset: int = 0, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None,
+              pads: Optional[Sequence[int]] = None, n_txt: Optional[int] = None) -> None:
     """out rows <- softmax(q k^T * scale) v for q,k,v [B,H,S,128] bf16 (see lx_attention)."""
     assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     B, H, S, Dh = q.shape
@@ -140,11 +151,13 @@ def attention(q, k, v, out, out_row_base, *, n_cond: int = 0, mask_mode: int = 0
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S
         d.lse = _ptr(lse)
+    _set_pads(d, S, n_cond, pads, n_txt)
     L.check(L.lib.lx_attention(C.byref(d), _stream()), "lx_attention")
 
 
 def attention_bwd(q, k, v, d_out_heads, lse, delta, dq_f32, dk, dv, *, n_cond: int = 0, mask_mode: int = 0,
-                  cross_bias: float = 0.0, scale: Optional[float] = None) -> None:
+                  cross_bias: float = 0.0, scale: Optional[float] = None, pads: Optional[Sequence[int]] = None,
+                  n_txt: Optional[int] = None) -> None:
     """dq_f32 (fp32, zeroed by the caller) += dQ; dk, dv (bf16) = dK, dV of lx_attention (see lx_attention_bwd)."""
     B, H, S, Dh = q.shape
     assert Dh == 128 and dq_f32.dtype == torch.float32 and dk.dtype == torch.bfloat16 and dv.dtype == torch.bfloat16
@@ -156,6 +169,7 @@ def attention_bwd(q, k, v, d_out_heads, lse, delta, dq_f32, dk, dv, *, n_cond: i
     d.B, d.H, d.S, d.n_cond, d.mask_mode = B, H, S, n_cond, mask_mode
     d.cross_bias = cross_bias
     d.scale = scale if scale is not None else 1.0 / (Dh ** 0.5)
+    _set_pads(d, S, n_cond, pads, n_txt)
     L.check(L.lib.lx_attention_bwd(C.byref(d), _stream()), "lx_attention_bwd")
 
 

@@ -301,6 +301,9 @@ class DitTrainer:
             raise NotImplementedError("training with model_config.latent_lora=True (LoRA gradients from the image rows)")
         if n_cond <= 0:
             raise NotImplementedError("the training step needs a condition stream (the LoRA lives on the condition branch)")
+        if n_txt % 128 or n_img % 128 or n_cond % 128:
+            raise NotImplementedError(f"training with stream lengths {(n_txt, n_img, n_cond)} that are not multiples of 128 "
+                                      "(inference pads and masks them; the trainer's loss / gradient plumbing does not yet)")
         self.w, self.cfg = weights, weights.cfg
         self.plan = DitPlan(weights, B, n_txt, n_img, n_cond, T=1, model_config=model_config)
         self.B, self.nt, self.ni, self.nc = B, n_txt, n_img, n_cond

@@ -220,3 +220,58 @@ def test_attention_backward_flux_shape_throughput():
     ms = e0.elapsed_time(e1) / 10
     print(f"\n[attn bwd] S=2560 H=24: {ms:.3f} ms  {10.0 * B * H * S * S * 128 / ms / 1e9:.0f} TFLOP/s")
     assert torch.isfinite(dk.float()).all()
+
+
+@pytest.mark.parametrize("nt,ni,nc,mask_mode", [(100, 200, 130, 0), (77, 128, 0, 0), (128, 250, 250, 2), (1, 129, 127, 1)])
+def test_attention_ragged_streams_forward_and_backward(nt, ni, nc, mask_mode):
+    """Ragged stream lengths: every stream padded to a multiple of 128 tokens, padding keys masked inside the kernels
+    (junk values in the padding must not leak).  Forward output rows and dq/dk/dv of the valid tokens vs fp32 autograd
+    on the un-padded tensors."""
+    from loongx_b200 import ops
+
+    B, H = 2, 2
+    pad = lambda n: (n + 127) // 128 * 128  # noqa: E731
+    ntp, nip, ncp = pad(nt), pad(ni), pad(nc)
+    Sp, S = ntp + nip + ncp, nt + ni + nc
+    g = torch.Generator(device="cuda").manual_seed(nt * 7 + ni)
+    mk = lambda *s: torch.randn(*s, generator=g, device="cuda").bfloat16()  # noqa: E731
+    qp, kp, vp, dop = mk(B, H, Sp, 128), mk(B, H, Sp, 128), mk(B, H, Sp, 128) * 3, mk(B, H, Sp, 128)
+    valid = torch.cat([torch.arange(0, nt), torch.arange(ntp, ntp + ni), torch.arange(ntp + nip, ntp + nip + nc)]).cuda()
+    q, k, v, d_o = (t[:, :, valid].contiguous() for t in (qp, kp, vp, dop))
+    o_ref, dq_ref, dk_ref, dv_ref = _sdpa_ref_grads(q, k, v, d_o, nc, mask_mode, None)
+    pads = (ntp - nt, nip - ni, ncp - nc)
+    tm = ops.make_tile_meta(B, ntp, nip, ncp, "cuda")
+    orb = ops.make_out_row_base(B, ntp, nip, ncp, "cuda")
+    D = H * 128
+    out_rows = torch.zeros(B * Sp, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Sp, device="cuda")
+    ops.attention(qp, kp, vp, out_rows, orb, n_cond=ncp, mask_mode=mask_mode, lse=lse, pads=pads, n_txt=ntp)
+
+    def rows_to_seq(rows):  # stream-major padded rows [B*Sp, D] -> [B, H, Sp, 128]
+        rt, ri = B * ntp, B * nip
+        xs = torch.cat([rows[:rt].view(B, ntp, D), rows[rt:rt + ri].view(B, nip, D), rows[rt + ri:].view(B, ncp, D)], 1)
+        return xs.view(B, Sp, H, 128).permute(0, 2, 1, 3)
+
+    def seq_to_rows(x):  # [B,H,Sp,128] -> [B*Sp, D]
+        xs = x.permute(0, 2, 1, 3).reshape(B, Sp, D)
+        return torch.cat([xs[:, :ntp].reshape(B * ntp, D), xs[:, ntp:ntp + nip].reshape(B * nip, D), xs[:, ntp + nip:].reshape(B * ncp, D)])
+
+    got = rows_to_seq(out_rows)[:, :, valid]
+    e_o = _rel(got, o_ref)
+    # backward: dO of the padding query rows is zero (what the training step guarantees)
+    dop_z = torch.zeros_like(dop)
+    dop_z[:, :, valid] = d_o
+    d_heads = torch.zeros_like(dop)
+    delta = torch.zeros(B, H, Sp, device="cuda")
+    ops.attention_bwd_prep(seq_to_rows(dop_z).contiguous(), out_rows, H, tm, d_heads, delta)
+    dq = torch.zeros(B, H, Sp, 128, device="cuda")
+    dk, dv = torch.zeros_like(qp), torch.zeros_like(qp)
+    ops.attention_bwd(qp, kp, vp, d_heads, lse, delta, dq, dk, dv, n_cond=ncp, mask_mode=mask_mode, pads=pads, n_txt=ntp)
+    torch.cuda.synchronize()
+    e = (_rel(dq[:, :, valid], dq_ref), _rel(dk[:, :, valid], dk_ref), _rel(dv[:, :, valid], dv_ref))
+    inv = torch.ones(Sp, dtype=torch.bool, device="cuda")
+    inv[valid] = False
+    print(f"\n[ragged attn {nt}/{ni}/{nc} mask{mask_mode}] out relL2 {e_o:.4g}; dq {e[0]:.4g} dk {e[1]:.4g} dv {e[2]:.4g}")
+    assert e_o < 1e-2 and max(e) < 2e-2
+    if inv.any():  # padding keys receive no gradient
+        assert float(dk[:, :, inv].abs().max()) == 0.0 and float(dv[:, :, inv].abs().max()) == 0.0

@@ -254,3 +254,41 @@ def test_dit_full_width_geometry(res, B):
     e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
     print(f"\n[full width {res}^2 B={B}] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
     assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (res, B, e_nat, e_bf)
+
+
+@pytest.mark.parametrize("nt,hw", [(77, (10, 12)), (300, (20, 18))])
+def test_dit_forward_ragged_stream_lengths(nt, hw):
+    """Stream lengths that are not multiples of 128 (e.g. a 77-token prompt, a 160x192-pixel edit -> 30 image tokens): the
+    plan pads every stream to 128-token tiles and masks the padding keys; result vs the fp32 oracle on the un-padded
+    inputs, same tolerance as the aligned cases."""
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights
+
+    dev = "cuda"
+    kw = dict(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=1234, dtype=torch.float32, device="cpu", w_std=0.05, bias_std=0.05, lora_b_std=0.05)
+    Pb = {k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}
+    P32 = {k: v.float() for k, v in Pb.items()}
+    h, w = hw
+    ni = h * w
+    B = 2
+    g = torch.Generator().manual_seed(nt)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(dev)  # noqa: E731
+    inp = dict(lat=r(B, ni, 64), cond=r(B, ni, 64), pe=r(B, nt, 256, scale=0.5), pooled=r(B, 64), img_ids=_ids(h, w).to(dev),
+               cond_ids=_ids(h, w, -w).to(dev), txt_ids=torch.zeros(nt, 3).to(dev), guidance=3.5)
+    plan = DitPlan(DitWeights(Pb, cfg, dev), B, nt, ni, ni, T=1)
+    assert plan.padded and plan.nip % 128 == 0
+    plan.set_ids(inp["txt_ids"], inp["img_ids"], inp["cond_ids"])
+    t = 0.45
+    plan.prepare(inp["pe"], inp["pooled"], inp["cond"], [t] * B, [3.5] * B, c_t=0.0)
+    got = plan.step(0, inp["lat"])
+    torch.cuda.synchronize()
+    assert got.shape == (B, ni, 64)
+    with torch.no_grad():
+        ref32 = _oracle_full(O, ocfg, P32, inp, t, torch.float32)
+        ref16 = _oracle_full(O, ocfg, Pb, inp, t, torch.bfloat16)
+    e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
+    print(f"\n[ragged nt={nt} ni={ni}] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
+    assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (e_nat, e_bf)

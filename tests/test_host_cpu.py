@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     from loongx_b200 import cs3, dit
 
     pairs = {"lx_tile_meta_t": L.TileMeta, "lx_gemm_group_t": L.GemmGroup, "lx_gemm_segment_t": L.GemmSegment,
-             "lx_gemm_desc_t": L.GemmDesc, "lx_attn_desc_t": L.AttnDesc, "lx_linear_t": dit.LxLinear,
+             "lx_gemm_desc_t": L.GemmDesc, "lx_attn_desc_t": L.AttnDesc, "lx_attn_bwd_desc_t": L.AttnBwdDesc, "lx_linear_t": dit.LxLinear,
              "lx_double_block_t": dit.LxDoubleBlock, "lx_single_block_t": dit.LxSingleBlock,
              "lx_dit_model_t": dit.LxDitModel, "lx_dit_plan_t": dit.LxDitPlan, "lx_sgemm_desc_t": cs3.SgemmDesc,
              "lx_duan_weights_t": cs3.DuanWeights}
