@@ -327,6 +327,84 @@ def run_native(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# training workload (BASELINE.json configs[4]; not the headline metric): OminiModel.step forward + backward + all-reduce
+# --------------------------------------------------------------------------------------------------------------------
+def run_train(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    from loongx_b200 import _lib as L
+    from src.train.model import OminiModel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = OminiModel("synthetic", lora_config={"r": 4, "lora_alpha": 4}, device=str(dev), model_config={
+        "union_cond_attn": True, "add_cond_attn": False, "latent_lora": False}, use_brain_condition=True, fuse_flag=True)
+    side = RES // 8
+    g = torch.Generator().manual_seed(7 + 1000 * rank)
+    r = lambda *s, scale=1.0, dt=torch.bfloat16: (torch.randn(*s, generator=g) * scale).to(dt).to(dev)  # noqa: E731
+    batch = dict(image=r(B, 16, side, side), condition=r(B, 16, side, side), prompt_embeds=r(B, N_TXT, 4096, scale=0.1),
+                 pooled_prompt_embeds=r(B, 768), position_delta=[[0, -(RES // 16)]], condition_type=["subject"] * B,
+                 eeg=r(B, 4, 5000, dt=torch.float32), fnirs=r(B, 6, 600, dt=torch.float32),
+                 ppg=r(B, 4, 256, dt=torch.float32), motion=r(B, 6, 100, dt=torch.float32))
+    model.step(batch)  # fixes the geometry, builds the transposed panels
+    opt = torch.optim.AdamW(model.lora_layers, lr=1e-4)
+
+    def one_step():
+        opt.zero_grad(set_to_none=True)
+        loss = model.step(batch)  # CS3/DGF conditioning (step fuse order) + native DiT forward
+        loss.backward()           # native backward + ONE NCCL all-reduce of the flat LoRA-gradient bucket
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        loss = one_step()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    L.lib.lx_launch_count_reset()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    secs = e0.elapsed_time(e1) / 1e3
+    if world > 1:
+        t = torch.tensor([secs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    launches = int(L.lib.lx_launch_count(-1))
+    n_img = (RES // 16) ** 2
+    S, D, nb = N_TXT + 2 * n_img, 3072, 57
+    F = nb * (24 * D * D * S + 4 * S * S * D)
+    flop = 2 * F + nb * 24 * D * D * S + 2.5 * nb * 4 * S * S * D  # fwd + recompute + bwd per sample
+    peaks = load_peaks()
+    if rank == 0:
+        tf = B * args.steps * flop / secs / 1e12
+        print(json.dumps({
+            "metric": "512x512 LoRA train samples/sec", "value": world * B * args.steps / secs, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[4]: train step, Flux-DiT LoRA r=4 + CS3/DGF conditioning (EEG+PPG, "
+                                   "fNIRS+Motion, fuse_flag), 512x512 + image condition, gradient checkpointing per block, AdamW "
+                                   "on the LoRA factors, mean all-reduce of the flat gradient bucket",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (NCCL all-reduce of 14.5 M fp32)"},
+            "gpu_launches": launches, "clocks": clk, "loss": float(loss.detach()),
+            "algorithmic_tflops_per_gpu": tf, "frac_of_peak_end_to_end": tf / peaks["tflops"]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,6 +413,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="edits per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="edit", choices=["edit", "train"],
+                    help="edit = the headline metric (default); train = BASELINE.json configs[4] (extra, not the headline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -344,6 +424,9 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    if args.workload == "train":
+        run_train(args, rank, local_rank, world)
+        return
     run_native(args, rank, local_rank, world)
 
 

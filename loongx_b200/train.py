@@ -283,9 +283,15 @@ class FlowStepFunction(torch.autograd.Function):
         tr.zero_grad()
         tr.backward(float(grad_out))
         allreduce_mean_(tr.grad_flat)
-        grads = []
+        # hand autograd a private copy: the trainer re-zeroes its bucket on the next backward, while `.grad` must keep
+        # accumulating across micro-batches (accumulate_grad_batches: 4 in train/config/seed_512.yaml:12)
+        flat = tr.grad_flat.clone()
+        grads, o = [], 0
         for f in tr.factors.values():
-            grads += [f.dA, f.dB]
+            grads.append(flat[o:o + f.A.numel()].view_as(f.A))
+            o += f.A.numel()
+            grads.append(flat[o:o + f.B.numel()].view_as(f.B))
+            o += f.B.numel()
         return (None, None, *grads)
 
 

@@ -376,6 +376,12 @@ def test_omini_model_step_api_and_optimizer():
     e = _rel(cat_g, cat_r)
     print(f"[OminiModel.step] LoRA .grad relL2 vs oracle autograd {e:.4g}")
     assert e < 6e-2
+    # gradient accumulation (accumulate_grad_batches, seed_512.yaml:12): a second backward adds to .grad
+    m.step(batch).backward()
+    cat_2 = torch.cat([got[n].grad.flatten() for n in sorted(got)])
+    assert _rel(cat_2, 2 * cat_g) < 5e-3  # fp32 atomics / TMA reductions are order-dependent: not bitwise reproducible
+    for n in got:
+        got[n].grad.mul_(0.5)
     for gr in opt.param_groups:
         gr["lr"] = 0.5 / float(cat_g.norm())
     opt.step()
