@@ -123,6 +123,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     trace[2] = clock64();
   }
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: the prologue above overlapped the QKV GEMM's tail; Q / K / V are read from here on
+  pdl_launch_dependents();
   // columns [128g, 128g+128): S_g fp32, its first 64 columns re-used for the packed bf16 P_g;  [256+128g, +128): O_g
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 256;
@@ -425,8 +427,18 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
   }
   LaunchScope scope(KC_ATTENTION, stream, 4.0 * d.B * d.H * pairs * 128.0);
-  if (has_pad) attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
-  else attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.dynamicSmemBytes = ATT_SMEM;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (has_pad) cudaLaunchKernelEx(&cfg, attention_kernel<true>, tmQ, tmK, tmV, tmO, p);
+  else cudaLaunchKernelEx(&cfg, attention_kernel<false>, tmQ, tmK, tmV, tmO, p);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_
   __shared__ float red[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x;
+  pdl_wait();  // PDL: x is the previous kernel's output
+  pdl_launch_dependents();
   const lx_tile_meta_t meta = d.tile_meta[row >> 7];
   const int nchunk = d.D >> 3;  // 16-byte chunks per row
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x) + (size_t)row * d.ldx;
@@ -200,7 +202,16 @@ extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.x && d.out && d.tile_meta, "lx_ln_modulate: null pointer");
   LX_CHECK_ARG(d.ldx % 8 == 0 && d.ldo % 8 == 0 && d.ldo >= d.D && d.ldx >= d.D, "lx_ln_modulate: bad strides");
   LaunchScope scope(KC_ROW, stream, 4.0 * d.rows * d.D);  // bytes: read + write bf16 rows
-  ln_modulate_kernel<<<d.rows, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(d);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d.rows);
+  cfg.blockDim = dim3(LN_THREADS);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, ln_modulate_kernel, d);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

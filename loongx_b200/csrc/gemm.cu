@@ -124,6 +124,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; its outputs (our A operand / residual) are read below
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -433,13 +436,15 @@ int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = TileCfg<BN, NCTA>::SMEM;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   LX_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, NCTA>, tmA, tmB[0], tmB[1], tmB[2], p));
   LX_CUDA(cudaGetLastError());
   return LX_OK;

@@ -106,6 +106,12 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64
   return LX_OK;
 }
 
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+}  // namespace lx
+extern "C" void lx_debug_set_pdl(int on) { lx::g_pdl = on; }
+namespace lx {
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

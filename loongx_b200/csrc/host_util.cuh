@@ -41,6 +41,8 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64
                       uint64_t outer_stride, uint32_t box_rows, uint32_t box_cols);
 
 int num_sms();
+// Programmatic dependent launch switch (default on; lx_debug_set_pdl(0) turns it off for A/B timing).
+bool pdl_enabled();
 
 // Launch accounting + optional per-kernel-class CUDA-event timing (bench.py's roofline numbers): every extern "C"
 // launcher opens a LaunchScope; with profiling off it only bumps a counter.

@@ -5,6 +5,8 @@ import torch
 from loongx_b200.config import FluxConfig
 from loongx_b200.dit import DitWeights, DitPlan, random_params, euler_step
 
+from loongx_b200 import _lib as _L
+_L.lib.lx_debug_set_pdl(int(os.environ.get("LX_PDL", "1")))  # A/B switch for programmatic dependent launch
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 4
