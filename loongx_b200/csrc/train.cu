@@ -99,14 +99,21 @@ __global__ void __launch_bounds__(128) gate_bwd_kernel(const __nv_bfloat16* __re
   const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(gate.p[m.stream] + (size_t)m.batch * gate.stride[m.stream] + c));
   float ax = 0.f, ay = 0.f;
   const int r0 = tile * 128, r1 = min(rows, r0 + 128);
-  for (int r = r0; r < r1; ++r) {
-    const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + (size_t)r * ld + c));
-    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + (size_t)r * ld + c));
-    ax += d.x * v.x;
-    ay += d.y * v.y;
-    *reinterpret_cast<uint32_t*>(dy + (size_t)r * ld + c) = pack_bf16(g.x * d.x, g.y * d.y);
-  }
   float* acc = dgate.p[m.stream];
+  if (acc != nullptr) {
+    for (int r = r0; r < r1; ++r) {
+      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + (size_t)r * ld + c));
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + (size_t)r * ld + c));
+      ax += d.x * v.x;
+      ay += d.y * v.y;
+      *reinterpret_cast<uint32_t*>(dy + (size_t)r * ld + c) = pack_bf16(g.x * d.x, g.y * d.y);
+    }
+  } else {  // no gate gradient wanted for this stream: y is not read at all (it may not even have been recomputed)
+    for (int r = r0; r < r1; ++r) {
+      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + (size_t)r * ld + c));
+      *reinterpret_cast<uint32_t*>(dy + (size_t)r * ld + c) = pack_bf16(g.x * d.x, g.y * d.y);
+    }
+  }
   if (acc != nullptr) {
     acc += (size_t)m.batch * dgate.stride[m.stream] + c;
     atomicAdd(acc, ax);

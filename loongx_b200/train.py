@@ -322,7 +322,7 @@ class DitTrainer:
         R = self.R
         bf = dict(device=dev, dtype=torch.bfloat16)
         z = lambda *s: torch.zeros(s, **bf)  # noqa: E731
-        self.a = dict(XN=self.plan.buf["XN"], QM=z(R, 7 * D), Cat=z(R, 5 * D), Y1=z(R, D), X1=z(R, D), XN2=z(R, D),
+        self.a = dict(XN=self.plan.buf["XN"], QM=z(R, 7 * D), Cat=z(R, 5 * D), Y1=z(R, D), XN2=z(R, D),
                       Hid=z(R, 4 * D), Y2=z(R, D))
         self.g = dict(dX=z(R, D), dX1=z(R, D), dY=z(R, D), dXN=z(R, D), dBig=z(R, 7 * D), dCat=z(R, 5 * D),
                       dOh=z(B, self.H, S, 128), dQh=z(B, self.H, S, 128), dKh=z(B, self.H, S, 128), dVh=z(B, self.H, S, 128))
@@ -332,6 +332,7 @@ class DitTrainer:
         self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
         self.lora_ws = torch.zeros((2 * max(self.Rc, B) * max(cfg.lora_rank, 1),), device=dev, dtype=torch.float32)
         self.ckpt = torch.zeros((cfg.num_layers + cfg.num_single_layers, R, D), **bf)
+        self.ckpt_mid = torch.zeros((max(cfg.num_layers, 1), R, D), **bf)  # residual stream after the attention branch
         self.dmod_dbl = torch.zeros((B, max(cfg.num_layers, 1) * 6 * D), device=dev, dtype=torch.float32)
         self.dmod_sgl = torch.zeros((B, max(cfg.num_single_layers, 1) * 3 * D), device=dev, dtype=torch.float32)
         self.loss = torch.zeros((1,), device=dev, dtype=torch.float32)
@@ -448,7 +449,15 @@ class DitTrainer:
         return g["dQh"], g["dKh"], g["dVh"]
 
     # -- blocks -------------------------------------------------------------------------------------------------------
-    def _double_fwd(self, i):
+    def _gemm_cond(self, A, main: PackedLinear, out):
+        """the condition rows only, against the LoRA-merged panel (recompute of a projection whose output the backward
+        needs on the condition stream alone: the gate gradient feeds the LoRA of the AdaLN linear)."""
+        c0 = self.Rt + self.Ri
+        ops.gemm(A[c0:], main.w_lora if main.w_lora is not None else main.w, main.bias, out[c0:], L.EPI_BIAS)
+
+    def _double_fwd(self, i, recompute: bool = False):
+        """recompute=True (backward): the residual stream after the attention branch comes from its checkpoint, the
+        pre-gate projection outputs are rebuilt for the condition rows only and the block output is not formed."""
         b, a, D, W = self.plan.buf, self.a, self.D, self.w.named
         X, tm = b["X"], b["tile_meta"]
         m = self._mods_double(i)
@@ -459,14 +468,22 @@ class DitTrainer:
         qkv_post_fwd(pre, self.H, tm, b["Q"], b["K"], b["V"], [naq, nq, nq], [nak, nk, nk], b["rope"])
         O = a["Cat"][:, :D]
         self._attention(O)
-        self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
-        gate_residual_fwd(X, a["Y1"], a["X1"], tm, m[2])
-        ln_modulate(a["X1"], a["XN2"], tm, m[3], m[4])
+        if recompute:
+            self._gemm_cond(O, W[f"double.{i}.out"], a["Y1"])
+            x1 = self.ckpt_mid[i]
+        else:
+            self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
+            x1 = self.ckpt_mid[i]  # written in place: the checkpoint IS the forward's buffer
+            gate_residual_fwd(X, a["Y1"], x1, tm, m[2])
+        ln_modulate(x1, a["XN2"], tm, m[3], m[4])
         pre_ff = a["QM"][:, 3 * D:7 * D]
         self._gemm(a["XN2"], W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], pre_ff)
         gelu_fwd(pre_ff, a["Hid"])
-        self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], a["Y2"])
-        gate_residual_fwd(a["X1"], a["Y2"], X, tm, m[5])
+        if recompute:
+            self._gemm_cond(a["Hid"], W[f"double.{i}.ff_down"], a["Y2"])
+        else:
+            self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], a["Y2"])
+            gate_residual_fwd(x1, a["Y2"], X, tm, m[5])
 
     def _double_bwd(self, i, x_in):
         """gradient wrt the block output is in g['dX']; leaves the gradient wrt the block input there."""
@@ -485,7 +502,7 @@ class DitTrainer:
         self._gemm(g["dY"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], d_hid, transposed=True)
         gelu_bwd(pre_ff, d_hid, d_hid)
         self._gemm(d_hid, W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], g["dXN"], transposed=True)
-        ln_modulate_bwd(a["X1"], g["dXN"], g["dX"], g["dX1"], tm, m[4], dm(4), dm(3), self.stats)
+        ln_modulate_bwd(self.ckpt_mid[i], g["dXN"], g["dX"], g["dX1"], tm, m[4], dm(4), dm(3), self.stats)
         # attention branch
         gate_bwd(g["dX1"], a["Y1"], g["dY"], tm, m[2], dm(2))
         self._lora_grads([pfx + "attn.to_out.0"], O[c0:], g["dY"][c0:])
@@ -499,7 +516,7 @@ class DitTrainer:
         self._gemm(d_pre, W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], g["dXN"], transposed=True)
         ln_modulate_bwd(x_in, g["dXN"], g["dX1"], g["dX"], tm, m[1], dm(1), dm(0), self.stats)
 
-    def _single_fwd(self, i):
+    def _single_fwd(self, i, recompute: bool = False):
         b, a, D, W = self.plan.buf, self.a, self.D, self.w.named
         X, tm = b["X"], b["tile_meta"]
         m = self._mods_single(i)
@@ -509,8 +526,11 @@ class DitTrainer:
         qkv_post_fwd(a["QM"], self.H, tm, b["Q"], b["K"], b["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
         gelu_fwd(a["QM"][:, 3 * D:], a["Cat"][:, D:])
         self._attention(a["Cat"])
-        self._gemm(a["Cat"], W[f"single.{i}.proj_out"], None, a["Y1"])
-        gate_residual_fwd(X, a["Y1"], X, tm, m[2])
+        if recompute:
+            self._gemm_cond(a["Cat"], W[f"single.{i}.proj_out"], a["Y1"])
+        else:
+            self._gemm(a["Cat"], W[f"single.{i}.proj_out"], None, a["Y1"])
+            gate_residual_fwd(X, a["Y1"], X, tm, m[2])
 
     def _single_bwd(self, i, x_in):
         b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
@@ -591,11 +611,11 @@ class DitTrainer:
                         [None] * 3, [None] * 3, None)
         for i in reversed(range(ns)):
             X.copy_(self.ckpt[nl + i])
-            self._single_fwd(i)  # recompute (gradient checkpointing, transformer.py:184-206)
+            self._single_fwd(i, recompute=True)  # gradient checkpointing, transformer.py:184-206
             self._single_bwd(i, self.ckpt[nl + i])
         for i in reversed(range(nl)):
             X.copy_(self.ckpt[i])
-            self._double_fwd(i)
+            self._double_fwd(i, recompute=True)
             self._double_bwd(i, self.ckpt[i])
         # x_embedder on the condition rows (transformer.py:93)
         c0 = self.Rt + self.Ri
