@@ -15,9 +15,9 @@ Python here is launch sequencing and pointer plumbing only; every arithmetic ste
             log-sum-exp rows the forward kernel records.  `attn_bwd="library"` swaps in torch's SDPA autograd for A/B
             checks only.
 
-Scope of the gradients: LoRA A / B of every target of train/config/seed_512.yaml:38 on the condition branch
-(`latent_lora=False`, the shipped configuration).  The CS3 / DGF encoders run forward-only (they are not in the
-reference's optimizer parameter list).
+Scope of the gradients: LoRA A / B of every target of train/config/seed_512.yaml:38 — on the condition branch
+(`latent_lora=False`, the shipped configuration) or on the image / text+image rows as well (`latent_lora=True`).  The
+CS3 / DGF encoders run forward-only (they are not in the reference's optimizer parameter list).
 """
 from __future__ import annotations
 
@@ -303,8 +303,7 @@ class DitTrainer:
         model_config = model_config or {}
         assert attn_bwd in ("native", "library")
         self.attn_bwd = attn_bwd
-        if model_config.get("latent_lora", False):
-            raise NotImplementedError("training with model_config.latent_lora=True (LoRA gradients from the image rows)")
+        self.latent_lora = bool(model_config.get("latent_lora", False))
         if n_cond <= 0:
             raise NotImplementedError("the training step needs a condition stream (the LoRA lives on the condition branch)")
         if n_txt % 128 or n_img % 128 or n_cond % 128:
@@ -330,11 +329,14 @@ class DitTrainer:
         self.delta = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
         self.dq32 = torch.zeros((B, self.H, S, 128), device=dev, dtype=torch.float32)
         self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
-        self.lora_ws = torch.zeros((2 * max(self.Rc, B) * max(cfg.lora_rank, 1),), device=dev, dtype=torch.float32)
+        self.lora_ws = torch.zeros((2 * max(R, B) * max(cfg.lora_rank, 1),), device=dev, dtype=torch.float32)
         self.ckpt = torch.zeros((cfg.num_layers + cfg.num_single_layers, R, D), **bf)
         self.ckpt_mid = torch.zeros((max(cfg.num_layers, 1), R, D), **bf)  # residual stream after the attention branch
         self.dmod_dbl = torch.zeros((B, max(cfg.num_layers, 1) * 6 * D), device=dev, dtype=torch.float32)
         self.dmod_sgl = torch.zeros((B, max(cfg.num_single_layers, 1) * 3 * D), device=dev, dtype=torch.float32)
+        if self.latent_lora:  # modulation gradients of the image stream (double) / the shared text+image vector (single)
+            self.dmod_dbl_img = torch.zeros_like(self.dmod_dbl)
+            self.dmod_sgl_ti = torch.zeros_like(self.dmod_sgl)
         self.loss = torch.zeros((1,), device=dev, dtype=torch.float32)
         self.factors: Dict[str, LoraFactor] = {}
         for key, panel in weights.named.items():
@@ -409,10 +411,11 @@ class DitTrainer:
         pick = (lambda p, lora: (p.w_loraT if lora and p.w_loraT is not None else p.wT)) if transposed else \
                (lambda p, lora: (p.w_lora if lora and p.w_lora is not None else p.w))
         bias = (lambda p: None) if transposed else (lambda p: p.bias)
+        ll = self.latent_lora  # model_config.latent_lora: the adapters stay active on the image (single: text+image) rows
         if ctx is not None:  # double block: [txt | img | cond]
-            return pick(ctx, False), bias(ctx), [(pick(main, False), bias(main), self.Rt),
+            return pick(ctx, False), bias(ctx), [(pick(main, ll), bias(main), self.Rt),
                                                  (pick(main, True), bias(main), self.Rt + self.Ri)]
-        return pick(main, False), bias(main), [(pick(main, True), bias(main), self.Rt + self.Ri)]  # single: [txt+img | cond]
+        return pick(main, ll), bias(main), [(pick(main, True), bias(main), self.Rt + self.Ri)]  # single: [txt+img | cond]
 
     def _gemm(self, A, main, ctx, out, transposed=False):
         W0, b0, extra = self._groups(main, ctx, transposed)
@@ -449,9 +452,12 @@ class DitTrainer:
         return g["dQh"], g["dKh"], g["dVh"]
 
     # -- blocks -------------------------------------------------------------------------------------------------------
-    def _gemm_cond(self, A, main: PackedLinear, out):
+    def _gemm_cond(self, A, main: PackedLinear, out, ctx: Optional[PackedLinear] = None):
         """the condition rows only, against the LoRA-merged panel (recompute of a projection whose output the backward
-        needs on the condition stream alone: the gate gradient feeds the LoRA of the AdaLN linear)."""
+        needs on the condition stream alone: the gate gradient feeds the LoRA of the AdaLN linear).  With latent_lora the
+        image (single blocks: text + image) rows carry LoRA as well, so everything is rebuilt."""
+        if self.latent_lora:
+            return self._gemm(A, main, ctx, out)
         c0 = self.Rt + self.Ri
         ops.gemm(A[c0:], main.w_lora if main.w_lora is not None else main.w, main.bias, out[c0:], L.EPI_BIAS)
 
@@ -469,7 +475,7 @@ class DitTrainer:
         O = a["Cat"][:, :D]
         self._attention(O)
         if recompute:
-            self._gemm_cond(O, W[f"double.{i}.out"], a["Y1"])
+            self._gemm_cond(O, W[f"double.{i}.out"], a["Y1"], W[f"double.{i}.out_ctx"])
             x1 = self.ckpt_mid[i]
         else:
             self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
@@ -480,7 +486,7 @@ class DitTrainer:
         self._gemm(a["XN2"], W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], pre_ff)
         gelu_fwd(pre_ff, a["Hid"])
         if recompute:
-            self._gemm_cond(a["Hid"], W[f"double.{i}.ff_down"], a["Y2"])
+            self._gemm_cond(a["Hid"], W[f"double.{i}.ff_down"], a["Y2"], W[f"double.{i}.ff_ctx_down"])
         else:
             self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], a["Y2"])
             gate_residual_fwd(x1, a["Y2"], X, tm, m[5])
@@ -490,8 +496,9 @@ class DitTrainer:
         b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
         tm = b["tile_meta"]
         m = self._mods_double(i)
-        c0 = self.Rt + self.Ri  # first condition row
-        dm = lambda c: [None, None, self.dmod_dbl[:, (i * 6 + c) * D:(i * 6 + c + 1) * D]]  # noqa: E731
+        c0 = self.Rt if self.latent_lora else self.Rt + self.Ri  # first row whose Linear carries LoRA
+        dm = lambda c: [None, self.dmod_dbl_img[:, (i * 6 + c) * D:(i * 6 + c + 1) * D] if self.latent_lora else None,  # noqa: E731
+                        self.dmod_dbl[:, (i * 6 + c) * D:(i * 6 + c + 1) * D]]
         pfx = f"transformer_blocks.{i}."
         pre, pre_ff = a["QM"][:, :3 * D], a["QM"][:, 3 * D:7 * D]
         O = a["Cat"][:, :D]
@@ -536,8 +543,9 @@ class DitTrainer:
         b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
         tm = b["tile_meta"]
         m = self._mods_single(i)
-        c0 = self.Rt + self.Ri
-        dm = lambda c: [None, None, self.dmod_sgl[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]]  # noqa: E731
+        c0 = 0 if self.latent_lora else self.Rt + self.Ri
+        dm = lambda c: ([self.dmod_sgl_ti[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]] * 2 if self.latent_lora else [None, None]) + \
+            [self.dmod_sgl[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]]  # noqa: E731
         pfx = f"single_transformer_blocks.{i}."
         gate_bwd(g["dX"], a["Y1"], g["dY"], tm, m[2], dm(2))
         self._lora_grads([pfx + "proj_out"], a["Cat"][c0:], g["dY"][c0:])
@@ -581,7 +589,7 @@ class DitTrainer:
         pred = torch.empty((B, self.ni, cfg.in_channels), device=X.device, dtype=torch.bfloat16)
         po = self.w.named["proj_out"]
         ops.gemm(XNi, po.w, po.bias, pred.view(self.Ri, cfg.in_channels), L.EPI_BIAS)
-        self._saved = dict(x0=x0, x1=x1.contiguous(), pred=pred, cond_latents=cond_latents.to(torch.bfloat16).contiguous(),
+        self._saved = dict(x0=x0, x1=x1.contiguous(), pred=pred, xt=xt, cond_latents=cond_latents.to(torch.bfloat16).contiguous(),
                            X_final=X.clone())
         self.loss.zero_()
         flow_mse_loss(pred, x0, self._saved["x1"], self.loss, None)
@@ -597,6 +605,9 @@ class DitTrainer:
         nl, ns = cfg.num_layers, cfg.num_single_layers
         self.dmod_dbl.zero_()
         self.dmod_sgl.zero_()
+        if self.latent_lora:
+            self.dmod_dbl_img.zero_()
+            self.dmod_sgl_ti.zero_()
         dpred = torch.empty_like(s["pred"])
         scratch_loss = torch.zeros_like(self.loss)
         flow_mse_loss(s["pred"], s["x0"], s["x1"], scratch_loss, dpred, grad_scale)
@@ -617,17 +628,23 @@ class DitTrainer:
             X.copy_(self.ckpt[i])
             self._double_fwd(i, recompute=True)
             self._double_bwd(i, self.ckpt[i])
-        # x_embedder on the condition rows (transformer.py:93)
+        # x_embedder on the condition rows (transformer.py:93) (+ the image rows with latent_lora, transformer.py:91-92)
         c0 = self.Rt + self.Ri
         self._lora_grads(["x_embedder"], s["cond_latents"].view(self.Rc, cfg.in_channels), g["dX"][c0:])
-        # AdaLN linears of the condition stream: emb -> [B, 6D | 3D] per block, input silu(cond_temb)
-        silu_c = b["silu_c"]
-        dmd, dms = cast_bf16(self.dmod_dbl), cast_bf16(self.dmod_sgl)
-        for i in range(nl):
-            self._lora_grads([f"transformer_blocks.{i}.norm1.linear"], silu_c, dmd[:, i * 6 * self.D:(i + 1) * 6 * self.D])
-        for i in range(ns):
-            self._lora_grads([f"single_transformer_blocks.{i}.norm.linear"], silu_c,
-                             dms[:, i * 3 * self.D:(i + 1) * 3 * self.D])
+        if self.latent_lora:
+            self._lora_grads(["x_embedder"], s["xt"].view(self.Ri, cfg.in_channels), g["dX"][self.Rt:c0])
+        # AdaLN linears: emb -> [B, 6D | 3D] per block; input silu(cond_temb) for the condition stream, silu(temb) for the
+        # image (double) / text+image (single) rows when latent_lora keeps their adapters active
+        silu_c, silu_t = b["silu_c"], b["silu_t"]
+        pairs = [(silu_c, cast_bf16(self.dmod_dbl), cast_bf16(self.dmod_sgl))]
+        if self.latent_lora:
+            pairs.append((silu_t, cast_bf16(self.dmod_dbl_img), cast_bf16(self.dmod_sgl_ti)))
+        for x_in, dmd, dms in pairs:
+            for i in range(nl):
+                self._lora_grads([f"transformer_blocks.{i}.norm1.linear"], x_in, dmd[:, i * 6 * self.D:(i + 1) * 6 * self.D])
+            for i in range(ns):
+                self._lora_grads([f"single_transformer_blocks.{i}.norm.linear"], x_in,
+                                 dms[:, i * 3 * self.D:(i + 1) * 3 * self.D])
 
     def grads(self) -> Dict[str, torch.Tensor]:
         out = {}

@@ -237,8 +237,9 @@ def _tiny_train_case(layers=(2, 2), B=2, nt=128, ni=128, nc=128, seed=0):
     return ocfg, cfg, P, batch
 
 
-@pytest.mark.parametrize("layers", [(1, 1), (2, 2)])
-def test_train_step_loss_and_lora_grads_vs_oracle(layers):
+@pytest.mark.parametrize("layers,mc", [((1, 1), {}), ((2, 2), {}), ((2, 2), {"latent_lora": True}),
+                                       ((1, 2), {"independent_condition": True})])
+def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc):
     """Native forward + backward vs fp32 autograd over the oracle restatement of model.py:569-729."""
     from oracle import sampler as OS
     from oracle import train_step as TS
@@ -250,9 +251,9 @@ def test_train_step_loss_and_lora_grads_vs_oracle(layers):
     P32 = {k: v.float().to(DEV) for k, v in P.items()}
     b_dev = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
     loss_ref, grads_ref, aux = TS.flow_step_grads(P32, ocfg, {k: (v.float() if isinstance(v, torch.Tensor) else v)
-                                                              for k, v in b_dev.items()}, model_config={})
+                                                              for k, v in b_dev.items()}, model_config=mc)
     W = DitWeights({k: v.to(DEV) for k, v in P.items()}, cfg, DEV)
-    tr = DitTrainer(W, B, 128, 128, 128, model_config={})
+    tr = DitTrainer(W, B, 128, 128, 128, model_config=mc)
     x0 = OS.pack_latents(b_dev["image"]).contiguous()
     cond = OS.pack_latents(b_dev["condition"]).contiguous()
     img_ids = OS.prepare_latent_image_ids(batch["image"].shape[2], batch["image"].shape[3]).to(DEV)
@@ -262,7 +263,7 @@ def test_train_step_loss_and_lora_grads_vs_oracle(layers):
     torch.cuda.synchronize()
     loss1 = loss.item()  # the trainer reuses its loss buffer
     e_pred = _rel(tr.pred, aux["pred"])
-    print(f"\n[train {layers}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
+    print(f"\n[train {layers} {mc}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
     assert e_pred < 2e-2
     assert abs(loss1 - loss_ref.item()) / loss_ref.item() < 2e-2
     tr.zero_grad()
