@@ -306,11 +306,13 @@ class DitTrainer:
         self.latent_lora = bool(model_config.get("latent_lora", False))
         if n_cond <= 0:
             raise NotImplementedError("the training step needs a condition stream (the LoRA lives on the condition branch)")
-        if n_txt % 128 or n_img % 128 or n_cond % 128:
-            raise NotImplementedError(f"training with stream lengths {(n_txt, n_img, n_cond)} that are not multiples of 128 "
-                                      "(inference pads and masks them; the trainer's loss / gradient plumbing does not yet)")
         self.w, self.cfg = weights, weights.cfg
         self.plan = DitPlan(weights, B, n_txt, n_img, n_cond, T=1, model_config=model_config)
+        # ragged stream lengths: the plan pads every stream to 128-token tiles; all row counts below are PADDED, the loss
+        # and dpred cover the valid image tokens only (padding rows carry zero gradients, padding keys are masked)
+        self.ni_valid, self.nc_valid = n_img, n_cond
+        n_txt, n_img, n_cond = self.plan.ntp, self.plan.nip, self.plan.ncp
+        self.pads = (self.plan.ntp - self.plan.nt, self.plan.nip - self.plan.ni, self.plan.ncp - self.plan.nc)
         self.B, self.nt, self.ni, self.nc = B, n_txt, n_img, n_cond
         cfg = self.cfg
         self.D, self.H = cfg.inner_dim, cfg.num_attention_heads
@@ -436,7 +438,7 @@ class DitTrainer:
         """out: [R, ld] view; head h lands in columns [128h, 128h+128).  Also records the log-sum-exp rows."""
         b, p = self.plan.buf, self.plan.plan
         ops.attention(b["Q"], b["K"], b["V"], out, b["out_row_base"], n_cond=self.nc, mask_mode=p.mask_mode,
-                      cross_bias=p.cross_bias, lse=self.lse)
+                      cross_bias=p.cross_bias, lse=self.lse, pads=self.pads, n_txt=self.nt)
 
     def _attention_bwd(self, d_rows, o_rows):
         """d_rows / o_rows: [R, >= D] views holding dO / O in their first D columns -> dq, dk, dv head-major (bf16)."""
@@ -447,7 +449,7 @@ class DitTrainer:
         ops.attention_bwd_prep(d_rows, o_rows, self.H, b["tile_meta"], g["dOh"], self.delta)
         self.dq32.zero_()
         ops.attention_bwd(b["Q"], b["K"], b["V"], g["dOh"], self.lse, self.delta, self.dq32, g["dKh"], g["dVh"],
-                          n_cond=self.nc, mask_mode=p.mask_mode, cross_bias=p.cross_bias)
+                          n_cond=self.nc, mask_mode=p.mask_mode, cross_bias=p.cross_bias, pads=self.pads, n_txt=self.nt)
         L.check(_lib.lx_cast(self.dq32.data_ptr(), g["dQh"].data_ptr(), self.dq32.numel(), 1, _stream()), "lx_cast")
         return g["dQh"], g["dKh"], g["dVh"]
 
@@ -565,13 +567,18 @@ class DitTrainer:
         """x0, x1: bf16 [B, n_img, C] packed latents / noise; t: fp32 [B] in (0, 1) -> loss (fp32 [1] tensor).
         model.py:590-594 (x_t), 705-723 (tranformer_forward), 726 (mse)."""
         B, cfg, b, a = self.B, self.cfg, self.plan.buf, self.a
-        assert x0.dtype == torch.bfloat16 and x0.shape == (B, self.ni, cfg.in_channels) and x0.is_contiguous()
+        assert x0.dtype == torch.bfloat16 and x0.shape == (B, self.ni_valid, cfg.in_channels) and x0.is_contiguous()
+        assert self.attn_bwd == "native" or not any(self.pads), "the library A/B path has no padding mask"
         t = t.to(device=x0.device, dtype=torch.float32).contiguous()
-        xt = flow_noise_mix(x0, x1.contiguous(), t)
+        pad_tok = self.plan._pad_tokens
+        x0, x1 = pad_tok(x0, self.ni), pad_tok(x1.contiguous(), self.ni)  # zero rows: pred - (x1 - x0) is masked below
+        cond_latents = pad_tok(cond_latents.to(torch.bfloat16).contiguous(), self.nc)
+        xt = flow_noise_mix(x0, x1, t)
         self.plan.set_ids(txt_ids, img_ids, cond_ids)
         ts = [float(v) for v in t.tolist()]
-        self.plan.prepare(prompt_embeds, pooled, cond_latents, ts, [guidance] * B if cfg.guidance_embeds else None, c_t=0.0)
-        self.plan.embed(xt)
+        self.plan.prepare(prompt_embeds, pooled, cond_latents[:, :self.nc_valid], ts,
+                          [guidance] * B if cfg.guidance_embeds else None, c_t=0.0)
+        self.plan.embed(xt[:, :self.ni_valid])
         X = b["X"]
         nl, ns = cfg.num_layers, cfg.num_single_layers
         for i in range(nl):
@@ -589,11 +596,14 @@ class DitTrainer:
         pred = torch.empty((B, self.ni, cfg.in_channels), device=X.device, dtype=torch.bfloat16)
         po = self.w.named["proj_out"]
         ops.gemm(XNi, po.w, po.bias, pred.view(self.Ri, cfg.in_channels), L.EPI_BIAS)
-        self._saved = dict(x0=x0, x1=x1.contiguous(), pred=pred, xt=xt, cond_latents=cond_latents.to(torch.bfloat16).contiguous(),
-                           X_final=X.clone())
+        if any(self.pads):  # padding image rows: make the residual exactly zero so they add nothing to loss / dpred
+            pred[:, self.ni_valid:].zero_()
+        self._saved = dict(x0=x0, x1=x1, pred=pred, xt=xt, cond_latents=cond_latents, X_final=X.clone())
         self.loss.zero_()
-        flow_mse_loss(pred, x0, self._saved["x1"], self.loss, None)
-        self.pred = pred
+        flow_mse_loss(pred, x0, x1, self.loss, None)
+        if any(self.pads):  # mean over the valid elements (the kernel divided by the padded count)
+            self.loss.mul_(self.ni / self.ni_valid)
+        self.pred = pred[:, :self.ni_valid]
         return self.loss
 
     @torch.no_grad()
@@ -610,7 +620,7 @@ class DitTrainer:
             self.dmod_sgl_ti.zero_()
         dpred = torch.empty_like(s["pred"])
         scratch_loss = torch.zeros_like(self.loss)
-        flow_mse_loss(s["pred"], s["x0"], s["x1"], scratch_loss, dpred, grad_scale)
+        flow_mse_loss(s["pred"], s["x0"], s["x1"], scratch_loss, dpred, grad_scale * (self.ni / self.ni_valid))
         # proj_out / norm_out backward on the image rows; text and condition rows of the final stream get no gradient
         g["dX"].zero_()
         sl = slice(self.Rt, self.Rt + self.Ri)

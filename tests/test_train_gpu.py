@@ -219,7 +219,7 @@ def test_flow_objective_kernels():
     assert _rel(dpred, gref) < 4e-3
 
 
-def _tiny_train_case(layers=(2, 2), B=2, nt=128, ni=128, nc=128, seed=0):
+def _tiny_train_case(layers=(2, 2), B=2, nt=128, hw=(16, 32), seed=0):
     from oracle import flux_dit as O
     from loongx_b200.config import FluxConfig
 
@@ -229,7 +229,8 @@ def _tiny_train_case(layers=(2, 2), B=2, nt=128, ni=128, nc=128, seed=0):
     P = O.init_params(ocfg, seed=1234, dtype=torch.float32, device="cpu", w_std=0.05, bias_std=0.05, lora_b_std=0.05)
     P = {k: v.to(torch.bfloat16) for k, v in P.items()}
     g = torch.Generator().manual_seed(seed)
-    h, w = 16, 2 * ni // 8  # latent grid: (h/2)*(w/2) = ni
+    h, w = hw  # latent grid: (h/2)*(w/2) image tokens
+    ni = (h // 2) * (w // 2)
     r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16()  # noqa: E731
     batch = dict(image=r(B, 16, h, w), condition=r(B, 16, h, w), prompt_embeds=r(B, nt, 256, scale=0.5),
                  pooled_prompt_embeds=r(B, 64), position_delta=[[0, -(w // 2)]], t=torch.tensor([0.35, 0.8][:B]),
@@ -237,33 +238,36 @@ def _tiny_train_case(layers=(2, 2), B=2, nt=128, ni=128, nc=128, seed=0):
     return ocfg, cfg, P, batch
 
 
-@pytest.mark.parametrize("layers,mc", [((1, 1), {}), ((2, 2), {}), ((2, 2), {"latent_lora": True}),
-                                       ((1, 2), {"independent_condition": True})])
-def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc):
+@pytest.mark.parametrize("layers,mc,nt,hw", [((1, 1), {}, 128, (16, 32)), ((2, 2), {}, 128, (16, 32)),
+                                             ((2, 2), {"latent_lora": True}, 128, (16, 32)),
+                                             ((1, 2), {"independent_condition": True}, 128, (16, 32)),
+                                             ((1, 1), {}, 100, (12, 20)), ((2, 1), {"latent_lora": True}, 77, (20, 36))])
+def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc, nt, hw):
     """Native forward + backward vs fp32 autograd over the oracle restatement of model.py:569-729."""
     from oracle import sampler as OS
     from oracle import train_step as TS
     from loongx_b200.dit import DitWeights
     from loongx_b200.train import DitTrainer
 
-    ocfg, cfg, P, batch = _tiny_train_case(layers)
+    ocfg, cfg, P, batch = _tiny_train_case(layers, nt=nt, hw=hw)
     B = batch["image"].shape[0]
+    ni = (hw[0] // 2) * (hw[1] // 2)
     P32 = {k: v.float().to(DEV) for k, v in P.items()}
     b_dev = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
     loss_ref, grads_ref, aux = TS.flow_step_grads(P32, ocfg, {k: (v.float() if isinstance(v, torch.Tensor) else v)
                                                               for k, v in b_dev.items()}, model_config=mc)
     W = DitWeights({k: v.to(DEV) for k, v in P.items()}, cfg, DEV)
-    tr = DitTrainer(W, B, 128, 128, 128, model_config=mc)
+    tr = DitTrainer(W, B, nt, ni, ni, model_config=mc)  # ragged lengths are padded to 128-token tiles inside
     x0 = OS.pack_latents(b_dev["image"]).contiguous()
     cond = OS.pack_latents(b_dev["condition"]).contiguous()
     img_ids = OS.prepare_latent_image_ids(batch["image"].shape[2], batch["image"].shape[3]).to(DEV)
     cond_ids = OS.condition_ids(img_ids, batch["position_delta"][0])
     loss = tr.forward(x0, b_dev["noise"], b_dev["t"], cond, b_dev["prompt_embeds"], b_dev["pooled_prompt_embeds"],
-                      torch.zeros(128, 3, device=DEV), img_ids, cond_ids, guidance=1.0)
+                      torch.zeros(nt, 3, device=DEV), img_ids, cond_ids, guidance=1.0)
     torch.cuda.synchronize()
     loss1 = loss.item()  # the trainer reuses its loss buffer
     e_pred = _rel(tr.pred, aux["pred"])
-    print(f"\n[train {layers} {mc}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
+    print(f"\n[train {layers} {mc} nt={nt} ni={ni}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
     assert e_pred < 2e-2
     assert abs(loss1 - loss_ref.item()) / loss_ref.item() < 2e-2
     tr.zero_grad()
@@ -290,7 +294,7 @@ def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc):
         f.B.data.add_(f.dB, alpha=-lr)
     tr.remerge()
     loss2 = tr.forward(x0, b_dev["noise"], b_dev["t"], cond, b_dev["prompt_embeds"], b_dev["pooled_prompt_embeds"],
-                       torch.zeros(128, 3, device=DEV), img_ids, cond_ids, guidance=1.0).item()
+                       torch.zeros(nt, 3, device=DEV), img_ids, cond_ids, guidance=1.0).item()
     print(f"[train {layers}] loss after one SGD step {loss2:.6f}")
     assert loss2 < loss1
 
