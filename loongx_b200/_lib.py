@@ -95,6 +95,12 @@ lib.lx_attention_bwd_prep.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_in
                                       c_int32, c_void_p]
 
 
+import os as _os
+
+if _os.environ.get("LX_RASTER_MB"):  # development aid: L2 budget of the GEMM raster bands (see gemm.cu::tile_coords)
+    lib.lx_debug_gemm_raster_budget_mb(int(_os.environ["LX_RASTER_MB"]))
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         raise LoongXNativeError(f"{what} failed ({rc}): {lib.lx_last_error().decode()}")

@@ -17,9 +17,10 @@ for M in Ms:
         A = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         res = []
-        for ncta in (1, 2):
-            L.lib.lx_debug_gemm_force_ncta(1 if ncta == 1 else 0)
-            for tn in (0, 256, 224, 192):
+        for budget in [int(b) for b in os.environ.get("LX_RASTER_MB", "100000,80").split(",")]:
+            L.lib.lx_debug_gemm_raster_budget_mb(budget)
+            ncta = 2
+            for tn in (0,):
                 reps = 3 * ncopy
                 for i in range(ncopy):
                     ops.gemm(A, Ws[i], None, out, tile_n=tn)
@@ -29,6 +30,6 @@ for M in Ms:
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / reps
-                res.append(f"ncta{ncta}/bn{tn or 'auto'}: {2.0 * M * N * K / ms / 1e9:7.1f}")
+                res.append(f"raster{budget}MB: {2.0 * M * N * K / ms / 1e9:7.1f}")
         print(f"M={M:6d} {name:15s} N={N:6d} K={K:6d} | " + "  ".join(res), flush=True)
         del Ws
