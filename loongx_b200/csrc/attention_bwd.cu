@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ AttnBwdParams p) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the 128-byte-swizzle atoms need a 1 KiB-aligned base (no slack left)
@@ -353,6 +355,8 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(const __nv_bfloat16*
                                                             int heads, const lx_tile_meta_t* __restrict__ tm,
                                                             __nv_bfloat16* __restrict__ do_heads, float* __restrict__ delta,
                                                             int seq_total) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const lx_tile_meta_t m = tm[row >> 7];
   const int seq = m.seq_row + (row & 127);
@@ -379,7 +383,7 @@ extern "C" int lx_attention_bwd_prep(const void* d_out_rows, int64_t ld_do, cons
                    ld_do % 4 == 0 && ld_o % 4 == 0,
                "lx_attention_bwd_prep: bad arguments");
   LaunchScope scope(KC_ROW, stream, 6.0 * rows * heads * 128);
-  attn_bwd_prep_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(attn_bwd_prep_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(d_out_rows), ld_do, reinterpret_cast<const __nv_bfloat16*>(out_rows), ld_o, rows,
       heads, tile_meta, reinterpret_cast<__nv_bfloat16*>(d_out_heads), delta, seq_total);
   LX_CUDA(cudaGetLastError());
@@ -433,7 +437,7 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
     if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
   }
   LaunchScope scope(KC_ATTENTION, stream, 10.0 * d.B * d.H * pairs * 128.0);  // five 2*S*S*128 products
-  attention_bwd_kernel<<<dim3(d.S / 128, d.H, d.B), AB_THREADS, AB_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV,
+  launch_pdl(attention_bwd_kernel, dim3(d.S / 128, d.H, d.B), dim3(AB_THREADS), AB_SMEM, static_cast<cudaStream_t>(stream), tmQ, tmK, tmV,
                                                                                                              tmdO, tmdQ, p);
   LX_CUDA(cudaGetLastError());
   return LX_OK;

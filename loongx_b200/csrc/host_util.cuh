@@ -47,6 +47,23 @@ bool pdl_enabled();
 // Launch accounting + optional per-kernel-class CUDA-event timing (bench.py's roofline numbers): every extern "C"
 // launcher opens a LaunchScope; with profiling off it only bumps a counter.
 enum KernelClass { KC_GEMM = 0, KC_ATTENTION = 1, KC_ROW = 2, KC_CS3DGF = 3, KC_COUNT = 4 };
+// Kernel launch with the programmatic-dependent-launch attribute (when enabled).  The kernel MUST call pdl_wait() before
+// its first global-memory access (ptx.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct LaunchScope {
   LaunchScope(int cls, void* stream, double work);  // work: FLOPs (tensor kernels) or bytes (HBM-bound kernels)
   ~LaunchScope();

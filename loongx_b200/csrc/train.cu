@@ -44,6 +44,8 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, int64_t ld_pre, __nv_bfloat16* __restrict__ out,
                                 int64_t ldo, int rows, int cols8) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * cols8) return;
   const int r = (int)(idx / cols8), c = (int)(idx % cols8) * 8;
@@ -56,6 +58,8 @@ __global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, int64_t l
 
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, int64_t ld_pre, const __nv_bfloat16* dy,
                                 int64_t ld_dy, __nv_bfloat16* dx /* may alias dy */, int64_t ld_dx, int rows, int cols8) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * cols8) return;
   const int r = (int)(idx / cols8), c = (int)(idx % cols8) * 8;
@@ -74,6 +78,8 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, int64_t l
 __global__ void gate_residual_fwd_kernel(const __nv_bfloat16* res, const __nv_bfloat16* __restrict__ y,
                                          __nv_bfloat16* out /* may alias res (element-local) */, int64_t ld, int rows, int D8,
                                          const lx_tile_meta_t* __restrict__ tm, Vec3 gate) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * D8) return;
   const int r = (int)(idx / D8), c = (int)(idx % D8) * 8;
@@ -93,6 +99,8 @@ __global__ void __launch_bounds__(128) gate_bwd_kernel(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy,
                                                        int64_t ld, int rows, int D, const lx_tile_meta_t* __restrict__ tm,
                                                        Vec3 gate, Acc3 dgate) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int tile = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x * 2;
   if (c >= D) return;
   const lx_tile_meta_t m = tm[tile];
@@ -143,6 +151,8 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_mod_bwd_row_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16* dres,
     __nv_bfloat16* dx /* may alias dres (row-local) */, int64_t ld, int D, const lx_tile_meta_t* __restrict__ tm, Vec3 scale, float eps,
     float2* __restrict__ stats) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   __shared__ float red[4];
   const int row = blockIdx.x;
   const lx_tile_meta_t m = tm[row >> 7];
@@ -212,6 +222,8 @@ __global__ void __launch_bounds__(128) ln_mod_bwd_col_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ dxn, int64_t ld, int rows,
                                                              int D, const lx_tile_meta_t* __restrict__ tm,
                                                              const float2* __restrict__ stats, Acc3 dscale, Acc3 dshift) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int tile = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x * 2;
   if (c >= D) return;
   const lx_tile_meta_t m = tm[tile];
@@ -265,6 +277,8 @@ __global__ void __launch_bounds__(128) qkv_post_fwd_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k,
                                                            __nv_bfloat16* __restrict__ v, int seq_total, RmsW w,
                                                            const float* __restrict__ rope, float eps) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const lx_tile_meta_t m = tm[row >> 7];
   const int seq = m.seq_row + (row & 127);  // batch * S + position in the joint sequence
@@ -309,6 +323,8 @@ __global__ void __launch_bounds__(128) qkv_post_bwd_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ dpre, int64_t ldo, int rows, int heads,
                                                            const lx_tile_meta_t* __restrict__ tm, int seq_total, RmsW w,
                                                            const float* __restrict__ rope, float eps) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const lx_tile_meta_t m = tm[row >> 7];
   const int seq = m.seq_row + (row & 127);
@@ -358,6 +374,8 @@ __global__ void __launch_bounds__(128) qkv_post_bwd_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(128) rows_to_heads_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld, int rows,
                                                             int heads, const lx_tile_meta_t* __restrict__ tm,
                                                             __nv_bfloat16* __restrict__ out, int seq_total) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const lx_tile_meta_t m = tm[row >> 7];
   const int seq = m.seq_row + (row & 127);
@@ -383,6 +401,8 @@ template <int RMAX, int RPW>
 __global__ void __launch_bounds__(128) lora_project_kernel(const __nv_bfloat16* __restrict__ Z, int64_t ldz, int M, int C,
                                                            const float* __restrict__ F, int64_t f_stride_c,
                                                            int64_t f_stride_j, int r, float* __restrict__ P) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int row0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * RPW, lane = threadIdx.x & 31;
   if (row0 >= M) return;
   const int c_begin = blockIdx.y * LORA_CCHUNK, c_end = min(C, c_begin + LORA_CCHUNK);  // column split: partial sums
@@ -424,6 +444,8 @@ template <int RMAX>
 __global__ void __launch_bounds__(128) lora_reduce_kernel(const __nv_bfloat16* __restrict__ Z, int64_t ldz, int M, int C,
                                                           const float* __restrict__ P, int r, float scaling,
                                                           float* __restrict__ G, int64_t g_stride_c, int64_t g_stride_j) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   __shared__ float ps[128 * RMAX];
   const int r0 = blockIdx.x * 128, r1 = min(M, r0 + 128);
   for (int i = threadIdx.x; i < 128 * RMAX; i += 128) {
@@ -472,6 +494,8 @@ __global__ void __launch_bounds__(128) lora_reduce_kernel(const __nv_bfloat16* _
 __global__ void lora_merge_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ A,
                                   const float* __restrict__ Bw, __nv_bfloat16* __restrict__ out, int64_t ldo, int N, int K,
                                   int r, float scaling) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int K2 = K >> 1;
   if (idx >= (int64_t)N * K2) return;
@@ -489,6 +513,8 @@ __global__ void lora_merge_kernel(const __nv_bfloat16* __restrict__ W, int64_t l
 // out[c, r] = in[r, c]   (32x32 shared-memory tiles; builds the K-major W^T panels the dX GEMMs multiply by)
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out,
                                       int64_t ld_out, int rows, int cols) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   __shared__ __nv_bfloat16 t[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -508,6 +534,8 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int6
 __global__ void flow_noise_mix_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                       const float* __restrict__ t, __nv_bfloat16* __restrict__ xt, int64_t per_sample8,
                                       int64_t n8) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n8) return;
   const float tt = t[idx / per_sample8];
@@ -524,6 +552,8 @@ __global__ void __launch_bounds__(256) flow_mse_kernel(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ x1, float* __restrict__ loss,
                                                        __nv_bfloat16* __restrict__ dpred, int64_t n8, float inv_n,
                                                        float grad_scale) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
   __shared__ float red[8];
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float s = 0.f;
@@ -577,7 +607,7 @@ extern "C" int lx_gelu_fwd(const void* pre, int64_t ld_pre, void* out, int64_t l
   LX_CHECK_ARG(pre && out && rows > 0 && cols > 0 && cols % 8 == 0 && ld_pre % 8 == 0 && ldo % 8 == 0, "lx_gelu_fwd: bad arguments");
   const int64_t n = (int64_t)rows * (cols / 8);
   LaunchScope scope(KC_ROW, stream, 4.0 * rows * cols);
-  gelu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs(stream)>>>(bf(pre), ld_pre, bf(out), ldo, rows, cols / 8);
+  launch_pdl(gelu_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cs(stream), bf(pre), ld_pre, bf(out), ldo, rows, cols / 8);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -588,7 +618,7 @@ extern "C" int lx_gelu_bwd(const void* pre, int64_t ld_pre, const void* dy, int6
                "lx_gelu_bwd: bad arguments");
   const int64_t n = (int64_t)rows * (cols / 8);
   LaunchScope scope(KC_ROW, stream, 6.0 * rows * cols);
-  gelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs(stream)>>>(bf(pre), ld_pre, bf(dy), ld_dy, bf(dx), ld_dx, rows,
+  launch_pdl(gelu_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cs(stream), bf(pre), ld_pre, bf(dy), ld_dy, bf(dx), ld_dx, rows,
                                                                       cols / 8);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -601,7 +631,7 @@ extern "C" int lx_gate_residual_fwd(const void* res, const void* y, void* out, i
                "lx_gate_residual_fwd: bad arguments");
   const int64_t n = (int64_t)rows * (D / 8);
   LaunchScope scope(KC_ROW, stream, 6.0 * rows * D);
-  gate_residual_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs(stream)>>>(bf(res), bf(y), bf(out), ld, rows, D / 8,
+  launch_pdl(gate_residual_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cs(stream), bf(res), bf(y), bf(out), ld, rows, D / 8,
                                                                                tile_meta, vec3(gate, gate_stride));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -614,7 +644,7 @@ extern "C" int lx_gate_bwd(const void* dout, const void* y, void* dy, int64_t ld
                    ld % 2 == 0,
                "lx_gate_bwd: bad arguments");
   LaunchScope scope(KC_ROW, stream, 6.0 * rows * D);
-  gate_bwd_kernel<<<dim3(rows / 128, (D + 255) / 256), 128, 0, cs(stream)>>>(bf(dout), bf(y), bf(dy), ld, rows, D, tile_meta,
+  launch_pdl(gate_bwd_kernel, dim3(rows / 128, (D + 255) / 256), dim3(128), 0, cs(stream), bf(dout), bf(y), bf(dy), ld, rows, D, tile_meta,
                                                                             vec3(gate, gate_stride), acc3(dgate, dgate_stride));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -632,14 +662,14 @@ extern "C" int lx_ln_modulate_bwd(const void* x, const void* dxn, const void* dr
   LX_CHECK_ARG(!cols || stats_workspace, "lx_ln_modulate_bwd: stats workspace [rows,2] fp32 needed for dscale / dshift");
   {
     LaunchScope scope(KC_ROW, stream, (dres ? 8.0 : 6.0) * rows * D);
-    ln_mod_bwd_row_kernel<<<rows, LNB_THREADS, 0, cs(stream)>>>(bf(x), bf(dxn), bf(dres), bf(dx), ld, D, tile_meta,
+    launch_pdl(ln_mod_bwd_row_kernel, dim3(rows), dim3(LNB_THREADS), 0, cs(stream), bf(x), bf(dxn), bf(dres), bf(dx), ld, D, tile_meta,
                                                                vec3(scale, scale_stride), eps,
                                                                reinterpret_cast<float2*>(stats_workspace));
     LX_CUDA(cudaGetLastError());
   }
   if (cols) {
     LaunchScope scope(KC_ROW, stream, 4.0 * rows * D);
-    ln_mod_bwd_col_kernel<<<dim3(rows / 128, (D + 255) / 256), 128, 0, cs(stream)>>>(
+    launch_pdl(ln_mod_bwd_col_kernel, dim3(rows / 128, (D + 255) / 256), dim3(128), 0, cs(stream), 
         bf(x), bf(dxn), ld, rows, D, tile_meta, reinterpret_cast<const float2*>(stats_workspace), acc3(dscale, dstride),
         acc3(dshift, dstride));
     LX_CUDA(cudaGetLastError());
@@ -661,7 +691,7 @@ extern "C" int lx_qkv_post_fwd(const void* qkv_pre, int64_t ld, int32_t rows, in
   LX_CHECK_ARG(qkv_pre && q && k && v && tile_meta && rows > 0 && heads > 0 && seq_total > 0 && ld % 4 == 0 && ld >= 3 * heads * 128,
                "lx_qkv_post_fwd: bad arguments");
   LaunchScope scope(KC_ROW, stream, 12.0 * rows * heads * 128);
-  qkv_post_fwd_kernel<<<rows, 128, 0, cs(stream)>>>(bf(qkv_pre), ld, rows, heads, tile_meta, bf(q), bf(k), bf(v), seq_total,
+  launch_pdl(qkv_post_fwd_kernel, dim3(rows), dim3(128), 0, cs(stream), bf(qkv_pre), ld, rows, heads, tile_meta, bf(q), bf(k), bf(v), seq_total,
                                                    rmsw(rms_q, rms_k), rope, eps);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -675,7 +705,7 @@ extern "C" int lx_qkv_post_bwd(const void* qkv_pre, int64_t ld, const void* dq, 
                    ldo % 4 == 0 && ld >= 3 * heads * 128 && ldo >= 3 * heads * 128,
                "lx_qkv_post_bwd: bad arguments");
   LaunchScope scope(KC_ROW, stream, 18.0 * rows * heads * 128);
-  qkv_post_bwd_kernel<<<rows, 128, 0, cs(stream)>>>(bf(qkv_pre), ld, bf(dq), bf(dk), bf(dv), bf(dqkv_pre), ldo, rows, heads,
+  launch_pdl(qkv_post_bwd_kernel, dim3(rows), dim3(128), 0, cs(stream), bf(qkv_pre), ld, bf(dq), bf(dk), bf(dv), bf(dqkv_pre), ldo, rows, heads,
                                                    tile_meta, seq_total, rmsw(rms_q, rms_k), rope, eps);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -686,7 +716,7 @@ extern "C" int lx_rows_to_heads(const void* rows_in, int64_t ld, void* heads_out
   LX_CHECK_ARG(rows_in && heads_out && tile_meta && rows > 0 && heads > 0 && seq_total > 0 && ld % 4 == 0 && ld >= heads * 128,
                "lx_rows_to_heads: bad arguments");
   LaunchScope scope(KC_ROW, stream, 4.0 * rows * heads * 128);
-  rows_to_heads_kernel<<<rows, 128, 0, cs(stream)>>>(bf(rows_in), ld, rows, heads, tile_meta, bf(heads_out), seq_total);
+  launch_pdl(rows_to_heads_kernel, dim3(rows), dim3(128), 0, cs(stream), bf(rows_in), ld, rows, heads, tile_meta, bf(heads_out), seq_total);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -706,16 +736,16 @@ extern "C" int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t 
   const unsigned gn = (N + LORA_CCHUNK - 1) / LORA_CCHUNK, gk = (K + LORA_CCHUNK - 1) / LORA_CCHUNK;
   if (r <= 4) {
     const unsigned gm = (M + 31) / 32;  // 4 warps x 8 rows
-    lora_project_kernel<4, 8><<<dim3(gm, gn), 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
-    lora_project_kernel<4, 8><<<dim3(gm, gk), 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);    // F[c=k, j] = A[j*K + k]
-    lora_reduce_kernel<4><<<dim3(gr, (K + 511) / 512), 128, 0, st>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
-    lora_reduce_kernel<4><<<dim3(gr, (N + 511) / 512), 128, 0, st>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
+    launch_pdl(lora_project_kernel<4, 8>, dim3(gm, gn), dim3(128), 0, st, bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
+    launch_pdl(lora_project_kernel<4, 8>, dim3(gm, gk), dim3(128), 0, st, bf(x), ldx, M, K, A, 1, K, r, P2);    // F[c=k, j] = A[j*K + k]
+    launch_pdl(lora_reduce_kernel<4>, dim3(gr, (K + 511) / 512), dim3(128), 0, st, bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
+    launch_pdl(lora_reduce_kernel<4>, dim3(gr, (N + 511) / 512), dim3(128), 0, st, bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
   } else {
     const unsigned gm = (M + 7) / 8;  // 4 warps x 2 rows
-    lora_project_kernel<LORA_MAX_R, 2><<<dim3(gm, gn), 128, 0, st>>>(bf(dy), ldy, M, N, Bw, r, 1, r, P1);
-    lora_project_kernel<LORA_MAX_R, 2><<<dim3(gm, gk), 128, 0, st>>>(bf(x), ldx, M, K, A, 1, K, r, P2);
-    lora_reduce_kernel<LORA_MAX_R><<<dim3(gr, (K + 511) / 512), 128, 0, st>>>(bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
-    lora_reduce_kernel<LORA_MAX_R><<<dim3(gr, (N + 511) / 512), 128, 0, st>>>(bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
+    launch_pdl(lora_project_kernel<LORA_MAX_R, 2>, dim3(gm, gn), dim3(128), 0, st, bf(dy), ldy, M, N, Bw, r, 1, r, P1);
+    launch_pdl(lora_project_kernel<LORA_MAX_R, 2>, dim3(gm, gk), dim3(128), 0, st, bf(x), ldx, M, K, A, 1, K, r, P2);
+    launch_pdl(lora_reduce_kernel<LORA_MAX_R>, dim3(gr, (K + 511) / 512), dim3(128), 0, st, bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
+    launch_pdl(lora_reduce_kernel<LORA_MAX_R>, dim3(gr, (N + 511) / 512), dim3(128), 0, st, bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
   }
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -727,7 +757,7 @@ extern "C" int lx_lora_merge(const void* W, int64_t ldw, const float* A, const f
                "lx_lora_merge: bad arguments");
   const int64_t n = (int64_t)N * (K / 2);
   LaunchScope scope(KC_ROW, stream, 4.0 * N * K);
-  lora_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs(stream)>>>(bf(W), ldw, A, Bw, bf(out), ldo, N, K, r, scaling);
+  launch_pdl(lora_merge_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cs(stream), bf(W), ldw, A, Bw, bf(out), ldo, N, K, r, scaling);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -736,7 +766,7 @@ extern "C" int lx_transpose_bf16(const void* in, int64_t ld_in, void* out, int64
                                  void* stream) {
   LX_CHECK_ARG(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "lx_transpose_bf16: bad arguments");
   LaunchScope scope(KC_ROW, stream, 4.0 * rows * cols);
-  transpose_bf16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, cs(stream)>>>(bf(in), ld_in, bf(out),
+  launch_pdl(transpose_bf16_kernel, dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, cs(stream), bf(in), ld_in, bf(out),
                                                                                                  ld_out, rows, cols);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -747,7 +777,7 @@ extern "C" int lx_flow_noise_mix(const void* x0, const void* x1, const float* t,
   LX_CHECK_ARG(x0 && x1 && t && xt && B > 0 && per_sample > 0 && per_sample % 8 == 0, "lx_flow_noise_mix: bad arguments");
   const int64_t n8 = (int64_t)B * per_sample / 8;
   LaunchScope scope(KC_ROW, stream, 6.0 * B * per_sample);
-  flow_noise_mix_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, cs(stream)>>>(bf(x0), bf(x1), t, bf(xt), per_sample / 8, n8);
+  launch_pdl(flow_noise_mix_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, cs(stream), bf(x0), bf(x1), t, bf(xt), per_sample / 8, n8);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -757,7 +787,7 @@ extern "C" int lx_flow_mse_loss(const void* pred, const void* x0, const void* x1
   LX_CHECK_ARG(pred && x0 && x1 && loss && n > 0 && n % 8 == 0, "lx_flow_mse_loss: bad arguments");
   const int64_t n8 = n / 8;
   LaunchScope scope(KC_ROW, stream, 8.0 * n);
-  flow_mse_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, cs(stream)>>>(bf(pred), bf(x0), bf(x1), loss, bf(dpred), n8,
+  launch_pdl(flow_mse_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, cs(stream), bf(pred), bf(x0), bf(x1), loss, bf(dpred), n8,
                                                                        1.0f / (float)n, grad_scale);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
