@@ -35,6 +35,7 @@ class _BlockHandle:
     def __init__(self, transformer: "NativeFluxTransformer", index: int, single: bool):
         self.transformer, self.index, self.single = transformer, index, single
         self.attn = _AttnHandle(transformer.cfg.num_attention_heads)
+        self.attn.block = self  # src.flux.block.attn_forward(attn, ...) finds its weights through the block
 
 
 class NativeFluxTransformer:

@@ -30,7 +30,8 @@ def tranformer_forward(transformer, condition_latents, condition_ids, condition_
     if joint_attention_kwargs is not None and joint_attention_kwargs.get("scale", 1.0) != 1.0:
         raise NotImplementedError("joint_attention_kwargs['scale'] != 1: LoRA is merged at load with scale 1")
     if transformer.training and transformer.gradient_checkpointing:
-        raise NotImplementedError("training (gradient-checkpointed) forward is not built yet (SURVEY.md §8 a17)")
+        raise NotImplementedError("tranformer_forward is the inference forward; the differentiable training path is "
+                                  "OminiModel.step (loongx_b200/train.py), which checkpoints / recomputes per block")
     model_config = model_config or {}
     use_condition = condition_latents is not None
     if txt_ids.ndim == 3:  # transformer.py:117-128 (deprecated batched ids)
