@@ -169,10 +169,14 @@ class DitWeights:
         self.cfg = cfg
         self.device = torch.device(device)
         dev = self.device
-        pk = lambda names, **kw: pack_linear(P, names, cfg, dev, pop=consume, **kw)  # noqa: E731
+        def pk(names, **kw):
+            self._last_names = list(names)
+            return pack_linear(P, names, cfg, dev, pop=consume, **kw)
+
         f32 = lambda key: (P.pop(key) if consume else P[key]).to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
         self.keep: List[object] = []
         self.named: Dict[str, PackedLinear] = {}  # "x_embedder", "double.3.qkv", "single.7.proj_out", ... -> panel
+        self.layout: Dict[str, List[str]] = {}    # panel / norm key -> diffusers module names stacked in it (for export)
         m = LxDitModel()
         m.num_layers, m.num_single_layers = cfg.num_layers, cfg.num_single_layers
         m.heads, m.in_channels = cfg.num_attention_heads, cfg.in_channels
@@ -184,6 +188,7 @@ class DitWeights:
         def put(field: str, pl: PackedLinear):
             self.keep.append(pl)
             self.named[field] = pl
+            self.layout[field] = self._last_names
             setattr(m, field, pl.c())
 
         put("x_embedder", pk(["x_embedder"]))
@@ -215,11 +220,13 @@ class DitWeights:
                 pl = pk(names)
                 self.keep.append(pl)
                 self.named[f"double.{i}.{field}"] = pl
+                self.layout[f"double.{i}.{field}"] = list(names)
                 setattr(blk, field, pl.c())
             for field in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
                 t = f32(p + f"attn.{field}.weight")
                 self.keep.append(t)
                 self.named[f"double.{i}.{field}"] = t
+                self.layout[f"double.{i}.{field}"] = [p + f"attn.{field}.weight"]
                 setattr(blk, field, t.data_ptr())
         self.sgl = (LxSingleBlock * max(cfg.num_single_layers, 1))()
         for i in range(cfg.num_single_layers):
@@ -228,19 +235,43 @@ class DitWeights:
             pl = pk([p + "attn.to_q", p + "attn.to_k", p + "attn.to_v", p + "proj_mlp"])
             self.keep.append(pl)
             self.named[f"single.{i}.qkv_mlp"] = pl
+            self.layout[f"single.{i}.qkv_mlp"] = [p + "attn.to_q", p + "attn.to_k", p + "attn.to_v", p + "proj_mlp"]
             blk.qkv_mlp = pl.c()
             pl = pk([p + "proj_out"])
             self.keep.append(pl)
             self.named[f"single.{i}.proj_out"] = pl
+            self.layout[f"single.{i}.proj_out"] = [p + "proj_out"]
             blk.proj_out = pl.c()
             for field in ("norm_q", "norm_k"):
                 t = f32(p + f"attn.{field}.weight")
                 self.keep.append(t)
                 self.named[f"single.{i}.{field}"] = t
+                self.layout[f"single.{i}.{field}"] = [p + f"attn.{field}.weight"]
                 setattr(blk, field, t.data_ptr())
         m.double_blocks = C.cast(self.dbl, c_void_p)
         m.single_blocks = C.cast(self.sgl, c_void_p)
         self.model = m
+
+    def export_params(self, dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+        """Inverse of the packing: flat dict in diffusers naming (`<module>.weight/.bias`, RMSNorm weights, LoRA factors as
+        `<module>.lora_A.weight` / `.lora_B.weight`), views / small copies of the packed panels."""
+        shapes = linear_shapes(self.cfg)
+        out: Dict[str, torch.Tensor] = {}
+        for key, names in self.layout.items():
+            obj = self.named[key]
+            if not isinstance(obj, PackedLinear):
+                out[names[0]] = obj.to(dtype)
+                continue
+            r0 = 0
+            for n in names:
+                rows = shapes[n][0]
+                out[n + ".weight"] = obj.w[r0:r0 + rows].to(dtype)
+                if obj.bias is not None:
+                    out[n + ".bias"] = obj.bias[r0:r0 + rows].to(dtype)
+                r0 += rows
+            for (n, _, _, A, Bw) in obj.lora:
+                out[n + ".lora_A.weight"], out[n + ".lora_B.weight"] = A, Bw
+        return out
 
     def param_bytes(self) -> int:
         tot = 0

@@ -88,6 +88,34 @@ class OminiModel(nn.Module):
         self._trainer_key = None  # a cached trainer holds views of the old factors
         return n
 
+    def save_lora(self, path: str):
+        """model.py:526-531: `pytorch_lora_weights.safetensors` in the layout of FluxPipeline.save_lora_weights."""
+        import os
+
+        from safetensors.torch import save_file
+
+        os.makedirs(path, exist_ok=True)
+        P = self.transformer.weights.export_params()
+        save_file({"transformer." + k: v.detach().float().cpu().contiguous() for k, v in P.items() if ".lora_" in k},
+                  os.path.join(path, "pytorch_lora_weights.safetensors"))
+
+    def state_dict(self, *args, **kwargs):
+        """The LoongX layout train.py:214-217 saves and inference.py:46-52 loads: `transformer.<diffusers name>` with the
+        peft-injected spellings (`.base_layer.weight`, `.lora_A.default.weight`) + the CS3 / DGF modules."""
+        sd = super().state_dict(*args, **kwargs)
+        P = self.transformer.weights.export_params()
+        targets = {k.rsplit(".lora_", 1)[0] for k in P if ".lora_" in k}
+        for k, v in P.items():
+            stem, kind = k.rsplit(".", 1)
+            if ".lora_" in k:
+                mod, ab = k[:-len(".weight")].rsplit(".lora_", 1)
+                sd[f"transformer.{mod}.lora_{ab}.default.weight"] = v
+            elif stem in targets:
+                sd[f"transformer.{stem}.base_layer.{kind}"] = v
+            else:
+                sd["transformer." + k] = v
+        return sd
+
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         """LoongX `model.state_dict()` (inference.py:46-52): `transformer.*` keys (peft spellings accepted) replace the
         native DiT weights, everything else goes to the CS3 / DGF modules."""

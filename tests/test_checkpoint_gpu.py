@@ -78,9 +78,19 @@ def test_checkpoint_formats_end_to_end(tmp_path):
             sd[f"transformer.{stem}.base_layer.{kind}"] = v
         else:
             sd["transformer." + k] = v
-    sd.update({k: v.clone() for k, v in m.state_dict().items()})  # CS3 / DGF modules, strict load
+    sd.update({k: v.clone() for k, v in m.state_dict().items() if not k.startswith("transformer.")})  # CS3 / DGF, strict
     res = m.load_state_dict(sd)
     assert not res.missing_keys and not res.unexpected_keys
     e2 = _rel(_forward(m, inp, B), oracle(P2))
+    # 4. export: state_dict() in the LoongX layout and save_lora() round-trip bit-exactly through a second model
+    sd_out = m.state_dict()
+    assert any(k.endswith("attn.to_q.base_layer.weight") for k in sd_out) and "transformer.proj_out.weight" in sd_out
+    m2 = OminiModel(str(tmp_path / "flux"), lora_config={"r": 4, "lora_alpha": 4}, device=dev)
+    m2.load_state_dict(sd_out)
+    assert torch.equal(_forward(m2, inp, B), _forward(m, inp, B))
+    m.save_lora(str(tmp_path / "exported"))
+    m3 = OminiModel(str(tmp_path / "flux"), lora_config={"r": 4, "lora_alpha": 4}, device=dev)
+    m3.load_lora(str(tmp_path / "exported"))
+    assert torch.equal(_forward(m3, inp, B), _forward(m, inp, B))
     print(f"\n[checkpoint] relL2 vs oracle: directory {e0:.4g}, +LoRA file {e1:.4g}, LoongX state dict {e2:.4g}; LoRA effect {d01:.4g}")
     assert max(e0, e1, e2) < 2e-2 and d01 > 5 * max(e0, e1)
