@@ -292,3 +292,46 @@ def test_dit_forward_ragged_stream_lengths(nt, hw):
     e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
     print(f"\n[ragged nt={nt} ni={ni}] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
     assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (e_nat, e_bf)
+
+
+def test_dit_full_flux_size_parity():
+    """The WHOLE FLUX.1-dev-sized DiT (19 double + 38 single blocks, 24 heads, D = 3072; 11.9 B synthetic parameters) at
+    BASELINE.json's configs[1] geometry (512x512 + image condition, S = 512 + 1024 + 1024, B = 1): one native forward vs
+    the fp32 oracle evaluated on the GPU with the same bf16-rounded weights.  Same stated tolerance as the small cases:
+    relL2 <= 1.5 x (torch bf16 eager vs fp32) + 2e-3, and <= 2e-2 absolute."""
+    import gc
+
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights, random_params
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs ~130 GB of free HBM (fp32 oracle weights + native panels)")
+    dev = "cuda"
+    ocfg, cfg = O.FluxConfig(), FluxConfig()
+    Pb = random_params(cfg, dev, seed=77, w_std=0.02, bias_std=0.02, lora_b_std=0.02)  # bf16, diffusers names
+    W = DitWeights(Pb, cfg, dev, consume=False)
+    side, nt = 32, 512
+    ni = side * side
+    g = torch.Generator().manual_seed(3)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(dev)  # noqa: E731
+    inp = dict(lat=r(1, ni, 64), cond=r(1, ni, 64), pe=r(1, nt, 4096, scale=0.1), pooled=r(1, 768), img_ids=_ids(side, side).to(dev),
+               cond_ids=_ids(side, side, -side).to(dev), txt_ids=torch.zeros(nt, 3).to(dev), guidance=3.5)
+    plan = DitPlan(W, 1, nt, ni, ni, T=1)
+    plan.set_ids(inp["txt_ids"], inp["img_ids"], inp["cond_ids"])
+    t = 0.6
+    plan.prepare(inp["pe"], inp["pooled"], inp["cond"], [t], [3.5], c_t=0.0)
+    got = plan.step(0, inp["lat"]).clone()
+    torch.cuda.synchronize()
+    del plan, W
+    gc.collect()
+    torch.cuda.empty_cache()
+    with torch.no_grad():
+        ref16 = _oracle_full(O, ocfg, Pb, inp, t, torch.bfloat16).float()
+        P32 = {k: Pb.pop(k).float() for k in list(Pb)}  # convert in place: never hold both copies
+        ref32 = _oracle_full(O, ocfg, P32, inp, t, torch.float32)
+    e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
+    print(f"\n[full FLUX-size DiT, 57 blocks, S=2560] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
+    assert torch.isfinite(got.float()).all()
+    assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (e_nat, e_bf)
