@@ -28,7 +28,8 @@ struct TileCfg {
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = NCTA == 2 ? (BN == 256 ? 6 : 7) : (BN == 256 ? 4 : 5);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = BN * 4 + BN * 2;  // bias fp32 + gate bf16 of one tile's columns
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * EPI_STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -73,7 +74,7 @@ __device__ __forceinline__ void chunk_bias(const uint32_t (&r)[32], const float*
     const float4* b4 = reinterpret_cast<const float4*>(bias + n);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
+      float4 b = b4[j];
       x[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
       x[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
       x[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
@@ -100,6 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES + 256;  // [2][bias fp32 BN | gate bf16 BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -253,7 +255,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const lx_gemm_segment_t& seg = d.seg[si];
       const int seg_n0 = si ? d.n_split : 0;
       const int mode = seg.mode;
-      const float* bias = d.group[group_of(p, tm)].bias;
+      const float* bias_g = d.group[group_of(p, tm)].bias;
+      // Stage the tile's bias (and gate) columns in shared memory before waiting for the accumulator: in the chunk loop
+      // they are broadcast shared-memory reads instead of one exposed L2 round trip per 32 columns.  Double-buffered by
+      // accumulator stage; the named barrier also keeps a fast warp from overwriting a buffer a slow warp still reads.
+      float* s_bias = reinterpret_cast<float*>(epi_stage + acc * TileCfg<BN, NCTA>::EPI_STAGE_BYTES);
+      __nv_bfloat16* s_gate = reinterpret_cast<__nv_bfloat16*>(s_bias + BN);
+      {
+        const int et = threadIdx.x - 64;  // 0..127 over the four epilogue warps
+        if (bias_g != nullptr)
+          for (int c = et; c < BN; c += 128) s_bias[c] = (n0 + c < d.N) ? __ldg(bias_g + n0 + c) : 0.f;
+        if (mode == LX_EPI_GATE_RESIDUAL && m0 < d.M) {  // (the odd CTA of the last pair may own no rows at all)
+          const lx_tile_meta_t mg = d.tile_meta[tm];
+          const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(d.gate[mg.stream]) +
+                                    (size_t)mg.batch * d.gate_stride[mg.stream];
+          for (int c = et; c < BN; c += 128) s_gate[c] = (n0 + c < d.N) ? gp[n0 + c] : __float2bfloat16(0.f);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const float* bias = bias_g != nullptr ? s_bias : nullptr;
+
+      // Gate-residual tiles: the residual row segment is fetched BEFORE waiting for the accumulator, so the (L2-latency,
+      // one 16-byte fragment per row) loads complete while the tensor pipe is still working on this tile; in the
+      // chunk loop below they would be one exposed round trip per 32 columns on the last tile of every CTA.
+      uint4 rres[BN / 8];
+      if (mode == LX_EPI_GATE_RESIDUAL && row_ok) {
+        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual) + (size_t)row * d.ldr +
+                                   (n0 - seg_n0 + seg.col_offset);
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j)
+          if (n0 + j * 8 < d.N) rres[j] = *reinterpret_cast<const uint4*>(res + j * 8);
+      }
+      if (BN == 256 && mode == LX_EPI_QKV && d.rope != nullptr && row_ok && n0 < 2 * d.heads * 128) {
+        // same idea for the q / k tiles: this row's 64 (cos, sin) pairs (shared by both heads of the tile) are in
+        // registers before the accumulator is ready
+        const lx_tile_meta_t meta_pf = d.tile_meta[tm];
+        const float4* rope_pf =
+            reinterpret_cast<const float4*>(d.rope + (size_t)(meta_pf.seq_row % d.seq_total + row_in_tile) * 128);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 t = __ldg(rope_pf + j);
+          rres[j % (BN / 8)] = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+        }
+      }
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -282,18 +326,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t r[32];
               float x[32];
               tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
-                  chunk_bias(r, bias, nh + c * 32, x);
+                  chunk_bias(r, bias, half * 128 + c * 32, x);
 #pragma unroll
               for (int j = 0; j < 32; ++j) ss += x[j] * x[j];
             }
             inv = rsqrtf(ss * (1.0f / 128.0f) + d.rms_eps);
           }
-#pragma unroll 1
+#pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             float x[32];
             tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
-              chunk_bias(r, bias, nh + c * 32, x);
+              chunk_bias(r, bias, half * 128 + c * 32, x);
             if (rmsw != nullptr) {
               const float4* w4 = reinterpret_cast<const float4*>(rmsw + c * 32);
 #pragma unroll
@@ -308,7 +352,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (rope_row != nullptr && row_ok) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                float4 cs = __ldg(rope_row + c * 8 + j);  // (cos0, sin0, cos1, sin1) for two rotary pairs
+                const uint4 cu = rres[(c * 8 + j) % (BN / 8)];  // prefetched (cos0, sin0, cos1, sin1) for two rotary pairs
+                const float4 cs = make_float4(__uint_as_float(cu.x), __uint_as_float(cu.y), __uint_as_float(cu.z),
+                                              __uint_as_float(cu.w));
                 float a0 = x[4 * j + 0], b0 = x[4 * j + 1], a1 = x[4 * j + 2], b1 = x[4 * j + 3];
                 x[4 * j + 0] = a0 * cs.x - b0 * cs.y;
                 x[4 * j + 1] = b0 * cs.x + a0 * cs.y;
@@ -323,37 +369,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else if (mode == LX_EPI_GATE_RESIDUAL) {
-        const lx_tile_meta_t meta = d.tile_meta[tm];
-        const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(d.gate[meta.stream]) +
-                                    (size_t)meta.batch * d.gate_stride[meta.stream];
-        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual) + (size_t)row * d.ldr;
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           const int n = n0 + c * 32;
-          if (n >= d.N) break;
-          uint32_t r[32];
-          float x[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          chunk_bias(r, bias, n, x);
-          const int oc = n - seg_n0 + seg.col_offset;
+          if (n < d.N) {
+            uint32_t r[32];
+            float x[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            chunk_bias(r, bias, c * 32, x);
+            const int oc = n - seg_n0 + seg.col_offset;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j * 8 < d.N) {
-              uint4 g = __ldg(reinterpret_cast<const uint4*>(gate + n + j * 8));
-              uint32_t gu[4] = {g.x, g.y, g.z, g.w};
-              if (row_ok) {
-                uint4 rr = *reinterpret_cast<const uint4*>(res + oc + j * 8);
-                uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
-                float o[8];
+            for (int j = 0; j < 4; ++j) {
+              if (n + j * 8 < d.N) {
+                const uint4 g = *reinterpret_cast<const uint4*>(s_gate + c * 32 + j * 8);
+                uint32_t gu[4] = {g.x, g.y, g.z, g.w};
+                if (row_ok) {
+                  const uint4 rr = rres[c * 4 + j];
+                  uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
+                  float o[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 gg = unpack_bf16(gu[e]);
-                  float2 r2 = unpack_bf16(ru[e]);
-                  o[2 * e + 0] = r2.x + gg.x * x[8 * j + 2 * e + 0];
-                  o[2 * e + 1] = r2.y + gg.y * x[8 * j + 2 * e + 1];
+                  for (int e = 0; e < 4; ++e) {
+                    float2 gg = unpack_bf16(gu[e]);
+                    float2 r2 = unpack_bf16(ru[e]);
+                    o[2 * e + 0] = r2.x + gg.x * x[8 * j + 2 * e + 0];
+                    o[2 * e + 1] = r2.y + gg.y * x[8 * j + 2 * e + 1];
+                  }
+                  store_bf16x8(out + oc + j * 8, o);
                 }
-                store_bf16x8(out + oc + j * 8, o);
               }
             }
           }
@@ -367,7 +410,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           float x[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
-          chunk_bias(r, bias, n, x);
+          chunk_bias(r, bias, c * 32, x);
           if (mode == LX_EPI_BIAS_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
