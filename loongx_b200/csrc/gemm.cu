@@ -140,8 +140,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: everything above overlapped the previous kernel's tail; its outputs (our A operand / residual) are read below
-  pdl_wait();
+  // PDL: everything above overlapped the previous kernel's tail; its outputs (our A operand / residual) are read below.
+  // The TMA producer thread defers its wait: the W tiles of the first pipeline stages do not depend on the previous
+  // kernel, so it requests them first (see the producer loop).
+  const bool defer_pdl = (warp == 0);
+  if (!defer_pdl) pdl_wait();
   pdl_launch_dependents();
 
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -151,6 +154,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {  // elect.sync: the compiler keeps descriptors in uniform registers (no per-MMA waterfall loop)
       int stage = 0;
       uint32_t phase = 0;
+      bool first_tile = true;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int tmi, tni;
         tile_coords(p, tile, tmi, tni);
@@ -160,19 +164,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int g = group_of(p, tm);
         const CUtensorMap* tmB = g == 0 ? &tmB0 : (g == 1 ? &tmB1 : &tmB2);
         const int nkb = p.num_kb[g];
+        // first tile: the W halves of the first min(STAGES, nkb) stages are requested BEFORE the PDL wait (weights do
+        // not depend on the previous kernel), the A halves right after it
+        const int n_early = first_tile ? min(STAGES, nkb) : 0;
+        if (first_tile) {
+          for (int kb = 0; kb < n_early; ++kb) {  // stage == kb here, every slot is free
+            uint8_t* sa = smem + kb * STAGE_BYTES;
+            if (NCTA == 2) {
+              if (rank == 0) mbar_expect_tx(&full[kb], 2 * STAGE_BYTES);
+              tma_load_2d_2sm(sa + A_BYTES, tmB, mapa_shared(smem_u32(&full[kb]), 0), kb * BK, n0);
+            } else {
+              mbar_expect_tx(&full[kb], STAGE_BYTES);
+              tma_load_2d(sa + A_BYTES, tmB, &full[kb], kb * BK, n0);
+            }
+          }
+          pdl_wait();
+          first_tile = false;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
+          const bool early = kb < n_early;  // W already requested and the expected bytes already posted
           if (NCTA == 2) {
             // both CTAs' bytes are counted on the LEADER's full barrier (the leader issues the pair's MMAs)
-            if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+            if (rank == 0 && !early) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
             const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
             tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
-            tma_load_2d_2sm(sa + A_BYTES, tmB, bar, kb * BK, n0);
+            if (!early) tma_load_2d_2sm(sa + A_BYTES, tmB, bar, kb * BK, n0);
           } else {
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            if (!early) mbar_expect_tx(&full[stage], STAGE_BYTES);
             tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-            tma_load_2d(sa + A_BYTES, tmB, &full[stage], kb * BK, n0);
+            if (!early) tma_load_2d(sa + A_BYTES, tmB, &full[stage], kb * BK, n0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -182,6 +204,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
+    pdl_wait();  // lanes that did not run the loop (and a CTA without tiles) still order themselves after the predecessor
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (rank == 0 && elect_one()) {
@@ -286,10 +309,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < BN / 8; ++j)
           if (n0 + j * 8 < d.N) rres[j] = *reinterpret_cast<const uint4*>(res + j * 8);
       }
+      lx_tile_meta_t meta_pf = {0, 0, 0, 0};
+      if (BN == 256 && mode == LX_EPI_QKV && m0 < d.M) meta_pf = d.tile_meta[tm];  // also fetched ahead of the wait
       if (BN == 256 && mode == LX_EPI_QKV && d.rope != nullptr && row_ok && n0 < 2 * d.heads * 128) {
         // same idea for the q / k tiles: this row's 64 (cos, sin) pairs (shared by both heads of the tile) are in
         // registers before the accumulator is ready
-        const lx_tile_meta_t meta_pf = d.tile_meta[tm];
         const float4* rope_pf =
             reinterpret_cast<const float4*>(d.rope + (size_t)(meta_pf.seq_row % d.seq_total + row_in_tile) * 128);
 #pragma unroll
@@ -304,7 +328,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
 
       if (BN == 256 && mode == LX_EPI_QKV) {
-        const lx_tile_meta_t meta = d.tile_meta[tm];
+        const lx_tile_meta_t meta = meta_pf;
         const int D = d.heads * 128;
         const int sec = n0 / D;  // 0 = q, 1 = k, 2 = v
         const int s_pos = meta.seq_row % d.seq_total + row_in_tile;
