@@ -295,6 +295,9 @@ def run_native(args, rank, local_rank, world):
     kernels = {names[i]: {"ms_per_edit": ms[i], "launches": int(cnt[i]), "share": ms[i] / tot_ms} for i in range(4)}
     kernels["attention_kernel"].update({"achieved_tflops": att_tf, "frac_of_peak": att_tf / peaks["tflops"]})
     kernels["dit_row_kernels"].update({"achieved_gbs": row_gbs, "frac_of_hbm_peak": row_gbs / peaks["hbm"]})
+    cs3_gbs = work[3] / ms[3] / 1e6 if ms[3] else 0.0  # algorithmic bytes of the CS3 / DGF kernels
+    kernels["cs3_dgf_kernels"].update({"achieved_gbs": cs3_gbs, "frac_of_hbm_peak": cs3_gbs / peaks["hbm"],
+                                       "note": "once per edit, ~30 small launches: latency-bound, 0.15 % of the edit"})
     n_img = (RES // 16) ** 2
     algo_tflops = B * DENOISE_STEPS * flops_per_forward(N_TXT, n_img, n_img) / (secs / args.steps) / 1e12
 

@@ -28,7 +28,7 @@ int lx_device_info(int32_t* out3);
 /* Launch accounting (bench.py's gpu_launches / roofline): kernel classes 0 = tcgen05 GEMM, 1 = attention, 2 = DiT row
  * kernels, 3 = CS3/DGF kernels; cls < 0 = all.  lx_profile_begin() switches on CUDA-event timing of every launch (on
  * the stream it is launched on); lx_profile_end() synchronises and returns per-class totals in arrays of 4:
- * milliseconds, launches, algorithmic work (FLOPs for classes 0-1, bytes for class 2, 0 for class 3). */
+ * milliseconds, launches, algorithmic work (FLOPs for classes 0-1, bytes for classes 2-3). */
 int64_t lx_launch_count(int32_t cls);
 void lx_launch_count_reset(void);
 int lx_profile_begin(void);

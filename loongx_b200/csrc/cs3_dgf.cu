@@ -521,7 +521,7 @@ using namespace lx;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 extern "C" int lx_pad_truncate(const float* in, float* out, int32_t rows, int32_t Lin, int32_t Lout, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 4.0 * rows * ((Lin < Lout ? Lin : Lout) + (double)Lout));  // algorithmic bytes
   LX_CHECK_ARG(in && out && rows > 0 && Lin > 0 && Lout > 0, "lx_pad_truncate: bad arguments");
   const int64_t n = (int64_t)rows * Lout;
   pad_truncate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(in, out, rows, Lin, Lout);
@@ -532,7 +532,7 @@ extern "C" int lx_pad_truncate(const float* in, float* out, int32_t rows, int32_
 extern "C" int lx_s4_kernel_gen(const void* lam, const void* p, const void* q, const void* Bm, const void* Ct,
                                 const float* log_step, float* K, void* workspace, int32_t d, int32_t n, int32_t L,
                                 void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 16.0 * d * (double)L);  // algorithmic bytes
   LX_CHECK_ARG(lam && p && q && Bm && Ct && log_step && K && workspace, "lx_s4_kernel_gen: null pointer");
   LX_CHECK_ARG(d > 0 && n > 0 && L > 0 && L * 16 <= 200 * 1024, "lx_s4_kernel_gen: L=%d too large for the twiddle table", L);
   dim3 g1((L + 127) / 128, d);
@@ -552,7 +552,7 @@ extern "C" int lx_s4_kernel_gen(const void* lam, const void* p, const void* q, c
 
 extern "C" int lx_s4_conv_gelu(const float* u, const float* K, const float* D, float* y, int32_t B, int32_t d, int32_t L,
                                void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 8.0 * B * d * (double)L + 4.0 * d * (double)L);  // algorithmic bytes
   LX_CHECK_ARG(u && K && D && y && B > 0 && d > 0 && L > 0, "lx_s4_conv_gelu: bad arguments");
   dim3 grid((L + CONV_T - 1) / CONV_T, d, B);
   s4_conv_gelu_kernel<<<grid, CONV_T, 0, ST(stream)>>>(u, K, D, y, d, L);
@@ -563,7 +563,7 @@ extern "C" int lx_s4_conv_gelu(const float* u, const float* K, const float* D, f
 extern "C" int lx_channel_linear(const float* in, const float* W, const float* bias, const float* residual,
                                  const float* ln_w, const float* ln_b, float* out, int32_t B, int32_t d_in, int32_t d_out,
                                  int32_t L, float eps, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 4.0 * B * (double)L * (d_in + d_out) + 4.0 * d_in * (double)d_out);  // algorithmic bytes
   LX_CHECK_ARG(in && W && bias && out && B > 0 && L > 0, "lx_channel_linear: bad arguments");
   LX_CHECK_ARG(d_in > 0 && d_in <= CL_MAX && d_out > 0 && d_out <= CL_MAX, "lx_channel_linear: d_in/d_out must be <= %d",
                CL_MAX);
@@ -577,7 +577,7 @@ extern "C" int lx_channel_linear(const float* in, const float* W, const float* b
 
 extern "C" int lx_adaptive_pool(const float* in, float* out, int32_t B, int32_t C, int32_t L, int32_t O,
                                 int64_t out_bstride, int32_t cs, int32_t is, int32_t off, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 4.0 * B * C * ((double)L + O));  // algorithmic bytes
   LX_CHECK_ARG(in && out && B > 0 && C > 0 && L > 0 && O > 0, "lx_adaptive_pool: bad arguments");
   dim3 grid((O + 127) / 128, C, B);
   adaptive_pool_kernel<<<grid, 128, 0, ST(stream)>>>(in, out, C, L, O, out_bstride, cs, is, off);
@@ -587,7 +587,7 @@ extern "C" int lx_adaptive_pool(const float* in, float* out, int32_t B, int32_t 
 
 extern "C" int lx_gemv_f32(const float* W, const float* bias, const float* x, float* y, int32_t B, int32_t n_out,
                            int32_t n_in, int64_t ldx, int64_t ldy, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 4.0 * n_out * (double)n_in + 4.0 * B * ((double)n_in + n_out));  // algorithmic bytes
   LX_CHECK_ARG(W && x && y && n_out > 0 && n_in > 0, "lx_gemv_f32: bad arguments");
   LX_CHECK_ARG(B > 0 && B <= GEMV_MAXB, "lx_gemv_f32: batch %d outside [1, %d]", B, GEMV_MAXB);
   LX_CHECK_ARG(n_in % 4 == 0 ? ldx % 4 == 0 : true, "lx_gemv_f32: ldx must be a multiple of 4");
@@ -598,7 +598,7 @@ extern "C" int lx_gemv_f32(const float* W, const float* bias, const float* x, fl
 
 extern "C" int lx_ln_relu_rows(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t n, float eps,
                                void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 8.0 * rows * (double)n);  // algorithmic bytes
   LX_CHECK_ARG(x && w && b && y && rows > 0 && n > 0, "lx_ln_relu_rows: bad arguments");
   ln_relu_kernel<<<rows, 256, 0, ST(stream)>>>(x, w, b, y, n, eps);
   LX_CUDA(cudaGetLastError());
@@ -607,7 +607,7 @@ extern "C" int lx_ln_relu_rows(const float* x, const float* w, const float* b, f
 
 extern "C" int lx_token_linear(const float* h, const float* W, const float* bias, float* out, int32_t B, int32_t tokens,
                                int32_t n_out, int64_t out_bstride, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 4.0 * B * tokens * (8.0 + n_out));  // algorithmic bytes
   LX_CHECK_ARG(h && W && bias && out && B > 0 && tokens > 0 && n_out > 0, "lx_token_linear: bad arguments");
   dim3 grid((n_out + 255) / 256, tokens, B);
   token_linear_kernel<<<grid, 256, 0, ST(stream)>>>(h, W, bias, out, tokens, n_out, out_bstride);
@@ -616,7 +616,7 @@ extern "C" int lx_token_linear(const float* h, const float* W, const float* bias
 }
 
 extern "C" int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, desc ? 4.0 * ((double)desc->M * desc->K + desc->batch * ((double)desc->K * desc->N + (double)desc->M * desc->N)) : 0.0);
   LX_CHECK_ARG(desc != nullptr, "lx_sgemm_f32: null descriptor");
   const lx_sgemm_desc_t& d = *desc;
   LX_CHECK_ARG(d.A && d.Bm && (d.C || d.rowmean) && d.M > 0 && d.N > 0 && d.K > 0 && d.batch > 0,
@@ -630,7 +630,7 @@ extern "C" int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream) {
 }
 
 extern "C" int lx_cast(const void* in, void* out, int64_t n, int32_t to_bf16, void* stream) {
-  LaunchScope scope(KC_CS3DGF, stream, 0.0);
+  LaunchScope scope(KC_CS3DGF, stream, 6.0 * n);  // algorithmic bytes
   LX_CHECK_ARG(in && out && n > 0, "lx_cast: bad arguments");
   if (to_bf16)
     cast_f32_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, ST(stream)>>>((const float*)in, (__nv_bfloat16*)out, n);
