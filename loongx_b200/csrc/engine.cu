@@ -93,10 +93,9 @@ int check_plan(const lx_dit_model_t* m, const lx_dit_plan_t* p) {
                    (p->n_cond > 0 || p->pad[2] == 0),
                "dit: stream padding must be in [0, 128)");
   LX_CHECK_ARG(m->in_channels % 8 == 0, "dit: in_channels=%d must be a multiple of 8", m->in_channels);
-  if (p->add_cond_attn) {
-    set_error("dit: model_config.add_cond_attn=True (block.py:233-234) is not implemented");
-    return LX_ERR_UNSUPPORTED;
-  }
+  LX_CHECK_ARG(!p->add_cond_attn || p->n_cond == 0 || p->n_cond == p->n_img,
+               "dit: add_cond_attn (block.py:233-234) adds the condition's attention output to the image stream, so "
+               "n_cond (%d) must equal n_img (%d)", p->n_cond, p->n_img);
   LX_CHECK_ARG(p->tile_meta && p->out_row_base && p->X && p->XN && p->Q && p->K && p->V && p->scratch,
                "dit: missing work buffer");
   return LX_OK;
@@ -165,6 +164,21 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
     lx_gemm_desc_t d = gemm_zero(p.scratch, D, g.R, D);
     double_groups(d, g, W.out_ctx, W.out, ll);
     gate_res(d, 2);
+    LX_TRY(lx_gemm_bf16(&d, stream));
+  }
+  // 4b. model_config.add_cond_attn (block.py:233-234): hidden_states += cond_gate_msa * cond_attn_output.  The gated
+  //     condition projection is recomputed as one more gate-residual GEMM whose A rows are the condition rows of the
+  //     attention output and whose residual / output rows are the IMAGE rows of X (same tile order: n_cond == n_img).
+  if (p.add_cond_attn && has_cond) {
+    const int64_t c0 = (int64_t)g.Rt + g.Ri;
+    lx_gemm_desc_t d = gemm_zero(off(p.scratch, c0 * D), D, g.Rc, D);
+    set_group(d, 0, lora_w(W.out), W.out, 0);
+    d.seg[0].mode = LX_EPI_GATE_RESIDUAL;
+    d.seg[0].out = off(p.X, (int64_t)g.Rt * D); d.seg[0].ldo = D;
+    d.residual = off(p.X, (int64_t)g.Rt * D); d.ldr = D;
+    d.tile_meta = p.tile_meta + c0 / 128;  // condition tiles: gate = cond_gate_msa of the right batch element
+    fill3(d.gate, 2);
+    for (int s = 0; s < 3; ++s) d.gate_stride[s] = ldm;
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
   // 5. norm2 + FiLM (shift_mlp / scale_mlp)

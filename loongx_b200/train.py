@@ -304,6 +304,8 @@ class DitTrainer:
         assert attn_bwd in ("native", "library")
         self.attn_bwd = attn_bwd
         self.latent_lora = bool(model_config.get("latent_lora", False))
+        if model_config.get("add_cond_attn", False):
+            raise NotImplementedError("training with model_config.add_cond_attn=True (inference supports it)")
         if n_cond <= 0:
             raise NotImplementedError("the training step needs a condition stream (the LoRA lives on the condition branch)")
         self.w, self.cfg = weights, weights.cfg

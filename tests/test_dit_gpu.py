@@ -115,7 +115,7 @@ def test_dit_stagewise_vs_oracle():
             assert r < 2e-2, (f"single block {i} {name}", r)
 
 
-@pytest.mark.parametrize("variant", ["default", "no_cond", "no_union", "independent", "c_factor", "latent_lora"])
+@pytest.mark.parametrize("variant", ["default", "no_cond", "no_union", "independent", "c_factor", "latent_lora", "add_cond_attn"])
 def test_dit_forward_vs_oracle(variant):
     mc, cf, nc = {}, None, 128
     if variant == "no_cond":
@@ -128,6 +128,8 @@ def test_dit_forward_vs_oracle(variant):
         cf = 1.6
     elif variant == "latent_lora":
         mc = {"latent_lora": True}
+    elif variant == "add_cond_attn":
+        mc = {"add_cond_attn": True}
     O, ocfg, Pb, P32, inp, W, plan = _setup(model_config=mc, c_factor=cf, n_cond=nc)
     for step, t in enumerate(inp["ts"]):
         ref32 = _oracle_full(O, ocfg, P32, inp, t, torch.float32, mc, cf)
