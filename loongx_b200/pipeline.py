@@ -110,6 +110,26 @@ class NativeFluxTransformer:
             raise KeyError(f"LoRA factors for modules that are not LoRA targets here: {sorted(unknown)[:4]}")
         return len(seen)
 
+    def set_lora_scale(self, scale: float) -> None:
+        """`joint_attention_kwargs["scale"]` (transformer.py:73-83: peft `scale_lora_layers(self, lora_scale)` around the
+        forward): re-merge every LoRA-carrying panel as W + scale * (alpha / r) B A with the native merge kernel.  A no-op
+        while the scale does not change; the reference's un-scaling at the end of the forward (transformer.py:246-248)
+        corresponds to calling this with 1.0 again."""
+        from .dit import PackedLinear
+        from .train import lora_merge, transpose
+
+        scale = float(scale)
+        if scale == getattr(self, "_lora_scale", 1.0):
+            return
+        for panel in self.weights.named.values():
+            if not isinstance(panel, PackedLinear):
+                continue
+            for (_, row0, rows, A, Bw) in panel.lora:
+                lora_merge(panel.w[row0:row0 + rows], A, Bw, panel.w_lora[row0:row0 + rows], panel.scaling * scale)
+                if panel.w_loraT is not None:
+                    transpose(panel.w_lora[row0:row0 + rows], panel.w_loraT[:, row0:row0 + rows])
+        self._lora_scale = scale
+
     # -- nn.Module-like surface --------------------------------------------------------------------------------
     def named_modules(self):
         yield "", self

@@ -96,6 +96,7 @@ def generate(model, pipeline, conditions: List[Condition] = None, config_path: s
         batch_size = prompt_embeds.shape[0]
     device = self._execution_device
     lora_scale = self.joint_attention_kwargs.get("scale", None) if self.joint_attention_kwargs is not None else None
+    self.transformer.set_lora_scale(1.0 if lora_scale is None else lora_scale)  # what scale_lora_layers does per forward
     prompt_embeds, pooled_prompt_embeds, text_ids = self.encode_prompt(
         prompt=prompt, prompt_2=prompt_2, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds,
         device=device, num_images_per_prompt=num_images_per_prompt, max_sequence_length=max_sequence_length,

@@ -27,8 +27,8 @@ def tranformer_forward(transformer, condition_latents, condition_ids, condition_
      joint_attention_kwargs, controlnet_block_samples, controlnet_single_block_samples, return_dict) = prepare_params(**params)
     if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
         raise NotImplementedError("controlnet residuals (transformer.py:172-181, 230-239) are not part of the LoongX path")
-    if joint_attention_kwargs is not None and joint_attention_kwargs.get("scale", 1.0) != 1.0:
-        raise NotImplementedError("joint_attention_kwargs['scale'] != 1: LoRA is merged at load with scale 1")
+    # transformer.py:73-83, 246-248: the LoRA layers are scaled by joint_attention_kwargs["scale"] for this forward
+    transformer.set_lora_scale(joint_attention_kwargs.get("scale", 1.0) if joint_attention_kwargs is not None else 1.0)
     if transformer.training and transformer.gradient_checkpointing:
         raise NotImplementedError("tranformer_forward is the inference forward; the differentiable training path is "
                                   "OminiModel.step (loongx_b200/train.py), which checkpoints / recomputes per block")

@@ -167,3 +167,47 @@ def test_tranformer_forward_shim_and_ids_bit_exact():
     packed, _ = pipe.prepare_latents(2, 16, H_PX, W_PX, torch.bfloat16, "cuda", gen, None)
     gen2 = torch.Generator(device="cuda").manual_seed(42)
     assert torch.equal(packed, OS.pack_latents(torch.randn((2, 16, 32, 16), generator=gen2, device="cuda", dtype=torch.bfloat16)))
+
+
+def test_joint_attention_kwargs_lora_scale():
+    """joint_attention_kwargs={"scale": s} (transformer.py:73-83): LoRA contribution scaled by s through a native re-merge
+    of the panels; s = 0 must equal a model without LoRA on any branch, and the scale is restored by the next call."""
+    from oracle import flux_dit as O
+    from oracle import sampler as OS
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.pipeline import NativeFluxTransformer
+    from src.flux.transformer import tranformer_forward
+
+    dev = "cuda"
+    kw = dict(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=3, w_std=0.05, bias_std=0.05, lora_b_std=0.05)
+    Pb = {k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}
+    tr = NativeFluxTransformer(cfg, params=dict(Pb), device=dev)
+    g = torch.Generator().manual_seed(1)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(dev)  # noqa: E731
+    img_ids = OS.prepare_latent_image_ids(16, 32).to(dev)
+    cond_ids = OS.condition_ids(img_ids, [0, -16])
+    kwargs = dict(hidden_states=r(1, 128, 64), encoder_hidden_states=r(1, 128, 256, scale=0.5), pooled_projections=r(1, 64),
+                  timestep=torch.tensor([0.5], device=dev), img_ids=img_ids, txt_ids=torch.zeros(128, 3, device=dev),
+                  guidance=torch.tensor([3.5], device=dev), return_dict=False)
+    cond = r(1, 128, 64)
+
+    def oracle(scale):
+        P32 = {k: v.float() for k, v in Pb.items()}
+        oc = O.FluxConfig(**kw, lora_alpha=4.0 * scale)
+        with torch.no_grad():
+            return O.tranformer_forward(P32, oc, cond.float(), cond_ids, None, {}, 0, hidden_states=kwargs["hidden_states"].float(),
+                                        encoder_hidden_states=kwargs["encoder_hidden_states"].float(),
+                                        pooled_projections=kwargs["pooled_projections"].float(), timestep=kwargs["timestep"],
+                                        img_ids=img_ids, txt_ids=kwargs["txt_ids"], guidance=kwargs["guidance"])
+
+    out1 = tranformer_forward(tr, cond, cond_ids, None, {}, 0, **kwargs)[0]
+    out_half = tranformer_forward(tr, cond, cond_ids, None, {}, 0, joint_attention_kwargs={"scale": 0.5}, **kwargs)[0]
+    out0 = tranformer_forward(tr, cond, cond_ids, None, {}, 0, joint_attention_kwargs={"scale": 0.0}, **kwargs)[0]
+    out1b = tranformer_forward(tr, cond, cond_ids, None, {}, 0, **kwargs)[0]
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()  # noqa: E731
+    e = (rel(out1, oracle(1.0)), rel(out_half, oracle(0.5)), rel(out0, oracle(0.0)))
+    print(f"\n[lora scale] relL2 vs oracle at scale 1 / 0.5 / 0: {e[0]:.4g} {e[1]:.4g} {e[2]:.4g}; effect {rel(out0, out1):.4g}")
+    assert max(e) < 1.5e-2 and rel(out0, out1) > 3 * max(e)
+    assert torch.equal(out1, out1b)
