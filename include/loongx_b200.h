@@ -132,6 +132,8 @@ typedef struct lx_attn_desc {
    * masked out; padding query rows produce don't-care output rows.  All zeros = no padding. */
   int32_t stream_end[3];
   int32_t pad[3];
+  int32_t q_tiles;  /* number of leading 128-row query tiles to compute (0 = all S/128); keys always span the whole S */
+  int32_t reserved;
 } lx_attn_desc_t;
 
 int lx_attention(const lx_attn_desc_t* desc, void* stream);
@@ -255,7 +257,13 @@ typedef struct lx_dit_plan {
   float* g_dev;          /* fp32 [T*B + B] device scratch for guidance values */
   int32_t pad[3];        /* padding tokens at the end of the txt / img / cond stream (n_* above are the PADDED lengths,
                             multiples of 128; the reference accepts any H, W divisible by 16) */
-  int32_t reserved3;
+  /* Step-invariant condition branch: under model_config.independent_condition the condition queries see
+   * only condition keys and the condition stream is modulated by cond_temb (c_t, constant), so its K / V of every block do
+   * not depend on the denoise step.  With cond_cached != 0 the block calls process the text + image rows only and read
+   * the condition keys / values that a full pass (cond_cached = 0, same kv_block_stride) left in each block's own K / V
+   * buffer: block b uses K + b*kv_block_stride (double blocks first, then single blocks). */
+  int32_t cond_cached;
+  int64_t kv_block_stride; /* elements between consecutive blocks' K (and V) buffers; 0 = one shared buffer */
 } lx_dit_plan_t;
 
 /* Step-invariant work, once per edit (generate.py:168-306 hoisted): context_embedder, x_embedder(cond), temb for all

@@ -70,6 +70,7 @@ class AttnDesc(C.Structure):
         ("cross_bias", c_float), ("scale", c_float),
         ("lse", c_void_p),
         ("stream_end", c_int32 * 3), ("pad", c_int32 * 3),
+        ("q_tiles", c_int32), ("reserved", c_int32),
     ]
 
 

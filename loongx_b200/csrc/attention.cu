@@ -419,7 +419,10 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     LX_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  dim3 grid(n_tiles / p.groups, d.H, d.B);
+  const int q_tiles = d.q_tiles > 0 ? d.q_tiles : n_tiles;
+  LX_CHECK_ARG(q_tiles <= n_tiles, "lx_attention: q_tiles=%d exceeds S/128=%d", q_tiles, n_tiles);
+  if (q_tiles % 2) p.groups = 1;
+  dim3 grid(q_tiles / p.groups, d.H, d.B);
   double pairs = (double)d.S * d.S;  // visible (query, key) pairs per head
   if (d.cross_bias == 0.f && d.n_cond > 0) {
     const double nc = d.n_cond, nr = d.S - d.n_cond;

@@ -24,6 +24,8 @@ using namespace lx;
 
 struct Geo {
   int B, nt, ni, nc, S, R, Rt, Ri, Rc, D, H, FF;
+  int Ract;     // rows the block kernels process: all of them, or text + image only when the condition branch is cached
+  bool cached;  // plan.cond_cached
 };
 
 Geo geo(const lx_dit_model_t& m, const lx_dit_plan_t& p) {
@@ -33,6 +35,8 @@ Geo geo(const lx_dit_model_t& m, const lx_dit_plan_t& p) {
   g.Rt = g.B * g.nt; g.Ri = g.B * g.ni; g.Rc = g.B * g.nc;
   g.R = g.B * g.S;
   g.H = m.heads; g.D = m.heads * 128; g.FF = 4 * g.D;
+  g.cached = p.cond_cached != 0 && g.nc > 0;
+  g.Ract = g.cached ? g.Rt + g.Ri : g.R;
   return g;
 }
 
@@ -73,12 +77,12 @@ int gemm_simple(const lx_linear_t& L, const void* W, const void* A, int64_t lda,
 void double_groups(lx_gemm_desc_t& d, const Geo& g, const lx_linear_t& ctx, const lx_linear_t& L, bool latent_lora) {
   set_group(d, 0, ctx.w, ctx, 0);
   set_group(d, 1, latent_lora ? lora_w(L) : L.w, L, g.Rt);
-  if (g.nc > 0) set_group(d, 2, lora_w(L), L, g.Rt + g.Ri);
+  if (g.nc > 0 && !g.cached) set_group(d, 2, lora_w(L), L, g.Rt + g.Ri);
 }
 // Row groups of a single-block GEMM: [txt + img | cond].
 void single_groups(lx_gemm_desc_t& d, const Geo& g, const lx_linear_t& L, bool latent_lora) {
   set_group(d, 0, latent_lora ? lora_w(L) : L.w, L, 0);
-  if (g.nc > 0) set_group(d, 1, lora_w(L), L, g.Rt + g.Ri);
+  if (g.nc > 0 && !g.cached) set_group(d, 1, lora_w(L), L, g.Rt + g.Ri);
 }
 
 int check_plan(const lx_dit_model_t* m, const lx_dit_plan_t* p) {
@@ -96,14 +100,17 @@ int check_plan(const lx_dit_model_t* m, const lx_dit_plan_t* p) {
   LX_CHECK_ARG(!p->add_cond_attn || p->n_cond == 0 || p->n_cond == p->n_img,
                "dit: add_cond_attn (block.py:233-234) adds the condition's attention output to the image stream, so "
                "n_cond (%d) must equal n_img (%d)", p->n_cond, p->n_img);
+  LX_CHECK_ARG(!p->cond_cached || (p->mask_mode == 2 && p->cross_bias == 0.f && !p->add_cond_attn && p->kv_block_stride > 0),
+               "dit: cond_cached needs independent_condition masking, no c_factor / add_cond_attn and per-block K/V buffers");
   LX_CHECK_ARG(p->tile_meta && p->out_row_base && p->X && p->XN && p->Q && p->K && p->V && p->scratch,
                "dit: missing work buffer");
   return LX_OK;
 }
 
-void fill_attn(lx_attn_desc_t& a, const lx_dit_plan_t& p, const Geo& g, int64_t ldo) {
+void fill_attn(lx_attn_desc_t& a, const lx_dit_plan_t& p, const Geo& g, int64_t ldo, int kv_slot) {
   memset(&a, 0, sizeof(a));
-  a.q = p.Q; a.k = p.K; a.v = p.V; a.out = p.scratch; a.ldo = ldo; a.out_row_base = p.out_row_base;
+  a.q = p.Q; a.k = off(p.K, kv_slot * p.kv_block_stride); a.v = off(p.V, kv_slot * p.kv_block_stride); a.out = p.scratch;
+  a.q_tiles = g.cached ? (g.nt + g.ni) / 128 : 0; a.ldo = ldo; a.out_row_base = p.out_row_base;
   a.B = g.B; a.H = g.H; a.S = g.S; a.n_cond = g.nc; a.mask_mode = p.mask_mode; a.cross_bias = p.cross_bias;
   a.scale = 0.08838834764831845f;  // 1/sqrt(128)
   a.stream_end[0] = g.nt; a.stream_end[1] = g.nt + g.ni; a.stream_end[2] = g.S;
@@ -128,7 +135,7 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   auto lnmod = [&](int shift_chunk, int scale_chunk) -> int {
     lx_lnmod_desc_t d;
     memset(&d, 0, sizeof(d));
-    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.R; d.D = D;
+    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.Ract; d.D = D;
     d.tile_meta = p.tile_meta; d.eps = 1e-6f;
     fill3(d.shift, shift_chunk); fill3(d.scale, scale_chunk);
     for (int s = 0; s < 3; ++s) d.stride[s] = ldm;
@@ -145,10 +152,11 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   LX_TRY(lnmod(0, 1));
   // 2. q/k/v of all streams in one launch; epilogue: bias + RMSNorm(q,k) + RoPE + scatter to [B,H,S,128]
   {
-    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.R, 3 * D);
+    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.Ract, 3 * D);
     double_groups(d, g, W.qkv_ctx, W.qkv, ll);
     d.seg[0].mode = LX_EPI_QKV; d.tile_meta = p.tile_meta;
-    d.q = p.Q; d.k = p.K; d.v = p.V; d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
+    d.q = p.Q; d.k = off(p.K, blk * p.kv_block_stride); d.v = off(p.V, blk * p.kv_block_stride);
+    d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
     d.rms_q[0] = W.norm_added_q; d.rms_k[0] = W.norm_added_k;
     d.rms_q[1] = d.rms_q[2] = W.norm_q; d.rms_k[1] = d.rms_k[2] = W.norm_k;
     LX_TRY(lx_gemm_bf16(&d, stream));
@@ -156,12 +164,12 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   // 3. joint attention -> scratch viewed as [R, D]
   {
     lx_attn_desc_t a;
-    fill_attn(a, p, g, D);
+    fill_attn(a, p, g, D, blk);
     LX_TRY(lx_attention(&a, stream));
   }
   // 4. to_out / to_add_out with gate_msa * y + residual
   {
-    lx_gemm_desc_t d = gemm_zero(p.scratch, D, g.R, D);
+    lx_gemm_desc_t d = gemm_zero(p.scratch, D, g.Ract, D);
     double_groups(d, g, W.out_ctx, W.out, ll);
     gate_res(d, 2);
     LX_TRY(lx_gemm_bf16(&d, stream));
@@ -185,13 +193,13 @@ int double_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   LX_TRY(lnmod(3, 4));
   // 6. feed-forward up (+GELU-tanh) -> scratch viewed as [R, 4D]; down with gate_mlp * y + residual
   {
-    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.R, g.FF);
+    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.Ract, g.FF);
     double_groups(d, g, W.ff_ctx_up, W.ff_up, ll);
     d.seg[0].mode = LX_EPI_BIAS_GELU; d.seg[0].out = p.scratch; d.seg[0].ldo = g.FF;
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
   {
-    lx_gemm_desc_t d = gemm_zero(p.scratch, g.FF, g.R, D);
+    lx_gemm_desc_t d = gemm_zero(p.scratch, g.FF, g.Ract, D);
     double_groups(d, g, W.ff_ctx_down, W.ff_down, ll);
     gate_res(d, 5);
     LX_TRY(lx_gemm_bf16(&d, stream));
@@ -217,7 +225,7 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   {
     lx_lnmod_desc_t d;
     memset(&d, 0, sizeof(d));
-    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.R; d.D = D;
+    d.x = p.X; d.ldx = D; d.out = p.XN; d.ldo = D; d.rows = g.Ract; d.D = D;
     d.tile_meta = p.tile_meta; d.eps = 1e-6f;
     fill3(d.shift, 0); fill3(d.scale, 1);
     for (int s = 0; s < 3; ++s) d.stride[s] = ldm;
@@ -225,23 +233,25 @@ int single_block(const lx_dit_model_t& m, const lx_dit_plan_t& p, int step, int 
   }
   {
     // [q|k|v] -> QKV epilogue, proj_mlp -> GELU into the concat buffer columns [D, 5D)
-    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.R, 7 * D);
+    lx_gemm_desc_t d = gemm_zero(p.XN, D, g.Ract, 7 * D);
     single_groups(d, g, W.qkv_mlp, ll);
     d.n_split = 3 * D;
     d.seg[0].mode = LX_EPI_QKV;
     d.seg[1].mode = LX_EPI_BIAS_GELU; d.seg[1].out = p.scratch; d.seg[1].ldo = ldcat; d.seg[1].col_offset = D;
     d.tile_meta = p.tile_meta;
-    d.q = p.Q; d.k = p.K; d.v = p.V; d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
+    d.q = p.Q; d.k = off(p.K, (m.num_layers + blk) * p.kv_block_stride);
+    d.v = off(p.V, (m.num_layers + blk) * p.kv_block_stride);
+    d.heads = g.H; d.seq_total = g.S; d.rope = p.rope;
     for (int s = 0; s < 3; ++s) { d.rms_q[s] = W.norm_q; d.rms_k[s] = W.norm_k; }
     LX_TRY(lx_gemm_bf16(&d, stream));
   }
   {
     lx_attn_desc_t a;
-    fill_attn(a, p, g, ldcat);
+    fill_attn(a, p, g, ldcat, m.num_layers + blk);
     LX_TRY(lx_attention(&a, stream));
   }
   {
-    lx_gemm_desc_t d = gemm_zero(p.scratch, ldcat, g.R, D);
+    lx_gemm_desc_t d = gemm_zero(p.scratch, ldcat, g.Ract, D);
     single_groups(d, g, W.proj_out, ll);
     d.seg[0].mode = LX_EPI_GATE_RESIDUAL; d.seg[0].out = p.X; d.seg[0].ldo = D;
     d.residual = p.X; d.ldr = D; d.tile_meta = p.tile_meta;
@@ -266,7 +276,7 @@ int embed_inputs(const lx_dit_model_t& m, const lx_dit_plan_t& p, const void* la
   LX_TRY(gemm_simple(m.x_embedder, p.latent_lora ? lora_w(m.x_embedder) : m.x_embedder.w, latents, C, g.Ri, LX_EPI_BIAS,
                      off(p.X, (int64_t)g.Rt * D), D, 0, stream));
   LX_CUDA(cudaMemcpyAsync(p.X, p.X0_txt, (size_t)g.Rt * D * 2, cudaMemcpyDeviceToDevice, st));
-  if (g.nc > 0)
+  if (g.nc > 0 && !g.cached)
     LX_CUDA(cudaMemcpyAsync(off(p.X, (int64_t)(g.Rt + g.Ri) * D), p.X0_cond, (size_t)g.Rc * D * 2,
                             cudaMemcpyDeviceToDevice, st));
   return LX_OK;

@@ -60,7 +60,8 @@ class LxDitPlan(C.Structure):
                 ("emb_tmp", c_void_p), ("sin_tmp", c_void_p), ("silu_t", c_void_p), ("silu_c", c_void_p),
                 ("mod_img", c_void_p), ("mod_txt", c_void_p), ("mod_single", c_void_p), ("mod_out", c_void_p),
                 ("mod_cond_img", c_void_p), ("mod_cond_single", c_void_p),
-                ("t_dev", c_void_p), ("g_dev", c_void_p), ("pad", c_int32 * 3), ("reserved3", c_int32)]
+                ("t_dev", c_void_p), ("g_dev", c_void_p), ("pad", c_int32 * 3), ("cond_cached", c_int32),
+                ("kv_block_stride", c_int64)]
 
 
 _lib = L.lib
@@ -309,7 +310,10 @@ class DitPlan:
     (layout plumbing)."""
 
     def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, T: int = 1,
-                 model_config: Optional[dict] = None, c_factor: Optional[float] = None):
+                 model_config: Optional[dict] = None, c_factor: Optional[float] = None, cache_cond: bool = False):
+        """cache_cond=True: under model_config.independent_condition the condition stream does not depend
+        on the denoise step, so prepare() runs it once, keeps every block's condition keys / values, and step() processes
+        the text + image rows only (-40 % rows at 512x512).  Ignored when the configuration does not allow it."""
         cfg = weights.cfg
         dev = weights.device
         if n_txt <= 0 or n_img <= 0 or n_cond < 0:
@@ -325,13 +329,18 @@ class DitPlan:
         L_, Ls = cfg.num_layers, cfg.num_single_layers
         bf = dict(device=dev, dtype=torch.bfloat16)
         M = T * B + B
+        self.cache_cond = bool(cache_cond and n_cond > 0 and c_factor is None and
+                               mask_mode_from_config(model_config) == MASK_INDEPENDENT and
+                               not model_config.get("add_cond_attn", False))
+        kv_slots = (L_ + Ls) if self.cache_cond else 1  # one K / V buffer per block when the condition part is kept
         self.buf = dict(
             tile_meta=ops.make_tile_meta(B, n_txt, n_img, n_cond, dev),
             out_row_base=ops.make_out_row_base(B, n_txt, n_img, n_cond, dev),
             rope=torch.zeros((S, 64, 2), device=dev, dtype=torch.float32),
             X=torch.zeros((R, D), **bf),
             XN=torch.zeros((R, D), **bf),
-            Q=torch.zeros((B, H, S, 128), **bf), K=torch.zeros((B, H, S, 128), **bf), V=torch.zeros((B, H, S, 128), **bf),
+            Q=torch.zeros((B, H, S, 128), **bf), K=torch.zeros((kv_slots, B, H, S, 128), **bf)[0],
+            V=torch.zeros((kv_slots, B, H, S, 128), **bf)[0],  # views of slot 0; slot b = base + b*kv_block_stride
             scratch=torch.zeros((R, 5 * D), **bf),
             X0_txt=torch.zeros((B * n_txt, D), **bf),
             X0_cond=torch.zeros((max(B * n_cond, 1), D), **bf),
@@ -357,6 +366,8 @@ class DitPlan:
         for k, v in self.buf.items():
             setattr(p, k, v.data_ptr())
         p.pad[0], p.pad[1], p.pad[2] = self.ntp - self.nt, self.nip - self.ni, self.ncp - self.nc
+        p.cond_cached = 0
+        p.kv_block_stride = B * H * S * 128 if self.cache_cond else 0
         self.plan = p
         self.has_rope = False
         if self.padded:  # staging for the zero-padded latents / predictions of step()
@@ -414,6 +425,18 @@ class DitPlan:
                                     cl.data_ptr() if cl is not None else None, ts, gs, float(c_t), _stream()),
                 "lx_dit_prepare")
         self._prep_keepalive = (pe, po, cl)
+        if self.cache_cond:
+            # one full pass with every block writing its own K / V buffer: the condition rows of each buffer are now the
+            # block's step-invariant condition keys / values (the text / image rows are rewritten by every step)
+            self.plan.cond_cached = 0
+            dummy = torch.zeros((self.B, self.nip if self.padded else self.ni, w.cfg.in_channels), device=w.device,
+                                dtype=torch.bfloat16)
+            L.check(_lib.lx_dit_embed(C.byref(w.model), C.byref(self.plan), dummy.data_ptr(), _stream()), "lx_dit_embed")
+            for i in range(w.cfg.num_layers):
+                self.double_block(0, i)
+            for i in range(w.cfg.num_single_layers):
+                self.single_block(0, i)
+            self.plan.cond_cached = 1
 
     def step(self, step: int, latents: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         w = self.weights

@@ -157,15 +157,15 @@ class NativeFluxTransformer:
 
     # -- plans -------------------------------------------------------------------------------------------------
     def plan(self, B: int, n_txt: int, n_img: int, n_cond: int, T: int, model_config: Optional[dict],
-             c_factor: Optional[float]) -> DitPlan:
+             c_factor: Optional[float], cache_cond: bool = False) -> DitPlan:
         mc = model_config or {}
-        key = (B, n_txt, n_img, n_cond, T, bool(mc.get("latent_lora", False)), bool(mc.get("union_cond_attn", True)),
+        key = (cache_cond, B, n_txt, n_img, n_cond, T, bool(mc.get("latent_lora", False)), bool(mc.get("union_cond_attn", True)),
                bool(mc.get("independent_condition", False)), bool(mc.get("add_cond_attn", False)), c_factor)
         pl = self._plans.get(key)
         if pl is None:
             if len(self._plans) >= 4:  # bounded cache: plans own large activation buffers
                 self._plans.pop(next(iter(self._plans)))
-            pl = DitPlan(self.weights, B, n_txt, n_img, n_cond, T=T, model_config=mc, c_factor=c_factor)
+            pl = DitPlan(self.weights, B, n_txt, n_img, n_cond, T=T, model_config=mc, c_factor=c_factor, cache_cond=cache_cond)
             self._plans[key] = pl
         return pl
 

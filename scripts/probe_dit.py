@@ -21,7 +21,9 @@ torch.cuda.synchronize()
 print(f"weights: {W.param_bytes()/1e9:.2f} GB packed in {time.time()-t0:.1f}s, mem {torch.cuda.memory_allocated()/1e9:.1f} GB")
 n = (res // 16) ** 2
 nt, ni, nc = 512, n, n
-plan = DitPlan(W, B, nt, ni, nc, T=T)
+_mc = {"independent_condition": True} if os.environ.get("LX_INDEP") else {}
+plan = DitPlan(W, B, nt, ni, nc, T=T, model_config=_mc, cache_cond=bool(os.environ.get("LX_CACHE_COND")))
+print("model_config", _mc, "cache_cond", plan.cache_cond)
 h = res // 16
 def ids(dc=0):
     i = torch.zeros(h, h, 3); i[..., 1] += torch.arange(h)[:, None]; i[..., 2] += torch.arange(h)[None, :] + dc

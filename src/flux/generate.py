@@ -170,8 +170,9 @@ def generate(model, pipeline, conditions: List[Condition] = None, config_path: s
     B = latents.shape[0]
     T = len(timesteps)
     n_cond = condition_latents.shape[1] if use_condition else 0
+    # cache_cond: with model_config.independent_condition the condition branch is step-invariant and runs once per edit
     plan = self.transformer.plan(B, prompt_embeds.shape[1], latents.shape[1], n_cond, T, model_config,
-                                 self.transformer.c_factor())
+                                 self.transformer.c_factor(), cache_cond=True)
     plan.set_ids(text_ids, latent_image_ids, condition_ids if use_condition else None)
     step_t = [float(t) / 1000.0 for t in timesteps for _ in range(B)]  # the embedder sees sigma * 1000 (transformer.py:95)
     guidance = [float(guidance_scale)] * B if self.transformer.config.guidance_embeds else None

@@ -337,3 +337,48 @@ def test_dit_full_flux_size_parity():
     print(f"\n[full FLUX-size DiT, 57 blocks, S=2560] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
     assert torch.isfinite(got.float()).all()
     assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (e_nat, e_bf)
+
+
+@pytest.mark.parametrize("nt,hw", [(128, (8, 16)), (77, (10, 12))])
+def test_dit_cached_condition_branch(nt, hw):
+    """with model_config.independent_condition the condition stream is step-invariant; a plan built with
+    cache_cond=True runs it once in prepare() and every step processes the text + image rows only.  The result must equal
+    the un-cached plan (same kernels on fewer rows) and the fp32 oracle, at every prepared step."""
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights
+
+    dev = "cuda"
+    kw = dict(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = O.init_params(ocfg, seed=1234, dtype=torch.float32, device="cpu", w_std=0.05, bias_std=0.05, lora_b_std=0.05)
+    Pb = {k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}
+    P32 = {k: v.float() for k, v in Pb.items()}
+    h, w = hw
+    ni, B, T = h * w, 2, 3
+    g = torch.Generator().manual_seed(nt + 1)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(dev)  # noqa: E731
+    inp = dict(cond=r(B, ni, 64), pe=r(B, nt, 256, scale=0.5), pooled=r(B, 64), img_ids=_ids(h, w).to(dev),
+               cond_ids=_ids(h, w, -w).to(dev), txt_ids=torch.zeros(nt, 3).to(dev), guidance=3.5)
+    mc = {"independent_condition": True}
+    Wt = DitWeights(Pb, cfg, dev)
+    ts = [0.9, 0.5, 0.2]
+    outs = {}
+    for cached in (False, True):
+        plan = DitPlan(Wt, B, nt, ni, ni, T=T, model_config=mc, cache_cond=cached)
+        assert plan.cache_cond == cached
+        plan.set_ids(inp["txt_ids"], inp["img_ids"], inp["cond_ids"])
+        plan.prepare(inp["pe"], inp["pooled"], inp["cond"], [t for t in ts for _ in range(B)], [3.5] * B, c_t=0.0)
+        lats = [r(B, ni, 64) for _ in range(T)] if not outs else lats  # noqa: F821
+        outs[cached] = [plan.step(s, lats[s]).clone() for s in range(T)]
+        torch.cuda.synchronize()
+    for s in range(T):
+        inp["lat"] = lats[s]
+        ref32 = _oracle_full(O, ocfg, P32, inp, ts[s], torch.float32, mc)
+        e_c, e_u = _rel(outs[True][s], ref32), _rel(outs[False][s], ref32)
+        d = _rel(outs[True][s], outs[False][s])
+        print(f"\n[cached cond nt={nt} ni={ni} step {s}] relL2 vs oracle cached {e_c:.4g} un-cached {e_u:.4g}; cached vs un-cached {d:.3g}")
+        assert e_c <= 2e-2 and d < 2e-3
+    # configurations that do not allow caching fall back silently
+    assert not DitPlan(Wt, B, nt, ni, ni, T=1, model_config={}, cache_cond=True).cache_cond
+    assert not DitPlan(Wt, B, nt, ni, ni, T=1, model_config=mc, c_factor=1.5, cache_cond=True).cache_cond
