@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libloongx_b200.so"
+import os as _os0
+
+# LX_LIB: development aid (A/B builds of the same ABI); the product always loads the in-tree library
+_LIB_PATH = Path(_os0.environ["LX_LIB"]) if _os0.environ.get("LX_LIB") else Path(__file__).resolve().parent / "lib" / "libloongx_b200.so"
 
 
 class LoongXNativeError(RuntimeError):
