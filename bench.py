@@ -390,7 +390,10 @@ def run_train(args, rank, local_rank, world):
     n_img = (RES // 16) ** 2
     S, D, nb = N_TXT + 2 * n_img, 3072, 57
     F = nb * (24 * D * D * S + 4 * S * S * D)
-    flop = 2 * F + nb * 24 * D * D * S + 2.5 * nb * 4 * S * S * D  # fwd + recompute + bwd per sample
+    tr = model._trainer_obj
+    # SURVEY.md §8d per sample: forward F (+ F again only when the blocks are recomputed in the backward) + backward
+    # [dX of every Linear + 2.5x the attention]
+    flop = (2 if tr.recompute else 1) * F + nb * 24 * D * D * S + 2.5 * nb * 4 * S * S * D
     peaks = load_peaks()
     if rank == 0:
         tf = B * args.steps * flop / secs / 1e12
@@ -401,7 +404,8 @@ def run_train(args, rank, local_rank, world):
             "config": {"workload": "BASELINE.json configs[4]: train step, Flux-DiT LoRA r=4 + CS3/DGF conditioning (EEG+PPG, "
                                    "fNIRS+Motion, fuse_flag), 512x512 + image condition, gradient checkpointing per block, AdamW "
                                    "on the LoRA factors, mean all-reduce of the flat gradient bucket",
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (NCCL all-reduce of 14.5 M fp32)"},
+                       "batch_per_gpu": B, "global_batch": B * world, "micro_batch": tr.B, "recompute": tr.recompute,
+                       "parallelism": f"dp{world} (NCCL all-reduce of 14.5 M fp32)"},
             "gpu_launches": launches, "clocks": clk, "loss": float(loss.detach()),
             "algorithmic_tflops_per_gpu": tf, "frac_of_peak_end_to_end": tf / peaks["tflops"]}), flush=True)
     if world > 1:

@@ -295,11 +295,45 @@ class FlowStepFunction(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class FlowStepMicroFunction(torch.autograd.Function):
+    """A step over k micro-batches (gradient accumulation inside the step): every micro-batch runs forward + backward
+    right away (its activations are dropped before the next one), the gradients accumulate in the trainer's flat bucket
+    and `loss.backward()` only all-reduces / scales / hands them out.  loss = mean of the micro-batch losses."""
+
+    @staticmethod
+    def forward(ctx, trainer, chunks, *params):
+        k = len(chunks)
+        trainer.zero_grad()
+        total = torch.zeros((), device=trainer.loss.device, dtype=torch.float32)
+        for inputs in chunks:
+            total += trainer.forward(*inputs).reshape(())
+            trainer.backward(1.0 / k)
+        ctx.trainer = trainer
+        return total / k
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tr = ctx.trainer
+        allreduce_mean_(tr.grad_flat)
+        flat = tr.grad_flat * grad_out.to(tr.grad_flat.dtype)
+        grads, o = [], 0
+        for f in tr.factors.values():
+            grads.append(flat[o:o + f.A.numel()].view_as(f.A))
+            o += f.A.numel()
+            grads.append(flat[o:o + f.B.numel()].view_as(f.B))
+            o += f.B.numel()
+        return (None, None, *grads)
+
+
 class DitTrainer:
     """Native forward + backward of the rectified-flow objective for one batch geometry."""
 
     def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, model_config: Optional[dict] = None,
-                 attn_bwd: str = "native"):
+                 attn_bwd: str = "native", recompute: Optional[bool] = None):
+        """recompute: True = checkpoint the residual stream per block and rebuild the block's intermediates in the
+        backward (the reference's gradient_checkpointing, train/config/seed_512.yaml:16); False = keep every block's
+        intermediates from the forward (15.5 GB per 512x512 sample for FLUX.1-dev: no second forward, ~1.3x faster);
+        None = keep them when they fit in the free HBM, else recompute.  Same gradients either way."""
         model_config = model_config or {}
         assert attn_bwd in ("native", "library")
         self.attn_bwd = attn_bwd
@@ -325,11 +359,21 @@ class DitTrainer:
         R = self.R
         bf = dict(device=dev, dtype=torch.bfloat16)
         z = lambda *s: torch.zeros(s, **bf)  # noqa: E731
-        self.a = dict(XN=self.plan.buf["XN"], QM=z(R, 7 * D), Cat=z(R, 5 * D), Y1=z(R, D), XN2=z(R, D),
-                      Hid=z(R, 4 * D), Y2=z(R, D))
+        nl_, ns_ = cfg.num_layers, cfg.num_single_layers
+        if recompute is None:
+            recompute = not self.activations_fit(weights, B, S)
+        self.recompute = bool(recompute)
+        pb = self.plan.buf
+        # shared workspace: everything in recompute mode; in store mode only the pieces no backward kernel reads
+        self.a = dict(XN=pb["XN"], XN2=z(R, D), Q=pb["Q"], K=pb["K"], V=pb["V"],
+                      lse=torch.zeros((B, self.H, S), device=dev, dtype=torch.float32))
+        if self.recompute:
+            self.a.update(QM=z(R, 7 * D), Cat=z(R, 5 * D), Y1=z(R, D), Hid=z(R, 4 * D), Y2=z(R, D))
+            self.slabs = None
+        else:
+            self.slabs = [self._slab(i < nl_, z, dev) for i in range(nl_ + ns_)]
         self.g = dict(dX=z(R, D), dX1=z(R, D), dY=z(R, D), dXN=z(R, D), dBig=z(R, 7 * D), dCat=z(R, 5 * D),
                       dOh=z(B, self.H, S, 128), dQh=z(B, self.H, S, 128), dKh=z(B, self.H, S, 128), dVh=z(B, self.H, S, 128))
-        self.lse = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
         self.delta = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
         self.dq32 = torch.zeros((B, self.H, S, 128), device=dev, dtype=torch.float32)
         self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
@@ -393,6 +437,11 @@ class DitTrainer:
     def zero_grad(self):
         self.grad_flat.zero_()
 
+    def step_loss_micro(self, chunks) -> torch.Tensor:
+        """`chunks`: list of input tuples (each of this trainer's batch size) -> differentiable mean loss."""
+        self.remerge_if_stale()
+        return FlowStepMicroFunction.apply(self, chunks, *self.parameters())
+
     def step_loss(self, *inputs) -> torch.Tensor:
         """Differentiable loss (0-dim fp32): forward now, native backward when autograd reaches it."""
         self.remerge_if_stale()
@@ -436,21 +485,50 @@ class DitTrainer:
             lora_grad(x_rows, dy_rows[:, c:c + width], f.A.data, f.B.data, f.dA, f.dB, f.panel.scaling, self.lora_ws)
             c += width
 
-    def _attention(self, out):
+    @staticmethod
+    def activation_bytes(cfg, B: int, S: int) -> int:
+        """HBM needed to keep every block's backward operands (store mode): 18 / 17 [R, D] bf16 buffers per double /
+        single block (see _slab) + the log-sum-exp rows."""
+        R, D, H = B * S, cfg.inner_dim, cfg.num_attention_heads
+        return (cfg.num_layers * 18 + cfg.num_single_layers * 17) * R * D * 2 + (cfg.num_layers + cfg.num_single_layers) * B * H * S * 4
+
+    @staticmethod
+    def activations_fit(weights: DitWeights, B: int, S: int) -> bool:
+        free, _ = torch.cuda.mem_get_info(weights.device)
+        already = any(isinstance(p, PackedLinear) and p.wT is not None for p in weights.named.values())
+        w_bytes = 0 if already else weights.param_bytes()  # transposed panels (built once) ~ as large as the block weights
+        return DitTrainer.activation_bytes(weights.cfg, B, S) + w_bytes + (10 << 30) <= free
+
+    def _slab(self, double: bool, z, dev):
+        """per-block activations the backward reads (store mode): modulated input, pre-activation projections, attention
+        operands + log-sum-exp, attention output / single-block concat, pre-gate projection outputs, FF hidden."""
+        B, H, S, R, D = self.B, self.H, self.S, self.R, self.D
+        a = dict(XN=z(R, D), QM=z(R, 7 * D), Cat=z(R, D if double else 5 * D), Y1=z(R, D), Q=z(B, H, S, 128),
+                 K=z(B, H, S, 128), V=z(B, H, S, 128), lse=torch.zeros((B, H, S), device=dev, dtype=torch.float32),
+                 XN2=self.a["XN2"])
+        if double:
+            a.update(Hid=z(R, 4 * D), Y2=z(R, D))
+        return a
+
+    def _act(self, blk: int):
+        """activation set of block `blk` (double blocks first): its own slab, or the shared recompute workspace."""
+        return self.a if self.slabs is None else self.slabs[blk]
+
+    def _attention(self, out, a):
         """out: [R, ld] view; head h lands in columns [128h, 128h+128).  Also records the log-sum-exp rows."""
         b, p = self.plan.buf, self.plan.plan
-        ops.attention(b["Q"], b["K"], b["V"], out, b["out_row_base"], n_cond=self.nc, mask_mode=p.mask_mode,
-                      cross_bias=p.cross_bias, lse=self.lse, pads=self.pads, n_txt=self.nt)
+        ops.attention(a["Q"], a["K"], a["V"], out, b["out_row_base"], n_cond=self.nc, mask_mode=p.mask_mode,
+                      cross_bias=p.cross_bias, lse=a["lse"], pads=self.pads, n_txt=self.nt)
 
-    def _attention_bwd(self, d_rows, o_rows):
+    def _attention_bwd(self, d_rows, o_rows, a):
         """d_rows / o_rows: [R, >= D] views holding dO / O in their first D columns -> dq, dk, dv head-major (bf16)."""
         b, p, g = self.plan.buf, self.plan.plan, self.g
         if self.attn_bwd == "library":  # A/B check only: torch SDPA autograd
             rows_to_heads(d_rows, self.H, b["tile_meta"], g["dOh"])
-            return sdpa_backward_library(b["Q"], b["K"], b["V"], g["dOh"], self.nc, p.mask_mode, p.cross_bias)
+            return sdpa_backward_library(a["Q"], a["K"], a["V"], g["dOh"], self.nc, p.mask_mode, p.cross_bias)
         ops.attention_bwd_prep(d_rows, o_rows, self.H, b["tile_meta"], g["dOh"], self.delta)
         self.dq32.zero_()
-        ops.attention_bwd(b["Q"], b["K"], b["V"], g["dOh"], self.lse, self.delta, self.dq32, g["dKh"], g["dVh"],
+        ops.attention_bwd(a["Q"], a["K"], a["V"], g["dOh"], a["lse"], self.delta, self.dq32, g["dKh"], g["dVh"],
                           n_cond=self.nc, mask_mode=p.mask_mode, cross_bias=p.cross_bias, pads=self.pads, n_txt=self.nt)
         L.check(_lib.lx_cast(self.dq32.data_ptr(), g["dQh"].data_ptr(), self.dq32.numel(), 1, _stream()), "lx_cast")
         return g["dQh"], g["dKh"], g["dVh"]
@@ -468,16 +546,16 @@ class DitTrainer:
     def _double_fwd(self, i, recompute: bool = False):
         """recompute=True (backward): the residual stream after the attention branch comes from its checkpoint, the
         pre-gate projection outputs are rebuilt for the condition rows only and the block output is not formed."""
-        b, a, D, W = self.plan.buf, self.a, self.D, self.w.named
+        b, a, D, W = self.plan.buf, self._act(i), self.D, self.w.named
         X, tm = b["X"], b["tile_meta"]
         m = self._mods_double(i)
         pre = a["QM"][:, :3 * D]
         ln_modulate(X, a["XN"], tm, m[0], m[1])
         self._gemm(a["XN"], W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], pre)
         nq, nk, naq, nak = (W[f"double.{i}.{n}"] for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
-        qkv_post_fwd(pre, self.H, tm, b["Q"], b["K"], b["V"], [naq, nq, nq], [nak, nk, nk], b["rope"])
+        qkv_post_fwd(pre, self.H, tm, a["Q"], a["K"], a["V"], [naq, nq, nq], [nak, nk, nk], b["rope"])
         O = a["Cat"][:, :D]
-        self._attention(O)
+        self._attention(O, a)
         if recompute:
             self._gemm_cond(O, W[f"double.{i}.out"], a["Y1"], W[f"double.{i}.out_ctx"])
             x1 = self.ckpt_mid[i]
@@ -497,7 +575,7 @@ class DitTrainer:
 
     def _double_bwd(self, i, x_in):
         """gradient wrt the block output is in g['dX']; leaves the gradient wrt the block input there."""
-        b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
+        b, a, g, D, W = self.plan.buf, self._act(i), self.g, self.D, self.w.named
         tm = b["tile_meta"]
         m = self._mods_double(i)
         c0 = self.Rt if self.latent_lora else self.Rt + self.Ri  # first row whose Linear carries LoRA
@@ -519,7 +597,7 @@ class DitTrainer:
         self._lora_grads([pfx + "attn.to_out.0"], O[c0:], g["dY"][c0:])
         d_o = g["dCat"][:, :D]
         self._gemm(g["dY"], W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], d_o, transposed=True)
-        dq, dk, dv = self._attention_bwd(d_o, O)
+        dq, dk, dv = self._attention_bwd(d_o, O, a)
         nq, nk, naq, nak = (W[f"double.{i}.{n}"] for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
         d_pre = g["dBig"][:, :3 * D]
         qkv_post_bwd(pre, dq, dk, dv, d_pre, self.H, tm, [naq, nq, nq], [nak, nk, nk], b["rope"])
@@ -528,15 +606,15 @@ class DitTrainer:
         ln_modulate_bwd(x_in, g["dXN"], g["dX1"], g["dX"], tm, m[1], dm(1), dm(0), self.stats)
 
     def _single_fwd(self, i, recompute: bool = False):
-        b, a, D, W = self.plan.buf, self.a, self.D, self.w.named
+        b, a, D, W = self.plan.buf, self._act(self.cfg.num_layers + i), self.D, self.w.named
         X, tm = b["X"], b["tile_meta"]
         m = self._mods_single(i)
         ln_modulate(X, a["XN"], tm, m[0], m[1])
         self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"])
         nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
-        qkv_post_fwd(a["QM"], self.H, tm, b["Q"], b["K"], b["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
+        qkv_post_fwd(a["QM"], self.H, tm, a["Q"], a["K"], a["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
         gelu_fwd(a["QM"][:, 3 * D:], a["Cat"][:, D:])
-        self._attention(a["Cat"])
+        self._attention(a["Cat"], a)
         if recompute:
             self._gemm_cond(a["Cat"], W[f"single.{i}.proj_out"], a["Y1"])
         else:
@@ -544,7 +622,7 @@ class DitTrainer:
             gate_residual_fwd(X, a["Y1"], X, tm, m[2])
 
     def _single_bwd(self, i, x_in):
-        b, a, g, D, W = self.plan.buf, self.a, self.g, self.D, self.w.named
+        b, a, g, D, W = self.plan.buf, self._act(self.cfg.num_layers + i), self.g, self.D, self.w.named
         tm = b["tile_meta"]
         m = self._mods_single(i)
         c0 = 0 if self.latent_lora else self.Rt + self.Ri
@@ -555,7 +633,7 @@ class DitTrainer:
         self._lora_grads([pfx + "proj_out"], a["Cat"][c0:], g["dY"][c0:])
         self._gemm(g["dY"], W[f"single.{i}.proj_out"], None, g["dCat"], transposed=True)
         gelu_bwd(a["QM"][:, 3 * D:], g["dCat"][:, D:], g["dBig"][:, 3 * D:])
-        dq, dk, dv = self._attention_bwd(g["dCat"], a["Cat"])
+        dq, dk, dv = self._attention_bwd(g["dCat"], a["Cat"], a)
         nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
         qkv_post_bwd(a["QM"], dq, dk, dv, g["dBig"], self.H, tm, [nq, nq, nq], [nk, nk, nk], b["rope"])
         self._lora_grads([pfx + "attn.to_q", pfx + "attn.to_k", pfx + "attn.to_v", pfx + "proj_mlp"], a["XN"][c0:],
@@ -633,12 +711,14 @@ class DitTrainer:
         ln_modulate_bwd(s["X_final"][sl], g["dXN"][sl], None, g["dX"][sl], tm[self.Rt // 128:], [sc, sc, sc],
                         [None] * 3, [None] * 3, None)
         for i in reversed(range(ns)):
-            X.copy_(self.ckpt[nl + i])
-            self._single_fwd(i, recompute=True)  # gradient checkpointing, transformer.py:184-206
+            if self.recompute:  # gradient checkpointing, transformer.py:184-206
+                X.copy_(self.ckpt[nl + i])
+                self._single_fwd(i, recompute=True)
             self._single_bwd(i, self.ckpt[nl + i])
         for i in reversed(range(nl)):
-            X.copy_(self.ckpt[i])
-            self._double_fwd(i, recompute=True)
+            if self.recompute:
+                X.copy_(self.ckpt[i])
+                self._double_fwd(i, recompute=True)
             self._double_bwd(i, self.ckpt[i])
         # x_embedder on the condition rows (transformer.py:93) (+ the image rows with latent_lora, transformer.py:91-92)
         c0 = self.Rt + self.Ri

@@ -20,7 +20,9 @@ cfg = FluxConfig(num_layers=layers[0], num_single_layers=layers[1])
 t0 = time.time()
 W = DitWeights(random_params(cfg, dev), cfg, dev, consume=True)
 nt, ni, nc = 512, 1024, 1024
-tr = DitTrainer(W, B, nt, ni, nc, model_config={})
+_rc = os.environ.get("LX_RECOMPUTE")
+tr = DitTrainer(W, B, nt, ni, nc, model_config={}, recompute=None if _rc is None else bool(int(_rc)))
+print("recompute", tr.recompute)
 torch.cuda.synchronize()
 print(f"weights + transposed panels + workspace: {torch.cuda.memory_allocated() / 1e9:.1f} GB in {time.time() - t0:.1f} s; "
       f"{len(tr.factors)} LoRA targets, {tr.grad_flat.numel() / 1e6:.2f} M trainable", flush=True)

@@ -171,6 +171,27 @@ class OminiModel(nn.Module):
             self._trainer_key = key
         return self._trainer_obj
 
+    def _micro_batch(self, B: int, S: int) -> int:
+        """Samples per native forward/backward: the whole batch when its block activations fit in the free HBM (no
+        recompute), else the largest divisor of B that does (the step then accumulates gradients over B / mb micro-
+        batches, same result); B itself (with per-block recompute) when not even one sample fits.  `self.micro_batch`
+        (int) overrides."""
+        from loongx_b200.train import DitTrainer
+
+        forced = getattr(self, "micro_batch", None)
+        if forced:
+            return int(forced)
+        cache = self.__dict__.setdefault("_mb_cache", {})  # decided once per geometry (the trainer then owns that memory)
+        if (B, S) not in cache:
+            pad = lambda n: (n + 127) // 128 * 128  # noqa: E731
+            w = self.transformer.weights
+            cache[(B, S)] = B
+            for mb in sorted((d for d in range(1, B + 1) if B % d == 0), reverse=True):
+                if DitTrainer.activations_fit(w, mb, pad(S) + 256):
+                    cache[(B, S)] = mb
+                    break
+        return cache[(B, S)]
+
     @property
     def lora_layers(self):
         """model.py:513-524: the LoRA factors (fp32 masters) — the only parameters the reference's optimizer trains."""
@@ -255,9 +276,15 @@ class OminiModel(nn.Module):
                 pe, po = self._step_conditioning(pe, po, batch.get("eeg"), batch.get("fnirs"), batch.get("ppg"),
                                                  batch.get("motion"))
             text_ids = torch.zeros(pe.shape[1], 3, device=dev)
-        tr = self._trainer(B, pe.shape[1], x_0.shape[1], condition_latents.shape[1])
-        loss = tr.step_loss(x_0.contiguous(), x_1.contiguous(), t, condition_latents, pe, po, text_ids, img_ids.float(),
-                            condition_ids, 1.0)
+        mb = self._micro_batch(B, pe.shape[1] + x_0.shape[1] + condition_latents.shape[1])
+        tr = self._trainer(mb, pe.shape[1], x_0.shape[1], condition_latents.shape[1])
+        if mb == B:
+            loss = tr.step_loss(x_0.contiguous(), x_1.contiguous(), t, condition_latents, pe, po, text_ids, img_ids.float(),
+                                condition_ids, 1.0)
+        else:  # gradient accumulation over micro-batches whose activations fit in HBM without recompute
+            chunks = [(x_0[i:i + mb].contiguous(), x_1[i:i + mb].contiguous(), t[i:i + mb], condition_latents[i:i + mb],
+                       pe[i:i + mb], po[i:i + mb], text_ids, img_ids.float(), condition_ids, 1.0) for i in range(0, B, mb)]
+            loss = tr.step_loss_micro(chunks)
         self.last_t = float(t.mean())
         return loss
 

@@ -238,11 +238,12 @@ def _tiny_train_case(layers=(2, 2), B=2, nt=128, hw=(16, 32), seed=0):
     return ocfg, cfg, P, batch
 
 
+@pytest.mark.parametrize("recompute", [False, True])
 @pytest.mark.parametrize("layers,mc,nt,hw", [((1, 1), {}, 128, (16, 32)), ((2, 2), {}, 128, (16, 32)),
                                              ((2, 2), {"latent_lora": True}, 128, (16, 32)),
                                              ((1, 2), {"independent_condition": True}, 128, (16, 32)),
                                              ((1, 1), {}, 100, (12, 20)), ((2, 1), {"latent_lora": True}, 77, (20, 36))])
-def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc, nt, hw):
+def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc, nt, hw, recompute):
     """Native forward + backward vs fp32 autograd over the oracle restatement of model.py:569-729."""
     from oracle import sampler as OS
     from oracle import train_step as TS
@@ -257,7 +258,8 @@ def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc, nt, hw):
     loss_ref, grads_ref, aux = TS.flow_step_grads(P32, ocfg, {k: (v.float() if isinstance(v, torch.Tensor) else v)
                                                               for k, v in b_dev.items()}, model_config=mc)
     W = DitWeights({k: v.to(DEV) for k, v in P.items()}, cfg, DEV)
-    tr = DitTrainer(W, B, nt, ni, ni, model_config=mc)  # ragged lengths are padded to 128-token tiles inside
+    tr = DitTrainer(W, B, nt, ni, ni, model_config=mc, recompute=recompute)  # ragged lengths are padded inside
+    assert tr.recompute == recompute
     x0 = OS.pack_latents(b_dev["image"]).contiguous()
     cond = OS.pack_latents(b_dev["condition"]).contiguous()
     img_ids = OS.prepare_latent_image_ids(batch["image"].shape[2], batch["image"].shape[3]).to(DEV)
@@ -267,7 +269,7 @@ def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc, nt, hw):
     torch.cuda.synchronize()
     loss1 = loss.item()  # the trainer reuses its loss buffer
     e_pred = _rel(tr.pred, aux["pred"])
-    print(f"\n[train {layers} {mc} nt={nt} ni={ni}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
+    print(f"\n[train {layers} {mc} nt={nt} ni={ni} recompute={recompute}] loss native {loss1:.6f} oracle {loss_ref.item():.6f}  pred relL2 {e_pred:.4g}")
     assert e_pred < 2e-2
     assert abs(loss1 - loss_ref.item()) / loss_ref.item() < 2e-2
     tr.zero_grad()
@@ -407,3 +409,33 @@ def test_ddp_gradient_allreduce_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-2000:], out.stderr[-2000:])
     assert out.returncode == 0
+
+
+def test_micro_batched_step_equals_full_batch():
+    """OminiModel.step with micro_batch < B (gradient accumulation inside the step, used when a batch's activations do not
+    fit without recompute): same loss and LoRA gradients as the one-shot step."""
+    from loongx_b200.config import FluxConfig
+    from src.train.model import OminiModel
+
+    kw = dict(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
+    g = torch.Generator().manual_seed(5)
+    B, h, w = 4, 16, 32
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(DEV)  # noqa: E731
+    batch = dict(image=r(B, 16, h, w), condition=r(B, 16, h, w), prompt_embeds=r(B, 128, 256, scale=0.5),
+                 pooled_prompt_embeds=r(B, 64), position_delta=[[0, -16]], condition_type=["subject"] * B,
+                 t=torch.tensor([0.2, 0.4, 0.6, 0.8]), noise=r(B, 128, 64))
+    res = {}
+    for mb in (None, 2, 1):
+        m = OminiModel(FluxConfig(**kw), lora_config={"r": 4, "lora_alpha": 4}, device=DEV, model_config={},
+                       use_brain_condition=False, seed=3)
+        m.micro_batch = mb
+        loss = m.step(batch)
+        loss.backward()
+        tr = m._trainer_obj
+        assert tr.B == (mb or B)
+        res[mb] = (float(loss.detach()), torch.cat([p.grad.flatten() for p in tr.parameters()]).clone())
+    for mb in (2, 1):
+        dl = abs(res[mb][0] - res[None][0]) / res[None][0]
+        dg = _rel(res[mb][1], res[None][1])
+        print(f"\n[micro-batch {mb}] loss rel diff {dl:.3g}, grad relL2 diff {dg:.3g}")
+        assert dl < 1e-3 and dg < 1e-2
