@@ -13,7 +13,8 @@
 //       dK_j += dS^T Q_i            TS   (B = Q_i MN-major)                                 -> TMEM cols [384,512)
 //       dQ_i  = dS   K_j            SS   (A = the dS^T tile read MN-major, B = K_j MN-major) -> TMEM cols [128,256),
 //               read back by the compute threads, staged in shared memory and added to the fp32 dQ accumulator in
-//               global memory by the TMA unit (cp.reduce.async.bulk.tensor .add, one bulk op per 128 x 32 chunk)
+//               global memory by the TMA unit (cp.reduce.async.bulk.tensor .add, one bulk op per 128 x 16 chunk, staging
+//               tiles double-buffered so the threads do not wait for the bulk reads)
 //   warp 0: TMA producer (K_j, V_j once; Q_i through a 2-stage ring, dO_i single-buffered: 192 KB of shared memory)
 //   warp 1: tcgen05.mma issuer        warps 2..9: compute, two threads per key row (TMEM lane quarter = warp & 3,
 //           64 of the 128 query columns each)
@@ -30,8 +31,8 @@ namespace lx {
 constexpr int AB_TILE_BYTES = 128 * 128 * 2;
 constexpr int AB_ATOM_BYTES = 128 * 64 * 2;
 constexpr int AB_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 compute warps
-constexpr int AB_DQ_SLOT = 128 * 32 * 4;  // 16 KiB: 128 query rows x 32 head dims fp32, one per compute group
-constexpr int AB_SMEM = 6 * AB_TILE_BYTES + 2 * AB_DQ_SLOT + 2 * 2 * 128 * 4 + 256;  // 226.25 KiB, base 1024-aligned
+constexpr int AB_DQ_SLOT = 128 * 16 * 4;  // 8 KiB: 128 query rows x 16 head dims fp32; two (double-buffered) per compute group
+constexpr int AB_SMEM = 6 * AB_TILE_BYTES + 4 * AB_DQ_SLOT + 2 * 2 * 128 * 4 + 256;  // 226.25 KiB, base 1024-aligned
 
 struct AttnBwdParams {
   const float* lse;    // [B*H*S] log2-domain log-sum-exp of the forward
@@ -64,7 +65,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sdO = sQ + 2 * AB_TILE_BYTES;
   uint8_t* sdS = sdO + AB_TILE_BYTES;
   uint8_t* sdQ = sdS + AB_TILE_BYTES;       // [2 compute groups] staging of dQ chunks for the TMA reduce
-  float* sStat = reinterpret_cast<float*>(sdQ + 2 * AB_DQ_SLOT);  // [2 parities][lse | delta][128]
+  float* sStat = reinterpret_cast<float*>(sdQ + 4 * AB_DQ_SLOT);  // [2 parities][lse | delta][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128);
   uint64_t* kv_full = bars;        // 1
   uint64_t* q_full = bars + 1;     // [2]
@@ -283,7 +284,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // 4096 scattered 16-byte atomics per tile
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
-      uint8_t* slot = sdQ + half * AB_DQ_SLOT;
+      uint8_t* slots = sdQ + half * 2 * AB_DQ_SLOT;  // this group's two 128 x 16 staging tiles
       const bool issuer = (threadIdx.x == 64 + 128 * half);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -293,19 +294,26 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tc_fence_before();
           mbar_arrive(dq_read);
         }
-        if (issuer) tma_store_wait_read<0>();  // the previous chunk's bulk read of the slot is complete
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-        if (!(p.dbg_flags & 1)) {
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            *reinterpret_cast<uint4*>(slot + r * 128 + ((ch ^ (r & 7)) << 4)) =
-                make_uint4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
-        }
-        fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-        if (issuer && !(p.dbg_flags & 1)) {
-          tma_reduce_add_2d(&tmdQ, slot, half * 64 + c * 32, head_row0 + qi * 128);
-          tma_store_commit();
+        for (int hc = 0; hc < 2; ++hc) {  // two 16-column chunks, alternating staging tiles
+          uint8_t* slot = slots + hc * AB_DQ_SLOT;
+          // the bulk read issued from this tile two chunks ago must be complete; the most recent one may still be in flight
+          if (issuer) tma_store_wait_read<1>();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          if (!(p.dbg_flags & 1)) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const uint32_t a = static_cast<uint32_t>(r * 64 + ch * 16);
+              *reinterpret_cast<uint4*>(slot + (a ^ (((a >> 7) & 3u) << 4))) =  // 64-byte swizzle of the TMA tile
+                  make_uint4(o[hc * 16 + 4 * ch], o[hc * 16 + 4 * ch + 1], o[hc * 16 + 4 * ch + 2], o[hc * 16 + 4 * ch + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          if (issuer && !(p.dbg_flags & 1)) {
+            tma_reduce_add_2d(&tmdQ, slot, half * 64 + c * 32 + hc * 16, head_row0 + qi * 128);
+            tma_store_commit();
+          }
         }
       }
     }
@@ -405,7 +413,7 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   const uint64_t rows = (uint64_t)d.B * d.H * d.S;
   CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
   int rc;
-  if ((rc = make_tmap_2d_f32(&tmdQ, d.dq, rows, 128, 128, 128, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&tmdQ, d.dq, rows, 128, 128, 128, 16))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmQ, d.q, rows, 128, 128, 128, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmK, d.k, rows, 128, 128, 128, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmV, d.v, rows, 128, 128, 128, 64))) return rc;
