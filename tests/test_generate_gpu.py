@@ -211,3 +211,47 @@ def test_joint_attention_kwargs_lora_scale():
     print(f"\n[lora scale] relL2 vs oracle at scale 1 / 0.5 / 0: {e[0]:.4g} {e[1]:.4g} {e[2]:.4g}; effect {rel(out0, out1):.4g}")
     assert max(e) < 1.5e-2 and rel(out0, out1) > 3 * max(e)
     assert torch.equal(out1, out1b)
+
+
+def test_generate_full_size_properties():
+    """BASELINE.json configs[1] at FULL size (FLUX.1-dev geometry, 512x512 + image condition, EEG-only CS3 conditioning, 28
+    steps) through src.flux.generate.generate, checked with size-independent properties (the fp32 oracle would need minutes
+    per edit): (1) determinism - the same call twice is bit-identical; (2) batch consistency - two identical edits in one
+    batch give identical rows, equal to the single-edit result up to GEMM tile-order effects (relL2 <= 1e-2);
+    (3) the output actually depends on the EEG signal and on the condition image; (4) finite, sane scale."""
+    from src.flux.condition import Condition
+    from src.flux.generate import generate
+    from src.train.model import OminiModel
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs the full-size model (56 GB of weights)")
+    model = OminiModel("synthetic", lora_config={"r": 4, "lora_alpha": 4}, device="cuda",
+                       model_config={"union_cond_attn": True, "add_cond_attn": False, "latent_lora": False})
+    pipe = model.flux_pipe
+    g = torch.Generator(device="cuda").manual_seed(7)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device="cuda") * scale)  # noqa: E731
+    lat, cond = r(1, 16, 64, 64).bfloat16(), r(1, 16, 64, 64).bfloat16()
+    pe, po, eeg = r(1, 512, 4096, scale=0.1).bfloat16(), r(1, 768).bfloat16(), r(1, 4, 5000)
+
+    def edit(lat, cond, pe, po, eeg):
+        c = Condition("subject", condition=cond, position_delta=[0, -32])
+        return generate(model, pipe, conditions=[c], prompt_embeds=pe, pooled_prompt_embeds=po, height=512, width=512,
+                        num_inference_steps=28, latents=pipe._pack_latents(lat), output_type="latent", default_lora=True,
+                        additional_condition1=eeg, use_brain_condition=True, fuse_flag=False, eeg_only_replace=True).images
+
+    a = edit(lat, cond, pe, po, eeg)
+    b = edit(lat, cond, pe, po, eeg)
+    assert a.shape == (1, 1024, 64) and torch.isfinite(a.float()).all()
+    assert torch.equal(a, b), "the denoise loop must be deterministic"
+    rep = lambda x: x.repeat(2, *([1] * (x.dim() - 1)))  # noqa: E731
+    ab = edit(rep(lat), rep(cond), rep(pe), rep(po), rep(eeg))
+    assert torch.equal(ab[0], ab[1])
+    d_batch = _rel(ab[0:1], a)
+    c2 = edit(lat, r(1, 16, 64, 64).bfloat16(), pe, po, eeg)
+    e2 = edit(lat, cond, pe, po, r(1, 4, 5000))
+    d_cond, d_eeg = _rel(c2, a), _rel(e2, a)
+    print(f"\n[full-size generate] std {a.float().std().item():.3f}; batch-of-2 vs single relL2 {d_batch:.3g}; "
+          f"other condition image {d_cond:.3g}; other EEG {d_eeg:.3g}")
+    assert d_batch <= 1e-2 and d_cond > 10 * d_batch and d_eeg > 10 * d_batch
+    assert 0.05 < a.float().std().item() < 50
