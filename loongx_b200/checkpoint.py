@@ -19,7 +19,7 @@ from __future__ import annotations
 import json
 import os
 import re
-from typing import Dict, Iterable, Optional, Tuple
+from typing import Dict, Iterable, Tuple
 
 import torch
 

@@ -22,14 +22,13 @@ CS3 / DGF encoders run forward-only (they are not in the reference's optimizer p
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from . import _lib as L
 from . import ops
-from .dit import DitPlan, DitWeights, LxDitPlan, PackedLinear, _stream, mask_mode_from_config
+from .dit import DitPlan, DitWeights, PackedLinear, _stream
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _P3 = c_void_p * 3

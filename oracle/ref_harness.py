@@ -32,7 +32,7 @@ import math
 import os
 import sys
 import types
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch
