@@ -4,26 +4,33 @@ Image pre-processing (canny / depth / blur, condition.py:53-90) and the VAE are 
 constructed from already-encoded latents ([B, 16, h, w]) or packed tokens ([B, N, 64]).  The position arithmetic on the
 ids (condition.py:126-137) is kept operation for operation so the resulting ids are bit-identical.
 """
-from typing import Tuple, Union
+from typing import Tuple
 
 import torch
 
 from .pipeline_tools import encode_images
 
-condition_dict = {
-    "depth": 0,
-    "canny": 1,
-    "subject": 4,
-    "coloring": 6,
-    "deblurring": 7,
-    "depth_pred": 8,
-    "fill": 9,
-    "sr": 10,
-    "cartoon": 11,
-    "eeg+fnirs": 12,
-}
+# type name -> type id (condition.py:10-21); the ids only matter as labels, `condition_type_ids` is ignored downstream
+_TYPE_IDS = (("depth", 0), ("canny", 1), ("subject", 4), ("coloring", 6), ("deblurring", 7), ("depth_pred", 8), ("fill", 9),
+             ("sr", 10), ("cartoon", 11), ("eeg+fnirs", 12))
+condition_dict = dict(_TYPE_IDS)
+_IMAGE_TYPES = tuple(name for name, _ in _TYPE_IDS if name != "eeg+fnirs")  # the types encode() accepts (condition.py:110-120)
 
-_IMAGE_TYPES = ("depth", "canny", "subject", "coloring", "deblurring", "depth_pred", "fill", "sr", "cartoon")
+
+def _shift_scale_ids(ids: torch.Tensor, delta, scale: float) -> torch.Tensor:
+    """Position arithmetic of condition.py:126-137 on the (row, col) columns of `ids`, in the reference's operation
+    order (add the delta, multiply by the scale, add (scale - 1) / 2) so the results are bit-identical."""
+    rc = (1, 2)
+    if delta is not None:
+        for col, d in zip(rc, delta):
+            ids[:, col] += d
+    if scale != 1.0:
+        half = (scale - 1.0) / 2
+        for col in rc:
+            ids[:, col] *= scale
+        for col in rc:
+            ids[:, col] += half
+    return ids
 
 
 class Condition(object):
@@ -68,14 +75,6 @@ class Condition(object):
         if self.position_delta is None and self.condition_type == "subject":
             width_px = c.size[0] if hasattr(c, "size") and not isinstance(c, torch.Tensor) else 16 * int(round(tokens.shape[1] ** 0.5))
             self.position_delta = [0, -width_px // 16]
-        if self.position_delta is not None:
-            ids[:, 1] += self.position_delta[0]
-            ids[:, 2] += self.position_delta[1]
-        if self.position_scale != 1.0:
-            scale_bias = (self.position_scale - 1.0) / 2
-            ids[:, 1] *= self.position_scale
-            ids[:, 2] *= self.position_scale
-            ids[:, 1] += scale_bias
-            ids[:, 2] += scale_bias
+        ids = _shift_scale_ids(ids, self.position_delta, self.position_scale)
         type_id = torch.ones_like(ids[:, :1]) * self.type_id
         return tokens, ids, type_id
