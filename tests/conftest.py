@@ -23,3 +23,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _release_gpu_memory_between_modules():
+    """GPU test modules build models of very different sizes (up to the full 56 GB FLUX.1-dev-sized one): hand the caching
+    allocator's blocks back to the driver after every module so the next one sees the whole device."""
+    yield
+    try:
+        import gc
+
+        import torch
+
+        if torch.cuda.is_available():
+            gc.collect()
+            torch.cuda.empty_cache()
+    except Exception:
+        pass

@@ -307,6 +307,10 @@ def test_dit_full_flux_size_parity():
     from loongx_b200.config import FluxConfig
     from loongx_b200.dit import DitPlan, DitWeights, random_params
 
+    import gc as _gc
+
+    _gc.collect()
+    torch.cuda.empty_cache()  # earlier tests leave their blocks in the caching allocator
     free, _ = torch.cuda.mem_get_info()
     if free < 150e9:
         pytest.skip("needs ~130 GB of free HBM (fp32 oracle weights + native panels)")

@@ -223,6 +223,10 @@ def test_generate_full_size_properties():
     from src.flux.generate import generate
     from src.train.model import OminiModel
 
+    import gc as _gc
+
+    _gc.collect()
+    torch.cuda.empty_cache()  # earlier tests leave their blocks in the caching allocator
     free, _ = torch.cuda.mem_get_info()
     if free < 100e9:
         pytest.skip("needs the full-size model (56 GB of weights)")
