@@ -37,7 +37,11 @@ lat = torch.randn(B, ni, 64, generator=g, device=dev).bfloat16()
 ts = [1.0 - 0.9 * s / T for s in range(T) for _ in range(B)]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); plan.prepare(pe, pooled, cond, ts, [3.5] * B); e1.record(); torch.cuda.synchronize()
-print(f"prepare (T={T}): {e0.elapsed_time(e1):.2f} ms")
+print(f"prepare (T={T}): {e0.elapsed_time(e1):.2f} ms (first call)")
+import time as _t
+_h0 = _t.perf_counter()
+e0.record(); plan.prepare(pe, pooled, cond, ts, [3.5] * B); e1.record(); torch.cuda.synchronize()
+print(f"prepare (T={T}): {e0.elapsed_time(e1):.2f} ms device, {(_t.perf_counter() - _h0) * 1e3:.2f} ms host wall (second call)")
 out = torch.empty_like(lat)
 for s in range(min(2, T)):
     plan.step(s, lat, out)
