@@ -151,3 +151,70 @@ def test_weight_packing_merges_lora_for_the_condition_rows():
     assert mask_mode_from_config({"independent_condition": True}) == 2
     with pytest.raises(ValueError):
         FluxConfig(num_attention_heads=3).validate()
+
+
+def test_training_kernels_validate_arguments_without_gpu():
+    """The training-step entry points fail loudly on bad arguments before touching the device."""
+    from loongx_b200 import _lib as L
+    import loongx_b200.train  # noqa: F401  (argtypes)
+
+    lib = L.lib
+    assert lib.lx_gelu_fwd(16, 8, 16, 8, 4, 12, None) == -1          # cols not a multiple of 8
+    assert lib.lx_lora_grad(16, 8, 16, 8, 16, 16, 16, 16, 4, 64, 64, 32, 1.0, 16, None) == -1 and b"rank" in lib.lx_last_error()
+    assert lib.lx_flow_mse_loss(16, 16, 16, 16, None, 12, 1.0, None) == -1  # n not a multiple of 8
+    b = L.AttnBwdDesc()
+    b.q = b.k = b.v = b.d_out = b.lse = b.delta = b.dq = b.dk = b.dv = 16
+    b.B, b.H, b.S, b.n_cond = 1, 1, 256, 100
+    assert lib.lx_attention_bwd(C.byref(b), None) == -1 and b"n_cond" in lib.lx_last_error()
+    a = L.AttnDesc()
+    a.q = a.k = a.v = a.out = a.out_row_base = 16
+    a.B, a.H, a.S = 1, 1, 256
+    a.pad[0] = 130  # padding must be < 128
+    assert lib.lx_attention(C.byref(a), None) == -1 and b"padding" in lib.lx_last_error()
+
+
+def test_plan_padding_arithmetic_and_micro_batch_choice(monkeypatch):
+    """Host-side geometry: streams padded to 128-token tiles; the training micro-batch is the largest divisor of the batch
+    whose block activations fit in the free HBM."""
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import _pad128
+    from loongx_b200.train import DitTrainer
+
+    assert [_pad128(n) for n in (1, 77, 128, 129, 1024, 1600)] == [128, 128, 128, 256, 1024, 1664]
+    cfg = FluxConfig()
+    per_sample = DitTrainer.activation_bytes(cfg, 1, 2560)
+    assert 15e9 < per_sample < 16.5e9 and DitTrainer.activation_bytes(cfg, 4, 2560) == 4 * per_sample
+
+    class _W:  # the attributes activations_fit() reads
+        device, named = "cuda", {}
+
+        @staticmethod
+        def param_bytes():
+            return 55 * 10**9
+
+    _W.cfg = cfg
+
+    for free_gb, expect in ((180, [True, True, False]), (100, [True, False, False]), (60, [False, False, False])):
+        monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None, f=free_gb: (f * 10**9, 192 * 10**9))
+        assert [DitTrainer.activations_fit(_W, B, 2560) for B in (1, 4, 8)] == expect, free_gb
+
+
+def test_checkpoint_key_renaming_is_total():
+    """Every parameter name of the FLUX.1-dev geometry survives the LoongX <-> diffusers renaming both ways."""
+    from loongx_b200 import checkpoint as CK
+    from loongx_b200.config import FluxConfig, lora_targets
+
+    cfg = FluxConfig()
+    keys = sorted(CK.expected_keys(cfg))
+    assert len(keys) == 2 * len(__import__("loongx_b200.config", fromlist=["linear_shapes"]).linear_shapes(cfg)) + 19 * 4 + 38 * 2
+    targets = set(lora_targets(cfg))
+    assert len(targets) == 1 + 19 * 6 + 38 * 6
+    sd = {}
+    for k in keys:
+        stem, kind = k.rsplit(".", 1)
+        sd[f"transformer.{stem}.base_layer.{kind}" if stem in targets else "transformer." + k] = k
+    for t in targets:
+        sd[f"transformer.{t}.lora_A.default.weight"] = t + ".lora_A.weight"
+        sd[f"transformer.{t}.lora_B.default.weight"] = t + ".lora_B.weight"
+    tr, rest = CK.split_loongx_state_dict(sd)
+    assert not rest and all(k == v for k, v in tr.items()) and len(tr) == len(keys) + 2 * len(targets)
