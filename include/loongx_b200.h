@@ -430,6 +430,48 @@ int lx_flow_noise_mix(const void* x0, const void* x1, const float* t, void* xt, 
 int lx_flow_mse_loss(const void* pred, const void* x0, const void* x1, float* loss, void* dpred, int64_t n,
                      float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * VAE either side of the loop: pipeline_tools.py:7-12 `vae.encode(images).latent_dist.sample()`,
+ * `(z - shift) * scale`; generate.py:375-380 `z / scale + shift`, `vae.decode(z)[0]`, `image_processor.postprocess`.
+ * Third-party arithmetic (diffusers 0.31.0 AutoencoderKL, FLUX.1-dev vae/config.json) restated in oracle/vae.py.
+ * Activations are bf16 rows [B*H*W, C] (NHWC); a convolution = lx_vae_im2col (GroupNorm affine + SiLU + nearest x2
+ * up-sampling + stride folded into the panel write) followed by lx_gemm_bf16 against the [Cout, taps*C] weight panel
+ * (columns ordered (ky, kx, c)); the residual add of ResnetBlock2D / the attention is the GEMM's LX_EPI_GATE_RESIDUAL
+ * epilogue with a gate of ones.
+ * ------------------------------------------------------------------------------------------------------ */
+/* GroupNorm(groups, C, eps) of x [B, hw, C] as per-(sample, channel) affine coefficients:
+ * coeff[b, c] = (a, b) with y = x * a + b, a = gamma[c] * rstd[b, g], b = beta[c] - mean[b, g] * a.
+ * sums: fp64 workspace [B, groups, 2] (zeroed here).  C = 8 * a power of two, <= 2048. */
+int lx_vae_group_norm_coeffs(const void* x, int32_t B, int64_t hw, int32_t C, int32_t groups, const float* gamma,
+                             const float* beta, float eps, double* sums, float* coeff, void* stream);
+typedef struct lx_vae_im2col_desc {
+  const void* x;      /* bf16 [B, H, W, C] */
+  void* out;          /* bf16 [B*Ho*Wo, ldk]; columns [taps*C, ldk) are written as zeros */
+  const float* coeff; /* fp32 [B, C, 2] from lx_vae_group_norm_coeffs, or NULL (no normalisation) */
+  int32_t B, H, W, C; /* C a multiple of 8 */
+  int32_t upsample;   /* 1, or 2 = the convolution sees the nearest-neighbour x2 image (Upsample2D) */
+  int32_t stride;     /* 1, or 2 (Downsample2D) */
+  int32_t pad_lo;     /* zero rows/columns before the image: 1 for padding=1; 0 for Downsample2D's F.pad(x, (0,1,0,1)) */
+  int32_t taps;       /* 9 = 3x3 kernel, 1 = 1x1 (normalised copy) */
+  int32_t silu;       /* apply SiLU after the affine (only with coeff) */
+  int32_t Ho, Wo;     /* output grid */
+  int64_t ldk;        /* multiple of 8, >= taps*C */
+} lx_vae_im2col_desc_t;
+int lx_vae_im2col(const lx_vae_im2col_desc_t* desc, void* stream);
+/* p[r, c] = softmax_c(s[r, :n] * scale) as bf16; columns [n, ldp) are written as zeros (mid-block attention, one head). */
+int lx_vae_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int32_t rows, int32_t n, float scale, void* stream);
+/* fp32 [B, C, hw] -> bf16 rows [B*hw, c_pad] = in * mul + add, channels >= C zero (image / latent entry:
+ * VaeImageProcessor.normalize is mul 2, add -1; generate.py:376-378 is mul 1/scaling_factor, add shift_factor). */
+int lx_vae_nchw_to_rows(const float* in, void* out, int32_t B, int32_t C, int64_t hw, int32_t c_pad, float mul, float add,
+                        void* stream);
+/* fp32 rows [B*hw, ld] -> fp32 [B, C, hw]; denormalize != 0 applies (x / 2 + 0.5).clamp(0, 1) (image_processor.postprocess). */
+int lx_vae_rows_to_nchw(const float* in, int64_t ld, float* out, int32_t B, int32_t C, int64_t hw, int32_t denormalize,
+                        void* stream);
+/* moments rows [B*hw, ld] = [mean(L) | logvar(L)] -> out fp32 [B, L, hw] =
+ * (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps - shift) * scale; eps fp32 [B, L, hw] or NULL (the mode). */
+int lx_vae_sample_latents(const float* moments, int64_t ld, const float* eps, float* out, int32_t B, int32_t L, int64_t hw,
+                          float shift, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

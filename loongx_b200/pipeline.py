@@ -291,6 +291,24 @@ class NativeFluxPipeline:
     def set_adapters(self, *args, **kwargs):  # LoRA adapters are merged into the cond row group at load
         return None
 
+    def attach_vae(self, source=None, seed: int = 1234):
+        """Give the pipeline its `vae` + `image_processor`.  `source`: a FLUX checkpoint directory
+        (reads <dir>/vae), a flat diffusers-named parameter dict, a `VaeWeights`, or None for seeded synthetic
+        parameters of FLUX.1-dev's VAE architecture."""
+        from .vae import ImageProcessor, NativeVae, VaeConfig, VaeWeights, synthetic_params
+
+        if isinstance(source, VaeWeights):
+            w = source
+        elif isinstance(source, str):
+            w = VaeWeights.from_pretrained(source, self.device)
+        else:
+            cfg = VaeConfig()
+            w = VaeWeights(cfg, source if source is not None else synthetic_params(cfg, seed), self.device)
+        self.vae = NativeVae(w)
+        self.vae_scale_factor = 2 ** len(w.cfg.block_out_channels)  # diffusers 0.31.0 FluxPipeline: 16
+        self.image_processor = ImageProcessor(self.vae_scale_factor)
+        return self.vae
+
     @contextlib.contextmanager
     def progress_bar(self, total=None):
         class _Bar:

@@ -201,8 +201,9 @@ def generate(model, pipeline, conditions: List[Condition] = None, config_path: s
         image = latents
     else:
         if pipe.vae is None:
-            raise NotImplementedError("no VAE in this build (SURVEY.md §8f.2): call generate(..., output_type='latent')")
-        z = pipe._unpack_latents(latents, height, width, pipe.vae_scale_factor)
+            raise NotImplementedError("no VAE attached (pipeline.attach_vae, SURVEY.md §8f.2): call "
+                                      "generate(..., output_type='latent')")
+        z = pipe._unpack_latents(latents, height, width, pipe.vae_scale_factor).float()  # fp32 like the reference's VAE
         z = z / pipe.vae.config.scaling_factor + pipe.vae.config.shift_factor
         image = pipe.image_processor.postprocess(pipe.vae.decode(z, return_dict=False)[0], output_type=a["output_type"])
     pipe.maybe_free_model_hooks()

@@ -6,14 +6,14 @@ from torch import Tensor
 def encode_images(pipeline, images: Tensor):
     """pipeline_tools.py:7-30: VAE-encode -> (x - shift) * scale -> _pack_latents -> ids.
 
-    The VAE is outside this build.  Already-encoded latents [B, 16, h, w] are accepted and go through
-    the same native pack kernel and the same id construction, including the reference's diffusers-version fallback for
-    the id grid size (pipeline_tools.py:22-29)."""
-    if pipeline.vae is None:
-        if not (isinstance(images, torch.Tensor) and images.dim() == 4 and images.shape[1] == 16):
-            raise NotImplementedError("no VAE in this build: pass pre-encoded latents [B, 16, h, w]")
+    With a VAE attached (`pipeline.attach_vae(...)`) images go through the native encoder.  Already-encoded
+    latents [B, 16, h, w] are accepted either way and go through the same native pack kernel and the same id
+    construction, including the reference's diffusers-version fallback for the id grid size (pipeline_tools.py:22-29)."""
+    if isinstance(images, torch.Tensor) and images.dim() == 4 and images.shape[1] == 16:
         latents = images.to(pipeline.device).to(pipeline.dtype)
-    else:  # pragma: no cover - needs a VAE implementation
+    elif pipeline.vae is None:
+        raise NotImplementedError("no VAE attached (pipeline.attach_vae): pass pre-encoded latents [B, 16, h, w]")
+    else:
         images = pipeline.image_processor.preprocess(images)
         images = images.to(pipeline.device).to(pipeline.dtype)
         latents = pipeline.vae.encode(images).latent_dist.sample()

@@ -22,7 +22,7 @@ class OminiModel(nn.Module):
                  gradient_checkpointing: bool = False, use_brain_condition: bool = True, fuse_flag: bool = True,
                  seed: int = 1234):
         """`flux_pipe_id`: a FluxConfig (random-init weights of that architecture, seeded) or the string "synthetic"
-        (FLUX.1-dev geometry).  Loading real diffusers / peft checkpoints is SURVEY.md §8f.1 (next)."""
+        (FLUX.1-dev geometry), or a diffusers-format FLUX directory (transformer/ and, when present, vae/)."""
         super().__init__()
         if dtype != torch.bfloat16:
             raise NotImplementedError("the native DiT computes in bf16 (fp32 accumulate); CS3/DGF run in float32")
@@ -56,6 +56,8 @@ class OminiModel(nn.Module):
             self.transformer = NativeFluxTransformer(cfg, device=device, seed=seed)
         self.transformer.gradient_checkpointing = gradient_checkpointing
         self.flux_pipe = NativeFluxPipeline(self.transformer)
+        if pretrained is not None and os.path.isdir(os.path.join(pretrained, "vae")):
+            self.flux_pipe.attach_vae(pretrained)  # FluxPipeline.from_pretrained loads the VAE too (model.py:398-400)
         self.fuse_flag = fuse_flag
         self.use_brain_condition = use_brain_condition
         self.eeg_fixed_length, self.fnirs_fixed_length, self.ppg_fixed_length, self.motion_fixed_length = 4096, 512, 256, 128
