@@ -103,6 +103,10 @@ typedef struct lx_gemm_desc {
   const float* rope; /* fp32 [seq_total, 64, 2] (cos, sin) per rotary pair, NULL = no RoPE */
   float rms_eps;
   int32_t tile_n; /* 0 = choose the N tile (256 / 224 / 192) that minimises wave quantisation; else force it */
+  /* != 0: some W panel is an activation written by an earlier kernel on this stream (e.g. K / V^T of the VAE's
+   * mid-block attention), not a constant weight: the kernel then requests no W tile ahead of its programmatic-dependency
+   * wait.  0 (weights): the first W tiles are prefetched while the previous kernel is still draining. */
+  int32_t w_dynamic;
 } lx_gemm_desc_t;
 
 int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream);
@@ -441,9 +445,11 @@ int lx_flow_mse_loss(const void* pred, const void* x0, const void* x1, float* lo
  * ------------------------------------------------------------------------------------------------------ */
 /* GroupNorm(groups, C, eps) of x [B, hw, C] as per-(sample, channel) affine coefficients:
  * coeff[b, c] = (a, b) with y = x * a + b, a = gamma[c] * rstd[b, g], b = beta[c] - mean[b, g] * a.
- * sums: fp64 workspace [B, groups, 2] (zeroed here).  C = 8 * a power of two, <= 2048. */
+ * workspace: fp64, lx_vae_group_norm_workspace(B, hw, groups) elements (per-chunk partial sums; no zeroing needed, the
+ * reduction order is fixed, so the result is bit-reproducible).  C = 8 * a power of two, <= 2048. */
+int64_t lx_vae_group_norm_workspace(int32_t B, int64_t hw, int32_t groups);
 int lx_vae_group_norm_coeffs(const void* x, int32_t B, int64_t hw, int32_t C, int32_t groups, const float* gamma,
-                             const float* beta, float eps, double* sums, float* coeff, void* stream);
+                             const float* beta, float eps, double* workspace, float* coeff, void* stream);
 typedef struct lx_vae_im2col_desc {
   const void* x;      /* bf16 [B, H, W, C] */
   void* out;          /* bf16 [B*Ho*Wo, ldk]; columns [taps*C, ldk) are written as zeros */

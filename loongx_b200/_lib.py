@@ -58,7 +58,7 @@ class GemmDesc(C.Structure):
         ("heads", c_int32), ("seq_total", c_int32),
         ("rms_q", c_void_p * 3), ("rms_k", c_void_p * 3),
         ("rope", c_void_p),
-        ("rms_eps", c_float), ("tile_n", c_int32),
+        ("rms_eps", c_float), ("tile_n", c_int32), ("w_dynamic", c_int32),
     ]
 
 

@@ -166,7 +166,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nkb = p.num_kb[g];
         // first tile: the W halves of the first min(STAGES, nkb) stages are requested BEFORE the PDL wait (weights do
         // not depend on the previous kernel), the A halves right after it
-        const int n_early = first_tile ? min(STAGES, nkb) : 0;
+        // (w_dynamic: W is an earlier kernel's output, nothing may be requested before the wait)
+        const int n_early = (first_tile && !p.d.w_dynamic) ? min(STAGES, nkb) : 0;
         if (first_tile) {
           for (int kb = 0; kb < n_early; ++kb) {  // stage == kb here, every slot is free
             uint8_t* sa = smem + kb * STAGE_BYTES;

@@ -64,6 +64,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Plain stream-ordered launch (no programmatic overlap with the predecessor).  Needed for the first kernel after a
+// cudaMemsetAsync whose target the kernel accumulates into: with the programmatic attribute the kernel is released by the
+// previous KERNEL's trigger and its griddepcontrol.wait only covers that kernel, so the memset — ordered after that same
+// kernel — can land on top of the first accumulations (observed as run-to-run noise in the VAE's GroupNorm sums).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ordered(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct LaunchScope {
   LaunchScope(int cls, void* stream, double work);  // work: FLOPs (tensor kernels) or bytes (HBM-bound kernels)
   ~LaunchScope();

@@ -736,13 +736,14 @@ extern "C" int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t 
   const unsigned gn = (N + LORA_CCHUNK - 1) / LORA_CCHUNK, gk = (K + LORA_CCHUNK - 1) / LORA_CCHUNK;
   if (r <= 4) {
     const unsigned gm = (M + 31) / 32;  // 4 warps x 8 rows
-    launch_pdl(lora_project_kernel<4, 8>, dim3(gm, gn), dim3(128), 0, st, bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
+    // (the first kernel after the memset is launched stream-ordered, see launch_ordered)
+    launch_ordered(lora_project_kernel<4, 8>, dim3(gm, gn), dim3(128), 0, st, bf(dy), ldy, M, N, Bw, r, 1, r, P1);  // F[c=n, j] = B[n*r + j]
     launch_pdl(lora_project_kernel<4, 8>, dim3(gm, gk), dim3(128), 0, st, bf(x), ldx, M, K, A, 1, K, r, P2);    // F[c=k, j] = A[j*K + k]
     launch_pdl(lora_reduce_kernel<4>, dim3(gr, (K + 511) / 512), dim3(128), 0, st, bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
     launch_pdl(lora_reduce_kernel<4>, dim3(gr, (N + 511) / 512), dim3(128), 0, st, bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);
   } else {
     const unsigned gm = (M + 7) / 8;  // 4 warps x 2 rows
-    launch_pdl(lora_project_kernel<LORA_MAX_R, 2>, dim3(gm, gn), dim3(128), 0, st, bf(dy), ldy, M, N, Bw, r, 1, r, P1);
+    launch_ordered(lora_project_kernel<LORA_MAX_R, 2>, dim3(gm, gn), dim3(128), 0, st, bf(dy), ldy, M, N, Bw, r, 1, r, P1);
     launch_pdl(lora_project_kernel<LORA_MAX_R, 2>, dim3(gm, gk), dim3(128), 0, st, bf(x), ldx, M, K, A, 1, K, r, P2);
     launch_pdl(lora_reduce_kernel<LORA_MAX_R>, dim3(gr, (K + 511) / 512), dim3(128), 0, st, bf(x), ldx, M, K, P1, r, scaling, dA, 1, K);
     launch_pdl(lora_reduce_kernel<LORA_MAX_R>, dim3(gr, (N + 511) / 512), dim3(128), 0, st, bf(dy), ldy, M, N, P2, r, scaling, dB, r, 1);

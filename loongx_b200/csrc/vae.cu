@@ -5,8 +5,8 @@
 // Layout: activations are bf16 rows [B*H*W, C] (NHWC), so every convolution is the tcgen05 GEMM of gemm.cu over an
 // im2col panel [B*Ho*Wo, taps*C] whose columns are ordered (ky, kx, c).  GroupNorm + SiLU — which precede every
 // convolution of a ResnetBlock2D — are folded into the panel write: the normalised activation is never stored.
-// GroupNorm statistics are fp32 partial sums per CTA combined in fp64 (sum and sum of squares; the subtraction
-// E[x^2] - mean^2 happens in fp64).  All kernels here are HBM / L2-bound: 16-byte accesses, each operand touched once
+// GroupNorm statistics are fp32 partial sums per thread combined in fp64 in a fixed order (sum and sum of squares; the
+// subtraction E[x^2] - mean^2 happens in fp64): the whole VAE is bit-reproducible run to run.  All kernels here are HBM / L2-bound: 16-byte accesses, each operand touched once
 // (the nine taps of a panel re-read the activation through L2).
 #include "host_util.cuh"
 #include "ptx.cuh"
@@ -21,23 +21,35 @@ __device__ __forceinline__ void vld8(const __nv_bfloat16* p, float* x) {
   x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
 }
 
+// SiLU as 0.5 x (1 + tanh(x / 2)): one MUFU op per element (the panel write applies it once per tap, nine times per
+// activation element, so exp + IEEE division would make the kernel MUFU-bound); tanh.approx is good to ~2^-11, the
+// result is stored in bf16.
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return 0.5f * x * (1.0f + t);
+}
+
 inline cudaStream_t vcs(void* s) { return static_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics.  grid (row chunks, B), 256 threads; thread = (row lane, 8-channel vector).
+// GroupNorm statistics, two deterministic stages (no atomics, nothing to zero):
+//   gn_stats_kernel     grid (row chunks, B), 256 threads; thread = (row lane, 8-channel vector).  fp32 partial sums per
+//                       thread over <= 512/lanes rows, combined through shared memory in a fixed order into one fp64
+//                       (sum, sum of squares) per (sample, chunk, group).
+//   gn_finalize_kernel  one CTA per (sample, group): fixed-order fp64 reduction over the chunks, then the per-channel
+//                       affine coefficients.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
 constexpr int GN_ROWS_PER_CTA = 512;
 
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ sums,
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ part,
                                                               long long hw, int C, int groups) {
-  extern __shared__ float gn_sh[];  // [2][C]
+  __shared__ float sh_s[GN_THREADS * 8], sh_q[GN_THREADS * 8];  // [row lane][channel] (lanes * C = 2048 floats each)
   pdl_wait();
   pdl_launch_dependents();
   const int vec = C / 8, lanes = GN_THREADS / vec;
   const int v = threadIdx.x % vec, r0 = threadIdx.x / vec;
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) gn_sh[i] = 0.f;
-  __syncthreads();
   const long long row_begin = (long long)blockIdx.x * GN_ROWS_PER_CTA;
   const long long row_end = min(hw, row_begin + GN_ROWS_PER_CTA);
   const __nv_bfloat16* xb = x + (size_t)blockIdx.y * hw * C + v * 8;
@@ -55,43 +67,65 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    atomicAdd(&gn_sh[v * 8 + e], s[e]);
-    atomicAdd(&gn_sh[C + v * 8 + e], q[e]);
+    sh_s[r0 * C + v * 8 + e] = s[e];
+    sh_q[r0 * C + v * 8 + e] = q[e];
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
     double a = 0.0, b = 0.0;
-    for (int c = 0; c < cpg; ++c) {
-      a += (double)gn_sh[g * cpg + c];
-      b += (double)gn_sh[C + g * cpg + c];
-    }
-    atomicAdd(&sums[((size_t)blockIdx.y * groups + g) * 2], a);
-    atomicAdd(&sums[((size_t)blockIdx.y * groups + g) * 2 + 1], b);
+    for (int l = 0; l < lanes; ++l)
+      for (int c = 0; c < cpg; ++c) {
+        a += (double)sh_s[l * C + g * cpg + c];
+        b += (double)sh_q[l * C + g * cpg + c];
+      }
+    double* dst = part + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 
-// (sum, sum of squares) -> per (sample, channel) affine coefficients: y = x * a + b, a = gamma * rstd, b = beta - mean * a
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float2* __restrict__ coeff, int B, long long hw, int C,
-                                   int groups, float eps) {
+// per (sample, group): sum the chunk partials, then y = x * a + b with a = gamma * rstd, b = beta - mean * a
+__global__ void __launch_bounds__(GN_THREADS) gn_finalize_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float2* __restrict__ coeff,
+                                                                 int chunks, long long hw, int C, int groups, float eps) {
+  __shared__ double sh[2][GN_THREADS];
   pdl_wait();
   pdl_launch_dependents();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * C) return;
-  const int b = idx / C, c = idx % C, cpg = C / groups, g = c / cpg;
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups, cpg = C / groups;
+  double a = 0.0, q = 0.0;
+  for (int ch = threadIdx.x; ch < chunks; ch += GN_THREADS) {
+    const double* src = part + (((size_t)b * chunks + ch) * groups + g) * 2;
+    a += src[0];
+    q += src[1];
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = GN_THREADS / 2; o > 0; o >>= 1) {  // fixed tree: deterministic
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
   const double n = (double)hw * cpg;
-  const double mean = sums[((size_t)b * groups + g) * 2] / n;
-  double var = sums[((size_t)b * groups + g) * 2 + 1] / n - mean * mean;
+  const double mean = sh[0][0] / n;
+  double var = sh[1][0] / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float a = gamma[c] * rstd;
-  coeff[idx] = make_float2(a, beta[c] - (float)mean * a);
+  for (int c = threadIdx.x; c < cpg; c += GN_THREADS) {
+    const int cc = g * cpg + c;
+    const float ga = gamma[cc] * rstd;
+    coeff[(size_t)b * C + cc] = make_float2(ga, beta[cc] - (float)mean * ga);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // im2col panel write with the optional GroupNorm affine + SiLU, nearest x2 up-sampling and stride.
-// thread = (output pixel m, 8-element vector j of the panel row); j -> (tap, channel vector).
+// Thread block = (16-byte vectors of one panel row, rows): threadIdx.y picks the output pixel, threadIdx.x the vector
+// j -> (tap, channel vector), so the only integer divisions are the two that decode the pixel (the channel-vector count
+// is a power of two for every FLUX layer and becomes a shift).
 // ---------------------------------------------------------------------------------------------------------------
 struct Im2col {
   const __nv_bfloat16* x;
@@ -100,52 +134,63 @@ struct Im2col {
   int H, W, C;          // stored input
   int up_shift;         // 0: as stored, 1: nearest x2 virtual image
   int Ho, Wo, stride, pad_lo, taps, silu;
-  long long ldk, total;  // total = M * ldk / 8
+  int M;         // output pixels = panel rows
+  int kv;        // 16-byte vectors per panel row (ldk / 8)
+  int cv_shift;  // log2(C / 8), or -1 when C / 8 is not a power of two
+  long long ldk;
 };
 
-__global__ void __launch_bounds__(256) im2col_kernel(const Im2col p) {
+__global__ void __launch_bounds__(1024) im2col_kernel(const Im2col p) {
   pdl_wait();
   pdl_launch_dependents();
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= p.total) return;
-  const int kv = (int)(p.ldk / 8), cv = p.C / 8;
-  const long long m = idx / kv;
-  const int j = (int)(idx % kv);
-  const int tap = j / cv, v = j % cv;
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if (tap < p.taps) {
-    const int hwo = p.Ho * p.Wo;
-    const int b = (int)(m / hwo), rem = (int)(m % hwo);
-    const int oy = rem / p.Wo, ox = rem % p.Wo;
-    const int ky = p.taps == 9 ? tap / 3 : 0, kx = p.taps == 9 ? tap % 3 : 0;
-    const int iy = oy * p.stride + ky - p.pad_lo, ix = ox * p.stride + kx - p.pad_lo;
-    if (iy >= 0 && ix >= 0 && iy < (p.H << p.up_shift) && ix < (p.W << p.up_shift)) {
-      const int sy = iy >> p.up_shift, sx = ix >> p.up_shift;
-      const __nv_bfloat16* src = p.x + (((size_t)b * p.H + sy) * p.W + sx) * p.C + v * 8;
-      if (p.coeff == nullptr) {
-        o = *reinterpret_cast<const uint4*>(src);
-      } else {
-        float t[8];
-        vld8(src, t);
-        const float4* cf = reinterpret_cast<const float4*>(p.coeff + (size_t)b * p.C + v * 8);
+  const int m = blockIdx.x * blockDim.y + threadIdx.y;
+  if (m >= p.M) return;
+  const int hwo = p.Ho * p.Wo;
+  const int b = m / hwo, rem = m - b * hwo;
+  const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+  const int cv = p.C / 8;
+  __nv_bfloat16* orow = p.out + (size_t)m * p.ldk;
+  for (int j = threadIdx.x; j < p.kv; j += blockDim.x) {
+    int tap, v;
+    if (p.cv_shift >= 0) {
+      tap = j >> p.cv_shift;
+      v = j & (cv - 1);
+    } else {
+      tap = j / cv;
+      v = j - tap * cv;
+    }
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (tap < p.taps) {
+      const int ky = p.taps == 9 ? tap / 3 : 0, kx = p.taps == 9 ? tap - 3 * ky : 0;
+      const int iy = oy * p.stride + ky - p.pad_lo, ix = ox * p.stride + kx - p.pad_lo;
+      if (iy >= 0 && ix >= 0 && iy < (p.H << p.up_shift) && ix < (p.W << p.up_shift)) {
+        const int sy = iy >> p.up_shift, sx = ix >> p.up_shift;
+        const __nv_bfloat16* src = p.x + (((size_t)b * p.H + sy) * p.W + sx) * p.C + v * 8;
+        if (p.coeff == nullptr) {
+          o = *reinterpret_cast<const uint4*>(src);
+        } else {
+          float t[8];
+          vld8(src, t);
+          const float4* cf = reinterpret_cast<const float4*>(p.coeff + (size_t)b * p.C + v * 8);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4 ab = __ldg(cf + e);  // (a, b) of two channels
-          t[2 * e] = fmaf(t[2 * e], ab.x, ab.y);
-          t[2 * e + 1] = fmaf(t[2 * e + 1], ab.z, ab.w);
-        }
-        if (p.silu) {
+          for (int e = 0; e < 4; ++e) {
+            const float4 ab = __ldg(cf + e);  // (a, b) of two channels
+            t[2 * e] = fmaf(t[2 * e], ab.x, ab.y);
+            t[2 * e + 1] = fmaf(t[2 * e + 1], ab.z, ab.w);
+          }
+          if (p.silu) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) t[e] = t[e] / (1.0f + __expf(-t[e]));
+            for (int e = 0; e < 8; ++e) t[e] = silu_tanh(t[e]);
+          }
+          o.x = pack_bf16(t[0], t[1]);
+          o.y = pack_bf16(t[2], t[3]);
+          o.z = pack_bf16(t[4], t[5]);
+          o.w = pack_bf16(t[6], t[7]);
         }
-        o.x = pack_bf16(t[0], t[1]);
-        o.y = pack_bf16(t[2], t[3]);
-        o.z = pack_bf16(t[4], t[5]);
-        o.w = pack_bf16(t[6], t[7]);
       }
     }
+    *reinterpret_cast<uint4*>(orow + (size_t)j * 8) = o;
   }
-  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldk + (size_t)j * 8) = o;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -251,18 +296,22 @@ __global__ void sample_latents_kernel(const float* __restrict__ mom, long long l
 
 using namespace lx;
 
+extern "C" int64_t lx_vae_group_norm_workspace(int32_t B, int64_t hw, int32_t groups) {
+  return 2 * (int64_t)B * ((hw + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA) * groups;
+}
+
 extern "C" int lx_vae_group_norm_coeffs(const void* x, int32_t B, int64_t hw, int32_t C, int32_t groups, const float* gamma,
-                                        const float* beta, float eps, double* sums, float* coeff, void* stream) {
-  LX_CHECK_ARG(x && gamma && beta && sums && coeff && B > 0 && hw > 0, "lx_vae_group_norm_coeffs: null argument or empty input");
+                                        const float* beta, float eps, double* workspace, float* coeff, void* stream) {
+  LX_CHECK_ARG(x && gamma && beta && workspace && coeff && B > 0 && hw > 0, "lx_vae_group_norm_coeffs: null argument or empty input");
   LX_CHECK_ARG(C >= 8 && C % 8 == 0 && GN_THREADS % (C / 8) == 0 && groups > 0 && C % groups == 0 && groups <= GN_THREADS,
                "lx_vae_group_norm_coeffs: C=%d must be 8 * a power of two <= 2048 and divisible by groups=%d", C, groups);
-  LX_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * groups, vcs(stream)));
+  const long long chunks = (hw + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA;
+  LX_CHECK_ARG(chunks < 65536 * 32, "lx_vae_group_norm_coeffs: hw=%lld too large", (long long)hw);
   LaunchScope scope(KC_ROW, stream, 2.0 * B * (double)hw * C);
-  const unsigned chunks = (unsigned)((hw + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA);
-  LX_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(GN_THREADS), 2 * C * sizeof(float), vcs(stream),
-                     reinterpret_cast<const __nv_bfloat16*>(x), sums, (long long)hw, C, groups));
-  LX_CUDA(launch_pdl(gn_finalize_kernel, dim3((B * C + 255) / 256), dim3(256), 0, vcs(stream), (const double*)sums, gamma, beta,
-                     reinterpret_cast<float2*>(coeff), B, (long long)hw, C, groups, eps));
+  LX_CUDA(launch_pdl(gn_stats_kernel, dim3((unsigned)chunks, B), dim3(GN_THREADS), 0, vcs(stream),
+                     reinterpret_cast<const __nv_bfloat16*>(x), workspace, (long long)hw, C, groups));
+  LX_CUDA(launch_pdl(gn_finalize_kernel, dim3(B * groups), dim3(GN_THREADS), 0, vcs(stream), (const double*)workspace, gamma, beta,
+                     reinterpret_cast<float2*>(coeff), (int)chunks, (long long)hw, C, groups, eps));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -290,10 +339,16 @@ extern "C" int lx_vae_im2col(const lx_vae_im2col_desc_t* d, void* stream) {
   p.Ho = d->Ho; p.Wo = d->Wo; p.stride = d->stride; p.pad_lo = d->pad_lo; p.taps = d->taps; p.silu = d->silu;
   p.ldk = d->ldk;
   const long long M = (long long)d->B * d->Ho * d->Wo;
-  p.total = M * (d->ldk / 8);
-  LX_CHECK_ARG((p.total + 255) / 256 < (1LL << 31), "lx_vae_im2col: panel too large for one launch");
+  LX_CHECK_ARG(M < (1LL << 31) && d->ldk / 8 < (1LL << 31), "lx_vae_im2col: panel too large for one launch");
+  p.M = (int)M;
+  p.kv = (int)(d->ldk / 8);
+  const int cv = d->C / 8;
+  p.cv_shift = -1;
+  for (int sft = 0; sft < 20; ++sft)
+    if ((1 << sft) == cv) p.cv_shift = sft;
+  const int tx = min((p.kv + 31) / 32 * 32, 1024), ty = max(1, 1024 / tx);
   LaunchScope scope(KC_ROW, stream, 2.0 * d->B * (double)d->H * d->W * d->C + 2.0 * M * (double)d->ldk);
-  LX_CUDA(launch_pdl(im2col_kernel, dim3((unsigned)((p.total + 255) / 256)), dim3(256), 0, vcs(stream), p));
+  LX_CUDA(launch_pdl(im2col_kernel, dim3((unsigned)((M + ty - 1) / ty)), dim3(tx, ty), 0, vcs(stream), p));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

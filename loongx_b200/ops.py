@@ -60,6 +60,7 @@ def gemm(
     rope: Optional[torch.Tensor] = None,
     rms_eps: float = 1e-6,
     tile_n: int = 0,
+    w_dynamic: bool = False,  # W is an activation written by an earlier kernel (no W prefetch ahead of the PDL wait)
 ) -> None:
     """C = epilogue(A[M,K] @ W[N,K]^T); A / W are 2-D bf16 views with unit inner stride.  `groups` adds row groups
     (rows >= m_begin use that weight panel / bias instead)."""
@@ -109,6 +110,7 @@ def gemm(
         d.rope = _ptr(rope)
     d.rms_eps = rms_eps
     d.tile_n = tile_n
+    d.w_dynamic = int(bool(w_dynamic))
     L.check(L.lib.lx_gemm_bf16(C.byref(d), _stream()), "lx_gemm_bf16")
 
 

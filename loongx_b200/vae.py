@@ -32,6 +32,8 @@ class Im2colDesc(C.Structure):
 
 _lib.lx_vae_group_norm_coeffs.argtypes = [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p,
                                           c_void_p, c_void_p]
+_lib.lx_vae_group_norm_workspace.argtypes = [c_int32, c_int64, c_int32]
+_lib.lx_vae_group_norm_workspace.restype = c_int64
 _lib.lx_vae_im2col.argtypes = [C.POINTER(Im2colDesc), c_void_p]
 _lib.lx_vae_softmax_rows.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]
 _lib.lx_vae_nchw_to_rows.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, c_float, c_float, c_void_p]
@@ -322,7 +324,7 @@ class NativeVae:
         gamma, beta = self.w.norm[norm]
         assert gamma.numel() == a.C, f"{norm}: {gamma.numel()} channels, activation has {a.C}"
         g = self.cfg.norm_num_groups
-        sums = torch.empty(a.B, g, 2, dtype=torch.float64, device=self.device)
+        sums = torch.empty(_lib.lx_vae_group_norm_workspace(a.B, a.H * a.W, g), dtype=torch.float64, device=self.device)
         coeff = torch.empty(a.B, a.C, 2, dtype=torch.float32, device=self.device)
         L.check(_lib.lx_vae_group_norm_coeffs(_cuda(a.x), a.B, a.H * a.W, a.C, g, _cuda(gamma), _cuda(beta), self.cfg.eps,
                                               _cuda(sums), _cuda(coeff), _stream()), "lx_vae_group_norm_coeffs")
@@ -391,12 +393,12 @@ class NativeVae:
         for b in range(B):
             r0 = b * hw
             q, k, v = qkv[r0:r0 + hw, :Cc], qkv[r0:r0 + n_pad, Cc:2 * Cc], qkv[r0:r0 + hw, 2 * Cc:]
-            ops.gemm(q, k, None, S, L.EPI_BIAS_F32)
+            ops.gemm(q, k, None, S, L.EPI_BIAS_F32, w_dynamic=True)  # W = this sample's keys
             L.check(_lib.lx_vae_softmax_rows(_cuda(S), S.stride(0), _cuda(Pm), Pm.stride(0), hw, hw, float(Cc) ** -0.5,
                                              _stream()), "lx_vae_softmax_rows")
             L.check(_lib.lx_transpose_bf16(_cuda(v), v.stride(0), _cuda(vT), vT.stride(0), hw, Cc, _stream()),
                     "lx_transpose_bf16")
-            ops.gemm(Pm, vT, None, attn[r0:r0 + hw], L.EPI_BIAS)
+            ops.gemm(Pm, vT, None, attn[r0:r0 + hw], L.EPI_BIAS, w_dynamic=True)  # W = V^T
         self.launches += 1 + 4 * B
         return _Act(self._gemm(attn, out_w, residual=a.x), B, a.H, a.W)
 

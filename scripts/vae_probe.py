@@ -31,6 +31,9 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     z = torch.randn(B, 16, px // 8, px // 8, generator=g, device="cuda")
     img = torch.rand(B, 3, px, px, generator=g, device="cuda") * 2 - 1
+    a, b = v.decode(z).sample, v.decode(z).sample
+    print(f"[vae determinism] LX_PDL={os.environ.get('LX_PDL', '1')}: two decodes bit-identical: {torch.equal(a, b)}, "
+          f"relL2 {((a - b).norm() / b.norm()).item():.3g}")
     for name, fn in (("decode", lambda: v.decode(z)), ("encode", lambda: v.encode(img).latent_dist.mode())):
         ms = timed(fn)
         v.launches = 0

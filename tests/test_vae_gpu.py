@@ -77,7 +77,7 @@ def test_im2col_panels(vae, case):
         want = cols.reshape(B, Cc, 9, L).permute(0, 3, 2, 1).reshape(B * L, 9 * Cc)  # -> (ky, kx, c)
         assert L == Ho * Wo
     assert panel.shape == (want.shape[0], ldk)
-    tol = 0.0 if coeff is None else 2e-2
+    tol = 0.0 if coeff is None else 3e-2  # bf16 rounding of values up to ~6, SiLU through tanh.approx
     assert (panel[:, :taps * Cc].float() - want).abs().max().item() <= tol
     assert (panel[:, taps * Cc:] == 0).all()
 
@@ -125,6 +125,7 @@ def test_decode_matches_the_oracle(vae, shape):
     want = O.decode_raw(P, z, ocfg)
     got = v.decode(z.cuda(), return_dict=False)[0]
     assert got.shape == want.shape and got.dtype == torch.float32
+    print(f"\n[vae decode {shape}] relL2 vs oracle {_rel(got, want):.3g}")
     assert _rel(got, want) <= 3e-2, _rel(got, want)
     img_err = (O.postprocess_pt(got.cpu()) - O.postprocess_pt(want)).abs().mean().item()
     assert img_err < 2 / 255, img_err
@@ -141,6 +142,7 @@ def test_encode_matches_the_oracle(vae, shape):
     rows, nb, h, w = v.encode_moments(img.cuda())
     got_m = rows.reshape(B, h, w, 32).permute(0, 3, 1, 2)
     assert (nb, h, w) == (B, H // 8, W // 8)
+    print(f"\n[vae encode {shape}] relL2 vs oracle {_rel(got_m, want_m):.3g}")
     assert _rel(got_m, want_m) <= 3e-2, _rel(got_m, want_m)
     dist = v.encode(img.cuda()).latent_dist
     assert _rel(dist.mode(), want_m[:, :16]) <= 3e-2
@@ -148,8 +150,10 @@ def test_encode_matches_the_oracle(vae, shape):
     eps = torch.randn(B, 16, h, w, generator=gen, device="cuda")
     gen.manual_seed(5)
     z = dist.sample(gen)
-    want_z = O.sample_latents(got_m.cpu(), eps.cpu())  # same moments, same noise: checks the sampling arithmetic
+    own_m = dist._m.reshape(B, h, w, 32).permute(0, 3, 1, 2)  # the moments this distribution holds
+    want_z = O.sample_latents(own_m.cpu(), eps.cpu())  # same moments, same noise: checks the sampling arithmetic
     assert torch.allclose(z.cpu(), want_z, rtol=1e-4, atol=1e-4)
+    assert torch.equal(own_m, got_m)  # two passes over the same input are bit-identical (fixed reduction orders)
 
 
 def test_batch_split_and_full_size_decode(vae):
@@ -166,8 +170,12 @@ def test_batch_split_and_full_size_decode(vae):
         one = v.decode(z, return_dict=False)[0]
     finally:
         v.PANEL_BYTES = keep
-    # GroupNorm statistics are combined with fp64 atomics, so two passes agree to fp32 rounding, not bit for bit
-    assert _rel(one, both) < 1e-3
+    again = v.decode(z, return_dict=False)[0]
+    print(f"\n[vae 512x512] split vs joint {_rel(one, both):.3g}, run to run {_rel(again, both):.3g}")
+    # every reduction has a fixed order (no atomics): bit-reproducible run to run, and a sample does not depend on its
+    # batch neighbours
+    assert torch.equal(again, both)
+    assert _rel(one, both) < 1e-3, _rel(one, both)
     assert v.launches > 0
 
 
