@@ -193,6 +193,62 @@ __global__ void __launch_bounds__(1024) im2col_kernel(const Im2col p) {
   }
 }
 
+// Scatter form of the same panel for the common case (3x3 kernel, ldk == 9 C): thread = (padded input pixel, channel
+// vector).  The activation element is loaded, normalised and passed through SiLU ONCE and stored to the (up to) nine
+// panel slots it occupies; the zero border is written by the threads of the padding pixels, so every (row, tap) slot is
+// written exactly once and nothing is pre-zeroed.  Per 16-byte store this is ~1/9 of the gather form's arithmetic and L1
+// traffic, which leaves the kernel bound by the panel write itself.
+__global__ void __launch_bounds__(1024) im2col_scatter_kernel(const Im2col p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int Hv = p.H << p.up_shift, Wv = p.W << p.up_shift;  // the image the convolution sees
+  const int Hp = Hv + 2, Wp = Wv + 2;                         // with one padding pixel on every side
+  const long long pp = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const int b = (int)(pp / ((long long)Hp * Wp));
+  if (b >= p.M) return;  // (p.M holds the batch size in this kernel)
+  const int rem = (int)(pp - (long long)b * Hp * Wp);
+  const int py = rem / Wp - 1, px = rem - (py + 1) * Wp - 1;
+  const int v = threadIdx.x;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (py >= 0 && py < Hv && px >= 0 && px < Wv) {
+    const __nv_bfloat16* src = p.x + (((size_t)b * p.H + (py >> p.up_shift)) * p.W + (px >> p.up_shift)) * p.C + v * 8;
+    if (p.coeff == nullptr) {
+      o = *reinterpret_cast<const uint4*>(src);
+    } else {
+      float t[8];
+      vld8(src, t);
+      const float4* cf = reinterpret_cast<const float4*>(p.coeff + (size_t)b * p.C + v * 8);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 ab = __ldg(cf + e);
+        t[2 * e] = fmaf(t[2 * e], ab.x, ab.y);
+        t[2 * e + 1] = fmaf(t[2 * e + 1], ab.z, ab.w);
+      }
+      if (p.silu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = silu_tanh(t[e]);
+      }
+      o.x = pack_bf16(t[0], t[1]);
+      o.y = pack_bf16(t[2], t[3]);
+      o.z = pack_bf16(t[4], t[5]);
+      o.w = pack_bf16(t[6], t[7]);
+    }
+  }
+  const int smask = p.stride - 1, sshift = p.stride >> 1;  // stride 1 or 2
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ty = py + p.pad_lo - ky;
+    if (ty < 0 || (ty & smask) || (ty >> sshift) >= p.Ho) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int tx = px + p.pad_lo - kx;
+      if (tx < 0 || (tx & smask) || (tx >> sshift) >= p.Wo) continue;
+      const size_t row = ((size_t)b * p.Ho + (ty >> sshift)) * p.Wo + (tx >> sshift);
+      *reinterpret_cast<uint4*>(p.out + row * p.ldk + (size_t)(ky * 3 + kx) * p.C + v * 8) = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Row softmax of the mid-block attention (one head of width C over H*W positions): fp32 logits -> bf16 probabilities.
 // One CTA per row; three passes over a row that stays in L1/L2 (<= 64 KB).
@@ -296,6 +352,10 @@ __global__ void sample_latents_kernel(const float* __restrict__ mom, long long l
 
 using namespace lx;
 
+static int g_im2col_force_gather = 0;
+// development / test knob: 1 = always use the gather form of the panel kernel
+extern "C" void lx_debug_vae_im2col_gather(int on) { g_im2col_force_gather = on; }
+
 extern "C" int64_t lx_vae_group_norm_workspace(int32_t B, int64_t hw, int32_t groups) {
   return 2 * (int64_t)B * ((hw + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA) * groups;
 }
@@ -346,9 +406,18 @@ extern "C" int lx_vae_im2col(const lx_vae_im2col_desc_t* d, void* stream) {
   p.cv_shift = -1;
   for (int sft = 0; sft < 20; ++sft)
     if ((1 << sft) == cv) p.cv_shift = sft;
-  const int tx = min((p.kv + 31) / 32 * 32, 1024), ty = max(1, 1024 / tx);
   LaunchScope scope(KC_ROW, stream, 2.0 * d->B * (double)d->H * d->W * d->C + 2.0 * M * (double)d->ldk);
-  LX_CUDA(launch_pdl(im2col_kernel, dim3((unsigned)((M + ty - 1) / ty)), dim3(tx, ty), 0, vcs(stream), p));
+  if (d->taps == 9 && d->ldk == 9LL * d->C && cv <= 1024 && !g_im2col_force_gather) {
+    // scatter form: one thread per (padded input pixel, channel vector)
+    const int ty = max(1, 1024 / cv);
+    const long long pixels = (long long)d->B * ((d->H << p.up_shift) + 2) * ((d->W << p.up_shift) + 2);
+    LX_CHECK_ARG((pixels + ty - 1) / ty < (1LL << 31), "lx_vae_im2col: input too large for one launch");
+    p.M = d->B;
+    LX_CUDA(launch_pdl(im2col_scatter_kernel, dim3((unsigned)((pixels + ty - 1) / ty)), dim3(cv, ty), 0, vcs(stream), p));
+  } else {
+    const int tx = min((p.kv + 31) / 32 * 32, 1024), ty = max(1, 1024 / tx);
+    LX_CUDA(launch_pdl(im2col_kernel, dim3((unsigned)((M + ty - 1) / ty)), dim3(tx, ty), 0, vcs(stream), p));
+  }
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -46,8 +46,21 @@ def test_group_norm_coefficients(vae):
         assert (got - want).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("gather", [False, True])
 @pytest.mark.parametrize("case", ["same", "up", "down", "odd_down", "norm_silu", "one_tap_norm"])
-def test_im2col_panels(vae, case):
+def test_im2col_panels(vae, case, gather):
+    """Both forms of the panel kernel (scatter: thread per input pixel, used when ldk == 9 C; gather: thread per panel
+    vector) against torch's unfold."""
+    from loongx_b200.vae import _lib
+
+    _lib.lx_debug_vae_im2col_gather(int(gather))
+    try:
+        _check_panel(vae, case)
+    finally:
+        _lib.lx_debug_vae_im2col_gather(0)
+
+
+def _check_panel(vae, case):
     v, _ = vae
     from loongx_b200.vae import _Act
 
