@@ -64,10 +64,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// Plain stream-ordered launch (no programmatic overlap with the predecessor).  Needed for the first kernel after a
-// cudaMemsetAsync whose target the kernel accumulates into: with the programmatic attribute the kernel is released by the
-// previous KERNEL's trigger and its griddepcontrol.wait only covers that kernel, so the memset — ordered after that same
-// kernel — can land on top of the first accumulations (observed as run-to-run noise in the VAE's GroupNorm sums).
+// Plain stream-ordered launch (no programmatic overlap with the predecessor).  Used, defensively, for the first kernel
+// after a cudaMemsetAsync whose target the kernel accumulates into.  (A first version of the VAE's GroupNorm statistics
+// - memset + atomics under programmatic launch - showed percent-level run-to-run noise; scripts/pdl_order_probe.cu did
+// NOT reproduce a memset / kernel reordering in isolation, so the cause is not established.  The VAE now has no memset
+// and no atomics and is bit-reproducible; this launcher keeps the remaining memset + accumulate site on plain ordering.)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ordered(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
