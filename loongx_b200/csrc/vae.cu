@@ -35,13 +35,13 @@ inline cudaStream_t vcs(void* s) { return static_cast<cudaStream_t>(s); }
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics, two deterministic stages (no atomics, nothing to zero):
 //   gn_stats_kernel     grid (row chunks, B), 256 threads; thread = (row lane, 8-channel vector).  fp32 partial sums per
-//                       thread over <= 512/lanes rows, combined through shared memory in a fixed order into one fp64
+//                       thread over <= 128/lanes rows, combined through shared memory in a fixed order into one fp64
 //                       (sum, sum of squares) per (sample, chunk, group).
 //   gn_finalize_kernel  one CTA per (sample, group): fixed-order fp64 reduction over the chunks, then the per-channel
 //                       affine coefficients.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
-constexpr int GN_ROWS_PER_CTA = 512;
+constexpr int GN_ROWS_PER_CTA = 128;  // many small CTAs: the kernel is latency-bound with few loads in flight per thread
 
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ part,
                                                               long long hw, int C, int groups) {
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+#pragma unroll 4
   for (long long r = row_begin + r0; r < row_end; r += lanes) {
     float t[8];
     vld8(xb + (size_t)r * C, t);
