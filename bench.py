@@ -412,6 +412,103 @@ def run_train(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# VAE workload (extra, not the headline metric): latents -> pixels either side of the loop
+# --------------------------------------------------------------------------------------------------------------------
+def run_vae(args, rank, local_rank, world):
+    import ctypes as C
+
+    from loongx_b200 import _lib as L
+    from loongx_b200.vae import NativeVae, VaeConfig, VaeWeights, synthetic_params
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    B, side = args.batch, RES // 8
+    cfg = VaeConfig()
+    P = synthetic_params(cfg, 1234)
+    vae = NativeVae(VaeWeights(cfg, P, dev))
+    g = torch.Generator().manual_seed(11 + rank)
+    z_host = torch.randn(B, 16, side, side, generator=g).pin_memory()
+    img_host = torch.empty(B, 3, RES, RES, dtype=torch.float32).pin_memory()
+    z_dev = z_host.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        secs = e0.elapsed_time(e1) / 1e3
+        if world > 1:
+            t = torch.tensor([secs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return secs
+
+    def e2e_step():
+        img_host.copy_(vae.decode(z_host.to(dev, non_blocking=True), return_dict=False)[0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    L.lib.lx_launch_count_reset()
+    secs = timed(lambda: vae.decode(z_dev, return_dict=False))
+    launches = int(L.lib.lx_launch_count(-1)) * args.steps // (args.steps + args.warmup)
+    clk = clocks.stop()
+    secs_e2e = timed(e2e_step)
+    L.lib.lx_profile_begin()
+    vae.decode(z_dev, return_dict=False)
+    ms, n, w = (C.c_double * 4)(), (C.c_int64 * 4)(), (C.c_double * 4)()
+    L.lib.lx_profile_end(ms, n, w)
+    peaks = load_peaks()
+    if rank == 0:
+        out = {
+            "metric": "512x512 VAE decodes/sec", "value": world * B * args.steps / secs, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "FLUX.1-dev AutoencoderKL decoder (generate.py:375-380), latents [B,16,64,64] -> image "
+                                   "[B,3,512,512], seeded synthetic weights", "batch_per_gpu": B, "global_batch": B * world,
+                       "l2": "each decode writes and re-reads 10.5 GB of im2col panels per sample (>> 126 MB L2)"},
+            "e2e": {"value": world * B * args.steps / secs_e2e, "unit": "images/s", "h2d_bytes_per_step": z_host.numel() * 4,
+                    "d2h_bytes_per_step": img_host.numel() * 4, "api": "pipeline.vae.decode(z) with pinned host latents, image copied to host"},
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "lx::im2col_scatter_kernel + GroupNorm statistics (VAE row kernels)",
+                         "achieved": w[2] / max(ms[2], 1e-9) / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": w[2] / max(ms[2], 1e-9) / 1e6 / peaks["hbm"], "traffic": None, "peak_source": peaks["which"],
+                         "share_of_step": ms[2] / max(ms[0] + ms[2], 1e-9),
+                         "method": "CUDA events around every launch of one extra decode (lx_profile_*)"},
+            "kernels": {"gemm_bf16_kernel": {"ms": ms[0], "launches": int(n[0]), "achieved_tflops": w[0] / max(ms[0], 1e-9) / 1e9},
+                        "vae_row_kernels": {"ms": ms[2], "launches": int(n[2])}},
+        }
+        if not args.no_cpu_baseline:
+            from oracle import vae as OV
+
+            torch.set_num_threads(os.cpu_count() or 1)
+            zs = z_host[:1, :, :side // 2, :side // 2].clone()
+            OV.decode_raw(P, zs, OV.VaeConfig())
+            t0 = time.perf_counter()
+            OV.decode_raw(P, zs, OV.VaeConfig())
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": 1.0 / (4 * dt), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": f"oracle/vae.py decode of one 256x256 image in fp32 ({dt:.2f} s), x4 pixels extrapolated"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -420,8 +517,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="edits per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="edit", choices=["edit", "train"],
-                    help="edit = the headline metric (default); train = BASELINE.json configs[4] (extra, not the headline)")
+    ap.add_argument("--workload", default="edit", choices=["edit", "train", "vae"],
+                    help="edit = the headline metric (default); train = BASELINE.json configs[4]; vae = the decoder either side "
+                         "of the loop (extras, not the headline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -433,6 +531,9 @@ def main():
         raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
     if args.workload == "train":
         run_train(args, rank, local_rank, world)
+        return
+    if args.workload == "vae":
+        run_vae(args, rank, local_rank, world)
         return
     run_native(args, rank, local_rank, world)
 

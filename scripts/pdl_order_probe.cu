@@ -34,6 +34,29 @@ __global__ void check_sum(const int* acc, int expect, int* bad) {
   if (s != expect) atomicAdd(bad, 1);
 }
 
+// case 3: the primary accumulates with fire-and-forget reductions (RED); the dependent reads the sums after its wait,
+// through ordinary loads or through the non-coherent path (const __restrict__ / __ldg)
+__global__ void fill_d(double* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+__global__ void red_primary(double* acc, float* sink, int spin) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+  float x = threadIdx.x;
+  for (int i = 0; i < spin * (1 + (blockIdx.x & 3)); ++i) x = x * 1.0001f + 0.5f;
+  if (x == 123.f) sink[0] = x;
+  atomicAdd(&acc[threadIdx.x & 63], 1.0);
+}
+__global__ void red_check(const double* acc, double expect, int* bad) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x < 64 && acc[threadIdx.x] != expect) atomicAdd(bad, 1);
+}
+__global__ void red_check_nc(const double* __restrict__ acc, double expect, int* bad) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x < 64 && __ldg(acc + threadIdx.x) != expect) atomicAdd(bad, 1);
+}
+
 template <typename... KArgs, typename... Args>
 void launch(bool pdl, void (*k)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -76,5 +99,21 @@ int main() {
     }
     CK(cudaFree(src)); CK(cudaFree(dst));
   }
+  double* dacc; CK(cudaMalloc(&dacc, 64 * 8));
+  for (int nc = 0; nc < 2; ++nc)
+    for (int pdl = 0; pdl < 2; ++pdl) {
+      CK(cudaMemset(bad, 0, 4));
+      const int grid = 512;
+      for (int it = 0; it < 1000; ++it) {
+        fill_d<<<1, 64, 0, st>>>(dacc, 64);
+        launch(true, red_primary, grid, 256, st, dacc, sink, 200);
+        if (nc) launch(pdl != 0, red_check_nc, 8, 64, st, (const double*)dacc, (double)(grid * 4), bad);
+        else launch(pdl != 0, red_check, 8, 64, st, (const double*)dacc, (double)(grid * 4), bad);
+      }
+      CK(cudaStreamSynchronize(st));
+      int h = 0; CK(cudaMemcpy(&h, bad, 4, cudaMemcpyDeviceToHost));
+      printf("[pdl probe] RED.F64 sums by the primary, read by a %s dependent through %s loads: wrong values seen: %d (1000 iterations x 512 slots-reads)\n",
+             pdl ? "PDL" : "stream-ordered", nc ? "non-coherent (__ldg)" : "ordinary", h);
+    }
   return 0;
 }
