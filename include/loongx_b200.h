@@ -102,7 +102,8 @@ typedef struct lx_gemm_desc {
   const float* rms_k[3];
   const float* rope; /* fp32 [seq_total, 64, 2] (cos, sin) per rotary pair, NULL = no RoPE */
   float rms_eps;
-  int32_t tile_n; /* 0 = choose the N tile (256 / 224 / 192) that minimises wave quantisation; else force it */
+  int32_t tile_n; /* 0 = choose the N tile (256 / 224 / 192) that minimises wave quantisation; else force it (128 is
+                     only available forced: for outputs of <= 128 columns) */
   /* != 0: some W panel is an activation written by an earlier kernel on this stream (e.g. K / V^T of the VAE's
    * mid-block attention), not a constant weight: the kernel then requests no W tile ahead of its programmatic-dependency
    * wait.  0 (weights): the first W tiles are prefetched while the previous kernel is still draining. */

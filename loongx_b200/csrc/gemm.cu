@@ -623,13 +623,17 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
   const int ncta = pair_ok ? 2 : 1;
   int bn = d.tile_n;
   if (bn == 0) bn = pick_tile_n(d.M, d.N, need_256, ncta);
-  LX_CHECK_ARG(bn == 256 || ((bn == 224 || bn == 192) && !need_256), "lx_gemm_bf16: tile_n=%d not allowed here", bn);
+  // 128 is never picked automatically (the DiT shapes are tuned on 256 / 224 / 192); callers with N <= 128 outputs (the
+  // VAE's 128-channel convolutions) force it to avoid a third of idle tile columns
+  LX_CHECK_ARG(bn == 256 || ((bn == 224 || bn == 192 || bn == 128) && !need_256), "lx_gemm_bf16: tile_n=%d not allowed here", bn);
   if (ncta == 2) {
     if (bn == 256) return launch_gemm<256, 2>(d, stream);
     if (bn == 224) return launch_gemm<224, 2>(d, stream);
+    if (bn == 128) return launch_gemm<128, 2>(d, stream);
     return launch_gemm<192, 2>(d, stream);
   }
   if (bn == 256) return launch_gemm<256, 1>(d, stream);
   if (bn == 224) return launch_gemm<224, 1>(d, stream);
+  if (bn == 128) return launch_gemm<128, 1>(d, stream);
   return launch_gemm<192, 1>(d, stream);
 }

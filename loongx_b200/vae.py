@@ -225,6 +225,23 @@ class VaeWeights:
         return VaeWeights(cfg, P, device)
 
 
+def write_diffusers_vae(path: str, cfg: VaeConfig, P: Dict[str, torch.Tensor]) -> None:
+    """Write <path>/vae/{config.json, diffusion_pytorch_model.safetensors} in the layout FluxPipeline.from_pretrained reads
+    (used by the tests and to export synthetic weights)."""
+    from safetensors.torch import save_file
+
+    vdir = os.path.join(path, "vae")
+    os.makedirs(vdir, exist_ok=True)
+    cj = {"_class_name": "AutoencoderKL", "in_channels": cfg.in_channels, "out_channels": cfg.out_channels,
+          "latent_channels": cfg.latent_channels, "block_out_channels": list(cfg.block_out_channels),
+          "layers_per_block": cfg.layers_per_block, "norm_num_groups": cfg.norm_num_groups, "act_fn": "silu",
+          "scaling_factor": cfg.scaling_factor, "shift_factor": cfg.shift_factor, "use_quant_conv": False,
+          "use_post_quant_conv": False, "mid_block_add_attention": True, "force_upcast": True}
+    with open(os.path.join(vdir, "config.json"), "w") as f:
+        json.dump(cj, f, indent=1)
+    save_file({k: v.contiguous().cpu() for k, v in P.items()}, os.path.join(vdir, "diffusion_pytorch_model.safetensors"))
+
+
 def synthetic_params(cfg: VaeConfig, seed: int = 1234) -> Dict[str, torch.Tensor]:
     """Seeded random parameters of the right shapes (no checkpoint in this image).  Same recipe as the oracle's
     init_params so the tests can build both sides from one seed: convolutions ~ N(0, 1/fan_in), biases 0.05 N(0,1),
@@ -351,12 +368,13 @@ class NativeVae:
     def _gemm(self, A, conv: _Conv, residual: Optional[torch.Tensor] = None, f32: bool = False) -> torch.Tensor:
         M = A.shape[0]
         out = torch.empty(M, conv.cout, dtype=torch.float32 if f32 else torch.bfloat16, device=self.device)
+        tile_n = 128 if conv.cout <= 128 else 0  # the 128-channel layers hold half of the decoder's FLOPs
         if residual is not None:
             assert not f32 and residual.shape == out.shape
             ops.gemm(A, conv.w, conv.bias, out, L.EPI_GATE_RESIDUAL, tile_meta=self._tile_meta(M), residual=residual,
-                     gate=[self._ones[:conv.cout], None, None])
+                     gate=[self._ones[:conv.cout], None, None], tile_n=tile_n)
         else:
-            ops.gemm(A, conv.w, conv.bias, out, L.EPI_BIAS_F32 if f32 else L.EPI_BIAS)
+            ops.gemm(A, conv.w, conv.bias, out, L.EPI_BIAS_F32 if f32 else L.EPI_BIAS, tile_n=tile_n)
         self.launches += 1
         return out
 

@@ -94,3 +94,20 @@ def test_checkpoint_formats_end_to_end(tmp_path):
     assert torch.equal(_forward(m3, inp, B), _forward(m, inp, B))
     print(f"\n[checkpoint] relL2 vs oracle: directory {e0:.4g}, +LoRA file {e1:.4g}, LoongX state dict {e2:.4g}; LoRA effect {d01:.4g}")
     assert max(e0, e1, e2) < 2e-2 and d01 > 5 * max(e0, e1)
+    # 5. a FLUX directory that also holds vae/ (FluxPipeline.from_pretrained loads it, model.py:398-400): the pipeline gets
+    #    the native VAE and image processor, with the file's scaling / shift factors
+    from loongx_b200.vae import VaeConfig, synthetic_params, write_diffusers_vae
+    from oracle import vae as OV
+
+    assert m.flux_pipe.vae is None
+    vcfg = VaeConfig(scaling_factor=0.5, shift_factor=0.25)
+    VP = synthetic_params(vcfg, 5)
+    write_diffusers_vae(str(tmp_path / "flux"), vcfg, VP)
+    m4 = OminiModel(str(tmp_path / "flux"), lora_config={"r": 4, "lora_alpha": 4}, device=dev)
+    pipe = m4.flux_pipe
+    assert pipe.vae is not None and pipe.image_processor is not None and pipe.vae_scale_factor == 16
+    assert (pipe.vae.config.scaling_factor, pipe.vae.config.shift_factor) == (0.5, 0.25)
+    z = torch.randn(1, 16, 8, 8, generator=torch.Generator().manual_seed(9))
+    got = pipe.vae.decode(z.to(dev), return_dict=False)[0]
+    want = OV.decode_raw(VP, z, OV.VaeConfig())
+    assert _rel(got.cpu(), want) < 3e-2

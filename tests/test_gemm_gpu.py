@@ -40,12 +40,12 @@ def test_gemm_bias(M, N, K):
     _close(out, ref, what=f"bias {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("tile_n", [256, 224, 192])
+@pytest.mark.parametrize("tile_n", [256, 224, 192, 128])
 def test_gemm_tile_variants(tile_n):
     """Every N-tile variant of the kernel (wave-quantisation tuning) gives the same answer, incl. ragged M/N/K."""
     from loongx_b200 import ops, _lib as L
 
-    for (M, N, K) in [(384, 3072, 320), (200, 456, 136)]:
+    for (M, N, K) in [(384, 3072, 320), (200, 456, 136), (640, 128, 1152), (100, 8, 192)]:
         A, W = _mk((M, K), 1.0, 41), _mk((N, K), 0.05, 42)
         bias = _mk((N,), 1.0, 43, torch.float32)
         out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)

@@ -176,3 +176,30 @@ def test_pipeline_without_vae_raises_loudly():
 
     with pytest.raises(NotImplementedError, match="attach_vae"):
         encode_images(_P(), torch.zeros(1, 3, 32, 32))
+
+
+def test_vae_checkpoint_directory_round_trip(tmp_path):
+    """<dir>/vae in the diffusers layout -> VaeWeights: config, key validation and panels (host-side packing runs on any
+    device; no kernels are involved)."""
+    from loongx_b200 import vae as V
+
+    cfg = V.VaeConfig(block_out_channels=(32, 64), layers_per_block=1, scaling_factor=0.5, shift_factor=0.25)
+    P = V.synthetic_params(cfg, 3)
+    V.write_diffusers_vae(str(tmp_path), cfg, P)
+    w = V.VaeWeights.from_pretrained(str(tmp_path), device="cpu")
+    assert w.cfg == cfg
+    direct = V.VaeWeights(cfg, P, "cpu")
+    assert w.conv.keys() == direct.conv.keys() and w.norm.keys() == direct.norm.keys()
+    for k in w.conv:
+        assert torch.equal(w.conv[k].w, direct.conv[k].w) and torch.equal(w.conv[k].bias, direct.conv[k].bias)
+    qkv = w.conv["decoder.mid_block.attentions.0.to_qkv"]
+    assert qkv.w.shape == (3 * 64, 64) and qkv.taps == 1
+    assert torch.equal(qkv.w[64:128], P["decoder.mid_block.attentions.0.to_k.weight"].to(torch.bfloat16))
+    bad = dict(P)
+    bad.pop("decoder.conv_out.bias")
+    with pytest.raises(KeyError, match="missing"):
+        V.VaeWeights(cfg, bad, "cpu")
+    bad = dict(P)
+    bad["decoder.conv_in.weight"] = bad["decoder.conv_in.weight"][:, :8]
+    with pytest.raises(ValueError, match="decoder.conv_in"):
+        V.VaeWeights(cfg, bad, "cpu")
