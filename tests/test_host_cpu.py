@@ -218,3 +218,19 @@ def test_checkpoint_key_renaming_is_total():
         sd[f"transformer.{t}.lora_B.default.weight"] = t + ".lora_B.weight"
     tr, rest = CK.split_loongx_state_dict(sd)
     assert not rest and all(k == v for k, v in tr.items()) and len(tr) == len(keys) + 2 * len(targets)
+
+
+def test_integration_doc_stub_matches_the_header():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer mirrors lx_attn_desc_t field for field."""
+    import ctypes as C
+    from pathlib import Path
+
+    from loongx_b200 import _lib as L
+
+    doc = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    code = doc[doc.index("class AttnDesc(C.Structure)"):doc.index("lib.lx_attention.argtypes")]
+    ns = {"C": C}
+    exec(code, ns)
+    stub = ns["AttnDesc"]
+    assert C.sizeof(stub) == C.sizeof(L.AttnDesc)
+    assert [(n, C.sizeof(t)) for n, t in stub._fields_] == [(n, C.sizeof(t)) for n, t in L.AttnDesc._fields_]
