@@ -479,6 +479,37 @@ int lx_vae_rows_to_nchw(const float* in, int64_t ld, float* out, int32_t B, int3
 int lx_vae_sample_latents(const float* moments, int64_t ld, const float* eps, float* out, int32_t B, int32_t L, int64_t hw,
                           float shift, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Text encoders behind FluxPipeline.encode_prompt (generate.py:156-165, pipeline_tools.py:33-52):
+ * transformers' T5EncoderModel (T5 v1.1 XXL) and CLIPTextModel (CLIP-L), restated and pinned in
+ * oracle/text_encoders.py.  Every Linear is lx_gemm_bf16 (fused q|k|v and wi_0|wi_1 panels, residual adds through
+ * LX_EPI_GATE_RESIDUAL); these are the remaining pieces.
+ * ------------------------------------------------------------------------------------------------------ */
+/* out[i, :] = table[ids[i], :] (+ pos[i % period, :]); bf16 tables [vocab, D] / [period, D]; pos may be NULL. */
+int lx_embed_rows(const void* table, const int32_t* ids, const void* pos, int32_t period, void* out, int32_t n, int32_t D,
+                  int32_t vocab, void* stream);
+/* rms != 0: y = x * rsqrt(mean(x^2) + eps) * gamma (T5LayerNorm); else (x - mean) * rstd * gamma + beta (nn.LayerNorm);
+ * bf16 rows in / out, fp32 gamma / beta [D]. */
+int lx_norm_rows(const void* x, int64_t ldx, const float* gamma, const float* beta, void* out, int64_t ldo, int32_t rows,
+                 int32_t D, float eps, int32_t rms, void* stream);
+/* out = a * b over bf16 [rows, cols] views (T5DenseGatedActDense: gelu_new(wi_0 x) * (wi_1 x)). */
+int lx_mul_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int32_t rows, int32_t cols,
+                void* stream);
+typedef struct lx_small_attn_desc {
+  const void* q;  /* bf16 rows [B*S, ld]; head h in columns [64h, 64h + 64) */
+  const void* k;
+  const void* v;
+  int64_t ldq, ldk, ldv;
+  void* out;         /* bf16 rows [B*S, ldo], same head layout */
+  int64_t ldo;
+  const float* bias; /* fp32 [H, S, S] added to the scaled logits (T5 relative position bias) or NULL */
+  int32_t B, H, S;   /* S <= 512 */
+  int32_t head_dim;  /* 64 */
+  int32_t causal;    /* != 0: key j > query i is masked (CLIP text) */
+  float scale;       /* logits = scale * q.k (T5: 1, CLIP: 1/8) */
+} lx_small_attn_desc_t;
+int lx_attention_small(const lx_small_attn_desc_t* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

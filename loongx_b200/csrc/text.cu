@@ -1,0 +1,277 @@
+// Text-encoder kernels: the pieces of transformers' T5EncoderModel / CLIPTextModel — which
+// FluxPipeline.encode_prompt runs once per edit (generate.py:156-165, pipeline_tools.py:33-52) — that are not a Linear:
+// token (+ position) embedding gather, T5 RMS norm / CLIP LayerNorm with fp32 weights, 64-wide-head attention with an
+// additive bias table (T5 relative positions) or a causal mask (CLIP), and the gated-GELU product.  Every Linear is the
+// tcgen05 GEMM of gemm.cu (fused q|k|v and wi_0|wi_1 panels, residual adds in its GATE_RESIDUAL epilogue).
+// Sequences are short (512 / 77 tokens, once per edit): these kernels are latency / L2-bound, written for simplicity.
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace lx {
+namespace {
+
+inline cudaStream_t tcs(void* s) { return static_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ void tld8(const __nv_bfloat16* p, float* x) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+__device__ __forceinline__ void tst8(__nv_bfloat16* p, const float* v) {
+  uint4 u;
+  u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// out[i, :] = table[ids[i], :] (+ pos[i % period, :])
+__global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
+                                  const __nv_bfloat16* __restrict__ pos, int period, __nv_bfloat16* __restrict__ out, int n,
+                                  int D8, int vocab) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * D8) return;
+  const int i = (int)(idx / D8), c = (int)(idx % D8) * 8;
+  int id = ids[i];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  float a[8];
+  tld8(table + (size_t)id * D8 * 8 + c, a);
+  if (pos != nullptr) {
+    float b[8];
+    tld8(pos + (size_t)(i % period) * D8 * 8 + c, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += b[e];
+  }
+  tst8(out + (size_t)i * D8 * 8 + c, a);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+  return r;
+}
+
+// rms != 0: y = x * rsqrt(mean(x^2) + eps) * gamma (T5LayerNorm);  else y = (x - mean) * rstd * gamma + beta (nn.LayerNorm)
+__global__ void __launch_bounds__(128) norm_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        __nv_bfloat16* __restrict__ out, long long ldo, int D, float eps, int rms) {
+  __shared__ float red[4];
+  pdl_wait();
+  pdl_launch_dependents();
+  const __nv_bfloat16* xr = x + (size_t)blockIdx.x * ldx;
+  __nv_bfloat16* orow = out + (size_t)blockIdx.x * ldo;
+  const int nch = D >> 3;
+  float mean = 0.f;
+  if (!rms) {
+    float s = 0.f;
+    for (int ch = threadIdx.x; ch < nch; ch += 128) {
+      float v[8];
+      tld8(xr + ch * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[e];
+    }
+    mean = block_sum(s, red) / D;
+  }
+  float q = 0.f;
+  for (int ch = threadIdx.x; ch < nch; ch += 128) {
+    float v[8];
+    tld8(xr + ch * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q = fmaf(v[e] - mean, v[e] - mean, q);
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / D + eps);
+  for (int ch = threadIdx.x; ch < nch; ch += 128) {
+    float v[8];
+    tld8(xr + ch * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float g = gamma[ch * 8 + e];
+      v[e] = (v[e] - mean) * rstd * g + (beta != nullptr ? beta[ch * 8 + e] : 0.f);
+    }
+    tst8(orow + ch * 8, v);
+  }
+}
+
+// out = a * b over [rows, cols] views
+__global__ void mul_rows_kernel(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* b, long long ldb,
+                                __nv_bfloat16* out /* may alias a or b */, long long ldo, int rows, int cols8) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols8) return;
+  const int r = (int)(idx / cols8), c = (int)(idx % cols8) * 8;
+  float x[8], y[8];
+  tld8(a + (size_t)r * lda + c, x);
+  tld8(b + (size_t)r * ldb + c, y);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] *= y[e];
+  tst8(out + (size_t)r * ldo + c, x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Attention for 64-wide heads over short sequences (S <= 512).  One CTA per (batch, head): K and V of the head live in
+// shared memory (row stride 66 bf16 = 33 words, so a warp reading one word of 32 different keys hits 32 banks); each warp
+// owns query rows i = warp, warp + 16, ...: lane l scores keys l, l+32, ... (q in registers), the softmax runs over the
+// warp, the probabilities go through a per-warp shared buffer, and lane l accumulates output dimensions 2l, 2l+1.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SA_DH = 64, SA_WARPS = 16, SA_MAX_S = 512, SA_KSTRIDE = SA_DH + 2;
+
+struct SmallAttn {
+  const __nv_bfloat16 *q, *k, *v;  // rows [B*S, ld], head h at column h * 64
+  long long ldq, ldk, ldv;
+  __nv_bfloat16* out;  // rows [B*S, ldo], head h at column h * 64
+  long long ldo;
+  const float* bias;  // [H, S, S] additive (may be null)
+  int B, H, S, causal;
+  float scale;
+};
+
+__global__ void __launch_bounds__(SA_WARPS * 32) small_attention_kernel(const SmallAttn p) {
+  extern __shared__ __align__(16) unsigned char sa_smem[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(sa_smem);
+  __nv_bfloat16* Vs = Ks + (size_t)p.S * SA_KSTRIDE;
+  float* Ps = reinterpret_cast<float*>(Vs + (size_t)p.S * SA_KSTRIDE);  // [SA_WARPS][S]
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row0 = (size_t)b * p.S;
+  // stage K and V: one 4-byte word (two dims) per thread step
+  for (int idx = threadIdx.x; idx < p.S * (SA_DH / 2); idx += SA_WARPS * 32) {
+    const int j = idx / (SA_DH / 2), w = idx % (SA_DH / 2);
+    reinterpret_cast<uint32_t*>(Ks + (size_t)j * SA_KSTRIDE)[w] =
+        reinterpret_cast<const uint32_t*>(p.k + (row0 + j) * p.ldk + h * SA_DH)[w];
+    reinterpret_cast<uint32_t*>(Vs + (size_t)j * SA_KSTRIDE)[w] =
+        reinterpret_cast<const uint32_t*>(p.v + (row0 + j) * p.ldv + h * SA_DH)[w];
+  }
+  __syncthreads();
+  float* Pw = Ps + (size_t)warp * p.S;
+  const int nj = (p.S + 31) / 32;
+  for (int i = warp; i < p.S; i += SA_WARPS) {
+    float2 q[SA_DH / 2];
+    const uint32_t* qg = reinterpret_cast<const uint32_t*>(p.q + (row0 + i) * p.ldq + h * SA_DH);
+#pragma unroll
+    for (int w = 0; w < SA_DH / 2; ++w) q[w] = unpack_bf16(qg[w]);
+    float sc[SA_MAX_S / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < SA_MAX_S / 32; ++jj) {
+      sc[jj] = -INFINITY;
+      const int j = jj * 32 + lane;
+      if (jj < nj && j < p.S && !(p.causal && j > i)) {
+        const uint32_t* kr = reinterpret_cast<const uint32_t*>(Ks + (size_t)j * SA_KSTRIDE);
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < SA_DH / 2; ++w) {
+          const float2 kk = unpack_bf16(kr[w]);
+          acc = fmaf(q[w].x, kk.x, acc);
+          acc = fmaf(q[w].y, kk.y, acc);
+        }
+        acc *= p.scale;
+        if (p.bias != nullptr) acc += p.bias[((size_t)h * p.S + i) * p.S + j];
+        sc[jj] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < SA_MAX_S / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      if (jj < nj && j < p.S) {
+        const float e = sc[jj] == -INFINITY ? 0.f : __expf(sc[jj] - mx);
+        Pw[j] = e;
+        sum += e;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    float ox = 0.f, oy = 0.f;
+    const int jend = p.causal ? i + 1 : p.S;
+    for (int j = 0; j < jend; ++j) {
+      const float pj = Pw[j];
+      const float2 vv = unpack_bf16(reinterpret_cast<const uint32_t*>(Vs + (size_t)j * SA_KSTRIDE)[lane]);
+      ox = fmaf(pj, vv.x, ox);
+      oy = fmaf(pj, vv.y, oy);
+    }
+    const float inv = 1.0f / sum;
+    reinterpret_cast<uint32_t*>(p.out + (row0 + i) * p.ldo + h * SA_DH)[lane] = pack_bf16(ox * inv, oy * inv);
+    __syncwarp();  // Pw is rewritten by the next row
+  }
+}
+
+}  // namespace
+}  // namespace lx
+
+using namespace lx;
+
+extern "C" int lx_embed_rows(const void* table, const int32_t* ids, const void* pos, int32_t period, void* out, int32_t n,
+                             int32_t D, int32_t vocab, void* stream) {
+  LX_CHECK_ARG(table && ids && out && n > 0 && D > 0 && D % 8 == 0 && vocab > 0, "lx_embed_rows: bad arguments");
+  LX_CHECK_ARG(pos == nullptr || period > 0, "lx_embed_rows: position table needs period > 0");
+  const long long total = (long long)n * (D / 8);
+  LaunchScope scope(KC_ROW, stream, 4.0 * n * D);
+  LX_CUDA(launch_pdl(embed_rows_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, tcs(stream),
+                     reinterpret_cast<const __nv_bfloat16*>(table), (const int*)ids, reinterpret_cast<const __nv_bfloat16*>(pos),
+                     period, reinterpret_cast<__nv_bfloat16*>(out), n, D / 8, vocab));
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_norm_rows(const void* x, int64_t ldx, const float* gamma, const float* beta, void* out, int64_t ldo,
+                            int32_t rows, int32_t D, float eps, int32_t rms, void* stream) {
+  LX_CHECK_ARG(x && gamma && out && rows > 0 && D > 0 && D % 8 == 0 && ldx >= D && ldo >= D && ldx % 8 == 0 && ldo % 8 == 0,
+               "lx_norm_rows: bad arguments");
+  LX_CHECK_ARG(!(rms && beta), "lx_norm_rows: the RMS form has no bias");
+  LaunchScope scope(KC_ROW, stream, 4.0 * rows * D);
+  LX_CUDA(launch_pdl(norm_rows_kernel, dim3(rows), dim3(128), 0, tcs(stream), reinterpret_cast<const __nv_bfloat16*>(x),
+                     (long long)ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), (long long)ldo, D, eps, rms));
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_mul_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int32_t rows,
+                           int32_t cols, void* stream) {
+  LX_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && cols % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0,
+               "lx_mul_rows: bad arguments");
+  const long long total = (long long)rows * (cols / 8);
+  LaunchScope scope(KC_ROW, stream, 6.0 * rows * cols);
+  LX_CUDA(launch_pdl(mul_rows_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, tcs(stream),
+                     reinterpret_cast<const __nv_bfloat16*>(a), (long long)lda, reinterpret_cast<const __nv_bfloat16*>(b),
+                     (long long)ldb, reinterpret_cast<__nv_bfloat16*>(out), (long long)ldo, rows, cols / 8));
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_attention_small(const lx_small_attn_desc_t* d, void* stream) {
+  LX_CHECK_ARG(d && d->q && d->k && d->v && d->out, "lx_attention_small: null argument");
+  LX_CHECK_ARG(d->head_dim == SA_DH, "lx_attention_small: head_dim=%d, only 64 is built", d->head_dim);
+  LX_CHECK_ARG(d->B > 0 && d->H > 0 && d->S > 0 && d->S <= SA_MAX_S, "lx_attention_small: S=%d outside [1, %d]", d->S, SA_MAX_S);
+  LX_CHECK_ARG(d->ldq % 2 == 0 && d->ldk % 2 == 0 && d->ldv % 2 == 0 && d->ldo % 2 == 0, "lx_attention_small: odd row stride");
+  SmallAttn p;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(d->q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(d->k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(d->v);
+  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  p.ldq = d->ldq; p.ldk = d->ldk; p.ldv = d->ldv; p.ldo = d->ldo;
+  p.bias = d->bias;
+  p.B = d->B; p.H = d->H; p.S = d->S; p.causal = d->causal;
+  p.scale = d->scale;
+  const size_t smem = 2 * (size_t)d->S * SA_KSTRIDE * sizeof(__nv_bfloat16) + (size_t)SA_WARPS * d->S * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LX_CUDA(cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  LaunchScope scope(KC_ATTENTION, stream, 4.0 * d->B * d->H * (double)d->S * d->S * SA_DH);
+  LX_CUDA(launch_pdl(small_attention_kernel, dim3(d->B * d->H), dim3(SA_WARPS * 32), smem, tcs(stream), p));
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}

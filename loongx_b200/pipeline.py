@@ -199,6 +199,8 @@ class NativeFluxPipeline:
         self.vae = None
         self.text_encoder = None
         self.text_encoder_2 = None
+        self.tokenizer = None
+        self.tokenizer_2 = None
         self.image_processor = None
         self.vae_scale_factor = 16  # diffusers 0.31.0
         self.default_sample_size = 64
@@ -249,9 +251,17 @@ class NativeFluxPipeline:
     def encode_prompt(self, prompt=None, prompt_2=None, device=None, num_images_per_prompt: int = 1, prompt_embeds=None,
                       pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None):
         if prompt_embeds is None:
-            raise NotImplementedError(
-                "text encoders (T5-XXL / CLIP-L) are outside this build's scope (SURVEY.md §8f.4): pass prompt_embeds "
-                "and pooled_prompt_embeds")
+            if self.text_encoder is None or self.text_encoder_2 is None or self.tokenizer is None or self.tokenizer_2 is None:
+                raise NotImplementedError(
+                    "no text encoders attached (pipeline.attach_text_encoders, SURVEY.md §8f.4): pass prompt_embeds and "
+                    "pooled_prompt_embeds")
+            from .text import tokenize
+
+            # FluxPipeline.encode_prompt: CLIP-L pooled output of `prompt` (77 tokens), T5 hidden states of `prompt_2`
+            prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+            prompts_2 = prompts if prompt_2 is None else ([prompt_2] if isinstance(prompt_2, str) else list(prompt_2))
+            pooled_prompt_embeds = self.text_encoder(tokenize(self.tokenizer, prompts, 77)).pooler_output
+            prompt_embeds = self.text_encoder_2(tokenize(self.tokenizer_2, prompts_2, max_sequence_length))[0]
         device = device or self._execution_device
         pe = prompt_embeds.to(device=device, dtype=self.dtype)
         po = pooled_prompt_embeds.to(device=device, dtype=self.dtype)
@@ -290,6 +300,21 @@ class NativeFluxPipeline:
 
     def set_adapters(self, *args, **kwargs):  # LoRA adapters are merged into the cond row group at load
         return None
+
+    def attach_text_encoders(self, source=None, tokenizers=None, clip=None, t5=None):
+        """Give the pipeline `text_encoder` (CLIP-L), `text_encoder_2` (T5-XXL) and their tokenizers so
+        that `generate(prompt=...)` / `prepare_text_input` work.  `source`: a FLUX checkpoint directory (text_encoder/,
+        text_encoder_2/, tokenizer/, tokenizer_2/); or pass already-built encoders and tokenizer callables."""
+        from .text import load_text_encoders, load_tokenizers
+
+        if source is not None:
+            clip, t5 = load_text_encoders(source, self.device)
+            tokenizers = tokenizers or load_tokenizers(source)
+        if clip is None or t5 is None or tokenizers is None:
+            raise ValueError("attach_text_encoders needs a checkpoint directory, or clip=, t5= and tokenizers=")
+        self.text_encoder, self.text_encoder_2 = clip, t5
+        self.tokenizer, self.tokenizer_2 = tokenizers
+        return clip, t5
 
     def attach_vae(self, source=None, seed: int = 1234):
         """Give the pipeline its `vae` + `image_processor`.  `source`: a FLUX checkpoint directory

@@ -28,9 +28,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header(tmp_path):
     from loongx_b200 import _lib as L
-    from loongx_b200 import cs3, dit
+    from loongx_b200 import cs3, dit, text, vae
 
-    pairs = {"lx_tile_meta_t": L.TileMeta, "lx_gemm_group_t": L.GemmGroup, "lx_gemm_segment_t": L.GemmSegment,
+    pairs = {"lx_vae_im2col_desc_t": vae.Im2colDesc, "lx_small_attn_desc_t": text.SmallAttnDesc,
+             "lx_tile_meta_t": L.TileMeta, "lx_gemm_group_t": L.GemmGroup, "lx_gemm_segment_t": L.GemmSegment,
              "lx_gemm_desc_t": L.GemmDesc, "lx_attn_desc_t": L.AttnDesc, "lx_attn_bwd_desc_t": L.AttnBwdDesc, "lx_linear_t": dit.LxLinear,
              "lx_double_block_t": dit.LxDoubleBlock, "lx_single_block_t": dit.LxSingleBlock,
              "lx_dit_model_t": dit.LxDitModel, "lx_dit_plan_t": dit.LxDitPlan, "lx_sgemm_desc_t": cs3.SgemmDesc,

@@ -59,3 +59,42 @@ def test_clip_oracle_matches_transformers():
             o = hf(input_ids=ids)
             h, pooled = T.clip_encode(P, ids, cfg)
         assert _rel(h, o.last_hidden_state) < 1e-5 and _rel(pooled, o.pooler_output) < 1e-5
+
+
+def test_host_side_of_the_native_encoders():
+    """Integer bookkeeping and argument validation of loongx_b200/text.py (no compute without a GPU)."""
+    import ctypes as C
+
+    from loongx_b200 import _lib as L
+    from loongx_b200 import text as N
+
+    for S in (1, 77, 300):
+        assert torch.equal(N.t5_relative_buckets(S, 32, 128), T.t5_relative_buckets(S, 32, 128))
+    assert N.T5Config.from_json({"vocab_size": 32128, "d_model": 4096, "d_kv": 64, "num_heads": 64, "d_ff": 10240,
+                                 "num_layers": 24, "feed_forward_proj": "gated-gelu"}) == N.T5Config()
+    assert N.ClipTextConfig.from_json({"vocab_size": 49408, "hidden_size": 768, "intermediate_size": 3072,
+                                       "num_hidden_layers": 12, "num_attention_heads": 12, "hidden_act": "quick_gelu",
+                                       "eos_token_id": 2}) == N.ClipTextConfig()
+    with pytest.raises(NotImplementedError):
+        N.T5Config.from_json({"vocab_size": 1, "d_model": 1, "d_kv": 1, "num_heads": 1, "d_ff": 1, "num_layers": 1,
+                              "feed_forward_proj": "relu"})
+    lib, one = L.lib, C.c_void_p(16)
+    d = N.SmallAttnDesc()
+    d.q = d.k = d.v = d.out = 16
+    d.ldq = d.ldk = d.ldv = d.ldo = 192
+    d.B, d.H, d.S, d.head_dim, d.scale = 1, 1, 77, 32, 1.0
+    assert lib.lx_attention_small(C.byref(d), None) != 0 and b"head_dim" in lib.lx_last_error()
+    d.head_dim, d.S = 64, 513
+    assert lib.lx_attention_small(C.byref(d), None) != 0 and b"S=513" in lib.lx_last_error()
+    assert lib.lx_norm_rows(one, 64, one, one, one, 64, 4, 64, 1e-6, 1, None) != 0  # RMS form with a bias
+    assert lib.lx_norm_rows(one, 60, one, None, one, 64, 4, 64, 1e-6, 1, None) != 0  # ldx < D
+    assert lib.lx_embed_rows(one, one, one, 0, one, 4, 64, 100, None) != 0  # position table without a period
+    assert lib.lx_mul_rows(one, 64, one, 64, one, 64, 4, 60, None) != 0  # cols not a multiple of 8
+
+    class _P:  # a pipeline without encoders refuses a text prompt loudly
+        text_encoder = text_encoder_2 = tokenizer = tokenizer_2 = None
+
+    from loongx_b200.pipeline import NativeFluxPipeline
+
+    with pytest.raises(NotImplementedError, match="attach_text_encoders"):
+        NativeFluxPipeline.encode_prompt(_P(), prompt="a photo")
