@@ -116,7 +116,7 @@ __global__ void mul_rows_kernel(const __nv_bfloat16* a, long long lda, const __n
 // ---------------------------------------------------------------------------------------------------------------
 // Attention for 64-wide heads over short sequences (S <= 512).  One CTA per (batch, head): K and V of the head live in
 // shared memory (row stride 66 bf16 = 33 words, so a warp reading one word of 32 different keys hits 32 banks); each warp
-// owns query rows i = warp, warp + 16, ...: lane l scores keys l, l+32, ... (q in registers), the softmax runs over the
+// owns query rows i = warp, warp + 16, ... (of the CTA's slice when the rows of a head are split over several CTAs): lane l scores keys l, l+32, ... (q in registers), the softmax runs over the
 // warp, the probabilities go through a per-warp shared buffer, and lane l accumulates output dimensions 2l, 2l+1.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SA_DH = 64, SA_WARPS = 16, SA_MAX_S = 512, SA_KSTRIDE = SA_DH + 2;
@@ -128,6 +128,7 @@ struct SmallAttn {
   long long ldo;
   const float* bias;  // [H, S, S] additive (may be null)
   int B, H, S, causal;
+  int qsplit;  // CTAs per (batch, head): each takes a contiguous slice of the query rows (all keys)
   float scale;
 };
 
@@ -138,7 +139,10 @@ __global__ void __launch_bounds__(SA_WARPS * 32) small_attention_kernel(const Sm
   float* Ps = reinterpret_cast<float*>(Vs + (size_t)p.S * SA_KSTRIDE);  // [SA_WARPS][S]
   pdl_wait();
   pdl_launch_dependents();
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int bh = blockIdx.x / p.qsplit, part = blockIdx.x % p.qsplit;
+  const int b = bh / p.H, h = bh % p.H;
+  const int rows_per_part = (p.S + p.qsplit - 1) / p.qsplit;
+  const int i_begin = part * rows_per_part, i_end = min(p.S, i_begin + rows_per_part);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t row0 = (size_t)b * p.S;
   // stage K and V: one 4-byte word (two dims) per thread step
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32) small_attention_kernel(const Sm
   __syncthreads();
   float* Pw = Ps + (size_t)warp * p.S;
   const int nj = (p.S + 31) / 32;
-  for (int i = warp; i < p.S; i += SA_WARPS) {
+  for (int i = i_begin + warp; i < i_end; i += SA_WARPS) {
     float2 q[SA_DH / 2];
     const uint32_t* qg = reinterpret_cast<const uint32_t*>(p.q + (row0 + i) * p.ldq + h * SA_DH);
 #pragma unroll
@@ -270,8 +274,10 @@ extern "C" int lx_attention_small(const lx_small_attn_desc_t* d, void* stream) {
     LX_CUDA(cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
+  // few (batch, head) pairs (T5-XXL at B = 1: 64): split the query rows so that the grid fills the SMs
+  p.qsplit = max(1, min(4, num_sms() / (d->B * d->H)));
   LaunchScope scope(KC_ATTENTION, stream, 4.0 * d->B * d->H * (double)d->S * d->S * SA_DH);
-  LX_CUDA(launch_pdl(small_attention_kernel, dim3(d->B * d->H), dim3(SA_WARPS * 32), smem, tcs(stream), p));
+  LX_CUDA(launch_pdl(small_attention_kernel, dim3(d->B * d->H * p.qsplit), dim3(SA_WARPS * 32), smem, tcs(stream), p));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -2,8 +2,9 @@
 consume from diffusers' FluxPipeline / FluxTransformer2DModel ("pipeline object consumed by generate()").
 
 They own the packed native weights and cached plans; every tensor operation they perform is either a native kernel or
-pure layout plumbing (views / copies).  Text encoders and the VAE are out of scope for this build:
-prompt embeddings and latents come in pre-computed, `output_type="latent"` is the supported output.
+pure layout plumbing (views / copies).  The VAE and the text encoders are optional attachments
+(`attach_vae`, `attach_text_encoders`): without them prompt embeddings and latents come in pre-computed and
+`output_type="latent"` is the supported output.
 """
 from __future__ import annotations
 

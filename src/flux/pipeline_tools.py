@@ -28,7 +28,7 @@ def encode_images(pipeline, images: Tensor):
 
 
 def prepare_text_input(pipeline, prompts, max_sequence_length=512):
-    """pipeline_tools.py:33-52 (needs the text encoders, which this build does not carry)."""
+    """pipeline_tools.py:33-52: -> (prompt_embeds, pooled_prompt_embeds, text_ids); needs `pipeline.attach_text_encoders`."""
     return pipeline.encode_prompt(prompt=prompts, prompt_2=None, prompt_embeds=None, pooled_prompt_embeds=None,
                                   device=pipeline.device, num_images_per_prompt=1,
                                   max_sequence_length=max_sequence_length, lora_scale=None)

@@ -26,7 +26,8 @@ def test_small_attention_kernel():
 
     g = torch.Generator(device="cuda").manual_seed(0)
     for (B, H, S, causal, with_bias, scale) in ((2, 3, 77, True, False, 0.125), (1, 4, 200, False, True, 1.0),
-                                                (1, 2, 512, False, True, 1.0), (2, 2, 33, True, True, 0.5)):
+                                                (1, 2, 512, False, True, 1.0), (2, 2, 33, True, True, 0.5),
+                                                (3, 30, 50, True, False, 0.125), (1, 64, 96, False, True, 1.0)):
         inner = H * 64
         qkv = (torch.randn(B * S, 3 * inner, generator=g, device="cuda") * (0.4 if scale == 1.0 else 1.0)).to(torch.bfloat16)
         bias = torch.randn(H, S, S, generator=g, device="cuda") if with_bias else None
