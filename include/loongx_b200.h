@@ -507,6 +507,9 @@ typedef struct lx_small_attn_desc {
   int32_t head_dim;  /* 64 */
   int32_t causal;    /* != 0: key j > query i is masked (CLIP text) */
   float scale;       /* logits = scale * q.k (T5: 1, CLIP: 1/8) */
+  int32_t bias_relative; /* != 0: bias is fp32 [H, 2S-1], entry (key - query + S - 1): a bias that depends on the distance
+                            only (T5), kept in shared memory instead of streaming H*S*S values per layer */
+  int32_t reserved;
 } lx_small_attn_desc_t;
 int lx_attention_small(const lx_small_attn_desc_t* desc, void* stream);
 

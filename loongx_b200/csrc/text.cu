@@ -128,7 +128,8 @@ struct SmallAttn {
   long long ldo;
   const float* bias;  // [H, S, S] additive (may be null)
   int B, H, S, causal;
-  int qsplit;  // CTAs per (batch, head): each takes a contiguous slice of the query rows (all keys)
+  int bias_rel;  // bias is [H, 2S-1] indexed by key - query + S - 1
+  int qsplit;    // CTAs per (batch, head): each takes a contiguous slice of the query rows (all keys)
   float scale;
 };
 
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(SA_WARPS * 32) small_attention_kernel(const Sm
           acc = fmaf(q[w].y, kk.y, acc);
         }
         acc *= p.scale;
-        if (p.bias != nullptr) acc += p.bias[((size_t)h * p.S + i) * p.S + j];
+        if (p.bias != nullptr)
+          acc += p.bias_rel ? p.bias[(size_t)h * (2 * p.S - 1) + (j - i + p.S - 1)] : p.bias[((size_t)h * p.S + i) * p.S + j];
         sc[jj] = acc;
         mx = fmaxf(mx, acc);
       }
@@ -211,10 +213,162 @@ __global__ void __launch_bounds__(SA_WARPS * 32) small_attention_kernel(const Sm
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the same attention (the default): mma.sync m16n8k16 bf16 tiles with an online softmax.  One CTA per
+// (batch, head, 128 query rows), 8 warps x 16 query rows; K [key][dim] and V^T [dim][key] of the head in shared memory
+// with row strides of 36 / (S64 + 8) / 2 words = 4 (mod 8), so the eight row groups x four lanes of a fragment load hit 32
+// different banks.  Per 64-key block: S = Q K^T (32 MMAs), scale / bias / mask in the accumulator layout, running max and
+// sum per row (the four lanes of a row group share a row), P re-used directly as the A fragments of O += P V (32 MMAs).
+// tcgen05 would be the wrong tool here: 64-wide heads, 77..512 keys, once per edit.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MA_WARPS = 8, MA_ROWS = 16 * MA_WARPS, MA_KB = 64, MA_KWORDS = 36;
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(MA_WARPS * 32) small_attention_mma_kernel(const SmallAttn p) {
+  extern __shared__ __align__(16) unsigned char sa_smem[];
+  const int S = p.S, S64 = (S + MA_KB - 1) / MA_KB * MA_KB, VT = S64 + 8;  // VT: bf16 per V^T row
+  uint32_t* Kw = reinterpret_cast<uint32_t*>(sa_smem);                       // [S64][36 words]
+  __nv_bfloat16* Vt = reinterpret_cast<__nv_bfloat16*>(Kw + (size_t)S64 * MA_KWORDS);  // [64][VT]
+  float* relb = reinterpret_cast<float*>(Vt + (size_t)SA_DH * VT);                      // [2S-1] (bias_rel only)
+  pdl_wait();
+  pdl_launch_dependents();
+  const int chunks = (S + MA_ROWS - 1) / MA_ROWS;
+  const int bh = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int b = bh / p.H, h = bh % p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const size_t row_base = (size_t)b * S;
+  const int kneed = p.causal ? min(S, (chunk + 1) * MA_ROWS) : S;  // keys any row of this CTA can see
+  const int kstage = (kneed + MA_KB - 1) / MA_KB * MA_KB;
+  for (int idx = threadIdx.x; idx < kstage * (SA_DH / 2); idx += MA_WARPS * 32) {
+    const int j = idx / (SA_DH / 2), w = idx % (SA_DH / 2);
+    uint32_t kw = 0u, vw = 0u;
+    if (j < S) {
+      kw = reinterpret_cast<const uint32_t*>(p.k + (row_base + j) * p.ldk + h * SA_DH)[w];
+      vw = reinterpret_cast<const uint32_t*>(p.v + (row_base + j) * p.ldv + h * SA_DH)[w];
+    }
+    Kw[(size_t)j * MA_KWORDS + w] = kw;
+    reinterpret_cast<uint16_t*>(Vt)[(size_t)(2 * w) * VT + j] = (uint16_t)(vw & 0xffffu);
+    reinterpret_cast<uint16_t*>(Vt)[(size_t)(2 * w + 1) * VT + j] = (uint16_t)(vw >> 16);
+  }
+  if (p.bias != nullptr && p.bias_rel)
+    for (int i = threadIdx.x; i < 2 * S - 1; i += MA_WARPS * 32) relb[i] = p.bias[(size_t)h * (2 * S - 1) + i];
+  __syncthreads();
+  const int row0 = chunk * MA_ROWS + warp * 16;
+  if (row0 >= S) return;
+  const int r0 = row0 + g, r1 = row0 + g + 8;
+  uint32_t qa[4][4];
+  {
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.q + (row_base + min(r0, S - 1)) * p.ldq + h * SA_DH);
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.q + (row_base + min(r1, S - 1)) * p.ldq + h * SA_DH);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa[ks][0] = q0[8 * ks + t];
+      qa[ks][1] = q1[8 * ks + t];
+      qa[ks][2] = q0[8 * ks + t + 4];
+      qa[ks][3] = q1[8 * ks + t + 4];
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int kend = p.causal ? min(S, row0 + 16) : S;
+  const uint32_t* Vw = reinterpret_cast<const uint32_t*>(Vt);
+  const int vt_words = VT / 2;
+  for (int kb = 0; kb < kend; kb += MA_KB) {
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t* kr = Kw + (size_t)(kb + nt * 8 + g) * MA_KWORDS;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_16816(s[nt], qa[ks], kr[8 * ks + t], kr[8 * ks + t + 4]);
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = e < 2 ? r0 : r1, key = kb + nt * 8 + 2 * t + (e & 1);
+        float v = s[nt][e] * p.scale;
+        if (p.bias != nullptr && row < S && key < S)
+          v += p.bias_rel ? relb[key - row + S - 1] : p.bias[((size_t)h * S + row) * S + key];
+        if (key >= S || (p.causal && key > row)) v = -INFINITY;
+        s[nt][e] = v;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = mn0 == -INFINITY ? 0.f : mn0, c1 = mn1 == -INFINITY ? 0.f : mn1;  // (only padding rows stay at -inf)
+    const float al0 = __expf(m0 - c0), al1 = __expf(m1 - c1);
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = __expf(s[nt][0] - c0);
+      s[nt][1] = __expf(s[nt][1] - c0);
+      s[nt][2] = __expf(s[nt][2] - c1);
+      s[nt][3] = __expf(s[nt][3] - c1);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+      o[nt][0] *= al0;
+      o[nt][1] *= al0;
+      o[nt][2] *= al1;
+      o[nt][3] *= al1;
+    }
+    l0 = l0 * al0 + rs0;  // lane-partial row sums: the rescale factor is the same on the four lanes of a row
+    l1 = l1 * al1 + rs1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t* vr = Vw + (size_t)(nt * 8 + g) * vt_words + (kb + 16 * kk) / 2;
+        mma_16816(o[nt], a, vr[t], vr[t + 4]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  if (r0 < S) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out + (row_base + r0) * p.ldo + h * SA_DH);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dst[nt * 4 + t] = pack_bf16(o[nt][0] * i0, o[nt][1] * i0);
+  }
+  if (r1 < S) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out + (row_base + r1) * p.ldo + h * SA_DH);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dst[nt * 4 + t] = pack_bf16(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
 }  // namespace
 }  // namespace lx
 
 using namespace lx;
+
+static int g_small_attention_scalar = 0;
+// development / test knob: 1 = use the scalar-FMA form of lx_attention_small instead of the mma.sync one
+extern "C" void lx_debug_small_attention_scalar(int on) { g_small_attention_scalar = on; }
 
 extern "C" int lx_embed_rows(const void* table, const int32_t* ids, const void* pos, int32_t period, void* out, int32_t n,
                              int32_t D, int32_t vocab, void* stream) {
@@ -268,16 +422,27 @@ extern "C" int lx_attention_small(const lx_small_attn_desc_t* d, void* stream) {
   p.bias = d->bias;
   p.B = d->B; p.H = d->H; p.S = d->S; p.causal = d->causal;
   p.scale = d->scale;
-  const size_t smem = 2 * (size_t)d->S * SA_KSTRIDE * sizeof(__nv_bfloat16) + (size_t)SA_WARPS * d->S * sizeof(float);
+  p.bias_rel = d->bias_relative != 0;
+  p.qsplit = 1;
+  LaunchScope scope(KC_ATTENTION, stream, 4.0 * d->B * d->H * (double)d->S * d->S * SA_DH);
   static bool attr_set = false;
   if (!attr_set) {
     LX_CUDA(cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LX_CUDA(cudaFuncSetAttribute(small_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  // few (batch, head) pairs (T5-XXL at B = 1: 64): split the query rows so that the grid fills the SMs
-  p.qsplit = max(1, min(4, num_sms() / (d->B * d->H)));
-  LaunchScope scope(KC_ATTENTION, stream, 4.0 * d->B * d->H * (double)d->S * d->S * SA_DH);
-  LX_CUDA(launch_pdl(small_attention_kernel, dim3(d->B * d->H * p.qsplit), dim3(SA_WARPS * 32), smem, tcs(stream), p));
+  if (!g_small_attention_scalar) {
+    const int S64 = (d->S + MA_KB - 1) / MA_KB * MA_KB;
+    const size_t smem = (size_t)S64 * MA_KWORDS * 4 + (size_t)SA_DH * (S64 + 8) * sizeof(__nv_bfloat16) +
+                        (size_t)(2 * d->S) * sizeof(float);
+    const int chunks = (d->S + MA_ROWS - 1) / MA_ROWS;
+    LX_CUDA(launch_pdl(small_attention_mma_kernel, dim3(d->B * d->H * chunks), dim3(MA_WARPS * 32), smem, tcs(stream), p));
+  } else {
+    // scalar form (kept as a cross-check): few (batch, head) pairs -> split the query rows so that the grid fills the SMs
+    const size_t smem = 2 * (size_t)d->S * SA_KSTRIDE * sizeof(__nv_bfloat16) + (size_t)SA_WARPS * d->S * sizeof(float);
+    p.qsplit = max(1, min(4, num_sms() / (d->B * d->H)));
+    LX_CUDA(launch_pdl(small_attention_kernel, dim3(d->B * d->H * p.qsplit), dim3(SA_WARPS * 32), smem, tcs(stream), p));
+  }
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -29,7 +29,7 @@ c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_floa
 class SmallAttnDesc(C.Structure):
     _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("ldq", c_int64), ("ldk", c_int64), ("ldv", c_int64),
                 ("out", c_void_p), ("ldo", c_int64), ("bias", c_void_p), ("B", c_int32), ("H", c_int32), ("S", c_int32),
-                ("head_dim", c_int32), ("causal", c_int32), ("scale", c_float)]
+                ("head_dim", c_int32), ("causal", c_int32), ("scale", c_float), ("bias_relative", c_int32), ("reserved", c_int32)]
 
 
 _lib.lx_embed_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p]
@@ -145,13 +145,14 @@ class _Blocks:
         self.launches += 1
         return out
 
-    def _attention(self, qkv, B, S, H, inner, bias, causal, scale):
+    def _attention(self, qkv, B, S, H, inner, bias, causal, scale, bias_relative=False):
         out = torch.empty(B * S, inner, dtype=torch.bfloat16, device=self.device)
         d = SmallAttnDesc()
         d.q, d.k, d.v = _cuda(qkv), _cuda(qkv[:, inner:]), _cuda(qkv[:, 2 * inner:])
         d.ldq = d.ldk = d.ldv = qkv.stride(0)
         d.out, d.ldo, d.bias = _cuda(out), out.stride(0), _cuda(bias)
         d.B, d.H, d.S, d.head_dim, d.causal, d.scale = B, H, S, inner // H, int(causal), scale
+        d.bias_relative = int(bool(bias_relative))
         L.check(_lib.lx_attention_small(C.byref(d), _stream()), "lx_attention_small")
         self.launches += 1
         return out
@@ -195,9 +196,12 @@ class NativeT5Encoder(_Blocks):
         self._bias_cache: Dict[int, torch.Tensor] = {}
 
     def _bias(self, S: int) -> torch.Tensor:
-        if S not in self._bias_cache:  # [H, S, S] fp32, shared by every layer (T5 computes it in block 0 only)
-            b = t5_relative_buckets(S, self.cfg.num_buckets, self.cfg.max_distance).to(self.device)
-            self._bias_cache[S] = self.rel_bias[b].permute(2, 0, 1).contiguous()
+        """Relative position bias as a distance table [H, 2S-1] (entry key - query + S - 1), shared by every layer (T5
+        computes it in block 0 only)."""
+        if S not in self._bias_cache:
+            b = t5_relative_buckets(S, self.cfg.num_buckets, self.cfg.max_distance)
+            by_distance = torch.cat([b[1:, 0].flip(0), b[0, :]]).to(self.device)  # distances -(S-1) .. S-1
+            self._bias_cache[S] = self.rel_bias[by_distance].t().contiguous()
         return self._bias_cache[S]
 
     def __call__(self, input_ids: torch.Tensor, **_) -> Tuple[torch.Tensor]:
@@ -209,7 +213,7 @@ class NativeT5Encoder(_Blocks):
         for lw in self.layers:
             n = self._norm(h, lw["ln1"], None, cfg.eps, True)
             qkv = self._linear(n, lw["qkv"], None)
-            a = self._attention(qkv, B, S, cfg.num_heads, inner, bias, False, 1.0)  # T5: no 1/sqrt(d) scaling
+            a = self._attention(qkv, B, S, cfg.num_heads, inner, bias, False, 1.0, bias_relative=True)  # T5: no 1/sqrt(d) scaling
             h = self._linear(a, lw["o"], None, residual=h)
             n = self._norm(h, lw["ln2"], None, cfg.eps, True)
             g = torch.empty(B * S, 2 * ff, dtype=torch.bfloat16, device=self.device)

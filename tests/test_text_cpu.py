@@ -98,3 +98,17 @@ def test_host_side_of_the_native_encoders():
 
     with pytest.raises(NotImplementedError, match="attach_text_encoders"):
         NativeFluxPipeline.encode_prompt(_P(), prompt="a photo")
+
+
+def test_distance_table_equals_the_full_bias():
+    """NativeT5Encoder keeps the relative position bias as [H, 2S-1] indexed by key - query + S - 1 (what
+    lx_attention_small's bias_relative mode reads): same values as transformers' full [H, S, S] bias."""
+    from loongx_b200.text import t5_relative_buckets
+
+    for S in (1, 2, 77, 300):
+        b = t5_relative_buckets(S, 32, 128)
+        by_distance = torch.cat([b[1:, 0].flip(0), b[0, :]])
+        w = torch.randn(32, 4, generator=torch.Generator().manual_seed(S))
+        table = w[by_distance].t()
+        idx = torch.arange(S)[None, :] - torch.arange(S)[:, None] + S - 1
+        assert torch.equal(table[:, idx], w[T.t5_relative_buckets(S)].permute(2, 0, 1))

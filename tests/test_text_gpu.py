@@ -18,7 +18,19 @@ def _round(P):
     return {k: v.to(torch.bfloat16).float() for k, v in P.items()}
 
 
-def test_small_attention_kernel():
+@pytest.mark.parametrize("scalar", [0, 1])
+def test_small_attention_kernel(scalar):
+    """Both forms of lx_attention_small (mma.sync tiles = the default, scalar FMA = the cross-check) against torch."""
+    from loongx_b200.text import _lib as lib
+
+    lib.lx_debug_small_attention_scalar(scalar)
+    try:
+        _check_small_attention()
+    finally:
+        lib.lx_debug_small_attention_scalar(0)
+
+
+def _check_small_attention():
     import ctypes as C
 
     from loongx_b200 import _lib as L
@@ -37,6 +49,11 @@ def test_small_attention_kernel():
         d.ldq = d.ldk = d.ldv = qkv.stride(0)
         d.out, d.ldo, d.bias = out.data_ptr(), out.stride(0), None if bias is None else bias.data_ptr()
         d.B, d.H, d.S, d.head_dim, d.causal, d.scale = B, H, S, 64, int(causal), scale
+        if with_bias and S % 2 == 0:  # the distance-table form of the bias: [H, 2S-1], entry key - query + S - 1
+            table = torch.randn(H, 2 * S - 1, generator=g, device="cuda")
+            idx = torch.arange(S, device="cuda")[None, :] - torch.arange(S, device="cuda")[:, None] + S - 1
+            bias = table[:, idx].contiguous()  # the equivalent full [H, S, S] bias for the torch reference
+            d.bias, d.bias_relative = table.data_ptr(), 1
         L.check(_lib.lx_attention_small(C.byref(d), _stream()), "lx_attention_small")
         q, k, v = (t.float().view(B, S, H, 64).transpose(1, 2) for t in qkv.split(inner, dim=1))
         logits = q @ k.transpose(2, 3) * scale
