@@ -58,6 +58,9 @@ class OminiModel(nn.Module):
         self.flux_pipe = NativeFluxPipeline(self.transformer)
         if pretrained is not None and os.path.isdir(os.path.join(pretrained, "vae")):
             self.flux_pipe.attach_vae(pretrained)  # FluxPipeline.from_pretrained loads the VAE too (model.py:398-400)
+        if pretrained is not None and all(os.path.isdir(os.path.join(pretrained, d)) for d in
+                                          ("text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2")):
+            self.flux_pipe.attach_text_encoders(pretrained)  # ... and both text encoders with their tokenizers
         self.fuse_flag = fuse_flag
         self.use_brain_condition = use_brain_condition
         self.eeg_fixed_length, self.fnirs_fixed_length, self.ppg_fixed_length, self.motion_fixed_length = 4096, 512, 256, 128

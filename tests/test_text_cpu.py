@@ -112,3 +112,44 @@ def test_distance_table_equals_the_full_bias():
         table = w[by_distance].t()
         idx = torch.arange(S)[None, :] - torch.arange(S)[:, None] + S - 1
         assert torch.equal(table[:, idx], w[T.t5_relative_buckets(S)].permute(2, 0, 1))
+
+
+def test_text_encoder_checkpoint_directories(tmp_path):
+    """<dir>/text_encoder (single safetensors file) and <dir>/text_encoder_2 (sharded, with index) in the layout
+    FluxPipeline.from_pretrained reads -> packed native weights (host-side packing only; no kernels run on the CPU)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from loongx_b200 import text as N
+
+    tcfg = T.T5Cfg(vocab_size=50, d_model=128, d_kv=64, num_heads=2, d_ff=256, num_layers=2)
+    ccfg = T.ClipCfg(vocab_size=50, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2, max_positions=77)
+    PT, PC = T.t5_init(tcfg, 1), T.clip_init(ccfg, 2)
+    PT["shared.weight"] = PT.pop("encoder.embed_tokens.weight")  # real T5 checkpoints may hold only the shared table
+    PC["text_model.embeddings.position_ids"] = torch.arange(77)[None]  # legacy buffer in older CLIP checkpoints: ignored
+    d1, d2 = tmp_path / "text_encoder", tmp_path / "text_encoder_2"
+    d1.mkdir()
+    d2.mkdir()
+    (d1 / "config.json").write_text(json.dumps({"vocab_size": 50, "hidden_size": 128, "intermediate_size": 256,
+                                                "num_hidden_layers": 2, "num_attention_heads": 2, "hidden_act": "quick_gelu",
+                                                "max_position_embeddings": 77, "eos_token_id": 2}))
+    save_file({k: v.contiguous() for k, v in PC.items()}, str(d1 / "model.safetensors"))
+    (d2 / "config.json").write_text(json.dumps({"vocab_size": 50, "d_model": 128, "d_kv": 64, "num_heads": 2, "d_ff": 256,
+                                                "num_layers": 2, "feed_forward_proj": "gated-gelu"}))
+    keys = sorted(PT)
+    shards = {"model-00001-of-00002.safetensors": keys[: len(keys) // 2], "model-00002-of-00002.safetensors": keys[len(keys) // 2:]}
+    for fn, ks in shards.items():
+        save_file({k: PT[k].contiguous() for k in ks}, str(d2 / fn))
+    (d2 / "model.safetensors.index.json").write_text(json.dumps({"weight_map": {k: fn for fn, ks in shards.items() for k in ks}}))
+    clip, t5 = N.load_text_encoders(str(tmp_path), device="cpu")
+    assert t5.cfg == N.T5Config(50, 128, 64, 2, 256, 2) and clip.cfg.hidden_size == 128
+    assert torch.equal(t5.embed, PT["shared.weight"].to(torch.bfloat16))
+    a = "encoder.block.1.layer.0.SelfAttention."
+    assert torch.equal(t5.layers[1]["qkv"][128:256], PT[a + "k.weight"].to(torch.bfloat16))
+    assert t5.layers[0]["wi"].shape == (512, 128) and t5.rel_bias.shape == (32, 2)
+    p = "text_model.encoder.layers.0."
+    assert torch.equal(clip.layers[0]["qkv_b"][256:], PC[p + "self_attn.v_proj.bias"])
+    # quick_gelu folding: fc1 carries the factor 1.702, fc2 its inverse
+    assert torch.allclose(clip.layers[0]["fc1_b"], PC[p + "mlp.fc1.bias"] * 1.702)
+    assert torch.allclose(clip.layers[0]["fc2"].float(), (PC[p + "mlp.fc2.weight"] / 1.702).to(torch.bfloat16).float())
