@@ -513,10 +513,21 @@ class ImageProcessor:
 
         if not isinstance(images, (list, tuple)):
             images = [images]
-        arr = np.stack([np.asarray(im.convert("RGB"), dtype=np.float32) / 255.0 for im in images], 0)
-        if arr.shape[1] % self.vae_scale_factor or arr.shape[2] % self.vae_scale_factor:
-            raise ValueError(f"image size {arr.shape[1]}x{arr.shape[2]} must be a multiple of {self.vae_scale_factor} "
-                             "(resizing is outside this build)")
+        f = self.vae_scale_factor
+        fitted = []
+        for im in images:  # VaeImageProcessor(do_resize=True): down to the next multiple of vae_scale_factor, lanczos
+            w, h = im.size
+            w2, h2 = w - w % f, h - h % f
+            if w2 == 0 or h2 == 0:
+                raise ValueError(f"image size {w}x{h} is smaller than the VAE scale factor {f}")
+            if (w2, h2) != (w, h):
+                from PIL import Image
+
+                im = im.resize((w2, h2), resample=Image.LANCZOS)
+            fitted.append(np.asarray(im.convert("RGB"), dtype=np.float32) / 255.0)
+        if len({a.shape for a in fitted}) != 1:
+            raise ValueError("images of one batch must have the same size")
+        arr = np.stack(fitted, 0)
         return 2.0 * torch.from_numpy(arr).permute(0, 3, 1, 2).contiguous() - 1.0
 
     def postprocess(self, image: torch.Tensor, output_type: str = "pil"):

@@ -1,7 +1,7 @@
 """Drop-in for the reference's src/flux/condition.py (Condition, condition_dict; condition.py:10-138).
 
-Image pre-processing (canny / depth / blur, condition.py:53-90) and the VAE are outside this build; a Condition is
-constructed from already-encoded latents ([B, 16, h, w]) or packed tokens ([B, N, 64]).  The position arithmetic on the
+A Condition is built from a raw picture (PIL; pre-processed on the host like condition.py:53-90 and VAE-encoded when
+the pipeline has a VAE attached), from already-encoded latents ([B, 16, h, w]) or from packed tokens ([B, N, 64]).  The position arithmetic on the
 ids (condition.py:126-137) is kept operation for operation so the resulting ids are bit-identical.
 """
 from typing import Tuple
@@ -15,6 +15,39 @@ _TYPE_IDS = (("depth", 0), ("canny", 1), ("subject", 4), ("coloring", 6), ("debl
              ("sr", 10), ("cartoon", 11), ("eeg+fnirs", 12))
 condition_dict = dict(_TYPE_IDS)
 _IMAGE_TYPES = tuple(name for name, _ in _TYPE_IDS if name != "eeg+fnirs")  # the types encode() accepts (condition.py:110-120)
+
+
+def _rgb(img):
+    return img.convert("RGB")
+
+
+def _gray(img):  # "coloring": the luminance image, as three equal channels
+    return img.convert("L").convert("RGB")
+
+
+def _blurred(img):  # "deblurring": Gaussian blur of radius 10
+    from PIL import ImageFilter
+
+    return _rgb(_rgb(img).filter(ImageFilter.GaussianBlur(10)))
+
+
+def _canny(img):  # "canny": OpenCV edges with thresholds (100, 200)
+    import cv2
+    import numpy as np
+    from PIL import Image
+
+    return _rgb(Image.fromarray(cv2.Canny(np.array(img), 100, 200)))
+
+
+def _depth(img):
+    raise NotImplementedError("'depth' runs a depth-estimation network (LiheYoung/depth-anything-small-hf through "
+                              "transformers.pipeline, condition.py:59-68): not part of this build, pass the depth map as "
+                              "`condition=` instead")
+
+
+# condition type -> raw picture -> condition picture (condition.py:59-89)
+_PREPROCESS = {"depth": _depth, "canny": _canny, "subject": lambda img: img, "coloring": _gray, "deblurring": _blurred,
+               "fill": _rgb, "cartoon": _rgb}
 
 
 def _shift_scale_ids(ids: torch.Tensor, delta, scale: float) -> torch.Tensor:
@@ -48,9 +81,14 @@ class Condition(object):
         assert mask is None, "Mask not supported yet"
 
     def get_condition(self, condition_type: str, raw_img):
+        """condition.py:53-90: the condition image derived from the raw picture (host-side PIL / OpenCV work, once per
+        edit).  Tensors (already-encoded latents or [0, 1] pictures) pass through untouched."""
         if isinstance(raw_img, torch.Tensor):
             return raw_img
-        raise NotImplementedError("PIL / OpenCV condition pre-processing is outside this build; pass encoded latents")
+        prepare = _PREPROCESS.get(condition_type)
+        if prepare is None:  # the reference falls through to `self.condition`, which does not exist yet at this point
+            raise NotImplementedError(f"no image preprocessing for condition type {condition_type!r}")
+        return prepare(raw_img)
 
     @property
     def type_id(self) -> int:

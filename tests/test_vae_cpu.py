@@ -162,8 +162,9 @@ def test_image_processor_preprocess_on_host():
     im = PIL.new("RGB", (32, 16), (255, 0, 128))
     t = ip.preprocess(im)
     assert t.shape == (1, 3, 16, 32) and torch.allclose(t[0, :, 0, 0], torch.tensor([1.0, -1.0, 2 * 128 / 255 - 1]), atol=1e-6)
+    assert ip.preprocess(PIL.new("RGB", (30, 16))).shape == (1, 3, 16, 16)  # resized down to the 16-pixel grid
     with pytest.raises(ValueError):
-        ip.preprocess(PIL.new("RGB", (30, 16)))
+        ip.preprocess(PIL.new("RGB", (30, 8)))
     assert ip.postprocess(x, "latent") is x
 
 

@@ -244,3 +244,43 @@ def test_generate_decodes_through_the_pipeline():
     want_lat = O.encode(P, O.preprocess(pic).to(torch.bfloat16).float(), ocfg, eps.cpu())
     want_tokens = pipe._pack_latents(want_lat.cuda().to(pipe.dtype))
     assert _rel(tokens, want_tokens) <= 3e-2, _rel(tokens, want_tokens)
+
+
+def test_condition_from_a_raw_picture():
+    """inference.py:86-98: Condition("subject", raw_img=PIL) -> host preprocessing -> image_processor.preprocess -> native VAE
+    encode -> tokens + shifted ids, and generate() runs on it."""
+    import numpy as np
+    from PIL import Image
+
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.vae import VaeConfig, synthetic_params
+    from oracle import sampler as OS
+    from src.flux.condition import Condition
+    from src.flux.generate import generate
+    from src.train.model import OminiModel
+
+    O, ocfg = _ocfg()
+    cfg = FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2)
+    model = OminiModel(cfg, lora_config={"r": 4, "lora_alpha": 4}, device="cuda", model_config={})
+    pipe = model.flux_pipe
+    pipe.attach_vae(None, seed=1234)
+    P = synthetic_params(VaeConfig(), 1234)
+    rng = np.random.default_rng(1)
+    pic = Image.fromarray(rng.integers(0, 255, (128, 256, 3), dtype=np.uint8))  # 256 wide, 128 high
+    cond = Condition("coloring", raw_img=pic, position_delta=[0, -16])
+    torch.manual_seed(11)
+    tokens, ids, type_id = cond.encode(pipe)
+    assert tokens.shape == (1, 8 * 16, 64) and ids.shape == (128, 3) and int(type_id[0]) == 6
+    assert torch.equal(ids[:, 2].cpu().float(), (OS.prepare_latent_image_ids(16, 32)[:, 2] - 16).float())
+    torch.manual_seed(11)
+    eps = torch.randn(1, 16, 16, 32, device="cuda")
+    gray = np.asarray(pic.convert("L").convert("RGB"), dtype=np.float32) / 255.0
+    x = (2 * torch.from_numpy(gray).permute(2, 0, 1)[None] - 1).to(torch.bfloat16).float()
+    want = pipe._pack_latents(O.encode(P, x, ocfg, eps.cpu()).cuda().to(pipe.dtype))
+    assert _rel(tokens, want) <= 3e-2, _rel(tokens, want)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pe, po = (0.1 * torch.randn(1, 512, 4096, generator=g, device="cuda")).bfloat16(), torch.randn(1, 768, generator=g, device="cuda").bfloat16()
+    out = generate(model, pipe, conditions=[cond], prompt_embeds=pe, pooled_prompt_embeds=po, height=128, width=256,
+                   num_inference_steps=2, output_type="pil", default_lora=True, use_brain_condition=False,
+                   generator=torch.Generator(device="cuda").manual_seed(1)).images
+    assert len(out) == 1 and out[0].size == (256, 128)
