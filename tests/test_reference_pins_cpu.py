@@ -123,3 +123,24 @@ def test_reference_generate_rejects_two_conditions():
         G.generate(None, pipe, conditions=[c, c], model_config={"x": 1}, default_lora=True, use_brain_condition=False,
                    prompt_embeds=inp["pe"], pooled_prompt_embeds=inp["pooled"], height=64, width=128,
                    num_inference_steps=2, latents=inp["lat"], output_type="latent")
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference is not on this machine")
+def test_reference_condition_preprocessing_matches():
+    """condition.py:53-90 executed for real on a PIL picture: the drop-in's host-side preprocessing returns the same
+    pixels for every condition type that needs no network (subject, coloring, deblurring, canny, fill, cartoon)."""
+    import numpy as np
+
+    PIL = pytest.importorskip("PIL.Image")
+    pytest.importorskip("cv2")
+    from src.flux.condition import Condition
+
+    Cn = R.ref_module("flux.condition")
+    rng = np.random.default_rng(5)
+    pic = PIL.fromarray(rng.integers(0, 255, (48, 64, 3), dtype=np.uint8))
+    for kind in ("subject", "coloring", "deblurring", "canny", "fill", "cartoon"):
+        want = Cn.Condition(kind, raw_img=pic).condition
+        got = Condition(kind, raw_img=pic).condition
+        assert got.mode == want.mode and got.size == want.size, kind
+        assert np.array_equal(np.asarray(got), np.asarray(want)), kind
+    assert Cn.condition_dict == __import__("src.flux.condition", fromlist=["condition_dict"]).condition_dict
