@@ -3,28 +3,39 @@ import torch
 from torch import Tensor
 
 
-def encode_images(pipeline, images: Tensor):
-    """pipeline_tools.py:7-30: VAE-encode -> (x - shift) * scale -> _pack_latents -> ids.
-
-    With a VAE attached (`pipeline.attach_vae(...)`) images go through the native encoder.  Already-encoded
-    latents [B, 16, h, w] are accepted either way and go through the same native pack kernel and the same id
-    construction, including the reference's diffusers-version fallback for the id grid size (pipeline_tools.py:22-29)."""
-    if isinstance(images, torch.Tensor) and images.dim() == 4 and images.shape[1] == 16:
-        latents = images.to(pipeline.device).to(pipeline.dtype)
-    elif pipeline.vae is None:
+def _to_latents(pipeline, images) -> Tensor:
+    """Pictures -> scaled VAE latents [B, 16, h, w] (pipeline_tools.py:8-13).  Tensors that already are latents (16
+    channels) skip the VAE; without a VAE only those are accepted."""
+    already_encoded = isinstance(images, Tensor) and images.dim() == 4 and images.shape[1] == 16
+    if already_encoded:
+        return images.to(pipeline.device).to(pipeline.dtype)
+    vae = pipeline.vae
+    if vae is None:
         raise NotImplementedError("no VAE attached (pipeline.attach_vae): pass pre-encoded latents [B, 16, h, w]")
-    else:
-        images = pipeline.image_processor.preprocess(images)
-        images = images.to(pipeline.device).to(pipeline.dtype)
-        latents = pipeline.vae.encode(images).latent_dist.sample()
-        latents = (latents - pipeline.vae.config.shift_factor) * pipeline.vae.config.scaling_factor
+    pixels = pipeline.image_processor.preprocess(images).to(pipeline.device).to(pipeline.dtype)
+    z = vae.encode(pixels).latent_dist.sample()
+    return (z - vae.config.shift_factor) * vae.config.scaling_factor
+
+
+def _ids_for(pipeline, latents: Tensor, n_tokens: int) -> Tensor:
+    """Position ids of the packed tokens; the reference retries with the halved grid when its diffusers version counts
+    the latent grid in pixels rather than in 2x2 patches (pipeline_tools.py:15-29)."""
+    B, _, h, w = latents.shape
+    for grid in ((h, w), (h // 2, w // 2)):
+        ids = pipeline._prepare_latent_image_ids(B, grid[0], grid[1], pipeline.device, pipeline.dtype)
+        if ids.shape[0] == n_tokens:
+            break
+    return ids
+
+
+def encode_images(pipeline, images: Tensor):
+    """pipeline_tools.py:7-30: VAE-encode -> (x - shift) * scale -> _pack_latents -> ids, as (tokens [B, N, 64], ids [N, 3]).
+
+    With a VAE attached (`pipeline.attach_vae(...)`) pictures go through the native encoder; latents go
+    straight to the native pack kernel."""
+    latents = _to_latents(pipeline, images)
     tokens = pipeline._pack_latents(latents, *latents.shape)
-    ids = pipeline._prepare_latent_image_ids(latents.shape[0], latents.shape[2], latents.shape[3], pipeline.device,
-                                             pipeline.dtype)
-    if tokens.shape[1] != ids.shape[0]:
-        ids = pipeline._prepare_latent_image_ids(latents.shape[0], latents.shape[2] // 2, latents.shape[3] // 2,
-                                                 pipeline.device, pipeline.dtype)
-    return tokens, ids
+    return tokens, _ids_for(pipeline, latents, tokens.shape[1])
 
 
 def prepare_text_input(pipeline, prompts, max_sequence_length=512):

@@ -204,3 +204,24 @@ def test_vae_checkpoint_directory_round_trip(tmp_path):
     bad["decoder.conv_in.weight"] = bad["decoder.conv_in.weight"][:, :8]
     with pytest.raises(ValueError, match="decoder.conv_in"):
         V.VaeWeights(cfg, bad, "cpu")
+
+
+def test_encode_images_ids_fallback_on_host():
+    """encode_images' id construction incl. the reference's retry with the halved grid (pipeline_tools.py:15-29), with a
+    torch-only pipeline stand-in (latents in, so no VAE and no kernels are involved)."""
+    from oracle import sampler as OS
+    from src.flux.pipeline_tools import encode_images
+
+    class _Pipe:
+        device, dtype, vae = "cpu", torch.float32, None
+        _pack_latents = staticmethod(lambda lat, *a: OS.pack_latents(lat))
+        _prepare_latent_image_ids = staticmethod(lambda B, h, w, dev, dt: OS.prepare_latent_image_ids(h, w).to(dt))
+
+    class _Legacy(_Pipe):  # a diffusers flavour that counts the id grid per latent pixel
+        _prepare_latent_image_ids = staticmethod(lambda B, h, w, dev, dt: torch.zeros(h * w, 3))
+
+    z = torch.randn(2, 16, 8, 12, generator=torch.Generator().manual_seed(0))
+    tokens, ids = encode_images(_Pipe(), z)
+    assert torch.equal(tokens, OS.pack_latents(z)) and torch.equal(ids, OS.prepare_latent_image_ids(8, 12))
+    tokens, ids = encode_images(_Legacy(), z)
+    assert ids.shape == (24, 3)
