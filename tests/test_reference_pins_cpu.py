@@ -144,3 +144,50 @@ def test_reference_condition_preprocessing_matches():
         assert got.mode == want.mode and got.size == want.size, kind
         assert np.array_equal(np.asarray(got), np.asarray(want)), kind
     assert Cn.condition_dict == __import__("src.flux.condition", fromlist=["condition_dict"]).condition_dict
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference is not on this machine")
+def test_reference_encoder_gradients_match_the_oracle():
+    """Groundwork for the encoder-gradient gap of a17: after the reference's own `step()` +
+    `loss.backward()` with brain conditioning, the gradients autograd leaves on the CS3 / DGF parameters (which the
+    reference never hands to its optimizer, model.py:533-541) equal torch autograd over the oracle's restatement."""
+    import types
+
+    from oracle import flux_dit as O
+    from oracle import train_step as TS
+
+    name, c = next((n, c) for n, c in MR.STEP_CASES.items() if c["brain"] and c["fuse"])
+    cfg = O.FluxConfig(**MR.TINY_BRAIN)
+    P = MR.dit_params(cfg)
+    batch = MR.step_batch(cfg, True, c["seed"])
+    nc = MR.make_conditioner()
+    # reference side: same assembly as make_ref_golden.ref_step, keeping the model to read the encoder gradients
+    model, _ = MR.ref_omini_model(nc, d1=False)
+    tr = R.build_transformer(P, cfg)
+    pipe = R.FluxPipeline(tr)
+    pipe.vae = R._PrecomputedVae(shift=0.0, scale=1.0)
+    pipe.image_processor = types.SimpleNamespace(preprocess=lambda z: z)
+    object.__setattr__(model, "flux_pipe", pipe)
+    object.__setattr__(model, "transformer", tr)
+    model.model_config, model.use_brain_condition, model.fuse_flag, model._dtype = {}, True, True, torch.float32
+    type(model).device = property(lambda self: torch.device("cpu"))
+    b = dict(image=batch["image"], condition=batch["condition"], condition_type=batch["condition_type"],
+             description=(batch["prompt_embeds"], batch["pooled_prompt_embeds"]), position_delta=batch["position_delta"],
+             **{k: batch[k] for k in ("eeg", "fnirs", "ppg", "motion")})
+    torch.manual_seed(c["seed"])
+    model.step(b).backward()
+    ref_grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    # oracle side
+    for p in nc.parameters():
+        p.grad = None
+    torch.manual_seed(c["seed"])
+    loss, _ = TS.flow_step(P, cfg, batch, model_config={}, conditioner=nc, use_brain_condition=True, fuse_flag=True)
+    params = dict(nc.named_parameters())
+    got = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+    ora_grads = {n: g for n, g in zip(params, got) if g is not None}
+    shared = sorted(set(ref_grads) & set(ora_grads))
+    assert len(shared) > 50, (len(ref_grads), len(ora_grads))
+    assert {n.split(".")[0] for n in shared} >= {"eeg_projection", "ppg_projection", "fnirs_projection", "motion_projection",
+                                                 "duan_norm1", "duan_norm2", "fusion3", "fusion4"}
+    worst = max(float((ref_grads[n] - ora_grads[n]).norm() / (ref_grads[n].norm() + 1e-30)) for n in shared)
+    assert worst <= 1e-5, worst
