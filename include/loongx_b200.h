@@ -25,6 +25,13 @@ int lx_version(void);
 /* Device properties the host layer needs for grid sizing: out[0]=SM count, out[1]=cc major, out[2]=cc minor. */
 int lx_device_info(int32_t* out3);
 
+/* Optional exchange workspace for the split-work schedules of lx_attention and lx_gemm_bf16 (a tile whose work is cut
+ * between two CTAs is finished by one of them from the other's fp32 partial).  `ptr`: 1024-byte-aligned device buffer of
+ * `bytes` (64 MiB covers every shape of the DiT path), owned by the caller and bound to `stream`: only launches on that
+ * stream use it, everything else (and every launch when no workspace is registered) runs the unsplit schedule with
+ * identical results up to fp32 summation order.  The call enqueues a small memset on `stream`; ptr = NULL unregisters. */
+int lx_set_workspace(void* ptr, int64_t bytes, void* stream);
+
 /* Launch accounting (bench.py's gpu_launches / roofline): kernel classes 0 = tcgen05 GEMM, 1 = attention, 2 = DiT row
  * kernels, 3 = CS3/DGF kernels; cls < 0 = all.  lx_profile_begin() switches on CUDA-event timing of every launch (on
  * the stream it is launched on); lx_profile_end() synchronises and returns per-class totals in arrays of 4:

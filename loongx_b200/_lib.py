@@ -107,6 +107,35 @@ if _os.environ.get("LX_RASTER_MB"):  # development aid: L2 budget of the GEMM ra
     lib.lx_debug_gemm_raster_budget_mb(int(_os.environ["LX_RASTER_MB"]))
 
 
+lib.lx_set_workspace.argtypes = [c_void_p, c_int64, c_void_p]
+lib.lx_debug_attention_ctas.argtypes = [c_int]
+
+WORKSPACE_BYTES = 64 << 20  # exchange buffer of the split-work attention / GEMM schedules (lx_set_workspace)
+_ws_cache: dict = {}
+_ws_key = None
+
+
+def current_stream() -> int:
+    """Raw handle of torch's current CUDA stream.  The first call on a (device, stream) pair allocates the 64 MiB
+    exchange workspace of the split-work kernels from the torch allocator and binds it to that stream; the library
+    holds one binding at a time, so switching streams re-binds (launches on any other stream run unsplit)."""
+    import torch
+
+    global _ws_key
+    s = torch.cuda.current_stream()
+    key = (s.device.index, s.cuda_stream)
+    if key != _ws_key:
+        buf = _ws_cache.get(key)
+        if buf is None:
+            if torch.cuda.is_current_stream_capturing():
+                return s.cuda_stream  # no allocation inside a graph capture: unsplit schedule
+            buf = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=s.device)
+            _ws_cache[key] = buf
+        check(lib.lx_set_workspace(buf.data_ptr(), buf.numel(), s.cuda_stream), "lx_set_workspace")
+        _ws_key = key
+    return s.cuda_stream
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         raise LoongXNativeError(f"{what} failed ({rc}): {lib.lx_last_error().decode()}")

@@ -19,6 +19,8 @@
 // Replaces F.scaled_dot_product_attention + the q/k/v concat + head transpose at block.py:70-72,102-104,129-135,
 // including the optional block masks (block.py:106-120) and the log(c_factor) bias (block.py:121-128), which are
 // uniform per 128x128 tile because every stream length is a multiple of 128.
+#include <string.h>
+
 #include "host_util.cuh"
 #include "ptx.cuh"
 #include "tmem_wide.cuh"
@@ -33,16 +35,89 @@ constexpr int ATT_KV_STAGES = 2;
 #define ATT_POLY_OF_8 2
 #endif
 constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA warp + MMA warp (+2 idle); warpgroups 1, 2: softmax of tiles A, B
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
+// Q (2 tiles) + K/V rings + ONE output staging tile shared by the two groups + barriers + alignment slack
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES + 1) + 1024 + 512;
+static_assert(ATT_SMEM <= 227 * 1024, "attention shared memory budget");
+// split-work exchange slot of one (CTA, query tile): un-normalised fp32 O[128 x 128] + (m, l)[128]
+constexpr int ATT_SLOT_FLOATS = 128 * 128 + 2 * 128;
+constexpr int ATT_WS_FLAG_BYTES = WS_FLAG_BYTES;  // flags [n_cta][2] at the start of the workspace region
 
 struct AttnParams {
-  long long* dbg;  // optional timeline buffer (development aid, NULL in production)
   long long* cta_trace;  // optional [n_ctas][6]: smid, t_entry, t_setup_done, t_first_s, t_loop_end, t_exit (CTA-level)
   lx_attn_desc_t d;
   float scale_log2;  // scale * log2(e)
   float bias_log2;   // cross_bias * log2(e)
-  int groups;        // query tiles per CTA (2, or 1 when the tile counts are odd)
+  int groups;        // query tiles per unit (2, or 1 when the tile counts are odd)
+  // ---- work list: unit = (batch, head, `groups` consecutive query tiles); its work = the visible KV tiles, one
+  //      iteration each.  Units are linearised (batch, head, unit) -> x in [0, total) counts KV iterations; CTA c owns
+  //      the contiguous range [lo(c), lo(c+1)).  split = 1: lo(c) = c*total/n_cta (balanced to one iteration; a unit cut
+  //      by a boundary is finished by the CTA that holds its first iteration, the others publish partials through the
+  //      workspace); split = 0: boundaries fall on unit boundaries.
+  int n_cta, split;
+  int units_rest, units_cond;  // units per head on the two sides of the rest | cond boundary
+  int it_rest, it_cond;        // KV iterations of a unit on each side
+  int kvb_cond;                // first KV tile visible to condition queries
+  int w_head;                  // iterations per (batch, head)
+  long long total;             // B * H * w_head
+  long long total_units;       // B * H * (units_rest + units_cond)
+  int* flags;                  // [n_cta][2]   (workspace; all zero between launches)
+  float* slots;                // [n_cta][2][ATT_SLOT_FLOATS]
 };
+
+struct AttnSeg {
+  int hh;      // batch * H + head
+  int qt0;     // first query tile of the unit
+  int kv0;     // first KV tile of this segment
+  int n;       // KV iterations in this segment
+  bool first;  // the segment starts at the unit's first iteration (this CTA finishes the unit)
+  bool last;   // the segment reaches the unit's last iteration
+  bool q_is_cond;
+  long long x_end;  // linear position of the unit's end
+};
+
+__device__ __forceinline__ long long attn_lo(const AttnParams& p, int c) {
+  if (c >= p.n_cta) return p.total;
+  if (p.split) return (long long)c * p.total / p.n_cta;
+  const long long U = (long long)c * p.total_units / p.n_cta;  // first unit of CTA c
+  const int uph = p.units_rest + p.units_cond;
+  const long long hh = U / uph;
+  const int u = (int)(U - hh * uph);
+  return hh * p.w_head + (u < p.units_rest ? u * p.it_rest : p.units_rest * p.it_rest + (u - p.units_rest) * p.it_cond);
+}
+// decode the segment that starts at linear position x and ends at the unit's end or at `hi`, whichever is first
+__device__ __forceinline__ AttnSeg attn_seg(const AttnParams& p, long long x, long long hi) {
+  AttnSeg s;
+  const long long hh = x / p.w_head;
+  const int rem = (int)(x - hh * p.w_head);
+  const int w_rest = p.units_rest * p.it_rest;
+  int u, it, n_it, kvb;
+  if (rem < w_rest) {
+    u = rem / p.it_rest; it = rem - u * p.it_rest; n_it = p.it_rest; kvb = 0;
+    s.q_is_cond = false;
+  } else {
+    const int r2 = rem - w_rest;
+    const int uc = r2 / p.it_cond;
+    it = r2 - uc * p.it_cond; u = p.units_rest + uc; n_it = p.it_cond; kvb = p.kvb_cond;
+    s.q_is_cond = true;
+  }
+  s.hh = (int)hh;
+  s.qt0 = u * p.groups;
+  s.kv0 = kvb + it;
+  s.x_end = x + (n_it - it);
+  s.n = (int)(min(s.x_end, hi) - x);
+  s.first = it == 0;
+  s.last = s.x_end <= hi;
+  return s;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // kPad: ragged streams (padding keys at the end of a stream's last tile are masked); a separate instantiation so that
 // the aligned case pays nothing for it.
@@ -57,36 +132,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sQ = smem;                                   // [2 groups]
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // [stages]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;    // [stages]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;          // 1
+  uint8_t* sO = sV + ATT_KV_STAGES * ATT_TILE_BYTES;    // output staging tile (both groups, in turn)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + ATT_TILE_BYTES);
+  uint64_t* q_full = bars;          // 1      Q tiles of the current segment landed
   uint64_t* k_full = bars + 1;      // [2]
   uint64_t* v_full = bars + 3;      // [2]
-  uint64_t* k_empty = bars + 5;     // [2] released by the commit after the last group's QK^T(it)
-  uint64_t* v_empty = bars + 7;     // [2] released by the commit after the last group's PV(it)
-  uint64_t* s_full = bars + 9;      // [2 groups] S_g(it) complete (and with it every earlier MMA, incl. PV_g(it-1))
-  uint64_t* p_full = bars + 11;     // [2 groups] P_g(it) packed into TMEM by all 128 rows
-  uint64_t* o_done = bars + 13;     // [2 groups] last PV_g complete
-  uint64_t* p_half = bars + 20;     // [2 groups] first 64 key columns of P_g(it) packed (PV k-slices 0..3 may start)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* k_empty = bars + 5;     // [2] released by the commit after the last group's QK^T(j)
+  uint64_t* v_empty = bars + 7;     // [2] released by the commit after the last group's PV(j)
+  uint64_t* s_full = bars + 9;      // [2 groups] S_g(j) complete (and with it every earlier MMA, incl. PV_g(j-1))
+  uint64_t* p_full = bars + 11;     // [2 groups] P_g(j) packed into TMEM by all 128 rows
+  uint64_t* o_done = bars + 13;     // [2 groups] last PV_g of a segment complete
+  uint64_t* p_half = bars + 15;     // [2 groups] first 64 key columns of P_g(j) packed (PV k-slices 0..3 may start)
+  uint64_t* o_free = bars + 17;     // [2 groups] O_g of the finished segment has been read out of TMEM (128 arrivals)
+  uint64_t* q_free = bars + 19;     // 1      every QK^T of the current segment has completed: Q may be overwritten
+  uint64_t* stage_free = bars + 20; // 1      the previous user's TMA store has finished reading the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const lx_attn_desc_t& d = p.d;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int G = p.groups;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int qt0 = blockIdx.x * G;  // first query tile of this CTA
+  const int cta = blockIdx.x;
   const int n_tiles = d.S / ATT_BKV;
   const int n_rest = (d.S - d.n_cond) / ATT_BKV;  // tiles of the non-condition part
-  // all query tiles of a CTA are on the same side of the rest|cond boundary (G == 2 only when n_rest is even)
-  const bool q_is_cond = qt0 >= n_rest;
-  int kv_begin = 0, kv_end = n_tiles;  // kv tile range visible to this CTA's query tiles
   const bool use_bias = p.bias_log2 != 0.0f;
-  if (!use_bias && d.n_cond > 0) {
-    if (q_is_cond && (d.mask_mode == 1 || d.mask_mode == 2)) kv_begin = n_rest;
-    if (!q_is_cond && d.mask_mode == 1) kv_end = n_rest;
-  }
-  const int n_it = kv_end - kv_begin;
-  const int head_row0 = (b * d.H + h) * d.S;  // first row of this head in the [(B*H*S), 128] view
+  const long long x_lo = attn_lo(p, cta), x_hi = attn_lo(p, cta + 1);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ);
@@ -94,6 +164,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmO);
     mbar_init(q_full, 1);
+    mbar_init(q_free, 1);
+    mbar_init(stage_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
@@ -103,6 +175,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&p_full[s], 128);
       mbar_init(&p_half[s], 128);
       mbar_init(&o_done[s], 1);
+      mbar_init(&o_free[s], 128);
     }
     fence_mbar_init();
   }
@@ -115,7 +188,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   long long* trace = nullptr;
   if (p.cta_trace != nullptr && threadIdx.x == 128) {  // first softmax thread of tile A
-    trace = p.cta_trace + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 6;
+    trace = p.cta_trace + (long long)cta * 6;
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     trace[0] = smid;
@@ -133,28 +206,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   reg_dealloc<96>();  // setmaxnreg: hand the producer warpgroup's registers to the softmax warpgroups
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, G * ATT_TILE_BYTES);
-      for (int g = 0; g < G; ++g) {
-        tma_load_2d(sQ + g * ATT_TILE_BYTES, &tmQ, q_full, 0, head_row0 + (qt0 + g) * ATT_BQ);
-        tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmQ, q_full, 64, head_row0 + (qt0 + g) * ATT_BQ);
-      }
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        const uint32_t par = ((it >> 1) & 1) ^ 1;
-        const int row = head_row0 + (kv_begin + it) * ATT_BKV;
-        mbar_wait(&k_empty[st], par);
-        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
-        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmK, &k_full[st], 0, row);
-        tma_load_2d(sK + st * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmK, &k_full[st], 64, row);
-        mbar_wait(&v_empty[st], par);
-        mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
-        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmV, &v_full[st], 0, row);
-        tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmV, &v_full[st], 64, row);
+      int j = 0, si = 0;  // global KV iteration / segment counters of this CTA
+      for (long long x = x_lo; x < x_hi; ++si) {
+        const AttnSeg sg = attn_seg(p, x, x_hi);
+        x += sg.n;
+        const int head_row0 = sg.hh * d.S;  // first row of this head in the [(B*H*S), 128] view
+        if (si > 0) mbar_wait(q_free, (si - 1) & 1);
+        mbar_expect_tx(q_full, G * ATT_TILE_BYTES);
+        for (int g = 0; g < G; ++g) {
+          tma_load_2d(sQ + g * ATT_TILE_BYTES, &tmQ, q_full, 0, head_row0 + (sg.qt0 + g) * ATT_BQ);
+          tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmQ, q_full, 64, head_row0 + (sg.qt0 + g) * ATT_BQ);
+        }
+        for (int it = 0; it < sg.n; ++it, ++j) {
+          const int st = j & 1;
+          const uint32_t par = ((j >> 1) & 1) ^ 1;
+          const int row = head_row0 + (sg.kv0 + it) * ATT_BKV;
+          mbar_wait(&k_empty[st], par);
+          mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+          tma_load_2d(sK + st * ATT_TILE_BYTES, &tmK, &k_full[st], 0, row);
+          tma_load_2d(sK + st * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmK, &k_full[st], 64, row);
+          mbar_wait(&v_empty[st], par);
+          mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+          tma_load_2d(sV + st * ATT_TILE_BYTES, &tmV, &v_full[st], 0, row);
+          tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmV, &v_full[st], 64, row);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (elect_one() && x_lo < x_hi) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);  // A = Q (K-major), B = K (K-major)
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, false, true);   // A = P (TMEM),    B = V (MN-major)
       // Base descriptors are built once; per MMA only the 14-bit address field (bytes >> 4) is advanced, so the issue
@@ -162,9 +242,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint64_t q_desc0 = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t k_desc0 = make_sdesc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(sV), ATT_ATOM_BYTES, 1024);
-      auto issue_qk = [&](int g, int it) {
-        const int st = it & 1;
-        mbar_wait(&k_full[st], (it >> 1) & 1);
+      // S_g(j) = Q_g K_j^T.  seg_last_qk: j is the last iteration of its segment -> after the last group's QK^T the Q
+      // tiles are dead (q_free lets the producer fetch the next segment's Q)
+      auto issue_qk = [&](int g, int j, bool seg_last_qk) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint64_t qd = q_desc0 + (uint64_t)(g * (ATT_TILE_BYTES >> 4));
         const uint64_t kd = k_desc0 + (uint64_t)(st * (ATT_TILE_BYTES >> 4));
@@ -175,43 +257,67 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ss(ts_g, qd + off, kd + off, idesc_qk, kk != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[g]);
-        if (g == G - 1) umma_commit(&k_empty[st]);
-      };
-      const bool mma_dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-      mbar_wait(q_full, 0);
-      for (int g = 0; g < G; ++g) issue_qk(g, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        const uint64_t vd = v_desc0 + (uint64_t)(st * (ATT_TILE_BYTES >> 4));
-        for (int g = 0; g < G; ++g) {
-          const uint32_t to_g = tmem_O + g * 128, tp_g = tmem_S + g * 128;
-          mbar_wait(&v_full[st], (it >> 1) & 1);
-          // A: P_g[128 x 16] slice kk = 8 TMEM columns of packed bf16 pairs; B: V rows [16kk, 16kk+16) x 128 d
-          // (MN-major: LBO = next 64-d atom).  The first four k-slices start as soon as the first 64 key columns of P
-          // are packed, while the softmax threads are still exponentiating the other 64.
-          mbar_wait(&p_half[g], it & 1);
-          tc_fence_after();
-          if (it == 0) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk != 0 ? 1u : 0u);
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
-          }
-          mbar_wait(&p_full[g], it & 1);
-          tc_fence_after();
-          if (mma_dbg) p.dbg[(g * n_it + it) * 8 + 6] = clock64();
-#pragma unroll
-          for (int kk = 4; kk < 8; ++kk)
-            umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
-          if (g == G - 1) umma_commit(&v_empty[st]);
-          // S_g(it+1) overwrites the columns P_g(it) is read from: the tensor pipe executes in issue order
-          if (it + 1 < n_it) issue_qk(g, it + 1);
-          else umma_commit(&o_done[g]);
-          if (mma_dbg) p.dbg[(g * n_it + it) * 8 + 7] = clock64();
+        if (g == G - 1) {
+          umma_commit(&k_empty[st]);
+          if (seg_last_qk) umma_commit(q_free);
         }
+      };
+      int j = 0, si = 0;
+      long long x = x_lo;
+      AttnSeg sg = attn_seg(p, x, x_hi);
+      x += sg.n;
+      mbar_wait(q_full, 0);
+      for (int g = 0; g < G; ++g) issue_qk(g, 0, sg.n == 1);
+      for (;;) {
+        const bool has_next = x < x_hi;
+        AttnSeg nx = sg;
+        if (has_next) nx = attn_seg(p, x, x_hi);
+        for (int it = 0; it < sg.n; ++it, ++j) {
+          const int st = j & 1;
+          const bool first = it == 0, last = it == sg.n - 1;
+          const uint64_t vd = v_desc0 + (uint64_t)(st * (ATT_TILE_BYTES >> 4));
+          for (int g = 0; g < G; ++g) {
+            const uint32_t to_g = tmem_O + g * 128, tp_g = tmem_S + g * 128;
+            mbar_wait(&v_full[st], (j >> 1) & 1);
+            // a new segment overwrites O_g: the previous segment's epilogue must have read it out of TMEM
+            if (first && si > 0) mbar_wait(&o_free[g], (si - 1) & 1);
+            // A: P_g[128 x 16] slice kk = 8 TMEM columns of packed bf16 pairs; B: V rows [16kk, 16kk+16) x 128 d
+            // (MN-major: LBO = next 64-d atom).  The first four k-slices start as soon as the first 64 key columns of P
+            // are packed, while the softmax threads are still exponentiating the other 64.
+            mbar_wait(&p_half[g], j & 1);
+            tc_fence_after();
+            if (first) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
+            }
+            mbar_wait(&p_full[g], j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 4; kk < 8; ++kk)
+              umma_ts(to_g, tp_g + kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, 1u);
+            if (g == G - 1) umma_commit(&v_empty[st]);
+            if (last) umma_commit(&o_done[g]);
+            // S_g(j+1) overwrites the columns P_g(j) is read from: the tensor pipe executes in issue order
+            if (!last) {
+              issue_qk(g, j + 1, it + 1 == sg.n - 1);
+            } else if (has_next) {
+              if (g == 0) {
+                mbar_wait(q_full, (si + 1) & 1);  // the next segment's Q tiles
+                tc_fence_after();
+              }
+              issue_qk(g, j + 1, nx.n == 1);
+            }
+          }
+        }
+        if (!has_next) break;
+        sg = nx;
+        x += sg.n;
+        ++si;
       }
     }
     __syncwarp();
@@ -226,139 +332,208 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t ts = tmem_S + g * 128 + lane_off;  // S_g row (fp32) / packed P_g row (first 64 columns)
       const uint32_t to = tmem_O + g * 128 + lane_off;
-      float m_run = -INFINITY;  // running (possibly stale) max in log2 units
-      float l_run = 0.f;
-      const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                          quarter == 2;
-#define DBG(slot) if (dbg_on) p.dbg[(g * n_it + it) * 8 + (slot)] = clock64();
-      for (int it = 0; it < n_it; ++it) {
-        const bool cross = use_bias && (q_is_cond != ((kv_begin + it) >= n_rest));
-        const float bias = cross ? p.bias_log2 : 0.f;
-        DBG(0)
-        mbar_wait(&s_full[g], it & 1);
-        tc_fence_after();
-        DBG(1)
-        if (trace != nullptr && it == 0) trace[3] = clock64();
-        uint32_t v[128];
-        {
-          uint32_t(&v0)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[0]);
-          uint32_t(&v1)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[64]);
-          tmem_ld_32x32b_x64(ts, v0);
-          tmem_ld_32x32b_x64(ts + 64, v1);
-        }
-        if (kPad) {  // ragged streams: the last key tile of a stream may end in padding tokens -> -inf logits
-          const int kend = (kv_begin + it + 1) * ATT_BKV;
-          int nvalid = ATT_BKV;
-#pragma unroll
-          for (int s3 = 0; s3 < 3; ++s3)
-            if (kend == d.stream_end[s3]) nvalid -= d.pad[s3];
-          if (nvalid < ATT_BKV) {
-#pragma unroll
-            for (int j = 0; j < 128; ++j)
-              if (j >= nvalid) v[j] = 0xff800000u;
+      int j = 0, si = 0, n_staged = 0;
+      for (long long x = x_lo; x < x_hi; ++si) {
+        const AttnSeg sg = attn_seg(p, x, x_hi);
+        x += sg.n;
+        float m_run = -INFINITY;  // running (possibly stale) max in log2 units
+        float l_run = 0.f;
+        for (int it = 0; it < sg.n; ++it, ++j) {
+          const bool cross = use_bias && (sg.q_is_cond != ((sg.kv0 + it) >= n_rest));
+          const float bias = cross ? p.bias_log2 : 0.f;
+          mbar_wait(&s_full[g], j & 1);
+          tc_fence_after();
+          if (trace != nullptr && j == 0) trace[3] = clock64();
+          uint32_t v[128];
+          {
+            uint32_t(&v0)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[0]);
+            uint32_t(&v1)[64] = *reinterpret_cast<uint32_t(*)[64]>(&v[64]);
+            tmem_ld_32x32b_x64(ts, v0);
+            tmem_ld_32x32b_x64(ts + 64, v1);
           }
-        }
-        DBG(2)
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          if (kPad) {  // ragged streams: the last key tile of a stream may end in padding tokens -> -inf logits
+            const int kend = (sg.kv0 + it + 1) * ATT_BKV;
+            int nvalid = ATT_BKV;
 #pragma unroll
-        for (int j = 0; j < 128; j += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(v[j]));
-          mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(v[j + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(v[j + 3]));
+            for (int s3 = 0; s3 < 3; ++s3)
+              if (kend == d.stream_end[s3]) nvalid -= d.pad[s3];
+            if (nvalid < ATT_BKV) {
+#pragma unroll
+              for (int jj = 0; jj < 128; ++jj)
+                if (jj >= nvalid) v[jj] = 0xff800000u;
+            }
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int jj = 0; jj < 128; jj += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[jj]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[jj + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[jj + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[jj + 3]));
+          }
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          const float m_tile = mx * p.scale_log2 + bias;
+          float alpha = 1.0f;
+          bool rescale = false;
+          if (m_tile > m_run + 8.0f) {  // also true on the first tile (m_run = -inf)
+            alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile
+            m_run = m_tile;
+            rescale = it > 0;
+          }
+          // s_full(j) also covers PV_g(j-1): O_g is stable here
+          if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(to + c * 32, o);
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
+              tmem_st_32x32b_x32(to + c * 32, o);
+            }
+          }
+          float2 ls = make_float2(0.f, 0.f);
+          const float moff = bias - m_run;
+          const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), moff2 = make_float2(moff, moff);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              // packed fp32x2 FMA / ADD halve the issue slots; ATT_POLY_OF_8 of every 8 pairs are exponentiated by a
+              // polynomial on the FMA pipe, the rest by the MUFU
+              float2 xx = __ffma2_rn(make_float2(__uint_as_float(v[c * 32 + 2 * jj]), __uint_as_float(v[c * 32 + 2 * jj + 1])),
+                                     scale2, moff2);
+              float2 e;
+              if ((jj & 7) < ATT_POLY_OF_8) {
+                e = ex2_poly2(xx);
+              } else {
+                e.x = ex2_approx_ordered(xx.x);
+                e.y = ex2_approx_ordered(xx.y);
+              }
+              ls = __fadd2_rn(ls, e);
+              pk[jj] = pack_bf16(e.x, e.y);
+            }
+            tmem_st_32x32b_x16(ts + c * 16, pk);
+            if (c == 1) {
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&p_half[g]);
+            }
+          }
+          l_run = l_run * alpha + (ls.x + ls.y);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[g]);
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        const float m_tile = mx * p.scale_log2 + bias;
-        float alpha = 1.0f;
-        bool rescale = false;
-        if (m_tile > m_run + 8.0f) {  // also true on the first tile (m_run = -inf)
-          alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile
-          m_run = m_tile;
-          rescale = it > 0;
-        }
-        DBG(3)
-        // s_full(it) also covers PV_g(it-1): O_g is stable here
-        if (__any_sync(0xffffffffu, rescale)) {
+        // ---------------------------------------------------------------- end of segment
+        if (trace != nullptr && x >= x_hi) trace[4] = clock64();
+        mbar_wait(&o_done[g], si & 1);
+        tc_fence_after();
+        if (!sg.first) {
+          // The unit's first iterations belong to an earlier CTA: publish (m, l, un-normalised O) for it.  Layout
+          // [chunk][16-byte fragment][row]: a warp's 32 rows write 512 contiguous bytes per instruction.
+          float* slot = p.slots + ((size_t)cta * 2 + g) * ATT_SLOT_FLOATS;
+          float4* so = reinterpret_cast<float4*>(slot);
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
             tmem_ld_32x32b_x32(to + c * 32, o);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st_32x32b_x32(to + c * 32, o);
+            for (int q4 = 0; q4 < 8; ++q4)
+              so[(c * 8 + q4) * 128 + r] = make_float4(__uint_as_float(o[4 * q4]), __uint_as_float(o[4 * q4 + 1]),
+                                                      __uint_as_float(o[4 * q4 + 2]), __uint_as_float(o[4 * q4 + 3]));
           }
-        }
-        float2 ls = make_float2(0.f, 0.f);
-        const float moff = bias - m_run;
-        const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), moff2 = make_float2(moff, moff);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // packed fp32x2 FMA / ADD halve the issue slots; ATT_POLY_OF_8 of every 8 pairs are exponentiated by a
-            // polynomial on the FMA pipe, the rest by the MUFU
-            float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c * 32 + 2 * j]), __uint_as_float(v[c * 32 + 2 * j + 1])),
-                                  scale2, moff2);
-            float2 e;
-            if ((j & 7) < ATT_POLY_OF_8) {
-              e = ex2_poly2(x);
-            } else {
-              e.x = ex2_approx_ordered(x.x);
-              e.y = ex2_approx_ordered(x.y);
+          tc_fence_before();
+          mbar_arrive(&o_free[g]);
+          reinterpret_cast<float2*>(slot + 128 * 128)[r] = make_float2(m_run, l_run);
+          __threadfence();
+          asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+          if (r == 0) st_release_gpu(p.flags + cta * 2 + g, 1);
+        } else {
+          // This CTA finishes the unit.  If the unit continues in later CTAs' ranges, fold their partials in.
+          float a_self = 1.0f;
+          int c_end = cta + 1;
+          if (!sg.last) {
+            while (c_end < p.n_cta && attn_lo(p, c_end) < sg.x_end) ++c_end;
+            float m_all = m_run;
+            for (int cc = cta + 1; cc < c_end; ++cc) {
+              const int* fl = p.flags + cc * 2 + g;
+              if (ld_acquire_gpu(fl) == 0) {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(fl) == 0) {
+                  __nanosleep(200);
+                  if (clock64() - t0 > 8000000000LL) {
+                    printf("lx: attention partial of CTA %d never arrived (CTA %d)\n", cc, cta);
+                    __trap();
+                  }
+                }
+              }
+              const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.slots + ((size_t)cc * 2 + g) * ATT_SLOT_FLOATS + 128 * 128) + r);
+              m_all = fmaxf(m_all, ml.x);
             }
-            ls = __fadd2_rn(ls, e);
-            pk[j] = pack_bf16(e.x, e.y);
+            a_self = ex2_approx(m_run - m_all);
+            l_run *= a_self;
+            for (int cc = cta + 1; cc < c_end; ++cc) {
+              const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.slots + ((size_t)cc * 2 + g) * ATT_SLOT_FLOATS + 128 * 128) + r);
+              l_run += ml.y * ex2_approx(ml.x - m_all);
+            }
+            m_run = m_all;
           }
-          tmem_st_32x32b_x16(ts + c * 16, pk);
-          if (c == 1) {
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_half[g]);
-          }
-        }
-        l_run = l_run * alpha + (ls.x + ls.y);
-        DBG(4)
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[g]);
-        DBG(5)
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)
-          p.dbg[2 * n_it * 8 + (g * n_it + it) * 4 + quarter] = clock64();
-      }
-      // epilogue: O / l -> bf16 -> out rows
-      if (trace != nullptr) trace[4] = clock64();
-      const float inv_l = 1.0f / l_run;
-      if (d.lse != nullptr) d.lse[head_row0 + (qt0 + g) * ATT_BQ + r] = m_run + log2f(l_run);  // for lx_attention_bwd
-      mbar_wait(&o_done[g], 0);
-      tc_fence_after();
-      // O_g / l -> bf16 -> this tile's (now idle) Q buffer in the 128-byte-swizzled TMA layout -> two TMA stores of
-      // 128 rows x 64 columns: full-line writes instead of 16-byte fragments at a 6 KB row stride
-      uint8_t* stage = sQ + g * ATT_TILE_BYTES;
+          const float inv_l = 1.0f / l_run;
+          const int head_row0 = sg.hh * d.S;
+          if (d.lse != nullptr) d.lse[head_row0 + (sg.qt0 + g) * ATT_BQ + r] = m_run + log2f(l_run);  // for lx_attention_bwd
+          // O_g / l -> bf16 -> staging tile in the 128-byte-swizzled TMA layout -> two TMA stores of 128 rows x 64
+          // columns (full-line writes).  The staging tile is shared by the two groups: use number e waits for use e-1.
+          const int e = n_staged * G + g;
+          if (e > 0) mbar_wait(stage_free, (e - 1) & 1);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(to + c * 32, o);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(to + c * 32, o);
+            float f[32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(o[8 * j + 0]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
-          const int c16 = c * 4 + j;  // 16-byte chunk of the 256-byte output row
-          *reinterpret_cast<uint4*>(stage + (c16 >> 3) * ATT_ATOM_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = u;
+            for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(o[jj]) * a_self;
+            for (int cc = cta + 1; cc < c_end; ++cc) {
+              const float* slot = p.slots + ((size_t)cc * 2 + g) * ATT_SLOT_FLOATS;
+              const float bb = ex2_approx(__ldcg(reinterpret_cast<const float2*>(slot + 128 * 128) + r).x - m_run);
+              const float4* so = reinterpret_cast<const float4*>(slot);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 t = __ldcg(so + (c * 8 + q4) * 128 + r);
+                f[4 * q4 + 0] += t.x * bb;
+                f[4 * q4 + 1] += t.y * bb;
+                f[4 * q4 + 2] += t.z * bb;
+                f[4 * q4 + 3] += t.w * bb;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16(f[8 * q + 0] * inv_l, f[8 * q + 1] * inv_l);
+              u.y = pack_bf16(f[8 * q + 2] * inv_l, f[8 * q + 3] * inv_l);
+              u.z = pack_bf16(f[8 * q + 4] * inv_l, f[8 * q + 5] * inv_l);
+              u.w = pack_bf16(f[8 * q + 6] * inv_l, f[8 * q + 7] * inv_l);
+              const int c16 = c * 4 + q;  // 16-byte chunk of the 256-byte output row
+              *reinterpret_cast<uint4*>(sO + (c16 >> 3) * ATT_ATOM_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = u;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&o_free[g]);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+          if (r == 0) {
+            for (int cc = cta + 1; cc < c_end; ++cc) p.flags[cc * 2 + g] = 0;  // consumed: back to the idle state
+            const int b = sg.hh / d.H, h = sg.hh - b * d.H;
+            const int out_row0 = d.out_row_base[b * n_tiles + sg.qt0 + g];
+            const int col0 = d.col_offset + h * ATT_D;
+            tma_store_2d(&tmO, sO, col0, out_row0);
+            tma_store_2d(&tmO, sO + ATT_ATOM_BYTES, col0 + 64, out_row0);
+            tma_store_commit();
+            tma_store_wait_read<0>();  // the staging tile must outlive the bulk read; global visibility at kernel end
+            mbar_arrive(stage_free);
+          }
+          ++n_staged;
         }
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
-      if (warp == 4 + 4 * g && elect_one()) {
-        const int out_row0 = d.out_row_base[b * n_tiles + qt0 + g];
-        const int col0 = d.col_offset + h * ATT_D;
-        tma_store_2d(&tmO, stage, col0, out_row0);
-        tma_store_2d(&tmO, stage + ATT_ATOM_BYTES, col0 + 64, out_row0);
-        tma_store_commit();
-        tma_store_wait_read<0>();  // the staging buffer must outlive the bulk read; global visibility at kernel end
       }
     }
   }
@@ -374,11 +549,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace lx
 
-static long long* g_attn_dbg = nullptr;
 static long long* g_attn_trace = nullptr;
+static int g_attn_force_ctas = 0;
 extern "C" void lx_attention_debug_cta_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
-// development aid: per-iteration clock64 timeline of CTA (0,0,0): 8 slots per (query tile, KV iteration)
-extern "C" void lx_attention_debug_timeline(long long* device_buffer) { g_attn_dbg = device_buffer; }
+// development / test aid: pretend the device has n SMs (0 = automatic), so that small shapes exercise the split-work path
+extern "C" void lx_debug_attention_ctas(int n) { g_attn_force_ctas = n; }
 
 extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   using namespace lx;
@@ -404,14 +579,42 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   CUtensorMap tmO;  // output rows in the stream-major activation layout: [B*S, ldo], head h at columns col_offset + 128 h
   if ((rc = make_tmap_2d_bf16(&tmO, d.out, (uint64_t)d.B * d.S, (uint64_t)d.ldo, (uint64_t)d.ldo, 128, 64))) return rc;
   AttnParams p;
+  memset(&p, 0, sizeof(p));
   p.d = d;
-  p.dbg = g_attn_dbg;
   p.cta_trace = g_attn_trace;
   const float log2e = 1.4426950408889634f;
   p.scale_log2 = d.scale * log2e;
   p.bias_log2 = d.cross_bias * log2e;
   const int n_tiles = d.S / 128, n_rest = (d.S - d.n_cond) / 128;
-  p.groups = (n_tiles % 2 == 0 && n_rest % 2 == 0) ? 2 : 1;
+  const int q_tiles = d.q_tiles > 0 ? d.q_tiles : n_tiles;
+  LX_CHECK_ARG(q_tiles <= n_tiles, "lx_attention: q_tiles=%d exceeds S/128=%d", q_tiles, n_tiles);
+  // both query tiles of a unit lie on the same side of the rest | cond boundary
+  p.groups = (n_tiles % 2 == 0 && n_rest % 2 == 0 && q_tiles % 2 == 0) ? 2 : 1;
+  const int G = p.groups;
+  const bool masked = d.cross_bias == 0.f && d.n_cond > 0;
+  const int kv_end_rest = (masked && d.mask_mode == 1) ? n_rest : n_tiles;
+  p.kvb_cond = (masked && (d.mask_mode == 1 || d.mask_mode == 2)) ? n_rest : 0;
+  p.units_rest = (q_tiles < n_rest ? q_tiles : n_rest) / G;
+  p.units_cond = (q_tiles > n_rest ? q_tiles - n_rest : 0) / G;
+  p.it_rest = kv_end_rest;
+  p.it_cond = n_tiles - p.kvb_cond;
+  p.w_head = p.units_rest * p.it_rest + p.units_cond * p.it_cond;
+  p.total = (long long)d.B * d.H * p.w_head;
+  p.total_units = (long long)d.B * d.H * (p.units_rest + p.units_cond);
+  const int sms = g_attn_force_ctas > 0 ? g_attn_force_ctas : num_sms();
+  p.n_cta = (int)(p.total_units < sms ? p.total_units : sms);
+  // split the work to one KV iteration when there are more units than SMs (else: one unit per CTA is already balanced)
+  // and the caller registered an exchange workspace for this stream (lx_set_workspace)
+  p.split = 0;
+  if (p.total_units > p.n_cta) {
+    const size_t need = ATT_WS_FLAG_BYTES + (size_t)p.n_cta * 2 * ATT_SLOT_FLOATS * sizeof(float);
+    char* ws = static_cast<char*>(workspace_region(stream, 0, need));
+    if (ws != nullptr && p.n_cta * 2 * sizeof(int) <= (size_t)ATT_WS_FLAG_BYTES) {
+      p.split = 1;
+      p.flags = reinterpret_cast<int*>(ws);
+      p.slots = reinterpret_cast<float*>(ws + ATT_WS_FLAG_BYTES);
+    }
+  }
   const bool has_pad = (d.pad[0] | d.pad[1] | d.pad[2]) != 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -419,12 +622,9 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     LX_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  const int q_tiles = d.q_tiles > 0 ? d.q_tiles : n_tiles;
-  LX_CHECK_ARG(q_tiles <= n_tiles, "lx_attention: q_tiles=%d exceeds S/128=%d", q_tiles, n_tiles);
-  if (q_tiles % 2) p.groups = 1;
-  dim3 grid(q_tiles / p.groups, d.H, d.B);
+  dim3 grid(p.n_cta);
   double pairs = (double)d.S * d.S;  // visible (query, key) pairs per head
-  if (d.cross_bias == 0.f && d.n_cond > 0) {
+  if (masked) {
     const double nc = d.n_cond, nr = d.S - d.n_cond;
     if (d.mask_mode == 1) pairs = nc * nc + nr * nr;
     if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;

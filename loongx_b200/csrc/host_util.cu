@@ -127,6 +127,21 @@ int num_sms() {
   return n;
 }
 
+// ------------------------------------------------------------------------------------------- exchange workspace
+// One caller-owned buffer bound to one stream (lx_set_workspace).  The split-work kernels (attention, GEMM) exchange
+// partial tiles through it; a launch on any other stream, or with no / too small a workspace, uses the unsplit schedule.
+static void* g_ws_ptr = nullptr;
+static int64_t g_ws_bytes = 0;
+static void* g_ws_stream = nullptr;
+static bool g_ws_set = false;
+
+void* workspace_region(void* stream, int which, size_t need_bytes) {
+  if (!g_ws_set || stream != g_ws_stream || which < 0 || which >= WS_REGIONS) return nullptr;
+  const size_t region = (size_t)(g_ws_bytes / WS_REGIONS) & ~(size_t)1023;
+  if (need_bytes > region) return nullptr;
+  return static_cast<char*>(g_ws_ptr) + (size_t)which * region;
+}
+
 // ------------------------------------------------------------------------------------------- launch accounting
 struct ProfRec {
   cudaEvent_t e0, e1;
@@ -189,6 +204,27 @@ int lx_profile_end(double* ms, int64_t* launches, double* work) {
     cudaEventDestroy(r.e1);
   }
   lx::g_recs.clear();
+  return LX_OK;
+}
+
+int lx_set_workspace(void* ptr, int64_t bytes, void* stream) {
+  if (ptr == nullptr || bytes <= 0) {
+    lx::g_ws_set = false;
+    lx::g_ws_ptr = nullptr;
+    lx::g_ws_bytes = 0;
+    return LX_OK;
+  }
+  LX_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 1023) == 0, "lx_set_workspace: pointer must be 1024-byte aligned");
+  LX_CHECK_ARG(bytes >= (int64_t)lx::WS_REGIONS * (lx::WS_FLAG_BYTES + 1024), "lx_set_workspace: %lld bytes is too small",
+               (long long)bytes);
+  const size_t region = (size_t)(bytes / lx::WS_REGIONS) & ~(size_t)1023;
+  // the flag words at the head of every region start (and, by protocol, return to) zero
+  for (int i = 0; i < lx::WS_REGIONS; ++i)
+    LX_CUDA(cudaMemsetAsync(static_cast<char*>(ptr) + i * region, 0, lx::WS_FLAG_BYTES, static_cast<cudaStream_t>(stream)));
+  lx::g_ws_ptr = ptr;
+  lx::g_ws_bytes = bytes;
+  lx::g_ws_stream = stream;
+  lx::g_ws_set = true;
   return LX_OK;
 }
 

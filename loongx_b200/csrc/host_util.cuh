@@ -41,6 +41,12 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t outer, uint64
                       uint64_t outer_stride, uint32_t box_rows, uint32_t box_cols);
 
 int num_sms();
+// Exchange workspace registered with lx_set_workspace: region `which` (0 = attention, 1 = GEMM) if the workspace is bound
+// to `stream` and the region holds `need_bytes`, else nullptr.  Every region starts with WS_FLAG_BYTES of flag words that
+// are zero between launches.
+constexpr int WS_REGIONS = 2;
+constexpr int WS_FLAG_BYTES = 4096;
+void* workspace_region(void* stream, int which, size_t need_bytes);
 // Programmatic dependent launch switch (default on; lx_debug_set_pdl(0) turns it off for A/B timing).
 bool pdl_enabled();
 

@@ -77,7 +77,7 @@ _lib.lx_pack_latents.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, 
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return L.current_stream()
 
 
 # ---------------------------------------------------------------------------------------------------------------

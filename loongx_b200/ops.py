@@ -21,7 +21,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return L.current_stream()
 
 
 def make_tile_meta(batch: int, n_txt: int, n_img: int, n_cond: int, device) -> torch.Tensor:

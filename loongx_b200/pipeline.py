@@ -85,51 +85,109 @@ class NativeFluxTransformer:
 
     def load_lora_factors(self, lora: Dict[str, torch.Tensor]) -> int:
         """Overwrite LoRA factors in place (`<module>.lora_A.weight` / `.lora_B.weight`) and re-merge the affected
-        panels with the native merge kernel; returns the number of modules updated."""
+        panels with the native merge kernel; returns the number of modules updated.  A file whose rank differs from the
+        constructed one re-packs the weight set at the file's rank (peft's load_lora_weights accepts any rank)."""
         from .dit import PackedLinear
-        from .train import lora_merge, transpose
+        from .train import LoraFactor, lora_shared
 
-        seen = set()
+        targets = {}
         for panel in self.weights.named.values():
-            if not isinstance(panel, PackedLinear):
-                continue
-            for (name, row0, rows, A, Bw) in panel.lora:
-                ka, kb = name + ".lora_A.weight", name + ".lora_B.weight"
-                if ka not in lora and kb not in lora:
-                    continue
-                if lora[ka].shape != A.shape or lora[kb].shape != Bw.shape:
-                    raise ValueError(f"{name}: LoRA factors {tuple(lora[ka].shape)} / {tuple(lora[kb].shape)} do not match "
-                                     f"rank-{A.shape[0]} factors {tuple(A.shape)} / {tuple(Bw.shape)}")
-                A.copy_(lora[ka].to(device=A.device, dtype=A.dtype))
-                Bw.copy_(lora[kb].to(device=A.device, dtype=A.dtype))
-                lora_merge(panel.w[row0:row0 + rows], A, Bw, panel.w_lora[row0:row0 + rows], panel.scaling)
-                if panel.w_loraT is not None:
-                    transpose(panel.w_lora[row0:row0 + rows], panel.w_loraT[:, row0:row0 + rows])
-                seen.add(name)
-        unknown = {k.rsplit(".lora_", 1)[0] for k in lora} - seen
+            if isinstance(panel, PackedLinear):
+                for (name, row0, rows, A, Bw) in panel.lora:
+                    targets[name] = (panel, row0, rows, A, Bw)
+        mods = {k.rsplit(".lora_", 1)[0] for k in lora}
+        unknown = mods - set(targets)
         if unknown:
             raise KeyError(f"LoRA factors for modules that are not LoRA targets here: {sorted(unknown)[:4]}")
-        return len(seen)
+        for name in mods:
+            ka, kb = name + ".lora_A.weight", name + ".lora_B.weight"
+            if ka not in lora or kb not in lora:
+                raise KeyError(f"{name}: a LoRA checkpoint must hold both lora_A and lora_B (found only "
+                               f"{'lora_A' if ka in lora else 'lora_B'})")
+            if lora[ka].shape[0] != lora[kb].shape[1]:
+                raise ValueError(f"{name}: lora_A {tuple(lora[ka].shape)} and lora_B {tuple(lora[kb].shape)} disagree on the rank")
+        ranks = {lora[name + ".lora_A.weight"].shape[0] for name in mods}
+        if mods and ranks != {self.cfg.lora_rank}:
+            if len(ranks) != 1:
+                raise ValueError(f"LoRA checkpoint mixes ranks {sorted(ranks)}")
+            return self._repack_with_lora(lora, ranks.pop())
+        shared = lora_shared(self.weights)
+        scale = getattr(self.weights, "lora_scale", 1.0)
+        for name in mods:
+            panel, row0, rows, A, Bw = targets[name]
+            a, b = lora[name + ".lora_A.weight"], lora[name + ".lora_B.weight"]
+            if a.shape != A.shape or b.shape != Bw.shape:
+                raise ValueError(f"{name}: LoRA factors {tuple(a.shape)} / {tuple(b.shape)} do not match "
+                                 f"rank-{A.shape[0]} factors {tuple(A.shape)} / {tuple(Bw.shape)}")
+            with torch.no_grad():
+                shared[name].A.copy_(a.to(device=A.device, dtype=A.dtype))
+                shared[name].B.copy_(b.to(device=A.device, dtype=A.dtype))
+            LoraFactor(name, panel, row0, rows, shared[name]).remerge(scale)
+        return len(mods)
+
+    def _repack_with_lora(self, lora: Dict[str, torch.Tensor], rank: int) -> int:
+        """Rank change: export the flat parameter dict, swap the factors (targets missing from the file get fresh
+        zero-B factors of the new rank), re-pack.  alpha keeps its constructed value, so the scaling becomes alpha / rank
+        (what peft computes from the LoraConfig when the adapter is re-created at another rank)."""
+        from .config import lora_targets
+
+        P = self.weights.export_params()
+        for k in [k for k in P if ".lora_" in k]:
+            del P[k]
+        self.cfg.lora_rank = int(rank)
+        for name in lora_targets(self.cfg):
+            ka, kb = name + ".lora_A.weight", name + ".lora_B.weight"
+            if ka in lora:
+                P[ka], P[kb] = lora[ka].to(self.device).float(), lora[kb].to(self.device).float()
+        init_lora_factors(P, self.cfg, self.device)
+        self.load_params(P)
+        return len({k.rsplit(".lora_", 1)[0] for k in lora})
 
     def set_lora_scale(self, scale: float) -> None:
         """`joint_attention_kwargs["scale"]` (transformer.py:73-83: peft `scale_lora_layers(self, lora_scale)` around the
         forward): re-merge every LoRA-carrying panel as W + scale * (alpha / r) B A with the native merge kernel.  A no-op
         while the scale does not change; the reference's un-scaling at the end of the forward (transformer.py:246-248)
-        corresponds to calling this with 1.0 again."""
-        from .dit import PackedLinear
-        from .train import lora_merge, transpose
+        corresponds to calling this with 1.0 again.  The scale in force lives on the weight set (train.set_lora_scale)."""
+        from .train import set_lora_scale
 
-        scale = float(scale)
-        if scale == getattr(self, "_lora_scale", 1.0):
-            return
+        set_lora_scale(self.weights, scale)
+
+    def remerge_lora(self) -> None:
+        """Rebuild every merged panel from the current LoRA factors (after an optimizer step or an in-place edit of
+        `lora_parameters()`), at the LoRA scale in force."""
+        from .dit import PackedLinear
+        from .train import LoraFactor, lora_shared
+
+        shared = lora_shared(self.weights)
+        scale = getattr(self.weights, "lora_scale", 1.0)
         for panel in self.weights.named.values():
-            if not isinstance(panel, PackedLinear):
-                continue
-            for (_, row0, rows, A, Bw) in panel.lora:
-                lora_merge(panel.w[row0:row0 + rows], A, Bw, panel.w_lora[row0:row0 + rows], panel.scaling * scale)
-                if panel.w_loraT is not None:
-                    transpose(panel.w_lora[row0:row0 + rows], panel.w_loraT[:, row0:row0 + rows])
-        self._lora_scale = scale
+            if isinstance(panel, PackedLinear):
+                for (name, row0, rows, _A, _B) in panel.lora:
+                    LoraFactor(name, panel, row0, rows, shared[name]).remerge(scale)
+
+    def lora_parameters(self):
+        """model.py:513-524: the LoRA factors as nn.Parameters (one stable set per weight set)."""
+        from .train import lora_parameters
+
+        return lora_parameters(self.weights)
+
+    def to(self, *args, **kwargs):
+        """nn.Module.to for the calls the reference makes (inference.py:55-56, model.py:398): the native weights live in
+        HBM in bf16 and stay there; a CUDA target is accepted, anything else raises."""
+        device = kwargs.get("device", None)
+        dtype = kwargs.get("dtype", None)
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+            elif a is not None:
+                device = a
+        if device is not None and torch.device(device).type != "cuda":
+            raise NotImplementedError("the native DiT weights live in HBM: there is no CPU representation to move to")
+        if device is not None and torch.device(device).index not in (None, self.device.index):
+            raise NotImplementedError(f"the weights were packed on {self.device}; re-create the model on {device}")
+        if dtype not in (None, torch.bfloat16, torch.float32):
+            raise NotImplementedError(f"dtype {dtype}: the native DiT computes in bf16 with fp32 accumulation")
+        return self
 
     # -- nn.Module-like surface --------------------------------------------------------------------------------
     def named_modules(self):
@@ -294,13 +352,22 @@ class NativeFluxPipeline:
         if isinstance(generator, list) and len(generator) != batch_size:
             raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
                              f"effective batch size of {batch_size}.")
-        gen = generator[0] if isinstance(generator, list) else generator
-        gen_dev = gen.device if gen is not None else torch.device(device)
-        noise = torch.randn(shape, generator=gen, device=gen_dev, dtype=dtype).to(device)  # diffusers randn_tensor
+        if isinstance(generator, list):  # diffusers randn_tensor: sample i comes from generator[i]
+            noise = torch.cat([torch.randn((1,) + shape[1:], generator=g, device=g.device, dtype=dtype).to(device)
+                               for g in generator], dim=0)
+        else:
+            gen_dev = generator.device if generator is not None else torch.device(device)
+            noise = torch.randn(shape, generator=generator, device=gen_dev, dtype=dtype).to(device)
         return self._pack_latents(noise), ids
 
     def set_adapters(self, *args, **kwargs):  # LoRA adapters are merged into the cond row group at load
         return None
+
+    def to(self, *args, **kwargs):
+        """FluxPipeline.to(...) as the reference calls it (inference.py:56 `model.flux_pipe.to("cuda")`, model.py:398
+        `.to(dtype=dtype).to(device)`): every component already lives on the GPU."""
+        self.transformer.to(*args, **kwargs)
+        return self
 
     def attach_text_encoders(self, source=None, tokenizers=None, clip=None, t5=None):
         """Give the pipeline `text_encoder` (CLIP-L), `text_encoder_2` (T5-XXL) and their tokenizers so

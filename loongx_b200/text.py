@@ -40,7 +40,7 @@ _lib.lx_attention_small.argtypes = [C.POINTER(SmallAttnDesc), c_void_p]
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return L.current_stream()
 
 
 def _cuda(t: Optional[torch.Tensor]):

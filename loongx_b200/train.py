@@ -229,29 +229,79 @@ def sdpa_backward_library(q, k, v, d_out, n_cond: int, mask_mode: int, cross_bia
 # ------------------------------------------------------------------------------------------------------------------
 # trainable LoRA factors
 # ------------------------------------------------------------------------------------------------------------------
-class LoraFactor:
-    """One LoRA-targeted Linear: fp32 master factors living inside a PackedLinear panel.  dA / dB are views into the
-    trainer's single flat gradient buffer (one NCCL all-reduce covers every factor)."""
+class _LoraShared:
+    """Per weight set, per LoRA target: the nn.Parameter wrappers of the fp32 master factors (created ONCE, so that an
+    optimizer built from them keeps training the same objects whatever trainers come and go) and the factor versions the
+    merged panel was last built from."""
 
-    def __init__(self, name: str, panel: PackedLinear, row0: int, rows: int, A: torch.Tensor, Bw: torch.Tensor):
-        self.name, self.panel, self.row0, self.rows = name, panel, row0, rows
+    __slots__ = ("A", "B", "merged")
+
+    def __init__(self, A: torch.Tensor, Bw: torch.Tensor):
         self.A = torch.nn.Parameter(A, requires_grad=True)
         self.B = torch.nn.Parameter(Bw, requires_grad=True)
+        self.merged = (self.A._version, self.B._version)
+
+
+def lora_shared(weights: DitWeights) -> Dict[str, _LoraShared]:
+    """name -> shared Parameter record of every LoRA target of `weights` (cached on the weights object)."""
+    cache = weights.__dict__.setdefault("_lora_shared", {})
+    for panel in weights.named.values():
+        if not isinstance(panel, PackedLinear):
+            continue
+        for (name, _row0, _rows, A, Bw) in panel.lora:
+            if name not in cache:
+                cache[name] = _LoraShared(A, Bw)
+    return cache
+
+
+def set_lora_scale(weights: DitWeights, scale: float) -> None:
+    """peft `scale_lora_layers` (transformer.py:73-83): every merged panel becomes W + scale * (alpha / r) B A.  The scale
+    in force is ONE attribute of the weight set (`weights.lora_scale`): every later re-merge (optimizer step, load_lora)
+    uses it, and the training step resets it to 1 before its forward."""
+    scale = float(scale)
+    if scale == getattr(weights, "lora_scale", 1.0):
+        return
+    weights.lora_scale = scale
+    shared = lora_shared(weights)
+    for panel in weights.named.values():
+        if not isinstance(panel, PackedLinear):
+            continue
+        for (name, row0, rows, _A, _B) in panel.lora:
+            LoraFactor(name, panel, row0, rows, shared[name]).remerge(scale)
+
+
+def lora_parameters(weights: DitWeights) -> List[torch.nn.Parameter]:
+    """The trainable parameters of the reference's optimizer (model.py:513-524, 541): every LoRA factor, in a fixed
+    order.  Available before any training step and stable across batch geometries."""
+    out: List[torch.nn.Parameter] = []
+    for rec in lora_shared(weights).values():
+        out += [rec.A, rec.B]
+    return out
+
+
+class LoraFactor:
+    """One LoRA-targeted Linear: fp32 master factors living inside a PackedLinear panel.  dA / dB are views into the
+    trainer's single flat gradient buffer (one NCCL all-reduce covers every factor); the Parameters are shared by every
+    trainer of the weight set (`lora_shared`)."""
+
+    def __init__(self, name: str, panel: PackedLinear, row0: int, rows: int, shared: _LoraShared):
+        self.name, self.panel, self.row0, self.rows = name, panel, row0, rows
+        self.shared = shared
+        self.A, self.B = shared.A, shared.B
         self.dA: Optional[torch.Tensor] = None
         self.dB: Optional[torch.Tensor] = None
-        self._merged_version = (self.A._version, self.B._version)
 
-    def remerge(self):
-        """w_lora[rows] = bf16(W + s B A) (+ the transposed panel) after the factors changed."""
+    def remerge(self, lora_scale: float = 1.0):
+        """w_lora[rows] = bf16(W + lora_scale * s B A) (+ the transposed panel) after the factors changed."""
         p = self.panel
         lora_merge(p.w[self.row0:self.row0 + self.rows], self.A.data, self.B.data,
-                   p.w_lora[self.row0:self.row0 + self.rows], p.scaling)
+                   p.w_lora[self.row0:self.row0 + self.rows], p.scaling * lora_scale)
         if p.w_loraT is not None:
             transpose(p.w_lora[self.row0:self.row0 + self.rows], p.w_loraT[:, self.row0:self.row0 + self.rows])
-        self._merged_version = (self.A._version, self.B._version)
+        self.shared.merged = (self.A._version, self.B._version)
 
     def stale(self) -> bool:
-        return self._merged_version != (self.A._version, self.B._version)
+        return self.shared.merged != (self.A._version, self.B._version)
 
 
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
@@ -386,11 +436,12 @@ class DitTrainer:
             self.dmod_sgl_ti = torch.zeros_like(self.dmod_sgl)
         self.loss = torch.zeros((1,), device=dev, dtype=torch.float32)
         self.factors: Dict[str, LoraFactor] = {}
+        shared = lora_shared(weights)
         for key, panel in weights.named.items():
             if not isinstance(panel, PackedLinear):
                 continue
             for (name, row0, rows, A, Bw) in panel.lora:
-                self.factors[name] = LoraFactor(name, panel, row0, rows, A, Bw)
+                self.factors[name] = LoraFactor(name, panel, row0, rows, shared[name])
         n_grad = sum(f.A.numel() + f.B.numel() for f in self.factors.values())
         self.grad_flat = torch.zeros((n_grad,), device=dev, dtype=torch.float32)
         o = 0
@@ -426,12 +477,15 @@ class DitTrainer:
     def remerge(self):
         """Call after an optimizer step: rebuild every merged panel from the updated factors."""
         for f in self.factors.values():
-            f.remerge()
+            f.remerge(getattr(self.w, "lora_scale", 1.0))
 
     def remerge_if_stale(self):
+        """Before a training forward: panels at LoRA scale 1 (a generate(..., joint_attention_kwargs={"scale": s}) may
+        have left them at s) and rebuilt from the current factors."""
+        set_lora_scale(self.w, 1.0)
         for f in self.factors.values():
             if f.stale():
-                f.remerge()
+                f.remerge(1.0)
 
     def zero_grad(self):
         self.grad_flat.zero_()

@@ -44,7 +44,7 @@ _lib.lx_transpose_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return L.current_stream()
 
 
 def _cuda(t: torch.Tensor) -> int:
@@ -508,6 +508,10 @@ class ImageProcessor:
         already holds negative values is passed through, as diffusers does."""
         if isinstance(images, torch.Tensor):
             x = images if images.dim() == 4 else images[None]
+            f = self.vae_scale_factor
+            if x.shape[-2] % f or x.shape[-1] % f:  # VaeImageProcessor resizes tensors too; here: be explicit
+                raise ValueError(f"tensor images must have H, W divisible by {f} (got {tuple(x.shape[-2:])}); resize them "
+                                 "first (PIL inputs are resized like VaeImageProcessor does)")
             return x if x.min() < 0 else 2.0 * x - 1.0
         import numpy as np
 

@@ -22,16 +22,32 @@ class enable_lora:
 
 
 class set_lora_scale:
-    """lora_controller.py:45-75.  A LoRA scale other than 1 would need re-merging W + s (alpha/r) B A."""
+    """lora_controller.py:45-75: multiply the LoRA scaling of the listed modules by `scale` inside the `with` block and
+    restore it afterwards.  Native granularity: the handles generate() / block.py see (`transformer.transformer_blocks[i]`,
+    `.attn`, or the transformer itself) stand for whole blocks of ONE weight set whose merged panels
+    W + s (alpha/r) B A are rebuilt by the native merge kernel, so the scale applies to every LoRA target of the
+    transformer(s) the listed modules belong to; objects that are not native handles are skipped, like the reference
+    skips modules that are not peft `BaseTunerLayer`s.  (The reference never calls this class; it is API surface.)"""
 
     def __init__(self, lora_modules: List[Any], scale: float) -> None:
-        if scale != 1:
-            raise NotImplementedError("set_lora_scale(scale != 1): LoRA is merged into the condition-row weight panel at load")
         self.lora_modules = list(lora_modules)
-        self.scale = scale
+        self.scale = float(scale)
+        seen, self._transformers = set(), []
+        for m in self.lora_modules:
+            tr = m if hasattr(m, "set_lora_scale") and hasattr(m, "weights") else getattr(m, "transformer", None)
+            if tr is None and hasattr(m, "block"):
+                tr = getattr(m.block, "transformer", None)
+            if tr is not None and id(tr) not in seen:
+                seen.add(id(tr))
+                self._transformers.append(tr)
+        self.scales = [float(getattr(tr.weights, "lora_scale", 1.0)) for tr in self._transformers]
 
     def __enter__(self) -> None:
+        for tr, prev in zip(self._transformers, self.scales):
+            tr.set_lora_scale(prev * self.scale)
         return None
 
-    def __exit__(self, exc_type, exc_val, exc_tb) -> None:
+    def __exit__(self, exc_type: Optional[Type[BaseException]], exc_val: Optional[BaseException], exc_tb: Optional[Any]) -> None:
+        for tr, prev in zip(self._transformers, self.scales):
+            tr.set_lora_scale(prev)
         return None

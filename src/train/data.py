@@ -49,7 +49,7 @@ class SeedDataset(Dataset):
     def _image(self, rel_path):
         name = rel_path.split("/")[-1]
         if self.latent_dir is not None:
-            return torch.load(os.path.join(self.latent_dir, name + ".pt"), map_location="cpu")
+            return torch.load(os.path.join(self.latent_dir, name + ".pt"), map_location="cpu", weights_only=True)
         from PIL import Image
 
         img = Image.open(os.path.join(self.image_dir, rel_path)).convert("RGB")
@@ -76,7 +76,7 @@ class SeedDataset(Dataset):
             "motion": np.array(bio["Motion"]) if "Motion" in bio else None,
         }
         if self.embed_dir is not None:
-            out.update(torch.load(os.path.join(self.embed_dir, name + ".pt"), map_location="cpu"))
+            out.update(torch.load(os.path.join(self.embed_dir, name + ".pt"), map_location="cpu", weights_only=True))
         return out
 
 

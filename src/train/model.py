@@ -16,16 +16,52 @@ from loongx_b200.cs3 import DUAN, EEGEncoder, FeaturePyramidPooling, FNIRSEncode
 from loongx_b200.pipeline import NativeFluxPipeline, NativeFluxTransformer
 
 
+class _StagedPipeline:
+    """`model.flux_pipe` between `OminiModel(device="cpu")` and `model.to("cuda")` (inference.py:35-56): the native
+    engine has no host representation, so nothing is built yet; `.to("cuda")` here materialises the model as well."""
+
+    def __init__(self, owner: "OminiModel"):
+        self._owner = owner
+
+    def to(self, *args, **kwargs):
+        self._owner.to(*args, **kwargs)
+        return self._owner.flux_pipe
+
+    def __getattr__(self, name):
+        raise RuntimeError(f"flux_pipe.{name}: the model was created with device='cpu' and is only staged; call "
+                           "model.to('cuda') first (the native DiT has no CPU path)")
+
+
+def _parse_to(args, kwargs):
+    device, dtype = kwargs.get("device"), kwargs.get("dtype")
+    for a in args:
+        if isinstance(a, torch.dtype):
+            dtype = a
+        elif isinstance(a, torch.Tensor):
+            device, dtype = a.device, a.dtype
+        elif a is not None:
+            device = a
+    return (torch.device(device) if device is not None else None), dtype
+
+
 class OminiModel(nn.Module):
     def __init__(self, flux_pipe_id, lora_path: str = None, lora_config: dict = None, device: str = "cuda",
                  dtype: torch.dtype = torch.bfloat16, model_config: dict = {}, optimizer_config: dict = None,
                  gradient_checkpointing: bool = False, use_brain_condition: bool = True, fuse_flag: bool = True,
                  seed: int = 1234):
         """`flux_pipe_id`: a FluxConfig (random-init weights of that architecture, seeded) or the string "synthetic"
-        (FLUX.1-dev geometry), or a diffusers-format FLUX directory (transformer/ and, when present, vae/)."""
+        (FLUX.1-dev geometry), or a diffusers-format FLUX directory (transformer/ and, when present, vae/, text encoders).
+
+        `dtype`: torch.bfloat16 or torch.float32 (train/config/seed_512.yaml:2 says "float32", the only dtype the
+        reference's CS3 / DGF modules work in).  Either way the DiT computes in bf16 with fp32 accumulation (the native
+        engine's one precision) and CS3 / DGF in float32; the value is kept as `_dtype` like model.py:394.
+
+        `device`: "cuda[:i]" builds the native engine right away.  "cpu" (what inference.py:35-41 passes) STAGES the
+        model: the CS3 / DGF modules are created on the host, `load_lora` / `load_state_dict` are recorded, and
+        `model.to("cuda")` (inference.py:55) builds the native engine and replays them.  Nothing computes on the CPU."""
         super().__init__()
-        if dtype != torch.bfloat16:
-            raise NotImplementedError("the native DiT computes in bf16 (fp32 accumulate); CS3/DGF run in float32")
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise NotImplementedError(f"dtype {dtype}: the native DiT computes in bf16 (fp32 accumulate); CS3/DGF run in float32")
         import os
 
         r = int((lora_config or {}).get("r", 4))
@@ -47,23 +83,18 @@ class OminiModel(nn.Module):
         self.optimizer_config = optimizer_config
         self._dtype = dtype
         self._device = torch.device(device)
+        self._build_args = dict(cfg=cfg, pretrained=pretrained, r=r, alpha=alpha, seed=seed,
+                                gradient_checkpointing=gradient_checkpointing)
+        self._pending = []  # load_lora / load_state_dict calls recorded while staged
         torch.manual_seed(seed)
-        if pretrained is not None:
-            self.transformer = NativeFluxTransformer.from_pretrained(pretrained, device=device, lora_rank=r, lora_alpha=alpha,
-                                                                     seed=seed)
-            cfg = self.transformer.cfg
-        else:
-            self.transformer = NativeFluxTransformer(cfg, device=device, seed=seed)
-        self.transformer.gradient_checkpointing = gradient_checkpointing
-        self.flux_pipe = NativeFluxPipeline(self.transformer)
-        if pretrained is not None and os.path.isdir(os.path.join(pretrained, "vae")):
-            self.flux_pipe.attach_vae(pretrained)  # FluxPipeline.from_pretrained loads the VAE too (model.py:398-400)
-        if pretrained is not None and all(os.path.isdir(os.path.join(pretrained, d)) for d in
-                                          ("text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2")):
-            self.flux_pipe.attach_text_encoders(pretrained)  # ... and both text encoders with their tokenizers
         self.fuse_flag = fuse_flag
         self.use_brain_condition = use_brain_condition
         self.eeg_fixed_length, self.fnirs_fixed_length, self.ppg_fixed_length, self.motion_fixed_length = 4096, 512, 256, 128
+
+        self.transformer = None
+        self.flux_pipe = _StagedPipeline(self)
+        if self._device.type == "cuda":
+            self._build_native(self._device)
 
         f32 = dict(device=device, dtype=torch.float32)
         self.fusion1 = nn.Sequential(nn.Linear(512 * 2, 512)).to(**f32)
@@ -80,18 +111,89 @@ class OminiModel(nn.Module):
         self.motion_projection = MotionEncoder(device=device)
         self.eval()
 
+    # ---- device handling (inference.py:35-58) ----------------------------------------------------------------------
+    def _build_native(self, device: torch.device) -> None:
+        """FluxPipeline.from_pretrained(...).to(dtype).to(device) (model.py:397-400) for the native engine."""
+        import os
+
+        a = self._build_args
+        pretrained = a["pretrained"]
+        if pretrained is not None:
+            self.transformer = NativeFluxTransformer.from_pretrained(pretrained, device=device, lora_rank=a["r"],
+                                                                     lora_alpha=a["alpha"], seed=a["seed"])
+        else:
+            self.transformer = NativeFluxTransformer(a["cfg"], device=device, seed=a["seed"])
+        self.transformer.gradient_checkpointing = a["gradient_checkpointing"]
+        self.transformer.train(self.training)
+        self.flux_pipe = NativeFluxPipeline(self.transformer)
+        if pretrained is not None and os.path.isdir(os.path.join(pretrained, "vae")):
+            self.flux_pipe.attach_vae(pretrained)  # FluxPipeline.from_pretrained loads the VAE too (model.py:398-400)
+        if pretrained is not None and all(os.path.isdir(os.path.join(pretrained, d)) for d in
+                                          ("text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2")):
+            self.flux_pipe.attach_text_encoders(pretrained)  # ... and both text encoders with their tokenizers
+
     @property
     def device(self):
         return self._device
 
+    @property
+    def staged(self) -> bool:
+        return self.transformer is None
+
+    def to(self, *args, **kwargs):
+        """nn.Module.to restricted to what the native engine can honour: a CUDA target materialises a staged model
+        (replaying the recorded checkpoint loads, inference.py:43-55) and moves the CS3 / DGF modules; dtype requests
+        other than bf16 / fp32 raise; parameters keep their dtypes (CS3 / DGF fp32 + complex64, DiT bf16)."""
+        device, dtype = _parse_to(args, kwargs)
+        if dtype not in (None, torch.bfloat16, torch.float32):
+            raise NotImplementedError(f"dtype {dtype}: the native DiT computes in bf16; CS3 / DGF run in float32")
+        if dtype is not None:
+            self._dtype = dtype
+        if device is None:
+            return self
+        if device.type != "cuda":
+            if self.staged:
+                return self
+            raise NotImplementedError("the native DiT weights live in HBM: a materialised model cannot move to the CPU")
+        if not torch.cuda.is_available():
+            raise RuntimeError("OminiModel.to('cuda'): no CUDA device — the native engine has no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self.staged:
+            self._build_native(device)
+        else:
+            self.transformer.to(device)
+        super().to(device=device)  # CS3 / DGF modules (fp32 parameters, complex64 S4 factors)
+        self._device = device
+        pending, self._pending = self._pending, []
+        for kind, payload in pending:
+            if kind == "lora":
+                self.load_lora(payload)
+            else:
+                self._load_transformer_state(payload)
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device) if isinstance(device, int) else (device or "cuda"))
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        if getattr(self, "transformer", None) is not None:
+            self.transformer.train(mode)
+        return self
+
     # ---- checkpoints (model.py:464-477, 526-531; inference.py:43-53) ------------------------------------------------
     def load_lora(self, checkpoint_path: str):
-        """peft LoRA weights written by `save_lora` / FluxPipeline.save_lora_weights -> factors + native re-merge."""
+        """peft LoRA weights written by `save_lora` / FluxPipeline.save_lora_weights -> factors + native re-merge
+        (model.py:464-477: also puts the transformer in eval mode)."""
+        if self.staged:
+            self._pending.append(("lora", checkpoint_path))
+            return self
         from loongx_b200.checkpoint import read_peft_lora
 
-        n = self.transformer.load_lora_factors(read_peft_lora(checkpoint_path, device=self.device))
-        self._trainer_key = None  # a cached trainer holds views of the old factors
-        return n
+        self.transformer.load_lora_factors(read_peft_lora(checkpoint_path, device=self.device))
+        self.transformer.eval()
+        return self
 
     def save_lora(self, path: str):
         """model.py:526-531: `pytorch_lora_weights.safetensors` in the layout of FluxPipeline.save_lora_weights."""
@@ -121,6 +223,16 @@ class OminiModel(nn.Module):
                 sd["transformer." + k] = v
         return sd
 
+    def _load_transformer_state(self, tr) -> None:
+        from loongx_b200.pipeline import init_lora_factors
+
+        ranks = {v.shape[0] for k, v in tr.items() if k.endswith(".lora_A.weight")}
+        if len(ranks) == 1:
+            self.transformer.cfg.lora_rank = int(next(iter(ranks)))  # a checkpoint saved at another rank
+        tr = {k: v.to(self.device) for k, v in tr.items()}
+        init_lora_factors(tr, self.transformer.cfg, self.device)
+        self.transformer.load_params(tr)
+
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         """LoongX `model.state_dict()` (inference.py:46-52): `transformer.*` keys (peft spellings accepted) replace the
         native DiT weights, everything else goes to the CS3 / DGF modules."""
@@ -128,12 +240,10 @@ class OminiModel(nn.Module):
 
         tr, rest = split_loongx_state_dict(state_dict)
         if tr:
-            from loongx_b200.pipeline import init_lora_factors
-
-            tr = {k: v.to(self.device) for k, v in tr.items()}
-            init_lora_factors(tr, self.transformer.cfg, self.device)
-            self.transformer.load_params(tr)
-            self._trainer_key = None
+            if self.staged:
+                self._pending.append(("state", tr))
+            else:
+                self._load_transformer_state(tr)
         return super().load_state_dict(rest, strict=strict, assign=assign)
 
     def to_model_dtype(self, x: torch.Tensor) -> torch.Tensor:
@@ -170,8 +280,9 @@ class OminiModel(nn.Module):
     def _trainer(self, B, n_txt, n_img, n_cond):
         from loongx_b200.train import DitTrainer
 
-        key = (B, n_txt, n_img, n_cond)
+        key = (B, n_txt, n_img, n_cond, id(self.transformer.weights))
         if getattr(self, "_trainer_key", None) != key:
+            self._trainer_obj = None  # free the old trainer's activations before building the new one
             self._trainer_obj = DitTrainer(self.transformer.weights, B, n_txt, n_img, n_cond, model_config=self.model_config)
             self._trainer_key = key
         return self._trainer_obj
@@ -199,11 +310,10 @@ class OminiModel(nn.Module):
 
     @property
     def lora_layers(self):
-        """model.py:513-524: the LoRA factors (fp32 masters) — the only parameters the reference's optimizer trains."""
-        tr = getattr(self, "_trainer_obj", None)
-        if tr is None:
-            raise RuntimeError("call step() once (it fixes the batch geometry) or _trainer(B, n_txt, n_img, n_cond) first")
-        return tr.parameters()
+        """model.py:513-524: the LoRA factors (fp32 masters) — the only parameters the reference's optimizer trains.  One
+        stable list of nn.Parameters per weight set: available before the first step() (Lightning calls
+        configure_optimizers first, model.py:533) and shared by every trainer, whatever the batch geometry."""
+        return self.transformer.lora_parameters()
 
     def configure_optimizers(self):
         """model.py:533-558 (Prodigy is a third-party optimiser that is not installed here)."""
@@ -213,6 +323,12 @@ class OminiModel(nn.Module):
             return torch.optim.AdamW(self.trainable_params, **opt["params"])
         if opt["type"] == "SGD":
             return torch.optim.SGD(self.trainable_params, **opt["params"])
+        if opt["type"] == "Prodigy":
+            try:
+                import prodigyopt
+            except ImportError as e:  # model.py:547-551 imports it at module level
+                raise NotImplementedError("optimizer type 'Prodigy' needs the third-party `prodigyopt` package") from e
+            return prodigyopt.Prodigy(self.trainable_params, **opt["params"])
         raise NotImplementedError(opt["type"])
 
     def _step_conditioning(self, prompt_embeds, pooled, eeg, fnirs, ppg, motion):
@@ -246,10 +362,10 @@ class OminiModel(nn.Module):
 
     def step(self, batch):
         """model.py:569-729 -> scalar loss whose `.backward()` runs the native backward (LoRA-factor gradients, mean
-        all-reduced across ranks when torch.distributed is initialised).  The VAE / text encoders are outside this build
-        (SURVEY.md §8f): `image` / `condition` are latents [B,16,h,w]; text comes as `prompt_embeds` +
-        `pooled_prompt_embeds` (or `description=(prompt_embeds, pooled)`).  `t` / `noise` may be supplied for
-        reproducibility; otherwise they are drawn like model.py:590-591."""
+        all-reduced across ranks when torch.distributed is initialised).  `image` / `condition`: pictures (with a VAE
+        attached, model.py:582,596) or latents [B,16,h,w]; text: `description` strings (with text encoders attached,
+        model.py:585-587), or pre-computed `prompt_embeds` + `pooled_prompt_embeds` (or `description=(prompt_embeds,
+        pooled)`).  `t` / `noise` may be supplied for reproducibility; otherwise they are drawn like model.py:590-591."""
         from src.flux.pipeline_tools import encode_images
 
         imgs, conditions = batch["image"], batch["condition"]
@@ -262,9 +378,15 @@ class OminiModel(nn.Module):
                 pe, po = batch["prompt_embeds"], batch["pooled_prompt_embeds"]
             elif isinstance(batch.get("description"), tuple):
                 pe, po = batch["description"]
+            elif self.flux_pipe.text_encoder is not None and self.flux_pipe.text_encoder_2 is not None:
+                from src.flux.pipeline_tools import prepare_text_input
+
+                prompts = batch["description"]  # list of strings, what SeedDataset / collate_step_batch produce
+                pe, po, _ = prepare_text_input(self.flux_pipe, [prompts] if isinstance(prompts, str) else list(prompts))
             else:
-                raise NotImplementedError("text encoders are outside this build: put prompt_embeds / pooled_prompt_embeds "
-                                          "in the batch")
+                raise NotImplementedError("step(): `description` holds strings but no text encoders are attached "
+                                          "(OminiModel(flux_pipe_id=<FLUX directory>) or flux_pipe.attach_text_encoders); "
+                                          "alternatively put prompt_embeds / pooled_prompt_embeds in the batch")
             pe, po = pe.to(dev), po.to(dev)
             B = x_0.shape[0]
             t = batch["t"].to(dev).float() if "t" in batch else torch.sigmoid(torch.randn((B,), device=dev))

@@ -93,6 +93,51 @@ def test_attention_strided_out():
     _run(1, 2, 128, 128, 128, col_offset=64, extra_cols=192)
 
 
+@pytest.mark.parametrize("cfg", [
+    # (B, H, nt, ni, nc, mask_mode, cross_bias, pretend-SM count)
+    (2, 2, 128, 256, 128, 0, 0.0, 3), (2, 2, 128, 256, 128, 0, 0.0, 7), (1, 2, 128, 256, 256, 1, 0.0, 3),
+    (1, 2, 128, 256, 256, 2, 0.0, 3), (1, 2, 512, 1024, 1024, 1, 0.0, 19), (1, 3, 128, 384, 256, 0, 0.0, 5),
+    (1, 2, 128, 128, 256, 1, math.log(1.7), 3), (1, 3, 256, 256, 1536, 1, 0.0, 23), (1, 2, 128, 384, 256, 0, 0.0, 4)])
+def test_attention_split_work_schedule(cfg):
+    """The persistent schedule with more units than SMs: CTA ranges cut units at arbitrary KV iterations, the cut
+    units are finished from fp32 partials exchanged through the workspace (1, 2 and 3 contributors per unit, one and
+    two query tiles per unit, masks, bias).  Same tolerance as the unsplit kernel; run twice (flags return to idle)."""
+    from loongx_b200 import _lib as L
+
+    B, H, nt, ni, nc, mask_mode, cross_bias, ctas = cfg
+    L.lib.lx_debug_attention_ctas(ctas)
+    try:
+        _run(B, H, nt, ni, nc, mask_mode=mask_mode, cross_bias=cross_bias)
+        _run(B, H, nt, ni, nc, mask_mode=mask_mode, cross_bias=cross_bias, qscale=4.0)
+    finally:
+        L.lib.lx_debug_attention_ctas(0)
+
+
+def test_attention_split_equals_unsplit_lse():
+    """lse and the output rows of the split schedule against the unsplit one (no workspace use when the pretended SM
+    count covers every unit): fp32 summation order differs, nothing else."""
+    from loongx_b200 import _lib as L
+    from loongx_b200 import ops
+
+    B, H, nt, ni, nc = 1, 4, 256, 512, 256
+    S = nt + ni + nc
+    q, k, v = _mk((B, H, S, 128), 2.0, 1), _mk((B, H, S, 128), 1.0, 2), _mk((B, H, S, 128), 1.0, 3)
+    orb = ops.make_out_row_base(B, nt, ni, nc, "cuda")
+    res = []
+    for ctas in (0, 5, 11):
+        L.lib.lx_debug_attention_ctas(ctas)
+        out = torch.zeros((B * S, H * 128), device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros((B, H, S), device="cuda", dtype=torch.float32)
+        ops.attention(q, k, v, out, orb, n_cond=nc, lse=lse)
+        torch.cuda.synchronize()
+        res.append((out.float(), lse))
+    L.lib.lx_debug_attention_ctas(0)
+    for out, lse in res[1:]:
+        assert (out - res[0][0]).abs().max().item() <= 2e-2 * res[0][0].abs().max().item()
+        assert _rel(out, res[0][0]) < 3e-3
+        assert (lse - res[0][1]).abs().max().item() < 1e-3
+
+
 def test_attention_flux_shape_throughput():
     """512x512 edit shape (S = 512 + 1024 + 1024, 24 heads): parity + printed TFLOP/s (informational)."""
     from loongx_b200 import ops

@@ -439,3 +439,79 @@ def test_micro_batched_step_equals_full_batch():
         dg = _rel(res[mb][1], res[None][1])
         print(f"\n[micro-batch {mb}] loss rel diff {dl:.3g}, grad relL2 diff {dg:.3g}")
         assert dl < 1e-3 and dg < 1e-2
+
+
+def test_optimizer_outlives_trainer_rebuilds_and_lora_scale_changes():
+    """configure_optimizers() BEFORE the first step (Lightning's order, model.py:533), then steps at two batch geometries
+    and a generate()-style LoRA scale change in between: the optimizer's Parameter objects are the ones every trainer
+    differentiates (one stable set per weight set), each step moves the factors and lowers its own loss."""
+    from loongx_b200.config import FluxConfig
+    from src.train.model import OminiModel
+
+    kw = dict(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
+    m = OminiModel(FluxConfig(**kw), lora_config={"r": 4, "lora_alpha": 4}, device=DEV, model_config={},
+                   optimizer_config={"type": "SGD", "params": {"lr": 2.0}}, use_brain_condition=False, seed=3)
+    opt = m.configure_optimizers()  # no step() yet
+    params = [p for grp in opt.param_groups for p in grp["params"]]
+    assert len(params) == len(m.lora_layers) and all(a is b for a, b in zip(params, m.lora_layers))
+    with torch.no_grad():
+        for p in params[1::2]:  # lora_B starts at zero: give the adapters something to differentiate through
+            p.normal_(0, 0.02)
+    g = torch.Generator().manual_seed(5)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(DEV)  # noqa: E731
+
+    def batch(B, h, w):
+        return dict(image=r(B, 16, h, w), condition=r(B, 16, h, w), prompt_embeds=r(B, 128, 256, scale=0.5),
+                    pooled_prompt_embeds=r(B, 64), position_delta=[[0, -16]], condition_type=["subject"] * B,
+                    t=torch.full((B,), 0.5), noise=r(B, (h // 2) * (w // 2), 64))
+
+    for (B, h, w) in ((2, 16, 32), (1, 16, 16), (2, 16, 32)):
+        b = batch(B, h, w)
+        m.transformer.set_lora_scale(0.5)  # what generate(joint_attention_kwargs={"scale": .5}) leaves behind
+        opt.zero_grad()
+        loss = m.step(b)
+        assert getattr(m.transformer.weights, "lora_scale", 1.0) == 1.0  # the step runs on scale-1 panels
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+        assert sum(float(p.grad.abs().sum()) for p in params) > 0
+        before = [p.detach().clone() for p in params]
+        opt.step()
+        assert any(not torch.equal(a, p.detach()) for a, p in zip(before, params))
+        loss2 = m.step(b)
+        print(f"\n[optimizer B={B} {h}x{w}] loss {float(loss.detach()):.6f} -> {float(loss2.detach()):.6f}")
+        assert float(loss2.detach()) < float(loss.detach())
+
+
+def test_step_takes_description_strings_when_text_encoders_are_attached():
+    """model.py:585-587: `description` is a list of strings (what SeedDataset / collate_step_batch produce); with text
+    encoders attached step() encodes them itself, without them it says what is missing."""
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.text import ClipTextConfig, NativeClipText, NativeT5Encoder, T5Config
+    from oracle import text_encoders as T
+    from src.flux.pipeline_tools import prepare_text_input
+    from src.train.model import OminiModel
+
+    cfg = FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2)
+    m = OminiModel(cfg, lora_config={"r": 4, "lora_alpha": 4}, device=DEV, model_config={}, use_brain_condition=False)
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s: torch.randn(*s, generator=g).bfloat16().to(DEV)  # noqa: E731
+    batch = dict(image=r(2, 16, 16, 16), condition=r(2, 16, 16, 16), description=["make it purple", "add a hat"],
+                 position_delta=[[0, -8]], condition_type=["subject"] * 2, t=torch.tensor([0.3, 0.7]), noise=r(2, 64, 64))
+    with pytest.raises(NotImplementedError, match="text encoders"):
+        m.step(batch)
+    tk = dict(vocab_size=300, d_model=4096, d_kv=64, num_heads=4, d_ff=512, num_layers=1)
+    ck = dict(vocab_size=300, hidden_size=768, intermediate_size=256, num_layers=1, num_heads=12, max_positions=77)
+    rnd = lambda P: {k: v.to(torch.bfloat16).float() for k, v in P.items()}  # noqa: E731
+
+    def fake_tokenizer(prompts, padding, max_length, truncation, return_tensors, **kw):
+        rows = [[(ord(c) * 7 + i) % 280 + 3 for i, c in enumerate(p[:max_length - 1])] + [299] for p in prompts]
+        return {"input_ids": torch.tensor([row + [1] * (max_length - len(row)) for row in rows])}
+
+    m.flux_pipe.attach_text_encoders(clip=NativeClipText(ClipTextConfig(**ck), rnd(T.clip_init(T.ClipCfg(**ck), 8)), "cuda"),
+                                     t5=NativeT5Encoder(T5Config(**tk), rnd(T.t5_init(T.T5Cfg(**tk), 7)), "cuda"),
+                                     tokenizers=(fake_tokenizer, fake_tokenizer))
+    loss_str = float(m.step(batch).detach())
+    pe, po, _ = prepare_text_input(m.flux_pipe, batch["description"])
+    b2 = {k: v for k, v in batch.items() if k != "description"}
+    b2.update(prompt_embeds=pe, pooled_prompt_embeds=po)
+    assert loss_str == float(m.step(b2).detach())
