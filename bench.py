@@ -314,6 +314,10 @@ def run_native(args, rank, local_rank, world):
                "sample": s.sample + f" ({len(reps)} repetitions, {time.perf_counter() - t0:.1f} s)",
                "s_per_edit_extrapolated": s.edit_seconds(td, ts)}
 
+    configs = None
+    if not args.no_config_legs:
+        configs = run_config_legs(args, model, dev, rank, local_rank, world, peaks)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "edits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -323,12 +327,138 @@ def run_native(args, rank, local_rank, world):
                     "api": "src.flux.generate.generate(model, pipe, ...) with pinned host inputs, result copied to host"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
             "algorithmic_tflops_per_gpu": algo_tflops, "frac_of_peak_end_to_end": algo_tflops / peaks["tflops"],
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# config legs: BASELINE.json configs[2], [3], [4] measured after the headline region of the same run (extra keys of the
+# same JSON line; the headline value / roofline above are untouched).  One warm-up pass + one timed pass each (a pass is
+# 28-50 DiT forwards), CUDA events, max over ranks, clocks sampled during the timed pass.
+# --------------------------------------------------------------------------------------------------------------------
+def run_config_legs(args, model, dev, rank, local_rank, world, peaks):
+    import gc
+
+    import torch.distributed as dist
+
+    from loongx_b200 import train as T
+    from src.flux.condition import Condition
+    from src.flux.generate import generate
+
+    pipe = model.flux_pipe
+
+    def mk(seed, *shape, scale=1.0, dtype=torch.bfloat16):
+        g = torch.Generator().manual_seed(seed + 1000 * rank)
+        return (torch.randn(*shape, generator=g) * scale).to(dtype).to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, warm=1, reps=1):
+        for _ in range(warm):
+            fn()
+        clocks = ClockSampler(local_rank)
+        barrier()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        clk = clocks.stop()
+        secs = e0.elapsed_time(e1) / 1e3 / reps
+        if world > 1:
+            t = torch.tensor([secs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return secs, clk
+
+    def free():
+        model.transformer._plans.clear()
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def edit_leg(B, res, steps, label):
+        side = res // 8
+        n_img = (res // 16) ** 2
+        t = dict(latents=mk(42, B, 16, side, side), cond=mk(43, B, 16, side, side), pe=mk(44, B, N_TXT, 4096, scale=0.1),
+                 pooled=mk(44, B, 768), eeg=mk(45, B, 4, 5000, dtype=torch.float32), fnirs=mk(46, B, 6, 600, dtype=torch.float32),
+                 ppg=mk(47, B, 4, 256, dtype=torch.float32), motion=mk(48, B, 6, 100, dtype=torch.float32))
+
+        def edit():
+            cnd = Condition("subject", condition=t["cond"], position_delta=[0, -(res // 16)])
+            return generate(model, pipe, conditions=[cnd], prompt_embeds=t["pe"], pooled_prompt_embeds=t["pooled"], height=res,
+                            width=res, num_inference_steps=steps, latents=pipe._pack_latents(t["latents"]), output_type="latent",
+                            default_lora=True, additional_condition1=t["eeg"], additional_condition2=t["fnirs"],
+                            additional_condition3=t["ppg"], additional_condition4=t["motion"], use_brain_condition=True,
+                            fuse_flag=True).images
+
+        free()
+        secs, clk = timed(edit)
+        tf = B * steps * flops_per_forward(N_TXT, n_img, n_img) / secs / 1e12
+        free()
+        return {"workload": label, "batch_per_gpu": B, "global_batch": B * world, "resolution": res, "denoise_steps": steps,
+                "tokens": N_TXT + 2 * n_img, "ms_per_edit_batch": secs * 1e3, "edits_per_s": world * B / secs,
+                "algorithmic_tflops_per_gpu": tf, "frac_of_peak_end_to_end": tf / peaks["tflops"], "clocks": clk,
+                "timing": "1 warm-up pass + 1 timed pass, CUDA events, max over ranks"}
+
+    out = {}
+    out["c2_dgf_b4"] = edit_leg(4, 512, DENOISE_STEPS, "BASELINE.json configs[2]: 512x512, 28 steps, EEG+PPG -> fuse_eeg (DGF) and "
+                                "fNIRS+Motion -> fuse_fnirs, DUAN fuse with the text embeddings (fuse_flag), per-GPU batch 4 "
+                                "(batch 32 on 8 GPUs)")
+    out["c3_1024_50"] = edit_leg(1, 1024, 50, "BASELINE.json configs[3]: 1024x1024, 50 steps, neural (all four signals, fuse_flag) + "
+                                 "text (speech -> prompt embeddings) conditioning, per-GPU batch 1 (batch 8 on 8 GPUs)")
+    # configs[4]: training step, per-GPU batch 8 (global batch 64 on 8 GPUs), one mean all-reduce of the flat gradient bucket
+    B, side = 8, RES // 8
+    g = torch.Generator().manual_seed(7 + 1000 * rank)
+    r = lambda *s, scale=1.0, dt=torch.bfloat16: (torch.randn(*s, generator=g) * scale).to(dt).to(dev)  # noqa: E731
+    batch = dict(image=r(B, 16, side, side), condition=r(B, 16, side, side), prompt_embeds=r(B, N_TXT, 4096, scale=0.1),
+                 pooled_prompt_embeds=r(B, 768), position_delta=[[0, -(RES // 16)]], condition_type=["subject"] * B,
+                 eeg=r(B, 4, 5000, dt=torch.float32), fnirs=r(B, 6, 600, dt=torch.float32),
+                 ppg=r(B, 4, 256, dt=torch.float32), motion=r(B, 6, 100, dt=torch.float32))
+    free()
+    model.use_brain_condition, model.fuse_flag = True, True
+    opt = torch.optim.AdamW(model.trainable_parameters() if hasattr(model, "trainable_parameters") else model.lora_layers, lr=1e-4)
+
+    def one_step():
+        opt.zero_grad(set_to_none=True)
+        loss = model.step(batch)
+        loss.backward()
+        opt.step()
+        return loss
+
+    T.ALLREDUCE_TIMING = True
+    one_step()  # builds the trainer (transposed panels, activation slabs)
+    T.ALLREDUCE_LOG.clear()
+    secs, clk = timed(one_step, warm=1, reps=2)
+    ar = T.ALLREDUCE_LOG[-2:]
+    ar_ms = [e0.elapsed_time(e1) for (e0, e1, _) in ar]
+    T.ALLREDUCE_TIMING = False
+    n_img = (RES // 16) ** 2
+    S, D, nb = N_TXT + 2 * n_img, 3072, 57
+    F = nb * (24 * D * D * S + 4 * S * S * D)
+    tr = model._trainer_obj
+    flop = (2 if tr.recompute else 1) * F + nb * 24 * D * D * S + 2.5 * nb * 4 * S * S * D  # executed work per sample
+    tf = B * flop / secs / 1e12
+    out["c4_train"] = {
+        "workload": "BASELINE.json configs[4]: OminiModel.step forward + backward + AdamW, Flux-DiT LoRA r=4 + CS3/DGF "
+                    "conditioning (step fuse order), 512x512 + image condition, per-GPU batch 8 (global 64 on 8 GPUs)",
+        "batch_per_gpu": B, "global_batch": B * world, "micro_batch": tr.B, "recompute": tr.recompute,
+        "ms_per_step": secs * 1e3, "samples_per_s": world * B / secs, "algorithmic_tflops_per_gpu": tf,
+        "frac_of_peak_end_to_end": tf / peaks["tflops"],
+        "allreduce": {"ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else 0.0, "bytes": (ar[-1][2] if ar else tr.grad_flat.numel() * 4),
+                      "calls_per_step": 1, "what": "NCCL all-reduce (sum) + 1/world scale of the flat fp32 gradient bucket; "
+                                                   "0 ms at n_gpus = 1 (no collective is issued)"},
+        "trainable_elements": int(tr.grad_flat.numel()), "clocks": clk,
+        "timing": "1 build step + 1 warm-up step + 2 timed steps, CUDA events, max over ranks"}
+    return out
 
 # --------------------------------------------------------------------------------------------------------------------
 # training workload (BASELINE.json configs[4]; not the headline metric): OminiModel.step forward + backward + all-reduce
@@ -517,6 +647,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="edits per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config-legs", action="store_true",
+                    help="skip the BASELINE.json configs[2..4] legs that follow the headline measurement")
     ap.add_argument("--workload", default="edit", choices=["edit", "train", "vae"],
                     help="edit = the headline metric (default); train = BASELINE.json configs[4]; vae = the decoder either side "
                          "of the loop (extras, not the headline)")

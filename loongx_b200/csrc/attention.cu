@@ -19,6 +19,7 @@
 // Replaces F.scaled_dot_product_attention + the q/k/v concat + head transpose at block.py:70-72,102-104,129-135,
 // including the optional block masks (block.py:106-120) and the log(c_factor) bias (block.py:121-128), which are
 // uniform per 128x128 tile because every stream length is a multiple of 128.
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_util.cuh"
@@ -43,7 +44,9 @@ constexpr int ATT_SLOT_FLOATS = 128 * 128 + 2 * 128;
 constexpr int ATT_WS_FLAG_BYTES = WS_FLAG_BYTES;  // flags [n_cta][2] at the start of the workspace region
 
 struct AttnParams {
-  long long* cta_trace;  // optional [n_ctas][6]: smid, t_entry, t_setup_done, t_first_s, t_loop_end, t_exit (CTA-level)
+  long long* tl;  // development-aid timeline row (ptx.cuh::timeline_mark) or nullptr
+  long long* cta_trace;  // optional [n_ctas][16] (development aid): smid, t_entry, t_setup_done, t_first_s, t_last_loop_end, t_exit,
+                         // flag-wait clk, #segments, (loop end, epilogue end) of the first 3 segments, globaltimer entry / exit
   lx_attn_desc_t d;
   float scale_log2;  // scale * log2(e)
   float bias_log2;   // cross_bias * log2(e)
@@ -60,6 +63,7 @@ struct AttnParams {
   int w_head;                  // iterations per (batch, head)
   long long total;             // B * H * w_head
   long long total_units;       // B * H * (units_rest + units_cond)
+  int l2_prefetch;             // K / V tiles are prefetched into the L2 this many KV iterations ahead of their TMA load
   int* flags;                  // [n_cta][2]   (workspace; all zero between launches)
   float* slots;                // [n_cta][2][ATT_SLOT_FLOATS]
 };
@@ -127,12 +131,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ AttnParams p) {
   const long long t_entry = clock64();
+  if (threadIdx.x == 0) timeline_mark(p.tl, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2 groups]
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // [stages]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;    // [stages]
-  uint8_t* sO = sV + ATT_KV_STAGES * ATT_TILE_BYTES;    // output staging tile (both groups, in turn)
+  uint8_t* sO = sV + ATT_KV_STAGES * ATT_TILE_BYTES;    // output staging: one 128 x 64 atom per group
   uint64_t* bars = reinterpret_cast<uint64_t*>(sO + ATT_TILE_BYTES);
   uint64_t* q_full = bars;          // 1      Q tiles of the current segment landed
   uint64_t* k_full = bars + 1;      // [2]
@@ -145,7 +150,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* p_half = bars + 15;     // [2 groups] first 64 key columns of P_g(j) packed (PV k-slices 0..3 may start)
   uint64_t* o_free = bars + 17;     // [2 groups] O_g of the finished segment has been read out of TMEM (128 arrivals)
   uint64_t* q_free = bars + 19;     // 1      every QK^T of the current segment has completed: Q may be overwritten
-  uint64_t* stage_free = bars + 20; // 1      the previous user's TMA store has finished reading the staging tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const lx_attn_desc_t& d = p.d;
@@ -165,7 +169,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     prefetch_tmap(&tmO);
     mbar_init(q_full, 1);
     mbar_init(q_free, 1);
-    mbar_init(stage_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
@@ -188,16 +191,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   long long* trace = nullptr;
   if (p.cta_trace != nullptr && threadIdx.x == 128) {  // first softmax thread of tile A
-    trace = p.cta_trace + (long long)cta * 6;
+    trace = p.cta_trace + (long long)cta * 16;
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     trace[0] = smid;
     trace[1] = t_entry;
     trace[2] = clock64();
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace[14] = gt;
   }
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // PDL: the prologue above overlapped the QKV GEMM's tail; Q / K / V are read from here on
   pdl_launch_dependents();
+  if (threadIdx.x == 0) timeline_mark(p.tl, 1);
   // columns [128g, 128g+128): S_g fp32, its first 64 columns re-used for the packed bf16 P_g;  [256+128g, +128): O_g
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 256;
@@ -217,10 +224,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_load_2d(sQ + g * ATT_TILE_BYTES, &tmQ, q_full, 0, head_row0 + (sg.qt0 + g) * ATT_BQ);
           tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmQ, q_full, 64, head_row0 + (sg.qt0 + g) * ATT_BQ);
         }
+        const int pf = p.l2_prefetch;
+        for (int it = 0; it < min(pf, sg.n); ++it) {  // the segment's first tiles
+          const int row = head_row0 + (sg.kv0 + it) * ATT_BKV;
+          tma_prefetch_2d(&tmK, 0, row);
+          tma_prefetch_2d(&tmK, 64, row);
+          tma_prefetch_2d(&tmV, 0, row);
+          tma_prefetch_2d(&tmV, 64, row);
+        }
         for (int it = 0; it < sg.n; ++it, ++j) {
           const int st = j & 1;
           const uint32_t par = ((j >> 1) & 1) ^ 1;
           const int row = head_row0 + (sg.kv0 + it) * ATT_BKV;
+          if (pf > 0 && it + pf < sg.n) {
+            const int prow = row + pf * ATT_BKV;
+            tma_prefetch_2d(&tmK, 0, prow);
+            tma_prefetch_2d(&tmK, 64, prow);
+            tma_prefetch_2d(&tmV, 0, prow);
+            tma_prefetch_2d(&tmV, 64, prow);
+          }
           mbar_wait(&k_empty[st], par);
           mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
           tma_load_2d(sK + st * ATT_TILE_BYTES, &tmK, &k_full[st], 0, row);
@@ -332,7 +354,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t ts = tmem_S + g * 128 + lane_off;  // S_g row (fp32) / packed P_g row (first 64 columns)
       const uint32_t to = tmem_O + g * 128 + lane_off;
-      int j = 0, si = 0, n_staged = 0;
+      int j = 0, si = 0;
       for (long long x = x_lo; x < x_hi; ++si) {
         const AttnSeg sg = attn_seg(p, x, x_hi);
         x += sg.n;
@@ -426,7 +448,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_arrive(&p_full[g]);
         }
         // ---------------------------------------------------------------- end of segment
-        if (trace != nullptr && x >= x_hi) trace[4] = clock64();
+        if (trace != nullptr) {
+          if (x >= x_hi) trace[4] = clock64();
+          if (si < 3) trace[8 + 2 * si] = clock64();
+          trace[7] = si + 1;
+        }
         mbar_wait(&o_done[g], si & 1);
         tc_fence_after();
         if (!sg.first) {
@@ -446,9 +472,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_before();
           mbar_arrive(&o_free[g]);
           reinterpret_cast<float2*>(slot + 128 * 128)[r] = make_float2(m_run, l_run);
-          __threadfence();
+          // one gpu-scope fence for the group: the barrier orders every row's stores before thread 0's fence
+          // (cumulative), the release store of the flag after it; the other 127 threads go straight on
           asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
-          if (r == 0) st_release_gpu(p.flags + cta * 2 + g, 1);
+          if (r == 0) {
+            __threadfence();
+            st_release_gpu(p.flags + cta * 2 + g, 1);
+          }
         } else {
           // This CTA finishes the unit.  If the unit continues in later CTAs' ranges, fold their partials in.
           float a_self = 1.0f;
@@ -460,6 +490,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               const int* fl = p.flags + cc * 2 + g;
               if (ld_acquire_gpu(fl) == 0) {
                 const long long t0 = clock64();
+                if (trace != nullptr) trace[6] -= t0;
                 while (ld_acquire_gpu(fl) == 0) {
                   __nanosleep(200);
                   if (clock64() - t0 > 8000000000LL) {
@@ -467,6 +498,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     __trap();
                   }
                 }
+                if (trace != nullptr) trace[6] += clock64();
               }
               const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.slots + ((size_t)cc * 2 + g) * ATT_SLOT_FLOATS + 128 * 128) + r);
               m_all = fmaxf(m_all, ml.x);
@@ -482,78 +514,96 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float inv_l = 1.0f / l_run;
           const int head_row0 = sg.hh * d.S;
           if (d.lse != nullptr) d.lse[head_row0 + (sg.qt0 + g) * ATT_BQ + r] = m_run + log2f(l_run);  // for lx_attention_bwd
-          // O_g / l -> bf16 -> staging tile in the 128-byte-swizzled TMA layout -> two TMA stores of 128 rows x 64
-          // columns (full-line writes).  The staging tile is shared by the two groups: use number e waits for use e-1.
-          const int e = n_staged * G + g;
-          if (e > 0) mbar_wait(stage_free, (e - 1) & 1);
+          // O_g / l -> bf16 -> this group's 128 x 64 staging atom (128-byte-swizzled TMA layout) -> one TMA store per
+          // 64-column half: full-line writes, and the two groups never wait for each other's stores.
+          uint8_t* sOg = sO + g * ATT_ATOM_BYTES;
+          const int bb_ = sg.hh / d.H, hd = sg.hh - bb_ * d.H;
+          const int out_row0 = d.out_row_base[bb_ * n_tiles + sg.qt0 + g];
+          const int col0 = d.col_offset + hd * ATT_D;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(to + c * 32, o);
-            float f[32];
+          for (int hf = 0; hf < 2; ++hf) {
+            uint4 u[8];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(o[jj]) * a_self;
-            for (int cc = cta + 1; cc < c_end; ++cc) {
-              const float* slot = p.slots + ((size_t)cc * 2 + g) * ATT_SLOT_FLOATS;
-              const float bb = ex2_approx(__ldcg(reinterpret_cast<const float2*>(slot + 128 * 128) + r).x - m_run);
-              const float4* so = reinterpret_cast<const float4*>(slot);
+            for (int cc2 = 0; cc2 < 2; ++cc2) {
+              const int c = hf * 2 + cc2;
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(to + c * 32, o);
+              float f[32];
 #pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 t = __ldcg(so + (c * 8 + q4) * 128 + r);
-                f[4 * q4 + 0] += t.x * bb;
-                f[4 * q4 + 1] += t.y * bb;
-                f[4 * q4 + 2] += t.z * bb;
-                f[4 * q4 + 3] += t.w * bb;
+              for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(o[jj]) * a_self;
+              for (int cc = cta + 1; cc < c_end; ++cc) {
+                const float* slot = p.slots + ((size_t)cc * 2 + g) * ATT_SLOT_FLOATS;
+                const float bb = ex2_approx(__ldcg(reinterpret_cast<const float2*>(slot + 128 * 128) + r).x - m_run);
+                const float4* so = reinterpret_cast<const float4*>(slot);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                  const float4 t = __ldcg(so + (c * 8 + q4) * 128 + r);
+                  f[4 * q4 + 0] += t.x * bb;
+                  f[4 * q4 + 1] += t.y * bb;
+                  f[4 * q4 + 2] += t.z * bb;
+                  f[4 * q4 + 3] += t.w * bb;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                u[cc2 * 4 + q].x = pack_bf16(f[8 * q + 0] * inv_l, f[8 * q + 1] * inv_l);
+                u[cc2 * 4 + q].y = pack_bf16(f[8 * q + 2] * inv_l, f[8 * q + 3] * inv_l);
+                u[cc2 * 4 + q].z = pack_bf16(f[8 * q + 4] * inv_l, f[8 * q + 5] * inv_l);
+                u[cc2 * 4 + q].w = pack_bf16(f[8 * q + 6] * inv_l, f[8 * q + 7] * inv_l);
               }
             }
+            if (hf == 1) {  // O_g is in registers: the next segment's first PV may overwrite it
+              tc_fence_before();
+              mbar_arrive(&o_free[g]);
+            }
+            // the previous store out of this atom (first half / previous segment) must have finished reading it
+            if (r == 0) tma_store_wait_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack_bf16(f[8 * q + 0] * inv_l, f[8 * q + 1] * inv_l);
-              u.y = pack_bf16(f[8 * q + 2] * inv_l, f[8 * q + 3] * inv_l);
-              u.z = pack_bf16(f[8 * q + 4] * inv_l, f[8 * q + 5] * inv_l);
-              u.w = pack_bf16(f[8 * q + 6] * inv_l, f[8 * q + 7] * inv_l);
-              const int c16 = c * 4 + q;  // 16-byte chunk of the 256-byte output row
-              *reinterpret_cast<uint4*>(sO + (c16 >> 3) * ATT_ATOM_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = u;
+            for (int q = 0; q < 8; ++q)  // q = 16-byte chunk of the 128-byte half row
+              *reinterpret_cast<uint4*>(sOg + r * 128 + ((q ^ (r & 7)) << 4)) = u[q];
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+            if (r == 0) {
+              tma_store_2d(&tmO, sOg, col0 + 64 * hf, out_row0);
+              tma_store_commit();
             }
           }
-          tc_fence_before();
-          mbar_arrive(&o_free[g]);
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
-          if (r == 0) {
+          if (r == 0)
             for (int cc = cta + 1; cc < c_end; ++cc) p.flags[cc * 2 + g] = 0;  // consumed: back to the idle state
-            const int b = sg.hh / d.H, h = sg.hh - b * d.H;
-            const int out_row0 = d.out_row_base[b * n_tiles + sg.qt0 + g];
-            const int col0 = d.col_offset + h * ATT_D;
-            tma_store_2d(&tmO, sO, col0, out_row0);
-            tma_store_2d(&tmO, sO + ATT_ATOM_BYTES, col0 + 64, out_row0);
-            tma_store_commit();
-            tma_store_wait_read<0>();  // the staging tile must outlive the bulk read; global visibility at kernel end
-            mbar_arrive(stage_free);
-          }
-          ++n_staged;
         }
+        if (trace != nullptr && si < 3) trace[9 + 2 * si] = clock64();
       }
+      if (r == 0) tma_store_wait_read<0>();  // the staging atom must outlive the last bulk read
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) timeline_mark(p.tl, 2);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
-  if (trace != nullptr) trace[5] = clock64();
+  if (trace != nullptr) {
+    trace[5] = clock64();
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace[15] = gt;
+  }
 }
 
 }  // namespace lx
 
 static long long* g_attn_trace = nullptr;
 static int g_attn_force_ctas = 0;
+static int g_attn_split = 1;
+static int g_attn_l2_prefetch = -1;  // -1: read LX_ATT_PF (default 0) on first use
 extern "C" void lx_attention_debug_cta_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 // development / test aid: pretend the device has n SMs (0 = automatic), so that small shapes exercise the split-work path
 extern "C" void lx_debug_attention_ctas(int n) { g_attn_force_ctas = n; }
+// development aid: 0 = never cut units between CTAs (A/B timing of the split-work schedule)
+extern "C" void lx_debug_attention_split(int on) { g_attn_split = on; }
 
 extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   using namespace lx;
@@ -606,15 +656,24 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
   // split the work to one KV iteration when there are more units than SMs (else: one unit per CTA is already balanced)
   // and the caller registered an exchange workspace for this stream (lx_set_workspace)
   p.split = 0;
-  if (p.total_units > p.n_cta) {
-    const size_t need = ATT_WS_FLAG_BYTES + (size_t)p.n_cta * 2 * ATT_SLOT_FLOATS * sizeof(float);
+  // batch invariance: with a CTA count that is a multiple of B every batch element's work is cut at the same relative
+  // positions (lo(c + k n/B) = k W + lo(c)), so identical edits of one batch give bit-identical rows
+  const int n_split = sms - sms % d.B;
+  if (p.total_units > p.n_cta && g_attn_split && n_split > 0 && p.total_units > n_split) {
+    const size_t need = ATT_WS_FLAG_BYTES + (size_t)n_split * 2 * ATT_SLOT_FLOATS * sizeof(float);
     char* ws = static_cast<char*>(workspace_region(stream, 0, need));
-    if (ws != nullptr && p.n_cta * 2 * sizeof(int) <= (size_t)ATT_WS_FLAG_BYTES) {
+    if (ws != nullptr && n_split * 2 * sizeof(int) <= (size_t)ATT_WS_FLAG_BYTES) {
       p.split = 1;
+      p.n_cta = n_split;
       p.flags = reinterpret_cast<int*>(ws);
       p.slots = reinterpret_cast<float*>(ws + ATT_WS_FLAG_BYTES);
     }
   }
+  if (g_attn_l2_prefetch < 0) {
+    const char* e = getenv("LX_ATT_PF");
+    g_attn_l2_prefetch = e ? atoi(e) : 0;
+  }
+  p.l2_prefetch = g_attn_l2_prefetch;
   const bool has_pad = (d.pad[0] | d.pad[1] | d.pad[2]) != 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -629,6 +688,8 @@ extern "C" int lx_attention(const lx_attn_desc_t* desc, void* stream) {
     if (d.mask_mode == 1) pairs = nc * nc + nr * nr;
     if (d.mask_mode == 2) pairs = nc * nc + nr * (double)d.S;
   }
+  if (debug_skip_mask() & 2) return LX_OK;  // timing experiments only (lx_debug_skip)
+  p.tl = timeline_next(KC_ATTENTION);
   LaunchScope scope(KC_ATTENTION, stream, 4.0 * d.B * d.H * pairs * 128.0);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;

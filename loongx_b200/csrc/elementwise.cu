@@ -5,6 +5,8 @@
 //   euler_step       FlowMatchEulerDiscreteScheduler.step                            (generate.py:349)
 //   rope_table       FluxPosEmbed (float64 internally, like the reference)          (transformer.py:130-134)
 //   pack / unpack    FluxPipeline._pack_latents / _unpack_latents (bit-exact index shuffles, generate.py:262,375)
+#include <stdlib.h>
+
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -38,9 +40,10 @@ constexpr int LN_MAX_NV = 12;    // D <= 3072: each lane owns up to 12 chunks of
 // reduction each, and the modulation vectors (shared by every row of a (stream, batch) pair: L1 hits) are fetched in
 // the store pass.  The round-1 version (one 128-thread CTA per row, two block reductions, four __syncthreads) ran at
 // 19 % of the HBM peak on L2-resident data; this form is bound by one L2 round trip per row.
-__global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_desc_t d) {
+__global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_desc_t d, long long* tl) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
+  if (threadIdx.x == 0) timeline_mark(tl, 0);
   if (row >= d.rows) {  // (whole warp) still take part in the PDL protocol
     pdl_wait();
     pdl_launch_dependents();
@@ -57,7 +60,9 @@ __global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_
   const uint4* shift = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(shift_p) + (size_t)meta.batch * mstride);
   const uint4* scale = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(scale_p) + (size_t)meta.batch * mstride);
   pdl_wait();  // PDL: x is the previous kernel's output
-  pdl_launch_dependents();
+  pdl_launch_dependents();  // (releasing the next GEMM's CTAs only at the end of the row was measured: no faster, and
+                            //  the GEMM loses the overlap of its prologue / first weight tiles)
+  if (threadIdx.x == 0) timeline_mark(tl, 1);
   uint4 raw[LN_MAX_NV];
 #pragma unroll
   for (int i = 0; i < LN_MAX_NV; ++i)
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_
       out[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+  if (threadIdx.x == 0) timeline_mark(tl, 2);  // one mark per CTA: 2560 same-address atomics would dominate the kernel
 }
 
 // out[m, 0:128] = cos(t*f_j), out[m, 128:256] = sin(t*f_j), f_j = exp(-ln(1e4) j / 128)
@@ -212,6 +218,7 @@ extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
                "lx_ln_modulate: D=%d must be a multiple of 256 and <= %d", d.D, LN_MAX_NV * 256);
   LX_CHECK_ARG(d.x && d.out && d.tile_meta, "lx_ln_modulate: null pointer");
   LX_CHECK_ARG(d.ldx % 8 == 0 && d.ldo % 8 == 0 && d.ldo >= d.D && d.ldx >= d.D, "lx_ln_modulate: bad strides");
+  if (lx::debug_skip_mask() & 4) return LX_OK;  // timing experiments only (lx_debug_skip): marginal cost of this kernel
   LaunchScope scope(KC_ROW, stream, 4.0 * d.rows * d.D);  // bytes: read + write bf16 rows
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((d.rows + LN_WARPS - 1) / LN_WARPS);
@@ -222,7 +229,8 @@ extern "C" int lx_ln_modulate(const lx_lnmod_desc_t* desc, void* stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, ln_modulate_kernel, d);
+  long long* tl = timeline_next(KC_ROW);
+  cudaLaunchKernelEx(&cfg, ln_modulate_kernel, d, tl);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -40,7 +40,70 @@ struct GemmParams {
   int num_kb[3];
   int tile_begin[3];  // first M tile of group g (unused groups: tiles_m)
   int raster_g;       // M tiles per raster band (see tile_coords); = tiles_m when the whole A operand fits the L2 budget
+  // Stream-K head (sk_tiles > 0): the first sk_tiles tiles (raster order) are not given to clusters whole; their
+  // sk_tiles * num_kb[0] k-blocks are cut into one contiguous, equally long range per cluster, processed BEFORE the
+  // remaining tiles, which form full waves of whole tiles.  A tile cut by a range boundary is finished by the cluster that
+  // holds its first k-block; the others publish fp32 partial accumulators through the workspace.
+  long long* tl;  // development-aid timeline row (ptx.cuh::timeline_mark) or nullptr
+  int sk_tiles;
+  int* flags;    // [gridDim.x]  (workspace; all zero between launches)
+  float* slots;  // [gridDim.x][GEMM_SLOT_FLOATS]: partial accumulator of one CTA, layout [chunk][16-byte fragment][row]
 };
+
+constexpr int GEMM_SLOT_FLOATS = 256 * 128;
+
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One unit of work of a cluster: k-blocks [kb0, kb0 + nk) of `tile`.
+struct GemmWork {
+  int tile, kb0, nk;
+  bool publish;  // the tile's first k-blocks belong to an earlier cluster: the accumulator goes to the workspace
+  bool fix;      // this cluster holds the tile's first k-blocks but not its last: fold the later clusters' partials in
+  int x_end;     // stream-K position of the tile's end (fix only)
+};
+// Work list of one cluster: its stream-K range first, then whole tiles sk_tiles + cluster_id + i * num_clusters.
+struct GemmSched {
+  int x, hi, dp_tile;
+  __device__ __forceinline__ GemmSched(const GemmParams& p, int cluster_id, int num_clusters) {
+    const long long sk_total = (long long)p.sk_tiles * p.num_kb[0];
+    x = (int)(cluster_id * sk_total / num_clusters);
+    hi = (int)((cluster_id + 1) * sk_total / num_clusters);
+    dp_tile = p.sk_tiles + cluster_id;
+  }
+  __device__ __forceinline__ bool next(const GemmParams& p, int num_clusters, int num_tiles, GemmWork& w) {
+    if (x < hi) {
+      const int nkb = p.num_kb[0];
+      w.tile = x / nkb;
+      w.kb0 = x - w.tile * nkb;
+      w.nk = min(nkb - w.kb0, hi - x);
+      w.publish = w.kb0 > 0;
+      w.fix = w.kb0 == 0 && w.nk < nkb;
+      w.x_end = (w.tile + 1) * nkb;
+      x += w.nk;
+      return true;
+    }
+    if (dp_tile < num_tiles) {
+      w.tile = dp_tile;
+      w.kb0 = 0;
+      w.nk = -1;  // whole tile: the caller looks the group's k-block count up
+      w.publish = w.fix = false;
+      w.x_end = 0;
+      dp_tile += num_clusters;
+      return true;
+    }
+    return false;
+  }
+};
+__device__ __forceinline__ int sk_lo(const GemmParams& p, int cluster, int num_clusters) {
+  return (int)(cluster * ((long long)p.sk_tiles * p.num_kb[0]) / num_clusters);
+}
 
 // Tile order: bands of `raster_g` M tiles; inside a band M runs fastest, then N.  A wave of CTAs then works on one band's
 // rows (A working set = raster_g * BM*NCTA * K * 2 bytes, sized for the L2) while sweeping the N tiles, instead of
@@ -106,6 +169,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const lx_gemm_desc_t& d = p.d;
+  if (threadIdx.x == 64) timeline_mark(p.tl, 0);
   // CTA pair bookkeeping (NCTA == 1: rank 0, every CTA is its own "cluster")
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / NCTA;
@@ -146,6 +210,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool defer_pdl = (warp == 0);
   if (!defer_pdl) pdl_wait();
   pdl_launch_dependents();
+  if (threadIdx.x == 64) timeline_mark(p.tl, 1);
 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -155,15 +220,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       bool first_tile = true;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      GemmSched sched(p, cluster_id, num_clusters);
+      GemmWork wk;
+      while (sched.next(p, num_clusters, num_tiles, wk)) {
         int tmi, tni;
-        tile_coords(p, tile, tmi, tni);
+        tile_coords(p, wk.tile, tmi, tni);
         const int tm = tmi * NCTA + rank;  // this CTA's 128-row tile
         const int m0 = tm * BM;
         const int n0 = tni * BN + rank * (BN / NCTA);  // this CTA's slice of the W tile
         const int g = group_of(p, tm);
         const CUtensorMap* tmB = g == 0 ? &tmB0 : (g == 1 ? &tmB1 : &tmB2);
-        const int nkb = p.num_kb[g];
+        const int nkb = wk.nk < 0 ? p.num_kb[g] : wk.nk;
+        const int kb_first = wk.kb0;
         // first tile: the W halves of the first min(STAGES, nkb) stages are requested BEFORE the PDL wait (weights do
         // not depend on the previous kernel), the A halves right after it
         // (w_dynamic: W is an earlier kernel's output, nothing may be requested before the wait)
@@ -173,10 +241,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sa = smem + kb * STAGE_BYTES;
             if (NCTA == 2) {
               if (rank == 0) mbar_expect_tx(&full[kb], 2 * STAGE_BYTES);
-              tma_load_2d_2sm(sa + A_BYTES, tmB, mapa_shared(smem_u32(&full[kb]), 0), kb * BK, n0);
+              tma_load_2d_2sm(sa + A_BYTES, tmB, mapa_shared(smem_u32(&full[kb]), 0), (kb_first + kb) * BK, n0);
             } else {
               mbar_expect_tx(&full[kb], STAGE_BYTES);
-              tma_load_2d(sa + A_BYTES, tmB, &full[kb], kb * BK, n0);
+              tma_load_2d(sa + A_BYTES, tmB, &full[kb], (kb_first + kb) * BK, n0);
             }
           }
           pdl_wait();
@@ -186,16 +254,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           const bool early = kb < n_early;  // W already requested and the expected bytes already posted
+          const int kc = (kb_first + kb) * BK;
           if (NCTA == 2) {
             // both CTAs' bytes are counted on the LEADER's full barrier (the leader issues the pair's MMAs)
             if (rank == 0 && !early) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
             const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
-            tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
-            if (!early) tma_load_2d_2sm(sa + A_BYTES, tmB, bar, kb * BK, n0);
+            tma_load_2d_2sm(sa, &tmA, bar, kc, m0);
+            if (!early) tma_load_2d_2sm(sa + A_BYTES, tmB, bar, kc, n0);
           } else {
             if (!early) mbar_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-            if (!early) tma_load_2d(sa + A_BYTES, tmB, &full[stage], kb * BK, n0);
+            tma_load_2d(sa, &tmA, &full[stage], kc, m0);
+            if (!early) tma_load_2d(sa + A_BYTES, tmB, &full[stage], kc, n0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -215,13 +284,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      GemmSched sched(p, cluster_id, num_clusters);
+      GemmWork wk;
+      while (sched.next(p, num_clusters, num_tiles, wk)) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
         int tmi, tni;
-        tile_coords(p, tile, tmi, tni);
-        const int nkb = p.num_kb[group_of(p, tmi * NCTA)];
+        tile_coords(p, wk.tile, tmi, tni);
+        const int nkb = wk.nk < 0 ? p.num_kb[group_of(p, tmi * NCTA)] : wk.nk;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -267,13 +338,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    GemmSched sched(p, cluster_id, num_clusters);
+    GemmWork wk;
+    while (sched.next(p, num_clusters, num_tiles, wk)) {
+      if (wk.publish) {
+        // stream-K: this cluster computed k-blocks [kb0, kb0 + nk) of a tile that an earlier cluster finishes.  The
+        // fp32 partial goes to this CTA's workspace slot, [chunk][16-byte fragment][row]: a warp's 32 rows write 512
+        // contiguous bytes per instruction; then the flag is raised (release) for the finishing CTA.
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr_p = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+        float4* slot = reinterpret_cast<float4*>(p.slots + (size_t)blockIdx.x * GEMM_SLOT_FLOATS);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr_p + c * 32, r);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            slot[(c * 8 + q4) * 128 + row_in_tile] = make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]),
+                                                                 __uint_as_float(r[4 * q4 + 2]), __uint_as_float(r[4 * q4 + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));
+          else mbar_arrive(&tempty[acc]);
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) st_release_gpu_s32(p.flags + blockIdx.x, 1);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       int tmi, tni;
-      tile_coords(p, tile, tmi, tni);
+      tile_coords(p, wk.tile, tmi, tni);
       const int tm = tmi * NCTA + rank;
       const int m0 = tm * BM;
       const int n0 = tni * BN;
       const int row = m0 + row_in_tile;
+      // stream-K: CTAs [fix_cta0, fix_cta0 + NCTA * fix_n) step NCTA (same rank in the following clusters) hold the
+      // partial accumulators of this tile's remaining k-blocks
+      int fix_n = 0;
+      if (wk.fix) {
+        int c_end = cluster_id + 1;
+        while (c_end < num_clusters && sk_lo(p, c_end, num_clusters) < wk.x_end) ++c_end;
+        fix_n = c_end - (cluster_id + 1);
+      }
+      const float* fix_slot0 = p.slots + (size_t)(blockIdx.x + NCTA) * GEMM_SLOT_FLOATS;
+      // accumulator chunk (32 columns from tile column `col`) of this thread's row: TMEM + the published partials
+      auto ld_acc = [&](uint32_t taddr_row, int col, uint32_t (&r)[32]) {
+        tmem_ld_32x32b_x32(taddr_row + col, r);
+        for (int f = 0; f < fix_n; ++f) {
+          const float4* sp = reinterpret_cast<const float4*>(fix_slot0 + (size_t)f * NCTA * GEMM_SLOT_FLOATS);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 t = __ldcg(sp + ((col >> 5) * 8 + q4) * 128 + row_in_tile);
+            r[4 * q4 + 0] = __float_as_uint(__uint_as_float(r[4 * q4 + 0]) + t.x);
+            r[4 * q4 + 1] = __float_as_uint(__uint_as_float(r[4 * q4 + 1]) + t.y);
+            r[4 * q4 + 2] = __float_as_uint(__uint_as_float(r[4 * q4 + 2]) + t.z);
+            r[4 * q4 + 3] = __float_as_uint(__uint_as_float(r[4 * q4 + 3]) + t.w);
+          }
+        }
+      };
       const bool row_ok = row < d.M;
       const int si = (n0 >= d.n_split) ? 1 : 0;
       const lx_gemm_segment_t& seg = d.seg[si];
@@ -327,6 +456,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int f = 0; f < fix_n; ++f) {  // the partials must have been published (acquire; normally long since)
+        const int* fl = p.flags + blockIdx.x + NCTA * (f + 1);
+        if (ld_acquire_gpu_s32(fl) == 0) {
+          const long long t0 = clock64();
+          while (ld_acquire_gpu_s32(fl) == 0) {
+            __nanosleep(100);
+            if (clock64() - t0 > 8000000000LL) {
+              printf("lx: gemm partial of CTA %d never arrived (CTA %d)\n", (int)(blockIdx.x + NCTA * (f + 1)), (int)blockIdx.x);
+              __trap();
+            }
+          }
+        }
+      }
 
       if (BN == 256 && mode == LX_EPI_QKV) {
         const lx_tile_meta_t meta = meta_pf;
@@ -350,7 +492,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int c = 0; c < 4; ++c) {
               uint32_t r[32];
               float x[32];
-              tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
+              ld_acc(taddr, half * 128 + c * 32, r);
                   chunk_bias(r, bias, half * 128 + c * 32, x);
 #pragma unroll
               for (int j = 0; j < 32; ++j) ss += x[j] * x[j];
@@ -361,7 +503,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             float x[32];
-            tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, r);
+            ld_acc(taddr, half * 128 + c * 32, r);
               chunk_bias(r, bias, half * 128 + c * 32, x);
             if (rmsw != nullptr) {
               const float4* w4 = reinterpret_cast<const float4*>(rmsw + c * 32);
@@ -401,7 +543,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (n < d.N) {
             uint32_t r[32];
             float x[32];
-            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            ld_acc(taddr, c * 32, r);
             chunk_bias(r, bias, c * 32, x);
             const int oc = n - seg_n0 + seg.col_offset;
 #pragma unroll
@@ -434,7 +576,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (n >= d.N) break;
           uint32_t r[32];
           float x[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          ld_acc(taddr, c * 32, r);
           chunk_bias(r, bias, c * 32, x);
           if (mode == LX_EPI_BIAS_GELU) {
 #pragma unroll
@@ -466,6 +608,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (NCTA == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));  // the leader's barrier
         else mbar_arrive(&tempty[acc]);
       }
+      if (fix_n > 0) {  // every epilogue thread has read the partials: the flags return to idle for the next launch
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64)
+          for (int f = 0; f < fix_n; ++f) p.flags[blockIdx.x + NCTA * (f + 1)] = 0;
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -475,6 +622,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 64) timeline_mark(p.tl, 2);
   if (NCTA == 2) cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
@@ -487,6 +635,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 namespace lx {
 
+static long long g_stream_k_launches = 0;
+// The stream-K head is OFF by default: measured on B200 (round 2, profiles/README.md) the fp32 partial-tile exchange
+// through L2 costs more than the partial last wave it removes (M = 2560: N = K = 3072 36.4 -> 41.3 us, N = 3072 /
+// K = 12288 136.9 -> 142.7 us, N = 12288 / K = 3072 134.1 -> 135.9 us; whole edit 962 -> 1037 ms).  lx_debug_gemm_stream_k(1)
+// switches it on (tests, further tuning).
+static int g_stream_k = 0;
+static int g_fake_sms = 0;  // lx_debug_gemm_sms(n): pretend the device has n SMs (tests: small shapes exercise stream-K)
 static long long g_raster_budget_mb = 40;  // L2 share given to the A rows of one raster band (the 126 MB L2 is two 63 MB
                                            // partitions; 40 MB measured best end to end at B = 4: -7.6 % per denoise step)
 
@@ -522,12 +677,37 @@ int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
                                  TileCfg<BN, NCTA>::SMEM));
     attr_set = true;
   }
-  const int grid = min(p.tiles_m * p.tiles_n, num_sms() / NCTA) * NCTA;
+  const int sms = g_fake_sms > 0 ? g_fake_sms : num_sms();
+  const int grid = min(p.tiles_m * p.tiles_n, max(sms / NCTA, 1)) * NCTA;
+  // Stream-K head: when the tile count is not a multiple of the cluster count, the `rem` tiles that would form a partial
+  // last wave are cut along K into one equal range per cluster and processed first; the rest runs as full waves of
+  // whole tiles.  Needs one k-block count for all row groups, enough k-blocks per cluster to amortise the partial-tile
+  // exchange (128 KB per CTA through L2), a partial wave that is actually wasteful, and the caller's workspace.
+  p.sk_tiles = 0;
+  p.flags = nullptr;
+  p.slots = nullptr;
+  {
+    const int clusters = grid / NCTA, tiles = p.tiles_m * p.tiles_n;
+    const int rem = tiles % clusters;
+    const bool same_k = p.num_kb[0] == p.num_kb[1] && p.num_kb[0] == p.num_kb[2];
+    if (g_stream_k && tiles > clusters && rem > 0 && rem * 100 < clusters * 92 && same_k &&
+        (long long)rem * p.num_kb[0] >= 8LL * clusters) {
+      const size_t need = WS_FLAG_BYTES + (size_t)grid * GEMM_SLOT_FLOATS * sizeof(float);
+      char* ws = static_cast<char*>(workspace_region(stream, 1, need));
+      if (ws != nullptr && (size_t)grid * sizeof(int) <= (size_t)WS_FLAG_BYTES) {
+        p.sk_tiles = rem;
+        ++g_stream_k_launches;
+        p.flags = reinterpret_cast<int*>(ws);
+        p.slots = reinterpret_cast<float*>(ws + WS_FLAG_BYTES);
+      }
+    }
+  }
   double flops = 0;
   for (int g = 0; g < d.n_groups; ++g) {
     const int m_end = g + 1 < d.n_groups ? d.group[g + 1].m_begin : d.M;
     flops += 2.0 * (m_end - d.group[g].m_begin) * (double)d.N * d.group[g].K;
   }
+  p.tl = timeline_next(KC_GEMM);
   LaunchScope scope(KC_GEMM, stream, flops);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -548,10 +728,11 @@ int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
   return LX_OK;
 }
 
-// N tile that minimises (number of waves) x (tile width); ties go to the wider tile.
-int pick_tile_n(int M, int N, bool need_256, int ncta) {
-  if (need_256) return 256;
-  const int units = num_sms() / ncta;
+// N tile that minimises (number of waves) x (tile width); ties go to the wider tile.  With the stream-K head available
+// (`frac_waves`: the partial last wave costs only its share) the widest tile always wins.
+int pick_tile_n(int M, int N, bool need_256, int ncta, bool frac_waves) {
+  if (need_256 || (frac_waves && N % 256 == 0)) return 256;
+  const int units = max((g_fake_sms > 0 ? g_fake_sms : num_sms()) / ncta, 1);
   const int tiles_m = (M + BM * ncta - 1) / (BM * ncta);
   int best = 256;
   long best_cost = -1;
@@ -573,6 +754,9 @@ static int g_force_ncta = 0;
 extern "C" void lx_debug_gemm_force_ncta(int ncta) { g_force_ncta = ncta; }
 // development aid: L2 budget (MB) for one raster band of A rows; a huge value restores the plain M-fastest order
 extern "C" void lx_debug_gemm_raster_budget_mb(int mb) { lx::g_raster_budget_mb = mb; }
+extern "C" void lx_debug_gemm_stream_k(int on) { lx::g_stream_k = on; }
+extern "C" void lx_debug_gemm_sms(int n) { lx::g_fake_sms = n; }
+extern "C" long long lx_debug_gemm_stream_k_launches(void) { return lx::g_stream_k_launches; }
 
 extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
   using namespace lx;
@@ -622,7 +806,14 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
   for (int g = 0; g < d.n_groups; ++g) pair_ok = pair_ok && d.group[g].m_begin % 256 == 0;
   const int ncta = pair_ok ? 2 : 1;
   int bn = d.tile_n;
-  if (bn == 0) bn = pick_tile_n(d.M, d.N, need_256, ncta);
+  if (bn == 0) {
+    bool same_k = true;
+    for (int g = 1; g < d.n_groups; ++g) same_k = same_k && (d.group[g].K + BK - 1) / BK == (d.group[0].K + BK - 1) / BK;
+    const bool frac_waves = g_stream_k && same_k && workspace_region(stream, 1, WS_FLAG_BYTES) != nullptr &&
+                            (long long)((d.M + BM * ncta - 1) / (BM * ncta)) * ((d.N + 255) / 256) >
+                                (g_fake_sms > 0 ? g_fake_sms : num_sms()) / ncta;
+    bn = pick_tile_n(d.M, d.N, need_256, ncta, frac_waves);
+  }
   // 128 is never picked automatically (the DiT shapes are tuned on 256 / 224 / 192); callers with N <= 128 outputs (the
   // VAE's 128-channel convolutions) force it to avoid a third of idle tile columns
   LX_CHECK_ARG(bn == 256 || ((bn == 224 || bn == 192 || bn == 128) && !need_256), "lx_gemm_bf16: tile_n=%d not allowed here", bn);

@@ -142,6 +142,17 @@ void* workspace_region(void* stream, int which, size_t need_bytes) {
   return static_cast<char*>(g_ws_ptr) + (size_t)which * region;
 }
 
+static int g_skip_mask = 0;
+int debug_skip_mask() { return g_skip_mask; }
+static long long* g_tl_buf = nullptr;
+static int g_tl_cap = 0, g_tl_next = 0;
+static std::vector<int> g_tl_cls;
+long long* timeline_next(int cls) {
+  if (g_tl_buf == nullptr || g_tl_next >= g_tl_cap) return nullptr;
+  g_tl_cls.push_back(cls);  // host side: nothing may be enqueued between two kernels (it would change what is measured)
+  return g_tl_buf + 4LL * g_tl_next++;
+}
+
 // ------------------------------------------------------------------------------------------- launch accounting
 struct ProfRec {
   cudaEvent_t e0, e1;
@@ -206,6 +217,16 @@ int lx_profile_end(double* ms, int64_t* launches, double* work) {
   lx::g_recs.clear();
   return LX_OK;
 }
+
+void lx_debug_skip(int mask) { lx::g_skip_mask = mask; }
+void lx_debug_timeline(long long* device_buffer, int capacity) {
+  lx::g_tl_buf = device_buffer;
+  lx::g_tl_cap = capacity;
+  lx::g_tl_next = 0;
+  lx::g_tl_cls.clear();
+}
+int lx_debug_timeline_count(void) { return lx::g_tl_next; }
+int lx_debug_timeline_class(int i) { return i >= 0 && i < (int)lx::g_tl_cls.size() ? lx::g_tl_cls[i] : -1; }
 
 int lx_set_workspace(void* ptr, int64_t bytes, void* stream) {
   if (ptr == nullptr || bytes <= 0) {

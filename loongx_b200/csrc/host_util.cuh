@@ -85,6 +85,15 @@ inline cudaError_t launch_ordered(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Development aid: device-side timeline of the three kernels of the DiT loop.  lx_debug_timeline(buf, capacity) hands the
+// library a device buffer of [capacity][4] int64 = (first CTA entry, first CTA past its programmatic-dependency wait, last
+// CTA exit, unused) in %globaltimer ns, pre-filled by the caller with (INT64_MAX, INT64_MAX, 0, 0); every launch
+// of lx_gemm_bf16 / lx_attention / lx_ln_modulate takes the next row.  NULL switches it off (the default).
+long long* timeline_next(int cls);
+// lx_debug_skip(mask): bit (1 << kernel class) set = that class's launcher returns without launching (timing experiments:
+// the marginal cost of a kernel inside the real loop, with the buffers keeping their last realistic contents)
+int debug_skip_mask();
+
 struct LaunchScope {
   LaunchScope(int cls, void* stream, double work);  // work: FLOPs (tensor kernels) or bytes (HBM-bound kernels)
   ~LaunchScope();

@@ -103,6 +103,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no barrier): warms the L2 ahead of the cp.async.bulk.tensor load
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -136,6 +142,18 @@ __device__ __forceinline__ void tma_store_wait_read() {
 // tail); pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as SM resources free up.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// development-aid timeline (host_util.cuh::timeline_next): row = (min entry, min past-dependency-wait, max exit) in ns
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void timeline_mark(long long* row, int slot) {
+  if (row == nullptr) return;
+  if (slot == 2) atomicMax(reinterpret_cast<unsigned long long*>(row + 2), (unsigned long long)globaltimer_ns());
+  else atomicMin(reinterpret_cast<unsigned long long*>(row + slot), (unsigned long long)globaltimer_ns());
+}
 
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM

@@ -304,6 +304,10 @@ class LoraFactor:
         return self.shared.merged != (self.A._version, self.B._version)
 
 
+ALLREDUCE_LOG: list = []  # (start event, end event, bytes) per gradient all-reduce when ALLREDUCE_TIMING is on (bench.py)
+ALLREDUCE_TIMING = False
+
+
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     """DDP gradient synchronisation of the reference's training harness (Lightning DDP): ONE all-reduce
     over the flat fp32 gradient bucket, divided by the world size.  NCCL over NVLink on the GPUs; gloo in the CPU test."""
@@ -311,8 +315,15 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return flat
+    timing = ALLREDUCE_TIMING and flat.is_cuda
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.mul_(1.0 / dist.get_world_size(group))
+    if timing:
+        e1.record()
+        ALLREDUCE_LOG.append((e0, e1, flat.numel() * flat.element_size()))
     return flat
 
 

@@ -343,6 +343,71 @@ def test_dit_full_flux_size_parity():
     assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (e_nat, e_bf)
 
 
+def test_full_flux_size_denoise_loop_parity():
+    """SURVEY.md §8d, 'after the full loop <= 5e-2': the sampler loop at BASELINE.json's configs[1] geometry with the WHOLE
+    FLUX.1-dev-sized DiT (57 blocks, 11.9 B synthetic parameters): LX_LOOP_STEPS (default 4) Euler steps of the shifted
+    sigma schedule, native (lx_dit_prepare once + lx_dit_step / lx_euler_step per step, bf16 latents) against the fp32
+    oracle evaluated on the GPU with the same bf16-rounded weights and an fp32 latent trajectory.  Tolerance: relL2 <= 5e-2
+    on the final latents (and on every intermediate step).  The fp32 oracle forward takes ~0.7 s at this size."""
+    import gc
+    import os
+
+    import numpy as np
+
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights, euler_step, random_params
+    from loongx_b200.sampler import FlowMatchEulerDiscreteScheduler, calculate_shift
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs ~130 GB of free HBM (fp32 oracle weights + native panels)")
+    T = int(os.environ.get("LX_LOOP_STEPS", "4"))
+    dev = "cuda"
+    ocfg, cfg = O.FluxConfig(), FluxConfig()
+    Pb = random_params(cfg, dev, seed=78, w_std=0.02, bias_std=0.02, lora_b_std=0.02)
+    W = DitWeights(Pb, cfg, dev, consume=False)
+    side, nt = 32, 512
+    ni = side * side
+    g = torch.Generator().manual_seed(4)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(dev)  # noqa: E731
+    inp = dict(lat=r(1, ni, 64), cond=r(1, ni, 64), pe=r(1, nt, 4096, scale=0.1), pooled=r(1, 768), img_ids=_ids(side, side).to(dev),
+               cond_ids=_ids(side, side, -side).to(dev), txt_ids=torch.zeros(nt, 3).to(dev), guidance=3.5)
+    sch = FlowMatchEulerDiscreteScheduler()
+    sc = sch.config
+    mu = calculate_shift(ni, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift)
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / T, T), mu=mu)  # generate.py:289-310
+    sig = [float(x) for x in sch.sigmas]  # T + 1 values, the last one 0
+    plan = DitPlan(W, 1, nt, ni, ni, T=T)
+    plan.set_ids(inp["txt_ids"], inp["img_ids"], inp["cond_ids"])
+    plan.prepare(inp["pe"], inp["pooled"], inp["cond"], sig[:T], [3.5], c_t=0.0)
+    lat = inp["lat"].clone()
+    traj = []
+    pred = torch.empty_like(lat)
+    for i in range(T):
+        plan.step(i, lat, pred)
+        lat = euler_step(lat, pred, sig[i + 1] - sig[i])
+        traj.append(lat.float().clone())
+    torch.cuda.synchronize()
+    del plan, W
+    gc.collect()
+    torch.cuda.empty_cache()
+    errs = []
+    with torch.no_grad():
+        P32 = {k: Pb.pop(k).float() for k in list(Pb)}
+        x = inp["lat"].float()
+        for i in range(T):
+            v = _oracle_full(O, ocfg, P32, dict(inp, lat=x), sig[i], torch.float32)
+            x = x + (sig[i + 1] - sig[i]) * v
+            errs.append(_rel(traj[i], x))
+    print(f"\n[full FLUX-size denoise loop, 57 blocks, S=2560, {T} steps] relL2 of the latents after each step: "
+          + " ".join(f"{e:.4g}" for e in errs))
+    assert all(torch.isfinite(t).all() for t in traj)
+    assert max(errs) <= 5e-2, errs
+
+
 @pytest.mark.parametrize("nt,hw", [(128, (8, 16)), (77, (10, 12))])
 def test_dit_cached_condition_branch(nt, hw):
     """with model_config.independent_condition the condition stream is step-invariant; a plan built with

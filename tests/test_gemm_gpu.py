@@ -178,6 +178,114 @@ def test_gemm_qkv_epilogue_and_split_gelu():
     assert (cat[:, :D] == 0).all() and (cat[:, D + F :] == 0).all(), "GELU segment wrote outside its columns"
 
 
+@pytest.mark.parametrize("sms", [6, 8, 12, 20])
+def test_gemm_stream_k_head(sms):
+    """The stream-K head (partial last wave cut along K, fp32 partial tiles exchanged through the workspace) on a
+    pretended SM count so that small shapes take it: plain / ragged, three row groups, gate-residual in place, and the
+    QKV + GELU two-segment epilogue; every case twice (the exchange flags must return to idle)."""
+    import ctypes
+
+    from loongx_b200 import ops, _lib as L
+
+    L.lib.lx_debug_gemm_stream_k_launches.restype = ctypes.c_longlong
+    L.lib.lx_debug_gemm_sms(sms)
+    L.lib.lx_debug_gemm_stream_k(1)  # off by default (slower than the partial wave it removes at the DiT's shapes)
+    n0 = L.lib.lx_debug_gemm_stream_k_launches()
+    try:
+        for rep in range(2):
+            # plain + ragged edges
+            for (M, N, K) in [(640, 1280, 1024), (600, 1096, 1032), (1280, 768, 2048)]:
+                A, W = _mk((M, K), 1.0, 61), _mk((N, K), 0.05, 62)
+                bias = _mk((N,), 1.0, 63, torch.float32)
+                out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+                ops.gemm(A, W, bias, out, L.EPI_BIAS_GELU)
+                ref = torch.nn.functional.gelu(A.float() @ W.float().t() + bias, approximate="tanh")
+                _close(out, ref, atol=3e-2, what=f"stream-k gelu {M}x{N}x{K} sms={sms}")
+            # three row groups
+            M, N, K = 1280, 768, 1536
+            A = _mk((M, K), 1.0, 50)
+            Ws = [_mk((N, K), 0.05, 51 + i) for i in range(3)]
+            bs = [_mk((N,), 1.0, 54 + i, torch.float32) for i in range(3)]
+            out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+            ops.gemm(A, Ws[0], bs[0], out, L.EPI_BIAS, groups=[(Ws[1], bs[1], 256), (Ws[2], bs[2], 768)])
+            ref = torch.cat([A[:256].float() @ Ws[0].float().t() + bs[0], A[256:768].float() @ Ws[1].float().t() + bs[1],
+                             A[768:].float() @ Ws[2].float().t() + bs[2]])
+            _close(out, ref, atol=3e-2, what=f"stream-k row groups sms={sms}")
+            # gate * y + residual, in place
+            B, nt, ni, nc, D, K = 2, 256, 512, 256, 1280, 2048
+            R = B * (nt + ni + nc)
+            meta = ops.make_tile_meta(B, nt, ni, nc, "cuda")
+            A, W = _mk((R, K), 1.0, 9), _mk((D, K), 0.03, 10)
+            bias = _mk((D,), 0.5, 11, torch.float32)
+            x = _mk((R, D), 1.0, 12)
+            gates = [_mk((B, 3 * D), 1.0, 13 + i) for i in range(3)]
+            gviews = [g[:, D: 2 * D] for g in gates]
+            x0 = x.clone()
+            ops.gemm(A, W, bias, x, L.EPI_GATE_RESIDUAL, tile_meta=meta, residual=x, gate=gviews)
+            lin = A.float() @ W.float().t() + bias
+            ref = torch.empty_like(lin)
+            for t, (stream, b, _, _) in enumerate(meta.cpu().tolist()):
+                sl = slice(t * 128, (t + 1) * 128)
+                ref[sl] = x0[sl].float() + gviews[stream][b].float()[None, :] * lin[sl]
+            _close(x, ref, atol=3e-2, what=f"stream-k gate_residual sms={sms}")
+            # QKV epilogue + GELU segment
+            B, nt, ni, nc, H, K, F = 2, 256, 256, 256, 2, 1024, 512
+            D = H * 128
+            S = nt + ni + nc
+            R = B * S
+            meta = ops.make_tile_meta(B, nt, ni, nc, "cuda")
+            A, W = _mk((R, K), 1.0, 20), _mk((3 * D + F, K), 0.04, 21)
+            bias = _mk((3 * D + F,), 0.3, 22, torch.float32)
+            rms_q = [(_mk((128,), 0.2, 23 + i, torch.float32) + 1.0) for i in range(3)]
+            rms_k = [(_mk((128,), 0.2, 26 + i, torch.float32) + 1.0) for i in range(3)]
+            rope = _rope_table(S, 29)
+            q = torch.full((B, H, S, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+            k, v = q.clone(), q.clone()
+            cat = torch.zeros((R, D + F + 64), device="cuda", dtype=torch.bfloat16)
+            ops.gemm(A, W, bias, None, L.EPI_QKV, n_split=3 * D, seg1=(L.EPI_BIAS_GELU, cat, D), tile_meta=meta,
+                     qkv=(q, k, v), rms_q=rms_q, rms_k=rms_k, rope=rope, rms_eps=1e-6)
+            lin = A.float() @ W.float().t() + bias
+            rq, rk, rv = _ref_qkv(lin[:, : 3 * D], meta, B, H, S, rms_q, rms_k, rope, 1e-6)
+            _close(q, rq, what=f"stream-k q sms={sms}")
+            _close(k, rk, what=f"stream-k k sms={sms}")
+            _close(v, rv, atol=3e-2, what=f"stream-k v sms={sms}")
+            _close(cat[:, D: D + F], torch.nn.functional.gelu(lin[:, 3 * D:], approximate="tanh"), atol=3e-2,
+                   what=f"stream-k mlp segment sms={sms}")
+        torch.cuda.synchronize()
+        assert L.lib.lx_debug_gemm_stream_k_launches() > n0, "no launch took the stream-K path: the test shapes are stale"
+    finally:
+        L.lib.lx_debug_gemm_sms(0)
+        L.lib.lx_debug_gemm_stream_k(0)
+
+
+def test_gemm_stream_k_on_off_agree_at_flux_shapes():
+    """The DiT's N = 3072 projections at M = 2560 with and without the stream-K head (same kernel, different schedule):
+    results agree to fp32 summation order; prints both timings (informational)."""
+    from loongx_b200 import ops, _lib as L
+
+    for (N, K) in [(3072, 3072), (3072, 12288), (12288, 3072)]:
+        M = 2560
+        A, W = _mk((M, K), 1.0, 71), _mk((N, K), 0.02, 72)
+        outs, times = [], []
+        for on in (0, 1):
+            L.lib.lx_debug_gemm_stream_k(on)
+            out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+            for _ in range(3):
+                ops.gemm(A, W, None, out, L.EPI_BIAS)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ops.gemm(A, W, None, out, L.EPI_BIAS)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 20)
+            outs.append(out.float())
+        L.lib.lx_debug_gemm_stream_k(0)
+        tf = [2 * M * N * K / t / 1e9 for t in times]
+        print(f"\n[gemm stream-k] {M}x{N}x{K}: off {times[0]*1e3:.1f} us ({tf[0]:.0f} TF), on {times[1]*1e3:.1f} us ({tf[1]:.0f} TF)")
+        assert ((outs[0] - outs[1]).abs() <= 2e-2 + outs[0].abs() / 128).all()
+
+
 def test_gemm_bad_args_raise():
     from loongx_b200 import ops, _lib as L
 

@@ -55,8 +55,8 @@ def _attach_small_encoders(model):
 
     pipe = model.flux_pipe
     pipe.attach_vae(None)
-    ck = dict(vocab_size=99, hidden_size=768, intermediate_size=128, num_layers=1, num_heads=12, max_positions=77)
-    tk = dict(vocab_size=99, d_model=4096, d_kv=64, d_ff=128, num_layers=1, num_heads=2)
+    ck = dict(vocab_size=99, hidden_size=768, intermediate_size=256, num_layers=1, num_heads=12, max_positions=77)
+    tk = dict(vocab_size=99, d_model=4096, d_kv=64, d_ff=256, num_layers=1, num_heads=2)
     PC = {k: v.to(torch.bfloat16).float() for k, v in OT.clip_init(OT.ClipCfg(**ck), 5).items()}
     PT = {k: v.to(torch.bfloat16).float() for k, v in OT.t5_init(OT.T5Cfg(**tk), 6).items()}
 
