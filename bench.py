@@ -281,8 +281,11 @@ def run_native(args, rank, local_rank, world):
     att_tf = work[1] / ms[1] / 1e9 if ms[1] else 0.0
     row_gbs = work[2] / ms[2] / 1e6 if ms[2] else 0.0
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "gemm_traffic_r1e.json")
-    if os.path.exists(tp) and B == 1:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    # DRAM bytes per launch of the dominant kernel: the newest committed ncu --set full capture (scripts/ncu_summary.py
+    # gemm_traffic); re-captured whenever csrc/gemm.cu changes
+    tps = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("gemm_traffic_") and f.endswith(".json"))
+    tp = os.path.join(ROOT, "profiles", tps[-1]) if tps else ""
+    if tp and B == 1:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
         tj = json.load(open(tp))
         traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     roofline = {"bound": "tensor", "kernel": "lx::gemm_bf16_kernel (tcgen05 GEMM + fused epilogues)", "achieved": gemm_tf,

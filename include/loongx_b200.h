@@ -317,6 +317,10 @@ int lx_channel_linear(const float* in, const float* W, const float* bias, const 
 /* nn.AdaptiveAvgPool1d(O) on in [B, C, L]; out[b*out_bstride + c*cs + i*is + off] (model.py:83-103, 345-373). */
 int lx_adaptive_pool(const float* in, float* out, int32_t B, int32_t C, int32_t L, int32_t O, int64_t out_bstride,
                      int32_t cs, int32_t is, int32_t off, void* stream);
+/* Several nn.AdaptiveAvgPool1d sizes of the same input in ONE launch (FeaturePyramidPooling, model.py:345-373): bin i of
+ * pool k -> out[b*out_bstride + c*cs + off[k] + i], n <= 8 (host arrays O, off). */
+int lx_adaptive_pool_multi(const float* in, float* out, int32_t B, int32_t C, int32_t L, int32_t n, const int32_t* O,
+                           const int32_t* off, int64_t out_bstride, int32_t cs, void* stream);
 /* y[b, :] = W[n_out, n_in] x[b, :] + bias for B <= 8 rows (weights streamed once). */
 int lx_gemv_f32(const float* W, const float* bias, const float* x, float* y, int32_t B, int32_t n_out, int32_t n_in,
                 int64_t ldx, int64_t ldy, void* stream);
@@ -344,6 +348,8 @@ typedef struct lx_sgemm_desc {
   int32_t M, N, K, batch;
   int32_t act;
   int32_t reserved;
+  float* rowpart; /* with rowmean: scratch [batch, M, ceil(N / 64)] -> the mean is summed in a fixed order (bit-reproducible);
+                     NULL = float atomics into a zeroed rowmean */
 } lx_sgemm_desc_t;
 int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream);
 
@@ -363,9 +369,80 @@ typedef struct lx_duan_weights {
   int32_t hidden;
   float eps;
 } lx_duan_weights_t;
-/* y[b] (batch stride y_bstride) = DUAN(x, c) for fp32 x, c [B, C, L]; workspace: fp32 [B*(12*C + hidden*(L+1))]. */
+/* y[b] (batch stride y_bstride) = DUAN(x, c) for fp32 x, c [B, C, L]; workspace: fp32
+ * [B*(12*C + hidden*(L+1) + C*ceil(L/64))].  Bit-reproducible (no float atomics). */
 int lx_duan_forward(const lx_duan_weights_t* w, const float* x, const float* c, float* y, int64_t y_bstride, int32_t B,
                     int32_t C, int32_t L, float keep_ratio, float* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Backward of CS3 / DGF (fp32): the gradients `loss.backward()` leaves on every encoder / fusion parameter of the
+ * reference's OminiModel.step (src/train/model.py:656-701 runs inside the autograd graph; Lightning's DDP all-reduces
+ * them together with the LoRA factors, train.py:181-183).  Weight / bias gradients are ACCUMULATED (+=).
+ * ------------------------------------------------------------------------------------------------------ */
+/* C[b] = alpha op(A[b]) op(B[b]) + beta C[b];  op(A) is [M, K] (stored [K, M] when trans_a), op(B) is [K, N] (stored
+ * [N, K] when trans_b).  reduce_batch != 0: ONE C = alpha sum_b op(A[b]) op(B[b]) + beta C (weight gradients). */
+typedef struct lx_sgemm_ex_desc {
+  const float* A;
+  int64_t lda, a_bstride;
+  const float* Bm;
+  int64_t ldb, b_bstride;
+  float* C;
+  int64_t ldc, c_bstride;
+  int32_t M, N, K, batch;
+  int32_t trans_a, trans_b, reduce_batch, reserved;
+  float alpha, beta;
+} lx_sgemm_ex_desc_t;
+int lx_sgemm_ex(const lx_sgemm_ex_desc_t* desc, void* stream);
+/* out[j] (+)= sum_r in[r*ld + j]  (bias gradient of a row-batched Linear). */
+int lx_sum_rows_f32(const float* in, int64_t ld, int32_t rows, int32_t n, float* out, int32_t accumulate, void* stream);
+/* out[c] (+)= sum_b sum_l a[b,c,l] (* b[b,c,l] when b != NULL) for [B, C, L] tensors (bias gradients of 1x1 convs /
+ * channel Linears; the S4 skip gradient dD = sum ds * u). */
+int lx_sum_last_f32(const float* a, const float* b, int32_t B, int32_t C, int32_t L, float* out, int32_t accumulate,
+                    void* stream);
+/* Backward of lx_ln_relu_rows: y = relu(LayerNorm(x) w + b) -> dx; dw, db += (model.py:60-72). */
+int lx_ln_relu_rows_bwd(const float* x, const float* w, const float* b, const float* dy, float* dx, float* dw, float* db,
+                        int32_t rows, int32_t n, float eps, void* stream);
+/* nn.Dropout(p) in train mode (model.py:64,68): y[i] = keep(seed, i) ? x[i] / (1 - p) : 0 with a counter-based mask, so
+ * the backward is the same call on the gradient with the same seed.  (The mask stream is not torch's Philox stream.) */
+int lx_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+/* Backward of lx_token_linear: dh[b, 8t+k] = sum_o dout[b,t,o] W[o,k]; dW, dbias +=. */
+int lx_token_linear_bwd(const float* h, const float* W, const float* dout, float* dh, float* dW, float* dbias, int32_t B,
+                        int32_t tokens, int32_t n_out, int64_t out_bstride, void* stream);
+/* Backward of lx_adaptive_pool (same index arguments): din[b,c,l] += dfeat[...] / bin length. */
+int lx_adaptive_pool_bwd(const float* dfeat, float* din, int32_t B, int32_t C, int32_t L, int32_t O, int64_t f_bstride,
+                         int32_t cs, int32_t is, int32_t off, void* stream);
+/* LayerNorm over the d channels of v [B, d, L] (S4Block post-norm): dv from dy; dw, db +=. */
+int lx_channel_ln_bwd(const float* v, const float* w, const float* dy, float* dv, float* dw, float* db, int32_t B, int32_t d,
+                      int32_t L, float eps, void* stream);
+/* ds = dg * gelu_erf'(s). */
+int lx_gelu_erf_bwd(const float* s, const float* dg, float* ds, int64_t n, void* stream);
+/* y = act(causal_conv(u, K) + D u) like lx_s4_conv_gelu, with: pre (optional) = the pre-activation; reverse != 0 =
+ * u and y are indexed time-reversed (the adjoint of the causal convolution: du = conv_reversed(ds, K) + D ds);
+ * gelu == 0 = no activation; D may be NULL. */
+int lx_s4_conv(const float* u, const float* K, const float* D, float* y, float* pre, int32_t B, int32_t d, int32_t L,
+               int32_t reverse, int32_t gelu, void* stream);
+/* dK[c, j] (+)= sum_b sum_{l>=j} ds[b,c,l] u[b,c,l-j]. */
+int lx_s4_conv_wgrad(const float* ds, const float* u, float* dK, int32_t B, int32_t d, int32_t L, int32_t accumulate,
+                     void* stream);
+/* Backward of lx_s4_kernel_gen: dK [d, L] -> dB, dCt (complex64 [d, n], +=; torch's dL/dRe + i dL/dIm convention),
+ * dlog_step [d] (+=).  workspace: 72 * d * L bytes. */
+int lx_s4_kernel_gen_bwd(const void* lam, const void* p, const void* q, const void* Bm, const void* Ct, const float* log_step,
+                         const float* dK, void* dB, void* dCt, float* dlog_step, void* workspace, int32_t d, int32_t n,
+                         int32_t L, void* stream);
+/* Backward of lx_duan_forward.  fwd_ws: the workspace the forward filled for the same (x, c); dw: where the eight weight
+ * gradients accumulate (same layout as w); dy has batch stride dy_bstride; dx / dc may be NULL, acc_* != 0 accumulates.
+ * ws: fp32 scratch [B*C*L + B*hidden*L + B*(8*C + 2*hidden)].  The top-k channel mask is a constant (as in autograd). */
+int lx_duan_backward(const lx_duan_weights_t* w, const lx_duan_weights_t* dw, const float* x, const float* c, const float* dy,
+                     int64_t dy_bstride, float* dx, float* dc, int32_t acc_dx, int32_t acc_dc, int32_t B, int32_t C, int32_t L,
+                     const float* fwd_ws, float* ws, void* stream);
+/* out[b, k] += sum_n d[b, n] W[n, k] for a bf16 panel W [N, K] read once, B <= 8 (gradient of the conditioning vectors
+ * through the DiT's AdaLN / time-text-embedding Linears, transformer.py:102-114). */
+int lx_skinny_xw_bf16(const float* d, int64_t ldd, const void* W, int64_t ldw, float* out, int64_t ldo, int32_t B, int32_t N,
+                      int32_t K, void* stream);
+/* dpre = dy * silu'(a + b + c[m % c_rows]) for bf16 a, b, c (backward of lx_add_silu_bcast); and the fp32 form. */
+int lx_silu_bwd_sum(const float* dy, const void* a, const void* b, const void* c, int32_t c_rows, float* dpre, int32_t M,
+                    int32_t D, void* stream);
+int lx_silu_bwd_f32(const float* dy, const float* pre, float* dpre, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Training step (OminiModel.step, src/train/model.py:569-729): rectified-flow objective around tranformer_forward with

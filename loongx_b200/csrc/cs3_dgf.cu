@@ -109,89 +109,169 @@ __global__ void s4_idft_kernel(const double2* __restrict__ at_roots, float* __re
   K[(size_t)c * L + k] = (float)(acc / L);
 }
 
-// ------------------------------------------------------------------------------------------------ S4 convolution
-// y[b,c,l] = gelu( sum_{j<=l} K[c,j] u[b,c,l-j] + D[c] u[b,c,l] ); one CTA = 128 outputs of one (b, c)
-constexpr int CONV_T = 128;
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// The same transform as a radix-2 FFT when L is a power of two (every signal length of the model is: 4096 / 512 / 256 /
+// 128): one CTA per channel, the L complex128 values stay in shared memory through the log2(L) butterfly stages.
+// kInverse: exp(+2 pi i jk / L) (kernel generation: K = Re(IDFT(at_roots)));  else exp(-2 pi i jk / L) (its adjoint:
+// G_at = DFT(dK) / L).  Input real (in_r) or complex (in_c); output real part (out_r) or complex (out_c), scaled by 1 / L.
+template <bool kInverse>
+__global__ void __launch_bounds__(512) s4_fft_kernel(const double2* __restrict__ in_c, const float* __restrict__ in_r,
+                                                     double2* __restrict__ out_c, float* __restrict__ out_r, int L, int logL) {
+  extern __shared__ double2 sf[];
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const int j = (int)(__brev((unsigned)i) >> (32 - logL));
+    sf[j] = in_c != nullptr ? in_c[(size_t)c * L + i] : make_double2((double)in_r[(size_t)c * L + i], 0.0);
+  }
+  __syncthreads();
+  for (int len = 2; len <= L; len <<= 1) {
+    const int half = len >> 1;
+    for (int t = threadIdx.x; t < (L >> 1); t += blockDim.x) {
+      const int grp = t / half, pos = t - grp * half;
+      const int i = grp * len + pos, j = i + half;
+      double sn, cs;
+      sincospi((kInverse ? 2.0 : -2.0) * (double)pos / (double)len, &sn, &cs);
+      const double2 u = sf[i], v = sf[j];
+      const double2 vw = make_double2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+      sf[i] = make_double2(u.x + vw.x, u.y + vw.y);
+      sf[j] = make_double2(u.x - vw.x, u.y - vw.y);
+    }
+    __syncthreads();
+  }
+  const double inv = 1.0 / (double)L;
+  for (int k = threadIdx.x; k < L; k += blockDim.x) {
+    if (out_r != nullptr) out_r[(size_t)c * L + k] = (float)(sf[k].x * inv);
+    else out_c[(size_t)c * L + k] = make_double2(sf[k].x * inv, sf[k].y * inv);
+  }
+}
 
-__global__ void __launch_bounds__(CONV_T) s4_conv_gelu_kernel(const float* __restrict__ u, const float* __restrict__ K,
-                                                              const float* __restrict__ Dp, float* __restrict__ y, int d,
-                                                              int L) {
+// ------------------------------------------------------------------------------------------------ S4 convolution
+// y[b,c,l] = act( sum_{j<=l} K[c,j] u[b,c,l-j] + D[c] u[b,c,l] ), act = GELU(erf) or identity, optional pre-activation
+// output, optional time reversal of u and y (the adjoint of a causal convolution is the causal convolution of the reversed
+// sequence: used by the backward).  One CTA = 1024 consecutive outputs of one (b, c): each of the 128 threads owns EIGHT
+// consecutive outputs and slides an 8-value register window over the input, so one shared-memory read of u and one
+// (broadcast) read of K feed eight FMAs (the first version did one FMA per two shared-memory reads).  The u window is
+// stored with a one-word skew per 32 words, which makes the stride-8 window reads conflict-free.
+constexpr int CONV_T = 128, CONV_R = 8, CONV_OUT = CONV_T * CONV_R;
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ int conv_skew(int i) { return i + (i >> 5); }
+
+template <bool kReverse, bool kGelu>
+__global__ void __launch_bounds__(CONV_T) s4_conv_kernel(const float* __restrict__ u, const float* __restrict__ K,
+                                                         const float* __restrict__ Dp, float* __restrict__ y,
+                                                         float* __restrict__ pre, int d, int L) {
+  constexpr int WIN = CONV_OUT + CONV_T;  // u[base .. base + WIN), base = l0 - j0 - 127 (one slot more than needed)
   __shared__ float sK[CONV_T];
-  __shared__ float sU[2 * CONV_T];
+  __shared__ float sU[WIN + WIN / 32 + 1];
   const int c = blockIdx.y, b = blockIdx.z;
-  const int l0 = blockIdx.x * CONV_T;
+  const int l0 = blockIdx.x * CONV_OUT;
   const int t = threadIdx.x;
-  const int l = l0 + t;
   const float* ub = u + ((size_t)b * d + c) * L;
   const float* Kc = K + (size_t)c * L;
-  float acc = 0.f;
-  // chunks of 128 kernel taps j in [j0, j0+128); output l uses u[l - j]
-  for (int j0 = 0; j0 <= l0 + CONV_T - 1; j0 += CONV_T) {
+  auto ld_u = [&](int i) -> float { return (i >= 0 && i < L) ? ub[kReverse ? L - 1 - i : i] : 0.f; };
+  float acc[CONV_R];
+#pragma unroll
+  for (int r = 0; r < CONV_R; ++r) acc[r] = 0.f;
+  const int l_hi = min(L, l0 + CONV_OUT) - 1;  // last output of this CTA
+  for (int j0 = 0; j0 <= l_hi; j0 += CONV_T) {
     __syncthreads();
     sK[t] = (j0 + t < L) ? Kc[j0 + t] : 0.f;
-    // u window: indices base .. base + 255 with base = l0 - j0 - 127
     const int base = l0 - j0 - (CONV_T - 1);
-    const int i0 = base + t, i1 = base + CONV_T + t;
-    sU[t] = (i0 >= 0 && i0 < L) ? ub[i0] : 0.f;
-    sU[CONV_T + t] = (i1 >= 0 && i1 < L) ? ub[i1] : 0.f;
+    for (int i = t; i < WIN; i += CONV_T) sU[conv_skew(i)] = ld_u(base + i);
     __syncthreads();
-    // u[l - (j0 + jj)] = sU[(l - j0 - jj) - base] = sU[t + 127 - jj]
-#pragma unroll 16
-    for (int jj = 0; jj < CONV_T; ++jj) acc = fmaf(sK[jj], sU[t + (CONV_T - 1) - jj], acc);
+    // output l_r = l0 + 8 t + r, tap j0 + jj: u[l_r - j0 - jj] = window[8 t + r + 127 - jj]
+    float w[CONV_R];
+#pragma unroll
+    for (int r = 0; r < CONV_R; ++r) w[r] = sU[conv_skew(CONV_R * t + r + CONV_T - 1)];
+#pragma unroll 8
+    for (int jj = 0; jj < CONV_T; ++jj) {
+      const float kv = sK[jj];
+#pragma unroll
+      for (int r = 0; r < CONV_R; ++r) acc[r] = fmaf(kv, w[r], acc[r]);
+#pragma unroll
+      for (int r = CONV_R - 1; r > 0; --r) w[r] = w[r - 1];
+      w[0] = sU[conv_skew(CONV_R * t + CONV_T - 2 - jj + (jj == CONV_T - 1 ? 1 : 0))];  // (last value unused)
+    }
   }
-  if (l < L) {
-    const float ul = ub[l];
-    y[((size_t)b * d + c) * L + l] = gelu_erf(acc + Dp[c] * ul);
+#pragma unroll
+  for (int r = 0; r < CONV_R; ++r) {
+    const int l = l0 + CONV_R * t + r;
+    if (l < L) {
+      const float sv = acc[r] + (Dp ? Dp[c] * ld_u(l) : 0.f);
+      const size_t o = ((size_t)b * d + c) * L + (kReverse ? L - 1 - l : l);
+      if (pre != nullptr) pre[o] = sv;
+      y[o] = kGelu ? gelu_erf(sv) : sv;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ channel linear
 // out[b, j, l] = sum_c W[j, c] in[b, c, l] + bias[j]; optional residual add + LayerNorm over the d_out channels.
-constexpr int CL_MAX = 64;
-__global__ void channel_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
-                                      const float* __restrict__ bias, const float* __restrict__ residual,
-                                      const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                      float* __restrict__ out, int d_in, int d_out, int L, float eps) {
+// One CTA = 32 positions x 8 output groups (one warp per group: the weight reads are shared-memory broadcasts, the
+// activation reads 128-byte rows); 128 CTAs per sample at L = 4096 (the first version ran 32 CTAs of 128 threads with all
+// d_out accumulators in one thread: 60 us per launch for 17 MFLOP).
+constexpr int CL_MAX = 64, CL_GROUPS = 8, CL_JPT = CL_MAX / CL_GROUPS;
+__global__ void __launch_bounds__(256) channel_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, const float* __restrict__ residual,
+                                                             const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                             float* __restrict__ out, int d_in, int d_out, int L, float eps) {
   extern __shared__ float sW[];  // [d_out * d_in] + [d_out] bias
+  __shared__ float red[CL_GROUPS][32];
   for (int i = threadIdx.x; i < d_out * d_in; i += blockDim.x) sW[i] = W[i];
   for (int i = threadIdx.x; i < d_out; i += blockDim.x) sW[d_out * d_in + i] = bias[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
-  float acc[CL_MAX];
+  const int lp = threadIdx.x & 31, jg = threadIdx.x >> 5;
+  const int l = blockIdx.x * 32 + lp;
+  const int jpt = (d_out + CL_GROUPS - 1) / CL_GROUPS;  // outputs per thread (<= CL_JPT)
+  const int jb = jg * jpt;
+  const bool lok = l < L;
+  float acc[CL_JPT];
 #pragma unroll
-  for (int j = 0; j < CL_MAX; ++j) acc[j] = (j < d_out) ? sW[d_out * d_in + j] : 0.f;
-  for (int c = 0; c < d_in; ++c) {
-    const float x = in[((size_t)b * d_in + c) * L + l];
+  for (int i = 0; i < CL_JPT; ++i) acc[i] = (i < jpt && jb + i < d_out) ? sW[d_out * d_in + jb + i] : 0.f;
+  if (lok) {
+    for (int c = 0; c < d_in; ++c) {
+      const float x = in[((size_t)b * d_in + c) * L + l];
 #pragma unroll
-    for (int j = 0; j < CL_MAX; ++j)
-      if (j < d_out) acc[j] = fmaf(sW[j * d_in + c], x, acc[j]);
+      for (int i = 0; i < CL_JPT; ++i)
+        if (i < jpt && jb + i < d_out) acc[i] = fmaf(sW[(jb + i) * d_in + c], x, acc[i]);
+    }
+    if (residual != nullptr) {
+#pragma unroll
+      for (int i = 0; i < CL_JPT; ++i)
+        if (i < jpt && jb + i < d_out) acc[i] += residual[((size_t)b * d_out + jb + i) * L + l];
+    }
   }
-  if (residual != nullptr) {
+  if (ln_w != nullptr) {  // LayerNorm over the channels of one position = over the 8 groups of this lane
+    float ps = 0.f;
 #pragma unroll
-    for (int j = 0; j < CL_MAX; ++j)
-      if (j < d_out) acc[j] += residual[((size_t)b * d_out + j) * L + l];
-  }
-  if (ln_w != nullptr) {
+    for (int i = 0; i < CL_JPT; ++i)
+      if (i < jpt && jb + i < d_out) ps += acc[i];
+    red[jg][lp] = ps;
+    __syncthreads();
     float mean = 0.f;
 #pragma unroll
-    for (int j = 0; j < CL_MAX; ++j)
-      if (j < d_out) mean += acc[j];
+    for (int g2 = 0; g2 < CL_GROUPS; ++g2) mean += red[g2][lp];
     mean /= d_out;
+    __syncthreads();
+    float pv = 0.f;
+#pragma unroll
+    for (int i = 0; i < CL_JPT; ++i)
+      if (i < jpt && jb + i < d_out) pv += (acc[i] - mean) * (acc[i] - mean);
+    red[jg][lp] = pv;
+    __syncthreads();
     float var = 0.f;
 #pragma unroll
-    for (int j = 0; j < CL_MAX; ++j)
-      if (j < d_out) var += (acc[j] - mean) * (acc[j] - mean);
+    for (int g2 = 0; g2 < CL_GROUPS; ++g2) var += red[g2][lp];
     const float rstd = rsqrtf(var / d_out + eps);
 #pragma unroll
-    for (int j = 0; j < CL_MAX; ++j)
-      if (j < d_out) acc[j] = (acc[j] - mean) * rstd * ln_w[j] + ln_b[j];
+    for (int i = 0; i < CL_JPT; ++i)
+      if (i < jpt && jb + i < d_out) acc[i] = (acc[i] - mean) * rstd * ln_w[jb + i] + ln_b[jb + i];
   }
+  if (lok) {
 #pragma unroll
-  for (int j = 0; j < CL_MAX; ++j)
-    if (j < d_out) out[((size_t)b * d_out + j) * L + l] = acc[j];
+    for (int i = 0; i < CL_JPT; ++i)
+      if (i < jpt && jb + i < d_out) out[((size_t)b * d_out + jb + i) * L + l] = acc[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ adaptive avg pool
@@ -209,6 +289,28 @@ __global__ void adaptive_pool_kernel(const float* __restrict__ in, float* __rest
   out[(size_t)b * out_bstride + (size_t)c * cs + (size_t)i * is + off] = acc / (float)(e - s);
 }
 
+// Several pooling sizes of the same input in one launch (FeaturePyramidPooling: concat over `n` output sizes, model.py:
+// 345-373): bin i of pool k goes to out[b * out_bstride + c * cs + off_k + i].
+struct PoolList {
+  int n;
+  int O[8], off[8], start[9];  // start = prefix sums of O (thread index -> pool)
+};
+__global__ void adaptive_pool_multi_kernel(const float* __restrict__ in, float* __restrict__ out, int Cc, int L,
+                                           int64_t out_bstride, int cs, const PoolList pl) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (idx >= pl.start[pl.n]) return;
+  int k = 0;
+  while (k + 1 < pl.n && idx >= pl.start[k + 1]) ++k;
+  const int O = pl.O[k], i = idx - pl.start[k];
+  const int s = (int)(((int64_t)i * L) / O);
+  const int e = (int)((((int64_t)(i + 1)) * L + O - 1) / O);
+  const float* x = in + ((size_t)b * Cc + c) * L;
+  float acc = 0.f;
+  for (int l = s; l < e; ++l) acc += x[l];
+  out[(size_t)b * out_bstride + (size_t)c * cs + pl.off[k] + i] = acc / (float)(e - s);
+}
+
 // ------------------------------------------------------------------------------------------------ GEMV (B <= 8)
 // y[b, j] = sum_i W[j, i] x[b, i] + bias[j]; one warp per output row j, W streamed once with float4 loads.
 constexpr int GEMV_MAXB = 8;
@@ -223,7 +325,23 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ W, 
 #pragma unroll
   for (int b = 0; b < GEMV_MAXB; ++b) acc[b] = 0.f;
   const int n4 = n_in >> 2;
-  for (int i = lane; i < n4; i += 32) {
+  int i = lane;
+  for (; i + 96 < n4; i += 128) {  // four independent 16-byte weight loads in flight per lane (the row is streamed once)
+    float4 wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wv[q] = __ldg(reinterpret_cast<const float4*>(w) + i + 32 * q);
+#pragma unroll
+    for (int b = 0; b < GEMV_MAXB; ++b) {
+      if (b < B) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 xv = *(reinterpret_cast<const float4*>(x + (size_t)b * ldx) + i + 32 * q);
+          acc[b] += wv[q].x * xv.x + wv[q].y * xv.y + wv[q].z * xv.z + wv[q].w * xv.w;
+        }
+      }
+    }
+  }
+  for (; i < n4; i += 32) {
     const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + i);
 #pragma unroll
     for (int b = 0; b < GEMV_MAXB; ++b) {
@@ -310,8 +428,8 @@ __global__ void token_linear_kernel(const float* __restrict__ h, const float* __
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
                                                     int64_t ldb, int64_t b_bstride, const float* __restrict__ bias,
                                                     const float* __restrict__ R, float* __restrict__ Cm, int64_t ldc,
-                                                    int64_t c_bstride, float* __restrict__ rowmean, int M, int N, int K,
-                                                    int act) {
+                                                    int64_t c_bstride, float* __restrict__ rowmean,
+                                                    float* __restrict__ rowpart, int M, int N, int K, int act) {
   __shared__ float sA[16][64 + 4];
   __shared__ float sB[16][64 + 4];
   const int b = blockIdx.z;
@@ -365,9 +483,22 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       // reduce over the 16 tx lanes that share this row (lanes of a half-warp)
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-      if (tx == 0 && m < M) atomicAdd(&rowmean[(size_t)b * M + m], rsum / (float)N);
+      if (tx == 0 && m < M) {
+        // deterministic: per-tile partial sums, added up in tile order by rowmean_finish_kernel (no float atomics)
+        if (rowpart != nullptr) rowpart[((size_t)b * M + m) * gridDim.x + blockIdx.x] = rsum;
+        else atomicAdd(&rowmean[(size_t)b * M + m], rsum / (float)N);
+      }
     }
   }
+}
+
+__global__ void rowmean_finish_kernel(const float* __restrict__ rowpart, float* __restrict__ rowmean, int rows, int tiles,
+                                      int N) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s2 = 0.f;
+  for (int t = 0; t < tiles; ++t) s2 += rowpart[(size_t)r * tiles + t];
+  rowmean[r] = s2 / (float)N;
 }
 
 // ------------------------------------------------------------------------------------------------ DUAN
@@ -515,6 +646,26 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float
   if (i < n) out[i] = __bfloat162float(in[i]);
 }
 
+// shared by the kernel generation (inverse, real output) and its backward (forward transform of the real dK, complex output)
+int s4_fft_launch(bool inverse, const double2* in_c, const float* in_r, double2* out_c, float* out_r, int d, int L,
+                  void* stream) {
+  int logL = 0;
+  while ((1 << logL) < L) ++logL;
+  const size_t smem = (size_t)L * sizeof(double2);
+  static int configured[2] = {0, 0};
+  if (smem > 48 * 1024 && (int)smem > configured[inverse ? 1 : 0]) {
+    if (inverse) LX_CUDA(cudaFuncSetAttribute(s4_fft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else LX_CUDA(cudaFuncSetAttribute(s4_fft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[inverse ? 1 : 0] = (int)smem;
+  }
+  const int threads = L / 2 >= 512 ? 512 : (L / 2 >= 32 ? L / 2 : 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (inverse) s4_fft_kernel<true><<<d, threads, smem, st>>>(in_c, in_r, out_c, out_r, L, logL);
+  else s4_fft_kernel<false><<<d, threads, smem, st>>>(in_c, in_r, out_c, out_r, L, logL);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
 }  // namespace lx
 
 using namespace lx;
@@ -540,6 +691,10 @@ extern "C" int lx_s4_kernel_gen(const void* lam, const void* p, const void* q, c
                                                (const float2*)Ct, log_step, (double2*)workspace, d, n, L);
   LX_CUDA(cudaGetLastError());
   const size_t smem = (size_t)L * sizeof(double2);
+  if ((L & (L - 1)) == 0 && L >= 2) {  // power of two: O(L log L) FFT, one CTA per channel
+    int rc = lx::s4_fft_launch(true, (const double2*)workspace, nullptr, nullptr, K, d, L, stream);
+    return rc;
+  }
   static int configured = 0;
   if (smem > 48 * 1024 && (int)smem > configured) {
     LX_CUDA(cudaFuncSetAttribute(s4_idft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -554,8 +709,37 @@ extern "C" int lx_s4_conv_gelu(const float* u, const float* K, const float* D, f
                                void* stream) {
   LaunchScope scope(KC_CS3DGF, stream, 8.0 * B * d * (double)L + 4.0 * d * (double)L);  // algorithmic bytes
   LX_CHECK_ARG(u && K && D && y && B > 0 && d > 0 && L > 0, "lx_s4_conv_gelu: bad arguments");
-  dim3 grid((L + CONV_T - 1) / CONV_T, d, B);
-  s4_conv_gelu_kernel<<<grid, CONV_T, 0, ST(stream)>>>(u, K, D, y, d, L);
+  return lx_s4_conv(u, K, D, y, nullptr, B, d, L, 0, 1, stream);
+}
+
+extern "C" int lx_s4_conv(const float* u, const float* K, const float* D, float* y, float* pre, int32_t B, int32_t d,
+                          int32_t L, int32_t reverse, int32_t gelu, void* stream) {
+  LaunchScope scope(KC_CS3DGF, stream, 8.0 * B * d * (double)L + 4.0 * d * (double)L);
+  LX_CHECK_ARG(u && K && y && B > 0 && d > 0 && L > 0, "lx_s4_conv: bad arguments");
+  dim3 grid((L + CONV_OUT - 1) / CONV_OUT, d, B);
+  if (reverse && gelu) s4_conv_kernel<true, true><<<grid, CONV_T, 0, ST(stream)>>>(u, K, D, y, pre, d, L);
+  else if (reverse) s4_conv_kernel<true, false><<<grid, CONV_T, 0, ST(stream)>>>(u, K, D, y, pre, d, L);
+  else if (gelu) s4_conv_kernel<false, true><<<grid, CONV_T, 0, ST(stream)>>>(u, K, D, y, pre, d, L);
+  else s4_conv_kernel<false, false><<<grid, CONV_T, 0, ST(stream)>>>(u, K, D, y, pre, d, L);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_adaptive_pool_multi(const float* in, float* out, int32_t B, int32_t C, int32_t L, int32_t n,
+                                      const int32_t* O, const int32_t* off, int64_t out_bstride, int32_t cs, void* stream) {
+  LX_CHECK_ARG(in && out && O && off && B > 0 && C > 0 && L > 0 && n > 0 && n <= 8, "lx_adaptive_pool_multi: bad arguments");
+  PoolList pl;
+  pl.n = n;
+  pl.start[0] = 0;
+  for (int k = 0; k < n; ++k) {
+    LX_CHECK_ARG(O[k] > 0, "lx_adaptive_pool_multi: bad output size");
+    pl.O[k] = O[k];
+    pl.off[k] = off[k];
+    pl.start[k + 1] = pl.start[k] + O[k];
+  }
+  LaunchScope scope(KC_CS3DGF, stream, 4.0 * B * C * ((double)L * n + pl.start[n]));
+  dim3 grid((pl.start[n] + 127) / 128, C, B);
+  adaptive_pool_multi_kernel<<<grid, 128, 0, ST(stream)>>>(in, out, C, L, out_bstride, cs, pl);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -568,9 +752,9 @@ extern "C" int lx_channel_linear(const float* in, const float* W, const float* b
   LX_CHECK_ARG(d_in > 0 && d_in <= CL_MAX && d_out > 0 && d_out <= CL_MAX, "lx_channel_linear: d_in/d_out must be <= %d",
                CL_MAX);
   LX_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "lx_channel_linear: LayerNorm needs both weight and bias");
-  dim3 grid((L + 127) / 128, B);
+  dim3 grid((L + 31) / 32, B);
   const size_t smem = (size_t)(d_out * d_in + d_out) * sizeof(float);
-  channel_linear_kernel<<<grid, 128, smem, ST(stream)>>>(in, W, bias, residual, ln_w, ln_b, out, d_in, d_out, L, eps);
+  channel_linear_kernel<<<grid, 256, smem, ST(stream)>>>(in, W, bias, residual, ln_w, ln_b, out, d_in, d_out, L, eps);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -624,8 +808,13 @@ extern "C" int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.act >= 0 && d.act <= 2, "lx_sgemm_f32: bad activation");
   dim3 grid((d.N + 63) / 64, (d.M + 63) / 64, d.batch);
   sgemm_kernel<<<grid, 256, 0, ST(stream)>>>(d.A, d.lda, d.Bm, d.ldb, d.b_bstride, d.bias, d.R, d.C, d.ldc, d.c_bstride,
-                                             d.rowmean, d.M, d.N, d.K, d.act);
+                                             d.rowmean, d.rowmean ? d.rowpart : nullptr, d.M, d.N, d.K, d.act);
   LX_CUDA(cudaGetLastError());
+  if (d.rowmean != nullptr && d.rowpart != nullptr) {
+    const int rows = d.batch * d.M;
+    rowmean_finish_kernel<<<(rows + 255) / 256, 256, 0, ST(stream)>>>(d.rowpart, d.rowmean, rows, (int)grid.x, d.N);
+    LX_CUDA(cudaGetLastError());
+  }
   return LX_OK;
 }
 
@@ -660,12 +849,12 @@ extern "C" int lx_duan_forward(const lx_duan_weights_t* w, const float* x, const
   float* gb = mask + BC;               // [B, 2C]
   float* hid_pool = gb + 2 * BC;       // [B, Hd]
   float* hid = hid_pool + (size_t)B * Hd;  // [B, Hd, L] gate hidden
+  float* rowpart = hid + (size_t)B * Hd * L;  // [B, C, ceil(L / 64)] partial gate sums (deterministic mean over L)
   cudaStream_t st = ST(stream);
 
   duan_row_stats_kernel<<<(unsigned)BC, 256, 0, st>>>(x, c, mean_x, m2_x, mean_c, L);
   LX_CUDA(cudaGetLastError());
   // gate: g_mix = mean_L sigmoid(W2 relu(W1 c + b1) + b2)
-  LX_CUDA(cudaMemsetAsync(g_mix, 0, BC * sizeof(float), st));
   lx_sgemm_desc_t g;
   memset(&g, 0, sizeof(g));
   g.A = w->gate_w1; g.lda = Cc; g.Bm = c; g.ldb = L; g.b_bstride = (int64_t)Cc * L; g.bias = w->gate_b1;
@@ -674,7 +863,7 @@ extern "C" int lx_duan_forward(const lx_duan_weights_t* w, const float* x, const
   if (rc) return rc;
   memset(&g, 0, sizeof(g));
   g.A = w->gate_w2; g.lda = Hd; g.Bm = hid; g.ldb = L; g.b_bstride = (int64_t)Hd * L; g.bias = w->gate_b2;
-  g.rowmean = g_mix; g.M = Cc; g.N = L; g.K = Hd; g.batch = B; g.act = 2;
+  g.rowmean = g_mix; g.rowpart = rowpart; g.M = Cc; g.N = L; g.K = Hd; g.batch = B; g.act = 2;
   rc = lx_sgemm_f32(&g, stream);
   if (rc) return rc;
   // FiLM: [gamma, beta] = W4 relu(W3 mean_L(c) + b3) + b4     (N = 1 "GEMMs")

@@ -94,6 +94,10 @@ long long* timeline_next(int cls);
 // the marginal cost of a kernel inside the real loop, with the buffers keeping their last realistic contents)
 int debug_skip_mask();
 
+// radix-2 FFT of d channels of L (power of two) values (cs3_dgf.cu): S4 kernel generation and its backward
+int s4_fft_launch(bool inverse, const double2* in_c, const float* in_r, double2* out_c, float* out_r, int d, int L,
+                  void* stream);
+
 struct LaunchScope {
   LaunchScope(int cls, void* stream, double work);  // work: FLOPs (tensor kernels) or bytes (HBM-bound kernels)
   ~LaunchScope();

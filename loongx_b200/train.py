@@ -327,77 +327,116 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def _hand_out(tr, flat, enc):
+    """Slices of the (all-reduced) flat bucket, in the order the parameters were passed to the autograd node."""
+    grads, o = [], 0
+    for f in tr.factors.values():
+        grads.append(flat[o:o + f.A.numel()].view_as(f.A))
+        o += f.A.numel()
+        grads.append(flat[o:o + f.B.numel()].view_as(f.B))
+        o += f.B.numel()
+    if enc is not None:
+        grads += enc.parameter_grads(flat[tr.n_lora_grad:])
+    return grads
+
+
+class EncoderBackward:
+    """The CS3 / DGF half of a training step: the conditioning context of this step, the encoder parameters and their
+    gradient views inside the trainer's flat bucket (after the LoRA factors)."""
+
+    def __init__(self, model, ctx, params, trainer):
+        from . import cs3_bwd as CB
+
+        self.CB, self.model, self.ctx, self.params = CB, model, ctx, list(params)
+        assert trainer.grad_extra.numel() >= CB.grad_elements(self.params)
+        self.views = CB.grad_views(self.params, trainer.grad_extra)
+
+    def backward(self, d_prompt: torch.Tensor, d_pooled: torch.Tensor) -> None:
+        self.CB.step_conditioning_backward(self.model, self.ctx, d_prompt.contiguous(), d_pooled.contiguous(), self.views)
+
+    def parameter_grads(self, flat_extra: torch.Tensor):
+        out = []
+        for p, (o, n) in zip(self.params, self.CB.grad_layout(self.params)[0]):
+            sl = flat_extra[o:o + n]
+            out.append(torch.view_as_complex(sl.view(*p.shape, 2)) if p.is_complex() else sl.view_as(p))
+        return out
+
+
 class FlowStepFunction(torch.autograd.Function):
     """loss = step(batch) as an autograd node: `loss.backward()` (what Lightning calls on the reference's step output)
-    runs the native backward, all-reduces the flat gradient bucket across ranks and hands every LoRA factor its slice."""
+    runs the native backward (DiT, then - with `enc` - the CS3 / DGF conditioning), all-reduces the ONE flat gradient bucket
+    across ranks and hands every LoRA factor and every encoder parameter its slice."""
 
     @staticmethod
-    def forward(ctx, trainer, inputs, *params):
+    def forward(ctx, trainer, inputs, enc, *params):
         loss = trainer.forward(*inputs)
-        ctx.trainer = trainer
+        ctx.trainer, ctx.enc = trainer, enc
         return loss.clone().reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        tr = ctx.trainer
+        tr, enc = ctx.trainer, ctx.enc
         tr.zero_grad()
         tr.backward(float(grad_out))
+        if enc is not None:
+            enc.backward(tr.d_prompt, tr.d_pooled)
         allreduce_mean_(tr.grad_flat)
         # hand autograd a private copy: the trainer re-zeroes its bucket on the next backward, while `.grad` must keep
         # accumulating across micro-batches (accumulate_grad_batches: 4 in train/config/seed_512.yaml:12)
         flat = tr.grad_flat.clone()
-        grads, o = [], 0
-        for f in tr.factors.values():
-            grads.append(flat[o:o + f.A.numel()].view_as(f.A))
-            o += f.A.numel()
-            grads.append(flat[o:o + f.B.numel()].view_as(f.B))
-            o += f.B.numel()
-        return (None, None, *grads)
+        return (None, None, None, *_hand_out(tr, flat, enc))
 
 
 class FlowStepMicroFunction(torch.autograd.Function):
     """A step over k micro-batches (gradient accumulation inside the step): every micro-batch runs forward + backward
     right away (its activations are dropped before the next one), the gradients accumulate in the trainer's flat bucket
-    and `loss.backward()` only all-reduces / scales / hands them out.  loss = mean of the micro-batch losses."""
+    and `loss.backward()` only all-reduces / scales / hands them out.  loss = mean of the micro-batch losses.  The
+    conditioning was computed for the whole batch: its backward runs once, on the concatenated input gradients."""
 
     @staticmethod
-    def forward(ctx, trainer, chunks, *params):
+    def forward(ctx, trainer, chunks, enc, *params):
         k = len(chunks)
         trainer.zero_grad()
         total = torch.zeros((), device=trainer.loss.device, dtype=torch.float32)
+        d_pe, d_po = [], []
         for inputs in chunks:
             total += trainer.forward(*inputs).reshape(())
             trainer.backward(1.0 / k)
-        ctx.trainer = trainer
+            if enc is not None:
+                d_pe.append(trainer.d_prompt.clone())
+                d_po.append(trainer.d_pooled.clone())
+        if enc is not None:
+            enc.backward(torch.cat(d_pe, 0), torch.cat(d_po, 0))
+        ctx.trainer, ctx.enc = trainer, enc
         return total / k
 
     @staticmethod
     def backward(ctx, grad_out):
-        tr = ctx.trainer
+        tr, enc = ctx.trainer, ctx.enc
         allreduce_mean_(tr.grad_flat)
         flat = tr.grad_flat * grad_out.to(tr.grad_flat.dtype)
-        grads, o = [], 0
-        for f in tr.factors.values():
-            grads.append(flat[o:o + f.A.numel()].view_as(f.A))
-            o += f.A.numel()
-            grads.append(flat[o:o + f.B.numel()].view_as(f.B))
-            o += f.B.numel()
-        return (None, None, *grads)
+        return (None, None, None, *_hand_out(tr, flat, enc))
 
 
 class DitTrainer:
     """Native forward + backward of the rectified-flow objective for one batch geometry."""
 
     def __init__(self, weights: DitWeights, B: int, n_txt: int, n_img: int, n_cond: int, model_config: Optional[dict] = None,
-                 attn_bwd: str = "native", recompute: Optional[bool] = None):
+                 attn_bwd: str = "native", recompute: Optional[bool] = None, input_grads: bool = False,
+                 extra_grad_elems: int = 0):
         """recompute: True = checkpoint the residual stream per block and rebuild the block's intermediates in the
         backward (the reference's gradient_checkpointing, train/config/seed_512.yaml:16); False = keep every block's
         intermediates from the forward (15.5 GB per 512x512 sample for FLUX.1-dev: no second forward, ~1.3x faster);
-        None = keep them when they fit in the free HBM, else recompute.  Same gradients either way."""
+        None = keep them when they fit in the free HBM, else recompute.  Same gradients either way.
+        input_grads: also produce d loss / d prompt_embeds and d loss / d pooled_projections (`self.d_prompt`, `self.d_pooled`
+        after backward()): what flows back into the CS3 / DGF conditioning of OminiModel.step (model.py:656-701).
+        extra_grad_elems: fp32 elements appended to the flat gradient bucket after the LoRA factors (`self.grad_extra`), so
+        that ONE all-reduce covers the encoder gradients as well."""
         model_config = model_config or {}
         assert attn_bwd in ("native", "library")
         self.attn_bwd = attn_bwd
         self.latent_lora = bool(model_config.get("latent_lora", False))
+        self.input_grads = bool(input_grads)
         if model_config.get("add_cond_attn", False):
             raise NotImplementedError("training with model_config.add_cond_attn=True (inference supports it)")
         if n_cond <= 0:
@@ -442,9 +481,14 @@ class DitTrainer:
         self.ckpt_mid = torch.zeros((max(cfg.num_layers, 1), R, D), **bf)  # residual stream after the attention branch
         self.dmod_dbl = torch.zeros((B, max(cfg.num_layers, 1) * 6 * D), device=dev, dtype=torch.float32)
         self.dmod_sgl = torch.zeros((B, max(cfg.num_single_layers, 1) * 3 * D), device=dev, dtype=torch.float32)
-        if self.latent_lora:  # modulation gradients of the image stream (double) / the shared text+image vector (single)
+        if self.latent_lora or self.input_grads:  # modulation gradients of the image stream (double) / the shared text+image vector (single)
             self.dmod_dbl_img = torch.zeros_like(self.dmod_dbl)
             self.dmod_sgl_ti = torch.zeros_like(self.dmod_sgl)
+        if self.input_grads:  # ... and of the text stream / the final AdaLayerNormContinuous: temb depends on `pooled`
+            self.dmod_dbl_txt = torch.zeros_like(self.dmod_dbl)
+            self.dmod_out = torch.zeros((B, 2 * D), device=dev, dtype=torch.float32)
+            self.d_prompt: Optional[torch.Tensor] = None
+            self.d_pooled: Optional[torch.Tensor] = None
         self.loss = torch.zeros((1,), device=dev, dtype=torch.float32)
         self.factors: Dict[str, LoraFactor] = {}
         shared = lora_shared(weights)
@@ -454,7 +498,9 @@ class DitTrainer:
             for (name, row0, rows, A, Bw) in panel.lora:
                 self.factors[name] = LoraFactor(name, panel, row0, rows, shared[name])
         n_grad = sum(f.A.numel() + f.B.numel() for f in self.factors.values())
-        self.grad_flat = torch.zeros((n_grad,), device=dev, dtype=torch.float32)
+        self.grad_flat = torch.zeros((n_grad + int(extra_grad_elems),), device=dev, dtype=torch.float32)
+        self.n_lora_grad = n_grad
+        self.grad_extra = self.grad_flat[n_grad:]
         o = 0
         for f in self.factors.values():
             f.dA = self.grad_flat[o:o + f.A.numel()].view_as(f.A)
@@ -467,7 +513,8 @@ class DitTrainer:
     # -- weights -----------------------------------------------------------------------------------------------------
     def _ensure_transposed(self):
         for key, p in self.w.named.items():
-            if not isinstance(p, PackedLinear) or not (key.startswith("double.") or key.startswith("single.") or key == "proj_out"):
+            if not isinstance(p, PackedLinear) or not (key.startswith("double.") or key.startswith("single.") or key == "proj_out" or
+                                                       (key == "context_embedder" and self.input_grads)):
                 continue
             if p.wT is None:
                 p.wT = transpose(p.w)
@@ -501,15 +548,15 @@ class DitTrainer:
     def zero_grad(self):
         self.grad_flat.zero_()
 
-    def step_loss_micro(self, chunks) -> torch.Tensor:
+    def step_loss_micro(self, chunks, enc: Optional["EncoderBackward"] = None) -> torch.Tensor:
         """`chunks`: list of input tuples (each of this trainer's batch size) -> differentiable mean loss."""
         self.remerge_if_stale()
-        return FlowStepMicroFunction.apply(self, chunks, *self.parameters())
+        return FlowStepMicroFunction.apply(self, chunks, enc, *self.parameters(), *(enc.params if enc is not None else ()))
 
-    def step_loss(self, *inputs) -> torch.Tensor:
+    def step_loss(self, *inputs, enc: Optional["EncoderBackward"] = None) -> torch.Tensor:
         """Differentiable loss (0-dim fp32): forward now, native backward when autograd reaches it."""
         self.remerge_if_stale()
-        return FlowStepFunction.apply(self, inputs, *self.parameters())
+        return FlowStepFunction.apply(self, inputs, enc, *self.parameters(), *(enc.params if enc is not None else ()))
 
     # -- per-block helpers ---------------------------------------------------------------------------------------------
     def _mods_double(self, i):
@@ -643,7 +690,9 @@ class DitTrainer:
         tm = b["tile_meta"]
         m = self._mods_double(i)
         c0 = self.Rt if self.latent_lora else self.Rt + self.Ri  # first row whose Linear carries LoRA
-        dm = lambda c: [None, self.dmod_dbl_img[:, (i * 6 + c) * D:(i * 6 + c + 1) * D] if self.latent_lora else None,  # noqa: E731
+        mg = self.latent_lora or self.input_grads
+        dm = lambda c: [self.dmod_dbl_txt[:, (i * 6 + c) * D:(i * 6 + c + 1) * D] if self.input_grads else None,  # noqa: E731
+                        self.dmod_dbl_img[:, (i * 6 + c) * D:(i * 6 + c + 1) * D] if mg else None,
                         self.dmod_dbl[:, (i * 6 + c) * D:(i * 6 + c + 1) * D]]
         pfx = f"transformer_blocks.{i}."
         pre, pre_ff = a["QM"][:, :3 * D], a["QM"][:, 3 * D:7 * D]
@@ -690,8 +739,9 @@ class DitTrainer:
         tm = b["tile_meta"]
         m = self._mods_single(i)
         c0 = 0 if self.latent_lora else self.Rt + self.Ri
-        dm = lambda c: ([self.dmod_sgl_ti[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]] * 2 if self.latent_lora else [None, None]) + \
-            [self.dmod_sgl[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]]  # noqa: E731
+        dm = lambda c: ([self.dmod_sgl_ti[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]] * 2  # noqa: E731
+                        if (self.latent_lora or self.input_grads) else [None, None]) + \
+            [self.dmod_sgl[:, (i * 3 + c) * D:(i * 3 + c + 1) * D]]
         pfx = f"single_transformer_blocks.{i}."
         gate_bwd(g["dX"], a["Y1"], g["dY"], tm, m[2], dm(2))
         self._lora_grads([pfx + "proj_out"], a["Cat"][c0:], g["dY"][c0:])
@@ -742,7 +792,8 @@ class DitTrainer:
         ops.gemm(XNi, po.w, po.bias, pred.view(self.Ri, cfg.in_channels), L.EPI_BIAS)
         if any(self.pads):  # padding image rows: make the residual exactly zero so they add nothing to loss / dpred
             pred[:, self.ni_valid:].zero_()
-        self._saved = dict(x0=x0, x1=x1, pred=pred, xt=xt, cond_latents=cond_latents, X_final=X.clone())
+        self._saved = dict(x0=x0, x1=x1, pred=pred, xt=xt, cond_latents=cond_latents, X_final=X.clone(),
+                           pooled=pooled.to(torch.bfloat16).contiguous())
         self.loss.zero_()
         flow_mse_loss(pred, x0, x1, self.loss, None)
         if any(self.pads):  # mean over the valid elements (the kernel divided by the padded count)
@@ -759,9 +810,12 @@ class DitTrainer:
         nl, ns = cfg.num_layers, cfg.num_single_layers
         self.dmod_dbl.zero_()
         self.dmod_sgl.zero_()
-        if self.latent_lora:
+        if self.latent_lora or self.input_grads:
             self.dmod_dbl_img.zero_()
             self.dmod_sgl_ti.zero_()
+        if self.input_grads:
+            self.dmod_dbl_txt.zero_()
+            self.dmod_out.zero_()
         dpred = torch.empty_like(s["pred"])
         scratch_loss = torch.zeros_like(self.loss)
         flow_mse_loss(s["pred"], s["x0"], s["x1"], scratch_loss, dpred, grad_scale * (self.ni / self.ni_valid))
@@ -772,8 +826,13 @@ class DitTrainer:
         ops.gemm(dpred.view(self.Ri, cfg.in_channels), po.wT, None, g["dXN"][sl], L.EPI_BIAS)
         mo = b["mod_out"]
         sc = mo[:, :self.D]
-        ln_modulate_bwd(s["X_final"][sl], g["dXN"][sl], None, g["dX"][sl], tm[self.Rt // 128:], [sc, sc, sc],
-                        [None] * 3, [None] * 3, None)
+        if self.input_grads:  # AdaLayerNormContinuous: scale first, then shift (transformer.py:243)
+            dsc, dsh = self.dmod_out[:, :self.D], self.dmod_out[:, self.D:]
+            ln_modulate_bwd(s["X_final"][sl], g["dXN"][sl], None, g["dX"][sl], tm[self.Rt // 128:], [sc, sc, sc],
+                            [None, dsc, None], [None, dsh, None], self.stats)
+        else:
+            ln_modulate_bwd(s["X_final"][sl], g["dXN"][sl], None, g["dX"][sl], tm[self.Rt // 128:], [sc, sc, sc],
+                            [None] * 3, [None] * 3, None)
         for i in reversed(range(ns)):
             if self.recompute:  # gradient checkpointing, transformer.py:184-206
                 X.copy_(self.ckpt[nl + i])
@@ -792,6 +851,8 @@ class DitTrainer:
         # AdaLN linears: emb -> [B, 6D | 3D] per block; input silu(cond_temb) for the condition stream, silu(temb) for the
         # image (double) / text+image (single) rows when latent_lora keeps their adapters active
         silu_c, silu_t = b["silu_c"], b["silu_t"]
+        if self.input_grads:
+            self._input_grads(s)
         pairs = [(silu_c, cast_bf16(self.dmod_dbl), cast_bf16(self.dmod_sgl))]
         if self.latent_lora:
             pairs.append((silu_t, cast_bf16(self.dmod_dbl_img), cast_bf16(self.dmod_sgl_ti)))
@@ -801,6 +862,61 @@ class DitTrainer:
             for i in range(ns):
                 self._lora_grads([f"single_transformer_blocks.{i}.norm.linear"], x_in,
                                  dms[:, i * 3 * self.D:(i + 1) * 3 * self.D])
+
+    def _input_grads(self, s) -> None:
+        """d loss / d prompt_embeds (through context_embedder, transformer.py:115) and d loss / d pooled_projections
+        (through time_text_embed's text branch into temb and cond_temb, then every AdaLN Linear: transformer.py:102-114,
+        block.py:192-207, 238-253, 301-305).  fp32 results in self.d_prompt [B, n_txt, joint_dim], self.d_pooled [B, pooled_dim]."""
+        from . import cs3_bwd as CB
+
+        b, g, cfg, W = self.plan.buf, self.g, self.cfg, self.w.named
+        B, D, dev = self.B, self.D, b["X"].device
+        assert B <= 8, "input gradients: micro-batches of at most 8 samples (skinny kernels)"
+        # text tokens: X0_txt = prompt_embeds W_ctx^T + b
+        ce = W["context_embedder"]
+        d_pe = torch.empty((self.Rt, cfg.joint_attention_dim), device=dev, dtype=torch.float32)
+        ops.gemm(g["dX"][:self.Rt], ce.wT, None, d_pe, L.EPI_BIAS_F32)
+        self.d_prompt = d_pe.view(B, self.nt, cfg.joint_attention_dim)[:, :self.plan.nt]
+        # conditioning vectors: d silu(temb) (rows of step 0 .. B-1) and d silu(cond_temb)
+        d_silu = torch.zeros((2 * B, D), device=dev, dtype=torch.float32)
+        d_t, d_c = d_silu[:B], d_silu[B:]
+        ll = self.latent_lora
+
+        def skinny(dm, panel, lora, out):
+            w = panel.w_lora if (lora and panel.w_lora is not None) else panel.w
+            L.check(CB._lib.lx_skinny_xw_bf16(dm.data_ptr(), dm.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), B,
+                                              w.shape[0], w.shape[1], _stream()), "lx_skinny_xw_bf16")
+
+        skinny(self.dmod_dbl_txt, W["mod_txt"], False, d_t)
+        skinny(self.dmod_dbl_img, W["mod_img"], ll, d_t)
+        skinny(self.dmod_sgl_ti, W["mod_single"], ll, d_t)
+        skinny(self.dmod_out, W["norm_out"], False, d_t)
+        skinny(self.dmod_dbl, W["mod_img"], True, d_c)
+        skinny(self.dmod_sgl, W["mod_single"], True, d_c)
+        # silu: temb = e_t + e_g + e_x (rows [0, B) of step 0; the cond rows follow at M - B)
+        emb = b["emb_tmp"]  # [4, M, D]: hidden, e_t, e_g, e_x
+        M = emb.shape[1]
+        assert M == 2 * B, "training plans have T = 1"
+        d_pre = torch.empty_like(d_silu)
+        e_g = emb[2] if cfg.guidance_embeds else None
+        L.check(CB._lib.lx_silu_bwd_sum(d_silu.data_ptr(), emb[1].data_ptr(), e_g.data_ptr() if e_g is not None else None,
+                                        emb[3].data_ptr(), B, d_pre.data_ptr(), M, D, _stream()), "lx_silu_bwd_sum")
+        d_ex = torch.zeros((B, D), device=dev, dtype=torch.float32)
+        CB._axpy(d_ex, d_pre[:B].contiguous())
+        CB._axpy(d_ex, d_pre[B:].contiguous())
+        # text branch: e_x = W2 silu(W1 pooled + b1) + b2
+        t1, t2 = W["text_1"], W["text_2"]
+        d_h = torch.zeros((B, D), device=dev, dtype=torch.float32)
+        L.check(CB._lib.lx_skinny_xw_bf16(d_ex.data_ptr(), D, t2.w.data_ptr(), t2.w.stride(0), d_h.data_ptr(), D, B, t2.w.shape[0],
+                                          t2.w.shape[1], _stream()), "lx_skinny_xw_bf16")
+        h_pre = torch.empty((B, D), device=dev, dtype=torch.float32)
+        ops.gemm(s["pooled"], t1.w, t1.bias, h_pre, L.EPI_BIAS_F32)
+        d_h1 = torch.empty_like(d_h)
+        L.check(CB._lib.lx_silu_bwd_f32(d_h.data_ptr(), h_pre.data_ptr(), d_h1.data_ptr(), d_h.numel(), _stream()), "lx_silu_bwd_f32")
+        d_po = torch.zeros((B, t1.w.shape[1]), device=dev, dtype=torch.float32)
+        L.check(CB._lib.lx_skinny_xw_bf16(d_h1.data_ptr(), D, t1.w.data_ptr(), t1.w.stride(0), d_po.data_ptr(), d_po.stride(0), B,
+                                          t1.w.shape[0], t1.w.shape[1], _stream()), "lx_skinny_xw_bf16")
+        self.d_pooled = d_po
 
     def grads(self) -> Dict[str, torch.Tensor]:
         out = {}

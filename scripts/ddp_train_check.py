@@ -18,26 +18,40 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-cfg = FluxConfig(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
-m = OminiModel(cfg, lora_config={"r": 4, "lora_alpha": 4}, device=str(dev), model_config={}, use_brain_condition=False, seed=7)
+BRAIN = bool(os.environ.get("LX_DDP_BRAIN"))  # with the CS3 / DGF conditioning: the bucket carries the encoder gradients too
+jd, pd, nt = (4096, 768, 512) if BRAIN else (256, 64, 128)
+cfg = FluxConfig(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=jd, pooled_projection_dim=pd)
+m = OminiModel(cfg, lora_config={"r": 4, "lora_alpha": 4}, device=str(dev), model_config={}, use_brain_condition=BRAIN, seed=7)
 g = torch.Generator().manual_seed(100 + rank)  # a different batch on every rank
 B, h, w = 2, 16, 32
 r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16().to(dev)  # noqa: E731
-batch = dict(image=r(B, 16, h, w), condition=r(B, 16, h, w), prompt_embeds=r(B, 128, 256, scale=0.5),
-             pooled_prompt_embeds=r(B, 64), position_delta=[[0, -16]], condition_type=["subject"] * B,
+batch = dict(image=r(B, 16, h, w), condition=r(B, 16, h, w), prompt_embeds=r(B, nt, jd, scale=0.5),
+             pooled_prompt_embeds=r(B, pd), position_delta=[[0, -16]], condition_type=["subject"] * B,
              t=torch.tensor([0.3, 0.7]), noise=r(B, 128, 64))
+if BRAIN:
+    batch.update(eeg=r(B, 4, 5000).float(), fnirs=r(B, 6, 600).float(), ppg=r(B, 4, 256).float(), motion=r(B, 6, 100).float())
 loss = m.step(batch)
 tr = m._trainer_obj
 # rank-local gradients, no collective
 tr.zero_grad()
 tr.backward(1.0)
+if BRAIN:
+    from loongx_b200 import cs3_bwd as CB
+    from loongx_b200.train import EncoderBackward
+
+    EncoderBackward(m, loss.grad_fn.enc.ctx, CB.trainable_parameters(m), tr).backward(tr.d_prompt, tr.d_pooled)
 local_grad = tr.grad_flat.clone()
 gathered = [torch.zeros_like(local_grad) for _ in range(world)]
 dist.all_gather(gathered, local_grad)
 mean = torch.stack(gathered).mean(0)
 # the product path: autograd node -> native backward -> ONE all-reduce(mean) of the flat bucket
 loss.backward()
-got = torch.cat([p.grad.flatten() for p in tr.parameters()])
+if BRAIN:
+    got = torch.cat([p.grad.flatten() for p in tr.parameters()] +
+                    [(torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).flatten() if p.grad is not None
+                     else torch.zeros(p.numel() * (2 if p.is_complex() else 1), device=dev) for p in CB.trainable_parameters(m)])
+else:
+    got = torch.cat([p.grad.flatten() for p in tr.parameters()])
 err = ((got - mean).norm() / mean.norm()).item()
 all_got = [torch.zeros_like(got) for _ in range(world)]
 dist.all_gather(all_got, got)

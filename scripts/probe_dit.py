@@ -57,3 +57,16 @@ for s in range(T):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / T
 print(f"B={B} res={res}: {ms:.2f} ms/step  {flop/ms/1e9:.1f} TFLOP/s (algorithmic)  host wall {(time.time()-t0)/T*1e3:.2f} ms/step")
+# marginal cost of a kernel class inside the real loop (lx_debug_skip: the launcher returns early, buffers keep their last
+# realistic contents so the data-dependent power draw of the other kernels does not change)
+if os.environ.get("LX_MARGINAL"):
+    for name, mask in (("ln_modulate", 4), ("attention", 2)):
+        _L.lib.lx_debug_skip(mask)
+        for s in range(min(2, T)):
+            plan.step(s, lat, out)
+        e0.record()
+        for s in range(T):
+            plan.step(s, lat, out)
+        e1.record(); torch.cuda.synchronize()
+        print(f"  without {name}: {e0.elapsed_time(e1) / T:.2f} ms/step  (marginal cost {ms - e0.elapsed_time(e1) / T:.2f} ms/step)")
+    _L.lib.lx_debug_skip(0)

@@ -280,12 +280,23 @@ class OminiModel(nn.Module):
     def _trainer(self, B, n_txt, n_img, n_cond):
         from loongx_b200.train import DitTrainer
 
-        key = (B, n_txt, n_img, n_cond, id(self.transformer.weights))
+        enc = self._wants_encoder_grads()
+        key = (B, n_txt, n_img, n_cond, id(self.transformer.weights), enc)
         if getattr(self, "_trainer_key", None) != key:
+            from loongx_b200 import cs3_bwd as CB
+
             self._trainer_obj = None  # free the old trainer's activations before building the new one
-            self._trainer_obj = DitTrainer(self.transformer.weights, B, n_txt, n_img, n_cond, model_config=self.model_config)
+            extra = CB.grad_elements(CB.trainable_parameters(self)) if enc else 0
+            self._trainer_obj = DitTrainer(self.transformer.weights, B, n_txt, n_img, n_cond, model_config=self.model_config,
+                                           input_grads=enc, extra_grad_elems=extra)
             self._trainer_key = key
         return self._trainer_obj
+
+    def _wants_encoder_grads(self) -> bool:
+        """The reference's step() leaves gradients on every CS3 / DGF parameter (they are inside the autograd graph,
+        model.py:656-701) and DDP all-reduces them with the LoRA factors; `self.encoder_grads = False` skips that half (the
+        reference's optimizer never updates those parameters, model.py:541)."""
+        return bool(self.use_brain_condition and getattr(self, "encoder_grads", True))
 
     def _micro_batch(self, B: int, S: int) -> int:
         """Samples per native forward/backward: the whole batch when its block activations fit in the free HBM (no
@@ -399,19 +410,35 @@ class OminiModel(nn.Module):
                 scale_bias = (position_scale - 1.0) / 2
                 condition_ids[:, 1:] *= position_scale
                 condition_ids[:, 1:] += scale_bias
-            if self.use_brain_condition:
+            cond_ctx = None
+            if self.use_brain_condition and self._wants_encoder_grads():
+                from loongx_b200 import cs3_bwd as CB
+
+                self._step_count = getattr(self, "_step_count", 0) + 1
+                pe, po, cond_ctx = CB.step_conditioning_train(self, pe, po, batch.get("eeg"), batch.get("fnirs"),
+                                                              batch.get("ppg"), batch.get("motion"), training=self.training,
+                                                              seed=1000003 * int(batch.get("dropout_seed", 0)) + self._step_count)
+            elif self.use_brain_condition:
                 pe, po = self._step_conditioning(pe, po, batch.get("eeg"), batch.get("fnirs"), batch.get("ppg"),
                                                  batch.get("motion"))
             text_ids = torch.zeros(pe.shape[1], 3, device=dev)
         mb = self._micro_batch(B, pe.shape[1] + x_0.shape[1] + condition_latents.shape[1])
+        if cond_ctx is not None:
+            mb = min(mb, max(d for d in range(1, 9) if B % d == 0))  # input-gradient kernels take <= 8 samples per pass
         tr = self._trainer(mb, pe.shape[1], x_0.shape[1], condition_latents.shape[1])
+        enc = None
+        if cond_ctx is not None:
+            from loongx_b200 import cs3_bwd as CB
+            from loongx_b200.train import EncoderBackward
+
+            enc = EncoderBackward(self, cond_ctx, CB.trainable_parameters(self), tr)
         if mb == B:
             loss = tr.step_loss(x_0.contiguous(), x_1.contiguous(), t, condition_latents, pe, po, text_ids, img_ids.float(),
-                                condition_ids, 1.0)
+                                condition_ids, 1.0, enc=enc)
         else:  # gradient accumulation over micro-batches whose activations fit in HBM without recompute
             chunks = [(x_0[i:i + mb].contiguous(), x_1[i:i + mb].contiguous(), t[i:i + mb], condition_latents[i:i + mb],
                        pe[i:i + mb], po[i:i + mb], text_ids, img_ids.float(), condition_ids, 1.0) for i in range(0, B, mb)]
-            loss = tr.step_loss_micro(chunks)
+            loss = tr.step_loss_micro(chunks, enc=enc)
         self.last_t = float(t.mean())
         return loss
 

@@ -71,6 +71,31 @@ def _grad_worker(rank, world, port, q):
     gathered = [torch.zeros(1000) for _ in range(world)]
     dist.all_gather(gathered, flat)
     same = torch.equal(gathered[0], gathered[1])  # replicas stay identical after the step
+    # the bucket layout of a step with CS3 / DGF gradients: [LoRA factors | encoder parameters (complex ones as float
+    # pairs)]; ONE all-reduce covers both halves and every parameter receives its slice of the reduced bucket
+    import types
+
+    from loongx_b200 import cs3_bwd as CB
+    from loongx_b200.train import EncoderBackward, _hand_out
+
+    fA, fB = torch.nn.Parameter(torch.zeros(4, 50)), torch.nn.Parameter(torch.zeros(100, 4))
+    enc_params = [torch.nn.Parameter(torch.zeros(3, 7)), torch.nn.Parameter(torch.zeros(5, 6, dtype=torch.complex64)),
+                  torch.nn.Parameter(torch.zeros(11))]
+    n_lora, n_enc = 600, CB.grad_elements(enc_params)
+    bucket = torch.randn(n_lora + n_enc, generator=torch.Generator().manual_seed(200 + rank))
+    tr = types.SimpleNamespace(factors={"m": types.SimpleNamespace(A=fA, B=fB)}, n_lora_grad=n_lora, grad_flat=bucket,
+                               grad_extra=bucket[n_lora:])
+    enc = EncoderBackward(model=None, ctx=None, params=enc_params, trainer=tr)
+    assert n_enc == 24 + 60 + 12 and sum(v.numel() for v in enc.views.values()) == 21 + 60 + 11  # 16-byte aligned slices
+    allreduce_mean_(tr.grad_flat)
+    both = [torch.randn(n_lora + n_enc, generator=torch.Generator().manual_seed(200 + r)) for r in range(world)]
+    want = (both[0] + both[1]) / 2
+    got = _hand_out(tr, tr.grad_flat, enc)
+    flat_again = torch.cat([(torch.view_as_real(t) if t.is_complex() else t).reshape(-1) for t in got])
+    lay = CB.grad_layout(enc_params)[0]
+    want = torch.cat([want[:n_lora]] + [want[n_lora + o:n_lora + o + n] for o, n in lay])
+    ok = ok and torch.allclose(flat_again, want, atol=1e-6) and [tuple(t.shape) for t in got] == [(4, 50), (100, 4), (3, 7), (5, 6), (11,)] \
+        and got[3].is_complex()
     if rank == 0:
         q.put((bool(ok), bool(same)))
     dist.barrier()
