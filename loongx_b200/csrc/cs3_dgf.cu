@@ -147,11 +147,14 @@ __global__ void __launch_bounds__(512) s4_fft_kernel(const double2* __restrict__
 // ------------------------------------------------------------------------------------------------ S4 convolution
 // y[b,c,l] = act( sum_{j<=l} K[c,j] u[b,c,l-j] + D[c] u[b,c,l] ), act = GELU(erf) or identity, optional pre-activation
 // output, optional time reversal of u and y (the adjoint of a causal convolution is the causal convolution of the reversed
-// sequence: used by the backward).  One CTA = 1024 consecutive outputs of one (b, c): each of the 128 threads owns EIGHT
+// sequence: used by the backward).  One CTA = 256 consecutive outputs of one (b, c), four warps: every lane owns EIGHT
 // consecutive outputs and slides an 8-value register window over the input, so one shared-memory read of u and one
-// (broadcast) read of K feed eight FMAs (the first version did one FMA per two shared-memory reads).  The u window is
-// stored with a one-word skew per 32 words, which makes the stride-8 window reads conflict-free.
-constexpr int CONV_T = 128, CONV_R = 8, CONV_OUT = CONV_T * CONV_R;
+// (broadcast) read of K feed eight FMAs; the four warps split the 512 taps of a staging round and their partial sums are
+// added in a fixed order at the end (bit-reproducible).  The u window is stored with a one-word skew per 32 words, which
+// makes the stride-8 window reads conflict-free.  (History, L = 4096: one output per thread, one FMA per two shared reads:
+// 84 us for 64 channels; 1024 outputs per CTA with the register window: 94 us, bound by the single longest CTA - also
+// 66 us for FOUR channels; this form spreads the longest tap range over 4x more warps.)
+constexpr int CONV_T = 128, CONV_R = 8, CONV_OUT = 32 * CONV_R, CONV_J = 512, CONV_JW = CONV_J / 4;
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ int conv_skew(int i) { return i + (i >> 5); }
 
@@ -159,12 +162,13 @@ template <bool kReverse, bool kGelu>
 __global__ void __launch_bounds__(CONV_T) s4_conv_kernel(const float* __restrict__ u, const float* __restrict__ K,
                                                          const float* __restrict__ Dp, float* __restrict__ y,
                                                          float* __restrict__ pre, int d, int L) {
-  constexpr int WIN = CONV_OUT + CONV_T;  // u[base .. base + WIN), base = l0 - j0 - 127 (one slot more than needed)
-  __shared__ float sK[CONV_T];
+  constexpr int WIN = CONV_OUT + CONV_J;  // u[base .. base + WIN), base = l0 - j0 - (CONV_J - 1) (one slot more than needed)
+  __shared__ float sK[CONV_J];
   __shared__ float sU[WIN + WIN / 32 + 1];
+  __shared__ float sAcc[3][CONV_OUT];
   const int c = blockIdx.y, b = blockIdx.z;
-  const int l0 = blockIdx.x * CONV_OUT;
-  const int t = threadIdx.x;
+  const int l0 = (gridDim.x - 1 - blockIdx.x) * CONV_OUT;  // the CTAs with the longest tap range are scheduled first
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
   const float* ub = u + ((size_t)b * d + c) * L;
   const float* Kc = K + (size_t)c * L;
   auto ld_u = [&](int i) -> float { return (i >= 0 && i < L) ? ub[kReverse ? L - 1 - i : i] : 0.f; };
@@ -172,34 +176,46 @@ __global__ void __launch_bounds__(CONV_T) s4_conv_kernel(const float* __restrict
 #pragma unroll
   for (int r = 0; r < CONV_R; ++r) acc[r] = 0.f;
   const int l_hi = min(L, l0 + CONV_OUT) - 1;  // last output of this CTA
-  for (int j0 = 0; j0 <= l_hi; j0 += CONV_T) {
+  for (int j0 = 0; j0 <= l_hi; j0 += CONV_J) {
     __syncthreads();
-    sK[t] = (j0 + t < L) ? Kc[j0 + t] : 0.f;
-    const int base = l0 - j0 - (CONV_T - 1);
-    for (int i = t; i < WIN; i += CONV_T) sU[conv_skew(i)] = ld_u(base + i);
+    for (int i = threadIdx.x; i < CONV_J; i += CONV_T) sK[i] = (j0 + i < L) ? Kc[j0 + i] : 0.f;
+    const int base = l0 - j0 - (CONV_J - 1);
+    for (int i = threadIdx.x; i < WIN; i += CONV_T) sU[conv_skew(i)] = ld_u(base + i);
     __syncthreads();
-    // output l_r = l0 + 8 t + r, tap j0 + jj: u[l_r - j0 - jj] = window[8 t + r + 127 - jj]
+    // output l_r = l0 + 8 lane + r, tap j0 + jj: u[l_r - j0 - jj] = window[8 lane + r + (CONV_J - 1) - jj];
+    // warp q takes the taps jj in [128 q, 128 q + 128)
+    const int jb = q * CONV_JW;
+    if (j0 + jb > l_hi) continue;  // (warp-uniform) only zero padding beyond the last output's index
     float w[CONV_R];
 #pragma unroll
-    for (int r = 0; r < CONV_R; ++r) w[r] = sU[conv_skew(CONV_R * t + r + CONV_T - 1)];
+    for (int r = 0; r < CONV_R; ++r) w[r] = sU[conv_skew(CONV_R * lane + r + CONV_J - 1 - jb)];
 #pragma unroll 8
-    for (int jj = 0; jj < CONV_T; ++jj) {
-      const float kv = sK[jj];
+    for (int jj = 0; jj < CONV_JW; ++jj) {
+      const float kv = sK[jb + jj];
 #pragma unroll
       for (int r = 0; r < CONV_R; ++r) acc[r] = fmaf(kv, w[r], acc[r]);
 #pragma unroll
       for (int r = CONV_R - 1; r > 0; --r) w[r] = w[r - 1];
-      w[0] = sU[conv_skew(CONV_R * t + CONV_T - 2 - jj + (jj == CONV_T - 1 ? 1 : 0))];  // (last value unused)
+      w[0] = sU[conv_skew(max(CONV_R * lane + CONV_J - 2 - jb - jj, 0))];  // (the value loaded on the very last tap is unused)
     }
   }
+  __syncthreads();
+  if (q > 0) {
 #pragma unroll
-  for (int r = 0; r < CONV_R; ++r) {
-    const int l = l0 + CONV_R * t + r;
-    if (l < L) {
-      const float sv = acc[r] + (Dp ? Dp[c] * ld_u(l) : 0.f);
-      const size_t o = ((size_t)b * d + c) * L + (kReverse ? L - 1 - l : l);
-      if (pre != nullptr) pre[o] = sv;
-      y[o] = kGelu ? gelu_erf(sv) : sv;
+    for (int r = 0; r < CONV_R; ++r) sAcc[q - 1][CONV_R * lane + r] = acc[r];
+  }
+  __syncthreads();
+  if (q == 0) {
+#pragma unroll
+    for (int r = 0; r < CONV_R; ++r) {
+      const int l = l0 + CONV_R * lane + r;
+      if (l < L) {
+        const float tot = ((acc[r] + sAcc[0][CONV_R * lane + r]) + sAcc[1][CONV_R * lane + r]) + sAcc[2][CONV_R * lane + r];
+        const float sv = tot + (Dp ? Dp[c] * ld_u(l) : 0.f);
+        const size_t o = ((size_t)b * d + c) * L + (kReverse ? L - 1 - l : l);
+        if (pre != nullptr) pre[o] = sv;
+        y[o] = kGelu ? gelu_erf(sv) : sv;
+      }
     }
   }
 }
@@ -287,6 +303,20 @@ __global__ void adaptive_pool_kernel(const float* __restrict__ in, float* __rest
   float acc = 0.f;
   for (int l = s; l < e; ++l) acc += x[l];
   out[(size_t)b * out_bstride + (size_t)c * cs + (size_t)i * is + off] = acc / (float)(e - s);
+}
+// long bins (O << L, e.g. the 4 bins of 1024 samples over the S4 output, model.py:83-87): one warp per bin, coalesced
+__global__ void __launch_bounds__(128) adaptive_pool_warp_kernel(const float* __restrict__ in, float* __restrict__ out, int Cc,
+                                                                 int L, int O, int64_t out_bstride, int cs, int is, int off) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (i >= O) return;
+  const int s = (int)(((int64_t)i * L) / O);
+  const int e = (int)((((int64_t)(i + 1)) * L + O - 1) / O);
+  const float* x = in + ((size_t)b * Cc + c) * L;
+  float acc = 0.f;
+  for (int l = s + (threadIdx.x & 31); l < e; l += 32) acc += x[l];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) out[(size_t)b * out_bstride + (size_t)c * cs + (size_t)i * is + off] = acc / (float)(e - s);
 }
 
 // Several pooling sizes of the same input in one launch (FeaturePyramidPooling: concat over `n` output sizes, model.py:
@@ -763,8 +793,12 @@ extern "C" int lx_adaptive_pool(const float* in, float* out, int32_t B, int32_t 
                                 int64_t out_bstride, int32_t cs, int32_t is, int32_t off, void* stream) {
   LaunchScope scope(KC_CS3DGF, stream, 4.0 * B * C * ((double)L + O));  // algorithmic bytes
   LX_CHECK_ARG(in && out && B > 0 && C > 0 && L > 0 && O > 0, "lx_adaptive_pool: bad arguments");
-  dim3 grid((O + 127) / 128, C, B);
-  adaptive_pool_kernel<<<grid, 128, 0, ST(stream)>>>(in, out, C, L, O, out_bstride, cs, is, off);
+  if (L >= 64 * O) {  // (sums in a different order than the thread-per-bin form: both are plain fp32 sums of the bin)
+    adaptive_pool_warp_kernel<<<dim3((O + 3) / 4, C, B), 128, 0, ST(stream)>>>(in, out, C, L, O, out_bstride, cs, is, off);
+  } else {
+    dim3 grid((O + 127) / 128, C, B);
+    adaptive_pool_kernel<<<grid, 128, 0, ST(stream)>>>(in, out, C, L, O, out_bstride, cs, is, off);
+  }
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

@@ -27,6 +27,7 @@ struct SgemmEx {
   int64_t lda, ldb, ldc, a_bs, b_bs, c_bs;
   int M, N, K, batch;
   int trans_a, trans_b, reduce_batch;
+  int ksplit;  // reduce mode: grid.z = batch * ksplit CTAs add their (batch element, K range) partial into C with fp32 atomics
   float alpha, beta;
 };
 
@@ -38,21 +39,24 @@ __global__ void __launch_bounds__(256) sgemm_ex_kernel(const SgemmEx p) {
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4] = {};
-  const int b_lo = p.reduce_batch ? 0 : blockIdx.z, b_hi = p.reduce_batch ? p.batch : blockIdx.z + 1;
-  for (int b = b_lo; b < b_hi; ++b) {
+  // reduce mode: CTA z = (batch element, K slice); the slices are multiples of 16
+  const int b = p.reduce_batch ? blockIdx.z / p.ksplit : blockIdx.z;
+  const int kper = p.reduce_batch ? ((p.K + p.ksplit * 16 - 1) / (p.ksplit * 16)) * 16 : p.K;
+  const int k_lo = p.reduce_batch ? (blockIdx.z % p.ksplit) * kper : 0, k_hi = min(p.K, k_lo + kper);
+  {
     const float* Ab = p.A + (size_t)b * p.a_bs;
     const float* Bb = p.Bm + (size_t)b * p.b_bs;
-    for (int k0 = 0; k0 < p.K; k0 += 16) {
+    for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
       for (int i = threadIdx.x; i < 64 * 16; i += 256) {
         int m, k;
         if (p.trans_a) { k = i >> 6; m = i & 63; } else { m = i >> 4; k = i & 15; }
-        const bool ok = m0 + m < p.M && k0 + k < p.K;
+        const bool ok = m0 + m < p.M && k0 + k < k_hi;
         sA[k][m] = ok ? (p.trans_a ? Ab[(size_t)(k0 + k) * p.lda + m0 + m] : Ab[(size_t)(m0 + m) * p.lda + k0 + k]) : 0.f;
       }
       for (int i = threadIdx.x; i < 16 * 64; i += 256) {
         int n, k;
         if (p.trans_b) { n = i >> 4; k = i & 15; } else { k = i >> 6; n = i & 63; }
-        const bool ok = k0 + k < p.K && n0 + n < p.N;
+        const bool ok = k0 + k < k_hi && n0 + n < p.N;
         sB[k][n] = ok ? (p.trans_b ? Bb[(size_t)(n0 + n) * p.ldb + k0 + k] : Bb[(size_t)(k0 + k) * p.ldb + n0 + n]) : 0.f;
       }
       __syncthreads();
@@ -80,7 +84,8 @@ __global__ void __launch_bounds__(256) sgemm_ex_kernel(const SgemmEx p) {
       const int n = n0 + tx * 4 + j;
       if (m < p.M && n < p.N) {
         float* c = Cb + (size_t)m * p.ldc + n;
-        *c = p.alpha * acc[i][j] + (p.beta != 0.f ? p.beta * *c : 0.f);
+        if (p.reduce_batch) atomicAdd(c, p.alpha * acc[i][j]);  // beta == 1 (checked by the launcher): C accumulates
+        else *c = p.alpha * acc[i][j] + (p.beta != 0.f ? p.beta * *c : 0.f);
       }
     }
   }
@@ -454,21 +459,22 @@ __global__ void s4_cauchy_bwd_kernel(const float2* __restrict__ lam, const float
 }
 
 // per (c, n): sum over the roots.  dB[c,n] += conj(a0) S00 + conj(a1) S10;  dCt[c,n] += conj( conj(b) S00 + conj(p) S01 )
-// with S.. = sum_l conj(inv_n(l)) G_k..(l), plus the w = -1 root.  Gradients are complex64 (float2), accumulated.
-__global__ void s4_param_grad_kernel(const float2* __restrict__ lam, const float2* __restrict__ p, const float2* __restrict__ q,
-                                     const float2* __restrict__ Bm, const float2* __restrict__ Ct,
-                                     const float* __restrict__ log_step, const double2* __restrict__ G,
-                                     const double2* __restrict__ Gk, float2* __restrict__ dB, float2* __restrict__ dCt, int d,
-                                     int n, int L) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y;
-  if (j >= n) return;
+// with S.. = sum_l conj(inv_n(l)) G_k..(l), plus the w = -1 root.  One CTA per (n, c): 128 threads stride over l, fixed-order
+// block reduction of the three complex sums.  Gradients are complex64 (float2), accumulated.
+__global__ void __launch_bounds__(128) s4_param_grad_kernel(const float2* __restrict__ lam, const float2* __restrict__ p,
+                                                            const float2* __restrict__ q, const float2* __restrict__ Bm,
+                                                            const float2* __restrict__ Ct, const float* __restrict__ log_step,
+                                                            const double2* __restrict__ G, const double2* __restrict__ Gk,
+                                                            float2* __restrict__ dB, float2* __restrict__ dCt, int d, int n,
+                                                            int L) {
+  __shared__ double red[4][6];
+  const int j = blockIdx.x, c = blockIdx.y;
   const double step = exp((double)log_step[c]);
   const cdd lj = zf(lam[j]), pj = zf(p[j]), qj = zf(q[j]);
   const cdd ct = zf(Ct[c * n + j]), b = zf(Bm[c * n + j]);
   const cdd one = {1.0, 0.0};
   cdd S00 = {0, 0}, S01 = {0, 0}, S10 = {0, 0};
-  for (int l = 0; l < L; ++l) {
+  for (int l = threadIdx.x; l < L; l += 128) {
     if (2 * l == L) continue;
     double sn, cs;
     sincospi(-2.0 * (double)l / (double)L, &sn, &cs);
@@ -482,6 +488,18 @@ __global__ void s4_param_grad_kernel(const float2* __restrict__ lam, const float
     S01 = zadd(S01, zmul(cinv, {gk[1].x, gk[1].y}));
     S10 = zadd(S10, zmul(cinv, {gk[2].x, gk[2].y}));
   }
+  double v[6] = {S00.x, S00.y, S01.x, S01.y, S10.x, S10.y};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < 6; ++i) v[i] = ((red[0][i] + red[1][i]) + red[2][i]) + red[3][i];
+  S00 = {v[0], v[1]};
+  S01 = {v[2], v[3]};
+  S10 = {v[4], v[5]};
   const cdd a0 = zconj(ct), a1 = zconj(qj);
   cdd gB = zadd(zmul(zconj(a0), S00), zmul(zconj(a1), S10));
   cdd gA0 = zadd(zmul(zconj(b), S00), zmul(zconj(pj), S01));
@@ -690,7 +708,15 @@ extern "C" int lx_sgemm_ex(const lx_sgemm_ex_desc_t* desc, void* stream) {
   p.M = d.M; p.N = d.N; p.K = d.K; p.batch = d.batch;
   p.trans_a = d.trans_a; p.trans_b = d.trans_b; p.reduce_batch = d.reduce_batch;
   p.alpha = d.alpha; p.beta = d.beta;
-  dim3 grid((d.N + 63) / 64, (d.M + 63) / 64, d.reduce_batch ? 1 : d.batch);
+  p.ksplit = 1;
+  if (d.reduce_batch) {
+    LX_CHECK_ARG(d.beta == 1.0f, "lx_sgemm_ex: reduce_batch accumulates into C (beta must be 1)");
+    // enough CTAs to fill the GPU a few times over: tiles x batch x K slices >= ~4 x SMs, slices of at least 64
+    const long tiles = (long)((d.N + 63) / 64) * ((d.M + 63) / 64) * d.batch;
+    const long want = 4L * num_sms();
+    while (tiles * p.ksplit < want && d.K / (p.ksplit * 2) >= 64) p.ksplit *= 2;
+  }
+  dim3 grid((d.N + 63) / 64, (d.M + 63) / 64, d.reduce_batch ? d.batch * p.ksplit : d.batch);
   sgemm_ex_kernel<<<grid, 256, 0, ST(stream)>>>(p);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
@@ -811,7 +837,7 @@ extern "C" int lx_s4_kernel_gen_bwd(const void* lam, const void* p, const void* 
   s4_cauchy_bwd_kernel<<<g1, 128, 0, st>>>((const float2*)lam, (const float2*)p, (const float2*)q, (const float2*)Bm,
                                            (const float2*)Ct, log_step, G, Gk, dls, d, n, L);
   LX_CUDA(cudaGetLastError());
-  s4_param_grad_kernel<<<dim3((n + 63) / 64, d), 64, 0, st>>>((const float2*)lam, (const float2*)p, (const float2*)q,
+  s4_param_grad_kernel<<<dim3(n, d), 128, 0, st>>>((const float2*)lam, (const float2*)p, (const float2*)q,
                                                               (const float2*)Bm, (const float2*)Ct, log_step, G, Gk,
                                                               (float2*)dB, (float2*)dCt, d, n, L);
   LX_CUDA(cudaGetLastError());
