@@ -535,10 +535,10 @@ def run_train(args, rank, local_rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[4]: train step, Flux-DiT LoRA r=4 + CS3/DGF conditioning (EEG+PPG, "
-                                   "fNIRS+Motion, fuse_flag), 512x512 + image condition, gradient checkpointing per block, AdamW "
-                                   "on the LoRA factors, mean all-reduce of the flat gradient bucket",
+                                   "fNIRS+Motion, fuse_flag), 512x512 + image condition, LoRA + CS3/DGF encoder gradients, AdamW on the "
+                                   "LoRA factors (model.py:533-558), mean all-reduce of the one flat gradient bucket",
                        "batch_per_gpu": B, "global_batch": B * world, "micro_batch": tr.B, "recompute": tr.recompute,
-                       "parallelism": f"dp{world} (NCCL all-reduce of 14.5 M fp32)"},
+                       "parallelism": f"dp{world} (NCCL all-reduce of {tr.grad_flat.numel() / 1e6:.1f} M fp32)"},
             "gpu_launches": launches, "clocks": clk, "loss": float(loss.detach()),
             "algorithmic_tflops_per_gpu": tf, "frac_of_peak_end_to_end": tf / peaks["tflops"]}), flush=True)
     if world > 1:

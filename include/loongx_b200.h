@@ -65,7 +65,10 @@ enum lx_epilogue {
   LX_EPI_BIAS_SILU = 2,     /* out = silu(acc + bias)                             -> bf16                */
   LX_EPI_GATE_RESIDUAL = 3, /* out = residual + gate[stream,batch] * (acc + bias) -> bf16 (in place ok)  */
   LX_EPI_QKV = 4,           /* bias, per-head RMSNorm(q,k), RoPE, scatter to Q/K/V [B,H,S,128] -> bf16    */
-  LX_EPI_BIAS_F32 = 5       /* out = acc + bias                                   -> fp32                */
+  LX_EPI_BIAS_F32 = 5,      /* out = acc + bias                                   -> fp32                */
+  /* training step (model.py:569-729): the GELU's neighbours fused into the GEMMs either side of it */
+  LX_EPI_BIAS_GELU_DUAL = 6, /* out = gelu_tanh'(acc + bias) (the backward's factor) AND out2 = gelu_tanh(acc + bias) -> bf16 */
+  LX_EPI_MUL_AUX = 7         /* out = (acc + bias) * residual[row, col]  -> bf16 (residual = BIAS_GELU_DUAL's `out`)     */
 };
 
 typedef struct lx_gemm_segment {
@@ -95,8 +98,8 @@ typedef struct lx_gemm_desc {
   lx_gemm_group_t group[3];
   lx_gemm_segment_t seg[2];
   const lx_tile_meta_t* tile_meta; /* [ceil(M/128)]; required by GATE_RESIDUAL and QKV */
-  /* LX_EPI_GATE_RESIDUAL */
-  const void* residual; /* bf16 [M, ldr] */
+  /* LX_EPI_GATE_RESIDUAL / LX_EPI_MUL_AUX */
+  const void* residual; /* bf16 [M, ldr]; column = (n - first column of the segment) + col_offset */
   int64_t ldr;
   const void* gate[3];    /* bf16 gate vectors per stream: gate[s] + batch*gate_stride[s] + n */
   int64_t gate_stride[3]; /* elements */
@@ -115,6 +118,12 @@ typedef struct lx_gemm_desc {
    * mid-block attention), not a constant weight: the kernel then requests no W tile ahead of its programmatic-dependency
    * wait.  0 (weights): the first W tiles are prefetched while the previous kernel is still draining. */
   int32_t w_dynamic;
+  /* Second output (at most one segment uses it), column = (n - first column of the segment) + col_offset2:
+   * LX_EPI_BIAS_GELU_DUAL: gelu_tanh(acc + bias); LX_EPI_GATE_RESIDUAL (optional, NULL = none): acc + bias, the pre-gate
+   * projection the training backward needs for the gate gradient */
+  int32_t col_offset2;
+  void* out2; /* bf16 [M, ldo2] */
+  int64_t ldo2;
 } lx_gemm_desc_t;
 
 int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream);
@@ -501,6 +510,10 @@ int lx_qkv_post_fwd(const void* qkv_pre, int64_t ld, int32_t rows, int32_t heads
 int lx_qkv_post_bwd(const void* qkv_pre, int64_t ld, const void* dq, const void* dk, const void* dv, void* dqkv_pre,
                     int64_t ldo, int32_t rows, int32_t heads, const lx_tile_meta_t* tile_meta, int32_t seq_total,
                     const float* const rms_q[3], const float* const rms_k[3], const float* rope, float eps, void* stream);
+/* the same with dq read straight from lx_attention_bwd's fp32 accumulation buffer [B,H,S,128] (no cast pass) */
+int lx_qkv_post_bwd_f32dq(const void* qkv_pre, int64_t ld, const float* dq, const void* dk, const void* dv, void* dqkv_pre,
+                          int64_t ldo, int32_t rows, int32_t heads, const lx_tile_meta_t* tile_meta, int32_t seq_total,
+                          const float* const rms_q[3], const float* const rms_k[3], const float* rope, float eps, void* stream);
 /* rows [rows, ld] with head h in columns [128h, 128h+128) -> [B,H,S,128] (inverse of the attention output layout). */
 int lx_rows_to_heads(const void* rows_in, int64_t ld, void* heads_out, int32_t rows, int32_t heads,
                      const lx_tile_meta_t* tile_meta, int32_t seq_total, void* stream);
@@ -508,6 +521,20 @@ int lx_rows_to_heads(const void* rows_in, int64_t ld, void* heads_out, int32_t r
  * dy [M,N] and fp32 factors A [r,K], B [N,r] (r <= 16).  workspace: fp32 [2*M*r]. */
 int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t ldy, const float* A, const float* Bw, float* dA,
                  float* dB, int32_t M, int32_t K, int32_t N, int32_t r, float scaling, float* workspace, void* stream);
+/* The same gradients for up to 4 sub-Linears that share x and whose outputs are adjacent column blocks of one dy
+ * (to_q | to_k | to_v (| proj_mlp), block.py:50-58, 292-300): four launches for the whole group, x and dy read twice each.
+ * rank in {4, 8, 16}, groups * rank <= 16, widths multiples of 256, factors 16-byte aligned; workspace: fp32 [2*M*groups*r]. */
+typedef struct {
+  int32_t groups, r;
+  int32_t width[4];  /* output columns of sub-Linear g inside dy */
+  const float* A[4]; /* [r, K] */
+  const float* B[4]; /* [width, r] */
+  float* dA[4];
+  float* dB[4];
+  float scaling[4];
+} lx_lora_stack_t;
+int lx_lora_grad_stacked(const void* x, int64_t ldx, const void* dy, int64_t ldy, int32_t M, int32_t K,
+                         const lx_lora_stack_t* st, float* workspace, void* stream);
 /* out = bf16(W + s B A): the merged panel of the LoRA-active row group, rebuilt after every optimizer step. */
 int lx_lora_merge(const void* W, int64_t ldw, const float* A, const float* Bw, void* out, int64_t ldo, int32_t N, int32_t K,
                   int32_t r, float scaling, void* stream);

@@ -59,6 +59,7 @@ class GemmDesc(C.Structure):
         ("rms_q", c_void_p * 3), ("rms_k", c_void_p * 3),
         ("rope", c_void_p),
         ("rms_eps", c_float), ("tile_n", c_int32), ("w_dynamic", c_int32),
+        ("col_offset2", c_int32), ("out2", c_void_p), ("ldo2", c_int64),
     ]
 
 
@@ -87,7 +88,7 @@ class AttnBwdDesc(C.Structure):
     ]
 
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_QKV, EPI_BIAS_F32 = range(6)
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_QKV, EPI_BIAS_F32, EPI_BIAS_GELU_DUAL, EPI_MUL_AUX = range(8)
 
 lib.lx_last_error.restype = C.c_char_p
 lib.lx_version.restype = c_int

@@ -432,7 +432,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // one 16-byte fragment per row) loads complete while the tensor pipe is still working on this tile; in the
       // chunk loop below they would be one exposed round trip per 32 columns on the last tile of every CTA.
       uint4 rres[BN / 8];
-      if (mode == LX_EPI_GATE_RESIDUAL && row_ok) {
+      if ((mode == LX_EPI_GATE_RESIDUAL || mode == LX_EPI_MUL_AUX) && row_ok) {
         const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual) + (size_t)row * d.ldr +
                                    (n0 - seg_n0 + seg.col_offset);
 #pragma unroll
@@ -535,8 +535,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-      } else if (mode == LX_EPI_GATE_RESIDUAL) {
+      } else if (mode == LX_EPI_GATE_RESIDUAL || mode == LX_EPI_MUL_AUX) {
+        // MUL_AUX (training, dX through an activation): the "residual" rows hold the activation's derivative, written by
+        // the forward's BIAS_GELU_DUAL epilogue -- one multiply per element here; evaluating gelu' in this fully unrolled
+        // branch (255 registers, no room for instruction-level parallelism) cost +45 % on the whole GEMM
+        const bool mul_aux = mode == LX_EPI_MUL_AUX;
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo;
+        // GATE_RESIDUAL with out2 (training forward): the pre-gate projection y = acc + bias survives for the gate gradient
+        __nv_bfloat16* y_out = (!mul_aux && d.out2 != nullptr)
+                                   ? reinterpret_cast<__nv_bfloat16*>(d.out2) + (size_t)row * d.ldo2 + (d.col_offset2 - seg_n0)
+                                   : nullptr;
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           const int n = n0 + c * 32;
@@ -552,6 +560,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint4 g = *reinterpret_cast<const uint4*>(s_gate + c * 32 + j * 8);
                 uint32_t gu[4] = {g.x, g.y, g.z, g.w};
                 if (row_ok) {
+                  if (y_out != nullptr) store_bf16x8(y_out + n + j * 8, &x[8 * j]);
                   const uint4 rr = rres[c * 4 + j];
                   uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
                   float o[8];
@@ -559,8 +568,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int e = 0; e < 4; ++e) {
                     float2 gg = unpack_bf16(gu[e]);
                     float2 r2 = unpack_bf16(ru[e]);
-                    o[2 * e + 0] = r2.x + gg.x * x[8 * j + 2 * e + 0];
-                    o[2 * e + 1] = r2.y + gg.y * x[8 * j + 2 * e + 1];
+                    if (mul_aux) {
+                      o[2 * e + 0] = r2.x * x[8 * j + 2 * e + 0];
+                      o[2 * e + 1] = r2.y * x[8 * j + 2 * e + 1];
+                    } else {
+                      o[2 * e + 0] = r2.x + gg.x * x[8 * j + 2 * e + 0];
+                      o[2 * e + 1] = r2.y + gg.y * x[8 * j + 2 * e + 1];
+                    }
                   }
                   store_bf16x8(out + oc + j * 8, o);
                 }
@@ -578,7 +592,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float x[32];
           ld_acc(taddr, c * 32, r);
           chunk_bias(r, bias, c * 32, x);
-          if (mode == LX_EPI_BIAS_GELU) {
+          if (mode == LX_EPI_BIAS_GELU_DUAL) {  // training forward: gelu' goes to `out` for the backward's MUL_AUX epilogue
+            float gp[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gelu_tanh_pair(x[j], x[j], gp[j]);
+            if (row_ok) {
+              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo + (n - seg_n0 + seg.col_offset);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j * 8 < d.N) store_bf16x8(out + j * 8, &gp[8 * j]);
+            }
+          } else if (mode == LX_EPI_BIAS_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
           } else if (mode == LX_EPI_BIAS_SILU) {
@@ -594,7 +618,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (n + j * 4 < d.N)
                   *reinterpret_cast<float4*>(out + j * 4) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             } else {
-              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo + oc;
+              __nv_bfloat16* out = mode == LX_EPI_BIAS_GELU_DUAL
+                                       ? reinterpret_cast<__nv_bfloat16*>(d.out2) + (size_t)row * d.ldo2 + (n - seg_n0 + d.col_offset2)
+                                       : reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo + oc;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (n + j * 8 < d.N) store_bf16x8(out + j * 8, &x[8 * j]);
@@ -778,7 +804,7 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
   bool need_256 = nseg == 2;
   for (int s = 0; s < nseg; ++s) {
     const lx_gemm_segment_t& g = d.seg[s];
-    LX_CHECK_ARG(g.mode >= LX_EPI_BIAS && g.mode <= LX_EPI_BIAS_F32, "lx_gemm_bf16: bad epilogue mode %d", g.mode);
+    LX_CHECK_ARG(g.mode >= LX_EPI_BIAS && g.mode <= LX_EPI_MUL_AUX, "lx_gemm_bf16: bad epilogue mode %d", g.mode);
     if (g.mode == LX_EPI_QKV) {
       need_256 = true;
       LX_CHECK_ARG(s == 0, "lx_gemm_bf16: QKV segment must be segment 0");
@@ -794,6 +820,16 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
     }
     if (g.mode == LX_EPI_GATE_RESIDUAL) {
       LX_CHECK_ARG(d.residual && d.tile_meta && d.ldr % 8 == 0, "lx_gemm_bf16: GATE_RESIDUAL needs residual, tile_meta");
+    }
+    if (g.mode == LX_EPI_MUL_AUX) {
+      LX_CHECK_ARG(d.residual && d.ldr % 8 == 0, "lx_gemm_bf16: MUL_AUX needs the factor rows in residual / ldr");
+    }
+    if (g.mode == LX_EPI_GATE_RESIDUAL && d.out2) {
+      LX_CHECK_ARG(d.ldo2 > 0 && d.ldo2 % 8 == 0 && d.col_offset2 % 8 == 0, "lx_gemm_bf16: out2 needs ldo2 (multiple of 8)");
+    }
+    if (g.mode == LX_EPI_BIAS_GELU_DUAL) {
+      LX_CHECK_ARG(d.out2 && d.ldo2 > 0 && d.ldo2 % 8 == 0 && d.col_offset2 % 8 == 0,
+                   "lx_gemm_bf16: BIAS_GELU_DUAL needs out2 / ldo2 (multiple of 8)");
     }
   }
   // CTA pairs (256-row tiles) whenever every row group starts on a 256-row boundary; LX_GEMM_NCTA=1 forces single CTAs

@@ -341,6 +341,26 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return 0.5f * x * (1.0f + t);
 }
+// d/dx of 0.5 x (1 + tanh(k0 (x + k1 x^3)))
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u = k0 * (x + k1 * x * x2);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));  // one MUFU: this runs in GEMM epilogues (LX_EPI_GELU_GRAD)
+  return 0.5f * (1.0f + t) + (0.5f * k0) * x * (1.0f - t * t) * (1.0f + 3.0f * k1 * x2);
+}
+// both at once (one MUFU): y = gelu_tanh(x), dy = gelu_tanh'(x)
+__device__ __forceinline__ void gelu_tanh_pair(float x, float& y, float& dy) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u = k0 * (x + k1 * x * x2);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * (1.0f + t);
+  dy = h + (0.5f * k0) * x * (1.0f - t * t) * (1.0f + 3.0f * k1 * x2);
+  y = x * h;
+}
 // single MUFU.EX2 (flush-to-zero), the softmax exponential
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

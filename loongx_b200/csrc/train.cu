@@ -20,6 +20,11 @@ struct Acc3 {
   int64_t stride[3];
 };
 
+__device__ __forceinline__ void unpack8(const uint4& u, float* x) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+
 __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* x) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
   float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
@@ -29,14 +34,6 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
   uint4 u;
   u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = u;
-}
-
-// d/dx of 0.5 x (1 + tanh(k0 (x + k1 x^3)))
-__device__ __forceinline__ float gelu_tanh_grad(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float u = k0 * (x + k1 * x * x * x);
-  const float t = tanhf(u);
-  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -93,39 +90,60 @@ __global__ void gate_residual_fwd_kernel(const __nv_bfloat16* res, const __nv_bf
   st8(out + (size_t)r * ld + c, a);
 }
 
-// dy = gate * dout ; dgate[stream, batch, col] += sum_rows dout * y.   One CTA = one 128-row tile x 256 columns; each
-// thread owns 2 adjacent columns and walks the 128 rows (a warp reads 128 contiguous bytes per row).
+// dy = gate * dout ; dgate[stream, batch, col] += sum_rows dout * y.   One CTA = one 128-row tile x 256 columns: a warp
+// owns 32 of the rows, a lane 8 adjacent columns (16-byte loads, a warp reads 512 contiguous bytes per row, four rows in
+// flight); the four warps' column sums meet in shared memory, then one atomicAdd per column.
 __global__ void __launch_bounds__(128) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
                                                        const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy,
                                                        int64_t ld, int rows, int D, const lx_tile_meta_t* __restrict__ tm,
                                                        Vec3 gate, Acc3 dgate) {
   pdl_wait();  // PDL: inputs are the previous kernel's outputs
   pdl_launch_dependents();
-  const int tile = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x * 2;
-  if (c >= D) return;
+  __shared__ float part[4][256];
+  const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 256 + lane * 8;
   const lx_tile_meta_t m = tm[tile];
-  const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(gate.p[m.stream] + (size_t)m.batch * gate.stride[m.stream] + c));
-  float ax = 0.f, ay = 0.f;
-  const int r0 = tile * 128, r1 = min(rows, r0 + 128);
   float* acc = dgate.p[m.stream];
-  if (acc != nullptr) {
-    for (int r = r0; r < r1; ++r) {
-      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + (size_t)r * ld + c));
-      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + (size_t)r * ld + c));
-      ax += d.x * v.x;
-      ay += d.y * v.y;
-      *reinterpret_cast<uint32_t*>(dy + (size_t)r * ld + c) = pack_bf16(g.x * d.x, g.y * d.y);
-    }
-  } else {  // no gate gradient wanted for this stream: y is not read at all (it may not even have been recomputed)
-    for (int r = r0; r < r1; ++r) {
-      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + (size_t)r * ld + c));
-      *reinterpret_cast<uint32_t*>(dy + (size_t)r * ld + c) = pack_bf16(g.x * d.x, g.y * d.y);
+  float sum[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sum[e] = 0.f;
+  if (c < D) {
+    float g[8];
+    ld8(gate.p[m.stream] + (size_t)m.batch * gate.stride[m.stream] + c, g);
+    const int r0 = tile * 128 + warp * 32, r1 = min(rows, r0 + 32);
+    for (int r = r0; r < r1; r += 4) {
+      uint4 d[4], v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const size_t off = (size_t)min(r + i, r1 - 1) * ld + c;
+        d[i] = *reinterpret_cast<const uint4*>(dout + off);
+        // no gate gradient wanted for this stream: y is not read at all (it may not even have been recomputed)
+        v[i] = acc != nullptr ? *reinterpret_cast<const uint4*>(y + off) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r + i < r1) {
+          float df[8], vf[8], o[8];
+          unpack8(d[i], df);
+          unpack8(v[i], vf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sum[e] += df[e] * vf[e];
+            o[e] = g[e] * df[e];
+          }
+          st8(dy + (size_t)(r + i) * ld + c, o);
+        }
+      }
     }
   }
-  if (acc != nullptr) {
-    acc += (size_t)m.batch * dgate.stride[m.stream] + c;
-    atomicAdd(acc, ax);
-    atomicAdd(acc + 1, ay);
+  if (acc == nullptr) return;  // uniform over the CTA
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[warp][lane * 8 + e] = sum[e];
+  __syncthreads();
+  for (int k = threadIdx.x; k < 256; k += 128) {
+    const int col = blockIdx.y * 256 + k;
+    if (col < D)
+      atomicAdd(acc + (size_t)m.batch * dgate.stride[m.stream] + col, part[0][k] + part[1][k] + part[2][k] + part[3][k]);
   }
 }
 
@@ -218,36 +236,64 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_mod_bwd_row_kernel(
   if (threadIdx.x == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
 }
 
+// CTA = one 128-row tile x 256 columns: a warp owns 32 of the rows, a lane 8 adjacent columns (16-byte loads, four rows in
+// flight); the four warps' column sums meet in shared memory, then one atomicAdd per column and output.
 __global__ void __launch_bounds__(128) ln_mod_bwd_col_kernel(const __nv_bfloat16* __restrict__ x,
                                                              const __nv_bfloat16* __restrict__ dxn, int64_t ld, int rows,
                                                              int D, const lx_tile_meta_t* __restrict__ tm,
                                                              const float2* __restrict__ stats, Acc3 dscale, Acc3 dshift) {
   pdl_wait();  // PDL: inputs are the previous kernel's outputs
   pdl_launch_dependents();
-  const int tile = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x * 2;
-  if (c >= D) return;
+  __shared__ float part[2][4][256];
+  const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 256 + lane * 8;
   const lx_tile_meta_t m = tm[tile];
-  if (dscale.p[m.stream] == nullptr && dshift.p[m.stream] == nullptr) return;
-  float sx = 0.f, sy = 0.f, hx = 0.f, hy = 0.f;
-  const int r0 = tile * 128, r1 = min(rows, r0 + 128);
-  for (int r = r0; r < r1; ++r) {
-    const float2 st = stats[r];
-    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + (size_t)r * ld + c));
-    const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dxn + (size_t)r * ld + c));
-    sx += d.x * (v.x - st.x) * st.y;
-    sy += d.y * (v.y - st.x) * st.y;
-    hx += d.x;
-    hy += d.y;
+  if (dscale.p[m.stream] == nullptr && dshift.p[m.stream] == nullptr) return;  // uniform over the CTA
+  float ss[8], hh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ss[e] = hh[e] = 0.f;
+  if (c < D) {
+    const int r0 = tile * 128 + warp * 32, r1 = min(rows, r0 + 32);
+    for (int r = r0; r < r1; r += 4) {
+      uint4 xv[4], dv[4];
+      float2 st[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = min(r + i, r1 - 1);
+        xv[i] = *reinterpret_cast<const uint4*>(x + (size_t)rr * ld + c);
+        dv[i] = *reinterpret_cast<const uint4*>(dxn + (size_t)rr * ld + c);
+        st[i] = stats[rr];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r + i < r1) {
+          float xf[8], df[8];
+          unpack8(xv[i], xf);
+          unpack8(dv[i], df);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ss[e] += df[e] * (xf[e] - st[i].x) * st[i].y;
+            hh[e] += df[e];
+          }
+        }
+      }
+    }
   }
-  if (dscale.p[m.stream] != nullptr) {
-    float* a = dscale.p[m.stream] + (size_t)m.batch * dscale.stride[m.stream] + c;
-    atomicAdd(a, sx);
-    atomicAdd(a + 1, sy);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    part[0][warp][lane * 8 + e] = ss[e];
+    part[1][warp][lane * 8 + e] = hh[e];
   }
-  if (dshift.p[m.stream] != nullptr) {
-    float* a = dshift.p[m.stream] + (size_t)m.batch * dshift.stride[m.stream] + c;
-    atomicAdd(a, hx);
-    atomicAdd(a + 1, hy);
+  __syncthreads();
+  for (int k = threadIdx.x; k < 256; k += 128) {
+    const int col = blockIdx.y * 256 + k;
+    if (col >= D) continue;
+    if (dscale.p[m.stream] != nullptr)
+      atomicAdd(dscale.p[m.stream] + (size_t)m.batch * dscale.stride[m.stream] + col,
+                part[0][0][k] + part[0][1][k] + part[0][2][k] + part[0][3][k]);
+    if (dshift.p[m.stream] != nullptr)
+      atomicAdd(dshift.p[m.stream] + (size_t)m.batch * dshift.stride[m.stream] + col,
+                part[1][0][k] + part[1][1][k] + part[1][2][k] + part[1][3][k]);
   }
 }
 
@@ -316,8 +362,10 @@ __global__ void __launch_bounds__(128) qkv_post_fwd_kernel(const __nv_bfloat16* 
   }
 }
 
+// kDqF32: dq is the fp32 accumulation buffer of lx_attention_bwd (read directly: no separate cast pass)
+template <bool kDqF32>
 __global__ void __launch_bounds__(128) qkv_post_bwd_kernel(const __nv_bfloat16* __restrict__ pre, int64_t ld,
-                                                           const __nv_bfloat16* __restrict__ dq,
+                                                           const void* __restrict__ dq,
                                                            const __nv_bfloat16* __restrict__ dk,
                                                            const __nv_bfloat16* __restrict__ dv,
                                                            __nv_bfloat16* __restrict__ dpre, int64_t ldo, int rows, int heads,
@@ -341,7 +389,12 @@ __global__ void __launch_bounds__(128) qkv_post_bwd_kernel(const __nv_bfloat16* 
     for (int which = 0; which < 3; ++which) {
       __nv_bfloat16* out = dpre + (size_t)row * ldo + which * D + h * 128 + lane * 4;
       float g[4];
-      ld4((which == 0 ? dq : which == 1 ? dk : dv) + src, g);
+      if (kDqF32 && which == 0) {
+        const float4 t4 = *reinterpret_cast<const float4*>(static_cast<const float*>(dq) + src);
+        g[0] = t4.x; g[1] = t4.y; g[2] = t4.z; g[3] = t4.w;
+      } else {
+        ld4((which == 0 ? static_cast<const __nv_bfloat16*>(dq) : which == 1 ? dk : dv) + src, g);
+      }
       if (which == 2) {
         st4(out, g);
         continue;
@@ -490,6 +543,276 @@ __global__ void __launch_bounds__(128) lora_reduce_kernel(const __nv_bfloat16* _
       if (j < r) atomicAdd(G + (size_t)(c + e) * g_stride_c + j * g_stride_j, scaling * acc[e][j]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stacked LoRA factor gradients: G <= 4 sub-Linears that read the same x and whose outputs are adjacent column blocks
+// of one dy (to_q | to_k | to_v (| proj_mlp)), rank r in {4, 8, 16}, RT = G * r <= 16.  Four launches for the whole
+// group, each reading its operand once with 16-byte (8-byte in the widest reduce) loads:
+//   project_x:  PX[m, g r + j] = sum_k x[m, k] A_g[j, k]                 project_dy: PY[m, g r + j] = sum_n dy[m, c_g + n] B_g[n, j]
+//   reduce_x:   dA_g[j, k] += s_g sum_m PY[m, g r + j] x[m, k]           reduce_dy:  dB_g[n, j] += s_g sum_m dy[m, c_g + n] PX[m, g r + j]
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LORA_STACK_G = 4;
+constexpr int LORA_STACK_RT = 16;
+struct LoraStack {
+  int G, r;
+  int col0[LORA_STACK_G + 1];          // first dy column of group g; col0[G] = total width
+  const float* a_row[LORA_STACK_RT];   // a_row[g r + j] = A_g + j K
+  float* da_row[LORA_STACK_RT];        // dA_g + j K
+  float s_row[LORA_STACK_RT];          // s_g
+  float s_grp[LORA_STACK_G];
+  const float* B[LORA_STACK_G];
+  float* dB[LORA_STACK_G];
+};
+
+// The two projections run as ONE launch (the first CTAs take x, the rest dy), and so do the two reductions: each of the
+// four pieces alone leaves SMs idle on the DiT's shapes (M = the condition rows, 25-100 MB per operand).
+//
+// project_x piece: CTA = 8 warps x 4 rows x one K chunk (partial sums meet in PX through atomics; PX zeroed by the launcher).
+template <int RT>
+__device__ __forceinline__ void lora_stack_project_x(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int K, int kchunk,
+                                                     const LoraStack& p, float* __restrict__ PX, int bx, int by) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = bx * 32 + warp * 4;
+  if (row0 >= M) return;
+  const int c_begin = by * kchunk, c_end = min(K, c_begin + kchunk);
+  float acc[4][RT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
+  const __nv_bfloat16* xr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xr[i] = x + (size_t)min(row0 + i, M - 1) * ldx;
+  constexpr bool kPrefetch = RT <= 8;  // the wide variants have no registers to spare; their FMAs cover the latency
+  uint4 nxt[4];  // the next iteration's rows are in flight while this one is multiplied
+  if constexpr (kPrefetch) {
+    const int c = c_begin + lane * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nxt[i] = c < c_end ? __ldg(reinterpret_cast<const uint4*>(xr[i] + c)) : make_uint4(0, 0, 0, 0);
+  }
+  for (int c = c_begin + lane * 8; c < c_end; c += 256) {
+    float z[4][8];
+    if constexpr (kPrefetch) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack8(nxt[i], z[i]);
+      if (c + 256 < c_end) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nxt[i] = __ldg(reinterpret_cast<const uint4*>(xr[i] + c + 256));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack8(__ldg(reinterpret_cast<const uint4*>(xr[i] + c)), z[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      const float4 f0 = __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c));
+      const float4 f1 = __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c + 4));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        acc[i][j] += z[i][0] * f0.x + z[i][1] * f0.y + z[i][2] * f0.z + z[i][3] * f0.w + z[i][4] * f1.x + z[i][5] * f1.y +
+                     z[i][6] * f1.z + z[i][7] * f1.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      const float sm = warp_sum(acc[i][j]);
+      if (lane == 0 && row0 + i < M) atomicAdd(PX + (size_t)(row0 + i) * RT + j, sm);
+    }
+}
+
+// project_dy piece: CTA = 8 warps x RPW rows inside ONE column chunk of one group (chunk divides every group width).
+template <int R, int RPW>
+__device__ __forceinline__ void lora_stack_project_dy(const __nv_bfloat16* __restrict__ dy, int64_t ldy, int M, int chunk,
+                                                      const LoraStack& p, float* __restrict__ PY, int bx, int by) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (bx * 8 + warp) * RPW;
+  if (row0 >= M) return;
+  const int c_begin = by * chunk;
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < LORA_STACK_G; ++i) g += (i < p.G && c_begin >= p.col0[i]) ? 1 : 0;
+  // (selects: run-time indexing of kernel-parameter arrays goes through local memory)
+  const float* __restrict__ Bg = g == 0 ? p.B[0] : (g == 1 ? p.B[1] : (g == 2 ? p.B[2] : p.B[3]));
+  const int cg = g == 0 ? 0 : (g == 1 ? p.col0[1] : (g == 2 ? p.col0[2] : p.col0[3]));  // B_g row of dy column c: c - cg
+  float acc[RPW][R];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
+  const int c_end = c_begin + chunk;
+  uint4 nxt[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+    nxt[i] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)min(row0 + i, M - 1) * ldy + c_begin + lane * 8));
+  for (int c = c_begin + lane * 8; c < c_end; c += 256) {
+    float z[RPW][8];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) unpack8(nxt[i], z[i]);
+    if (c + 256 < c_end) {
+#pragma unroll
+      for (int i = 0; i < RPW; ++i)
+        nxt[i] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)min(row0 + i, M - 1) * ldy + c + 256));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float b[R];
+#pragma unroll
+      for (int q = 0; q < R / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)(c + e - cg) * R + q * 4));
+        b[q * 4] = t.x; b[q * 4 + 1] = t.y; b[q * 4 + 2] = t.z; b[q * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < RPW; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] += z[i][e] * b[j];
+    }
+  }
+  const int RT = p.G * R;
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const float sm = warp_sum(acc[i][j]);
+      if (lane == 0 && row0 + i < M) atomicAdd(PY + (size_t)(row0 + i) * RT + g * R + j, sm);
+    }
+}
+
+struct LoraStackGrid {
+  int x_bx, x_n;   // project / reduce over x: CTAs [0, x_n), (bx, by) = (b % x_bx, b / x_bx)
+  int dy_bx;       // the rest work on dy: b - x_n -> (b % dy_bx, b / dy_bx)
+};
+
+template <int RT, int R, int RPW>
+__global__ void __launch_bounds__(256, 2) lora_stack_project_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                                    const __nv_bfloat16* __restrict__ dy, int64_t ldy, int M,
+                                                                    int K, int kchunk, int chunk, const LoraStackGrid gr,
+                                                                    const LoraStack p, float* __restrict__ PX,
+                                                                    float* __restrict__ PY) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x;
+  if (b < gr.x_n) lora_stack_project_x<RT>(x, ldx, M, K, kchunk, p, PX, b % gr.x_bx, b / gr.x_bx);
+  else lora_stack_project_dy<R, RPW>(dy, ldy, M, chunk, p, PY, (b - gr.x_n) % gr.dy_bx, (b - gr.x_n) / gr.dy_bx);
+}
+
+// reduce pieces: CTA = 32 rows x 512 columns of x (4 adjacent columns per thread, 8 rows in flight) or 32 rows x
+// (128 * COLS) columns of dy (a thread's COLS adjacent columns lie inside one group); P rows from shared memory.
+constexpr int LORA_RROWS = 32;
+template <int RT>
+__device__ __forceinline__ void lora_stack_reduce_x(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int K,
+                                                    const LoraStack& p, const float* __restrict__ PY, float* ps, int bx, int by) {
+  const int r0 = bx * LORA_RROWS, nrow = min(M - r0, LORA_RROWS);
+  for (int i = threadIdx.x; i < LORA_RROWS * RT; i += 128) ps[i] = (i / RT < nrow) ? PY[(size_t)r0 * RT + i] : 0.f;
+  __syncthreads();
+  const int c = by * 512 + threadIdx.x * 4;
+  if (c >= K) return;
+  float acc[4][RT];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int j = 0; j < RT; ++j) acc[e][j] = 0.f;
+  for (int m = 0; m < nrow; m += 8) {
+    uint2 u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)  // rows past the end re-read the last row; their P rows are zero
+      u[i] = __ldg(reinterpret_cast<const uint2*>(x + (size_t)(r0 + min(m + i, nrow - 1)) * ldx + c));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = unpack_bf16(u[i].x), b = unpack_bf16(u[i].y);
+      const float* pr = ps + (m + i) * RT;  // m + i < LORA_RROWS always (m a multiple of 8)
+#pragma unroll
+      for (int q = 0; q < RT / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(pr + q * 4);
+        const float pv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          acc[0][q * 4 + jj] += a.x * pv[jj];
+          acc[1][q * 4 + jj] += a.y * pv[jj];
+          acc[2][q * 4 + jj] += b.x * pv[jj];
+          acc[3][q * 4 + jj] += b.y * pv[jj];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    const float s = p.s_row[j];
+    atomicAdd(reinterpret_cast<float4*>(p.da_row[j] + c), make_float4(s * acc[0][j], s * acc[1][j], s * acc[2][j], s * acc[3][j]));
+  }
+}
+
+template <int R, int COLS>
+__device__ __forceinline__ void lora_stack_reduce_dy(const __nv_bfloat16* __restrict__ dy, int64_t ldy, int M, const LoraStack& p,
+                                                     const float* __restrict__ PX, float* ps, int bx, int by) {
+  const int RT = p.G * R;
+  const int r0 = bx * LORA_RROWS, nrow = min(M - r0, LORA_RROWS);
+  for (int i = threadIdx.x; i < LORA_RROWS * RT; i += 128) ps[i] = (i / RT < nrow) ? PX[(size_t)r0 * RT + i] : 0.f;
+  __syncthreads();
+  const int c = (by * 128 + threadIdx.x) * COLS;
+  if (c >= p.col0[LORA_STACK_G]) return;
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < LORA_STACK_G; ++i) g += (i < p.G && c >= p.col0[i]) ? 1 : 0;
+  float acc[COLS][R];
+#pragma unroll
+  for (int e = 0; e < COLS; ++e)
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[e][j] = 0.f;
+  constexpr int INF = 64 / COLS;  // rows in flight: 128 bytes per thread
+  for (int m = 0; m < nrow; m += INF) {
+    float z[INF][COLS];
+#pragma unroll
+    for (int i = 0; i < INF; ++i) {
+      const __nv_bfloat16* src = dy + (size_t)(r0 + min(m + i, nrow - 1)) * ldy + c;
+      if constexpr (COLS == 8) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), z[i]);
+      } else {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(src));
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        z[i][0] = a.x; z[i][1] = a.y; z[i][2] = b.x; z[i][3] = b.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < INF; ++i) {
+      const float* pr = ps + (m + i) * RT + g * R;  // m + i < LORA_RROWS always (INF divides it)
+      float pv[R];
+#pragma unroll
+      for (int q = 0; q < R / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(pr + q * 4);
+        pv[q * 4] = t.x; pv[q * 4 + 1] = t.y; pv[q * 4 + 2] = t.z; pv[q * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int e = 0; e < COLS; ++e)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[e][j] += z[i][e] * pv[j];
+    }
+  }
+  const float s = g == 0 ? p.s_grp[0] : (g == 1 ? p.s_grp[1] : (g == 2 ? p.s_grp[2] : p.s_grp[3]));
+  float* dBg = g == 0 ? p.dB[0] : (g == 1 ? p.dB[1] : (g == 2 ? p.dB[2] : p.dB[3]));
+  const int cg = g == 0 ? 0 : (g == 1 ? p.col0[1] : (g == 2 ? p.col0[2] : p.col0[3]));
+  float* out = dBg + (size_t)(c - cg) * R;
+#pragma unroll
+  for (int e = 0; e < COLS; ++e)
+#pragma unroll
+    for (int q = 0; q < R / 4; ++q)
+      atomicAdd(reinterpret_cast<float4*>(out + (size_t)e * R + q * 4),
+                make_float4(s * acc[e][q * 4], s * acc[e][q * 4 + 1], s * acc[e][q * 4 + 2], s * acc[e][q * 4 + 3]));
+}
+
+template <int RT, int R, int COLS>
+__global__ void __launch_bounds__(128) lora_stack_reduce_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                                const __nv_bfloat16* __restrict__ dy, int64_t ldy, int M, int K,
+                                                                const LoraStackGrid gr, const LoraStack p,
+                                                                const float* __restrict__ PX, const float* __restrict__ PY) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) float ps[LORA_RROWS * LORA_STACK_RT];
+  const int b = blockIdx.x;
+  if (b < gr.x_n) lora_stack_reduce_x<RT>(x, ldx, M, K, p, PY, ps, b % gr.x_bx, b / gr.x_bx);
+  else lora_stack_reduce_dy<R, COLS>(dy, ldy, M, p, PX, ps, (b - gr.x_n) % gr.dy_bx, (b - gr.x_n) / gr.dy_bx);
+}
+
 // out[n, k] = bf16(W[n, k] + s * sum_j B[n, j] A[j, k])   (the merged panel the LoRA-active row group multiplies by)
 __global__ void lora_merge_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ A,
                                   const float* __restrict__ Bw, __nv_bfloat16* __restrict__ out, int64_t ldo, int N, int K,
@@ -547,17 +870,18 @@ __global__ void flow_noise_mix_kernel(const __nv_bfloat16* __restrict__ x0, cons
   st8(xt + idx * 8, a);
 }
 
-__global__ void __launch_bounds__(256) flow_mse_kernel(const __nv_bfloat16* __restrict__ pred,
-                                                       const __nv_bfloat16* __restrict__ x0,
-                                                       const __nv_bfloat16* __restrict__ x1, float* __restrict__ loss,
-                                                       __nv_bfloat16* __restrict__ dpred, int64_t n8, float inv_n,
-                                                       float grad_scale) {
+// ONE CTA walks the whole prediction (a few hundred KB once per step) and reduces in a fixed order: the loss is
+// bit-reproducible from run to run (a grid of CTAs meeting in an atomicAdd was not).
+__global__ void __launch_bounds__(1024) flow_mse_kernel(const __nv_bfloat16* __restrict__ pred,
+                                                        const __nv_bfloat16* __restrict__ x0,
+                                                        const __nv_bfloat16* __restrict__ x1, float* __restrict__ loss,
+                                                        __nv_bfloat16* __restrict__ dpred, int64_t n8, float inv_n,
+                                                        float grad_scale) {
   pdl_wait();  // PDL: inputs are the previous kernel's outputs
   pdl_launch_dependents();
-  __shared__ float red[8];
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[32];
   float s = 0.f;
-  if (idx < n8) {
+  for (int64_t idx = threadIdx.x; idx < n8; idx += 1024) {
     float p[8], a[8], b[8];
     ld8(pred + idx * 8, p);
     ld8(x0 + idx * 8, a);
@@ -577,8 +901,8 @@ __global__ void __launch_bounds__(256) flow_mse_kernel(const __nv_bfloat16* __re
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
-    for (int i = 0; i < 8; ++i) tot += red[i];
-    atomicAdd(loss, tot * inv_n);
+    for (int i = 0; i < 32; ++i) tot += red[i];
+    *loss += tot * inv_n;  // accumulates (micro-batches): the caller zeroes it
   }
 }
 
@@ -640,9 +964,9 @@ extern "C" int lx_gate_residual_fwd(const void* res, const void* y, void* out, i
 extern "C" int lx_gate_bwd(const void* dout, const void* y, void* dy, int64_t ld, int32_t rows, int32_t D,
                            const lx_tile_meta_t* tile_meta, const void* const gate[3], const int64_t gate_stride[3],
                            float* const dgate[3], const int64_t dgate_stride[3], void* stream) {
-  LX_CHECK_ARG(dout && y && dy && tile_meta && gate && gate_stride && rows > 0 && rows % 128 == 0 && D > 0 && D % 2 == 0 &&
-                   ld % 2 == 0,
-               "lx_gate_bwd: bad arguments");
+  LX_CHECK_ARG(dout && y && dy && tile_meta && gate && gate_stride && rows > 0 && rows % 128 == 0 && D > 0 && D % 8 == 0 &&
+                   ld % 8 == 0,
+               "lx_gate_bwd: bad arguments (rows a multiple of 128, D / ld multiples of 8)");
   LaunchScope scope(KC_ROW, stream, 6.0 * rows * D);
   launch_pdl(gate_bwd_kernel, dim3(rows / 128, (D + 255) / 256), dim3(128), 0, cs(stream), bf(dout), bf(y), bf(dy), ld, rows, D, tile_meta,
                                                                             vec3(gate, gate_stride), acc3(dgate, dgate_stride));
@@ -705,8 +1029,22 @@ extern "C" int lx_qkv_post_bwd(const void* qkv_pre, int64_t ld, const void* dq, 
                    ldo % 4 == 0 && ld >= 3 * heads * 128 && ldo >= 3 * heads * 128,
                "lx_qkv_post_bwd: bad arguments");
   LaunchScope scope(KC_ROW, stream, 18.0 * rows * heads * 128);
-  launch_pdl(qkv_post_bwd_kernel, dim3(rows), dim3(128), 0, cs(stream), bf(qkv_pre), ld, bf(dq), bf(dk), bf(dv), bf(dqkv_pre), ldo, rows, heads,
+  launch_pdl(qkv_post_bwd_kernel<false>, dim3(rows), dim3(128), 0, cs(stream), bf(qkv_pre), ld, dq, bf(dk), bf(dv), bf(dqkv_pre), ldo, rows, heads,
                                                    tile_meta, seq_total, rmsw(rms_q, rms_k), rope, eps);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_qkv_post_bwd_f32dq(const void* qkv_pre, int64_t ld, const float* dq, const void* dk, const void* dv,
+                                     void* dqkv_pre, int64_t ldo, int32_t rows, int32_t heads, const lx_tile_meta_t* tile_meta,
+                                     int32_t seq_total, const float* const rms_q[3], const float* const rms_k[3],
+                                     const float* rope, float eps, void* stream) {
+  LX_CHECK_ARG(qkv_pre && dq && dk && dv && dqkv_pre && tile_meta && rows > 0 && heads > 0 && seq_total > 0 && ld % 4 == 0 &&
+                   ldo % 4 == 0 && ld >= 3 * heads * 128 && ldo >= 3 * heads * 128,
+               "lx_qkv_post_bwd_f32dq: bad arguments");
+  LaunchScope scope(KC_ROW, stream, 20.0 * rows * heads * 128);
+  launch_pdl(qkv_post_bwd_kernel<true>, dim3(rows), dim3(128), 0, cs(stream), bf(qkv_pre), ld, static_cast<const void*>(dq), bf(dk), bf(dv),
+             bf(dqkv_pre), ldo, rows, heads, tile_meta, seq_total, rmsw(rms_q, rms_k), rope, eps);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }
@@ -752,6 +1090,78 @@ extern "C" int lx_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t 
   return LX_OK;
 }
 
+extern "C" int lx_lora_grad_stacked(const void* x, int64_t ldx, const void* dy, int64_t ldy, int32_t M, int32_t K,
+                                    const lx_lora_stack_t* st, float* workspace, void* stream) {
+  LX_CHECK_ARG(x && dy && st && workspace && M > 0 && K > 0, "lx_lora_grad_stacked: bad arguments");
+  const int G = st->groups, r = st->r, RT = G * r;
+  LX_CHECK_ARG(G >= 1 && G <= LORA_STACK_G && (r == 4 || r == 8 || r == 16) && RT <= LORA_STACK_RT,
+               "lx_lora_grad_stacked: %d groups of rank %d (rank in {4, 8, 16}, groups * rank <= %d)", G, r, LORA_STACK_RT);
+  LX_CHECK_ARG(K % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "lx_lora_grad_stacked: K / strides must be multiples of 8");
+  LoraStack p{};
+  p.G = G;
+  p.r = r;
+  int chunk = 2048, N = 0;
+  for (int g = 0; g < G; ++g) {
+    LX_CHECK_ARG(st->A[g] && st->B[g] && st->dA[g] && st->dB[g] && st->width[g] > 0 && st->width[g] % 256 == 0,
+                 "lx_lora_grad_stacked: group %d: null factor or width %d not a multiple of 256", g, st->width[g]);
+    LX_CHECK_ARG(((uintptr_t)st->A[g] | (uintptr_t)st->B[g] | (uintptr_t)st->dA[g] | (uintptr_t)st->dB[g]) % 16 == 0,
+                 "lx_lora_grad_stacked: group %d: factors must be 16-byte aligned", g);
+    p.col0[g] = N;
+    N += st->width[g];
+    while (st->width[g] % chunk) chunk >>= 1;
+    p.B[g] = st->B[g];
+    p.dB[g] = st->dB[g];
+    p.s_grp[g] = st->scaling[g];
+    for (int j = 0; j < r; ++j) {
+      p.a_row[g * r + j] = st->A[g] + (size_t)j * K;
+      p.da_row[g * r + j] = st->dA[g] + (size_t)j * K;
+      p.s_row[g * r + j] = st->scaling[g];
+    }
+  }
+  for (int g = G; g <= LORA_STACK_G; ++g) p.col0[g] = N;
+  float* PX = workspace;                   // [M, RT] = x A^T (all groups)
+  float* PY = workspace + (size_t)M * RT;  // [M, RT] = dy_g B_g
+  cudaStream_t s = cs(stream);
+  LaunchScope scope(KC_ROW, stream, 4.0 * M * ((double)K + N));
+  LX_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * (size_t)M * RT, s));
+  // K chunks of project_x: enough CTAs to fill the GPU, at least 512 columns each
+  const int gmx = (M + 31) / 32;
+  int ksplit = 1;
+  while (gmx * ksplit < 592 && K / (ksplit * 2) >= 512 && K % (ksplit * 2 * 256) == 0) ksplit *= 2;
+  const int kchunk = (K / ksplit + 255) / 256 * 256;
+  const int gky = (K + kchunk - 1) / kchunk;
+  // column chunks of project_dy: at least 1024 columns (4 iterations per warp) unless a group is narrower
+  const int rpw = r == 16 ? 2 : 4;
+  const int gmy = (M + 8 * rpw - 1) / (8 * rpw);
+  while (chunk > 1024 && (long long)gmy * (N / chunk) < 592) chunk >>= 1;
+  const LoraStackGrid gp{gmx, gmx * gky, gmy};
+  const unsigned n_project = (unsigned)(gmx * gky + gmy * (N / chunk));
+  const int grr = (M + LORA_RROWS - 1) / LORA_RROWS;
+  const int cols = r == 16 ? 4 : 8;
+  const LoraStackGrid gq{grr, grr * ((K + 511) / 512), grr};
+  const unsigned n_reduce = (unsigned)(gq.x_n + grr * ((N + 128 * cols - 1) / (128 * cols)));
+  // (the first kernel after the memset is launched stream-ordered, see launch_ordered)
+#define LX_STACK(RTV, RV, RPWV, COLSV)                                                                                       \
+  LX_CUDA(launch_ordered(lora_stack_project_kernel<RTV, RV, RPWV>, dim3(n_project), dim3(256), 0, s, bf(x), ldx, bf(dy), ldy, \
+                         M, K, kchunk, chunk, gp, p, PX, PY));                                                               \
+  LX_CUDA(launch_pdl(lora_stack_reduce_kernel<RTV, RV, COLSV>, dim3(n_reduce), dim3(128), 0, s, bf(x), ldx, bf(dy), ldy, M, K, \
+                     gq, p, static_cast<const float*>(PX), static_cast<const float*>(PY)))
+  if (r == 4) {
+    if (RT == 4) { LX_STACK(4, 4, 4, 8); }
+    else if (RT == 8) { LX_STACK(8, 4, 4, 8); }
+    else if (RT == 12) { LX_STACK(12, 4, 4, 8); }
+    else { LX_STACK(16, 4, 4, 8); }
+  } else if (r == 8) {
+    if (RT == 8) { LX_STACK(8, 8, 4, 8); }
+    else { LX_STACK(16, 8, 4, 8); }
+  } else {
+    LX_STACK(16, 16, 2, 4);
+  }
+#undef LX_STACK
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
 extern "C" int lx_lora_merge(const void* W, int64_t ldw, const float* A, const float* Bw, void* out, int64_t ldo, int32_t N,
                              int32_t K, int32_t r, float scaling, void* stream) {
   LX_CHECK_ARG(W && A && Bw && out && N > 0 && K > 0 && K % 2 == 0 && r > 0 && ldw % 2 == 0 && ldo % 2 == 0,
@@ -788,7 +1198,7 @@ extern "C" int lx_flow_mse_loss(const void* pred, const void* x0, const void* x1
   LX_CHECK_ARG(pred && x0 && x1 && loss && n > 0 && n % 8 == 0, "lx_flow_mse_loss: bad arguments");
   const int64_t n8 = n / 8;
   LaunchScope scope(KC_ROW, stream, 8.0 * n);
-  launch_pdl(flow_mse_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, cs(stream), bf(pred), bf(x0), bf(x1), loss, bf(dpred), n8,
+  launch_pdl(flow_mse_kernel, dim3(1), dim3(1024), 0, cs(stream), bf(pred), bf(x0), bf(x1), loss, bf(dpred), n8,
                                                                        1.0f / (float)n, grad_scale);
   LX_CUDA(cudaGetLastError());
   return LX_OK;

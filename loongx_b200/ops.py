@@ -50,6 +50,7 @@ def gemm(
     col_offset: int = 0,
     n_split: Optional[int] = None,
     seg1: Optional[tuple] = None,  # (mode, out, col_offset)
+    out2: Optional[tuple] = None,  # (tensor, col_offset2): second output of the EPI_BIAS_GELU_DUAL segment
     groups: Optional[Sequence[tuple]] = None,  # extra row groups: (W, bias, m_begin)
     tile_meta: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
@@ -88,6 +89,10 @@ def gemm(
     if seg1 is not None:
         m1, o1, c1 = seg1
         d.seg[1].mode, d.seg[1].out, d.seg[1].ldo, d.seg[1].col_offset = m1, _ptr(o1), o1.stride(0), c1
+    if out2 is not None:
+        o2, c2 = out2
+        assert o2.dtype == torch.bfloat16 and o2.stride(-1) == 1
+        d.out2, d.ldo2, d.col_offset2 = _ptr(o2), o2.stride(0), c2
     d.tile_meta = _ptr(tile_meta)
     if residual is not None:
         d.residual, d.ldr = _ptr(residual), residual.stride(0)

@@ -22,6 +22,7 @@ CS3 / DGF encoders run forward-only (they are not in the reference's optimizer p
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -53,6 +54,7 @@ _lib.lx_qkv_post_fwd.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, 
                                  _P3, c_void_p, c_float, c_void_p]
 _lib.lx_qkv_post_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                  c_void_p, c_int32, _P3, _P3, c_void_p, c_float, c_void_p]
+_lib.lx_qkv_post_bwd_f32dq.argtypes = _lib.lx_qkv_post_bwd.argtypes
 _lib.lx_rows_to_heads.argtypes = [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]
 _lib.lx_lora_grad.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                               c_int32, c_int32, c_float, c_void_p, c_void_p]
@@ -147,7 +149,9 @@ def qkv_post_fwd(pre, heads, tile_meta, q, k, v, rms_q, rms_k, rope, eps=1e-6):
 
 
 def qkv_post_bwd(pre, dq, dk, dv, dpre, heads, tile_meta, rms_q, rms_k, rope, eps=1e-6):
-    L.check(_lib.lx_qkv_post_bwd(pre.data_ptr(), pre.stride(0), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dpre.data_ptr(),
+    """dq: bf16, or the fp32 accumulation buffer of attention_bwd (read directly)."""
+    fn = _lib.lx_qkv_post_bwd_f32dq if dq.dtype == torch.float32 else _lib.lx_qkv_post_bwd
+    L.check(fn(pre.data_ptr(), pre.stride(0), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dpre.data_ptr(),
                                  dpre.stride(0), pre.shape[0], heads, tile_meta.data_ptr(), dq.shape[2], _rms3(rms_q),
                                  _rms3(rms_k), _ptr(rope), eps, _stream()), "lx_qkv_post_bwd")
 
@@ -166,6 +170,39 @@ def lora_grad(x, dy, A, Bw, dA, dB, scaling, workspace):
     L.check(_lib.lx_lora_grad(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), A.data_ptr(), Bw.data_ptr(),
                               dA.data_ptr(), dB.data_ptr(), M, K, N, r, float(scaling), workspace.data_ptr(), _stream()),
             "lx_lora_grad")
+
+
+class LoraStack(C.Structure):
+    """lx_lora_stack_t (include/loongx_b200.h)."""
+    _fields_ = [("groups", C.c_int32), ("r", C.c_int32), ("width", C.c_int32 * 4), ("A", c_void_p * 4), ("B", c_void_p * 4),
+                ("dA", c_void_p * 4), ("dB", c_void_p * 4), ("scaling", C.c_float * 4)]
+
+
+_lib.lx_lora_grad_stacked.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, C.POINTER(LoraStack), c_void_p,
+                                      c_void_p]
+
+
+def lora_grad_stackable(factors) -> bool:
+    """can lx_lora_grad_stacked take these sub-Linears (sharing x, adjacent outputs) in one pass?"""
+    r = factors[0].A.shape[0]
+    return (r in (4, 8, 16) and len(factors) * r <= 16 and len(factors) <= 4 and factors[0].A.shape[1] % 8 == 0 and
+            all(f.A.shape[0] == r and f.rows % 256 == 0 and f.A.data_ptr() % 16 == 0 and f.B.data_ptr() % 16 == 0 and
+                f.dA.data_ptr() % 16 == 0 and f.dB.data_ptr() % 16 == 0 for f in factors))
+
+
+def lora_grad_stacked(x, dy, factors, workspace):
+    """dA / dB of `factors` (LoraFactor list): x [M, K] shared, outputs = adjacent column blocks of dy [M, sum widths]."""
+    M, K = x.shape
+    st = LoraStack()
+    st.groups, st.r = len(factors), factors[0].A.shape[0]
+    assert dy.shape == (M, sum(f.rows for f in factors)) and workspace.numel() >= 2 * M * st.groups * st.r
+    assert x.stride(1) == 1 and dy.stride(1) == 1 and x.stride(0) % 8 == 0 and dy.stride(0) % 8 == 0
+    for g, f in enumerate(factors):
+        assert f.A.shape == (st.r, K) and f.B.shape == (f.rows, st.r) and f.A.is_contiguous() and f.B.is_contiguous()
+        st.width[g], st.scaling[g] = f.rows, float(f.panel.scaling)
+        st.A[g], st.B[g], st.dA[g], st.dB[g] = f.A.data_ptr(), f.B.data_ptr(), f.dA.data_ptr(), f.dB.data_ptr()
+    L.check(_lib.lx_lora_grad_stacked(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), M, K, C.byref(st),
+                                      workspace.data_ptr(), _stream()), "lx_lora_grad_stacked")
 
 
 def lora_merge(W, A, Bw, out, scaling):
@@ -476,7 +513,10 @@ class DitTrainer:
         self.delta = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
         self.dq32 = torch.zeros((B, self.H, S, 128), device=dev, dtype=torch.float32)
         self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
-        self.lora_ws = torch.zeros((2 * max(R, B) * max(cfg.lora_rank, 1),), device=dev, dtype=torch.float32)
+        self.lora_ws = torch.zeros((2 * max(R, B) * max(cfg.lora_rank, 16),), device=dev, dtype=torch.float32)
+        self.stack_lora = os.environ.get("LX_LORA_STACK", "1") != "0"  # A/B knob: per-factor kernels instead
+        self.fuse_gate = os.environ.get("LX_FUSE_GATE", "1") != "0"  # A/B knob: separate gate + residual kernel
+        self.fuse_gelu = os.environ.get("LX_FUSE_GELU", "1") != "0"  # A/B knob: separate GELU forward / backward kernels
         self.ckpt = torch.zeros((cfg.num_layers + cfg.num_single_layers, R, D), **bf)
         self.ckpt_mid = torch.zeros((max(cfg.num_layers, 1), R, D), **bf)  # residual stream after the attention branch
         self.dmod_dbl = torch.zeros((B, max(cfg.num_layers, 1) * 6 * D), device=dev, dtype=torch.float32)
@@ -581,20 +621,24 @@ class DitTrainer:
                                                  (pick(main, True), bias(main), self.Rt + self.Ri)]
         return pick(main, ll), bias(main), [(pick(main, True), bias(main), self.Rt + self.Ri)]  # single: [txt+img | cond]
 
-    def _gemm(self, A, main, ctx, out, transposed=False):
+    def _gemm(self, A, main, ctx, out, transposed=False, mode=L.EPI_BIAS, **kw):
         W0, b0, extra = self._groups(main, ctx, transposed)
-        ops.gemm(A, W0, b0, out, L.EPI_BIAS, groups=extra)
+        ops.gemm(A, W0, b0, out, mode, groups=extra, **kw)
 
     def _lora_grads(self, names, x_rows, dy_rows, col0=0):
         """accumulate dA / dB of consecutive sub-Linears `names` whose outputs are adjacent column blocks of dy_rows."""
+        fs = [self.factors[n] for n in names]
         c = col0
-        for n in names:
-            f = self.factors.get(n)
-            width = f.rows if f is not None else None
-            if f is None:
-                raise KeyError(n)
-            lora_grad(x_rows, dy_rows[:, c:c + width], f.A.data, f.B.data, f.dA, f.dB, f.panel.scaling, self.lora_ws)
-            c += width
+        if self.stack_lora and x_rows.shape[0] >= 32:
+            per = max(1, 16 // max(fs[0].A.shape[0], 1))  # sub-Linears per pass: groups * rank <= 16
+            while fs and lora_grad_stackable(fs[:per]) and (x_rows.data_ptr() | dy_rows[:, c:].data_ptr()) % 16 == 0:
+                part, fs = fs[:per], fs[per:]
+                width = sum(f.rows for f in part)
+                lora_grad_stacked(x_rows, dy_rows[:, c:c + width], part, self.lora_ws)
+                c += width
+        for f in fs:  # ranks / widths the stacked kernels do not take, tiny row counts
+            lora_grad(x_rows, dy_rows[:, c:c + f.rows], f.A.data, f.B.data, f.dA, f.dB, f.panel.scaling, self.lora_ws)
+            c += f.rows
 
     @staticmethod
     def activation_bytes(cfg, B: int, S: int) -> int:
@@ -641,8 +685,7 @@ class DitTrainer:
         self.dq32.zero_()
         ops.attention_bwd(a["Q"], a["K"], a["V"], g["dOh"], a["lse"], self.delta, self.dq32, g["dKh"], g["dVh"],
                           n_cond=self.nc, mask_mode=p.mask_mode, cross_bias=p.cross_bias, pads=self.pads, n_txt=self.nt)
-        L.check(_lib.lx_cast(self.dq32.data_ptr(), g["dQh"].data_ptr(), self.dq32.numel(), 1, _stream()), "lx_cast")
-        return g["dQh"], g["dKh"], g["dVh"]
+        return self.dq32, g["dKh"], g["dVh"]  # (qkv_post_bwd reads the fp32 dQ directly)
 
     # -- blocks -------------------------------------------------------------------------------------------------------
     def _gemm_cond(self, A, main: PackedLinear, out, ctx: Optional[PackedLinear] = None):
@@ -671,18 +714,30 @@ class DitTrainer:
             self._gemm_cond(O, W[f"double.{i}.out"], a["Y1"], W[f"double.{i}.out_ctx"])
             x1 = self.ckpt_mid[i]
         else:
-            self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
             x1 = self.ckpt_mid[i]  # written in place: the checkpoint IS the forward's buffer
-            gate_residual_fwd(X, a["Y1"], x1, tm, m[2])
+            if self.fuse_gate:  # x1 = X + gate * y from the GEMM epilogue, which also keeps y for the gate gradient
+                self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], x1, mode=L.EPI_GATE_RESIDUAL, residual=X,
+                           gate=m[2], tile_meta=tm, out2=(a["Y1"], 0))
+            else:
+                self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
+                gate_residual_fwd(X, a["Y1"], x1, tm, m[2])
         ln_modulate(x1, a["XN2"], tm, m[3], m[4])
         pre_ff = a["QM"][:, 3 * D:7 * D]
-        self._gemm(a["XN2"], W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], pre_ff)
-        gelu_fwd(pre_ff, a["Hid"])
+        if self.fuse_gelu:  # one launch writes the GELU and, where the pre-activation would go, gelu' for the backward
+            self._gemm(a["XN2"], W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], pre_ff, mode=L.EPI_BIAS_GELU_DUAL,
+                       out2=(a["Hid"], 0))
+        else:
+            self._gemm(a["XN2"], W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], pre_ff)
+            gelu_fwd(pre_ff, a["Hid"])
         if recompute:
             self._gemm_cond(a["Hid"], W[f"double.{i}.ff_down"], a["Y2"], W[f"double.{i}.ff_ctx_down"])
         else:
-            self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], a["Y2"])
-            gate_residual_fwd(x1, a["Y2"], X, tm, m[5])
+            if self.fuse_gate:
+                self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], X, mode=L.EPI_GATE_RESIDUAL,
+                           residual=x1, gate=m[5], tile_meta=tm, out2=(a["Y2"], 0))
+            else:
+                self._gemm(a["Hid"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], a["Y2"])
+                gate_residual_fwd(x1, a["Y2"], X, tm, m[5])
 
     def _double_bwd(self, i, x_in):
         """gradient wrt the block output is in g['dX']; leaves the gradient wrt the block input there."""
@@ -701,8 +756,12 @@ class DitTrainer:
         gate_bwd(g["dX"], a["Y2"], g["dY"], tm, m[5], dm(5))
         self._lora_grads([pfx + "ff.net.2"], a["Hid"][c0:], g["dY"][c0:])
         d_hid = g["dBig"][:, :4 * D]
-        self._gemm(g["dY"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], d_hid, transposed=True)
-        gelu_bwd(pre_ff, d_hid, d_hid)
+        if self.fuse_gelu:  # d_hid = (dY W_down) * gelu' in the GEMM epilogue (pre_ff holds gelu', see _double_fwd)
+            self._gemm(g["dY"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], d_hid, transposed=True,
+                       mode=L.EPI_MUL_AUX, residual=pre_ff)
+        else:
+            self._gemm(g["dY"], W[f"double.{i}.ff_down"], W[f"double.{i}.ff_ctx_down"], d_hid, transposed=True)
+            gelu_bwd(pre_ff, d_hid, d_hid)
         self._gemm(d_hid, W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], g["dXN"], transposed=True)
         ln_modulate_bwd(self.ckpt_mid[i], g["dXN"], g["dX"], g["dX1"], tm, m[4], dm(4), dm(3), self.stats)
         # attention branch
@@ -723,16 +782,26 @@ class DitTrainer:
         X, tm = b["X"], b["tile_meta"]
         m = self._mods_single(i)
         ln_modulate(X, a["XN"], tm, m[0], m[1])
-        self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"])
+        fuse = self.fuse_gelu and D % 256 == 0  # (the same condition as _single_bwd: QM[:, 3D:] holds gelu', not the pre-activation)
+        if fuse:  # columns [3D, 7D) = proj_mlp: its GELU into the concat buffer, gelu' (for the backward) into QM
+            self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"], n_split=3 * D,
+                       seg1=(L.EPI_BIAS_GELU_DUAL, a["QM"], 3 * D), out2=(a["Cat"], D))
+        else:
+            self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"])
         nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
         qkv_post_fwd(a["QM"], self.H, tm, a["Q"], a["K"], a["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
-        gelu_fwd(a["QM"][:, 3 * D:], a["Cat"][:, D:])
+        if not fuse:
+            gelu_fwd(a["QM"][:, 3 * D:], a["Cat"][:, D:])
         self._attention(a["Cat"], a)
         if recompute:
             self._gemm_cond(a["Cat"], W[f"single.{i}.proj_out"], a["Y1"])
         else:
-            self._gemm(a["Cat"], W[f"single.{i}.proj_out"], None, a["Y1"])
-            gate_residual_fwd(X, a["Y1"], X, tm, m[2])
+            if self.fuse_gate:
+                self._gemm(a["Cat"], W[f"single.{i}.proj_out"], None, X, mode=L.EPI_GATE_RESIDUAL, residual=X, gate=m[2],
+                           tile_meta=tm, out2=(a["Y1"], 0))
+            else:
+                self._gemm(a["Cat"], W[f"single.{i}.proj_out"], None, a["Y1"])
+                gate_residual_fwd(X, a["Y1"], X, tm, m[2])
 
     def _single_bwd(self, i, x_in):
         b, a, g, D, W = self.plan.buf, self._act(self.cfg.num_layers + i), self.g, self.D, self.w.named
@@ -745,8 +814,12 @@ class DitTrainer:
         pfx = f"single_transformer_blocks.{i}."
         gate_bwd(g["dX"], a["Y1"], g["dY"], tm, m[2], dm(2))
         self._lora_grads([pfx + "proj_out"], a["Cat"][c0:], g["dY"][c0:])
-        self._gemm(g["dY"], W[f"single.{i}.proj_out"], None, g["dCat"], transposed=True)
-        gelu_bwd(a["QM"][:, 3 * D:], g["dCat"][:, D:], g["dBig"][:, 3 * D:])
+        if self.fuse_gelu and D % 256 == 0:  # columns [D, 5D) of dCat times gelu' (QM[:, 3D:]) = d(proj_mlp pre-activation)
+            self._gemm(g["dY"], W[f"single.{i}.proj_out"], None, g["dCat"], transposed=True, n_split=D,
+                       seg1=(L.EPI_MUL_AUX, g["dBig"], 3 * D), residual=a["QM"])
+        else:
+            self._gemm(g["dY"], W[f"single.{i}.proj_out"], None, g["dCat"], transposed=True)
+            gelu_bwd(a["QM"][:, 3 * D:], g["dCat"][:, D:], g["dBig"][:, 3 * D:])
         dq, dk, dv = self._attention_bwd(g["dCat"], a["Cat"], a)
         nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
         qkv_post_bwd(a["QM"], dq, dk, dv, g["dBig"], self.H, tm, [nq, nq, nq], [nk, nk, nk], b["rope"])
