@@ -124,6 +124,10 @@ typedef struct lx_gemm_desc {
   int32_t col_offset2;
   void* out2; /* bf16 [M, ldo2] */
   int64_t ldo2;
+  /* LX_EPI_QKV, optional (NULL = none): the projection before RMSNorm / RoPE (acc + bias) is also written here, row-major
+   * [M, ld_qkv_pre] with q | k | v in columns [0, 3*heads*128) -- what the training backward differentiates through */
+  void* qkv_pre;
+  int64_t ld_qkv_pre;
 } lx_gemm_desc_t;
 
 int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream);

@@ -60,6 +60,7 @@ class GemmDesc(C.Structure):
         ("rope", c_void_p),
         ("rms_eps", c_float), ("tile_n", c_int32), ("w_dynamic", c_int32),
         ("col_offset2", c_int32), ("out2", c_void_p), ("ldo2", c_int64),
+        ("qkv_pre", c_void_p), ("ld_qkv_pre", c_int64),
     ]
 
 

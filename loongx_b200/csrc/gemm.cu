@@ -505,6 +505,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float x[32];
             ld_acc(taddr, half * 128 + c * 32, r);
               chunk_bias(r, bias, half * 128 + c * 32, x);
+            if (d.qkv_pre != nullptr && row_ok) {  // training forward: the pre-norm projection survives for the backward
+              __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(d.qkv_pre) + (size_t)row * d.ld_qkv_pre + nh + c * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) store_bf16x8(pre + j * 8, &x[8 * j]);
+            }
             if (rmsw != nullptr) {
               const float4* w4 = reinterpret_cast<const float4*>(rmsw + c * 32);
 #pragma unroll
@@ -814,6 +819,8 @@ extern "C" int lx_gemm_bf16(const lx_gemm_desc_t* desc, void* stream) {
       LX_CHECK_ARG(d.seq_total % 128 == 0, "lx_gemm_bf16: seq_total must be a multiple of 128");
       LX_CHECK_ARG(d.heads % 2 == 0, "lx_gemm_bf16: QKV epilogue needs an even head count (256-column tiles)");
       LX_CHECK_ARG(d.M % 128 == 0, "lx_gemm_bf16: QKV epilogue needs M to be a multiple of 128");
+      LX_CHECK_ARG(d.qkv_pre == nullptr || (d.ld_qkv_pre >= d.n_split && d.ld_qkv_pre % 8 == 0),
+                   "lx_gemm_bf16: qkv_pre needs ld_qkv_pre >= 3*heads*128 (multiple of 8)");
     } else {
       LX_CHECK_ARG(g.out != nullptr && g.ldo > 0 && g.ldo % 8 == 0 && g.col_offset % 8 == 0,
                    "lx_gemm_bf16: segment %d needs out / ldo (multiple of 8)", s);

@@ -566,134 +566,160 @@ struct LoraStack {
 // The two projections run as ONE launch (the first CTAs take x, the rest dy), and so do the two reductions: each of the
 // four pieces alone leaves SMs idle on the DiT's shapes (M = the condition rows, 25-100 MB per operand).
 //
-// project_x piece: CTA = 8 warps x 4 rows x one K chunk (partial sums meet in PX through atomics; PX zeroed by the launcher).
-template <int RT>
-__device__ __forceinline__ void lora_stack_project_x(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int K, int kchunk,
-                                                     const LoraStack& p, float* __restrict__ PX, int bx, int by) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = bx * 32 + warp * 4;
-  if (row0 >= M) return;
-  const int c_begin = by * kchunk, c_end = min(K, c_begin + kchunk);
-  float acc[4][RT];
+// Projection: a warp owns a strip of 32 * COLS columns (lane = COLS adjacent columns) and LP_RB rows.  Its factor values
+// F[COLS][RT] are loaded ONCE into registers; the rows then stream through with eight 16-byte (8-byte) loads in flight per
+// lane and nothing else on the load path.  Per row a lane holds RT partial sums; 32 of them (32 / RT rows) are reduced
+// across the warp with a 31-shuffle transposing butterfly (lane l ends up with the total of value l).  The 8 warps of a CTA
+// take 8 neighbouring strips of the same rows and meet in shared memory, so the strip sums reach P with one atomicAdd per
+// (row, output, CTA).  (The first version re-loaded the factors for every 4 rows x 256 columns: 1.4 TB/s, latency-bound.)
+constexpr int LP_RB = 64;     // rows per CTA
+constexpr int LP_WARPS = 8;   // strips per CTA
+
+__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int s = 0; s < 5; ++s) {
+    const int o = 16 >> s;  // lane distance = number of values that survive this stage
+    const bool up = (lane & o) != 0;
 #pragma unroll
-    for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
-  const __nv_bfloat16* xr[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) xr[i] = x + (size_t)min(row0 + i, M - 1) * ldx;
-  constexpr bool kPrefetch = RT <= 8;  // the wide variants have no registers to spare; their FMAs cover the latency
-  uint4 nxt[4];  // the next iteration's rows are in flight while this one is multiplied
-  if constexpr (kPrefetch) {
-    const int c = c_begin + lane * 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) nxt[i] = c < c_end ? __ldg(reinterpret_cast<const uint4*>(xr[i] + c)) : make_uint4(0, 0, 0, 0);
-  }
-  for (int c = c_begin + lane * 8; c < c_end; c += 256) {
-    float z[4][8];
-    if constexpr (kPrefetch) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) unpack8(nxt[i], z[i]);
-      if (c + 256 < c_end) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) nxt[i] = __ldg(reinterpret_cast<const uint4*>(xr[i] + c + 256));
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) unpack8(__ldg(reinterpret_cast<const uint4*>(xr[i] + c)), z[i]);
-    }
-#pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      const float4 f0 = __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c));
-      const float4 f1 = __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c + 4));
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        acc[i][j] += z[i][0] * f0.x + z[i][1] * f0.y + z[i][2] * f0.z + z[i][3] * f0.w + z[i][4] * f1.x + z[i][5] * f1.y +
-                     z[i][6] * f1.z + z[i][7] * f1.w;
+    for (int k = 0; k < o; ++k) {
+      const float send = up ? v[k] : v[k + o];
+      const float keep = up ? v[k + o] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
     }
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      const float sm = warp_sum(acc[i][j]);
-      if (lane == 0 && row0 + i < M) atomicAdd(PX + (size_t)(row0 + i) * RT + j, sm);
-    }
+  return v[0];
 }
 
-// project_dy piece: CTA = 8 warps x RPW rows inside ONE column chunk of one group (chunk divides every group width).
-template <int R, int RPW>
-__device__ __forceinline__ void lora_stack_project_dy(const __nv_bfloat16* __restrict__ dy, int64_t ldy, int M, int chunk,
-                                                      const LoraStack& p, float* __restrict__ PY, int bx, int by) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (bx * 8 + warp) * RPW;
-  if (row0 >= M) return;
-  const int c_begin = by * chunk;
-  int g = 0;
+// rows [row0, row0 + LP_RB) of Z times F -> slot[(row - row0) * RT + j] (this warp's strip only)
+template <int RT, int COLS>
+__device__ __forceinline__ void lora_strip_rows(const __nv_bfloat16* __restrict__ Z, int64_t ldz, int M, int row0, int c,
+                                                bool live, const float (&F)[COLS][RT], float* __restrict__ slot) {
+  constexpr int U = 32 / RT;  // rows per butterfly
+  const int lane = threadIdx.x & 31;
+  for (int rb = 0; rb < LP_RB; rb += 8) {
+    float z[8][COLS];
 #pragma unroll
-  for (int i = 1; i < LORA_STACK_G; ++i) g += (i < p.G && c_begin >= p.col0[i]) ? 1 : 0;
-  // (selects: run-time indexing of kernel-parameter arrays goes through local memory)
-  const float* __restrict__ Bg = g == 0 ? p.B[0] : (g == 1 ? p.B[1] : (g == 2 ? p.B[2] : p.B[3]));
-  const int cg = g == 0 ? 0 : (g == 1 ? p.col0[1] : (g == 2 ? p.col0[2] : p.col0[3]));  // B_g row of dy column c: c - cg
-  float acc[RPW][R];
-#pragma unroll
-  for (int i = 0; i < RPW; ++i)
-#pragma unroll
-    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
-  const int c_end = c_begin + chunk;
-  uint4 nxt[RPW];
-#pragma unroll
-  for (int i = 0; i < RPW; ++i)
-    nxt[i] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)min(row0 + i, M - 1) * ldy + c_begin + lane * 8));
-  for (int c = c_begin + lane * 8; c < c_end; c += 256) {
-    float z[RPW][8];
-#pragma unroll
-    for (int i = 0; i < RPW; ++i) unpack8(nxt[i], z[i]);
-    if (c + 256 < c_end) {
-#pragma unroll
-      for (int i = 0; i < RPW; ++i)
-        nxt[i] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)min(row0 + i, M - 1) * ldy + c + 256));
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat16* src = Z + (size_t)min(row0 + rb + i, M - 1) * ldz + c;
+      if constexpr (COLS == 8) {
+        unpack8(live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0), z[i]);
+      } else {
+        const uint2 u = live ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0, 0);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        z[i][0] = a.x; z[i][1] = a.y; z[i][2] = b.x; z[i][3] = b.y;
+      }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float b[R];
+    for (int u = 0; u < 8 / U; ++u) {
+      float v[32];
 #pragma unroll
-      for (int q = 0; q < R / 4; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)(c + e - cg) * R + q * 4));
-        b[q * 4] = t.x; b[q * 4 + 1] = t.y; b[q * 4 + 2] = t.z; b[q * 4 + 3] = t.w;
-      }
+      for (int q = 0; q < U; ++q)
 #pragma unroll
-      for (int i = 0; i < RPW; ++i)
+        for (int j = 0; j < RT; ++j) {
+          float a = 0.f;
 #pragma unroll
-        for (int j = 0; j < R; ++j) acc[i][j] += z[i][e] * b[j];
+          for (int e = 0; e < COLS; ++e) a += z[u * U + q][e] * F[e][j];
+          v[q * RT + j] = a;
+        }
+      slot[(rb + u * U) * RT + lane] = butterfly32(v, lane);  // value l = (row l / RT, output l % RT)
     }
   }
-  const int RT = p.G * R;
-#pragma unroll
-  for (int i = 0; i < RPW; ++i)
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const float sm = warp_sum(acc[i][j]);
-      if (lane == 0 && row0 + i < M) atomicAdd(PY + (size_t)(row0 + i) * RT + g * R + j, sm);
-    }
 }
 
 struct LoraStackGrid {
-  int x_bx, x_n;   // project / reduce over x: CTAs [0, x_n), (bx, by) = (b % x_bx, b / x_bx)
-  int dy_bx;       // the rest work on dy: b - x_n -> (b % dy_bx, b / dy_bx)
+  int x_bx, x_n;   // CTAs [0, x_n) work on x: (bx, by) = (b % x_bx, b / x_bx); the rest on dy: b - x_n -> (% dy_bx, / dy_bx)
+  int dy_bx;
 };
 
-template <int RT, int R, int RPW>
+__device__ __forceinline__ int lora_group_of(const LoraStack& p, int c) {
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < LORA_STACK_G; ++i) g += (i < p.G && c >= p.col0[i]) ? 1 : 0;
+  return g;
+}
+
+// RT: outputs per row of the x part (G r, 12 rounded up to 16); R: rank = outputs per row of the dy part
+template <int RT, int R>
 __global__ void __launch_bounds__(256, 2) lora_stack_project_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                                                     const __nv_bfloat16* __restrict__ dy, int64_t ldy, int M,
-                                                                    int K, int kchunk, int chunk, const LoraStackGrid gr,
-                                                                    const LoraStack p, float* __restrict__ PX,
-                                                                    float* __restrict__ PY) {
+                                                                    int K, const LoraStackGrid gr, const LoraStack p,
+                                                                    float* __restrict__ PX, float* __restrict__ PY) {
   pdl_wait();
   pdl_launch_dependents();
+  constexpr int RS = RT > R ? RT : R;
+  __shared__ __align__(16) float slots[LP_WARPS][LP_RB * RS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
-  if (b < gr.x_n) lora_stack_project_x<RT>(x, ldx, M, K, kchunk, p, PX, b % gr.x_bx, b / gr.x_bx);
-  else lora_stack_project_dy<R, RPW>(dy, ldy, M, chunk, p, PY, (b - gr.x_n) % gr.dy_bx, (b - gr.x_n) / gr.dy_bx);
+  const int rt_tot = p.G * p.r;  // row stride of PX / PY
+  if (b < gr.x_n) {
+    constexpr int COLS = RT == 16 ? 4 : 8;
+    const int row0 = (b % gr.x_bx) * LP_RB;
+    const int strip = (b / gr.x_bx) * LP_WARPS + warp;
+    const int c = strip * (32 * COLS) + lane * COLS;
+    const bool live = c < K;  // (K is a multiple of 8: a lane is all in or all out)
+    float F[COLS][RT];
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      const bool on = live && j < rt_tot;
+      if constexpr (COLS == 8) {
+        const float4 f0 = on ? __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f1 = on ? __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        F[0][j] = f0.x; F[1][j] = f0.y; F[2][j] = f0.z; F[3][j] = f0.w;
+        F[4][j] = f1.x; F[5][j] = f1.y; F[6][j] = f1.z; F[7][j] = f1.w;
+      } else {
+        const float4 f0 = on ? __ldg(reinterpret_cast<const float4*>(p.a_row[j] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        F[0][j] = f0.x; F[1][j] = f0.y; F[2][j] = f0.z; F[3][j] = f0.w;
+      }
+    }
+    const int n_strip = (K + 32 * COLS - 1) / (32 * COLS);
+    if (strip < n_strip) lora_strip_rows<RT, COLS>(x, ldx, M, row0, live ? c : 0, live, F, slots[warp]);
+    __syncthreads();
+    const int n_w = min(LP_WARPS, n_strip - (b / gr.x_bx) * LP_WARPS);
+    for (int i = threadIdx.x; i < LP_RB * RT; i += 256) {
+      const int row = row0 + i / RT, j = i % RT;
+      if (row >= M || j >= rt_tot) continue;
+      float a = 0.f;
+      for (int w = 0; w < n_w; ++w) a += slots[w][i];
+      atomicAdd(PX + (size_t)row * rt_tot + j, a);
+    }
+  } else {
+    constexpr int COLS = R == 16 ? 4 : 8;
+    const int bb = b - gr.x_n;
+    const int row0 = (bb % gr.dy_bx) * LP_RB;
+    const int strip0 = (bb / gr.dy_bx) * LP_WARPS, strip = strip0 + warp;
+    const int N = p.col0[LORA_STACK_G], n_strip = N / (32 * COLS);  // (every group width is a multiple of 256)
+    const int c = strip * (32 * COLS) + lane * COLS;
+    if (strip < n_strip) {
+      const int g = lora_group_of(p, c);
+      // (selects: run-time indexing of kernel-parameter arrays goes through local memory)
+      const float* __restrict__ Bg = g == 0 ? p.B[0] : (g == 1 ? p.B[1] : (g == 2 ? p.B[2] : p.B[3]));
+      const int cg = g == 0 ? 0 : (g == 1 ? p.col0[1] : (g == 2 ? p.col0[2] : p.col0[3]));  // B_g row of dy column c: c - cg
+      float F[COLS][R];
+#pragma unroll
+      for (int e = 0; e < COLS; ++e)
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)(c + e - cg) * R + q * 4));
+          F[e][q * 4] = t.x; F[e][q * 4 + 1] = t.y; F[e][q * 4 + 2] = t.z; F[e][q * 4 + 3] = t.w;
+        }
+      lora_strip_rows<R, COLS>(dy, ldy, M, row0, c, true, F, slots[warp]);
+    }
+    __syncthreads();
+    const int n_w = min(LP_WARPS, n_strip - strip0);
+    for (int i = threadIdx.x; i < LP_RB * R; i += 256) {
+      const int row = row0 + i / R, j = i % R;
+      if (row >= M) continue;
+      float a = 0.f;
+      for (int w = 0; w < n_w; ++w) {  // neighbouring strips of one group are summed before they go out
+        a += slots[w][i];
+        const int g = lora_group_of(p, (strip0 + w) * (32 * COLS));
+        if (w + 1 == n_w || lora_group_of(p, (strip0 + w + 1) * (32 * COLS)) != g) {
+          atomicAdd(PY + (size_t)row * rt_tot + g * R + j, a);
+          a = 0.f;
+        }
+      }
+    }
+  }
 }
 
 // reduce pieces: CTA = 32 rows x 512 columns of x (4 adjacent columns per thread, 8 rows in flight) or 32 rows x
@@ -1124,38 +1150,34 @@ extern "C" int lx_lora_grad_stacked(const void* x, int64_t ldx, const void* dy, 
   cudaStream_t s = cs(stream);
   LaunchScope scope(KC_ROW, stream, 4.0 * M * ((double)K + N));
   LX_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * (size_t)M * RT, s));
-  // K chunks of project_x: enough CTAs to fill the GPU, at least 512 columns each
-  const int gmx = (M + 31) / 32;
-  int ksplit = 1;
-  while (gmx * ksplit < 592 && K / (ksplit * 2) >= 512 && K % (ksplit * 2 * 256) == 0) ksplit *= 2;
-  const int kchunk = (K / ksplit + 255) / 256 * 256;
-  const int gky = (K + kchunk - 1) / kchunk;
-  // column chunks of project_dy: at least 1024 columns (4 iterations per warp) unless a group is narrower
-  const int rpw = r == 16 ? 2 : 4;
-  const int gmy = (M + 8 * rpw - 1) / (8 * rpw);
-  while (chunk > 1024 && (long long)gmy * (N / chunk) < 592) chunk >>= 1;
-  const LoraStackGrid gp{gmx, gmx * gky, gmy};
-  const unsigned n_project = (unsigned)(gmx * gky + gmy * (N / chunk));
+  // projection launch: CTA = LP_RB rows x LP_WARPS strips of 32 * COLS columns; the x part first, then the dy part
+  const int nrb = (M + LP_RB - 1) / LP_RB;
+  const int rtx = RT == 12 ? 16 : RT;  // (three groups of rank 4 run the 16-output variant with four idle outputs)
+  const int strip_x = 32 * (rtx == 16 ? 4 : 8), strip_y = 32 * (r == 16 ? 4 : 8);
+  const int nsx = (K + strip_x - 1) / strip_x, nsy = N / strip_y;
+  const LoraStackGrid gp{nrb, nrb * ((nsx + LP_WARPS - 1) / LP_WARPS), nrb};
+  const unsigned n_project = (unsigned)(gp.x_n + nrb * ((nsy + LP_WARPS - 1) / LP_WARPS));
+  (void)chunk;
   const int grr = (M + LORA_RROWS - 1) / LORA_RROWS;
   const int cols = r == 16 ? 4 : 8;
   const LoraStackGrid gq{grr, grr * ((K + 511) / 512), grr};
   const unsigned n_reduce = (unsigned)(gq.x_n + grr * ((N + 128 * cols - 1) / (128 * cols)));
   // (the first kernel after the memset is launched stream-ordered, see launch_ordered)
-#define LX_STACK(RTV, RV, RPWV, COLSV)                                                                                       \
-  LX_CUDA(launch_ordered(lora_stack_project_kernel<RTV, RV, RPWV>, dim3(n_project), dim3(256), 0, s, bf(x), ldx, bf(dy), ldy, \
-                         M, K, kchunk, chunk, gp, p, PX, PY));                                                               \
+#define LX_STACK(RTV, RTXV, RV, COLSV)                                                                                        \
+  LX_CUDA(launch_ordered(lora_stack_project_kernel<RTXV, RV>, dim3(n_project), dim3(256), 0, s, bf(x), ldx, bf(dy), ldy, M, K, \
+                         gp, p, PX, PY));                                                                                    \
   LX_CUDA(launch_pdl(lora_stack_reduce_kernel<RTV, RV, COLSV>, dim3(n_reduce), dim3(128), 0, s, bf(x), ldx, bf(dy), ldy, M, K, \
                      gq, p, static_cast<const float*>(PX), static_cast<const float*>(PY)))
   if (r == 4) {
     if (RT == 4) { LX_STACK(4, 4, 4, 8); }
-    else if (RT == 8) { LX_STACK(8, 4, 4, 8); }
-    else if (RT == 12) { LX_STACK(12, 4, 4, 8); }
-    else { LX_STACK(16, 4, 4, 8); }
+    else if (RT == 8) { LX_STACK(8, 8, 4, 8); }
+    else if (RT == 12) { LX_STACK(12, 16, 4, 8); }
+    else { LX_STACK(16, 16, 4, 8); }
   } else if (r == 8) {
-    if (RT == 8) { LX_STACK(8, 8, 4, 8); }
-    else { LX_STACK(16, 8, 4, 8); }
+    if (RT == 8) { LX_STACK(8, 8, 8, 8); }
+    else { LX_STACK(16, 16, 8, 8); }
   } else {
-    LX_STACK(16, 16, 2, 4);
+    LX_STACK(16, 16, 16, 4);
   }
 #undef LX_STACK
   LX_CUDA(cudaGetLastError());

@@ -56,6 +56,7 @@ def gemm(
     residual: Optional[torch.Tensor] = None,
     gate: Optional[Sequence[Optional[torch.Tensor]]] = None,  # per stream [B, *] views (row = batch)
     qkv: Optional[tuple] = None,  # (q, k, v) each [B, H, S, 128]
+    qkv_pre: Optional[torch.Tensor] = None,  # EPI_QKV: also keep the pre-norm projection [M, >= 3 H 128] (training)
     rms_q: Optional[Sequence[Optional[torch.Tensor]]] = None,
     rms_k: Optional[Sequence[Optional[torch.Tensor]]] = None,
     rope: Optional[torch.Tensor] = None,
@@ -113,6 +114,9 @@ def gemm(
             if rms_k is not None and rms_k[i] is not None:
                 d.rms_k[i] = _ptr(rms_k[i])
         d.rope = _ptr(rope)
+        if qkv_pre is not None:
+            assert qkv_pre.dtype == torch.bfloat16 and qkv_pre.stride(-1) == 1
+            d.qkv_pre, d.ld_qkv_pre = _ptr(qkv_pre), qkv_pre.stride(0)
     d.rms_eps = rms_eps
     d.tile_n = tile_n
     d.w_dynamic = int(bool(w_dynamic))

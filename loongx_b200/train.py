@@ -509,12 +509,16 @@ class DitTrainer:
         else:
             self.slabs = [self._slab(i < nl_, z, dev) for i in range(nl_ + ns_)]
         self.g = dict(dX=z(R, D), dX1=z(R, D), dY=z(R, D), dXN=z(R, D), dBig=z(R, 7 * D), dCat=z(R, 5 * D),
-                      dOh=z(B, self.H, S, 128), dQh=z(B, self.H, S, 128), dKh=z(B, self.H, S, 128), dVh=z(B, self.H, S, 128))
+                      dOh=z(B, self.H, S, 128), dKh=z(B, self.H, S, 128), dVh=z(B, self.H, S, 128))
         self.delta = torch.zeros((B, self.H, S), device=dev, dtype=torch.float32)
         self.dq32 = torch.zeros((B, self.H, S, 128), device=dev, dtype=torch.float32)
         self.stats = torch.zeros((R, 2), device=dev, dtype=torch.float32)
         self.lora_ws = torch.zeros((2 * max(R, B) * max(cfg.lora_rank, 16),), device=dev, dtype=torch.float32)
         self.stack_lora = os.environ.get("LX_LORA_STACK", "1") != "0"  # A/B knob: per-factor kernels instead
+        # q/k/v post-processing (RMSNorm, RoPE, head scatter) in the GEMM epilogue, as at inference, with the pre-norm projection
+        # kept (qkv_pre): measured no faster than the separate row kernel (the 256-column tile the epilogue needs costs what
+        # the kernel saves: 450 vs 359 + 83 us per double block at B = 4), so off unless LX_FUSE_QKV=1
+        self.fuse_qkv = os.environ.get("LX_FUSE_QKV", "0") == "1" and self.H % 2 == 0
         self.fuse_gate = os.environ.get("LX_FUSE_GATE", "1") != "0"  # A/B knob: separate gate + residual kernel
         self.fuse_gelu = os.environ.get("LX_FUSE_GELU", "1") != "0"  # A/B knob: separate GELU forward / backward kernels
         self.ckpt = torch.zeros((cfg.num_layers + cfg.num_single_layers, R, D), **bf)
@@ -629,7 +633,7 @@ class DitTrainer:
         """accumulate dA / dB of consecutive sub-Linears `names` whose outputs are adjacent column blocks of dy_rows."""
         fs = [self.factors[n] for n in names]
         c = col0
-        if self.stack_lora and x_rows.shape[0] >= 32:
+        if self.stack_lora:
             per = max(1, 16 // max(fs[0].A.shape[0], 1))  # sub-Linears per pass: groups * rank <= 16
             while fs and lora_grad_stackable(fs[:per]) and (x_rows.data_ptr() | dy_rows[:, c:].data_ptr()) % 16 == 0:
                 part, fs = fs[:per], fs[per:]
@@ -705,9 +709,13 @@ class DitTrainer:
         m = self._mods_double(i)
         pre = a["QM"][:, :3 * D]
         ln_modulate(X, a["XN"], tm, m[0], m[1])
-        self._gemm(a["XN"], W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], pre)
         nq, nk, naq, nak = (W[f"double.{i}.{n}"] for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
-        qkv_post_fwd(pre, self.H, tm, a["Q"], a["K"], a["V"], [naq, nq, nq], [nak, nk, nk], b["rope"])
+        if self.fuse_qkv:  # the inference epilogue (RMSNorm, RoPE, head scatter) + the pre-norm projection kept for the backward
+            self._gemm(a["XN"], W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], None, mode=L.EPI_QKV, tile_meta=tm,
+                       qkv=(a["Q"], a["K"], a["V"]), rms_q=[naq, nq, nq], rms_k=[nak, nk, nk], rope=b["rope"], qkv_pre=pre)
+        else:
+            self._gemm(a["XN"], W[f"double.{i}.qkv"], W[f"double.{i}.qkv_ctx"], pre)
+            qkv_post_fwd(pre, self.H, tm, a["Q"], a["K"], a["V"], [naq, nq, nq], [nak, nk, nk], b["rope"])
         O = a["Cat"][:, :D]
         self._attention(O, a)
         if recompute:
@@ -783,13 +791,19 @@ class DitTrainer:
         m = self._mods_single(i)
         ln_modulate(X, a["XN"], tm, m[0], m[1])
         fuse = self.fuse_gelu and D % 256 == 0  # (the same condition as _single_bwd: QM[:, 3D:] holds gelu', not the pre-activation)
-        if fuse:  # columns [3D, 7D) = proj_mlp: its GELU into the concat buffer, gelu' (for the backward) into QM
-            self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"], n_split=3 * D,
-                       seg1=(L.EPI_BIAS_GELU_DUAL, a["QM"], 3 * D), out2=(a["Cat"], D))
-        else:
-            self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"])
         nq, nk = W[f"single.{i}.norm_q"], W[f"single.{i}.norm_k"]
-        qkv_post_fwd(a["QM"], self.H, tm, a["Q"], a["K"], a["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
+        # columns [0, 3D) = q | k | v, [3D, 7D) = proj_mlp (fused: its GELU into the concat buffer, gelu' for the backward into QM)
+        seg1 = dict(n_split=3 * D, seg1=(L.EPI_BIAS_GELU_DUAL, a["QM"], 3 * D), out2=(a["Cat"], D)) if fuse else \
+            dict(n_split=3 * D, seg1=(L.EPI_BIAS, a["QM"], 3 * D))
+        if self.fuse_qkv:
+            self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, None, mode=L.EPI_QKV, tile_meta=tm, qkv=(a["Q"], a["K"], a["V"]),
+                       rms_q=[nq, nq, nq], rms_k=[nk, nk, nk], rope=b["rope"], qkv_pre=a["QM"], **seg1)
+        else:
+            if fuse:
+                self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"], **seg1)
+            else:
+                self._gemm(a["XN"], W[f"single.{i}.qkv_mlp"], None, a["QM"])
+            qkv_post_fwd(a["QM"], self.H, tm, a["Q"], a["K"], a["V"], [nq, nq, nq], [nk, nk, nk], b["rope"])
         if not fuse:
             gelu_fwd(a["QM"][:, 3 * D:], a["Cat"][:, D:])
         self._attention(a["Cat"], a)
@@ -929,12 +943,9 @@ class DitTrainer:
         pairs = [(silu_c, cast_bf16(self.dmod_dbl), cast_bf16(self.dmod_sgl))]
         if self.latent_lora:
             pairs.append((silu_t, cast_bf16(self.dmod_dbl_img), cast_bf16(self.dmod_sgl_ti)))
-        for x_in, dmd, dms in pairs:
-            for i in range(nl):
-                self._lora_grads([f"transformer_blocks.{i}.norm1.linear"], x_in, dmd[:, i * 6 * self.D:(i + 1) * 6 * self.D])
-            for i in range(ns):
-                self._lora_grads([f"single_transformer_blocks.{i}.norm.linear"], x_in,
-                                 dms[:, i * 3 * self.D:(i + 1) * 3 * self.D])
+        for x_in, dmd, dms in pairs:  # every block's AdaLN Linear reads the same x: stacks of four per pass
+            self._lora_grads([f"transformer_blocks.{i}.norm1.linear" for i in range(nl)], x_in, dmd)
+            self._lora_grads([f"single_transformer_blocks.{i}.norm.linear" for i in range(ns)], x_in, dms)
 
     def _input_grads(self, s) -> None:
         """d loss / d prompt_embeds (through context_embedder, transformer.py:115) and d loss / d pooled_projections

@@ -178,6 +178,70 @@ def test_gemm_qkv_epilogue_and_split_gelu():
     assert (cat[:, :D] == 0).all() and (cat[:, D + F :] == 0).all(), "GELU segment wrote outside its columns"
 
 
+def test_gemm_training_epilogues():
+    """The epilogues the training step adds (model.py:569-729 differentiated by hand): the single block's fused projection
+    with the pre-norm q|k|v kept (qkv_pre) and the MLP segment written twice (gelu' for the backward, GELU for the
+    forward: BIAS_GELU_DUAL); dX through the GELU as one multiply (MUL_AUX); gate + residual that also keeps the pre-gate
+    projection (GATE_RESIDUAL with out2)."""
+    from loongx_b200 import ops, _lib as L
+
+    B, nt, ni, nc, H, K, F = 2, 128, 128, 256, 2, 320, 512
+    D = H * 128
+    S = nt + ni + nc
+    R = B * S
+    meta = ops.make_tile_meta(B, nt, ni, nc, "cuda")
+    A, W = _mk((R, K), 1.0, 20), _mk((3 * D + F, K), 0.06, 21)
+    bias = _mk((3 * D + F,), 0.3, 22, torch.float32)
+    rms_q = [(_mk((128,), 0.2, 23 + i, torch.float32) + 1.0) for i in range(3)]
+    rms_k = [(_mk((128,), 0.2, 26 + i, torch.float32) + 1.0) for i in range(3)]
+    rope = _rope_table(S, 29)
+    q = torch.full((B, H, S, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+    k, v = q.clone(), q.clone()
+    qm = torch.zeros((R, 3 * D + F + 64), device="cuda", dtype=torch.bfloat16)  # [q | k | v pre-norm | gelu' | guard]
+    cat = torch.zeros((R, D + F + 64), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, None, L.EPI_QKV, n_split=3 * D, seg1=(L.EPI_BIAS_GELU_DUAL, qm, 3 * D), out2=(cat, D),
+             tile_meta=meta, qkv=(q, k, v), rms_q=rms_q, rms_k=rms_k, rope=rope, rms_eps=1e-6, qkv_pre=qm)
+    torch.cuda.synchronize()
+    lin = A.float() @ W.float().t() + bias
+    rq, rk, rv = _ref_qkv(lin[:, : 3 * D], meta, B, H, S, rms_q, rms_k, rope, 1e-6)
+    _close(q, rq, what="q")
+    _close(k, rk, what="k")
+    _close(v, rv, what="v")
+    _close(qm[:, : 3 * D], lin[:, : 3 * D], what="qkv_pre")
+    pre = lin[:, 3 * D :].clone().requires_grad_(True)
+    act = torch.nn.functional.gelu(pre, approximate="tanh")
+    (dact,) = torch.autograd.grad(act.sum(), pre)
+    _close(cat[:, D : D + F], act, what="GELU of the dual segment")
+    _close(qm[:, 3 * D : 3 * D + F], dact, what="gelu' of the dual segment")
+    assert (cat[:, :D] == 0).all() and (cat[:, D + F :] == 0).all() and (qm[:, 3 * D + F :] == 0).all()
+    # MUL_AUX: [plain | times the stored factor] like the single block's dCat (proj_out^T)
+    G, Wt = _mk((R, K), 1.0, 31), _mk((256 + F, K), 0.06, 32)
+    d_cat = torch.zeros((R, 256), device="cuda", dtype=torch.bfloat16)
+    d_big = torch.zeros((R, 3 * D + F), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(G, Wt, None, d_cat, L.EPI_BIAS, n_split=256, seg1=(L.EPI_MUL_AUX, d_big, 3 * D), residual=qm)
+    torch.cuda.synchronize()
+    lin2 = G.float() @ Wt.float().t()
+    _close(d_cat, lin2[:, :256], what="plain segment")
+    _close(d_big[:, 3 * D :], lin2[:, 256:] * qm[:, 3 * D : 3 * D + F].float(), what="MUL_AUX segment")
+    assert (d_big[:, : 3 * D] == 0).all()
+    # GATE_RESIDUAL + out2
+    A3, W3 = _mk((R, K), 1.0, 9), _mk((D, K), 0.06, 10)
+    b3 = _mk((D,), 0.5, 11, torch.float32)
+    x = _mk((R, D), 1.0, 12)
+    gates = [_mk((B, 3 * D), 1.0, 13 + i)[:, D : 2 * D] for i in range(3)]
+    x0, y = x.clone(), torch.zeros((R, D + 8), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A3, W3, b3, x, L.EPI_GATE_RESIDUAL, tile_meta=meta, residual=x, gate=gates, out2=(y, 8))
+    torch.cuda.synchronize()
+    lin3 = A3.float() @ W3.float().t() + b3
+    ref = torch.empty_like(lin3)
+    for t, (stream, b, _, _) in enumerate(meta.cpu().tolist()):
+        sl = slice(t * 128, (t + 1) * 128)
+        ref[sl] = x0[sl].float() + gates[stream][b].float()[None, :] * lin3[sl]
+    _close(x, ref, what="gate_residual")
+    _close(y[:, 8:], lin3, what="pre-gate projection (out2)")
+    assert (y[:, :8] == 0).all()
+
+
 @pytest.mark.parametrize("sms", [6, 8, 12, 20])
 def test_gemm_stream_k_head(sms):
     """The stream-K head (partial last wave cut along K, fp32 partial tiles exchanged through the workspace) on a
