@@ -149,7 +149,10 @@ __device__ __forceinline__ void chunk_bias(const uint32_t (&r)[32], const float*
   }
 }
 
-template <int BN, int NCTA>
+// kTrain: the training-step epilogues (BIAS_GELU_DUAL, MUL_AUX, GATE_RESIDUAL + out2, QKV + qkv_pre) are compiled only into
+// this variant; the inference kernels (kTrain = false) are instruction-for-instruction what they were without them (with the
+// branches compiled in, the 255-register epilogue scheduled worse and the edit lost 2.3 %, A/B on one box).
+template <int BN, int NCTA, bool kTrain>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
@@ -432,7 +435,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // one 16-byte fragment per row) loads complete while the tensor pipe is still working on this tile; in the
       // chunk loop below they would be one exposed round trip per 32 columns on the last tile of every CTA.
       uint4 rres[BN / 8];
-      if ((mode == LX_EPI_GATE_RESIDUAL || mode == LX_EPI_MUL_AUX) && row_ok) {
+      if ((mode == LX_EPI_GATE_RESIDUAL || (kTrain && mode == LX_EPI_MUL_AUX)) && row_ok) {
         const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual) + (size_t)row * d.ldr +
                                    (n0 - seg_n0 + seg.col_offset);
 #pragma unroll
@@ -505,7 +508,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float x[32];
             ld_acc(taddr, half * 128 + c * 32, r);
               chunk_bias(r, bias, half * 128 + c * 32, x);
-            if (d.qkv_pre != nullptr && row_ok) {  // training forward: the pre-norm projection survives for the backward
+            if (kTrain && d.qkv_pre != nullptr && row_ok) {  // training forward: the pre-norm projection survives for the backward
               __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(d.qkv_pre) + (size_t)row * d.ld_qkv_pre + nh + c * 32;
 #pragma unroll
               for (int j = 0; j < 4; ++j) store_bf16x8(pre + j * 8, &x[8 * j]);
@@ -540,14 +543,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-      } else if (mode == LX_EPI_GATE_RESIDUAL || mode == LX_EPI_MUL_AUX) {
+      } else if (mode == LX_EPI_GATE_RESIDUAL || (kTrain && mode == LX_EPI_MUL_AUX)) {
         // MUL_AUX (training, dX through an activation): the "residual" rows hold the activation's derivative, written by
         // the forward's BIAS_GELU_DUAL epilogue -- one multiply per element here; evaluating gelu' in this fully unrolled
         // branch (255 registers, no room for instruction-level parallelism) cost +45 % on the whole GEMM
-        const bool mul_aux = mode == LX_EPI_MUL_AUX;
+        const bool mul_aux = kTrain && mode == LX_EPI_MUL_AUX;
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo;
         // GATE_RESIDUAL with out2 (training forward): the pre-gate projection y = acc + bias survives for the gate gradient
-        __nv_bfloat16* y_out = (!mul_aux && d.out2 != nullptr)
+        __nv_bfloat16* y_out = (kTrain && !mul_aux && d.out2 != nullptr)
                                    ? reinterpret_cast<__nv_bfloat16*>(d.out2) + (size_t)row * d.ldo2 + (d.col_offset2 - seg_n0)
                                    : nullptr;
 #pragma unroll
@@ -597,7 +600,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float x[32];
           ld_acc(taddr, c * 32, r);
           chunk_bias(r, bias, c * 32, x);
-          if (mode == LX_EPI_BIAS_GELU_DUAL) {  // training forward: gelu' goes to `out` for the backward's MUL_AUX epilogue
+          if (kTrain && mode == LX_EPI_BIAS_GELU_DUAL) {  // training forward: gelu' goes to `out` for the backward's MUL_AUX epilogue
             float gp[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) gelu_tanh_pair(x[j], x[j], gp[j]);
@@ -623,7 +626,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (n + j * 4 < d.N)
                   *reinterpret_cast<float4*>(out + j * 4) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             } else {
-              __nv_bfloat16* out = mode == LX_EPI_BIAS_GELU_DUAL
+              __nv_bfloat16* out = (kTrain && mode == LX_EPI_BIAS_GELU_DUAL)
                                        ? reinterpret_cast<__nv_bfloat16*>(d.out2) + (size_t)row * d.ldo2 + (n - seg_n0 + d.col_offset2)
                                        : reinterpret_cast<__nv_bfloat16*>(seg.out) + (size_t)row * seg.ldo + oc;
 #pragma unroll
@@ -676,8 +679,8 @@ static int g_fake_sms = 0;  // lx_debug_gemm_sms(n): pretend the device has n SM
 static long long g_raster_budget_mb = 40;  // L2 share given to the A rows of one raster band (the 126 MB L2 is two 63 MB
                                            // partitions; 40 MB measured best end to end at B = 4: -7.6 % per denoise step)
 
-template <int BN, int NCTA>
-int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
+template <int BN, int NCTA, bool kTrain>
+int launch_gemm_t(const lx_gemm_desc_t& d, void* stream) {
   CUtensorMap tmA, tmB[3];
   GemmParams p;
   p.d = d;
@@ -704,7 +707,7 @@ int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, NCTA, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TileCfg<BN, NCTA>::SMEM));
     attr_set = true;
   }
@@ -754,9 +757,16 @@ int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  LX_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, NCTA>, tmA, tmB[0], tmB[1], tmB[2], p));
+  LX_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, NCTA, kTrain>, tmA, tmB[0], tmB[1], tmB[2], p));
   LX_CUDA(cudaGetLastError());
   return LX_OK;
+}
+
+template <int BN, int NCTA>
+int launch_gemm(const lx_gemm_desc_t& d, void* stream) {
+  bool train = d.out2 != nullptr || d.qkv_pre != nullptr;
+  for (int s = 0; s < 2; ++s) train = train || d.seg[s].mode == LX_EPI_BIAS_GELU_DUAL || d.seg[s].mode == LX_EPI_MUL_AUX;
+  return train ? launch_gemm_t<BN, NCTA, true>(d, stream) : launch_gemm_t<BN, NCTA, false>(d, stream);
 }
 
 // N tile that minimises (number of waves) x (tile width); ties go to the wider tile.  With the stream-K head available
