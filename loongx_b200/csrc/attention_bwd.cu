@@ -194,6 +194,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t acc = it > 0 ? 1u : 0u;
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
+        // dQ_i = dS K_j FIRST: A = dS^T tile [key rows][query cols] read MN-major (M = queries), k-slice = 16 key rows.
+        // Its read-back / reduction by the compute threads then runs under the dV / dK products below instead of after
+        // them (the tensor pipe executes in issue order: dq_full used to fire only when all three products were done).
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tm_dP, ds_mn + (uint64_t)(kk * (2048 >> 4)), k_mn + (uint64_t)(kk * (2048 >> 4)), idesc_mm,
+                  kk != 0 ? 1u : 0u);
+        umma_commit(dq_full);
         // dV += P^T dO_i : k-slice kk = 16 queries = 8 packed TMEM columns / 16 rows (2048 B) of the dO tile
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
@@ -205,12 +213,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int kk = 0; kk < 8; ++kk)
           umma_ts(tm_dK, tm_S + 64 + kk * 8, qm + (uint64_t)(kk * (2048 >> 4)), idesc_tm, kk == 0 ? acc : 1u);
         umma_commit(&q_empty[st]);
-        // dQ_i = dS K_j : A = dS^T tile [key rows][query cols] read MN-major (M = queries), k-slice = 16 key rows
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tm_dP, ds_mn + (uint64_t)(kk * (2048 >> 4)), k_mn + (uint64_t)(kk * (2048 >> 4)), idesc_mm,
-                  kk != 0 ? 1u : 0u);
-        umma_commit(dq_full);
         if (it + 1 < n_it) {
           issue_s(it + 1);
           mbar_wait(dq_read, it & 1);  // dQ_i has left TMEM cols [128,256)

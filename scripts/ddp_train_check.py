@@ -46,10 +46,14 @@ dist.all_gather(gathered, local_grad)
 mean = torch.stack(gathered).mean(0)
 # the product path: autograd node -> native backward -> ONE all-reduce(mean) of the flat bucket
 loss.backward()
-if BRAIN:
-    got = torch.cat([p.grad.flatten() for p in tr.parameters()] +
-                    [(torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).flatten() if p.grad is not None
-                     else torch.zeros(p.numel() * (2 if p.is_complex() else 1), device=dev) for p in CB.trainable_parameters(m)])
+if BRAIN:  # what autograd left on the parameters, laid out like the flat bucket (16-byte aligned encoder slices)
+    enc_params = CB.trainable_parameters(m)
+    layout, total = CB.grad_layout(enc_params)
+    enc_flat = torch.zeros(total, device=dev)
+    for p, (o, n) in zip(enc_params, layout):
+        if p.grad is not None:
+            enc_flat[o:o + n] = (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).flatten()
+    got = torch.cat([p.grad.flatten() for p in tr.parameters()] + [enc_flat])
 else:
     got = torch.cat([p.grad.flatten() for p in tr.parameters()])
 err = ((got - mean).norm() / mean.norm()).item()

@@ -447,6 +447,11 @@ def test_ddp_gradient_allreduce_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-2000:], out.stderr[-2000:])
     assert out.returncode == 0
+    # with the CS3 / DGF conditioning: the bucket carries the encoder gradients too (model.py:656-701, train.py:181-183)
+    cmd[cmd.index("29517")] = "29527"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, LX_DDP_BRAIN="1"))
+    print(out.stdout[-2000:], out.stderr[-2000:])
+    assert out.returncode == 0
 
 
 def test_micro_batched_step_equals_full_batch():
