@@ -12,9 +12,9 @@
 //       dV_j += P^T  dO_i           TS   (A from TMEM, B = dO_i as MN-major smem operand)   -> TMEM cols [256,384)
 //       dK_j += dS^T Q_i            TS   (B = Q_i MN-major)                                 -> TMEM cols [384,512)
 //       dQ_i  = dS   K_j            SS   (A = the dS^T tile read MN-major, B = K_j MN-major) -> TMEM cols [128,256),
-//               read back by the compute threads, staged in shared memory and added to the fp32 dQ accumulator in
-//               global memory by the TMA unit (cp.reduce.async.bulk.tensor .add, one bulk op per 128 x 16 chunk, staging
-//               tiles double-buffered so the threads do not wait for the bulk reads)
+//               issued FIRST of the three, so that its read-back by the compute threads runs under dV / dK; staged in
+//               shared memory in one round per iteration (half of it in the then-dead dS^T tile) and added to the fp32 dQ
+//               accumulator in global memory by the TMA unit (cp.reduce.async.bulk.tensor .add, 128 x 16 chunks)
 //   warp 0: TMA producer (K_j, V_j once; Q_i through a 2-stage ring, dO_i single-buffered: 192 KB of shared memory)
 //   warp 1: tcgen05.mma issuer        warps 2..9: compute, two threads per key row (TMEM lane quarter = warp & 3,
 //           64 of the 128 query columns each)
@@ -43,7 +43,9 @@ struct AttnBwdParams {
   int B, H, S, n_cond, mask_mode;
   float scale, scale_log2, bias_log2;
   int stream_end[3], pad[3];  // ragged streams (see lx_attn_desc_t): padding keys get P = dS = 0
-  int dbg_flags;  // development aid: bit 0 = skip the dQ reduction (timing experiments only)
+  int dbg_flags;  // development aid: bit 0 = skip the dQ reduction (timing experiments only); bit 1 = phase clocks -> prof
+  long long* prof;  // [CTAs][4]: clocks the first compute thread spent waiting for S^T / dP^T, in the softmax phase, waiting
+                    // for dQ, in the dQ read-back phase (lx_attention_bwd_debug_prof)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -237,6 +239,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if ((j + 1) * 128 == p.stream_end[s3]) nvalid -= p.pad[s3];
     const float keep = r < nvalid ? 1.0f : 0.0f;
     const bool has_pad = nvalid < 128;
+    // this thread's per-query statistic: lse (threads 0..127) or delta (128..255) of query tid % 128 of the current tile
+    const float* stat_src = (tid < 128 ? p.lse : p.delta) + head_row0 + (tid & 127);
+    float stat = n_it > 0 ? stat_src[(size_t)q_begin * 128] : 0.f;
+    const bool prof_on = (p.dbg_flags & 2) && p.prof != nullptr && threadIdx.x == 64;
+    long long pc[4] = {0, 0, 0, 0}, t_prev = prof_on ? clock64() : 0;
+    auto lap = [&](int k) {
+      if (prof_on) {
+        const long long t = clock64();
+        pc[k] += t - t_prev;
+        t_prev = t;
+      }
+    };
     for (int it = 0; it < n_it; ++it) {
       const int qi = q_begin + it;
       const bool cross = use_bias && (k_is_cond != (qi >= n_rest));
@@ -244,14 +258,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // per-query constants of this iteration, interleaved so that one 16-byte shared-memory load serves two queries:
       //   .x = bias - lse_q (log2 units)     .y = scale * delta_q
       float2* st_q = reinterpret_cast<float2*>(sStat + (it & 1) * 256);
-      if (tid < 128) st_q[tid].x = bias - p.lse[head_row0 + qi * 128 + tid];
-      else st_q[tid - 128].y = p.scale * p.delta[head_row0 + qi * 128 + tid - 128];
+      if (tid < 128) st_q[tid].x = bias - stat;
+      else st_q[tid - 128].y = p.scale * stat;
+      // the next iteration's statistic is requested now and consumed a whole iteration later (this global load used to sit
+      // at the top of every iteration: one exposed L2 round trip per (key tile, query tile) pair)
+      if (it + 1 < n_it) stat = stat_src[(size_t)(qi + 1) * 128];
+      lap(3);  // (tail of the previous read-back phase + staging of the statistics)
       mbar_wait(sp_full, it & 1);
+      lap(0);
       tc_fence_after();
       uint32_t s[64];
       tmem_ld_32x32b_x64(tm_S + lane_off + half * 64, s);
       // every thread has its S^T values in registers (and the statistics are staged) before anyone overwrites the
-      // S^T columns with packed P^T / dS^T
+      // S^T columns with packed P^T / dS^T; and the bulk reads of the two dQ chunks staged in the dS^T tile are complete
+      if (threadIdx.x == 64 || threadIdx.x == 192) tma_store_wait_read<2>();
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -290,43 +310,51 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
-      // dQ_i (lanes = query rows, this group's 64 of the 128 head dims): TMEM -> registers -> 128B-swizzled staging tile
-      // -> ONE cp.reduce.async.bulk.tensor (+=) per 128 x 32 chunk; the L2 does the fp32 adds on whole lines instead of
-      // 4096 scattered 16-byte atomics per tile
+      lap(1);
       mbar_wait(dq_full, it & 1);
+      lap(2);
       tc_fence_after();
-      uint8_t* slots = sdQ + half * 2 * AB_DQ_SLOT;  // this group's two 128 x 16 staging tiles
+      // dQ_i (lanes = query rows, this group's 64 of the 128 head dims): TMEM -> registers -> four 128 x 16 fp32 staging tiles
+      // (64-byte swizzle) -> four cp.reduce.async.bulk.tensor (+=): the L2 does the fp32 adds on whole lines.  ONE staging
+      // round per iteration: chunks 0, 1 go into the dS^T tile, which is dead between the dQ product (dq_full) and the next
+      // softmax phase, chunks 2, 3 into the group's own two slots; the next softmax phase only waits for the bulk reads of
+      // chunks 0, 1 (issued first) before it overwrites the tile.  History: 8 KB at a time through two slots = four rounds
+      // of wait / barrier / store / fence / barrier per iteration, 3000 of 5900 clk; the whole half in the dS^T tile = the
+      // next softmax phase waits 2100 clk for 32 KB of reductions to drain.
       const bool issuer = (threadIdx.x == 64 + 128 * half);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tm_dP + lane_off + half * 64 + c * 32, o);
-        if (c == 1) {  // this thread's part of dQ_i has left tensor memory
-          tc_fence_before();
-          mbar_arrive(dq_read);
-        }
+      uint32_t o[64];
+      tmem_ld_32x32b_x64(tm_dP + lane_off + half * 64, o);
+      tc_fence_before();
+      mbar_arrive(dq_read);  // this thread's part of dQ_i has left tensor memory
+      if (issuer) tma_store_wait_read<0>();  // the previous iteration's bulk reads of the staging tiles (a whole iteration ago)
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      if (!(p.dbg_flags & 1)) {
 #pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {  // two 16-column chunks, alternating staging tiles
-          uint8_t* slot = slots + hc * AB_DQ_SLOT;
-          // the bulk read issued from this tile two chunks ago must be complete; the most recent one may still be in flight
-          if (issuer) tma_store_wait_read<1>();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-          if (!(p.dbg_flags & 1)) {
+        for (int t = 0; t < 4; ++t) {
+          uint8_t* slot = (t < 2 ? sdS : sdQ) + (half * 2 + (t & 1)) * AB_DQ_SLOT;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const uint32_t a = static_cast<uint32_t>(r * 64 + ch * 16);
-              *reinterpret_cast<uint4*>(slot + (a ^ (((a >> 7) & 3u) << 4))) =  // 64-byte swizzle of the TMA tile
-                  make_uint4(o[hc * 16 + 4 * ch], o[hc * 16 + 4 * ch + 1], o[hc * 16 + 4 * ch + 2], o[hc * 16 + 4 * ch + 3]);
-            }
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-          if (issuer && !(p.dbg_flags & 1)) {
-            tma_reduce_add_2d(&tmdQ, slot, half * 64 + c * 32 + hc * 16, head_row0 + qi * 128);
-            tma_store_commit();
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t a = static_cast<uint32_t>(r * 64 + ch * 16);
+            *reinterpret_cast<uint4*>(slot + (a ^ (((a >> 7) & 3u) << 4))) =  // 64-byte swizzle of the TMA tile
+                make_uint4(o[t * 16 + 4 * ch], o[t * 16 + 4 * ch + 1], o[t * 16 + 4 * ch + 2], o[t * 16 + 4 * ch + 3]);
           }
         }
       }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      if (issuer && !(p.dbg_flags & 1)) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // one bulk group per chunk: the softmax phase waits for the first two only
+          tma_reduce_add_2d(&tmdQ, (t < 2 ? sdS : sdQ) + (half * 2 + (t & 1)) * AB_DQ_SLOT, half * 64 + t * 16,
+                            head_row0 + qi * 128);
+          tma_store_commit();
+        }
+      }
+    }
+    lap(3);
+    if (prof_on) {
+      long long* dst = p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 4;
+      for (int k = 0; k < 4; ++k) dst[k] = pc[k];
     }
     if (threadIdx.x == 64 || threadIdx.x == 192) tma_store_wait_read<0>();  // staging must outlive the last bulk read
     // epilogue: dV_j, dK_j (lanes = key rows, this thread's 64 head dims) -> bf16 rows
@@ -411,6 +439,9 @@ extern "C" int lx_attention_bwd_prep(const void* d_out_rows, int64_t ld_do, cons
 
 static int g_attn_bwd_dbg = 0;
 extern "C" void lx_attention_bwd_debug_flags(int flags) { g_attn_bwd_dbg = flags; }
+static long long* g_attn_bwd_prof = nullptr;
+// development aid: device buffer of [B * H * S/128][4] int64 for the phase clocks (flags bit 1); NULL switches it off
+extern "C" void lx_attention_bwd_debug_prof(long long* buf) { g_attn_bwd_prof = buf; }
 
 extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
   LX_CHECK_ARG(desc != nullptr, "lx_attention_bwd: null descriptor");
@@ -444,6 +475,7 @@ extern "C" int lx_attention_bwd(const lx_attn_bwd_desc_t* desc, void* stream) {
     p.pad[s3] = d.pad[s3];
   }
   p.dbg_flags = g_attn_bwd_dbg;
+  p.prof = g_attn_bwd_prof;
   static bool attr_set = false;
   if (!attr_set) {
     LX_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));

@@ -25,4 +25,16 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 4]:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"B={B} flags={flags}: {ms:.3f} ms  {10.0 * B * H * S * S * 128 / ms / 1e9:.0f} TFLOP/s", flush=True)
+    # phase clocks of the first compute thread of every CTA (flags bit 1)
+    import ctypes
+    prof = torch.zeros(B * H * (S // 128), 4, dtype=torch.int64, device="cuda")
+    L.lib.lx_attention_bwd_debug_prof.argtypes = [ctypes.c_void_p]
+    L.lib.lx_attention_bwd_debug_prof(prof.data_ptr())
+    L.lib.lx_attention_bwd_debug_flags(2)
+    ops.attention_bwd(q, k, v, d_o, lse, delta, dq, dk, dv, n_cond=1024)
+    torch.cuda.synchronize()
     L.lib.lx_attention_bwd_debug_flags(0)
+    L.lib.lx_attention_bwd_debug_prof(None)
+    m = prof.double().mean(0) / (S // 128)
+    print(f"B={B} clocks per (key tile, query tile) iteration, CTA mean: wait S^T/dP^T {m[0]:.0f}, softmax phase {m[1]:.0f}, "
+          f"wait dQ {m[2]:.0f}, dQ read-back {m[3]:.0f}, total {m.sum():.0f}", flush=True)
