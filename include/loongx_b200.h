@@ -542,6 +542,9 @@ int lx_lora_grad_stacked(const void* x, int64_t ldx, const void* dy, int64_t ldy
 /* out = bf16(W + s B A): the merged panel of the LoRA-active row group, rebuilt after every optimizer step. */
 int lx_lora_merge(const void* W, int64_t ldw, const float* A, const float* Bw, void* out, int64_t ldo, int32_t N, int32_t K,
                   int32_t r, float scaling, void* stream);
+/* the same merge writing the K-major copy too: outT[k, n] = out[n, k] (one pass over W) */
+int lx_lora_merge_t(const void* W, int64_t ldw, const float* A, const float* Bw, void* out, int64_t ldo, void* outT,
+                    int64_t ldt, int32_t N, int32_t K, int32_t r, float scaling, void* stream);
 /* out[c, r] = in[r, c] (bf16): K-major W^T panels for the dX GEMMs. */
 int lx_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols, void* stream);
 /* Rectified-flow objective (model.py:590-594, 726): x_t = (1 - t_b) x_0 + t_b x_1;

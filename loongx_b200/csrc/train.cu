@@ -859,6 +859,71 @@ __global__ void lora_merge_kernel(const __nv_bfloat16* __restrict__ W, int64_t l
   *reinterpret_cast<uint32_t*>(out + (size_t)n * ldo + k) = pack_bf16(w.x + scaling * ax, w.y + scaling * ay);
 }
 
+// The same merge writing BOTH panels in one pass over W: out[n, k] and outT[k, n] (the K-major copy the dX GEMMs multiply
+// by).  CTA = 64 x 64 tile, 256 threads; the merged tile goes out row-major directly and transposed through shared memory
+// (16-byte stores on both sides).  After every optimizer step all 343 LoRA targets are rebuilt: W is read once (24 GB for
+// FLUX.1-dev) instead of merge (read W, write out) + transpose (read out, write outT).
+constexpr int LMT = 64;
+__global__ void __launch_bounds__(256) lora_merge_t_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw,
+                                                           const float* __restrict__ A, const float* __restrict__ Bw,
+                                                           __nv_bfloat16* __restrict__ out, int64_t ldo,
+                                                           __nv_bfloat16* __restrict__ outT, int64_t ldt, int N, int K, int r,
+                                                           float scaling) {
+  pdl_wait();  // PDL: inputs are the previous kernel's outputs
+  pdl_launch_dependents();
+  __shared__ float sA[LORA_MAX_R][LMT];        // A[j, k0 + c]
+  __shared__ float sB[LMT][LORA_MAX_R + 1];    // B[n0 + row, j]
+  __shared__ __align__(16) __nv_bfloat16 sT[LMT][LMT + 8];  // merged tile [row][swizzled col] (+8: rows stay 16-byte aligned)
+  const int n0 = blockIdx.y * LMT, k0 = blockIdx.x * LMT;
+  for (int i = threadIdx.x; i < r * LMT; i += 256) {
+    const int j = i / LMT, c = i % LMT;
+    sA[j][c] = (k0 + c < K) ? A[(size_t)j * K + k0 + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < LMT * r; i += 256) {
+    const int row = i / r, j = i % r;
+    sB[row][j] = (n0 + row < N) ? Bw[(size_t)(n0 + row) * r + j] : 0.f;
+  }
+  __syncthreads();
+  // thread -> (row, 8-column chunk): 64 rows x 8 chunks = 512 slots, two per thread
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int slot = threadIdx.x + h * 256, row = slot >> 3, c8 = (slot & 7) * 8;
+    const int n = n0 + row, k = k0 + c8;
+    float v[8];
+    if (n < N && k < K) {
+      ld8(W + (size_t)n * ldw + k, v);
+      float ba[8];  // (B A)[n, k..k+8) summed in the order of lora_merge_kernel: the two kernels agree bit for bit
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ba[e] = 0.f;
+      for (int j = 0; j < r; ++j) {
+        const float b = sB[row][j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ba[e] = fmaf(b, sA[j][c8 + e], ba[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(scaling, ba[e], v[e]);
+      st8(out + (size_t)n * ldo + k, v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+    st8(&sT[row][c8 ^ (((row >> 3) & 7) << 3)], v);  // 8-column chunks XOR-swizzled by the row octet: conflict-free transposed reads
+  }
+  __syncthreads();
+  // transposed write: thread -> (column of the tile = row of outT, 8-row chunk)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int slot = threadIdx.x + h * 256, col = slot >> 3, r8 = (slot & 7) * 8;
+    const int k = k0 + col, n = n0 + r8;
+    if (k < K && n < N) {
+      __nv_bfloat16 t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = sT[r8 + e][(((col >> 3) ^ ((r8 >> 3) & 7)) << 3) | (col & 7)];
+      *reinterpret_cast<uint4*>(outT + (size_t)k * ldt + n) = *reinterpret_cast<const uint4*>(t);
+    }
+  }
+}
+
 // out[c, r] = in[r, c]   (32x32 shared-memory tiles; builds the K-major W^T panels the dX GEMMs multiply by)
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out,
                                       int64_t ld_out, int rows, int cols) {
@@ -1191,6 +1256,19 @@ extern "C" int lx_lora_merge(const void* W, int64_t ldw, const float* A, const f
   const int64_t n = (int64_t)N * (K / 2);
   LaunchScope scope(KC_ROW, stream, 4.0 * N * K);
   launch_pdl(lora_merge_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cs(stream), bf(W), ldw, A, Bw, bf(out), ldo, N, K, r, scaling);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_lora_merge_t(const void* W, int64_t ldw, const float* A, const float* Bw, void* out, int64_t ldo, void* outT,
+                               int64_t ldt, int32_t N, int32_t K, int32_t r, float scaling, void* stream) {
+  LX_CHECK_ARG(W && A && Bw && out && outT && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0 && r > 0 && r <= LORA_MAX_R &&
+                   ldw % 8 == 0 && ldo % 8 == 0 && ldt % 8 == 0,
+               "lx_lora_merge_t: bad arguments (N, K and the strides multiples of 8, r <= %d)", LORA_MAX_R);
+  LX_CHECK_ARG(((uintptr_t)W | (uintptr_t)out | (uintptr_t)outT) % 16 == 0, "lx_lora_merge_t: panels must be 16-byte aligned");
+  LaunchScope scope(KC_ROW, stream, 6.0 * N * K);
+  launch_pdl(lora_merge_t_kernel, dim3((K + LMT - 1) / LMT, (N + LMT - 1) / LMT), dim3(256), 0, cs(stream), bf(W), ldw, A, Bw,
+             bf(out), ldo, bf(outT), ldt, N, K, r, scaling);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

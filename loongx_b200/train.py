@@ -205,6 +205,18 @@ def lora_grad_stacked(x, dy, factors, workspace):
                                       workspace.data_ptr(), _stream()), "lx_lora_grad_stacked")
 
 
+_lib.lx_lora_merge_t.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32,
+                                 c_int32, C.c_float, c_void_p]
+
+
+def lora_merge_t(W, A, Bw, out, outT, scaling):
+    """out = bf16(W + s B A) and outT = out^T in one pass (outT: a [K, N] column view of the K-major panel)."""
+    N, K = W.shape
+    assert out.shape == (N, K) and outT.shape == (K, N) and outT.stride(1) == 1 and out.stride(1) == 1
+    L.check(_lib.lx_lora_merge_t(W.data_ptr(), W.stride(0), A.data_ptr(), Bw.data_ptr(), out.data_ptr(), out.stride(0),
+                                 outT.data_ptr(), outT.stride(0), N, K, A.shape[0], float(scaling), _stream()), "lx_lora_merge_t")
+
+
 def lora_merge(W, A, Bw, out, scaling):
     N, K = W.shape
     L.check(_lib.lx_lora_merge(W.data_ptr(), W.stride(0), A.data_ptr(), Bw.data_ptr(), out.data_ptr(), out.stride(0), N, K,
@@ -331,10 +343,15 @@ class LoraFactor:
     def remerge(self, lora_scale: float = 1.0):
         """w_lora[rows] = bf16(W + lora_scale * s B A) (+ the transposed panel) after the factors changed."""
         p = self.panel
-        lora_merge(p.w[self.row0:self.row0 + self.rows], self.A.data, self.B.data,
-                   p.w_lora[self.row0:self.row0 + self.rows], p.scaling * lora_scale)
-        if p.w_loraT is not None:
-            transpose(p.w_lora[self.row0:self.row0 + self.rows], p.w_loraT[:, self.row0:self.row0 + self.rows])
+        w, wl = p.w[self.row0:self.row0 + self.rows], p.w_lora[self.row0:self.row0 + self.rows]
+        wt = p.w_loraT[:, self.row0:self.row0 + self.rows] if p.w_loraT is not None else None
+        if wt is not None and self.rows % 8 == 0 and w.shape[1] % 8 == 0 and (w.data_ptr() | wl.data_ptr() | wt.data_ptr()) % 16 == 0 \
+                and w.stride(0) % 8 == 0 and wl.stride(0) % 8 == 0 and wt.stride(0) % 8 == 0:
+            lora_merge_t(w, self.A.data, self.B.data, wl, wt, p.scaling * lora_scale)  # both panels in one pass over W
+        else:
+            lora_merge(w, self.A.data, self.B.data, wl, p.scaling * lora_scale)
+            if wt is not None:
+                transpose(wl, wt)
         self.shared.merged = (self.A._version, self.B._version)
 
     def stale(self) -> bool:

@@ -198,6 +198,11 @@ def test_lora_grad_merge_transpose(M, K, N, r):
     T.lora_merge(W, A, Bw, out, s)
     assert torch.equal(out, torch.addmm(W.float(), Bw, A, alpha=s).bfloat16()) or _rel(out, W.float() + s * Bw @ A) < 3e-3
     assert torch.equal(T.transpose(W), W.t().contiguous())
+    if N % 8 == 0 and K % 8 == 0:  # both panels in one pass (what LoraFactor.remerge uses): bit-identical to merge + transpose
+        big, bigT = torch.zeros((N + 16, K), device=DEV, dtype=torch.bfloat16), torch.zeros((K, N + 16), device=DEV, dtype=torch.bfloat16)
+        T.lora_merge_t(W, A, Bw, big[8:8 + N], bigT[:, 8:8 + N], s)
+        assert torch.equal(big[8:8 + N], out) and torch.equal(bigT[:, 8:8 + N], out.t())
+        assert (big[:8] == 0).all() and (big[8 + N:] == 0).all() and (bigT[:, :8] == 0).all() and (bigT[:, 8 + N:] == 0).all()
 
 
 @pytest.mark.parametrize("M,K,widths,r", [(4096 + 40, 768, (256, 256, 256), 4), (300, 256, (512, 256, 256, 1024), 4),
