@@ -18,9 +18,14 @@ This file restates its published algorithm:
   models/attention_processor.py         Attention(heads=1, dim_head=C, group_norm 32, residual_connection=True) over the
                                         H*W positions
   image_processor.py                    VaeImageProcessor.normalize / denormalize / pt_to_numpy / numpy_to_pil
-PARITY UNPINNED for this third-party arithmetic: there is no diffusers here to execute and the reference holds no
-golden vectors for it; parity of the CUDA path is anchored on this restatement (tests/test_vae_gpu.py) and on the
-closed-form checks in tests/test_vae_cpu.py.
+PINNED (round 2): diffusers itself is not in this image and the reference holds no golden vectors for it, but the image
+ships an independent executable implementation of the same network -- Black Forest Labs' FLUX `AutoEncoder`
+(torchtitan/experiments/flux/model/autoencoder.py: ch 128, ch_mult (1, 2, 4, 4), z 16, scale 0.3611, shift 0.1159; the
+checkpoint layout diffusers converts FLUX.1-dev's VAE from).  tests/golden/make_vae_bfl_golden.py maps this file's
+diffusers-named parameters onto that module and writes tests/golden/vae_bfl_v1.npz; tests/test_vae_cpu.py replays the
+fixture and re-runs the module live at the fixture's width and at FLUX.1-dev's full widths: encoder moments, sampled +
+shifted + scaled latents and the decoded image agree to 1e-6 relL2.  What stays restated from memory is only the
+diffusers <-> BFL key correspondence and VaeImageProcessor's normalise / denormalise / uint8 rounding.
 
 Parameters are a flat dict in diffusers' state-dict naming ("decoder.up_blocks.0.resnets.1.conv1.weight", ...).
 """

@@ -225,3 +225,66 @@ def test_encode_images_ids_fallback_on_host():
     assert torch.equal(tokens, OS.pack_latents(z)) and torch.equal(ids, OS.prepare_latent_image_ids(8, 12))
     tokens, ids = encode_images(_Legacy(), z)
     assert ids.shape == (24, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the oracle pinned against an executable third-party implementation of the FLUX.1 autoencoder
+# ---------------------------------------------------------------------------------------------------------------------
+def _bfl_tools():
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_vae_bfl_golden.py")
+    spec = importlib.util.spec_from_file_location("make_vae_bfl_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _oracle_three(P, cfg, images, latents, seed):
+    from oracle import vae as V
+
+    moments = V.encode_moments(P, images, cfg)
+    torch.manual_seed(seed)  # the BFL module draws randn_like(mean) inside encode(): the same draw here
+    eps = torch.randn(moments.shape[0], cfg.latent_channels, *moments.shape[2:])  # (contiguous, like the module's chunk view)
+    return moments, V.encode(P, images, cfg, eps=eps), V.decode(P, latents, cfg)
+
+
+def test_oracle_vae_vs_bfl_autoencoder_fixture():
+    """tests/golden/vae_bfl_v1.npz: outputs of Black Forest Labs' AutoEncoder (torchtitan's copy) on seeded weights /
+    inputs at reduced width (generated by tests/golden/make_vae_bfl_golden.py).  The oracle must reproduce them: encoder
+    moments, the sampled + shifted + scaled latents, the decoded image."""
+    import numpy as np
+
+    from oracle import vae as V
+
+    G = _bfl_tools()
+    d = np.load(G.FIXTURE)
+    cfg = V.VaeConfig(**G.SMALL)
+    P = V.init_params(cfg, seed=77)
+    images, latents = torch.from_numpy(d["images"]), torch.from_numpy(d["latents"])
+    moments, z, img = _oracle_three(P, cfg, images, latents, seed=5)
+    for name, got in (("moments", moments), ("z", z), ("img", img)):
+        ref = torch.from_numpy(d[name])
+        err = float((got - ref).norm() / ref.norm())
+        print(f"[oracle vs BFL fixture] {name}: relL2 {err:.3g}")
+        assert err < 1e-5, name
+
+
+@pytest.mark.parametrize("width", ["small", "flux"])
+def test_oracle_vae_vs_bfl_autoencoder_live(width):
+    """The same comparison executed live where the torchtitan package is importable (it is part of this image), at the
+    fixture's width and at FLUX.1-dev's real widths (128, 256, 512, 512)."""
+    pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    from oracle import vae as V
+
+    G = _bfl_tools()
+    cfg = V.VaeConfig(**G.SMALL) if width == "small" else V.VaeConfig()
+    P = V.init_params(cfg, seed=78)
+    images, latents = G.inputs(seed=12, hw=(40, 56) if width == "small" else (32, 48))
+    ref = G.run_bfl(P, cfg, images, latents, seed=6)
+    got = _oracle_three(P, cfg, images, latents, seed=6)
+    for name, a, b in zip(("moments", "z", "img"), got, ref):
+        err = float((a - b).norm() / b.norm())
+        print(f"[oracle vs BFL live, {width}] {name}: relL2 {err:.3g}")
+        assert err < 1e-5, name

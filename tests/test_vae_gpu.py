@@ -1,5 +1,5 @@
 """GPU parity of the native VAE against oracle/vae.py (the restatement of diffusers 0.31.0's
-AutoencoderKL; parity unpinned for that third-party arithmetic, see the oracle header).
+AutoencoderKL, pinned at 1e-6 to Black Forest Labs' executable FLUX AutoEncoder: tests/test_vae_cpu.py, see the oracle header).
 
 Tolerances: the native path stores activations in bf16 and accumulates in fp32 (GroupNorm statistics in fp64), the
 oracle is fp32 throughout.  Kernel-level checks compare against the same arithmetic on the same bf16 inputs (<= 1 bf16
