@@ -19,10 +19,18 @@ PINNING.  (1) Pinned to the reference's OWN source: oracle/ref_harness.py import
 lora_controller.py / generate.py from /root/reference and executes them on the CPU; this restatement reproduces their
 outputs bit-for-bit on 7 model_config / c_factor / c_t / no-condition variants and 4 generate() runs
 (tests/golden/ref_v1.npz written by tests/golden/make_ref_golden.py, checked by tests/test_reference_pins_cpu.py).
-(2) PARITY UNPINNED for the third-party arithmetic: diffusers / peft are not installed and the reference ships no golden
-vectors or checkpoints, so in (1) the diffusers modules the reference receives as arguments are
-stand-ins written from the same published algorithm (App. A) — an independent, module-shaped second statement, plus
-the closed-form checks and the float64 golden of tests/test_oracle_cpu.py, but not diffusers' own code.
+(2) The third-party arithmetic: diffusers / peft are not installed and the reference ships no golden vectors or
+checkpoints, so in (1) the diffusers modules the reference receives as arguments are stand-ins written
+from the same published algorithm (App. A).  Round 2 PINNED that arithmetic to an executable third-party implementation
+of the same network: Black Forest Labs' FLUX model as shipped in the image's `torchtitan` package (EmbedND RoPE,
+timestep_embedding, MLPEmbedder, Modulation, QK-RMSNorm, Double / SingleStreamBlock, LastLayer).
+tests/golden/make_dit_bfl_golden.py maps this file's diffusers-named parameters onto that model (the published
+diffusers <-> BFL key correspondence, incl. the shift / scale swap of norm_out) and writes tests/golden/dit_bfl_v1.npz;
+tests/test_oracle_cpu.py replays it and re-runs the model live: `tranformer_forward` agrees to 3e-7 relL2 both without a
+condition branch (the stock forward) and through the reference's three-stream forward with the condition tokens at
+c_t = t and LoRA B = 0 (where they are arithmetically more image tokens).  Left PARITY UNPINNED: the guidance embedder
+(torchtitan's copy has none; it is the timestep MLPEmbedder once more, covered structurally), peft's LoRA Linear (closed
+form y = W x + s B A x, checked in tests/test_oracle_cpu.py) and s4torch (oracle/cs3_dgf.py).
 
 Parameters live in a flat dict keyed by the diffusers state-dict names of SURVEY.md App. A.9; LoRA factors are stored
 as "<linear>.lora_A.weight" [r, in] and "<linear>.lora_B.weight" [out, r] with scaling = lora_alpha / r.

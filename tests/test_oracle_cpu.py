@@ -156,3 +156,55 @@ def test_lora_masking_semantics():
     assert not torch.allclose(base, lora)
     assert "transformer_blocks.0.attn.add_q_proj.lora_A.weight" not in P  # text stream is never a LoRA target
     assert "transformer_blocks.0.ff.net.0.proj.lora_A.weight" not in P
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the DiT restatement pinned against an executable third-party implementation of FLUX (Black Forest Labs' model as
+# shipped in the image's torchtitan package): tests/golden/make_dit_bfl_golden.py
+# ---------------------------------------------------------------------------------------------------------------------
+def _dit_bfl_tools():
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_dit_bfl_golden.py")
+    spec = importlib.util.spec_from_file_location("make_dit_bfl_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("case", ["plain", "condition"])
+def test_oracle_dit_vs_bfl_flux_fixture(case):
+    """tests/golden/dit_bfl_v1.npz holds the BFL model's outputs on seeded tiny weights / inputs.  `plain`: the stock
+    forward (no condition branch).  `condition`: the reference's three-stream forward (transformer.py:47-252) with the
+    condition tokens at c_t = t and LoRA B = 0, where they are arithmetically just more image tokens."""
+    import numpy as np
+
+    from oracle import flux_dit as O
+
+    G = _dit_bfl_tools()
+    cfg = O.FluxConfig(**G.TINY)
+    P = G.params(cfg)
+    with_cond = case == "condition"
+    got = G.run_oracle(P, cfg, G.inputs(cfg, with_cond=with_cond), with_cond)
+    ref = torch.from_numpy(np.load(G.FIXTURE)["out_" + case])
+    err = float((got - ref).norm() / ref.norm())
+    print(f"[oracle DiT vs BFL fixture, {case}] relL2 {err:.3g}")
+    assert err < 1e-5
+
+
+def test_oracle_dit_vs_bfl_flux_live():
+    """The same comparison executed live where torchtitan imports (it is part of this image), on other seeds / shapes and
+    with FLUX.1-dev's head count per width ratio (4 heads of 128)."""
+    pytest.importorskip("torchtitan.experiments.flux.model.model")
+    from oracle import flux_dit as O
+
+    G = _dit_bfl_tools()
+    cfg = O.FluxConfig(**dict(G.TINY, num_attention_heads=4, num_layers=1, num_single_layers=2))
+    P = G.params(cfg, seed=22)
+    for with_cond in (False, True):
+        d = G.inputs(cfg, seed=4, B=1, n_txt=16, hw=(4, 10), with_cond=with_cond)
+        ref, got = G.run_bfl(P, cfg, d, with_cond), G.run_oracle(P, cfg, d, with_cond)
+        err = float((got - ref).norm() / ref.norm())
+        print(f"[oracle DiT vs BFL live, condition={with_cond}] relL2 {err:.3g}")
+        assert err < 1e-5
