@@ -5,8 +5,9 @@ Restatement of the sampler side of the reference: the denoise loop of src/flux/g
 `FluxPipeline._pack_latents / _unpack_latents / _prepare_latent_image_ids`), plus the id
 arithmetic of src/flux/condition.py:126-137.  The loop and the id arithmetic are pinned bit-for-bit to the reference's
 own generate.py / condition.py / pipeline_tools.py executed on the CPU (oracle/ref_harness.py, tests/golden/ref_v1.npz);
-diffusers itself is absent from /root/reference and from this image, so its scheduler / packing helpers are PARITY
-UNPINNED beyond the closed-form checks in tests/test_oracle_cpu.py.
+diffusers itself is absent from /root/reference and from this image; its sigma schedule is pinned to Black Forest Labs'
+own `get_schedule` (torchtitan's copy, tests/test_oracle_cpu.py::test_oracle_sigma_schedule_vs_bfl_get_schedule), the
+packing / id helpers by the closed-form checks in tests/test_oracle_cpu.py.
 """
 from __future__ import annotations
 

@@ -208,3 +208,15 @@ def test_oracle_dit_vs_bfl_flux_live():
         err = float((got - ref).norm() / ref.norm())
         print(f"[oracle DiT vs BFL live, condition={with_cond}] relL2 {err:.3g}")
         assert err < 1e-5
+
+
+def test_oracle_sigma_schedule_vs_bfl_get_schedule():
+    """diffusers' FlowMatchEulerDiscreteScheduler.set_timesteps(sigmas=linspace(1, 1/n, n), mu=calculate_shift(L)) as
+    restated in oracle/sampler.py against Black Forest Labs' own `get_schedule` (torchtitan's copy of flux/sampling.py):
+    the two discretisations coincide (t_i = 1 - i/n, exponential time shift, final 0)."""
+    S = pytest.importorskip("torchtitan.experiments.flux.sampling")
+    from oracle import sampler as OS
+
+    for n, L in ((4, 1024), (28, 1024), (50, 4096), (28, 256), (8, 2304)):
+        a, b = OS.flow_match_sigmas(n, L), torch.tensor(S.get_schedule(n, L))
+        assert a.shape == b.shape and float((a - b).abs().max()) < 1e-6, (n, L)
