@@ -3,6 +3,11 @@ lx_dit_step through the C ABI) against the oracle restatement of transformer.py 
 
 Stated tolerance: with identical bf16-rounded weights and inputs,
   relL2(native, oracle_fp32) <= 1.5 * relL2(oracle_bf16_eager, oracle_fp32) + 2e-3   and   <= 2e-2 absolute.
+Which clause binds: on the small geometries the relative clause does (bf16 eager sits at a few 1e-3).  At full FLUX width /
+depth the torch-bf16-eager restatement is itself ~0.4 relL2 away from fp32 -- the reference casts the timestep to the model
+dtype before multiplying by 1000 (transformer.py:95-100), and a bf16 timestep moves the whole conditioning vector -- so
+there the relative clause is vacuous and ONLY the 2e-2 absolute bound constrains the native path (which keeps the timestep
+embedding in fp32 and lands at ~1e-2).  The full-size tests print both numbers.
 """
 import pytest
 import torch
