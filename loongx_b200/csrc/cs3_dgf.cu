@@ -467,18 +467,29 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   const float* Bb = Bm + (size_t)b * b_bstride;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    // A tile: 64 rows x 16 k  -> sA[k][m]
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int m = i >> 4, k = i & 15;
-      sA[k][m] = (m0 + m < M && k0 + k < K) ? A[(size_t)(m0 + m) * lda + k0 + k] : 0.f;
+  // The next k-tile's global loads are issued before this tile's FMAs (registers as the second buffer): the loads of a
+  // tile used to be exposed between two __syncthreads.  Accumulation order per output element is unchanged (k ascending).
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256;
+      const int m = i >> 4, ka = i & 15;  // A tile: 64 rows x 16 k  -> sA[k][m]
+      ra[t] = (m0 + m < M && k0 + ka < K) ? A[(size_t)(m0 + m) * lda + k0 + ka] : 0.f;
+      const int kb = i >> 6, n = i & 63;  // B tile: 16 k x 64 n
+      rb[t] = (k0 + kb < K && n0 + n < N) ? Bb[(size_t)(k0 + kb) * ldb + n0 + n] : 0.f;
     }
-    // B tile: 16 k x 64 n
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int k = i >> 6, n = i & 63;
-      sB[k][n] = (k0 + k < K && n0 + n < N) ? Bb[(size_t)(k0 + k) * ldb + n0 + n] : 0.f;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256;
+      sA[i & 15][i >> 4] = ra[t];
+      sB[i >> 6][i & 63] = rb[t];
     }
     __syncthreads();
+    if (k0 + 16 < K) fetch(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       float a[4], bb[4];

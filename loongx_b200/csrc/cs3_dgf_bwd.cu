@@ -46,20 +46,33 @@ __global__ void __launch_bounds__(256) sgemm_ex_kernel(const SgemmEx p) {
   {
     const float* Ab = p.A + (size_t)b * p.a_bs;
     const float* Bb = p.Bm + (size_t)b * p.b_bs;
-    for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
-      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    // The next k-tile's global loads are issued before this tile's FMAs (registers as the second buffer); per output
+    // element the accumulation order is unchanged (k ascending inside the slice).
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = threadIdx.x + t * 256;
         int m, k;
         if (p.trans_a) { k = i >> 6; m = i & 63; } else { m = i >> 4; k = i & 15; }
-        const bool ok = m0 + m < p.M && k0 + k < k_hi;
-        sA[k][m] = ok ? (p.trans_a ? Ab[(size_t)(k0 + k) * p.lda + m0 + m] : Ab[(size_t)(m0 + m) * p.lda + k0 + k]) : 0.f;
-      }
-      for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-        int n, k;
+        const bool oka = m0 + m < p.M && k0 + k < k_hi;
+        ra[t] = oka ? (p.trans_a ? Ab[(size_t)(k0 + k) * p.lda + m0 + m] : Ab[(size_t)(m0 + m) * p.lda + k0 + k]) : 0.f;
+        int n;
         if (p.trans_b) { n = i >> 4; k = i & 15; } else { k = i >> 6; n = i & 63; }
-        const bool ok = k0 + k < k_hi && n0 + n < p.N;
-        sB[k][n] = ok ? (p.trans_b ? Bb[(size_t)(n0 + n) * p.ldb + k0 + k] : Bb[(size_t)(k0 + k) * p.ldb + n0 + n]) : 0.f;
+        const bool okb = k0 + k < k_hi && n0 + n < p.N;
+        rb[t] = okb ? (p.trans_b ? Bb[(size_t)(n0 + n) * p.ldb + k0 + k] : Bb[(size_t)(k0 + k) * p.ldb + n0 + n]) : 0.f;
+      }
+    };
+    if (k_lo < k_hi) fetch(k_lo);
+    for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = threadIdx.x + t * 256;
+        if (p.trans_a) sA[i >> 6][i & 63] = ra[t]; else sA[i & 15][i >> 4] = ra[t];
+        if (p.trans_b) sB[i & 15][i >> 4] = rb[t]; else sB[i >> 6][i & 63] = rb[t];
       }
       __syncthreads();
+      if (k0 + 16 < k_hi) fetch(k0 + 16);
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         float a[4], bb[4];
