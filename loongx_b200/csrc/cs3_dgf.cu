@@ -844,6 +844,101 @@ extern "C" int lx_token_linear(const float* h, const float* W, const float* bias
   return LX_OK;
 }
 
+namespace lx {
+
+// 128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs per thread as 2 x 2 blocks of 4 x 4 (rows ty*4.. and 64+ty*4.., columns
+// tx*4.. and 64+tx*4..: every operand fragment is one conflict-free 16-byte shared-memory load, 16 FMAs per load), the next
+// k-tile in registers while this one is multiplied.  Per output element the products are added in ascending k like the
+// 64 x 64 kernels (same results bit for bit where no K split is used); the 64 x 64 kernels reach ~12-16 TFLOP/s on the
+// M = 512, N = K = 1024..4096, batch 8 products of the DUANs / fusion layers, this one is used for those.
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16;
+__global__ void __launch_bounds__(256, 2) sgemm128_kernel(const Sgemm128 p) {
+  __shared__ __align__(16) float sA[SG_BK][SG_BM + 4];
+  __shared__ __align__(16) float sB[SG_BK][SG_BN + 4];
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int b = p.reduce_batch ? blockIdx.z / p.ksplit : blockIdx.z;
+  const int kper = p.reduce_batch ? ((p.K + p.ksplit * SG_BK - 1) / (p.ksplit * SG_BK)) * SG_BK : p.K;
+  const int k_lo = p.reduce_batch ? (blockIdx.z % p.ksplit) * kper : 0, k_hi = min(p.K, k_lo + kper);
+  const float* Ab = p.A + (size_t)b * p.a_bs;
+  const float* Bb = p.B + (size_t)b * p.b_bs;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int i = threadIdx.x + t * 256;
+      int m, k;
+      if (p.trans_a) { k = i >> 7; m = i & 127; } else { m = i >> 4; k = i & 15; }
+      const bool oka = m0 + m < p.M && k0 + k < k_hi;
+      ra[t] = oka ? (p.trans_a ? Ab[(size_t)(k0 + k) * p.lda + m0 + m] : Ab[(size_t)(m0 + m) * p.lda + k0 + k]) : 0.f;
+      int n;
+      if (p.trans_b) { n = i >> 4; k = i & 15; } else { k = i >> 7; n = i & 127; }
+      const bool okb = k0 + k < k_hi && n0 + n < p.N;
+      rb[t] = okb ? (p.trans_b ? Bb[(size_t)(n0 + n) * p.ldb + k0 + k] : Bb[(size_t)(k0 + k) * p.ldb + n0 + n]) : 0.f;
+    }
+  };
+  if (k_lo < k_hi) fetch(k_lo);
+  for (int k0 = k_lo; k0 < k_hi; k0 += SG_BK) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int i = threadIdx.x + t * 256;
+      if (p.trans_a) sA[i >> 7][i & 127] = ra[t]; else sA[i & 15][i >> 4] = ra[t];
+      if (p.trans_b) sB[i & 15][i >> 4] = rb[t]; else sB[i >> 7][i & 127] = rb[t];
+    }
+    __syncthreads();
+    if (k0 + SG_BK < k_hi) fetch(k0 + SG_BK);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[k][ty * 4]), a1 = *reinterpret_cast<const float4*>(&sA[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sB[k][tx * 4]), b1 = *reinterpret_cast<const float4*>(&sB[k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Cb = p.C + (p.reduce_batch ? 0 : (size_t)blockIdx.z * p.c_bs);
+  const float* Rb = p.R != nullptr ? p.R + (size_t)blockIdx.z * p.c_bs : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (m >= p.M) continue;
+    const float bias = p.bias != nullptr ? p.bias[m] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (n >= p.N) continue;
+      float* c = Cb + (size_t)m * p.ldc + n;
+      if (p.reduce_batch) {
+        atomicAdd(c, p.alpha * acc[i][j]);  // beta == 1 (checked by the caller): C accumulates
+      } else {
+        float v = p.alpha * acc[i][j] + bias;
+        if (Rb != nullptr) v += Rb[(size_t)m * p.ldc + n];
+        if (p.act == 1) v = fmaxf(v, 0.f);
+        else if (p.act == 2) v = 1.0f / (1.0f + expf(-v));
+        *c = v + (p.beta != 0.f ? p.beta * *c : 0.f);
+      }
+    }
+  }
+}
+
+int sgemm128_launch(const Sgemm128& p, int batch, void* stream) {
+  dim3 grid((p.N + SG_BN - 1) / SG_BN, (p.M + SG_BM - 1) / SG_BM, p.reduce_batch ? batch * p.ksplit : batch);
+  sgemm128_kernel<<<grid, 256, 0, ST(stream)>>>(p);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+}  // namespace lx
+
 extern "C" int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream) {
   LaunchScope scope(KC_CS3DGF, stream, desc ? 4.0 * ((double)desc->M * desc->K + desc->batch * ((double)desc->K * desc->N + (double)desc->M * desc->N)) : 0.0);
   LX_CHECK_ARG(desc != nullptr, "lx_sgemm_f32: null descriptor");
@@ -851,6 +946,13 @@ extern "C" int lx_sgemm_f32(const lx_sgemm_desc_t* desc, void* stream) {
   LX_CHECK_ARG(d.A && d.Bm && (d.C || d.rowmean) && d.M > 0 && d.N > 0 && d.K > 0 && d.batch > 0,
                "lx_sgemm_f32: bad arguments");
   LX_CHECK_ARG(d.act >= 0 && d.act <= 2, "lx_sgemm_f32: bad activation");
+  if (d.rowmean == nullptr && d.M >= 128 && d.N >= 128 && (long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch >= num_sms()) {
+    lx::Sgemm128 p{};  // the larger products: 128 x 128 tiles (same results bit for bit)
+    p.A = d.A; p.B = d.Bm; p.C = d.C; p.bias = d.bias; p.R = d.R;
+    p.lda = d.lda; p.ldb = d.ldb; p.ldc = d.ldc; p.a_bs = 0; p.b_bs = d.b_bstride; p.c_bs = d.c_bstride;
+    p.M = d.M; p.N = d.N; p.K = d.K; p.act = d.act; p.ksplit = 1; p.alpha = 1.0f; p.beta = 0.0f;
+    return lx::sgemm128_launch(p, d.batch, stream);
+  }
   dim3 grid((d.N + 63) / 64, (d.M + 63) / 64, d.batch);
   sgemm_kernel<<<grid, 256, 0, ST(stream)>>>(d.A, d.lda, d.Bm, d.ldb, d.b_bstride, d.bias, d.R, d.C, d.ldc, d.c_bstride,
                                              d.rowmean, d.rowmean ? d.rowpart : nullptr, d.M, d.N, d.K, d.act);

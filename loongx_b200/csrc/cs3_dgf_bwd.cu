@@ -759,6 +759,20 @@ extern "C" int lx_sgemm_ex(const lx_sgemm_ex_desc_t* desc, void* stream) {
     const long want = 4L * num_sms();
     while (tiles * p.ksplit < want && d.K / (p.ksplit * 2) >= 64) p.ksplit *= 2;
   }
+  {  // the larger products go to the 128 x 128 tile (host_util.cuh: Sgemm128) when that still fills the GPU
+    long tiles128 = (long)((d.N + 127) / 128) * ((d.M + 127) / 128) * d.batch;
+    int ks = 1;
+    if (d.reduce_batch)
+      while (tiles128 * ks < 2L * num_sms() && d.K / (ks * 2) >= 64) ks *= 2;
+    if (d.M >= 128 && d.N >= 128 && tiles128 * ks >= num_sms()) {
+      Sgemm128 q{};
+      q.A = d.A; q.B = d.Bm; q.C = d.C;
+      q.lda = d.lda; q.ldb = d.ldb; q.ldc = d.ldc; q.a_bs = d.a_bstride; q.b_bs = d.b_bstride; q.c_bs = d.c_bstride;
+      q.M = d.M; q.N = d.N; q.K = d.K; q.trans_a = d.trans_a; q.trans_b = d.trans_b;
+      q.reduce_batch = d.reduce_batch; q.ksplit = ks; q.alpha = d.alpha; q.beta = d.beta;
+      return sgemm128_launch(q, d.batch, stream);
+    }
+  }
   dim3 grid((d.N + 63) / 64, (d.M + 63) / 64, d.reduce_batch ? d.batch * p.ksplit : d.batch);
   sgemm_ex_kernel<<<grid, 256, 0, ST(stream)>>>(p);
   LX_CUDA(cudaGetLastError());

@@ -98,6 +98,23 @@ int debug_skip_mask();
 int s4_fft_launch(bool inverse, const double2* in_c, const float* in_r, double2* out_c, float* out_r, int d, int L,
                   void* stream);
 
+// 128 x 128 x 16 fp32 SIMT GEMM tile for the larger products of the CS3 / DGF path (cs3_dgf.cu; shared by the forward
+// lx_sgemm_f32 and the backward lx_sgemm_ex): C[b] = epilogue(alpha op(A[b]) op(B[b])), op = stored [M,K] / [K,N] or
+// transposed; reduce mode adds (batch element, K slice) partials into one C with fp32 atomics.
+struct Sgemm128 {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;  // [M] added per output row, or NULL
+  const float* R;     // residual with C's layout, or NULL
+  int64_t lda, ldb, ldc, a_bs, b_bs, c_bs;
+  int M, N, K;
+  int trans_a, trans_b, act;  // act: 0 none, 1 relu, 2 sigmoid
+  int reduce_batch, ksplit;
+  float alpha, beta;
+};
+int sgemm128_launch(const Sgemm128& p, int batch, void* stream);
+
 struct LaunchScope {
   LaunchScope(int cls, void* stream, double work);  // work: FLOPs (tensor kernels) or bytes (HBM-bound kernels)
   ~LaunchScope();
