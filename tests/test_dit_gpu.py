@@ -350,7 +350,7 @@ def test_dit_full_flux_size_parity():
 
 def test_full_flux_size_denoise_loop_parity():
     """SURVEY.md §8d, 'after the full loop <= 5e-2': the sampler loop at BASELINE.json's configs[1] geometry with the WHOLE
-    FLUX.1-dev-sized DiT (57 blocks, 11.9 B synthetic parameters): LX_LOOP_STEPS (default 4) Euler steps of the shifted
+    FLUX.1-dev-sized DiT (57 blocks, 11.9 B synthetic parameters): LX_LOOP_STEPS (default 28 = the whole edit) Euler steps of the shifted
     sigma schedule, native (lx_dit_prepare once + lx_dit_step / lx_euler_step per step, bf16 latents) against the fp32
     oracle evaluated on the GPU with the same bf16-rounded weights and an fp32 latent trajectory.  Tolerance: relL2 <= 5e-2
     on the final latents (and on every intermediate step).  The fp32 oracle forward takes ~0.7 s at this size."""
@@ -369,7 +369,7 @@ def test_full_flux_size_denoise_loop_parity():
     free, _ = torch.cuda.mem_get_info()
     if free < 150e9:
         pytest.skip("needs ~130 GB of free HBM (fp32 oracle weights + native panels)")
-    T = int(os.environ.get("LX_LOOP_STEPS", "4"))
+    T = int(os.environ.get("LX_LOOP_STEPS", "28"))  # the full 28-step edit takes ~30 s (profiles/gpurun_logs/full_size_loop_parity_28_r2.log: 0.9 % after step 28)
     dev = "cuda"
     ocfg, cfg = O.FluxConfig(), FluxConfig()
     Pb = random_params(cfg, dev, seed=78, w_std=0.02, bias_std=0.02, lora_b_std=0.02)
