@@ -207,7 +207,8 @@ def test_lora_grad_merge_transpose(M, K, N, r):
 
 @pytest.mark.parametrize("M,K,widths,r", [(4096 + 40, 768, (256, 256, 256), 4), (300, 256, (512, 256, 256, 1024), 4),
                                           (64, 64, (768,), 4), (130, 512, (256, 512), 8), (257, 256, (512,), 16),
-                                          (1000, 1024, (2048,), 4)])
+                                          (1000, 1024, (2048,), 4), (5, 256, (512, 256), 4), (1, 512, (256,), 4),
+                                          (4, 3072, (1024, 1024, 1024, 1024), 4)])
 def test_lora_grad_stacked_vs_autograd_and_per_factor(M, K, widths, r):
     """lx_lora_grad_stacked: the sub-Linears of one fused projection (to_q | to_k | to_v (| proj_mlp)) in four launches;
     fp32 autograd over y_g = s_g (x A_g^T) B_g^T is the checker, and the per-factor kernels must agree."""
