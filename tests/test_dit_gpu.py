@@ -456,3 +456,52 @@ def test_dit_cached_condition_branch(nt, hw):
     # configurations that do not allow caching fall back silently
     assert not DitPlan(Wt, B, nt, ni, ni, T=1, model_config={}, cache_cond=True).cache_cond
     assert not DitPlan(Wt, B, nt, ni, ni, T=1, model_config=mc, c_factor=1.5, cache_cond=True).cache_cond
+
+
+@pytest.mark.parametrize("with_cond", [False, True])
+def test_dit_forward_vs_bfl_flux_model_directly(with_cond):
+    """The native engine against an executable THIRD-PARTY implementation of the network, not through this repo's oracle:
+    Black Forest Labs' FLUX model (torchtitan's copy, fp32 on the GPU) with the same bf16-rounded weights mapped by
+    tests/golden/make_dit_bfl_golden.py.  Without a condition branch the forwards are the same function; with it, the
+    reference's three-stream forward at c_t = t and LoRA B = 0 equals BFL's model fed img = [image ; condition] tokens
+    (image rows compared).  torchtitan has no guidance embedder, hence guidance_embeds=False.  bf16 tolerance 2e-2."""
+    pytest.importorskip("torchtitan.experiments.flux.model.model")
+    import importlib.util
+    import os
+
+    from oracle import flux_dit as O
+    from loongx_b200.config import FluxConfig
+    from loongx_b200.dit import DitPlan, DitWeights
+
+    spec = importlib.util.spec_from_file_location(
+        "make_dit_bfl_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_dit_bfl_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    dev = "cuda"
+    kw = dict(num_layers=2, num_single_layers=3, num_attention_heads=4, joint_attention_dim=256, pooled_projection_dim=64,
+              guidance_embeds=False)
+    ocfg, cfg = O.FluxConfig(**kw), FluxConfig(**kw)
+    P = G.params(ocfg, seed=31)
+    Pb = {k: v.to(torch.bfloat16).to(dev) for k, v in P.items()}  # the shared, bf16-rounded weights
+    P32 = {k: v.float().cpu() for k, v in Pb.items()}
+    B, nt, side = 2, 128, (8, 16)
+    ni = side[0] * side[1]
+    nc = ni if with_cond else 0
+    t = 0.37
+    g = torch.Generator().manual_seed(5)
+    r = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).bfloat16()  # noqa: E731
+    d = dict(hidden_states=r(B, ni, 64).float(), encoder_hidden_states=r(B, nt, 256, scale=0.5).float(), pooled_projections=r(B, 64).float(),
+             timestep=torch.full((B,), t), img_ids=_ids(*side), txt_ids=torch.zeros(nt, 3))
+    if with_cond:
+        d.update(condition_latents=r(B, ni, 64).float(), condition_ids=_ids(side[0], side[1], -side[1]))
+    ref = G.run_bfl(P32, ocfg, d, with_cond).to(dev)  # fp32, CPU (tiny)
+    W = DitWeights(Pb, cfg, dev)
+    plan = DitPlan(W, B, nt, ni, nc, T=1, model_config={})
+    plan.set_ids(d["txt_ids"].to(dev), d["img_ids"].to(dev), d["condition_ids"].to(dev) if with_cond else None)
+    plan.prepare(d["encoder_hidden_states"].bfloat16().to(dev), d["pooled_projections"].bfloat16().to(dev),
+                 d["condition_latents"].bfloat16().to(dev) if with_cond else None, [t] * B, None, c_t=t)
+    got = plan.step(0, d["hidden_states"].bfloat16().to(dev))
+    torch.cuda.synchronize()
+    err = _rel(got, ref)
+    print(f"\n[native vs BFL FLUX model, condition={with_cond}] relL2 {err:.4g}")
+    assert err < 2e-2
