@@ -284,3 +284,33 @@ def test_condition_from_a_raw_picture():
                    num_inference_steps=2, output_type="pil", default_lora=True, use_brain_condition=False,
                    generator=torch.Generator(device="cuda").manual_seed(1)).images
     assert len(out) == 1 and out[0].size == (256, 128)
+
+
+def test_decode_and_encode_vs_bfl_autoencoder_directly(vae):
+    """The native VAE against an executable THIRD-PARTY implementation, not through this repo's oracle: Black Forest Labs'
+    FLUX AutoEncoder (torchtitan's copy, fp32 on the CPU) with the same weights mapped by
+    tests/golden/make_vae_bfl_golden.py, at FLUX.1-dev's full widths.  Decoder on z / scale + shift, encoder moments."""
+    pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "make_vae_bfl_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_vae_bfl_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    v, P = vae
+    O, ocfg = _ocfg()
+    ae = G.bfl_autoencoder({k: t.float().cpu() for k, t in P.items()}, ocfg)
+    g = torch.Generator().manual_seed(31)
+    lat = torch.randn(1, 16, 24, 40, generator=g) * 0.8  # "pipeline" latents: the decoder sees lat / scale + shift
+    img = torch.rand(1, 3, 64, 96, generator=g) * 2 - 1
+    with torch.no_grad():
+        want_img = ae.decode(lat)
+        want_m = ae.encoder(img)
+    got_img = v.decode((lat / ocfg.scaling_factor + ocfg.shift_factor).cuda(), return_dict=False)[0]
+    rows, nb, h, w = v.encode_moments(img.cuda())
+    got_m = rows.reshape(1, h, w, 32).permute(0, 3, 1, 2)
+    e_d, e_e = _rel(got_img, want_img), _rel(got_m, want_m)
+    print(f"\n[native VAE vs BFL AutoEncoder] decode relL2 {e_d:.3g}, encoder moments relL2 {e_e:.3g}")
+    assert e_d <= 3e-2 and e_e <= 3e-2
+    assert (O.postprocess_pt(got_img.cpu()) - O.postprocess_pt(want_img)).abs().mean().item() < 2 / 255
