@@ -319,7 +319,13 @@ def run_native(args, rank, local_rank, world):
 
     configs = None
     if not args.no_config_legs:
-        configs = run_config_legs(args, model, dev, rank, local_rank, world, peaks)
+        if world == 1:  # the extra legs must never cost the headline line (at N > 1 a rank-local failure tears the job down anyway)
+            try:
+                configs = run_config_legs(args, model, dev, rank, local_rank, world, peaks)
+            except Exception as e:  # noqa: BLE001
+                configs = {"error": f"{type(e).__name__}: {e}"[:400]}
+        else:
+            configs = run_config_legs(args, model, dev, rank, local_rank, world, peaks)
 
     if rank == 0:
         line = {
