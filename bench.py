@@ -448,7 +448,8 @@ def run_config_legs(args, model, dev, rank, local_rank, world, peaks):
     T.ALLREDUCE_LOG.clear()
     secs, clk = timed(one_step, warm=1, reps=2)
     ar = T.ALLREDUCE_LOG[-2:]
-    ar_ms = [e0.elapsed_time(e1) for (e0, e1, _) in ar]
+    ar_ms = [e[0].elapsed_time(e[1]) for e in ar]
+    skew_ms = [e[3].elapsed_time(e[0]) for e in ar]  # waiting for the slowest rank's backward before the exchange
     T.ALLREDUCE_TIMING = False
     n_img = (RES // 16) ** 2
     S, D, nb = N_TXT + 2 * n_img, 3072, 57
@@ -463,8 +464,10 @@ def run_config_legs(args, model, dev, rank, local_rank, world, peaks):
         "ms_per_step": secs * 1e3, "samples_per_s": world * B / secs, "algorithmic_tflops_per_gpu": tf,
         "frac_of_peak_end_to_end": tf / peaks["tflops"],
         "allreduce": {"ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else 0.0, "bytes": (ar[-1][2] if ar else tr.grad_flat.numel() * 4),
-                      "calls_per_step": 1, "what": "NCCL all-reduce (sum) + 1/world scale of the flat fp32 gradient bucket; "
-                                                   "0 ms at n_gpus = 1 (no collective is issued)"},
+                      "calls_per_step": 1, "rank_skew_ms": (sum(skew_ms) / len(skew_ms)) if skew_ms else 0.0,
+                      "what": "NCCL all-reduce (sum) + 1/world scale of the flat fp32 gradient bucket, timed after a one-element "
+                              "all-reduce has lined the ranks up (rank_skew_ms = the wait for the slowest rank's backward, not "
+                              "part of the exchange); 0 ms at n_gpus = 1 (no collective is issued)"},
         "trainable_elements": int(tr.grad_flat.numel()), "clocks": clk,
         "timing": "1 build step + 1 warm-up step + 2 timed steps, CUDA events, max over ranks"}
     return out

@@ -358,7 +358,7 @@ class LoraFactor:
         return self.shared.merged != (self.A._version, self.B._version)
 
 
-ALLREDUCE_LOG: list = []  # (start event, end event, bytes) per gradient all-reduce when ALLREDUCE_TIMING is on (bench.py)
+ALLREDUCE_LOG: list = []  # (start event, end event, bytes, rank-alignment start event) per gradient all-reduce when ALLREDUCE_TIMING is on (bench.py)
 ALLREDUCE_TIMING = False
 
 
@@ -371,13 +371,18 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
         return flat
     timing = ALLREDUCE_TIMING and flat.is_cuda
     if timing:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # measurement mode (bench.py): a one-element all-reduce first lines the ranks up on the device, so that the events
+        # around the bucket's all-reduce time the exchange itself; the wait for the slowest rank's backward (clock spread
+        # under the power cap) is logged separately instead of being charged to the collective
+        es, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        es.record()
+        dist.all_reduce(torch.zeros(1, device=flat.device), op=dist.ReduceOp.SUM, group=group)
         e0.record()
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.mul_(1.0 / dist.get_world_size(group))
     if timing:
         e1.record()
-        ALLREDUCE_LOG.append((e0, e1, flat.numel() * flat.element_size()))
+        ALLREDUCE_LOG.append((e0, e1, flat.numel() * flat.element_size(), es))
     return flat
 
 
