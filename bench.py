@@ -317,6 +317,15 @@ def run_native(args, rank, local_rank, world):
                "sample": s.sample + f" ({len(reps)} repetitions, {time.perf_counter() - t0:.1f} s)",
                "s_per_edit_extrapolated": s.edit_seconds(td, ts)}
 
+    if rank == 0 and world == 1 and not args.no_vendor_leg:
+        try:
+            mix = gemm_mix_leg(dev)
+            mix["in_loop_frac_of_cublas_same_shapes"] = gemm_tf / mix["cublas_tflops"]
+            roofline["same_shapes_sustained"] = mix
+        except Exception as e:  # noqa: BLE001  (context only: must never cost the headline line)
+            roofline["same_shapes_sustained"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
     configs = None
     if not args.no_config_legs:
         if world == 1:  # the extra legs must never cost the headline line (at N > 1 a rank-local failure tears the job down anyway)
@@ -342,6 +351,53 @@ def run_native(args, rank, local_rank, world):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# roofline context: the GEMM mix of one denoise step (M = 2560 projections of a batch-1 edit), stand-alone and SUSTAINED
+# (seconds, i.e. at the power cap like the loop itself), once with lx_gemm_bf16 and once with the vendor library
+# (torch.matmul -> cuBLAS).  MEASURED_PEAKS' sustained figure was taken on an 8192^3 problem; this is what the vendor
+# GEMM reaches on THESE shapes under the same power cap.  Reported next to the roofline, never part of the headline.
+# --------------------------------------------------------------------------------------------------------------------
+def gemm_mix_leg(dev, warm=16, passes=64):
+    from loongx_b200 import ops
+
+    M, ncopy = 2560, 4
+    shapes = {"qkv": (9216, 3072), "attn_out": (3072, 3072), "ff_up": (12288, 3072), "ff_down": (3072, 12288),
+              "single_qkv_mlp": (21504, 3072), "single_out": (3072, 15360)}
+    g = torch.Generator(device=dev).manual_seed(5)
+    W = {k: [torch.randn(n, kk, generator=g, device=dev, dtype=torch.bfloat16) * 0.02 for _ in range(ncopy)]
+         for k, (n, kk) in shapes.items()}  # 4 x 452 MB: every launch streams its weights from HBM, as in the loop
+    A = {kk: torch.randn(M, kk, generator=g, device=dev, dtype=torch.bfloat16) for kk in {v[1] for v in shapes.values()}}
+    O = {n: torch.empty(M, n, device=dev, dtype=torch.bfloat16) for n in {v[0] for v in shapes.values()}}
+    seq = ["qkv", "attn_out", "ff_up", "ff_down"] * 19 + ["single_qkv_mlp", "single_out"] * 38
+    flop = sum(2.0 * M * shapes[k][0] * shapes[k][1] for k in seq)
+    out = {"what": "GEMM mix of one denoise step (19 x [qkv, attn_out, ff_up, ff_down] + 38 x [single qkv|mlp, single out], "
+                   f"M = 2560, rotating weight copies > L2), {warm} warm-up + {passes} timed passes back to back per library "
+                   "(sustained: at the power cap), CUDA events", "tflop_per_pass": flop / 1e12}
+    for which in ("lx", "cublas"):
+        def one(it):
+            for j, k in enumerate(seq):
+                n, kk = shapes[k]
+                w = W[k][(it + j) % ncopy]
+                if which == "lx":
+                    ops.gemm(A[kk], w, None, O[n])
+                else:
+                    torch.matmul(A[kk], w.t(), out=O[n])
+        for it in range(warm):
+            one(it)
+        clocks = ClockSampler(dev.index or 0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.start()
+        e0.record()
+        for it in range(passes):
+            one(it)
+        e1.record()
+        torch.cuda.synchronize()
+        clk = clocks.stop()
+        out[which + "_tflops"] = passes * flop / e0.elapsed_time(e1) / 1e9
+        out[which + "_sm_mhz"] = clk.get("sm_mhz")
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -659,6 +715,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="edits per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vendor-leg", action="store_true",
+                    help="skip the sustained lx / cuBLAS GEMM-mix context measurement (roofline.same_shapes_sustained)")
     ap.add_argument("--no-config-legs", action="store_true",
                     help="skip the BASELINE.json configs[2..4] legs that follow the headline measurement")
     ap.add_argument("--workload", default="edit", choices=["edit", "train", "vae"],
