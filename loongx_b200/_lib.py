@@ -105,6 +105,8 @@ import os as _os
 
 if _os.environ.get("LX_PDL"):  # development aid: programmatic dependent launch on (1, default) / off (0)
     lib.lx_debug_set_pdl(int(_os.environ["LX_PDL"]))
+if _os.environ.get("LX_ATT_SPLIT"):  # development aid: split-work attention schedule on (1, default) / off (0)
+    lib.lx_debug_attention_split(int(_os.environ["LX_ATT_SPLIT"]))
 if _os.environ.get("LX_RASTER_MB"):  # development aid: L2 budget of the GEMM raster bands (see gemm.cu::tile_coords)
     lib.lx_debug_gemm_raster_budget_mb(int(_os.environ["LX_RASTER_MB"]))
 

@@ -32,8 +32,12 @@ constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_D = 128;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KiB: two 128x64 swizzle atoms
 constexpr int ATT_ATOM_BYTES = 128 * 64 * 2;   // 16 KiB
 constexpr int ATT_KV_STAGES = 2;
+// pairs of every 8 whose exponentials run as a degree-3 polynomial on the FMA pipe instead of the MUFU.  Burst timing at
+// 1.9 GHz preferred 2; at the power cap, where the loop runs, the 6 extra issue slots per element cost more energy than
+// the MUFU slot they free: sustained 889 (2) / 914 (1) / 912 (0) / 876 (3) / 831 (4) TFLOP/s, in-loop 727 -> 752
+// (scripts/attn_sustained.py, profiles/gpurun_logs/attn_poly_sweep_r2.log)
 #ifndef ATT_POLY_OF_8
-#define ATT_POLY_OF_8 2
+#define ATT_POLY_OF_8 1
 #endif
 constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA warp + MMA warp (+2 idle); warpgroups 1, 2: softmax of tiles A, B
 // Q (2 tiles) + K/V rings + ONE output staging tile shared by the two groups + barriers + alignment slack

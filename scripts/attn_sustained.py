@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch.nn.attention import SDPBackend, sdpa_kernel
 
+from loongx_b200 import _lib as L
 from loongx_b200 import ops
 
 n_launch = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
@@ -26,6 +27,8 @@ qkv = [[torch.randn((B, H, S, 128), generator=g, device="cuda").bfloat16() for _
 out = torch.empty((B * S, H * 128), device="cuda", dtype=torch.bfloat16)
 orb = ops.make_out_row_base(B, nt, ni, nc, "cuda")
 flop = 4.0 * B * H * S * S * 128
+if os.environ.get("LX_ATT_SPLIT"):  # A/B: 0 = units are never cut between CTAs (no partial exchange, 1.62 waves)
+    L.lib.lx_debug_attention_split(int(os.environ["LX_ATT_SPLIT"]))
 
 try:
     import pynvml
