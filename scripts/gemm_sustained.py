@@ -6,7 +6,8 @@ step (19 x [qkv, attn_out, ff_up, ff_down] + 38 x [single qkv|mlp, single out], 
 than the L2) for several seconds per library, alternating, and reports sustained TFLOP/s and the SM clock under load.
 Development aid, not a bench value.
 
-  python scripts/gemm_sustained.py [passes_per_leg] [rounds]
+  python scripts/gemm_sustained.py [passes_per_leg] [rounds] [legs, e.g. lx,cublas,lx256,lx224,lx192]
+  (lxNNN: lx_gemm_bf16 with the N tile forced to NNN instead of the wave-count heuristic of gemm.cu::pick_tile_n)
 """
 import os
 import sys
@@ -33,8 +34,8 @@ def one_pass(which, it):
     for j, s in enumerate(seq):
         n, kk = shapes[s]
         w = W[s][(it + j) % NCOPY]
-        if which == "lx":
-            ops.gemm(A[kk], w, None, O[n])
+        if which.startswith("lx"):
+            ops.gemm(A[kk], w, None, O[n], tile_n=int(which[2:] or 0))
         else:
             torch.matmul(A[kk], w.t(), out=O[n])
 
@@ -56,7 +57,7 @@ def clock():
 
 print(f"GEMM mix of one denoise step: {flop_pass / 1e12:.2f} TFLOP per pass, {len(seq)} launches", flush=True)
 for r in range(rounds):
-    for which in ("lx", "cublas"):
+    for which in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("lx", "cublas")):
         for it in range(3):
             one_pass(which, it)
         torch.cuda.synchronize()
