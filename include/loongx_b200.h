@@ -190,6 +190,9 @@ int lx_timestep_embed(const float* t, void* out, int64_t ldo, int32_t M, float m
  * text_emb followed by the SiLU every AdaLN applies (transformer.py:102-114, App. A.2/A.5). */
 int lx_add_silu_bcast(const void* a, const void* b, const void* c, int32_t c_rows, void* out, int64_t ldo, int32_t M,
                       int32_t D, void* stream);
+/* x[m, 0:D] = bf16(float(x[m]) + float(r[m])), bf16 rows with strides ldx / ldr: `hidden_states + controlnet_block_samples[i]`
+ * (transformer.py:172-181) and its single-block form on the image rows (transformer.py:230-239). */
+int lx_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int32_t rows, int32_t D, void* stream);
 /* FlowMatchEulerDiscreteScheduler.step (generate.py:349): out = bf16(float(x) + dt*float(v)), n elements. */
 int lx_euler_step(const void* x, const void* v, void* out, float dt, int64_t n, void* stream);
 /* FluxPosEmbed (transformer.py:130-134): ids fp32 [S,3] -> table fp32 [S,64,2] (cos, sin), float64 internally. */
@@ -302,6 +305,10 @@ int lx_dit_embed(const lx_dit_model_t* model, const lx_dit_plan_t* plan, const v
 /* One DiT forward at prepared step `step`: latents bf16 [B, n_img, in_channels] -> noise_pred (same shape). */
 int lx_dit_step(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, const void* latents,
                 void* noise_pred, void* stream);
+/* The tail of lx_dit_step on its own: AdaLayerNormContinuous (norm_out) on the image rows of plan->X + proj_out
+ * (transformer.py:241-244).  lx_dit_embed + the block calls below + lx_dit_head = lx_dit_step; the split form is what a
+ * caller with controlnet residuals between the blocks (transformer.py:172-181, 230-239; lx_add_rows) uses. */
+int lx_dit_head(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, void* noise_pred, void* stream);
 /* Reference-granularity entry points for parity tests (block.py:179-278 / 281-339): run ONE block of the prepared
  * plan in place on plan->X. */
 int lx_dit_double_block(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, int32_t block,

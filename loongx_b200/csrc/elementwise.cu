@@ -109,6 +109,21 @@ __global__ void __launch_bounds__(LN_THREADS) ln_modulate_kernel(const lx_lnmod_
   if (threadIdx.x == 0) timeline_mark(tl, 2);  // one mark per CTA: 2560 same-address atomics would dominate the kernel
 }
 
+// x[m, 0:D] = bf16(float(x[m]) + float(r[m])): the controlnet residual of transformer.py:172-181, 230-239 on the image rows
+__global__ void add_rows_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ r, int64_t ldr,
+                                int rows, int D) {
+  const int per_row = D >> 3;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 8 elements per thread
+  if (idx >= (int64_t)rows * per_row) return;
+  const int m = (int)(idx / per_row), c0 = (int)(idx % per_row) * 8;
+  float a[8], b[8];
+  load8(x + (size_t)m * ldx + c0, a);
+  load8_ldg(r + (size_t)m * ldr + c0, b);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] += b[e];
+  *reinterpret_cast<uint4*>(x + (size_t)m * ldx + c0) = pack8(a);
+}
+
 // out[m, 0:128] = cos(t*f_j), out[m, 128:256] = sin(t*f_j), f_j = exp(-ln(1e4) j / 128)
 __global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int64_t ldo, int M,
                                       float mult) {
@@ -253,6 +268,17 @@ extern "C" int lx_add_silu_bcast(const void* a, const void* b, const void* c, in
   add_silu_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
       reinterpret_cast<const __nv_bfloat16*>(c), c_rows, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, D);
+  LX_CUDA(cudaGetLastError());
+  return LX_OK;
+}
+
+extern "C" int lx_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int32_t rows, int32_t D, void* stream) {
+  LX_CHECK_ARG(x && r && rows > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldr % 8 == 0 && ldx >= D && ldr >= D,
+               "lx_add_rows: bad arguments (rows=%d D=%d)", rows, D);
+  const int64_t n = (int64_t)rows * (D / 8);
+  LaunchScope scope(KC_ROW, stream, 6.0 * rows * D);
+  add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(r), ldr, rows, D);
   LX_CUDA(cudaGetLastError());
   return LX_OK;
 }

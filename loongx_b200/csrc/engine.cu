@@ -361,12 +361,23 @@ extern "C" int lx_dit_step(const lx_dit_model_t* model, const lx_dit_plan_t* pla
   const lx_dit_plan_t& p = *plan;
   LX_CHECK_ARG(step >= 0 && step < p.T, "lx_dit_step: step %d outside [0, %d)", step, p.T);
   LX_CHECK_ARG(latents && noise_pred, "lx_dit_step: null tensor");
-  const Geo g = geo(m, p);
-  const int D = g.D;
   LX_TRY(embed_inputs(m, p, latents, stream));
   for (int i = 0; i < m.num_layers; ++i) LX_TRY(double_block(m, p, step, i, stream));
   for (int i = 0; i < m.num_single_layers; ++i) LX_TRY(single_block(m, p, step, i, stream));
-  // norm_out (AdaLayerNormContinuous: scale first, then shift) on the image rows, then proj_out
+  return lx_dit_head(model, plan, step, noise_pred, stream);
+}
+
+// norm_out (AdaLayerNormContinuous: scale first, then shift) on the image rows of plan->X, then proj_out
+// (transformer.py:241-244)
+extern "C" int lx_dit_head(const lx_dit_model_t* model, const lx_dit_plan_t* plan, int32_t step, void* noise_pred,
+                           void* stream) {
+  LX_TRY(check_plan(model, plan));
+  const lx_dit_model_t& m = *model;
+  const lx_dit_plan_t& p = *plan;
+  LX_CHECK_ARG(step >= 0 && step < p.T, "lx_dit_head: step %d outside [0, %d)", step, p.T);
+  LX_CHECK_ARG(noise_pred != nullptr, "lx_dit_head: null tensor");
+  const Geo g = geo(m, p);
+  const int D = g.D;
   {
     lx_lnmod_desc_t d;
     memset(&d, 0, sizeof(d));

@@ -69,6 +69,8 @@ _lib.lx_dit_prepare.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_v
                                 C.POINTER(c_float), C.POINTER(c_float), c_float, c_void_p]
 _lib.lx_dit_embed.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_void_p, c_void_p]
 _lib.lx_dit_step.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_void_p, c_void_p, c_void_p]
+_lib.lx_dit_head.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_void_p, c_void_p]
+_lib.lx_add_rows.argtypes = [c_void_p, C.c_int64, c_void_p, C.c_int64, c_int32, c_int32, c_void_p]
 _lib.lx_dit_double_block.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_int32, c_void_p]
 _lib.lx_dit_single_block.argtypes = [C.POINTER(LxDitModel), C.POINTER(LxDitPlan), c_int32, c_int32, c_void_p]
 _lib.lx_euler_step.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p]
@@ -451,6 +453,47 @@ class DitPlan:
             src, dst = latents, out
         L.check(_lib.lx_dit_step(C.byref(w.model), C.byref(self.plan), step, src.data_ptr(), dst.data_ptr(),
                                  _stream()), "lx_dit_step")
+        if self.padded:
+            out.copy_(self._out_pad[:, :self.ni])
+        return out
+
+    def step_with_residuals(self, step: int, latents: torch.Tensor, block_samples: Optional[Sequence[torch.Tensor]] = None,
+                            single_block_samples: Optional[Sequence[torch.Tensor]] = None,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """step() with controlnet residuals (transformer.py:172-181, 230-239): after double block i the image stream gets
+        `block_samples[i // ceil(n_blocks / len(block_samples))]` added, after single block i the image rows of the joint
+        stream get `single_block_samples[...]`; samples are [B, n_img, inner_dim].  The forward runs block by block through
+        the reference-granularity entry points (lx_dit_embed / lx_dit_double_block / lx_dit_single_block / lx_dit_head) with
+        lx_add_rows between them."""
+        w = self.weights
+        cfg = w.cfg
+        assert latents.dtype == torch.bfloat16 and latents.is_contiguous()
+        assert latents.shape == (self.B, self.ni, cfg.in_channels), latents.shape
+        if out is None:
+            out = torch.empty_like(latents)
+        D = cfg.inner_dim
+        img = self.split_streams()[1]  # [B, n_img, D] view of the image rows of plan->X
+
+        def add(samples, i, n_blocks):
+            if samples is None:
+                return
+            interval = -(-n_blocks // len(samples))  # int(np.ceil(len(blocks) / len(samples)))
+            r = samples[i // interval].to(device=w.device, dtype=torch.bfloat16)
+            assert r.shape == (self.B, self.ni, D), (tuple(r.shape), (self.B, self.ni, D))
+            for b in range(self.B):  # (a padded plan leaves a gap between the batches' image rows)
+                rb = r[b] if r[b].stride(1) == 1 and r[b].stride(0) % 8 == 0 else r[b].contiguous()
+                L.check(_lib.lx_add_rows(img[b].data_ptr(), img[b].stride(0), rb.data_ptr(), rb.stride(0), self.ni, D,
+                                         _stream()), "lx_add_rows")
+
+        self.embed(latents)
+        for i in range(cfg.num_layers):
+            self.double_block(step, i)
+            add(block_samples, i, cfg.num_layers)
+        for i in range(cfg.num_single_layers):
+            self.single_block(step, i)
+            add(single_block_samples, i, cfg.num_single_layers)
+        dst = self._out_pad if self.padded else out
+        L.check(_lib.lx_dit_head(C.byref(w.model), C.byref(self.plan), step, dst.data_ptr(), _stream()), "lx_dit_head")
         if self.padded:
             out.copy_(self._out_pad[:, :self.ni])
         return out

@@ -447,9 +447,11 @@ def single_block_forward(P, cfg, idx, hidden_states, temb, image_rotary_emb=None
 
 def tranformer_forward(P, cfg, condition_latents, condition_ids, condition_type_ids=None,
                        model_config: Optional[dict] = None, c_t=0, *, hidden_states, encoder_hidden_states,
-                       pooled_projections, timestep, img_ids, txt_ids, guidance=None, c_factor=None):
+                       pooled_projections, timestep, img_ids, txt_ids, guidance=None, c_factor=None,
+                       controlnet_block_samples=None, controlnet_single_block_samples=None):
     """transformer.py:47-252 -> noise prediction [B, N_img, in_channels].  condition_type_ids is ignored exactly like
-    the reference (transformer.py:133 is commented out)."""
+    the reference (transformer.py:133 is commented out).  controlnet_*_samples: lists of [B, N_img, inner_dim] residuals
+    added to the image stream after the blocks (transformer.py:172-181, 230-239)."""
     model_config = model_config or {}
     use_condition = condition_latents is not None
     latent_lora = model_config.get("latent_lora", False)
@@ -475,6 +477,9 @@ def tranformer_forward(P, cfg, condition_latents, condition_ids, condition_type_
         encoder_hidden_states, hidden_states, condition_latents = block_forward(
             P, cfg, i, hidden_states, encoder_hidden_states, condition_latents if use_condition else None, temb,
             cond_temb if use_condition else None, cond_rotary_emb, image_rotary_emb, model_config, c_factor)
+        if controlnet_block_samples is not None:  # :172-181
+            interval_control = int(math.ceil(cfg.num_layers / len(controlnet_block_samples)))
+            hidden_states = hidden_states + controlnet_block_samples[i // interval_control]
     n_txt = encoder_hidden_states.shape[1]
     hidden_states = torch.cat([encoder_hidden_states, hidden_states], dim=1)  # :182
     for i in range(cfg.num_single_layers):  # :184-228
@@ -485,6 +490,10 @@ def tranformer_forward(P, cfg, condition_latents, condition_ids, condition_type_
             hidden_states, condition_latents = result
         else:
             hidden_states = result
+        if controlnet_single_block_samples is not None:  # :230-239 (image rows of the joint [txt | img] stream)
+            interval_control = int(math.ceil(cfg.num_single_layers / len(controlnet_single_block_samples)))
+            hidden_states = torch.cat([hidden_states[:, :n_txt],
+                                       hidden_states[:, n_txt:] + controlnet_single_block_samples[i // interval_control]], dim=1)
     hidden_states = hidden_states[:, n_txt:, ...]  # :241
     hidden_states = ada_layer_norm_continuous(P, "norm_out", hidden_states, temb, cfg)  # :243
     return linear(P, "proj_out", hidden_states, False, cfg)  # :244

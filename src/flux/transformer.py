@@ -25,8 +25,6 @@ def tranformer_forward(transformer, condition_latents, condition_ids, condition_
                        model_config: Optional[Dict[str, Any]] = {}, c_t=0, **params):
     (hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
      joint_attention_kwargs, controlnet_block_samples, controlnet_single_block_samples, return_dict) = prepare_params(**params)
-    if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
-        raise NotImplementedError("controlnet residuals (transformer.py:172-181, 230-239) are not part of the LoongX path")
     # transformer.py:73-83, 246-248: the LoRA layers are scaled by joint_attention_kwargs["scale"] for this forward
     transformer.set_lora_scale(joint_attention_kwargs.get("scale", 1.0) if joint_attention_kwargs is not None else 1.0)
     if transformer.training and transformer.gradient_checkpointing:
@@ -54,7 +52,12 @@ def tranformer_forward(transformer, condition_latents, condition_ids, condition_
             gd = gd * B
     plan.prepare(encoder_hidden_states, pooled_projections, condition_latents if use_condition else None, ts, gd,
                  c_t=float(c_t))
-    output = plan.step(0, hidden_states.to(torch.bfloat16).contiguous()).to(hidden_states.dtype)
+    if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
+        # transformer.py:172-181, 230-239: residuals on the image stream after every block -> block-by-block forward
+        output = plan.step_with_residuals(0, hidden_states.to(torch.bfloat16).contiguous(), controlnet_block_samples,
+                                          controlnet_single_block_samples).to(hidden_states.dtype)
+    else:
+        output = plan.step(0, hidden_states.to(torch.bfloat16).contiguous()).to(hidden_states.dtype)
     if not return_dict:
         return (output,)
     return Transformer2DModelOutput(sample=output)

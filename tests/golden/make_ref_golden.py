@@ -79,7 +79,7 @@ def make_conditioner(seed=1234) -> OC.NeuralConditioner:
 # ------------------------------------------------------------------------------------------------------------------
 # reference-side runners (need /root/reference)
 # ------------------------------------------------------------------------------------------------------------------
-def ref_dit_forward(cfg, P, inp, model_config, c_factor=None, use_cond=True, c_t=0):
+def ref_dit_forward(cfg, P, inp, model_config, c_factor=None, use_cond=True, c_t=0, **extra):
     T = R.ref_module("flux.transformer")
     model = R.build_transformer(P, cfg)
     if c_factor is not None:  # generate.py:90-94
@@ -90,15 +90,15 @@ def ref_dit_forward(cfg, P, inp, model_config, c_factor=None, use_cond=True, c_t
         return T.tranformer_forward(
             model, inp["cond"] if use_cond else None, inp["cond_ids"].clone() if use_cond else None, None, model_config, c_t,
             hidden_states=inp["lat"], encoder_hidden_states=inp["pe"], pooled_projections=inp["pooled"], timestep=inp["t"],
-            img_ids=inp["img_ids"], txt_ids=inp["txt_ids"], guidance=inp["guidance"], return_dict=False)[0]
+            img_ids=inp["img_ids"], txt_ids=inp["txt_ids"], guidance=inp["guidance"], return_dict=False, **extra)[0]
 
 
-def oracle_dit_forward(cfg, P, inp, model_config, c_factor=None, use_cond=True, c_t=0):
+def oracle_dit_forward(cfg, P, inp, model_config, c_factor=None, use_cond=True, c_t=0, **extra):
     with torch.no_grad():
         return O.tranformer_forward(
             P, cfg, inp["cond"] if use_cond else None, inp["cond_ids"] if use_cond else None, None, model_config, c_t,
             hidden_states=inp["lat"], encoder_hidden_states=inp["pe"], pooled_projections=inp["pooled"], timestep=inp["t"],
-            img_ids=inp["img_ids"], txt_ids=inp["txt_ids"], guidance=inp["guidance"], c_factor=c_factor)
+            img_ids=inp["img_ids"], txt_ids=inp["txt_ids"], guidance=inp["guidance"], c_factor=c_factor, **extra)
 
 
 class _D1(nn.Module):

@@ -147,6 +147,65 @@ def test_dit_forward_vs_oracle(variant):
         assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (variant, step, e_nat, e_bf)
 
 
+@pytest.mark.parametrize("n_dbl, n_sgl, ragged", [(2, 1, False), (1, 2, False), (0, 2, False), (2, 2, True)])
+def test_dit_controlnet_residuals(n_dbl, n_sgl, ragged):
+    """transformer.py:172-181, 230-239: residuals added to the image stream after the blocks (lists shorter than the block
+    lists use the ceil interval).  Native block-by-block forward (lx_dit_embed / block calls / lx_add_rows / lx_dit_head)
+    against the oracle, whose controlnet path is pinned to the reference's own code in test_reference_pins_cpu.py; through
+    DitPlan and through the reference-facing src.flux.transformer.tranformer_forward."""
+    from src.flux.transformer import tranformer_forward
+    from loongx_b200.pipeline import NativeFluxTransformer
+
+    O, ocfg, Pb, P32, inp, W, plan = _setup()
+    B, ni = inp["lat"].shape[:2]
+    D = ocfg.inner_dim
+    g = torch.Generator().manual_seed(3)
+    mk = lambda n: [(torch.randn(B, ni, D, generator=g) * 0.3).bfloat16().cuda() for _ in range(n)] if n else None  # noqa: E731
+    bs, ss = mk(n_dbl), mk(n_sgl)
+    step, t = 1, inp["ts"][1]
+    f32 = lambda xs: [x.float() for x in xs] if xs else None  # noqa: E731
+
+    def oracle(P, dtype):
+        c = lambda x: x.to(dtype) if x is not None else None  # noqa: E731
+        cast = lambda xs: [x.to(dtype) for x in xs] if xs else None  # noqa: E731
+        return O.tranformer_forward(
+            P, ocfg, c(inp["cond"]), inp["cond_ids"], None, {}, 0, hidden_states=c(inp["lat"]),
+            encoder_hidden_states=c(inp["pe"]), pooled_projections=c(inp["pooled"]),
+            timestep=torch.full((B,), t, device="cuda", dtype=dtype), img_ids=inp["img_ids"], txt_ids=inp["txt_ids"],
+            guidance=torch.full((B,), inp["guidance"], device="cuda", dtype=dtype),
+            controlnet_block_samples=cast(bs), controlnet_single_block_samples=cast(ss))
+
+    ref32, ref16 = oracle(P32, torch.float32), oracle(Pb, torch.bfloat16)
+    plain = plan.step(step, inp["lat"]).clone()
+    assert torch.equal(plan.step_with_residuals(step, inp["lat"]), plain)  # no residuals: the same kernels, same bits
+    got = plan.step_with_residuals(step, inp["lat"], bs, ss)
+    torch.cuda.synchronize()
+    e_nat, e_bf = _rel(got, ref32), _rel(ref16, ref32)
+    print(f"\n[controlnet {n_dbl}+{n_sgl}] relL2 native {e_nat:.4g}  torch-bf16-eager {e_bf:.4g}")
+    assert e_nat <= 1.5 * e_bf + 2e-3 and e_nat <= 2e-2, (e_nat, e_bf)
+    assert _rel(got, plain) > 1e-2  # the residuals do change the prediction
+    if not ragged:
+        return
+    # the reference-facing call, with a ragged prompt length (padded plan: the image rows of the batches are not adjacent)
+    cfg = W.cfg
+    tr = NativeFluxTransformer(cfg, params=dict(Pb), device="cuda")
+    nt = 100
+    kw = dict(hidden_states=inp["lat"], encoder_hidden_states=inp["pe"][:, :nt].contiguous(), pooled_projections=inp["pooled"],
+              timestep=torch.full((B,), t, device="cuda"), img_ids=inp["img_ids"], txt_ids=inp["txt_ids"][:nt],
+              guidance=torch.full((B,), inp["guidance"], device="cuda"), return_dict=False)
+    out = tranformer_forward(tr, inp["cond"], inp["cond_ids"], None, {}, 0, controlnet_block_samples=bs,
+                             controlnet_single_block_samples=ss, **kw)[0]
+    ref = O.tranformer_forward(
+        P32, ocfg, inp["cond"].float(), inp["cond_ids"], None, {}, 0, hidden_states=inp["lat"].float(),
+        encoder_hidden_states=inp["pe"][:, :nt].float(), pooled_projections=inp["pooled"].float(),
+        timestep=torch.full((B,), t, device="cuda"), img_ids=inp["img_ids"], txt_ids=inp["txt_ids"][:nt],
+        guidance=torch.full((B,), inp["guidance"], device="cuda"), controlnet_block_samples=f32(bs),
+        controlnet_single_block_samples=f32(ss))
+    e = _rel(out, ref)
+    print(f"[controlnet via tranformer_forward, ragged prompt] relL2 {e:.4g}")
+    assert e <= 2e-2, e
+
+
 def test_dit_wider_model_and_batch():
     """heads=4 (D=512), B=3, one prepared step, condition present."""
     O, ocfg, Pb, P32, inp, W, plan = _setup(heads=4, layers=(1, 2), B=3, T=1)
