@@ -65,6 +65,8 @@ ref = F.scaled_dot_product_attention(qkv[0][0].float(), qkv[0][1].float(), qkv[0
 lx(0)
 got = out.view(B, S, H, 128).permute(0, 2, 1, 3).float()
 # (row order of `out` is stream-major [txt | img | cond] x batch; at B = 1 it is the token order)
+if os.environ.get("LX_ATT_DUMP"):  # A/B of two builds: the outputs must be bit-identical when only the schedule changed
+    torch.save(out.cpu(), os.environ["LX_ATT_DUMP"])
 if B == 1:
     print(f"lx vs fp32 SDPA relL2 {float((got - ref).norm() / ref.norm()):.3e}", flush=True)
 for r in range(rounds):
