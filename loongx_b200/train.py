@@ -113,6 +113,13 @@ def gate_residual_fwd(res, y, out, tile_meta, gate):
                                       tile_meta.data_ptr(), gp, gs, _stream()), "lx_gate_residual_fwd")
 
 
+def add_rows(x, r):
+    """x += r, bf16 rows (fp32 add, one rounding)."""
+    assert x.shape == r.shape and x.stride(1) == 1 and r.stride(1) == 1
+    L.check(_lib.lx_add_rows(x.data_ptr(), x.stride(0), r.data_ptr(), r.stride(0), x.shape[0], x.shape[1], _stream()),
+            "lx_add_rows")
+
+
 def gate_bwd(dout, y, dy, tile_meta, gate, dgate):
     assert dout.stride(0) == y.stride(0) == dy.stride(0)
     gp, gs = _vec3(gate)
@@ -496,8 +503,10 @@ class DitTrainer:
         self.attn_bwd = attn_bwd
         self.latent_lora = bool(model_config.get("latent_lora", False))
         self.input_grads = bool(input_grads)
-        if model_config.get("add_cond_attn", False):
-            raise NotImplementedError("training with model_config.add_cond_attn=True (inference supports it)")
+        # block.py:233-234: the gated attention output of the condition stream is also added to the image stream
+        self.add_cond_attn = bool(model_config.get("add_cond_attn", False))
+        if self.add_cond_attn and n_cond != n_img:
+            raise ValueError("model_config.add_cond_attn needs condition and image streams of the same length (block.py:234)")
         if n_cond <= 0:
             raise NotImplementedError("the training step needs a condition stream (the LoRA lives on the condition branch)")
         self.w, self.cfg = weights, weights.cfg
@@ -751,6 +760,9 @@ class DitTrainer:
             else:
                 self._gemm(O, W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], a["Y1"])
                 gate_residual_fwd(X, a["Y1"], x1, tm, m[2])
+            if self.add_cond_attn:  # block.py:233-234: hidden_states += cond_gate_msa * cond_attn_output (row for row)
+                ri, rc = self.Rt, self.Rt + self.Ri
+                gate_residual_fwd(x1[ri:rc], a["Y1"][rc:], x1[ri:rc], tm[rc // 128:], m[2])
         ln_modulate(x1, a["XN2"], tm, m[3], m[4])
         pre_ff = a["QM"][:, 3 * D:7 * D]
         if self.fuse_gelu:  # one launch writes the GELU and, where the pre-activation would go, gelu' for the backward
@@ -795,7 +807,17 @@ class DitTrainer:
         self._gemm(d_hid, W[f"double.{i}.ff_up"], W[f"double.{i}.ff_ctx_up"], g["dXN"], transposed=True)
         ln_modulate_bwd(self.ckpt_mid[i], g["dXN"], g["dX"], g["dX1"], tm, m[4], dm(4), dm(3), self.stats)
         # attention branch
-        gate_bwd(g["dX1"], a["Y1"], g["dY"], tm, m[2], dm(2))
+        if self.add_cond_attn:
+            # the condition's gated projection also feeds the image stream (block.py:233-234): its upstream gradient is
+            # d x1[cond] + d x1[img]; the residual path of the condition rows keeps d x1[cond] alone (dXN is free here)
+            ri, rc = self.Rt, self.Rt + self.Ri
+            d_c = g["dXN"][rc:]
+            d_c.copy_(g["dX1"][rc:])
+            add_rows(d_c, g["dX1"][ri:rc])
+            gate_bwd(g["dX1"][:rc], a["Y1"][:rc], g["dY"][:rc], tm[:rc // 128], m[2], dm(2))
+            gate_bwd(d_c, a["Y1"][rc:], g["dY"][rc:], tm[rc // 128:], m[2], dm(2))
+        else:
+            gate_bwd(g["dX1"], a["Y1"], g["dY"], tm, m[2], dm(2))
         self._lora_grads([pfx + "attn.to_out.0"], O[c0:], g["dY"][c0:])
         d_o = g["dCat"][:, :D]
         self._gemm(g["dY"], W[f"double.{i}.out"], W[f"double.{i}.out_ctx"], d_o, transposed=True)

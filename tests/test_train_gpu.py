@@ -286,6 +286,7 @@ def _tiny_train_case(layers=(2, 2), B=2, nt=128, hw=(16, 32), seed=0):
 @pytest.mark.parametrize("layers,mc,nt,hw", [((1, 1), {}, 128, (16, 32)), ((2, 2), {}, 128, (16, 32)),
                                              ((2, 2), {"latent_lora": True}, 128, (16, 32)),
                                              ((1, 2), {"independent_condition": True}, 128, (16, 32)),
+                                             ((2, 1), {"add_cond_attn": True}, 128, (16, 32)),
                                              ((1, 1), {}, 100, (12, 20)), ((2, 1), {"latent_lora": True}, 77, (20, 36))])
 def test_train_step_loss_and_lora_grads_vs_oracle(layers, mc, nt, hw, recompute):
     """Native forward + backward vs fp32 autograd over the oracle restatement of model.py:569-729."""
