@@ -356,7 +356,42 @@ def all_cases(ref: bool) -> dict:
     return res
 
 
+CONTROLNET_CASES = {"2+2": (2, 2), "1+1": (1, 1), "2+0": (2, 0), "0+1": (0, 1)}
+
+
+def controlnet_cases(ref: bool) -> dict:
+    """tranformer_forward with controlnet residuals (transformer.py:172-181, 230-239): residual lists as long as / shorter
+    than the block lists (interval = ceil(n_blocks / n_samples)), either list absent.  Kept in its own fixture
+    (ref_controlnet_v1.npz, written by `python make_ref_golden.py controlnet`) so that ref_v1.npz stays byte-identical."""
+    cfg = O.FluxConfig(**TINY)
+    P, inp = dit_params(cfg), dit_inputs(cfg)
+    B, ni = inp["lat"].shape[:2]
+    out = {}
+    for name, (n_dbl, n_sgl) in CONTROLNET_CASES.items():
+        g = torch.Generator().manual_seed(9)
+        mk = lambda n: [torch.randn(B, ni, cfg.inner_dim, generator=g) * 0.3 for _ in range(n)] if n else None  # noqa: E731
+        extra = dict(controlnet_block_samples=mk(n_dbl), controlnet_single_block_samples=mk(n_sgl))
+        out["controlnet_" + name] = (ref_dit_forward if ref else oracle_dit_forward)(cfg, P, inp, {}, **extra)
+    return out
+
+
+def main_controlnet():
+    assert R.available(), "needs /root/reference"
+    ref, orc = controlnet_cases(True), controlnet_cases(False)
+    store = {}
+    for k, v in ref.items():
+        a, b = v.double(), orc[k].double()
+        print(f"{k:28s} shape {tuple(v.shape)!s:20s} relL2(oracle, reference) = {float((a - b).norm() / (a.norm() + 1e-30)):.3e}")
+        for kk, vv in digest(v).items():
+            store[f"{k}/{kk}"] = vv
+    path = os.path.join(HERE, "ref_controlnet_v1.npz")
+    np.savez_compressed(path, **store)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "controlnet":
+        return main_controlnet()
     assert R.available(), "needs /root/reference"
     ref, orc = all_cases(True), all_cases(False)
     store = {}

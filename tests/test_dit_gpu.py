@@ -151,7 +151,7 @@ def test_dit_forward_vs_oracle(variant):
 def test_dit_controlnet_residuals(n_dbl, n_sgl, ragged):
     """transformer.py:172-181, 230-239: residuals added to the image stream after the blocks (lists shorter than the block
     lists use the ceil interval).  Native block-by-block forward (lx_dit_embed / block calls / lx_add_rows / lx_dit_head)
-    against the oracle, whose controlnet path is pinned to the reference's own code in test_reference_pins_cpu.py; through
+    against the oracle, whose controlnet path is pinned to the reference's own code (tests/golden/ref_controlnet_v1.npz); through
     DitPlan and through the reference-facing src.flux.transformer.tranformer_forward."""
     from src.flux.transformer import tranformer_forward
     from loongx_b200.pipeline import NativeFluxTransformer

@@ -93,27 +93,24 @@ def test_reference_live_equals_fixture_and_oracle(oracle_out):
             assert rel <= max(_tol(name), 0.0), (name, rel)
 
 
-@pytest.mark.skipif(not R.available(), reason="/root/reference is not on this machine")
-@pytest.mark.parametrize("n_dbl, n_sgl", [(2, 2), (1, 1), (2, 0), (0, 1)])
-def test_reference_controlnet_residuals_match_the_oracle(n_dbl, n_sgl):
-    """transformer.py:172-181, 230-239 executed for real: residual lists shorter than the block lists (the interval is
-    ceil(n_blocks / n_samples)), either list absent.  Live pin only: the committed fixture predates this case."""
-    from oracle import flux_dit as O
+GOLD_CN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_controlnet_v1.npz"))
 
-    cfg = O.FluxConfig(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=64,
-                       pooled_projection_dim=32)
-    P = MR.dit_params(cfg)
-    inp = MR.dit_inputs(cfg)
-    g = torch.Generator().manual_seed(9)
-    B, ni = inp["lat"].shape[:2]
-    mk = lambda n: [torch.randn(B, ni, cfg.inner_dim, generator=g) * 0.3 for _ in range(n)] if n else None  # noqa: E731
-    extra = dict(controlnet_block_samples=mk(n_dbl), controlnet_single_block_samples=mk(n_sgl))
-    ref = MR.ref_dit_forward(cfg, P, inp, {}, **extra)
-    got = MR.oracle_dit_forward(cfg, P, inp, {}, **extra)
-    plain = MR.oracle_dit_forward(cfg, P, inp, {})
-    rel = float((ref.double() - got.double()).norm() / ref.double().norm())
-    assert rel <= 2e-5, rel
-    assert float((got - plain).norm() / plain.norm()) > 1e-2  # the residuals do change the prediction
+
+def test_oracle_controlnet_residuals_match_reference_fixture():
+    """transformer.py:172-181, 230-239 (residual lists shorter than the block lists use the ceil interval; either list
+    absent): the oracle against outputs of the reference's own code, committed as tests/golden/ref_controlnet_v1.npz
+    (`python tests/golden/make_ref_golden.py controlnet`); where /root/reference exists it is re-executed as well."""
+    got = MR.controlnet_cases(ref=False)
+    assert sorted({k.split("/")[0] for k in GOLD_CN.files}) == sorted(got)
+    plain = MR.oracle_dit_forward(MR.O.FluxConfig(**MR.TINY), MR.dit_params(MR.O.FluxConfig(**MR.TINY)),
+                                  MR.dit_inputs(MR.O.FluxConfig(**MR.TINY)), {})
+    for name, t in got.items():
+        _check(name, t, {k: GOLD_CN[f"{name}/{k}"] for k in ("sample", "sum", "abssum", "shape")})
+        assert float((t - plain).norm() / plain.norm()) > 1e-2  # the residuals do change the prediction
+    if R.available():
+        for name, t in MR.controlnet_cases(ref=True).items():
+            _check(name, t, {k: GOLD_CN[f"{name}/{k}"] for k in ("sample", "sum", "abssum", "shape")})
+            assert float((t.double() - got[name].double()).norm() / t.double().norm()) <= 2e-5, name
 
 
 @pytest.mark.skipif(not R.available(), reason="/root/reference is not on this machine")
