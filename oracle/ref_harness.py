@@ -416,15 +416,35 @@ class _PrecomputedVae:
 # ------------------------------------------------------------------------------------------------------------------
 # stub installation + import of the reference tree
 # ------------------------------------------------------------------------------------------------------------------
+_displaced: Dict[str, object] = {}  # stand-in name -> what sys.modules held before (None = nothing)
+
+
 def _module(name: str, **attrs) -> types.ModuleType:
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
     m.__path__ = []  # behave like a package so `import a.b` resolves through sys.modules
+    _displaced.setdefault(name, sys.modules.get(name))
     sys.modules[name] = m
     return m
 
 
 _installed = False
+
+
+def uninstall_stubs():
+    """Take the stand-ins (and the reference modules imported on top of them) out of sys.modules again and put back what
+    they displaced.  Libraries that probe for optional packages with importlib.util.find_spec (transformers: accelerate,
+    peft) trip over stand-ins without a spec, so a test module that used the harness removes them when it is done."""
+    global _installed
+    for name, prev in _displaced.items():
+        if prev is None:
+            sys.modules.pop(name, None)
+        else:
+            sys.modules[name] = prev
+    _displaced.clear()
+    for name in [n for n in sys.modules if n == PKG or n.startswith(PKG + ".")]:
+        del sys.modules[name]
+    _installed = False
 
 
 def install_stubs():
