@@ -33,15 +33,16 @@ def _config(flux_path):
             "train": {"lora_config": {"r": 4, "lora_alpha": 4, "init_lora_weights": "gaussian"}}}
 
 
-def _import_reference_inference():
-    """/root/reference/inference.py as a module; `accelerate` (imported at its top, unused on this path) is stubbed."""
+def _import_reference_inference(monkeypatch):
+    """/root/reference/inference.py as a module; `accelerate` (imported at its top, unused on this path) is stubbed for
+    the duration of the test (a stand-in without a spec left in sys.modules would break libraries that probe for it)."""
     if "accelerate" not in sys.modules:
         try:
             import accelerate  # noqa: F401
         except ImportError:
             stub = types.ModuleType("accelerate")
             stub.init_empty_weights = stub.infer_auto_device_map = lambda *a, **k: None
-            sys.modules["accelerate"] = stub
+            monkeypatch.setitem(sys.modules, "accelerate", stub)
     spec = importlib.util.spec_from_file_location("ref_inference", REF)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -80,7 +81,7 @@ def _signals():
 def test_reference_inference_py_runs_against_this_repo(tmp_path, monkeypatch):
     from src.train import model as our_model
 
-    ref = _import_reference_inference()
+    ref = _import_reference_inference(monkeypatch)
     assert ref.OminiModel is our_model.OminiModel, "inference.py must bind this repo's src.train.model"
     # inference.py passes config["flux_path"] (a string) as flux_pipe_id: hand it a name that resolves to a tiny config
     real_init = our_model.OminiModel.__init__
