@@ -150,7 +150,18 @@ class NativeFluxTransformer:
         corresponds to calling this with 1.0 again.  The scale in force lives on the weight set (train.set_lora_scale)."""
         from .train import set_lora_scale
 
-        set_lora_scale(self.weights, scale)
+        self.weights.lora_inner = float(scale)
+        set_lora_scale(self.weights, float(scale) * getattr(self.weights, "lora_outer", 1.0))
+
+    def set_lora_outer(self, factor: float) -> None:
+        """The multiplier the reference's context managers put on peft's `scaling` from OUTSIDE a forward
+        (lora_controller.py: `enable_lora(..., False)` = 0, `set_lora_scale(..., s)` = s): like there it composes with the
+        per-forward `joint_attention_kwargs["scale"]` (peft's scale_lora_layers multiplies), so the scale in force is
+        inner * outer."""
+        from .train import set_lora_scale
+
+        self.weights.lora_outer = float(factor)
+        set_lora_scale(self.weights, getattr(self.weights, "lora_inner", 1.0) * float(factor))
 
     def remerge_lora(self) -> None:
         """Rebuild every merged panel from the current LoRA factors (after an optimizer step or an in-place edit of

@@ -211,6 +211,17 @@ def test_joint_attention_kwargs_lora_scale():
     print(f"\n[lora scale] relL2 vs oracle at scale 1 / 0.5 / 0: {e[0]:.4g} {e[1]:.4g} {e[2]:.4g}; effect {rel(out0, out1):.4g}")
     assert max(e) < 1.5e-2 and rel(out0, out1) > 3 * max(e)
     assert torch.equal(out1, out1b)
+    # the reference's context managers used AROUND a forward (lora_controller.py:5-75): they compose with the per-forward scale
+    from src.flux.lora_controller import enable_lora, set_lora_scale
+
+    with enable_lora([tr], False):
+        out_off = tranformer_forward(tr, cond, cond_ids, None, {}, 0, **kwargs)[0]
+    with set_lora_scale([tr.transformer_blocks[0]], 0.5):
+        out_ctx_half = tranformer_forward(tr, cond, cond_ids, None, {}, 0, **kwargs)[0]
+        out_ctx_quarter = tranformer_forward(tr, cond, cond_ids, None, {}, 0, joint_attention_kwargs={"scale": 0.5}, **kwargs)[0]
+    assert torch.equal(out_off, out0) and torch.equal(out_ctx_half, out_half)
+    assert rel(out_ctx_quarter, oracle(0.25)) < 1.5e-2
+    assert torch.equal(tranformer_forward(tr, cond, cond_ids, None, {}, 0, **kwargs)[0], out1)  # restored
 
 
 def test_generate_full_size_properties():

@@ -235,3 +235,46 @@ def test_integration_doc_stub_matches_the_header():
     stub = ns["AttnDesc"]
     assert C.sizeof(stub) == C.sizeof(L.AttnDesc)
     assert [(n, C.sizeof(t)) for n, t in stub._fields_] == [(n, C.sizeof(t)) for n, t in L.AttnDesc._fields_]
+
+
+def test_lora_context_managers_compose_with_the_per_forward_scale():
+    """src/flux/lora_controller.py on a stand-in transformer (no GPU): enable_lora(activated=False) and set_lora_scale put a
+    multiplier NEXT to the per-forward joint_attention_kwargs scale (peft's scale_lora_layers multiplies, lora_controller.py
+    :5-75), restore it on exit (also on an exception), nest, and skip objects that are not native handles."""
+    from src.flux.lora_controller import enable_lora, set_lora_scale
+
+    class W:
+        pass
+
+    class Tr:
+        def __init__(self):
+            self.weights, self.log = W(), []
+
+        def set_lora_outer(self, f):
+            self.weights.lora_outer = float(f)
+            self.log.append(float(f))
+
+    class Block:  # what transformer.transformer_blocks[i] looks like to a caller
+        def __init__(self, tr):
+            self.transformer = tr
+
+    tr = Tr()
+    with enable_lora([Block(tr), Block(tr), object()], False):  # one weight set behind both handles: one switch
+        assert tr.weights.lora_outer == 0.0
+        with set_lora_scale([tr], 0.5):
+            assert tr.weights.lora_outer == 0.0  # 0 * 0.5
+        assert tr.weights.lora_outer == 0.0
+    assert tr.weights.lora_outer == 1.0 and tr.log == [0.0, 0.0, 0.0, 1.0]
+    with enable_lora([tr], True):  # activated: nothing changes
+        assert tr.weights.lora_outer == 1.0
+    with set_lora_scale([tr], 0.5):
+        with set_lora_scale([Block(tr)], 0.5):
+            assert tr.weights.lora_outer == 0.25
+        assert tr.weights.lora_outer == 0.5
+    assert tr.weights.lora_outer == 1.0
+    try:
+        with enable_lora([tr], False):
+            raise KeyError("x")
+    except KeyError:
+        pass
+    assert tr.weights.lora_outer == 1.0
